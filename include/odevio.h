@@ -1,0 +1,150 @@
+/*
+ * odevio.h -- C ABI of the B200-native ODE-VIO latent-dynamics integration path.
+ *
+ * The reference (mc1017/ODE-VIO) has no FFI layer: its seam for this path is the
+ * nn.Module contract of the pose regressors.  Each entry point below replaces the
+ * arithmetic behind one reference interface (file:line into the reference tree):
+ *
+ *   odevio_odernn_forward      PoseODERNN.forward            src/models/PoseODERNN.py:88-123
+ *                              + PoseODERNN.evolve_state     src/models/PoseODERNN.py:70-75
+ *                              + torchode AutoDiffAdjoint.solve / Dopri5|Tsit5|Heun|Euler.step /
+ *                                IntegralController (call sites src/models/PoseODERNN.py:55-60,125-137)
+ *                              + ODEFunc.forward             src/models/ODEFunc.py:38-39
+ *                              + nn.RNN / nn.GRU one-step    src/models/PoseODERNN.py:114,139-148
+ *                              + regressor head              src/models/PoseODERNN.py:64-68,122
+ *   odevio_odernn_backward     loss.backward() through the above (to.AutoDiffAdjoint is plain
+ *                              autograd = discretise-then-optimise)  scripts/train_model.py:78
+ *   odevio_cde_forward         PoseCDE.forward               src/models/PoseCDE.py:76-103
+ *                              + torchcde linear_interpolation_coeffs / LinearInterpolation / cdeint
+ *                                (call sites src/models/PoseCDE.py:94-101)
+ *                              + CDEFunc.forward             src/models/ODEFunc.py:81-84
+ *   odevio_*_workspace_bytes   (torch allocator; the reference allocates implicitly)
+ *
+ * Conventions: plain pointers and sizes only; every pointer is DEVICE memory owned by the
+ * caller (PyTorch in the shipped host layer) unless marked HOST; all tensors are contiguous
+ * row-major fp32 with the PyTorch shapes quoted; `stream` is a cudaStream_t passed as void*.
+ * Calls are asynchronous on `stream`, allocate nothing, never synchronise the device, and are
+ * re-entrant across devices (the current device of the calling thread is used).
+ * Return value: 0 ok; <0 invalid argument (ODEVIO_E_*); >0 a cudaError_t from launch.
+ * Per-row solver failures (non-finite error norm, max_steps hit) are reported through the
+ * `status` output, never by hanging.
+ */
+#ifndef ODEVIO_H_
+#define ODEVIO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODEVIO_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ODEVIO_API __attribute__((visibility("default")))
+#else
+#define ODEVIO_API
+#endif
+
+#define ODEVIO_MAX_ODE_LINEARS 6   /* ode_fn_num_layers + 1 <= 6 */
+#define ODEVIO_MAX_RNN_LAYERS 4
+#define ODEVIO_MAX_STAGES 7
+
+/* error codes (negative returns) */
+#define ODEVIO_E_NULL        -1   /* required pointer is NULL */
+#define ODEVIO_E_SHAPE       -2   /* unsupported / inconsistent dimension */
+#define ODEVIO_E_ENUM        -3   /* unknown activation / rnn / solver id */
+#define ODEVIO_E_WORKSPACE   -4   /* workspace too small or misaligned */
+#define ODEVIO_E_DEVICE      -5   /* not an sm_100 device / no device */
+
+/* activations: reference src/models/ODEFunc.py:23-36 */
+enum { ODEVIO_ACT_TANH = 0, ODEVIO_ACT_RELU = 1, ODEVIO_ACT_LEAKY_RELU = 2, ODEVIO_ACT_SOFTPLUS = 3 };
+/* recurrent jump: reference src/models/PoseODERNN.py:139-148 */
+enum { ODEVIO_RNN_TANH = 0, ODEVIO_RNN_GRU = 1 };
+/* solver menu: reference src/models/PoseODERNN.py:125-137 (+ north_star fixed-step rk4, and
+ * torchdiffeq's 3/8-rule "rk4" reachable through src/models/PoseCDE.py:72,101) */
+enum {
+  ODEVIO_SOLVER_DOPRI5 = 0, ODEVIO_SOLVER_TSIT5 = 1, ODEVIO_SOLVER_HEUN = 2,
+  ODEVIO_SOLVER_EULER = 3, ODEVIO_SOLVER_RK4 = 4, ODEVIO_SOLVER_RK4_38 = 5
+};
+/* per-row status codes written to `status` */
+enum { ODEVIO_STATUS_OK = 0, ODEVIO_STATUS_MAX_STEPS = 1, ODEVIO_STATUS_INFINITE_NORM = 2 };
+/* arithmetic mode of the vector-field GEMMs */
+enum { ODEVIO_PRECISION_FP32 = 0 };
+
+typedef struct odevio_odernn_cfg {
+  int32_t B;            /* sequences */
+  int32_t S;            /* observation intervals (= seq_len - 1) */
+  int32_t D;            /* state dim = v_f_len + i_f_len */
+  int32_t H;            /* ODEFunc hidden dim */
+  int32_t n_hidden;     /* ODEFunc num_hidden_layers (reference default 3) -> n_hidden+1 Linears */
+  int32_t L;            /* rnn_num_layers */
+  int32_t activation;   /* ODEVIO_ACT_* */
+  int32_t rnn_type;     /* ODEVIO_RNN_* */
+  int32_t solver;       /* ODEVIO_SOLVER_* */
+  int32_t substeps;     /* fixed-step solvers: steps per interval */
+  float atol;           /* reference 1e-6  (PoseODERNN.py:57) */
+  float rtol;           /* reference 1e-2  (PoseODERNN.py:57) */
+  float dt0;            /* reference 1e-4  (PoseODERNN.py:72) */
+  float safety;         /* 0.9  */
+  float factor_min;     /* 0.2  */
+  float factor_max;     /* 10.0 */
+  int32_t accept_strict;      /* 1: accept iff ratio < 1 (torchode); 0: <= 1 */
+  int32_t floor_factor;       /* 1: factor >= 1 after an accepted step (torchdiffeq rule) */
+  int32_t endpoint_dense;     /* 1: end point from the step's dense output (torchode); 0: y1 */
+  int32_t max_steps;          /* per-interval guard; rows still running get STATUS_MAX_STEPS */
+  int32_t precision;          /* ODEVIO_PRECISION_* */
+  int32_t save_checkpoints;   /* 1: record what odevio_odernn_backward needs in `ckpt` */
+  int32_t rows_per_tile;      /* 0 = auto; else 8 or 16 sequences per CTA */
+  int32_t reserved[7];
+} odevio_odernn_cfg;
+
+/* PyTorch-layout parameters ([out, in] row-major), exactly the reference's state_dict tensors */
+typedef struct odevio_odernn_weights {
+  const float* ode_w[ODEVIO_MAX_ODE_LINEARS];   /* ode_func.net.{0,2,4,...}.weight */
+  const float* ode_b[ODEVIO_MAX_ODE_LINEARS];   /* ode_func.net.{0,2,4,...}.bias   */
+  const float* rnn_w_ih[ODEVIO_MAX_RNN_LAYERS]; /* rnn.weight_ih_l{k}: [G*D, D], G = 1 (rnn) | 3 (gru) */
+  const float* rnn_w_hh[ODEVIO_MAX_RNN_LAYERS]; /* rnn.weight_hh_l{k} */
+  const float* rnn_b_ih[ODEVIO_MAX_RNN_LAYERS]; /* rnn.bias_ih_l{k}:  [G*D] */
+  const float* rnn_b_hh[ODEVIO_MAX_RNN_LAYERS]; /* rnn.bias_hh_l{k} */
+  const float* reg_w0;  /* regressor.0.weight [128, D] */
+  const float* reg_b0;  /* regressor.0.bias   [128]    */
+  const float* reg_w1;  /* regressor.2.weight [6, 128] */
+  const float* reg_b1;  /* regressor.2.bias   [6]      */
+} odevio_odernn_weights;
+
+/* ABI version of the loaded library (== ODEVIO_ABI_VERSION of the header it was built from). */
+ODEVIO_API int32_t odevio_version(void);
+
+/* Human-readable text for a negative return code (static storage). */
+ODEVIO_API const char* odevio_error_string(int32_t code);
+
+/* Fill *cfg with the reference's defaults (scripts/config.py:50-69, PoseODERNN.py:57,72). */
+ODEVIO_API void odevio_odernn_default_cfg(odevio_odernn_cfg* cfg);
+
+/* Bytes of device workspace odevio_odernn_forward needs for this cfg (0 on invalid cfg). */
+ODEVIO_API size_t odevio_odernn_workspace_bytes(const odevio_odernn_cfg* cfg);
+
+/*
+ * Fused ODE-RNN regressor forward.
+ *   fv   [B,S,Dv], fi [B,S,D-Dv]   visual / inertial features (fusion "cat" happens in-kernel);
+ *                                  pass fi = NULL and Dv = D when fv already holds fused features
+ *   ts   [B,S+1]                   timestamps exactly as the solver must see them (the host layer
+ *                                  has already applied `ts - ts[:, :1]` when prev is None)
+ *   h0   [L,B,D] or NULL (zeros)
+ *   pose [B,S,6]  hT [L,B,D]       outputs
+ *   stats  [S,L,B,2] int32 or NULL: (n_steps, n_accepted) per interval / layer / row
+ *   status [B] int32 or NULL:       worst ODEVIO_STATUS_* seen by the row
+ *   workspace: >= odevio_odernn_workspace_bytes(cfg), 256-byte aligned
+ */
+ODEVIO_API int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_weights* w,
+                              const float* fv, const float* fi, int32_t Dv,
+                              const float* ts, const float* h0,
+                              float* pose, float* hT, int32_t* stats, int32_t* status,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODEVIO_H_ */

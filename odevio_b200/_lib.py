@@ -1,0 +1,105 @@
+"""ctypes binding of libodevio_b200.so (the C ABI declared in include/odevio.h).
+
+PyTorch only supplies device memory and the current stream; no torch types cross the
+boundary.  There is no CPU fallback: if the library cannot be loaded, or a tensor is not a
+contiguous fp32 CUDA tensor, the call raises.
+"""
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libodevio_b200.so")
+
+MAX_ODE_LINEARS = 6
+MAX_RNN_LAYERS = 4
+
+ACT = {"tanh": 0, "relu": 1, "leaky_relu": 2, "softplus": 3}
+RNN = {"rnn": 0, "gru": 1}
+SOLVER = {"dopri5": 0, "tsit5": 1, "heun": 2, "euler": 3, "rk4": 4, "rk4_38": 5}
+STATUS_OK, STATUS_MAX_STEPS, STATUS_INFINITE_NORM = 0, 1, 2
+
+
+class OdeRnnCfg(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("S", C.c_int32), ("D", C.c_int32), ("H", C.c_int32),
+        ("n_hidden", C.c_int32), ("L", C.c_int32), ("activation", C.c_int32),
+        ("rnn_type", C.c_int32), ("solver", C.c_int32), ("substeps", C.c_int32),
+        ("atol", C.c_float), ("rtol", C.c_float), ("dt0", C.c_float),
+        ("safety", C.c_float), ("factor_min", C.c_float), ("factor_max", C.c_float),
+        ("accept_strict", C.c_int32), ("floor_factor", C.c_int32), ("endpoint_dense", C.c_int32),
+        ("max_steps", C.c_int32), ("precision", C.c_int32), ("save_checkpoints", C.c_int32),
+        ("rows_per_tile", C.c_int32), ("reserved", C.c_int32 * 7),
+    ]
+
+
+_FP = C.c_void_p
+
+
+class OdeRnnWeights(C.Structure):
+    _fields_ = [
+        ("ode_w", _FP * MAX_ODE_LINEARS), ("ode_b", _FP * MAX_ODE_LINEARS),
+        ("rnn_w_ih", _FP * MAX_RNN_LAYERS), ("rnn_w_hh", _FP * MAX_RNN_LAYERS),
+        ("rnn_b_ih", _FP * MAX_RNN_LAYERS), ("rnn_b_hh", _FP * MAX_RNN_LAYERS),
+        ("reg_w0", _FP), ("reg_b0", _FP), ("reg_w1", _FP), ("reg_b1", _FP),
+    ]
+
+
+_lib = None
+
+
+class OdevioError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OdevioError(
+            f"{LIB_PATH} is missing: build it with `python -m odevio_b200.build` "
+            "(there is no CPU or PyTorch fallback for this path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.odevio_version.restype = C.c_int32
+    lib.odevio_error_string.restype = C.c_char_p
+    lib.odevio_error_string.argtypes = [C.c_int32]
+    lib.odevio_odernn_default_cfg.restype = None
+    lib.odevio_odernn_default_cfg.argtypes = [C.POINTER(OdeRnnCfg)]
+    lib.odevio_odernn_workspace_bytes.restype = C.c_size_t
+    lib.odevio_odernn_workspace_bytes.argtypes = [C.POINTER(OdeRnnCfg)]
+    lib.odevio_odernn_forward.restype = C.c_int32
+    lib.odevio_odernn_forward.argtypes = [
+        C.POINTER(OdeRnnCfg), C.POINTER(OdeRnnWeights),
+        _FP, _FP, C.c_int32, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_size_t, _FP]
+    if lib.odevio_version() != 1:
+        raise OdevioError("libodevio_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        msg = load().odevio_error_string(code).decode()
+        raise OdevioError(f"odevio call failed ({code}): {msg}")
+
+
+def dptr(t, name="tensor"):
+    """Device pointer of a contiguous fp32 (or int32) CUDA tensor; None -> NULL."""
+    import torch
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise OdevioError(f"{name} must be a CUDA tensor (odevio_b200 has no CPU path)")
+    if not t.is_contiguous():
+        raise OdevioError(f"{name} must be contiguous")
+    if t.dtype not in (torch.float32, torch.int32, torch.uint8):
+        raise OdevioError(f"{name} must be float32/int32, got {t.dtype}")
+    return C.c_void_p(t.data_ptr())
+
+
+def default_odernn_cfg():
+    cfg = OdeRnnCfg()
+    load().odevio_odernn_default_cfg(C.byref(cfg))
+    return cfg

@@ -1,0 +1,329 @@
+// extern "C" surface of libodevio_b200.so (declared in include/odevio.h).
+// Host side only: argument validation, workspace planning, weight pre-pack launches and the
+// fused-kernel launch, all asynchronous on the caller's stream.
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include "../../include/odevio.h"
+#include "odernn_params.h"
+
+namespace odevio {
+
+cudaError_t transpose_pack(const float* src, int N, int K, float* dst, int ldN, int k_off, int n_off,
+                           cudaStream_t stream);
+cudaError_t bias_sum(const float* a, const float* b, float* dst, int n, cudaStream_t stream);
+cudaError_t launch_odernn_fwd(const FwdParams& prm, int rows_per_tile, int grid, size_t smem_bytes,
+                              cudaStream_t stream);
+
+namespace {
+
+constexpr size_t kSmemLimit = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100
+constexpr int kStageK = 8;              // == KC in tile_gemm.cuh
+constexpr int kMaxStagesRing = 4;       // == MAX_STAGES
+
+// ------------------------------------------------------------------ tableaus (oracle/tableaus.py)
+void zero_tab(DevTableau& t) { memset(&t, 0, sizeof(t)); }
+
+void set_row(DevTableau& t, int i, const double* row, int n) {
+  for (int j = 0; j < n; ++j) t.a[i][j] = static_cast<float>(row[j]);
+}
+
+bool make_tableau(int solver, DevTableau& t) {
+  zero_tab(t);
+  switch (solver) {
+    case ODEVIO_SOLVER_DOPRI5: {
+      t.n_stages = 7; t.fsal = 1; t.ssal = 1; t.has_err = 1; t.has_mid = 1; t.exponent = -1.0f / 5.0f;
+      const double a1[] = {1.0 / 5};
+      const double a2[] = {3.0 / 40, 9.0 / 40};
+      const double a3[] = {44.0 / 45, -56.0 / 15, 32.0 / 9};
+      const double a4[] = {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729};
+      const double a5[] = {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656};
+      const double a6[] = {35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+      set_row(t, 1, a1, 1); set_row(t, 2, a2, 2); set_row(t, 3, a3, 3);
+      set_row(t, 4, a4, 4); set_row(t, 5, a5, 5); set_row(t, 6, a6, 6);
+      const double b[] = {35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84, 0.0};
+      const double e[] = {0.0012326388888888873, 0.0, -0.004252770290506136, 0.036979166666666674,
+                          -0.05086379716981132, 0.04190476190476192, -0.025};
+      const double m[] = {0.10013431883002395, 0.0, 0.3918321794184259, -0.02982460176594817,
+                          0.05893268337240795, -0.04497888809104361, 0.023904308236133973};
+      for (int j = 0; j < 7; ++j) { t.b[j] = (float)b[j]; t.e[j] = (float)e[j]; t.bmid[j] = (float)m[j]; }
+      return true;
+    }
+    case ODEVIO_SOLVER_TSIT5: {
+      t.n_stages = 7; t.fsal = 1; t.ssal = 1; t.has_err = 1; t.has_mid = 1; t.exponent = -1.0f / 5.0f;
+      const double a1[] = {0.161};
+      const double a2[] = {-0.008480655492356989, 0.335480655492357};
+      const double a3[] = {2.8971530571054935, -6.359448489975075, 4.3622954328695815};
+      const double a4[] = {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525};
+      const double a5[] = {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401,
+                           -0.028269050394068383};
+      const double a6[] = {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742,
+                           -3.290069515436081, 2.324710524099774};
+      set_row(t, 1, a1, 1); set_row(t, 2, a2, 2); set_row(t, 3, a3, 3);
+      set_row(t, 4, a4, 4); set_row(t, 5, a5, 5); set_row(t, 6, a6, 6);
+      const double e[] = {-0.001780011052225777, -0.0008164344596567469, 0.007880878010261995,
+                          -0.1447110071732629, 0.5823571654525552, -0.45808210592918697,
+                          0.015151515151515152};
+      const double m[] = {0.10741235230096871, 0.01135625, 0.39560903056045305, -0.34475214352593553,
+                          1.3161853649581645, -1.0170608542936508, 0.031249999999999993};
+      for (int j = 0; j < 6; ++j) t.b[j] = (float)a6[j];
+      t.b[6] = 0.f;
+      for (int j = 0; j < 7; ++j) { t.e[j] = (float)e[j]; t.bmid[j] = (float)m[j]; }
+      return true;
+    }
+    case ODEVIO_SOLVER_HEUN:
+      t.n_stages = 2; t.has_err = 1; t.exponent = -1.0f / 2.0f;
+      t.a[1][0] = 1.f; t.b[0] = 0.5f; t.b[1] = 0.5f; t.e[0] = -0.5f; t.e[1] = 0.5f;
+      return true;
+    case ODEVIO_SOLVER_EULER:
+      t.n_stages = 1; t.exponent = -1.0f; t.b[0] = 1.f;
+      return true;
+    case ODEVIO_SOLVER_RK4:
+      t.n_stages = 4; t.exponent = -1.0f / 4.0f;
+      t.a[1][0] = 0.5f; t.a[2][1] = 0.5f; t.a[3][2] = 1.f;
+      t.b[0] = (float)(1.0 / 6); t.b[1] = (float)(1.0 / 3); t.b[2] = (float)(1.0 / 3); t.b[3] = (float)(1.0 / 6);
+      return true;
+    case ODEVIO_SOLVER_RK4_38:
+      t.n_stages = 4; t.exponent = -1.0f / 4.0f;
+      t.a[1][0] = (float)(1.0 / 3); t.a[2][0] = (float)(-1.0 / 3); t.a[2][1] = 1.f;
+      t.a[3][0] = 1.f; t.a[3][1] = -1.f; t.a[3][2] = 1.f;
+      t.b[0] = (float)(1.0 / 8); t.b[1] = (float)(3.0 / 8); t.b[2] = (float)(3.0 / 8); t.b[3] = (float)(1.0 / 8);
+      return true;
+    default:
+      return false;
+  }
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return 148;
+  }
+  return n;
+}
+
+// Everything derived from cfg: launch geometry, shared-memory carve-up, workspace offsets.
+struct OdePlan {
+  int RT, R, ncons, threads, ntiles, grid, nst, G;
+  size_t bufA_floats, bufB_floats, stage_floats, smem_bytes;
+  size_t off_Wode[kMaxLinears];                 // float offsets into the workspace
+  size_t off_Wrnn[kMaxRnnLayers][4], off_brnn[kMaxRnnLayers][4];
+  size_t off_Wreg0;
+  size_t off_scratch, scratch_floats_per_cta;
+  size_t total_bytes;
+  int Kode[kMaxLinears], Node[kMaxLinears];
+};
+
+int plan_odernn(const odevio_odernn_cfg& c, OdePlan& pl) {
+  if (c.B <= 0 || c.S <= 0 || c.D <= 0 || c.H <= 0) return ODEVIO_E_SHAPE;
+  if (c.n_hidden < 1 || c.n_hidden + 1 > ODEVIO_MAX_ODE_LINEARS) return ODEVIO_E_SHAPE;
+  if (c.L < 1 || c.L > ODEVIO_MAX_RNN_LAYERS) return ODEVIO_E_SHAPE;
+  if (c.D % 8 || c.H % 8) return ODEVIO_E_SHAPE;                 // K chunks of 8, float4 rows
+  if (c.activation < 0 || c.activation > ODEVIO_ACT_SOFTPLUS) return ODEVIO_E_ENUM;
+  if (c.rnn_type != ODEVIO_RNN_TANH && c.rnn_type != ODEVIO_RNN_GRU) return ODEVIO_E_ENUM;
+  if (c.solver < 0 || c.solver > ODEVIO_SOLVER_RK4_38) return ODEVIO_E_ENUM;
+  if (c.precision != ODEVIO_PRECISION_FP32) return ODEVIO_E_ENUM;
+  if (c.rows_per_tile != 0 && c.rows_per_tile != 8 && c.rows_per_tile != 16) return ODEVIO_E_SHAPE;
+  const bool fixed = c.solver == ODEVIO_SOLVER_RK4 || c.solver == ODEVIO_SOLVER_RK4_38;
+  if (fixed && c.substeps < 1) return ODEVIO_E_SHAPE;
+  if (!fixed && c.max_steps < 1) return ODEVIO_E_SHAPE;
+
+  const int nsm = sm_count();
+  int rt = c.rows_per_tile;
+  if (rt == 0) {
+    // pick the tile height that minimises waves x relative tile cost (16-row tiles amortise the
+    // weight stream better: ~1.6x the time of an 8-row tile for 2x the rows)
+    const long w8 = ((c.B + 7) / 8 + nsm - 1) / nsm, w16 = ((c.B + 15) / 16 + nsm - 1) / nsm;
+    rt = (c.L <= 2 && w16 * 16 < w8 * 10) ? 16 : 8;
+  }
+  if (rt == 16 && c.L > 2) return ODEVIO_E_SHAPE;
+  pl.RT = rt;
+  pl.R = rt * c.L;
+  pl.ncons = 128 * c.L;
+  pl.threads = pl.ncons + 32;
+  pl.ntiles = (c.B + rt - 1) / rt;
+  pl.grid = pl.ntiles < nsm ? pl.ntiles : nsm;
+  pl.G = c.rnn_type == ODEVIO_RNN_GRU ? 3 : 1;
+
+  const int NL = c.n_hidden + 1;
+  int nmax = kRegHidden;
+  for (int j = 0; j < NL; ++j) {
+    pl.Kode[j] = j == 0 ? c.D : c.H;
+    pl.Node[j] = j == NL - 1 ? c.D : c.H;
+    if (pl.Node[j] > nmax) nmax = pl.Node[j];
+  }
+  if (c.D > nmax) nmax = c.D;
+  // column pairs per thread <= 4: ODE GEMMs use 128 threads per row block, the jump all consumers
+  if (nmax > 2 * 4 * 128) return ODEVIO_E_SHAPE;
+
+  const size_t maxdh = static_cast<size_t>(c.D > c.H ? c.D : c.H);
+  size_t a = maxdh * pl.R, a2 = static_cast<size_t>(2) * c.D * rt;
+  pl.bufA_floats = a > a2 ? a : a2;
+  size_t b = static_cast<size_t>(c.H) * pl.R, b2 = static_cast<size_t>(c.D) * rt;
+  pl.bufB_floats = b > b2 ? b : b2;
+  pl.stage_floats = static_cast<size_t>(kStageK) * nmax;
+  const size_t fixed_bytes = (pl.bufA_floats + pl.bufB_floats + 4 * static_cast<size_t>(pl.ncons) +
+                              14 * static_cast<size_t>(pl.R)) * sizeof(float) + 8 + 2 * kMaxStagesRing * 8 + 128;
+  if (fixed_bytes + 2 * pl.stage_floats * sizeof(float) > kSmemLimit) return ODEVIO_E_SHAPE;
+  size_t nst = (kSmemLimit - fixed_bytes) / (pl.stage_floats * sizeof(float));
+  if (nst > kMaxStagesRing) nst = kMaxStagesRing;
+  pl.nst = static_cast<int>(nst);
+  pl.smem_bytes = fixed_bytes + nst * pl.stage_floats * sizeof(float);
+
+  // ---- workspace layout (floats), every block 64-float (256 B) aligned
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = align_up(off + n, 64); return o; };
+  for (int j = 0; j < NL; ++j) pl.off_Wode[j] = take(static_cast<size_t>(pl.Kode[j]) * pl.Node[j]);
+  const size_t DD = static_cast<size_t>(c.D) * c.D;
+  for (int l = 0; l < c.L; ++l) {
+    if (pl.G == 1) {
+      pl.off_Wrnn[l][0] = take(2 * DD); pl.off_brnn[l][0] = take(c.D);
+    } else {
+      pl.off_Wrnn[l][0] = take(2 * DD); pl.off_Wrnn[l][1] = take(2 * DD);
+      pl.off_Wrnn[l][2] = take(DD); pl.off_Wrnn[l][3] = take(DD);
+      for (int g = 0; g < 4; ++g) pl.off_brnn[l][g] = take(c.D);
+    }
+  }
+  pl.off_Wreg0 = take(static_cast<size_t>(c.D) * kRegHidden);
+  pl.scratch_floats_per_cta = align_up(static_cast<size_t>(kMaxStages + 2) * c.D * pl.R, 64);
+  pl.off_scratch = take(pl.scratch_floats_per_cta * pl.grid);
+  pl.total_bytes = off * sizeof(float);
+  return 0;
+}
+
+#define ODEVIO_CUDA_TRY(expr)                                   \
+  do {                                                          \
+    cudaError_t _e = (expr);                                    \
+    if (_e != cudaSuccess) return static_cast<int32_t>(_e);     \
+  } while (0)
+
+}  // namespace
+}  // namespace odevio
+
+using namespace odevio;
+
+extern "C" {
+
+int32_t odevio_version(void) { return ODEVIO_ABI_VERSION; }
+
+const char* odevio_error_string(int32_t code) {
+  switch (code) {
+    case 0: return "ok";
+    case ODEVIO_E_NULL: return "required pointer is NULL";
+    case ODEVIO_E_SHAPE: return "unsupported or inconsistent dimension";
+    case ODEVIO_E_ENUM: return "unknown activation / rnn / solver / precision id";
+    case ODEVIO_E_WORKSPACE: return "workspace too small or misaligned";
+    case ODEVIO_E_DEVICE: return "no usable sm_100 device";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown odevio error";
+  }
+}
+
+void odevio_odernn_default_cfg(odevio_odernn_cfg* cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->B = 1; cfg->S = 10; cfg->D = 768; cfg->H = 512; cfg->n_hidden = 3; cfg->L = 2;
+  cfg->activation = ODEVIO_ACT_TANH; cfg->rnn_type = ODEVIO_RNN_TANH; cfg->solver = ODEVIO_SOLVER_DOPRI5;
+  cfg->substeps = 1;
+  cfg->atol = 1e-6f; cfg->rtol = 1e-2f; cfg->dt0 = 1e-4f;
+  cfg->safety = 0.9f; cfg->factor_min = 0.2f; cfg->factor_max = 10.0f;
+  cfg->accept_strict = 1; cfg->floor_factor = 0; cfg->endpoint_dense = 1;
+  cfg->max_steps = 100000;
+  cfg->precision = ODEVIO_PRECISION_FP32;
+}
+
+size_t odevio_odernn_workspace_bytes(const odevio_odernn_cfg* cfg) {
+  if (!cfg) return 0;
+  OdePlan pl;
+  if (plan_odernn(*cfg, pl) != 0) return 0;
+  return pl.total_bytes;
+}
+
+int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_weights* w,
+                              const float* fv, const float* fi, int32_t Dv,
+                              const float* ts, const float* h0,
+                              float* pose, float* hT, int32_t* stats, int32_t* status,
+                              void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!cfg || !w || !fv || !ts || !pose || !hT || !workspace) return ODEVIO_E_NULL;
+  const odevio_odernn_cfg& c = *cfg;
+  OdePlan pl;
+  const int rc = plan_odernn(c, pl);
+  if (rc != 0) return rc;
+  if (Dv <= 0 || Dv > c.D || (Dv < c.D && !fi) || (Dv == c.D && fi)) return ODEVIO_E_SHAPE;
+  if (workspace_bytes < pl.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ODEVIO_E_WORKSPACE;
+  const int NL = c.n_hidden + 1;
+  for (int j = 0; j < NL; ++j) if (!w->ode_w[j] || !w->ode_b[j]) return ODEVIO_E_NULL;
+  for (int l = 0; l < c.L; ++l)
+    if (!w->rnn_w_ih[l] || !w->rnn_w_hh[l] || !w->rnn_b_ih[l] || !w->rnn_b_hh[l]) return ODEVIO_E_NULL;
+  if (!w->reg_w0 || !w->reg_b0 || !w->reg_w1 || !w->reg_b1) return ODEVIO_E_NULL;
+
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* ws = static_cast<float*>(workspace);
+  const int D = c.D;
+
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = c.B; p.S = c.S; p.D = D; p.H = c.H; p.NL = NL; p.L = c.L;
+  p.act = c.activation; p.rnn_type = c.rnn_type;
+  p.adaptive = !(c.solver == ODEVIO_SOLVER_RK4 || c.solver == ODEVIO_SOLVER_RK4_38);
+  p.substeps = c.substeps;
+  p.atol = c.atol; p.rtol = c.rtol; p.dt0 = c.dt0; p.safety = c.safety; p.fmin = c.factor_min; p.fmax = c.factor_max;
+  p.accept_strict = c.accept_strict; p.floor_factor = c.floor_factor; p.endpoint_dense = c.endpoint_dense;
+  p.max_steps = c.max_steps;
+  if (!make_tableau(c.solver, p.tab)) return ODEVIO_E_ENUM;
+
+  // ---- pre-pack weights into the workspace
+  for (int j = 0; j < NL; ++j) {
+    float* dst = ws + pl.off_Wode[j];
+    ODEVIO_CUDA_TRY(transpose_pack(w->ode_w[j], pl.Node[j], pl.Kode[j], dst, pl.Node[j], 0, 0, stream));
+    p.Wode[j] = dst; p.bode[j] = w->ode_b[j]; p.Kode[j] = pl.Kode[j]; p.Node[j] = pl.Node[j];
+  }
+  const size_t DD = static_cast<size_t>(D) * D;
+  for (int l = 0; l < c.L; ++l) {
+    if (pl.G == 1) {
+      float* dst = ws + pl.off_Wrnn[l][0];
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l], D, D, dst, D, 0, 0, stream));
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_hh[l], D, D, dst, D, D, 0, stream));
+      float* bd = ws + pl.off_brnn[l][0];
+      ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_ih[l], w->rnn_b_hh[l], bd, D, stream));
+      p.Wrnn[l][0] = dst; p.brnn[l][0] = bd;
+    } else {
+      // PyTorch GRU gate order (r, z, n) along the rows of weight_ih / weight_hh
+      float* wr = ws + pl.off_Wrnn[l][0]; float* wz = ws + pl.off_Wrnn[l][1];
+      float* wi = ws + pl.off_Wrnn[l][2]; float* wh = ws + pl.off_Wrnn[l][3];
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l], D, D, wr, D, 0, 0, stream));
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_hh[l], D, D, wr, D, D, 0, stream));
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l] + DD, D, D, wz, D, 0, 0, stream));
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_hh[l] + DD, D, D, wz, D, D, 0, stream));
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l] + 2 * DD, D, D, wi, D, 0, 0, stream));
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_hh[l] + 2 * DD, D, D, wh, D, 0, 0, stream));
+      float* br = ws + pl.off_brnn[l][0]; float* bz = ws + pl.off_brnn[l][1];
+      float* bi = ws + pl.off_brnn[l][2]; float* bh = ws + pl.off_brnn[l][3];
+      ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_ih[l], w->rnn_b_hh[l], br, D, stream));
+      ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_ih[l] + D, w->rnn_b_hh[l] + D, bz, D, stream));
+      ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_ih[l] + 2 * D, nullptr, bi, D, stream));
+      ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_hh[l] + 2 * D, nullptr, bh, D, stream));
+      p.Wrnn[l][0] = wr; p.Wrnn[l][1] = wz; p.Wrnn[l][2] = wi; p.Wrnn[l][3] = wh;
+      p.brnn[l][0] = br; p.brnn[l][1] = bz; p.brnn[l][2] = bi; p.brnn[l][3] = bh;
+    }
+  }
+  {
+    float* dst = ws + pl.off_Wreg0;
+    ODEVIO_CUDA_TRY(transpose_pack(w->reg_w0, kRegHidden, D, dst, kRegHidden, 0, 0, stream));
+    p.Wreg0 = dst; p.breg0 = w->reg_b0; p.Wreg1 = w->reg_w1; p.breg1 = w->reg_b1;
+  }
+  p.fv = fv; p.fi = fi; p.Dv = Dv; p.ts = ts; p.h0 = h0;
+  p.pose = pose; p.hT = hT; p.stats = stats; p.status = status;
+  p.scratch = ws + pl.off_scratch; p.scratch_floats_per_cta = pl.scratch_floats_per_cta;
+  p.ntiles = pl.ntiles; p.nst = pl.nst;
+  p.bufA_floats = static_cast<int>(pl.bufA_floats); p.bufB_floats = static_cast<int>(pl.bufB_floats);
+  p.stage_floats = static_cast<int>(pl.stage_floats);
+
+  ODEVIO_CUDA_TRY(launch_odernn_fwd(p, pl.RT, pl.grid, pl.smem_bytes, stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,548 @@
+// Fused ODE-RNN regressor forward: ONE persistent kernel runs, for a tile of sequences, every
+// observation interval's ODE solves (all RK stages, Butcher combines, error norm, step-size
+// controller, dense-output end point), the RNN/GRU jump and the pose head, without returning
+// to the host.
+//
+// Replaces the arithmetic behind (reference file:line):
+//   PoseODERNN.forward / evolve_state      src/models/PoseODERNN.py:88-123, :70-75
+//   torchode AutoDiffAdjoint.solve et al.  (call sites src/models/PoseODERNN.py:55-60) -- semantics
+//                                          as restated in oracle/torchode_like.py
+//   ODEFunc.forward                        src/models/ODEFunc.py:38-39
+//   nn.RNN / nn.GRU single step            src/models/PoseODERNN.py:114
+//   regressor head                         src/models/PoseODERNN.py:64-68,122
+//
+// Tile = RT sequences x L rnn layers = R "ODE rows" that share one ODEFunc (the reference's
+// jit.fork over layers, PoseODERNN.py:109, becomes extra rows of the same GEMM).  Row r = l*RT+m.
+// State/stage vectors of a tile live in per-CTA global scratch (L2 resident) in T-layout
+// [d][R]; GEMM operands in shared memory; weights stream through the TMA ring of tile_gemm.cuh.
+#include "odernn_params.h"
+#include "tile_gemm.cuh"
+
+namespace odevio {
+
+namespace {
+
+struct RowState {      // shared-memory per-row solver state (arrays of R)
+  float* t; float* dt; float* tend; float* tmin; float* tmax;
+  float* dtstep; float* x;
+  int* run; int* noteval; int* upd; int* toeval; int* nsteps; int* nacc; int* status;
+};
+
+template <int RT>
+struct Ctx {
+  const FwdParams* prm;
+  TileThread th;
+  WeightRing ring;
+  RingPos pos;
+  float* bufA; float* bufB; float* partial;
+  RowState rs;
+  float* K[kMaxStages]; float* Y; float* Y1;
+  int R;        // rows in the tile
+  int rq4;      // R / 4
+  int rq;       // this consumer's row quad for elementwise passes
+  int tile;     // current tile index
+};
+
+// ---- elementwise helpers over T-layout [D][R]; one float4 = 4 rows of one feature ---------
+
+__device__ __forceinline__ float4 wsum4(const float* const* K, const float* coef, int n, size_t off,
+                                        bool& any) {
+  // acc = c0*k0 + c1*k1 + ... left to right, skipping exact zeros (oracle/_weighted_sum)
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  any = false;
+  for (int j = 0; j < n; ++j) {
+    const float cj = coef[j];
+    if (cj == 0.f) continue;
+    const float4 k = ld4(K[j] + off);
+    if (!any) {
+      acc = make_float4(mul_(k.x, cj), mul_(k.y, cj), mul_(k.z, cj), mul_(k.w, cj));
+      any = true;
+    } else {
+      acc = make_float4(add_(acc.x, mul_(k.x, cj)), add_(acc.y, mul_(k.y, cj)),
+                        add_(acc.z, mul_(k.z, cj)), add_(acc.w, mul_(k.w, cj)));
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ float4 axpy4(float4 y, float4 dt, float4 acc) {   // y + dt*acc
+  return make_float4(add_(y.x, mul_(dt.x, acc.x)), add_(y.y, mul_(dt.y, acc.y)),
+                     add_(y.z, mul_(dt.z, acc.z)), add_(y.w, mul_(dt.w, acc.w)));
+}
+
+// stage argument i -> bufA (shared T-layout).  i == 0 copies Y.
+template <int RT>
+__device__ __forceinline__ void stage_input(Ctx<RT>& c, int i) {
+  if (c.th.producer) return;
+  const FwdParams& p = *c.prm;
+  const int nvec = p.D * c.rq4;
+  const float4 dt = ld4(c.rs.dt + 4 * c.rq);
+  for (int e = c.th.ctid; e < nvec; e += c.th.ncons) {
+    const size_t off = static_cast<size_t>(e) * 4;
+    float4 y = ld4(c.Y + off);
+    if (i > 0) {
+      bool any;
+      const float4 acc = wsum4(c.K, p.tab.a[i], i, off, any);
+      if (any) y = axpy4(y, dt, acc);
+    }
+    st4(c.bufA + off, y);
+  }
+  named_bar_sync(1, c.th.ncons);
+}
+
+// ODEFunc evaluation: bufA (x, [D][R]) -> global K[dst] ([D][R]).
+template <int RT>
+__device__ __forceinline__ void eval_vector_field(Ctx<RT>& c, int dst) {
+  const FwdParams& p = *c.prm;
+  float* in = c.bufA;
+  float* out = c.bufB;
+  for (int j = 0; j < p.NL; ++j) {
+    Epilogue e;
+    e.mode = EPI_STORE;
+    e.bias = p.bode[j];
+    e.out1 = nullptr; e.ld1 = 0; e.off1 = 0;
+    if (j == p.NL - 1) {       // output layer: Tanh, straight to the stage array in scratch
+      e.act = ACT_TANH; e.out0 = c.K[dst]; e.ld0 = c.R; e.off0 = 0;
+    } else {
+      e.act = p.act; e.out0 = out; e.ld0 = c.R; e.off0 = 0;
+    }
+    tile_gemm<RT>(c.ring, c.pos, c.th, p.Wode[j], p.Kode[j], p.Node[j], in, c.R, p.L, e);
+    float* t = in; in = out; out = t;
+  }
+}
+
+// Error pass: y1 -> Y1, per-row sum of (err / bound)^2 -> partial[].
+template <int RT>
+__device__ __forceinline__ void error_pass(Ctx<RT>& c) {
+  if (c.th.producer) return;
+  const FwdParams& p = *c.prm;
+  const DevTableau& tb = p.tab;
+  const int nvec = p.D * c.rq4;
+  const int s = tb.n_stages;
+  const float4 dt = ld4(c.rs.dt + 4 * c.rq);
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e = c.th.ctid; e < nvec; e += c.th.ncons) {
+    const size_t off = static_cast<size_t>(e) * 4;
+    const float4 y0 = ld4(c.Y + off);
+    bool any;
+    float4 acc = tb.ssal ? wsum4(c.K, tb.a[s - 1], s - 1, off, any) : wsum4(c.K, tb.b, s, off, any);
+    const float4 y1 = any ? axpy4(y0, dt, acc) : y0;
+    st4(c.Y1 + off, y1);
+    if (tb.has_err) {
+      acc = wsum4(c.K, tb.e, s, off, any);
+      const float ex = mul_(dt.x, acc.x), ey = mul_(dt.y, acc.y), ez = mul_(dt.z, acc.z), ew = mul_(dt.w, acc.w);
+      const float bx = add_(p.atol, mul_(p.rtol, fmaxf(fabsf(y0.x), fabsf(y1.x))));
+      const float by = add_(p.atol, mul_(p.rtol, fmaxf(fabsf(y0.y), fabsf(y1.y))));
+      const float bz = add_(p.atol, mul_(p.rtol, fmaxf(fabsf(y0.z), fabsf(y1.z))));
+      const float bw = add_(p.atol, mul_(p.rtol, fmaxf(fabsf(y0.w), fabsf(y1.w))));
+      const float rx = __fdiv_rn(ex, bx), ry = __fdiv_rn(ey, by), rz = __fdiv_rn(ez, bz), rw = __fdiv_rn(ew, bw);
+      sum.x = fmaf(rx, rx, sum.x); sum.y = fmaf(ry, ry, sum.y);
+      sum.z = fmaf(rz, rz, sum.z); sum.w = fmaf(rw, rw, sum.w);
+    }
+  }
+  st4(c.partial + 4 * c.th.ctid, sum);
+  named_bar_sync(1, c.th.ncons);
+}
+
+// Per-row step-size controller + bookkeeping (thread ctid == row).  Returns "row still running".
+template <int RT>
+__device__ __forceinline__ int controller(Ctx<RT>& c, int loops) {
+  if (c.th.producer || c.th.ctid >= c.R) return 0;
+  const FwdParams& p = *c.prm;
+  const int r = c.th.ctid;
+  RowState& rs = c.rs;
+  int run = rs.run[r];
+  const float dt = rs.dt[r];
+  float t = rs.t[r];
+  const float tend = rs.tend[r];
+  bool accept = true, finite = true;
+  float dt_next = dt;
+  if (p.tab.has_err) {
+    // deterministic reduction of the partial sums of this row's quad, in thread order
+    const int rq = r >> 2, j = r & 3;
+    float total = 0.f;
+    for (int k = rq; k < c.th.ncons; k += c.rq4) total = add_(total, c.partial[4 * k + j]);
+    const float ratio = sqrtf(__fdiv_rn(total, static_cast<float>(p.D)));
+    finite = isfinite(ratio);
+    accept = p.accept_strict ? (ratio < 1.0f) : (ratio <= 1.0f);
+    float factor = mul_(p.safety, powf(ratio, p.tab.exponent));
+    factor = fminf(fmaxf(factor, p.fmin), p.fmax);
+    if (p.floor_factor && accept) factor = fmaxf(factor, 1.0f);
+    dt_next = mul_(dt, factor);
+  }
+  const int upd = (accept && run) ? 1 : 0;
+  rs.nsteps[r] += run;
+  rs.nacc[r] += upd;
+  const float t_new = upd ? add_(t, dt) : t;
+  const int toeval = (upd && t_new >= tend && rs.noteval[r]) ? 1 : 0;
+  if (toeval) {
+    rs.x[r] = __fdiv_rn(sub_(tend, t), dt);
+    rs.noteval[r] = 0;
+  }
+  rs.upd[r] = upd;
+  rs.toeval[r] = toeval;
+  rs.dtstep[r] = dt;
+  t = t_new;
+  if (run && !finite) rs.status[r] = max(rs.status[r], 2);
+  run = (run && t < tend && finite) ? 1 : 0;
+  if (run && loops >= p.max_steps) { rs.status[r] = max(rs.status[r], 1); run = 0; }
+  float dtn = run ? dt_next : dt;
+  dtn = fminf(fmaxf(dtn, sub_(rs.tmin[r], t)), sub_(rs.tmax[r], t));
+  rs.t[r] = t;
+  rs.dt[r] = dtn;
+  rs.run[r] = run;
+  return run;
+}
+
+// Commit pass: accepted rows take y1 (or the dense-output value at t_end), FSAL carry.
+template <int RT>
+__device__ __forceinline__ void commit_pass(Ctx<RT>& c) {
+  if (c.th.producer) return;
+  const FwdParams& p = *c.prm;
+  const DevTableau& tb = p.tab;
+  const int s = tb.n_stages;
+  const int r0 = 4 * c.rq;
+  int upd[4], tev[4];
+  float dts[4], xs[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    upd[j] = c.rs.upd[r0 + j]; tev[j] = c.rs.toeval[r0 + j] && p.endpoint_dense;
+    dts[j] = c.rs.dtstep[r0 + j]; xs[j] = c.rs.x[r0 + j];
+  }
+  if (!(upd[0] | upd[1] | upd[2] | upd[3])) return;
+  const bool any_dense = tev[0] | tev[1] | tev[2] | tev[3];
+  const int nvec = p.D * c.rq4;
+  for (int e = c.th.ctid; e < nvec; e += c.th.ncons) {
+    const size_t off = static_cast<size_t>(e) * 4;
+    const float4 y0v = ld4(c.Y + off);
+    const float4 y1v = ld4(c.Y1 + off);
+    float y0[4] = {y0v.x, y0v.y, y0v.z, y0v.w};
+    float y1[4] = {y1v.x, y1v.y, y1v.z, y1v.w};
+    float out[4];
+    float ymid[4] = {0.f, 0.f, 0.f, 0.f}, f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (any_dense && tb.has_mid) {
+      bool any;
+      const float4 dtv = make_float4(dts[0], dts[1], dts[2], dts[3]);
+      const float4 acc = wsum4(c.K, tb.bmid, s, off, any);
+      const float4 ym = axpy4(y0v, dtv, acc);
+      const float4 k0 = ld4(c.K[0] + off), kl = ld4(c.K[s - 1] + off);
+      ymid[0] = ym.x; ymid[1] = ym.y; ymid[2] = ym.z; ymid[3] = ym.w;
+      f0[0] = mul_(dts[0], k0.x); f0[1] = mul_(dts[1], k0.y); f0[2] = mul_(dts[2], k0.z); f0[3] = mul_(dts[3], k0.w);
+      f1[0] = mul_(dts[0], kl.x); f1[1] = mul_(dts[1], kl.y); f1[2] = mul_(dts[2], kl.z); f1[3] = mul_(dts[3], kl.w);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = y0[j];
+      if (upd[j]) {
+        v = y1[j];
+        if (tev[j]) {
+          const float x = xs[j];
+          if (tb.has_mid) {
+            // quartic through (y0, y1, f0, f1, y_mid); operation order mirrors oracle/dense_eval
+            const float a = add_(sub_(mul_(2.0f, sub_(f1[j], f0[j])), mul_(8.0f, add_(y1[j], y0[j]))),
+                                 mul_(16.0f, ymid[j]));
+            const float b = sub_(add_(add_(sub_(mul_(5.0f, f0[j]), mul_(3.0f, f1[j])), mul_(18.0f, y0[j])),
+                                      mul_(14.0f, y1[j])), mul_(32.0f, ymid[j]));
+            const float cc = add_(sub_(sub_(sub_(f1[j], mul_(4.0f, f0[j])), mul_(11.0f, y0[j])),
+                                       mul_(5.0f, y1[j])), mul_(16.0f, ymid[j]));
+            v = add_(mul_(add_(mul_(add_(mul_(add_(mul_(a, x), b), x), cc), x), f0[j]), x), y0[j]);
+          } else {
+            v = add_(y0[j], mul_(x, sub_(y1[j], y0[j])));
+          }
+        }
+      }
+      out[j] = v;
+    }
+    st4(c.Y + off, make_float4(out[0], out[1], out[2], out[3]));
+    if (tb.fsal) {
+      const float4 kold = ld4(c.K[0] + off), kl = ld4(c.K[s - 1] + off);
+      st4(c.K[0] + off, make_float4(upd[0] ? kl.x : kold.x, upd[1] ? kl.y : kold.y,
+                                    upd[2] ? kl.z : kold.z, upd[3] ? kl.w : kold.w));
+    }
+  }
+}
+
+// Fixed-step commit: Y <- y0 + dt * sum b_j k_j  (every row).
+template <int RT>
+__device__ __forceinline__ void fixed_commit(Ctx<RT>& c) {
+  if (c.th.producer) return;
+  const FwdParams& p = *c.prm;
+  const int nvec = p.D * c.rq4;
+  const float4 dt = ld4(c.rs.dt + 4 * c.rq);
+  for (int e = c.th.ctid; e < nvec; e += c.th.ncons) {
+    const size_t off = static_cast<size_t>(e) * 4;
+    const float4 y0 = ld4(c.Y + off);
+    bool any;
+    const float4 acc = wsum4(c.K, p.tab.b, p.tab.n_stages, off, any);
+    st4(c.Y + off, any ? axpy4(y0, dt, acc) : y0);
+  }
+}
+
+// One observation interval: evolve all R rows from ts[b,i] to ts[b,i+1].
+template <int RT>
+__device__ __forceinline__ void solve_interval(Ctx<RT>& c, int i) {
+  const FwdParams& p = *c.prm;
+  const DevTableau& tb = p.tab;
+  RowState& rs = c.rs;
+  int run = 0;
+  if (!c.th.producer && c.th.ctid < c.R) {
+    const int r = c.th.ctid;
+    const int b = c.tile * RT + (r % RT);
+    float t0 = 0.f, t1 = 0.f;
+    if (b < p.B) {
+      t0 = p.ts[static_cast<size_t>(b) * (p.S + 1) + i];
+      t1 = p.ts[static_cast<size_t>(b) * (p.S + 1) + i + 1];
+    }
+    rs.t[r] = t0; rs.tend[r] = t1;
+    rs.tmin[r] = fminf(t0, t1); rs.tmax[r] = fmaxf(t0, t1);
+    rs.nsteps[r] = 0; rs.nacc[r] = 0;
+    rs.upd[r] = 0; rs.toeval[r] = 0; rs.x[r] = 1.f;
+    if (p.adaptive) {
+      rs.dt[r] = fminf(fmaxf(p.dt0, sub_(rs.tmin[r], t0)), sub_(rs.tmax[r], t0));
+      run = (t0 < t1) ? 1 : 0;
+    } else {
+      rs.dt[r] = __fdiv_rn(sub_(t1, t0), static_cast<float>(p.substeps));
+      run = 1;
+    }
+    rs.dtstep[r] = rs.dt[r];
+    rs.run[r] = run; rs.noteval[r] = run;
+  }
+  int any_running = __syncthreads_or(run);
+
+  // One loop serves adaptive and fixed-step solvers; the first pass evaluates stage 0 (for FSAL
+  // methods that is torchode's up-front vector-field evaluation), later passes reuse it.
+  int loops = 0;
+  bool have_k0 = false;
+  while (any_running) {
+    ++loops;
+    for (int st = (tb.fsal && have_k0) ? 1 : 0; st < tb.n_stages; ++st) {
+      stage_input<RT>(c, st);
+      eval_vector_field<RT>(c, st);
+    }
+    have_k0 = true;
+    if (p.adaptive) {
+      error_pass<RT>(c);
+      run = controller<RT>(c, loops);
+      any_running = __syncthreads_or(run);
+      commit_pass<RT>(c);
+    } else {
+      fixed_commit<RT>(c);
+      if (!c.th.producer && c.th.ctid < c.R) { rs.nsteps[c.th.ctid] += 1; rs.nacc[c.th.ctid] += 1; }
+      any_running = loops < p.substeps;
+    }
+  }
+  // stats[S][L][B][2]
+  if (!c.th.producer && c.th.ctid < c.R) {
+    const int r = c.th.ctid;
+    const int l = r / RT, b = c.tile * RT + (r % RT);
+    if (b < p.B) {
+      if (p.stats) {
+        int* sp = p.stats + ((static_cast<size_t>(i) * p.L + l) * p.B + b) * 2;
+        sp[0] = rs.nsteps[r]; sp[1] = rs.nacc[r];
+      }
+    }
+  }
+}
+
+// RNN / GRU jump for all layers + pose head for interval i.
+template <int RT>
+__device__ __forceinline__ void jump_and_regress(Ctx<RT>& c, int i) {
+  const FwdParams& p = *c.prm;
+  const int D = p.D;
+  const TileThread& th = c.th;
+  for (int l = 0; l < p.L; ++l) {
+    // ---- assemble [x ; h] in bufA as T-layout [2D][RT]
+    if (!th.producer) {
+      if (l == 0) {
+        for (int e = th.ctid; e < D * RT; e += th.ncons) {
+          const int m = e / D, k = e - m * D;          // coalesced along k
+          const int b = c.tile * RT + m;
+          float v = 0.f;
+          if (b < p.B) {
+            const size_t row = static_cast<size_t>(b) * p.S + i;
+            v = (k < p.Dv) ? p.fv[row * p.Dv + k] : p.fi[row * (D - p.Dv) + (k - p.Dv)];
+          }
+          c.bufA[k * RT + m] = v;
+        }
+      } else {
+        for (int e = th.ctid; e < D * RT / 4; e += th.ncons) st4(c.bufA + 4 * e, ld4(c.bufB + 4 * e));
+      }
+      for (int e = th.ctid; e < D * RT / 4; e += th.ncons) {
+        const int d = e / (RT / 4), q = e - d * (RT / 4);
+        st4(c.bufA + static_cast<size_t>(D + d) * RT + 4 * q,
+            ld4(c.Y + static_cast<size_t>(d) * c.R + l * RT + 4 * q));
+      }
+      named_bar_sync(1, th.ncons);
+    }
+    Epilogue e;
+    e.mode = EPI_STORE;
+    e.ld0 = RT; e.off0 = 0; e.out1 = nullptr; e.ld1 = 0; e.off1 = 0;
+    e.rg = e.zg = e.hn = e.hprev = nullptr;
+    if (p.rnn_type == 0) {
+      e.bias = p.brnn[l][0]; e.act = ACT_TANH;
+      e.out0 = c.bufB;
+      e.out1 = c.Y; e.ld1 = c.R; e.off1 = l * RT;
+      tile_gemm<RT>(c.ring, c.pos, th, p.Wrnn[l][0], 2 * D, D, c.bufA, RT, 1, e);
+    } else {
+      // gates r, z (K = 2D), hn (K = D on the h half), then the new gate on the x half
+      float* RG = c.K[1]; float* ZG = c.K[2]; float* HN = c.K[3];   // scratch, [D][RT]
+      e.bias = p.brnn[l][0]; e.act = ACT_SIGMOID; e.out0 = RG;
+      tile_gemm<RT>(c.ring, c.pos, th, p.Wrnn[l][0], 2 * D, D, c.bufA, RT, 1, e);
+      e.bias = p.brnn[l][1]; e.out0 = ZG;
+      tile_gemm<RT>(c.ring, c.pos, th, p.Wrnn[l][1], 2 * D, D, c.bufA, RT, 1, e);
+      e.bias = p.brnn[l][3]; e.act = ACT_NONE; e.out0 = HN;
+      tile_gemm<RT>(c.ring, c.pos, th, p.Wrnn[l][3], D, D, c.bufA + static_cast<size_t>(D) * RT, RT, 1, e);
+      e.mode = EPI_GRU_NEW;
+      e.bias = p.brnn[l][2]; e.rg = RG; e.zg = ZG; e.hn = HN;
+      e.hprev = c.bufA + static_cast<size_t>(D) * RT;
+      e.out0 = c.bufB;
+      e.out1 = c.Y; e.ld1 = c.R; e.off1 = l * RT;
+      tile_gemm<RT>(c.ring, c.pos, th, p.Wrnn[l][2], D, D, c.bufA, RT, 1, e);
+    }
+  }
+  // ---- pose head on the top layer's output (bufB, [D][RT])
+  {
+    Epilogue e;
+    e.mode = EPI_STORE;
+    e.bias = p.breg0; e.act = ACT_LEAKY01;
+    e.out0 = c.bufA; e.ld0 = RT; e.off0 = 0;
+    e.out1 = nullptr; e.ld1 = 0; e.off1 = 0;
+    e.rg = e.zg = e.hn = e.hprev = nullptr;
+    tile_gemm<RT>(c.ring, c.pos, th, p.Wreg0, D, kRegHidden, c.bufB, RT, 1, e);
+    if (!th.producer) {
+      if (th.ctid < RT * kPoseDim) {
+        const int m = th.ctid / kPoseDim, o = th.ctid - m * kPoseDim;
+        const int b = c.tile * RT + m;
+        float acc = 0.f;
+        for (int k = 0; k < kRegHidden; ++k) acc = fmaf(c.bufA[k * RT + m], p.Wreg1[o * kRegHidden + k], acc);
+        if (b < p.B) p.pose[(static_cast<size_t>(b) * p.S + i) * kPoseDim + o] = acc + p.breg1[o];
+      }
+      named_bar_sync(1, th.ncons);
+    }
+  }
+}
+
+}  // namespace
+
+template <int RT, int LL>
+__global__ void __launch_bounds__(128 * LL + 32, 1)
+odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Ctx<RT> c;
+  c.prm = &prm;
+  const int tid = threadIdx.x;
+  constexpr int ncons = 128 * LL;
+  c.th.ncons = ncons;
+  c.th.lane = tid & 31;
+  c.th.producer = tid >= ncons;
+  c.th.ctid = c.th.producer ? 0 : tid;
+  constexpr int R = RT * LL;
+  c.R = R;
+  c.rq4 = R / 4;
+  c.rq = c.th.ctid % (R / 4);
+
+  // ---- shared memory carve-up (sizes mirrored by plan_odernn in api.cu)
+  float* sm = reinterpret_cast<float*>(smem_raw);
+  c.bufA = sm; sm += prm.bufA_floats;
+  c.bufB = sm; sm += prm.bufB_floats;
+  float* stages = sm; sm += static_cast<size_t>(prm.nst) * prm.stage_floats;
+  c.partial = sm; sm += 4 * ncons;
+  RowState& rs = c.rs;
+  rs.t = sm; sm += R; rs.dt = sm; sm += R; rs.tend = sm; sm += R; rs.tmin = sm; sm += R;
+  rs.tmax = sm; sm += R; rs.dtstep = sm; sm += R; rs.x = sm; sm += R;
+  int* si = reinterpret_cast<int*>(sm);
+  rs.run = si; si += R; rs.noteval = si; si += R; rs.upd = si; si += R; rs.toeval = si; si += R;
+  rs.nsteps = si; si += R; rs.nacc = si; si += R; rs.status = si; si += R;
+  uintptr_t bp = (reinterpret_cast<uintptr_t>(si) + 7) & ~static_cast<uintptr_t>(7);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bp);
+  c.ring.buf = stages;
+  c.ring.buf_off = static_cast<uint32_t>(reinterpret_cast<unsigned char*>(stages) - smem_raw);
+  c.ring.full = bars;
+  c.ring.empty = bars + MAX_STAGES;
+  c.ring.stage_floats = prm.stage_floats;
+  c.ring.nst = prm.nst;
+  c.pos.stage = 0;
+  c.pos.phase = 0;
+  if (tid == 0) {
+    for (int s = 0; s < prm.nst; ++s) {
+      mbar_init(&c.ring.full[s], 1);
+      mbar_init(&c.ring.empty[s], ncons / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // ---- per-CTA scratch
+  const size_t arr = static_cast<size_t>(prm.D) * R;
+  float* sc = prm.scratch + static_cast<size_t>(blockIdx.x) * prm.scratch_floats_per_cta;
+  for (int j = 0; j < kMaxStages; ++j) c.K[j] = sc + j * arr;
+  c.Y = sc + kMaxStages * arr;
+  c.Y1 = c.Y + arr;
+
+  for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+    c.tile = tile;
+    // ---- load h0 -> Y (T-layout); rows past B are zero
+    if (!c.th.producer) {
+      for (int e = c.th.ctid; e < prm.D * R; e += ncons) {
+        const int r = e / prm.D, d = e - r * prm.D;      // coalesced along d
+        const int l = r / RT, b = tile * RT + (r % RT);
+        float v = 0.f;
+        if (prm.h0 && b < prm.B) v = prm.h0[(static_cast<size_t>(l) * prm.B + b) * prm.D + d];
+        c.Y[static_cast<size_t>(d) * R + r] = v;
+      }
+      if (c.th.ctid < R) rs.status[c.th.ctid] = 0;
+    }
+    __syncthreads();
+    for (int i = 0; i < prm.S; ++i) {
+      solve_interval<RT>(c, i);
+      __syncthreads();
+      jump_and_regress<RT>(c, i);
+      __syncthreads();
+    }
+    // ---- final hidden state and status
+    if (!c.th.producer) {
+      for (int e = c.th.ctid; e < prm.D * R; e += ncons) {
+        const int r = e / prm.D, d = e - r * prm.D;
+        const int l = r / RT, b = tile * RT + (r % RT);
+        if (b < prm.B) prm.hT[(static_cast<size_t>(l) * prm.B + b) * prm.D + d] = c.Y[static_cast<size_t>(d) * R + r];
+      }
+      if (prm.status && c.th.ctid < RT) {
+        const int b = tile * RT + c.th.ctid;
+        int st = 0;
+        for (int l = 0; l < LL; ++l) st = max(st, rs.status[l * RT + c.th.ctid]);
+        if (b < prm.B) prm.status[b] = st;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int RT, int LL>
+static cudaError_t launch_one(const FwdParams& prm, int grid, size_t smem_bytes, cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(odernn_fwd_kernel<RT, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem_bytes));
+  if (err != cudaSuccess) return err;
+  odernn_fwd_kernel<RT, LL><<<grid, 128 * LL + 32, smem_bytes, stream>>>(prm);
+  return cudaGetLastError();
+}
+
+// host-visible launcher (api.cu).  Supported: 8-row tiles for L = 1..4, 16-row tiles for L = 1..2.
+cudaError_t launch_odernn_fwd(const FwdParams& prm, int rows_per_tile, int grid, size_t smem_bytes,
+                              cudaStream_t stream) {
+  if (rows_per_tile == 8) {
+    switch (prm.L) {
+      case 1: return launch_one<8, 1>(prm, grid, smem_bytes, stream);
+      case 2: return launch_one<8, 2>(prm, grid, smem_bytes, stream);
+      case 3: return launch_one<8, 3>(prm, grid, smem_bytes, stream);
+      case 4: return launch_one<8, 4>(prm, grid, smem_bytes, stream);
+    }
+  } else if (rows_per_tile == 16) {
+    switch (prm.L) {
+      case 1: return launch_one<16, 1>(prm, grid, smem_bytes, stream);
+      case 2: return launch_one<16, 2>(prm, grid, smem_bytes, stream);
+    }
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace odevio

@@ -1,0 +1,59 @@
+// Kernel parameter block of the fused ODE-RNN kernels (host <-> device, internal).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace odevio {
+
+constexpr int kMaxStages = 7;
+constexpr int kMaxLinears = 6;
+constexpr int kMaxRnnLayers = 4;
+constexpr int kRegHidden = 128;   // regressor: Linear(D,128) -> LeakyReLU(0.1) -> Linear(128,6)
+constexpr int kPoseDim = 6;
+
+// Explicit Runge-Kutta tableau in fp32 (same numbers as oracle/tableaus.py).
+struct DevTableau {
+  int n_stages;
+  int fsal;       // last stage's vector field is next step's first
+  int ssal;       // y1 is the last stage's argument
+  int has_err;    // embedded error estimate present
+  int has_mid;    // quartic dense output available (else linear)
+  float exponent; // -1 / order
+  float a[kMaxStages][kMaxStages];
+  float b[kMaxStages];
+  float e[kMaxStages];
+  float bmid[kMaxStages];
+};
+
+struct FwdParams {
+  // dims / enums
+  int B, S, D, H, NL, L;     // NL = number of Linear layers of ODEFunc (= n_hidden + 1)
+  int act, rnn_type, adaptive, substeps;
+  // controller
+  float atol, rtol, dt0, safety, fmin, fmax;
+  int accept_strict, floor_factor, endpoint_dense, max_steps;
+  DevTableau tab;
+  // packed weights (K-major [K][N]) and biases
+  const float* Wode[kMaxLinears];
+  const float* bode[kMaxLinears];
+  int Kode[kMaxLinears], Node[kMaxLinears];
+  // rnn (tanh): [0] = [W_ih^T ; W_hh^T] ([2D][D]), bias[0] = b_ih + b_hh
+  // gru:        [0] = r-gate cat ([2D][D]), [1] = z-gate cat, [2] = W_in^T ([D][D]), [3] = W_hn^T
+  const float* Wrnn[kMaxRnnLayers][4];
+  const float* brnn[kMaxRnnLayers][4];
+  const float* Wreg0;  // [D][128] packed
+  const float* breg0;  // [128]
+  const float* Wreg1;  // [6][128]  (PyTorch layout, used directly)
+  const float* breg1;  // [6]
+  // io
+  const float* fv; const float* fi; int Dv;
+  const float* ts; const float* h0;
+  float* pose; float* hT; int* stats; int* status;
+  // per-CTA global scratch (L2 resident), T-layout [D][R] arrays: K[0..6], Y, Y1
+  float* scratch; size_t scratch_floats_per_cta;
+  // launch geometry
+  int ntiles, nst;
+  int bufA_floats, bufB_floats, stage_floats;
+};
+
+}  // namespace odevio

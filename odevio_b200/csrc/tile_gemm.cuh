@@ -1,0 +1,196 @@
+// Streaming tile GEMM used by every fused kernel on the path.
+//
+//   out[r][n] = epilogue( sum_k in[r][k] * W[n][k] )     for the rows of ONE sequence tile
+//
+// * activations live in shared memory in "T-layout": inT[k * ld + r]  (k-major, the tile's rows
+//   contiguous), so one broadcast LDS.128 feeds 4 rows of the thread tile;
+// * weights are pre-packed K-major (Wt[k][n], see prepack.cu) so that KC consecutive k-rows are
+//   ONE contiguous block: a dedicated producer lane streams them L2 -> shared memory with 1-D
+//   bulk TMA (cp.async.bulk, SASS UBLKCP) through an mbarrier full/empty ring;
+// * each consumer thread owns RT rows x P column-pairs (strided by the threads of its row
+//   block) and accumulates in fp32 registers with FFMA, sequentially over k (deterministic).
+//
+// The producer only touches the ring, so it runs ahead of the consumers across GEMM
+// boundaries; control flow is identical for all threads of the CTA.
+#pragma once
+#include "common.cuh"
+
+namespace odevio {
+
+constexpr int KC = 8;           // k-rows per weight stage
+constexpr int MAX_STAGES = 4;
+constexpr int MAX_P = 4;        // column pairs per thread -> N <= 2 * MAX_P * threads_per_row_block
+
+// Ring geometry (uniform, lives in registers / constant bank).
+struct WeightRing {
+  float* buf;            // shared: nst * stage_floats
+  uint32_t buf_off;      // byte offset of buf from the dynamic shared-memory base
+  uint64_t* full;        // [nst] armed by the producer, completed by TMA bytes
+  uint64_t* empty;       // [nst] one arrive per consumer warp
+  uint32_t stage_floats;
+  uint32_t nst;
+};
+
+// Running position in the ring; every thread keeps its own copy, all in lock-step.
+struct RingPos {
+  uint32_t stage;
+  uint32_t phase;
+  __device__ __forceinline__ void advance(uint32_t nst) {
+    if (++stage == nst) { stage = 0; phase ^= 1u; }
+  }
+};
+
+// Identity of a thread inside the CTA (consumers first, producer warp last).
+struct TileThread {
+  int ctid;          // consumer thread id, [0, ncons)
+  int ncons;         // consumer threads (multiple of 32)
+  int lane;
+  bool producer;     // member of the producer warp
+};
+
+// Epilogue description: v = act(acc + bias[n]) stored to up to two T-layout destinations, or the
+// GRU new-gate combination.
+enum { EPI_STORE = 0, EPI_GRU_NEW = 1 };
+struct Epilogue {
+  int mode;
+  const float* bias;   // [N] or nullptr
+  int act;
+  float* out0; int ld0; int off0;   // out0[n * ld0 + off0 + rb * RT + r]   (shared or global)
+  float* out1; int ld1; int off1;   // optional second destination
+  // EPI_GRU_NEW: n = tanh(acc + bias + hn * r);  h' = (hprev - n) * z + n   (ATen gru_cell order)
+  const float* rg; const float* zg; const float* hn; const float* hprev;   // [N][RT]
+};
+
+// One lane of the producer warp: stream Wt[K][N] in KC-row chunks.
+__device__ __forceinline__ void pipe_produce(const WeightRing& ring, RingPos& pos,
+                                             const float* __restrict__ Wt, int K, int N) {
+  const uint32_t bytes = static_cast<uint32_t>(KC) * N * sizeof(float);
+  const int nch = K / KC;
+  for (int ch = 0; ch < nch; ++ch) {
+    mbar_wait(&ring.empty[pos.stage], pos.phase ^ 1u);
+    mbar_arrive_expect_tx(&ring.full[pos.stage], bytes);
+    tma_load_1d(ring.buf + static_cast<size_t>(pos.stage) * ring.stage_floats,
+                Wt + static_cast<size_t>(ch) * KC * N, bytes, &ring.full[pos.stage]);
+    pos.advance(ring.nst);
+  }
+}
+
+template <int RT>
+__device__ __forceinline__ void run_epilogue(const Epilogue& e, int n, int rb, const float (&acc)[RT]) {
+  const float b = e.bias ? e.bias[n] : 0.f;
+  float v[RT];
+  if (e.mode == EPI_STORE) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) v[r] = apply_act(acc[r] + b, e.act);
+  } else {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const size_t o = static_cast<size_t>(n) * RT + r;
+      const float ng = apply_act((acc[r] + b) + e.hn[o] * e.rg[o], ACT_TANH);
+      v[r] = (e.hprev[o] - ng) * e.zg[o] + ng;
+    }
+  }
+  float* p0 = e.out0 + static_cast<size_t>(n) * e.ld0 + e.off0 + rb * RT;
+#pragma unroll
+  for (int q = 0; q < RT / 4; ++q) st4(p0 + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+  if (e.out1) {
+    float* p1 = e.out1 + static_cast<size_t>(n) * e.ld1 + e.off1 + rb * RT;
+#pragma unroll
+    for (int q = 0; q < RT / 4; ++q) st4(p1 + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+  }
+}
+
+// Consumer body, compiled once per (RT, P) and shared by every call site.  Returns the
+// advanced ring position packed as stage | phase << 8.
+// Operands are addressed as offsets from the dynamic shared-memory base so the compiler emits
+// LDS (shared-space) loads in the hot loop instead of generic LD.
+template <int RT, int P>
+__device__ __noinline__ uint32_t gemm_body(WeightRing ring, uint32_t pos_packed, uint32_t in_off,
+                                           int ld, int K, int N, int rb, int cg, int tpb, int lane,
+                                           const Epilogue* __restrict__ epi) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const float* __restrict__ inT = reinterpret_cast<const float*>(smem_raw + in_off);
+  const float* __restrict__ ring_buf = reinterpret_cast<const float*>(smem_raw + ring.buf_off);
+  RingPos pos{pos_packed & 0xffu, pos_packed >> 8};
+  float acc[P][2][RT];
+  int col[P];
+  const int npairs = N >> 1;
+#pragma unroll
+  for (int pp = 0; pp < P; ++pp) {
+    const int q = cg + pp * tpb;
+    col[pp] = 2 * (q < npairs ? q : npairs - 1);   // clamp: surplus slots compute a discarded duplicate
+#pragma unroll
+    for (int r = 0; r < RT; ++r) { acc[pp][0][r] = 0.f; acc[pp][1][r] = 0.f; }
+  }
+  const int nch = K / KC;
+  for (int ch = 0; ch < nch; ++ch) {
+    mbar_wait(&ring.full[pos.stage], pos.phase);
+    const float* __restrict__ ws = ring_buf + pos.stage * ring.stage_floats;
+    const float* __restrict__ xp = inT + ch * KC * ld;
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      float x[RT];
+#pragma unroll
+      for (int q = 0; q < RT / 4; ++q) {
+        const float4 v = ld4(xp + kk * ld + 4 * q);
+        x[4 * q + 0] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int pp = 0; pp < P; ++pp) {
+        const float2 w = *reinterpret_cast<const float2*>(ws + kk * N + col[pp]);
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          acc[pp][0][r] = fmaf(x[r], w.x, acc[pp][0][r]);
+          acc[pp][1][r] = fmaf(x[r], w.y, acc[pp][1][r]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ring.empty[pos.stage]);
+    pos.advance(ring.nst);
+  }
+  const Epilogue e = *epi;
+#pragma unroll
+  for (int pp = 0; pp < P; ++pp) {
+    const int q = cg + pp * tpb;
+    if (q < npairs) {
+      run_epilogue<RT>(e, 2 * q, rb, acc[pp][0]);
+      run_epilogue<RT>(e, 2 * q + 1, rb, acc[pp][1]);
+    }
+  }
+  return pos.stage | (pos.phase << 8);
+}
+
+// All threads of the CTA call this with identical arguments.
+//   Wt: packed [K][N] (K % KC == 0, N even, N <= 2*MAX_P*tpb), inT: shared T-layout, nrb row
+//   blocks of RT rows (row block rb starts at inT + rb*RT), ncons % nrb == 0.
+// Ends with a consumer-wide named barrier so the epilogue's stores are visible to the next phase.
+template <int RT>
+__device__ __forceinline__ void tile_gemm(const WeightRing& ring, RingPos& pos, const TileThread& th,
+                                          const float* __restrict__ Wt, int K, int N,
+                                          const float* inT, int ld, int nrb, const Epilogue& epi) {
+  if (th.producer) {
+    if (th.lane == 0) pipe_produce(ring, pos, Wt, K, N);
+    __syncwarp();
+    return;
+  }
+  const int tpb = th.ncons / nrb;
+  const int rb = th.ctid / tpb;
+  const int cg = th.ctid - rb * tpb;
+  const int P = ((N >> 1) + tpb - 1) / tpb;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t in_rb = static_cast<uint32_t>(reinterpret_cast<const unsigned char*>(inT + rb * RT) - smem_raw);
+  const uint32_t pk = pos.stage | (pos.phase << 8);
+  uint32_t nk;
+  switch (P) {
+    case 1: nk = gemm_body<RT, 1>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
+    case 2: nk = gemm_body<RT, 2>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
+    case 3: nk = gemm_body<RT, 3>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
+    default: nk = gemm_body<RT, 4>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
+  }
+  pos.stage = nk & 0xffu;
+  pos.phase = nk >> 8;
+  named_bar_sync(1, th.ncons);
+}
+
+}  // namespace odevio

@@ -1,0 +1,277 @@
+"""Host-side mirror of the reference's regressor interfaces for the latent-dynamics path.
+
+Same constructor namespace (``opt``), ``forward`` signatures, attribute names and state_dict
+keys as the reference, so ``DeepVIO.forward`` (reference src/models/DeepVIO.py:61-68) is a
+drop-in and reference checkpoints load:
+
+  * :class:`ODEFunc`      -- reference src/models/ODEFunc.py:5-39
+  * :class:`CDEFunc`      -- reference src/models/ODEFunc.py:44-84
+  * :class:`FusionModule` -- reference src/models/FusionModule.py:8-29
+  * :class:`PoseODERNN`   -- reference src/models/PoseODERNN.py:39-154
+
+The modules only *hold* parameters (ordinary ``nn.Parameter``) and pack pointers; all of the
+path's arithmetic runs in the sm_100a kernels behind the C ABI (``include/odevio.h``).  There
+is no eager/PyTorch/CPU fallback: without the CUDA library or on CPU tensors, ``forward`` raises.
+
+Optional ``opt`` attributes beyond the reference's argparse namespace (reference values are the
+defaults; ``getattr(opt, name, default)``):
+  ode_atol=1e-6, ode_rtol=1e-2, ode_dt0=1e-4   (hard-coded at PoseODERNN.py:57,72)
+  ode_substeps=1        steps per interval for the fixed-step solvers {"rk4", "rk4_38"}
+  ode_max_steps=100000  per-interval guard (rows still running get status MAX_STEPS)
+  ode_accept_strict=True, ode_floor_factor=False, ode_endpoint="dense"   (SURVEY.md A.1 switches)
+  ode_rows_per_tile=0   (auto) | 8 | 16
+"""
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+_ACTS = {"tanh": nn.Tanh, "relu": nn.ReLU, "leaky_relu": nn.LeakyReLU, "softplus": nn.Softplus}
+
+
+def _activation(name):
+    if name not in _ACTS:
+        raise ValueError(f"Activation function {name} not supported")     # ODEFunc.py:33-34
+    return _ACTS[name]()
+
+
+def _vector_field_net(sizes, activation):
+    layers = []
+    last = len(sizes) - 2
+    for i in range(len(sizes) - 1):
+        lin = nn.Linear(sizes[i], sizes[i + 1])
+        nn.init.normal_(lin.weight, mean=0.0, std=0.1)                      # ODEFunc.py:18-21
+        nn.init.zeros_(lin.bias)
+        layers += [lin, nn.Tanh() if i == last else _activation(activation)]
+    return nn.Sequential(*layers)
+
+
+class ODEFunc(nn.Module):
+    """Parameter container for the autonomous vector field
+    f(t, x) = tanh(W_n a(... a(W_0 x + b_0) ...) + b_n)  (keys ``net.{0,2,..}.{weight,bias}``)."""
+
+    def __init__(self, feature_dim, hidden_dim, num_hidden_layers=3, activation="tanh"):
+        super().__init__()
+        self.feature_dim, self.hidden_dim = feature_dim, hidden_dim
+        self.num_hidden_layers, self.activation = num_hidden_layers, activation
+        self.net = _vector_field_net([feature_dim] + [hidden_dim] * num_hidden_layers + [feature_dim],
+                                     activation)
+
+    def linears(self):
+        return [m for m in self.net if isinstance(m, nn.Linear)]
+
+    def forward(self, t, x):
+        # Single evaluations are not on the fused path (the solver kernels read the weights
+        # directly); kept for interface compatibility with callers that probe the field.
+        return self.net(x)
+
+
+class CDEFunc(nn.Module):
+    """Parameter container for g(t, z) = tanh(MLP(z)).view(B, hidden, channels)."""
+
+    def __init__(self, feature_dim, hidden_dim, num_hidden_layers=3, activation="tanh"):
+        super().__init__()
+        self.hidden_dim, self.feature_dim = hidden_dim, feature_dim
+        self.num_hidden_layers, self.activation = num_hidden_layers, activation
+        self.net = _vector_field_net([hidden_dim] * (num_hidden_layers + 1) + [hidden_dim * feature_dim],
+                                     activation)
+
+    def linears(self):
+        return [m for m in self.net if isinstance(m, nn.Linear)]
+
+    def forward(self, t, z):
+        return self.net(z).view(z.size(0), self.hidden_dim, self.feature_dim)
+
+
+class FusionModule(nn.Module):
+    """cat / soft / hard fusion (FusionModule.py:17-29).  "cat" is folded into the kernel's
+    feature load (no concatenated tensor is materialised); "soft"/"hard" are one Linear upstream
+    of the path and stay in PyTorch."""
+
+    def __init__(self, feature_dim, fuse_method):
+        super().__init__()
+        self.fuse_method, self.f_len = fuse_method, feature_dim
+        if fuse_method == "soft":
+            self.net = nn.Sequential(nn.Linear(feature_dim, feature_dim))
+        elif fuse_method == "hard":
+            self.net = nn.Sequential(nn.Linear(feature_dim, 2 * feature_dim))
+
+    def forward(self, v, i):
+        cat = torch.cat((v, i), -1)
+        if self.fuse_method == "cat":
+            return cat
+        if self.fuse_method == "soft":
+            return cat * self.net(cat)
+        if self.fuse_method == "hard":
+            w = self.net(cat).view(v.shape[0], v.shape[1], self.f_len, 2)
+            return cat * F.gumbel_softmax(w, tau=1, hard=True, dim=-1)[:, :, :, 0]
+        raise ValueError(f"fuse method {self.fuse_method} not supported")
+
+
+def _f32c(t, name):
+    if t.dtype != torch.float32:
+        raise _lib.OdevioError(f"{name} must be float32 (the path computes in fp32), got {t.dtype}")
+    return t.contiguous()
+
+
+class PoseODERNN(nn.Module):
+    """ODE-RNN pose regressor; ``forward`` launches the fused sm_100a kernel
+    (``odevio_odernn_forward``)."""
+
+    SOLVERS = ("dopri5", "heun", "tsit5", "euler", "rk4", "rk4_38")
+
+    def __init__(self, opt):
+        super().__init__()
+        self.f_len = opt.v_f_len + opt.i_f_len
+        self.rnn_hidden_dim = getattr(opt, "rnn_hidden_dim", self.f_len)    # unused, as in the reference
+        self.rnn_num_layers = opt.rnn_num_layers
+        self.fuse_method = opt.fuse_method
+        self.ode_func = ODEFunc(feature_dim=self.f_len, hidden_dim=opt.ode_hidden_dim,
+                                num_hidden_layers=opt.ode_fn_num_layers,
+                                activation=opt.ode_activation_fn)
+        self.ode_solver = self._set_solver(opt.ode_solver)
+        self.rnn_type = opt.ode_rnn_type
+        self.rnn = self._set_rnn(opt.ode_rnn_type)
+        self.rnn_drop_out = nn.Dropout(getattr(opt, "rnn_dropout_out", 0.0))   # constructed, never applied
+        self.fuse = FusionModule(feature_dim=self.f_len, fuse_method=self.fuse_method)
+        self.regressor = nn.Sequential(nn.Linear(self.f_len, 128), nn.LeakyReLU(0.1, inplace=True),
+                                       nn.Linear(128, 6))
+        # solver knobs (reference values hard-coded at PoseODERNN.py:57,72)
+        self.atol = float(getattr(opt, "ode_atol", 1e-6))
+        self.rtol = float(getattr(opt, "ode_rtol", 1e-2))
+        self.dt0 = float(getattr(opt, "ode_dt0", 1e-4))
+        self.substeps = int(getattr(opt, "ode_substeps", 1))
+        self.max_steps = int(getattr(opt, "ode_max_steps", 100000))
+        self.accept_strict = bool(getattr(opt, "ode_accept_strict", True))
+        self.floor_factor = bool(getattr(opt, "ode_floor_factor", False))
+        self.endpoint = getattr(opt, "ode_endpoint", "dense")
+        self.rows_per_tile = int(getattr(opt, "ode_rows_per_tile", 0))
+        self.collect_stats = bool(getattr(opt, "ode_collect_stats", True))
+        self.last_stats = None      # int32 [S, L, B, 2] = (n_steps, n_accepted) of the last forward
+        self.last_status = None     # int32 [B]
+
+    # -- reference menu (PoseODERNN.py:125-148) ------------------------------------------
+    def _set_solver(self, ode_solver):
+        if ode_solver not in self.SOLVERS:
+            raise ValueError(f"Solver {ode_solver} not supported")
+        return ode_solver
+
+    def _set_rnn(self, rnn_type):
+        if rnn_type == "rnn":
+            return nn.RNN(input_size=self.f_len, hidden_size=self.f_len, num_layers=self.rnn_num_layers,
+                          batch_first=True)
+        if rnn_type == "gru":
+            return nn.GRU(input_size=self.f_len, hidden_size=self.f_len, num_layers=self.rnn_num_layers,
+                          batch_first=True)
+        raise ValueError(f"RNN type {rnn_type} not supported")
+
+    def get_regressor_params(self):
+        return self.regressor.parameters()
+
+    def get_other_params(self):
+        return [p for n, p in self.named_parameters() if not n.startswith("regressor")]
+
+    # -- C-ABI plumbing -------------------------------------------------------------------
+    def _cfg(self, B, S):
+        cfg = _lib.default_odernn_cfg()
+        cfg.B, cfg.S, cfg.D, cfg.H = B, S, self.f_len, self.ode_func.hidden_dim
+        cfg.n_hidden, cfg.L = self.ode_func.num_hidden_layers, self.rnn_num_layers
+        cfg.activation = _lib.ACT[self.ode_func.activation]
+        cfg.rnn_type = _lib.RNN[self.rnn_type]
+        cfg.solver = _lib.SOLVER[self.ode_solver]
+        cfg.substeps = self.substeps
+        cfg.atol, cfg.rtol, cfg.dt0 = self.atol, self.rtol, self.dt0
+        cfg.accept_strict = int(self.accept_strict)
+        cfg.floor_factor = int(self.floor_factor)
+        cfg.endpoint_dense = int(self.endpoint == "dense")
+        cfg.max_steps = self.max_steps
+        cfg.rows_per_tile = self.rows_per_tile
+        return cfg
+
+    def _weights(self):
+        w = _lib.OdeRnnWeights()
+        keep = []
+
+        def ptr(p, name):
+            t = _f32c(p.detach(), name)
+            keep.append(t)
+            return _lib.dptr(t, name)
+
+        for j, lin in enumerate(self.ode_func.linears()):
+            w.ode_w[j] = ptr(lin.weight, f"ode_func.net.{2 * j}.weight")
+            w.ode_b[j] = ptr(lin.bias, f"ode_func.net.{2 * j}.bias")
+        for l in range(self.rnn_num_layers):
+            w.rnn_w_ih[l] = ptr(getattr(self.rnn, f"weight_ih_l{l}"), f"rnn.weight_ih_l{l}")
+            w.rnn_w_hh[l] = ptr(getattr(self.rnn, f"weight_hh_l{l}"), f"rnn.weight_hh_l{l}")
+            w.rnn_b_ih[l] = ptr(getattr(self.rnn, f"bias_ih_l{l}"), f"rnn.bias_ih_l{l}")
+            w.rnn_b_hh[l] = ptr(getattr(self.rnn, f"bias_hh_l{l}"), f"rnn.bias_hh_l{l}")
+        w.reg_w0 = ptr(self.regressor[0].weight, "regressor.0.weight")
+        w.reg_b0 = ptr(self.regressor[0].bias, "regressor.0.bias")
+        w.reg_w1 = ptr(self.regressor[2].weight, "regressor.2.weight")
+        w.reg_b1 = ptr(self.regressor[2].bias, "regressor.2.bias")
+        return w, keep
+
+    def forward(self, fv, fi, ts, prev=None, do_profile=False):
+        lib = _lib.load()
+        if not fv.is_cuda:
+            raise _lib.OdevioError("PoseODERNN.forward needs CUDA tensors: odevio_b200 has no CPU path")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training goes through the autograd wrapper once the fused backward is built
+            from .autograd import odernn_apply
+            return odernn_apply(self, fv, fi, ts, prev)
+        return self._forward_impl(fv, fi, ts, prev, do_profile)
+
+    @torch.no_grad()
+    def _forward_impl(self, fv, fi, ts, prev=None, do_profile=False):
+        lib = _lib.load()
+        B, S = fv.shape[0], fv.shape[1]
+        dev = fv.device
+        if self.fuse_method == "cat":
+            fvc, fic, Dv = _f32c(fv, "fv"), _f32c(fi, "fi"), fv.shape[2]     # concat happens in-kernel
+        else:
+            fvc, fic, Dv = _f32c(self.fuse(fv, fi), "fused"), None, self.f_len
+        ts = _f32c(ts, "ts")
+        ts_in = (ts - ts[:, :1]) if prev is None else ts                       # PoseODERNN.py:100
+        ts_in = ts_in.contiguous()
+        h0 = None if prev is None else _f32c(prev, "prev")
+        if h0 is not None and tuple(h0.shape) != (self.rnn_num_layers, B, self.f_len):
+            raise _lib.OdevioError(f"prev must be [L,B,D]={self.rnn_num_layers, B, self.f_len}, got {tuple(h0.shape)}")
+        cfg = self._cfg(B, S)
+        nbytes = lib.odevio_odernn_workspace_bytes(C.byref(cfg))
+        if nbytes == 0:
+            raise _lib.OdevioError("unsupported PoseODERNN configuration for the fused kernel "
+                                   f"(D={cfg.D}, H={cfg.H}, L={cfg.L}, n={cfg.n_hidden})")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        pose = torch.empty(B, S, 6, dtype=torch.float32, device=dev)
+        hT = torch.empty(self.rnn_num_layers, B, self.f_len, dtype=torch.float32, device=dev)
+        stats = (torch.zeros(S, self.rnn_num_layers, B, 2, dtype=torch.int32, device=dev)
+                 if self.collect_stats else None)
+        status = torch.zeros(B, dtype=torch.int32, device=dev)
+        w, keep = self._weights()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if do_profile:
+            torch.cuda.nvtx.range_push("odeint")                               # PoseODERNN.py:103-104
+        with torch.cuda.device(dev):
+            rc = lib.odevio_odernn_forward(
+                C.byref(cfg), C.byref(w), _lib.dptr(fvc, "fv"), _lib.dptr(fic, "fi"), Dv,
+                _lib.dptr(ts_in, "ts"), _lib.dptr(h0, "prev"), _lib.dptr(pose), _lib.dptr(hT),
+                _lib.dptr(stats), _lib.dptr(status), _lib.dptr(ws), nbytes, C.c_void_p(stream))
+        if do_profile:
+            torch.cuda.nvtx.range_pop()
+        _lib.check(rc)
+        del keep
+        self.last_stats, self.last_status = stats, status
+        return pose, hT
+
+    def check_status(self):
+        """Synchronising check of the last forward's per-row solver status."""
+        if self.last_status is None:
+            return
+        bad = int(self.last_status.max().item())
+        if bad != 0:
+            what = {1: "max_steps reached", 2: "non-finite error norm"}.get(bad, str(bad))
+            raise RuntimeError(f"ODE solve failed for some rows: {what}")
