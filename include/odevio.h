@@ -92,12 +92,17 @@ typedef struct odevio_odernn_cfg {
   float factor_max;     /* 10.0 */
   int32_t accept_strict;      /* 1: accept iff ratio < 1 (torchode); 0: <= 1 */
   int32_t floor_factor;       /* 1: factor >= 1 after an accepted step (torchdiffeq rule) */
-  int32_t endpoint_dense;     /* 1: end point from the step's dense output (torchode); 0: y1 */
+  int32_t endpoint_dense;     /* 1: end point = the step's fp32 quartic dense output at x=1 (literal
+                                 torchode); 0: y1, its exact-arithmetic value (default) */
   int32_t max_steps;          /* per-interval guard; rows still running get STATUS_MAX_STEPS */
   int32_t precision;          /* ODEVIO_PRECISION_* */
   int32_t save_checkpoints;   /* 1: record what odevio_odernn_backward needs in `ckpt` */
-  int32_t rows_per_tile;      /* 0 = auto; else 8 or 16 sequences per CTA */
-  int32_t reserved[7];
+  int32_t rows_per_tile;      /* 0 = auto; else 4, 8 or 16 sequences per CTA */
+  int32_t exact_landing;      /* 1 (default): a step clamped to the remaining interval ends exactly at
+                                 t_end; 0: literal fp32 t + (t_end - t), may need a 1-ulp extra step */
+  int32_t trace_steps;        /* T >= 0: additionally record (dt, error ratio) of the first T steps of
+                                 every solve; the stats row then has 2 + 2*T int32 (floats as bits) */
+  int32_t reserved[5];
 } odevio_odernn_cfg;
 
 /* PyTorch-layout parameters ([out, in] row-major), exactly the reference's state_dict tensors */
@@ -134,7 +139,8 @@ ODEVIO_API size_t odevio_odernn_workspace_bytes(const odevio_odernn_cfg* cfg);
  *                                  has already applied `ts - ts[:, :1]` when prev is None)
  *   h0   [L,B,D] or NULL (zeros)
  *   pose [B,S,6]  hT [L,B,D]       outputs
- *   stats  [S,L,B,2] int32 or NULL: (n_steps, n_accepted) per interval / layer / row
+ *   stats  [S,L,B,2+2T] int32 or NULL: (n_steps, n_accepted, then T x (dt, ratio) as float bits,
+ *                                  T = cfg->trace_steps) per interval / layer / row; zero-fill it
  *   status [B] int32 or NULL:       worst ODEVIO_STATUS_* seen by the row
  *   workspace: >= odevio_odernn_workspace_bytes(cfg), 256-byte aligned
  */

@@ -29,7 +29,8 @@ class OdeRnnCfg(C.Structure):
         ("safety", C.c_float), ("factor_min", C.c_float), ("factor_max", C.c_float),
         ("accept_strict", C.c_int32), ("floor_factor", C.c_int32), ("endpoint_dense", C.c_int32),
         ("max_steps", C.c_int32), ("precision", C.c_int32), ("save_checkpoints", C.c_int32),
-        ("rows_per_tile", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("rows_per_tile", C.c_int32), ("exact_landing", C.c_int32), ("trace_steps", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 

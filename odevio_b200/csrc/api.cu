@@ -127,28 +127,13 @@ int plan_odernn(const odevio_odernn_cfg& c, OdePlan& pl) {
   if (c.rnn_type != ODEVIO_RNN_TANH && c.rnn_type != ODEVIO_RNN_GRU) return ODEVIO_E_ENUM;
   if (c.solver < 0 || c.solver > ODEVIO_SOLVER_RK4_38) return ODEVIO_E_ENUM;
   if (c.precision != ODEVIO_PRECISION_FP32) return ODEVIO_E_ENUM;
-  if (c.rows_per_tile != 0 && c.rows_per_tile != 8 && c.rows_per_tile != 16) return ODEVIO_E_SHAPE;
+  if (c.rows_per_tile != 0 && c.rows_per_tile != 4 && c.rows_per_tile != 8 && c.rows_per_tile != 16) return ODEVIO_E_SHAPE;
   const bool fixed = c.solver == ODEVIO_SOLVER_RK4 || c.solver == ODEVIO_SOLVER_RK4_38;
   if (fixed && c.substeps < 1) return ODEVIO_E_SHAPE;
   if (!fixed && c.max_steps < 1) return ODEVIO_E_SHAPE;
+  if (c.trace_steps < 0 || c.trace_steps > 64) return ODEVIO_E_SHAPE;
 
   const int nsm = sm_count();
-  int rt = c.rows_per_tile;
-  if (rt == 0) {
-    // pick the tile height that minimises waves x relative tile cost (16-row tiles amortise the
-    // weight stream better: ~1.6x the time of an 8-row tile for 2x the rows)
-    const long w8 = ((c.B + 7) / 8 + nsm - 1) / nsm, w16 = ((c.B + 15) / 16 + nsm - 1) / nsm;
-    rt = (c.L <= 2 && w16 * 16 < w8 * 10) ? 16 : 8;
-  }
-  if (rt == 16 && c.L > 2) return ODEVIO_E_SHAPE;
-  pl.RT = rt;
-  pl.R = rt * c.L;
-  pl.ncons = 128 * c.L;
-  pl.threads = pl.ncons + 32;
-  pl.ntiles = (c.B + rt - 1) / rt;
-  pl.grid = pl.ntiles < nsm ? pl.ntiles : nsm;
-  pl.G = c.rnn_type == ODEVIO_RNN_GRU ? 3 : 1;
-
   const int NL = c.n_hidden + 1;
   int nmax = kRegHidden;
   for (int j = 0; j < NL; ++j) {
@@ -159,20 +144,45 @@ int plan_odernn(const odevio_odernn_cfg& c, OdePlan& pl) {
   if (c.D > nmax) nmax = c.D;
   // column pairs per thread <= 4: ODE GEMMs use 128 threads per row block, the jump all consumers
   if (nmax > 2 * 4 * 128) return ODEVIO_E_SHAPE;
-
-  const size_t maxdh = static_cast<size_t>(c.D > c.H ? c.D : c.H);
-  size_t a = maxdh * pl.R, a2 = static_cast<size_t>(2) * c.D * rt;
-  pl.bufA_floats = a > a2 ? a : a2;
-  size_t b = static_cast<size_t>(c.H) * pl.R, b2 = static_cast<size_t>(c.D) * rt;
-  pl.bufB_floats = b > b2 ? b : b2;
+  pl.ncons = 128 * c.L;
+  pl.threads = pl.ncons + 32;
+  pl.G = c.rnn_type == ODEVIO_RNN_GRU ? 3 : 1;
   pl.stage_floats = static_cast<size_t>(kStageK) * nmax;
-  const size_t fixed_bytes = (pl.bufA_floats + pl.bufB_floats + 4 * static_cast<size_t>(pl.ncons) +
-                              14 * static_cast<size_t>(pl.R)) * sizeof(float) + 8 + 2 * kMaxStagesRing * 8 + 128;
-  if (fixed_bytes + 2 * pl.stage_floats * sizeof(float) > kSmemLimit) return ODEVIO_E_SHAPE;
-  size_t nst = (kSmemLimit - fixed_bytes) / (pl.stage_floats * sizeof(float));
-  if (nst > kMaxStagesRing) nst = kMaxStagesRing;
-  pl.nst = static_cast<int>(nst);
-  pl.smem_bytes = fixed_bytes + nst * pl.stage_floats * sizeof(float);
+
+  // shared-memory carve-up for a tile of rt sequences (mirrors odernn_fwd_kernel); false if it
+  // cannot hold at least two weight stages
+  auto fit = [&](int rt) -> bool {
+    const int R = rt * c.L;
+    const size_t maxdh = static_cast<size_t>(c.D > c.H ? c.D : c.H);
+    size_t a = maxdh * R, a2 = static_cast<size_t>(2) * c.D * rt;
+    pl.bufA_floats = a > a2 ? a : a2;
+    size_t b = static_cast<size_t>(c.H) * R, b2 = static_cast<size_t>(c.D) * rt;
+    pl.bufB_floats = b > b2 ? b : b2;
+    const size_t fixed_bytes = (pl.bufA_floats + pl.bufB_floats + 4 * static_cast<size_t>(pl.ncons) +
+                                14 * static_cast<size_t>(R)) * sizeof(float) + 8 + 2 * kMaxStagesRing * 8 + 128;
+    if (fixed_bytes + 2 * pl.stage_floats * sizeof(float) > kSmemLimit) return false;
+    size_t nst = (kSmemLimit - fixed_bytes) / (pl.stage_floats * sizeof(float));
+    if (nst > kMaxStagesRing) nst = kMaxStagesRing;
+    pl.nst = static_cast<int>(nst);
+    pl.smem_bytes = fixed_bytes + nst * pl.stage_floats * sizeof(float);
+    return true;
+  };
+  int rt = c.rows_per_tile;
+  if (rt == 0) {
+    // Tile height: 16-row tiles amortise the weight stream better (~1.6x the time of an 8-row
+    // tile for 2x the rows) but halve the CTA count and need <= 3 column pairs per thread to
+    // stay in registers; fall back to smaller tiles when shared memory does not fit.
+    const long w8 = ((c.B + 7) / 8 + nsm - 1) / nsm, w16 = ((c.B + 15) / 16 + nsm - 1) / nsm;
+    if (c.L <= 2 && nmax <= 768 && w16 * 16 < w8 * 10 && fit(16)) rt = 16;
+    else if (fit(8)) rt = 8;
+    else rt = 4;
+  }
+  if (rt == 16 && c.L > 2) return ODEVIO_E_SHAPE;
+  if (!fit(rt)) return ODEVIO_E_SHAPE;
+  pl.RT = rt;
+  pl.R = rt * c.L;
+  pl.ntiles = (c.B + rt - 1) / rt;
+  pl.grid = pl.ntiles < nsm ? pl.ntiles : nsm;
 
   // ---- workspace layout (floats), every block 64-float (256 B) aligned
   size_t off = 0;
@@ -230,7 +240,7 @@ void odevio_odernn_default_cfg(odevio_odernn_cfg* cfg) {
   cfg->substeps = 1;
   cfg->atol = 1e-6f; cfg->rtol = 1e-2f; cfg->dt0 = 1e-4f;
   cfg->safety = 0.9f; cfg->factor_min = 0.2f; cfg->factor_max = 10.0f;
-  cfg->accept_strict = 1; cfg->floor_factor = 0; cfg->endpoint_dense = 1;
+  cfg->accept_strict = 1; cfg->floor_factor = 0; cfg->endpoint_dense = 0; cfg->exact_landing = 1;
   cfg->max_steps = 100000;
   cfg->precision = ODEVIO_PRECISION_FP32;
 }
@@ -272,7 +282,7 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
   p.substeps = c.substeps;
   p.atol = c.atol; p.rtol = c.rtol; p.dt0 = c.dt0; p.safety = c.safety; p.fmin = c.factor_min; p.fmax = c.factor_max;
   p.accept_strict = c.accept_strict; p.floor_factor = c.floor_factor; p.endpoint_dense = c.endpoint_dense;
-  p.max_steps = c.max_steps;
+  p.max_steps = c.max_steps; p.exact_landing = c.exact_landing; p.trace_steps = c.trace_steps;
   if (!make_tableau(c.solver, p.tab)) return ODEVIO_E_ENUM;
 
   // ---- pre-pack weights into the workspace

@@ -146,7 +146,7 @@ __device__ __forceinline__ void error_pass(Ctx<RT>& c) {
 
 // Per-row step-size controller + bookkeeping (thread ctid == row).  Returns "row still running".
 template <int RT>
-__device__ __forceinline__ int controller(Ctx<RT>& c, int loops) {
+__device__ __forceinline__ int controller(Ctx<RT>& c, int loops, int interval) {
   if (c.th.producer || c.th.ctid >= c.R) return 0;
   const FwdParams& p = *c.prm;
   const int r = c.th.ctid;
@@ -157,6 +157,7 @@ __device__ __forceinline__ int controller(Ctx<RT>& c, int loops) {
   const float tend = rs.tend[r];
   bool accept = true, finite = true;
   float dt_next = dt;
+  float ratio_out = 0.f;
   if (p.tab.has_err) {
     // deterministic reduction of the partial sums of this row's quad, in thread order
     const int rq = r >> 2, j = r & 3;
@@ -164,16 +165,26 @@ __device__ __forceinline__ int controller(Ctx<RT>& c, int loops) {
     for (int k = rq; k < c.th.ncons; k += c.rq4) total = add_(total, c.partial[4 * k + j]);
     const float ratio = sqrtf(__fdiv_rn(total, static_cast<float>(p.D)));
     finite = isfinite(ratio);
+    ratio_out = ratio;
     accept = p.accept_strict ? (ratio < 1.0f) : (ratio <= 1.0f);
     float factor = mul_(p.safety, powf(ratio, p.tab.exponent));
     factor = fminf(fmaxf(factor, p.fmin), p.fmax);
     if (p.floor_factor && accept) factor = fmaxf(factor, 1.0f);
     dt_next = mul_(dt, factor);
   }
+  if (p.stats && loops <= p.trace_steps && run) {      // diagnostic trace of the first T steps
+    const int b = c.tile * RT + (r % RT);
+    if (b < p.B) {
+      int* sp = p.stats + ((static_cast<size_t>(interval) * p.L + r / RT) * p.B + b) * (2 + 2 * p.trace_steps);
+      sp[2 + 2 * (loops - 1)] = __float_as_int(dt);
+      sp[3 + 2 * (loops - 1)] = __float_as_int(ratio_out);
+    }
+  }
   const int upd = (accept && run) ? 1 : 0;
   rs.nsteps[r] += run;
   rs.nacc[r] += upd;
-  const float t_new = upd ? add_(t, dt) : t;
+  const bool lands = p.exact_landing && dt >= sub_(tend, t);
+  const float t_new = upd ? (lands ? tend : add_(t, dt)) : t;
   const int toeval = (upd && t_new >= tend && rs.noteval[r]) ? 1 : 0;
   if (toeval) {
     rs.x[r] = __fdiv_rn(sub_(tend, t), dt);
@@ -322,7 +333,7 @@ __device__ __forceinline__ void solve_interval(Ctx<RT>& c, int i) {
     have_k0 = true;
     if (p.adaptive) {
       error_pass<RT>(c);
-      run = controller<RT>(c, loops);
+      run = controller<RT>(c, loops, i);
       any_running = __syncthreads_or(run);
       commit_pass<RT>(c);
     } else {
@@ -337,7 +348,7 @@ __device__ __forceinline__ void solve_interval(Ctx<RT>& c, int i) {
     const int l = r / RT, b = c.tile * RT + (r % RT);
     if (b < p.B) {
       if (p.stats) {
-        int* sp = p.stats + ((static_cast<size_t>(i) * p.L + l) * p.B + b) * 2;
+        int* sp = p.stats + ((static_cast<size_t>(i) * p.L + l) * p.B + b) * (2 + 2 * p.trace_steps);
         sp[0] = rs.nsteps[r]; sp[1] = rs.nacc[r];
       }
     }
@@ -526,10 +537,17 @@ static cudaError_t launch_one(const FwdParams& prm, int grid, size_t smem_bytes,
   return cudaGetLastError();
 }
 
-// host-visible launcher (api.cu).  Supported: 8-row tiles for L = 1..4, 16-row tiles for L = 1..2.
+// host-visible launcher (api.cu).  Supported: 4- and 8-row tiles for L = 1..4, 16-row tiles for L = 1..2.
 cudaError_t launch_odernn_fwd(const FwdParams& prm, int rows_per_tile, int grid, size_t smem_bytes,
                               cudaStream_t stream) {
-  if (rows_per_tile == 8) {
+  if (rows_per_tile == 4) {
+    switch (prm.L) {
+      case 1: return launch_one<4, 1>(prm, grid, smem_bytes, stream);
+      case 2: return launch_one<4, 2>(prm, grid, smem_bytes, stream);
+      case 3: return launch_one<4, 3>(prm, grid, smem_bytes, stream);
+      case 4: return launch_one<4, 4>(prm, grid, smem_bytes, stream);
+    }
+  } else if (rows_per_tile == 8) {
     switch (prm.L) {
       case 1: return launch_one<8, 1>(prm, grid, smem_bytes, stream);
       case 2: return launch_one<8, 2>(prm, grid, smem_bytes, stream);

@@ -31,7 +31,7 @@ struct FwdParams {
   int act, rnn_type, adaptive, substeps;
   // controller
   float atol, rtol, dt0, safety, fmin, fmax;
-  int accept_strict, floor_factor, endpoint_dense, max_steps;
+  int accept_strict, floor_factor, endpoint_dense, max_steps, exact_landing, trace_steps;
   DevTableau tab;
   // packed weights (K-major [K][N]) and biases
   const float* Wode[kMaxLinears];

@@ -18,8 +18,10 @@ defaults; ``getattr(opt, name, default)``):
   ode_atol=1e-6, ode_rtol=1e-2, ode_dt0=1e-4   (hard-coded at PoseODERNN.py:57,72)
   ode_substeps=1        steps per interval for the fixed-step solvers {"rk4", "rk4_38"}
   ode_max_steps=100000  per-interval guard (rows still running get status MAX_STEPS)
-  ode_accept_strict=True, ode_floor_factor=False, ode_endpoint="dense"   (SURVEY.md A.1 switches)
-  ode_rows_per_tile=0   (auto) | 8 | 16
+  ode_accept_strict=True, ode_floor_factor=False                         (SURVEY.md A.1 switches)
+  ode_endpoint="y1" | "dense", ode_exact_landing=True   ("dense"/False = literal fp32 torchode
+                        arithmetic, which is ill-conditioned; see oracle/torchode_like.py)
+  ode_rows_per_tile=0   (auto) | 4 | 8 | 16
 """
 
 import ctypes as C
@@ -148,10 +150,13 @@ class PoseODERNN(nn.Module):
         self.max_steps = int(getattr(opt, "ode_max_steps", 100000))
         self.accept_strict = bool(getattr(opt, "ode_accept_strict", True))
         self.floor_factor = bool(getattr(opt, "ode_floor_factor", False))
-        self.endpoint = getattr(opt, "ode_endpoint", "dense")
+        self.endpoint = getattr(opt, "ode_endpoint", "y1")
+        self.exact_landing = bool(getattr(opt, "ode_exact_landing", True))
         self.rows_per_tile = int(getattr(opt, "ode_rows_per_tile", 0))
         self.collect_stats = bool(getattr(opt, "ode_collect_stats", True))
+        self.trace_steps = int(getattr(opt, "ode_trace_steps", 0))   # diagnostic: (dt, ratio) of first T steps
         self.last_stats = None      # int32 [S, L, B, 2] = (n_steps, n_accepted) of the last forward
+        self.last_trace = None      # float32 [S, L, B, T, 2] = (dt, error ratio) when trace_steps = T > 0
         self.last_status = None     # int32 [B]
 
     # -- reference menu (PoseODERNN.py:125-148) ------------------------------------------
@@ -188,8 +193,10 @@ class PoseODERNN(nn.Module):
         cfg.accept_strict = int(self.accept_strict)
         cfg.floor_factor = int(self.floor_factor)
         cfg.endpoint_dense = int(self.endpoint == "dense")
+        cfg.exact_landing = int(self.exact_landing)
         cfg.max_steps = self.max_steps
         cfg.rows_per_tile = self.rows_per_tile
+        cfg.trace_steps = self.trace_steps
         return cfg
 
     def _weights(self):
@@ -248,8 +255,9 @@ class PoseODERNN(nn.Module):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         pose = torch.empty(B, S, 6, dtype=torch.float32, device=dev)
         hT = torch.empty(self.rnn_num_layers, B, self.f_len, dtype=torch.float32, device=dev)
-        stats = (torch.zeros(S, self.rnn_num_layers, B, 2, dtype=torch.int32, device=dev)
-                 if self.collect_stats else None)
+        T = self.trace_steps
+        stats = (torch.zeros(S, self.rnn_num_layers, B, 2 + 2 * T, dtype=torch.int32, device=dev)
+                 if (self.collect_stats or T) else None)
         status = torch.zeros(B, dtype=torch.int32, device=dev)
         w, keep = self._weights()
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -264,7 +272,10 @@ class PoseODERNN(nn.Module):
             torch.cuda.nvtx.range_pop()
         _lib.check(rc)
         del keep
-        self.last_stats, self.last_status = stats, status
+        self.last_status = status
+        self.last_stats = None if stats is None else stats[..., :2]
+        self.last_trace = (stats[..., 2:].contiguous().view(torch.float32).view(S, self.rnn_num_layers, B, T, 2)
+                           if T else None)
         return pose, hT
 
     def check_status(self):

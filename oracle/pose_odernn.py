@@ -46,9 +46,15 @@ class OraclePoseODERNN(nn.Module):
             raise ValueError(f"Solver {opt.ode_solver} not supported")
         self.solver_name = opt.ode_solver
         self.ctrl = ControllerOptions(atol=getattr(opt, "ode_atol", 1e-6),
-                                      rtol=getattr(opt, "ode_rtol", 1e-2))
+                                      rtol=getattr(opt, "ode_rtol", 1e-2),
+                                      accept_strict=getattr(opt, "ode_accept_strict", True),
+                                      floor_factor_after_accept=getattr(opt, "ode_floor_factor", False),
+                                      endpoint=getattr(opt, "ode_endpoint", "y1"),
+                                      exact_landing=getattr(opt, "ode_exact_landing", True),
+                                      max_steps=getattr(opt, "ode_max_steps", 100000))
         self.dt0 = getattr(opt, "ode_dt0", 1e-4)
         self.substeps = getattr(opt, "ode_substeps", 1)
+        self.trace_steps = getattr(opt, "ode_trace_steps", 0)
         if opt.ode_rnn_type == "rnn":
             self.rnn = nn.RNN(self.f_len, self.f_len, num_layers=opt.rnn_num_layers, batch_first=True)
         elif opt.ode_rnn_type == "gru":
@@ -78,6 +84,8 @@ class OraclePoseODERNN(nn.Module):
         n_steps = torch.zeros(S, L, B, dtype=torch.int64)
         n_acc = torch.zeros(S, L, B, dtype=torch.int64)
         n_f = 0
+        T = self.trace_steps
+        trace = torch.zeros(S, L, B, T, 2, dtype=torch.float32) if T else None
         for i in range(S):
             evolved = []
             for j in range(L):
@@ -85,10 +93,16 @@ class OraclePoseODERNN(nn.Module):
                 evolved.append(sol["y_end"])
                 n_steps[i, j], n_acc[i, j] = sol["n_steps"], sol["n_accepted"]
                 n_f += sol["n_f_evals"]
+                if T and "trace_dt" in sol:
+                    running = torch.ones(B, dtype=torch.bool)
+                    for k in range(min(T, len(sol["trace_dt"]))):   # only steps the row actually took
+                        took = sol["n_steps"] > k
+                        trace[i, j, :, k, 0] = torch.where(took, sol["trace_dt"][k].float(), trace[i, j, :, k, 0])
+                        trace[i, j, :, k, 1] = torch.where(took, sol["trace_ratio"][k].float(), trace[i, j, :, k, 1])
             out_i, h = self.rnn(fused[:, i:i + 1, :], torch.stack(evolved, 0))
             outs.append(out_i)
         pose = self.regressor(torch.cat(outs, 1))
-        self.last_stats = dict(n_steps=n_steps, n_accepted=n_acc, n_f_evals=n_f)
+        self.last_stats = dict(n_steps=n_steps, n_accepted=n_acc, n_f_evals=n_f, trace=trace)
         return pose, h
 
     def get_regressor_params(self):

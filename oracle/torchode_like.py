@@ -32,7 +32,16 @@ class ControllerOptions:
     factor_max: float = 10.0
     accept_strict: bool = True            # accept iff ratio < 1 (A.1, confidence M)
     floor_factor_after_accept: bool = False   # torchdiffeq/diffrax rule; torchode believed not (L)
-    endpoint: str = "dense"               # "dense": quartic/linear dense output at t_end (M); "y1"
+    # End point of the interval.  torchode (as recalled, confidence M) evaluates the step's
+    # quartic dense output at t_end.  In this call pattern (t_eval = interval ends only, dt clamped
+    # to land on t_end) that is ALWAYS x = (t_end - t0)/dt = 1, where the quartic equals y1 in exact
+    # arithmetic but carries ~32|y| ulp of cancellation noise in fp32 (hard part 4).
+    # "y1" returns that exact-arithmetic value; "dense" reproduces the literal fp32 Horner form.
+    endpoint: str = "y1"
+    # When the controller clamps dt to the remaining interval the step ends at t_end.  Literal fp32
+    # arithmetic computes fl(t + fl(t_end - t)), which can fall one ulp short and trigger an extra
+    # one-ulp step whose occurrence depends on rounding noise; exact_landing sets t = t_end.
+    exact_landing: bool = True
     max_steps: int = 100000               # torchode max_steps=None; guard so nothing spins forever
     detach_dt: bool = False               # True: treat step sizes as constants under autograd
                                           # (torchode backprop_through_step_size_control=True => False here)
@@ -116,17 +125,21 @@ def solve_adaptive(f: Callable, y0: torch.Tensor, t_eval: torch.Tensor, dt0: tor
     not_evaluated = running.clone()
     exponent = -1.0 / tab.order
     loops = 0
+    trace_dt, trace_ratio = [], []
     while bool(running.any()):
         loops += 1
         y1, err, ks = rk_step(f, tab, t, y, dt, k0)
         n_f += tab.n_stages - (1 if tab.fsal else 0)
+        trace_dt.append(dt.detach().clone())
         if err is None:
+            trace_ratio.append(torch.zeros(B, dtype=tdt))
             accept = torch.ones(B, dtype=torch.bool)
             dt_next = dt.clone()
             finite = torch.ones(B, dtype=torch.bool)
         else:
             ratio = error_ratio(err, y, y1, opts.atol, opts.rtol).to(tdt)
             finite = torch.isfinite(ratio)
+            trace_ratio.append(ratio.detach().clone())
             accept = (ratio < 1.0) if opts.accept_strict else (ratio <= 1.0)
             factor = opts.safety * torch.pow(ratio, exponent)
             factor = torch.clamp(factor, opts.factor_min, opts.factor_max)
@@ -138,7 +151,10 @@ def solve_adaptive(f: Callable, y0: torch.Tensor, t_eval: torch.Tensor, dt0: tor
         upd = accept & running
         n_steps += running
         n_acc += upd
-        t_new = torch.where(upd, t + dt, t)
+        t_next = t + dt
+        if opts.exact_landing:
+            t_next = torch.where(dt >= t_end - t, t_end, t_next)
+        t_new = torch.where(upd, t_next, t)
         # dense output at t_end for rows that just reached / passed it
         to_eval = upd & (t_new >= t_end) & not_evaluated
         if bool(to_eval.any()):
@@ -161,8 +177,10 @@ def solve_adaptive(f: Callable, y0: torch.Tensor, t_eval: torch.Tensor, dt0: tor
             break
         dt = torch.where(running, dt_next, dt)
         dt = torch.clamp(dt, t_min - t, t_max - t)
+    # rows that failed (max_steps / non-finite norm) return their last accepted state
+    y_end = torch.where((status != STATUS_OK)[:, None], y, y_end)
     return dict(y_end=y_end, n_steps=n_steps, n_accepted=n_acc, status=status,
-                n_f_evals=n_f, loops=loops)
+                n_f_evals=n_f, loops=loops, trace_dt=trace_dt, trace_ratio=trace_ratio)
 
 
 def solve_fixed(f: Callable, y0: torch.Tensor, t_eval: torch.Tensor, tab: Tableau,

@@ -44,19 +44,78 @@ def rel_err(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 
-def run_pair(ref, mod, fv, fi, ts, prev=None, device="cuda"):
+ULP = 2.0 ** -23
+
+
+def noise_ensemble(ref, fv, fi, ts, prev=None, n_members=6, eps_ulps=(2.0, 8.0, 32.0)):
+    """How well the REFERENCE SEMANTICS pin the result at fp32 precision.
+
+    Re-runs the oracle itself with relative noise of 2, 8 and 32 ulp injected into every vector-field
+    evaluation (k <- k * (1 + eps * N(0,1))) plus once in fp64 (no noise), and returns
+      stable  [S,L,B] bool: entries whose (n_steps, n_accepted) every member reproduces,
+      spread_pose, spread_h: max-norm relative deviation of the members from the fp32 oracle.
+    torchode's controller is noise-sensitive by construction: it starts from dt0 = 1e-4, where the
+    embedded error estimate is pure rounding noise, and the growth factor 0.9 * ratio^-0.2 only
+    saturates at 10 for ratio <= 0.09^5; with KITTI's 0.1 s frames the fourth step lands on t_end
+    iff ratio <= 1.06e-5, which is the noise level when |y| ~ 0 (first interval).  Different step
+    SIZES then change the solution at the solver-tolerance scale (rtol = 1e-2 in the reference).
+    The range brackets correct fp32 implementations: a K=512..768 dot product accumulated
+    sequentially with FMA (this kernel) carries ~sqrt(K)/2 ulp of rounding error, a blocked/vectorised
+    one (MKL, the oracle's backend) a few ulp, through 4 layers; the kernel's trace diagnostic
+    (ode_trace_steps) shows its noise-regime error ratios at a steady ~3.2x the oracle's."""
+    import types
+    with torch.no_grad():
+        p0, h0 = ref(fv, fi, ts, prev=prev)
+    steps0, acc0 = ref.last_stats["n_steps"].clone(), ref.last_stats["n_accepted"].clone()
+    stable = torch.ones_like(steps0, dtype=torch.bool)
+    spread_p = spread_h = 0.0
+    members = []
+    for k in range(n_members):
+        eps = ULP * eps_ulps[k % len(eps_ulps)]
+        m = copy.deepcopy(ref)
+        g = torch.Generator().manual_seed(4242 + k)
+        net = m.ode_func.net
+
+        def noisy(self, t, x, net=net, g=g, eps=eps):
+            o = net(x)
+            return o * (1 + eps * torch.randn(o.shape, generator=g, dtype=o.dtype))
+
+        m.ode_func.forward = types.MethodType(noisy, m.ode_func)
+        members.append((m, torch.float32))
+    members.append((copy.deepcopy(ref).double(), torch.float64))
+    with torch.no_grad():
+        for m, dt in members:
+            p, h = m(fv.to(dt), fi.to(dt), ts.to(dt), prev=None if prev is None else prev.to(dt))
+            stable &= (m.last_stats["n_steps"] == steps0) & (m.last_stats["n_accepted"] == acc0)
+            if dt == torch.float32:
+                spread_p = max(spread_p, rel_err(p, p0))
+                spread_h = max(spread_h, rel_err(h, h0))
+    ref.last_stats["n_steps"], ref.last_stats["n_accepted"] = steps0, acc0
+    return stable, spread_p, spread_h
+
+
+def run_pair(ref, mod, fv, fi, ts, prev=None, device="cuda", ensemble=0):
     with torch.no_grad():
         p_ref, h_ref = ref(fv, fi, ts, prev=prev)
         p, h = mod(fv.to(device), fi.to(device), ts.to(device),
                    prev=None if prev is None else prev.to(device))
     torch.cuda.synchronize()
     out = dict(pose_ref=p_ref, h_ref=h_ref, pose=p.cpu(), h=h.cpu(),
-               pose_err=rel_err(p.cpu(), p_ref), h_err=rel_err(h.cpu(), h_ref))
+               pose_err=rel_err(p.cpu(), p_ref), h_err=rel_err(h.cpu(), h_ref),
+               spread_pose=0.0, spread_h=0.0)
     if mod.last_stats is not None and ref.last_stats is not None:
         st = mod.last_stats.cpu().long()
-        out["steps_equal"] = bool((st[..., 0] == ref.last_stats["n_steps"]).all())
-        out["acc_equal"] = bool((st[..., 1] == ref.last_stats["n_accepted"]).all())
-        out["n_mismatch_rows"] = int(((st[..., 0] != ref.last_stats["n_steps"]) |
-                                      (st[..., 1] != ref.last_stats["n_accepted"])).any(0).any(0).sum())
+        neq = (st[..., 0] != ref.last_stats["n_steps"]) | (st[..., 1] != ref.last_stats["n_accepted"])
+        out["steps_equal"] = not bool(neq.any())
+        out["n_mismatch_entries"] = int(neq.sum())
+        out["n_entries"] = neq.numel()
+        out["n_mismatch_rows"] = int(neq.any(0).any(0).sum())
         out["status_max"] = int(mod.last_status.max().item())
+        out["n_unstable_entries"] = 0
+        out["n_mismatch_stable_entries"] = int(neq.sum())
+        if ensemble:
+            stable, sp, sh = noise_ensemble(ref, fv, fi, ts, prev, n_members=2 * ensemble)
+            out["n_unstable_entries"] = int((~stable).sum())
+            out["n_mismatch_stable_entries"] = int((neq & stable).sum())
+            out["spread_pose"], out["spread_h"] = sp, sh
     return out

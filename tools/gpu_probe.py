@@ -11,11 +11,12 @@ print(torch.cuda.get_device_name(0), flush=True)
 
 def parity(name, B, S, irregular=True, **over):
     ref, mod = make_pair(dev, bias_std=0.05, **over)
-    out = run_pair(ref, mod, *inputs(B, S, irregular=irregular))
+    out = run_pair(ref, mod, *inputs(B, S, irregular=irregular), ensemble=3 if B <= 64 else 1)
     st = mod.last_stats.cpu()
-    print(f"[parity] {name}: pose_err={out['pose_err']:.3e} h_err={out['h_err']:.3e} steps_equal={out.get('steps_equal')} "
-          f"acc_equal={out.get('acc_equal')} mismatch_rows={out.get('n_mismatch_rows')} status={out.get('status_max')} "
-          f"mean_steps={st[...,0].float().mean():.2f}", flush=True)
+    print(f"[parity] {name}: pose_err={out['pose_err']:.3e} (oracle spread {out['spread_pose']:.3e}) h_err={out['h_err']:.3e} ({out['spread_h']:.3e}) "
+          f"steps_equal={out.get('steps_equal')} mismatch_entries={out.get('n_mismatch_entries')}/{out.get('n_entries')} "
+          f"unstable={out.get('n_unstable_entries')} mismatch_stable={out.get('n_mismatch_stable_entries')} "
+          f"status={out.get('status_max')} mean_steps={st[...,0].float().mean():.2f}", flush=True)
 
 def timing(name, B, S=10, iters=3, **over):
     ref, mod = make_pair(dev, bias_std=0.05, **over)
@@ -56,6 +57,9 @@ if "parity" in cases:
     parity("gru B=16", 16, 10, ode_rnn_type="gru")
     parity("L3 H1024 n2 B=11", 11, 4, rnn_num_layers=3, ode_hidden_dim=1024, ode_fn_num_layers=2)
     parity("rows16 B=24", 24, 4, ode_rows_per_tile=16)
+    parity("rows4 B=24", 24, 4, ode_rows_per_tile=4)
+    parity("literal dopri5 B=16", 16, 10, ode_endpoint="dense", ode_exact_landing=False)
+    parity("dopri5 rtol1e-3 B=256", 256, 10, ode_rtol=1e-3)
 if "timing" in cases:
     timing("rk4 B=16", 16, ode_solver="rk4")
     timing("dopri5 rtol1e-3 B=1024 rt8", 1024, ode_rtol=1e-3, ode_rows_per_tile=8)
