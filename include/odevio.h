@@ -150,6 +150,14 @@ ODEVIO_API int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const ode
                               float* pose, float* hT, int32_t* stats, int32_t* status,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Diagnostics (no reference counterpart): launch a dense FFMA loop on `blocks` CTAs of 512 threads
+ * and report the FLOPs it performs in *flops_out (HOST); time it with events around the call to
+ * obtain this GPU's fp32 FMA peak, the roofline denominator of ODEVIO_PRECISION_FP32.
+ */
+ODEVIO_API int32_t odevio_microbench_ffma(int32_t iters, int32_t blocks, float* sink, double* flops_out,
+                                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,8 @@ def load():
     lib.odevio_odernn_forward.argtypes = [
         C.POINTER(OdeRnnCfg), C.POINTER(OdeRnnWeights),
         _FP, _FP, C.c_int32, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_size_t, _FP]
+    lib.odevio_microbench_ffma.restype = C.c_int32
+    lib.odevio_microbench_ffma.argtypes = [C.c_int32, C.c_int32, _FP, C.POINTER(C.c_double), _FP]
     if lib.odevio_version() != 1:
         raise OdevioError("libodevio_b200.so ABI version mismatch; rebuild")
     _lib = lib

@@ -90,27 +90,6 @@ __device__ __forceinline__ void stage_input(Ctx<RT>& c, int i) {
   named_bar_sync(1, c.th.ncons);
 }
 
-// ODEFunc evaluation: bufA (x, [D][R]) -> global K[dst] ([D][R]).
-template <int RT>
-__device__ __forceinline__ void eval_vector_field(Ctx<RT>& c, int dst) {
-  const FwdParams& p = *c.prm;
-  float* in = c.bufA;
-  float* out = c.bufB;
-  for (int j = 0; j < p.NL; ++j) {
-    Epilogue e;
-    e.mode = EPI_STORE;
-    e.bias = p.bode[j];
-    e.out1 = nullptr; e.ld1 = 0; e.off1 = 0;
-    if (j == p.NL - 1) {       // output layer: Tanh, straight to the stage array in scratch
-      e.act = ACT_TANH; e.out0 = c.K[dst]; e.ld0 = c.R; e.off0 = 0;
-    } else {
-      e.act = p.act; e.out0 = out; e.ld0 = c.R; e.off0 = 0;
-    }
-    tile_gemm<RT>(c.ring, c.pos, c.th, p.Wode[j], p.Kode[j], p.Node[j], in, c.R, p.L, e);
-    float* t = in; in = out; out = t;
-  }
-}
-
 // Error pass: y1 -> Y1, per-row sum of (err / bound)^2 -> partial[].
 template <int RT>
 __device__ __forceinline__ void error_pass(Ctx<RT>& c) {
@@ -289,11 +268,10 @@ __device__ __forceinline__ void fixed_commit(Ctx<RT>& c) {
   }
 }
 
-// One observation interval: evolve all R rows from ts[b,i] to ts[b,i+1].
+// Per-row solver state for interval i; returns "row runs" for the CTA-wide OR.
 template <int RT>
-__device__ __forceinline__ void solve_interval(Ctx<RT>& c, int i) {
+__device__ __forceinline__ int interval_begin(Ctx<RT>& c, int i) {
   const FwdParams& p = *c.prm;
-  const DevTableau& tb = p.tab;
   RowState& rs = c.rs;
   int run = 0;
   if (!c.th.producer && c.th.ctid < c.R) {
@@ -318,120 +296,77 @@ __device__ __forceinline__ void solve_interval(Ctx<RT>& c, int i) {
     rs.dtstep[r] = rs.dt[r];
     rs.run[r] = run; rs.noteval[r] = run;
   }
-  int any_running = __syncthreads_or(run);
+  return run;
+}
 
-  // One loop serves adaptive and fixed-step solvers; the first pass evaluates stage 0 (for FSAL
-  // methods that is torchode's up-front vector-field evaluation), later passes reuse it.
-  int loops = 0;
-  bool have_k0 = false;
-  while (any_running) {
-    ++loops;
-    for (int st = (tb.fsal && have_k0) ? 1 : 0; st < tb.n_stages; ++st) {
-      stage_input<RT>(c, st);
-      eval_vector_field<RT>(c, st);
-    }
-    have_k0 = true;
-    if (p.adaptive) {
-      error_pass<RT>(c);
-      run = controller<RT>(c, loops, i);
-      any_running = __syncthreads_or(run);
-      commit_pass<RT>(c);
-    } else {
-      fixed_commit<RT>(c);
-      if (!c.th.producer && c.th.ctid < c.R) { rs.nsteps[c.th.ctid] += 1; rs.nacc[c.th.ctid] += 1; }
-      any_running = loops < p.substeps;
-    }
-  }
-  // stats[S][L][B][2]
-  if (!c.th.producer && c.th.ctid < c.R) {
-    const int r = c.th.ctid;
-    const int l = r / RT, b = c.tile * RT + (r % RT);
-    if (b < p.B) {
-      if (p.stats) {
-        int* sp = p.stats + ((static_cast<size_t>(i) * p.L + l) * p.B + b) * (2 + 2 * p.trace_steps);
-        sp[0] = rs.nsteps[r]; sp[1] = rs.nacc[r];
-      }
-    }
+// stats[S][L][B][2 + 2T] <- (n_steps, n_accepted) of interval i
+template <int RT>
+__device__ __forceinline__ void write_stats(Ctx<RT>& c, int i) {
+  const FwdParams& p = *c.prm;
+  if (c.th.producer || c.th.ctid >= c.R || !p.stats) return;
+  const int r = c.th.ctid;
+  const int l = r / RT, b = c.tile * RT + (r % RT);
+  if (b < p.B) {
+    int* sp = p.stats + ((static_cast<size_t>(i) * p.L + l) * p.B + b) * (2 + 2 * p.trace_steps);
+    sp[0] = c.rs.nsteps[r]; sp[1] = c.rs.nacc[r];
   }
 }
 
-// RNN / GRU jump for all layers + pose head for interval i.
+// [x ; h] for the jump of layer l -> bufA as T-layout [2D][RT]
 template <int RT>
-__device__ __forceinline__ void jump_and_regress(Ctx<RT>& c, int i) {
+__device__ __forceinline__ void assemble_jump_input(Ctx<RT>& c, int i, int l) {
+  if (c.th.producer) return;
   const FwdParams& p = *c.prm;
   const int D = p.D;
   const TileThread& th = c.th;
-  for (int l = 0; l < p.L; ++l) {
-    // ---- assemble [x ; h] in bufA as T-layout [2D][RT]
-    if (!th.producer) {
-      if (l == 0) {
-        for (int e = th.ctid; e < D * RT; e += th.ncons) {
-          const int m = e / D, k = e - m * D;          // coalesced along k
-          const int b = c.tile * RT + m;
-          float v = 0.f;
-          if (b < p.B) {
-            const size_t row = static_cast<size_t>(b) * p.S + i;
-            v = (k < p.Dv) ? p.fv[row * p.Dv + k] : p.fi[row * (D - p.Dv) + (k - p.Dv)];
-          }
-          c.bufA[k * RT + m] = v;
-        }
-      } else {
-        for (int e = th.ctid; e < D * RT / 4; e += th.ncons) st4(c.bufA + 4 * e, ld4(c.bufB + 4 * e));
+  if (l == 0) {
+    for (int e = th.ctid; e < D * RT; e += th.ncons) {
+      const int m = e / D, k = e - m * D;          // coalesced along k
+      const int b = c.tile * RT + m;
+      float v = 0.f;
+      if (b < p.B) {
+        const size_t row = static_cast<size_t>(b) * p.S + i;
+        v = (k < p.Dv) ? p.fv[row * p.Dv + k] : p.fi[row * (D - p.Dv) + (k - p.Dv)];
       }
-      for (int e = th.ctid; e < D * RT / 4; e += th.ncons) {
-        const int d = e / (RT / 4), q = e - d * (RT / 4);
-        st4(c.bufA + static_cast<size_t>(D + d) * RT + 4 * q,
-            ld4(c.Y + static_cast<size_t>(d) * c.R + l * RT + 4 * q));
-      }
-      named_bar_sync(1, th.ncons);
+      c.bufA[k * RT + m] = v;
     }
-    Epilogue e;
-    e.mode = EPI_STORE;
-    e.ld0 = RT; e.off0 = 0; e.out1 = nullptr; e.ld1 = 0; e.off1 = 0;
-    e.rg = e.zg = e.hn = e.hprev = nullptr;
-    if (p.rnn_type == 0) {
-      e.bias = p.brnn[l][0]; e.act = ACT_TANH;
-      e.out0 = c.bufB;
-      e.out1 = c.Y; e.ld1 = c.R; e.off1 = l * RT;
-      tile_gemm<RT>(c.ring, c.pos, th, p.Wrnn[l][0], 2 * D, D, c.bufA, RT, 1, e);
-    } else {
-      // gates r, z (K = 2D), hn (K = D on the h half), then the new gate on the x half
-      float* RG = c.K[1]; float* ZG = c.K[2]; float* HN = c.K[3];   // scratch, [D][RT]
-      e.bias = p.brnn[l][0]; e.act = ACT_SIGMOID; e.out0 = RG;
-      tile_gemm<RT>(c.ring, c.pos, th, p.Wrnn[l][0], 2 * D, D, c.bufA, RT, 1, e);
-      e.bias = p.brnn[l][1]; e.out0 = ZG;
-      tile_gemm<RT>(c.ring, c.pos, th, p.Wrnn[l][1], 2 * D, D, c.bufA, RT, 1, e);
-      e.bias = p.brnn[l][3]; e.act = ACT_NONE; e.out0 = HN;
-      tile_gemm<RT>(c.ring, c.pos, th, p.Wrnn[l][3], D, D, c.bufA + static_cast<size_t>(D) * RT, RT, 1, e);
-      e.mode = EPI_GRU_NEW;
-      e.bias = p.brnn[l][2]; e.rg = RG; e.zg = ZG; e.hn = HN;
-      e.hprev = c.bufA + static_cast<size_t>(D) * RT;
-      e.out0 = c.bufB;
-      e.out1 = c.Y; e.ld1 = c.R; e.off1 = l * RT;
-      tile_gemm<RT>(c.ring, c.pos, th, p.Wrnn[l][2], D, D, c.bufA, RT, 1, e);
-    }
+  } else {
+    for (int e = th.ctid; e < D * RT / 4; e += th.ncons) st4(c.bufA + 4 * e, ld4(c.bufB + 4 * e));
   }
-  // ---- pose head on the top layer's output (bufB, [D][RT])
-  {
-    Epilogue e;
-    e.mode = EPI_STORE;
-    e.bias = p.breg0; e.act = ACT_LEAKY01;
-    e.out0 = c.bufA; e.ld0 = RT; e.off0 = 0;
-    e.out1 = nullptr; e.ld1 = 0; e.off1 = 0;
-    e.rg = e.zg = e.hn = e.hprev = nullptr;
-    tile_gemm<RT>(c.ring, c.pos, th, p.Wreg0, D, kRegHidden, c.bufB, RT, 1, e);
-    if (!th.producer) {
-      if (th.ctid < RT * kPoseDim) {
-        const int m = th.ctid / kPoseDim, o = th.ctid - m * kPoseDim;
-        const int b = c.tile * RT + m;
-        float acc = 0.f;
-        for (int k = 0; k < kRegHidden; ++k) acc = fmaf(c.bufA[k * RT + m], p.Wreg1[o * kRegHidden + k], acc);
-        if (b < p.B) p.pose[(static_cast<size_t>(b) * p.S + i) * kPoseDim + o] = acc + p.breg1[o];
-      }
-      named_bar_sync(1, th.ncons);
-    }
+  for (int e = th.ctid; e < D * RT / 4; e += th.ncons) {
+    const int d = e / (RT / 4), q = e - d * (RT / 4);
+    st4(c.bufA + static_cast<size_t>(D + d) * RT + 4 * q,
+        ld4(c.Y + static_cast<size_t>(d) * c.R + l * RT + 4 * q));
+  }
+  named_bar_sync(1, th.ncons);
+}
+
+// final Linear(128, 6) of the pose head from bufA ([128][RT]) -> pose[b, i, :]
+template <int RT>
+__device__ __forceinline__ void pose_out(Ctx<RT>& c, int i) {
+  if (c.th.producer) return;
+  const FwdParams& p = *c.prm;
+  if (c.th.ctid < RT * kPoseDim) {
+    const int m = c.th.ctid / kPoseDim, o = c.th.ctid - m * kPoseDim;
+    const int b = c.tile * RT + m;
+    float acc = 0.f;
+    for (int k = 0; k < kRegHidden; ++k) acc = fmaf(c.bufA[k * RT + m], p.Wreg1[o * kRegHidden + k], acc);
+    if (b < p.B) p.pose[(static_cast<size_t>(b) * p.S + i) * kPoseDim + o] = acc + p.breg1[o];
   }
 }
+
+// One GEMM of the tile program.
+struct GemmOp {
+  const float* W; int K; int N;
+  const float* in; int ld; int nrb;
+  Epilogue epi;
+};
+
+// Phases of the per-tile program.  The whole forward is ONE loop whose body ends in the single
+// (inlined) tile_gemm call site: every GEMM of the path -- ODEFunc layers of every RK stage, the
+// RNN/GRU jump, the pose head -- is issued from there, so the hot loop is compiled once per
+// column-pair count and scheduled by ptxas as straight-line kernel code.
+enum { PH_INTERVAL = 0, PH_STEP_BEGIN, PH_STAGE, PH_LAYER, PH_STEP_END, PH_JUMP, PH_REG, PH_REG_OUT, PH_TILE_END };
 
 }  // namespace
 
@@ -441,6 +376,8 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Ctx<RT> c;
   c.prm = &prm;
+  const FwdParams& p = prm;
+  const DevTableau& tb = prm.tab;
   const int tid = threadIdx.x;
   constexpr int ncons = 128 * LL;
   c.th.ncons = ncons;
@@ -489,6 +426,8 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
   for (int j = 0; j < kMaxStages; ++j) c.K[j] = sc + j * arr;
   c.Y = sc + kMaxStages * arr;
   c.Y1 = c.Y + arr;
+  const int D = prm.D;
+  const int gemms_per_layer = prm.rnn_type == 0 ? 1 : 4;
 
   for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
     c.tile = tile;
@@ -504,24 +443,137 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
       if (c.th.ctid < R) rs.status[c.th.ctid] = 0;
     }
     __syncthreads();
-    for (int i = 0; i < prm.S; ++i) {
-      solve_interval<RT>(c, i);
-      __syncthreads();
-      jump_and_regress<RT>(c, i);
-      __syncthreads();
+
+    int ph = PH_INTERVAL;
+    int i = 0, st = 0, j = 0, l = 0, g = 0, loops = 0, any_running = 0;
+    bool have_k0 = false;
+    float* lin = c.bufA;      // ping-pong buffers of the vector-field MLP
+    float* lout = c.bufB;
+    while (ph != PH_TILE_END) {
+      GemmOp op;
+      bool do_gemm = false;
+      switch (ph) {
+        case PH_INTERVAL: {
+          const int run = interval_begin<RT>(c, i);
+          any_running = __syncthreads_or(run);
+          loops = 0; have_k0 = false;
+          if (any_running) {
+            ph = PH_STEP_BEGIN;
+          } else {
+            write_stats<RT>(c, i);
+            l = 0; g = 0; ph = PH_JUMP;
+          }
+          break;
+        }
+        case PH_STEP_BEGIN:
+          // first pass evaluates stage 0 (for FSAL methods: torchode's up-front evaluation)
+          ++loops;
+          st = (tb.fsal && have_k0) ? 1 : 0;
+          ph = PH_STAGE;
+          break;
+        case PH_STAGE:
+          stage_input<RT>(c, st);
+          j = 0; lin = c.bufA; lout = c.bufB;
+          ph = PH_LAYER;
+          break;
+        case PH_LAYER: {
+          // ODEFunc layer j of stage st: lin -> lout (hidden) or -> K[st] (output layer, Tanh)
+          op.W = p.Wode[j]; op.K = p.Kode[j]; op.N = p.Node[j];
+          op.in = lin; op.ld = R; op.nrb = LL;
+          op.epi.mode = EPI_STORE; op.epi.bias = p.bode[j];
+          op.epi.out1 = nullptr; op.epi.ld1 = 0; op.epi.off1 = 0;
+          op.epi.ld0 = R; op.epi.off0 = 0;
+          if (j == p.NL - 1) { op.epi.act = ACT_TANH; op.epi.out0 = c.K[st]; }
+          else { op.epi.act = p.act; op.epi.out0 = lout; }
+          do_gemm = true;
+          float* t = lin; lin = lout; lout = t;
+          if (++j == p.NL) { ph = (++st < tb.n_stages) ? PH_STAGE : PH_STEP_END; }
+          break;
+        }
+        case PH_STEP_END: {
+          have_k0 = true;
+          if (p.adaptive) {
+            error_pass<RT>(c);
+            const int run = controller<RT>(c, loops, i);
+            any_running = __syncthreads_or(run);
+            commit_pass<RT>(c);
+          } else {
+            fixed_commit<RT>(c);
+            if (!c.th.producer && c.th.ctid < R) { rs.nsteps[c.th.ctid] += 1; rs.nacc[c.th.ctid] += 1; }
+            any_running = loops < p.substeps;
+          }
+          if (any_running) {
+            ph = PH_STEP_BEGIN;
+          } else {
+            write_stats<RT>(c, i);
+            __syncthreads();
+            l = 0; g = 0; ph = PH_JUMP;
+          }
+          break;
+        }
+        case PH_JUMP: {
+          // RNN: one GEMM per layer on [x ; h] (K = 2D).  GRU: r, z (K = 2D), hn (h half), new gate
+          // (x half) -- PyTorch gate order (r, z, n).
+          if (g == 0) assemble_jump_input<RT>(c, i, l);
+          float* RG = c.K[1]; float* ZG = c.K[2]; float* HN = c.K[3];   // GRU scratch, [D][RT]
+          Epilogue& e = op.epi;
+          e.mode = EPI_STORE; e.ld0 = RT; e.off0 = 0; e.out1 = nullptr; e.ld1 = 0; e.off1 = 0;
+          e.rg = e.zg = e.hn = e.hprev = nullptr;
+          op.N = D; op.ld = RT; op.nrb = 1; op.in = c.bufA; op.K = 2 * D;
+          if (p.rnn_type == 0) {
+            op.W = p.Wrnn[l][0]; e.bias = p.brnn[l][0]; e.act = ACT_TANH;
+            e.out0 = c.bufB; e.out1 = c.Y; e.ld1 = R; e.off1 = l * RT;
+          } else if (g == 0) {
+            op.W = p.Wrnn[l][0]; e.bias = p.brnn[l][0]; e.act = ACT_SIGMOID; e.out0 = RG;
+          } else if (g == 1) {
+            op.W = p.Wrnn[l][1]; e.bias = p.brnn[l][1]; e.act = ACT_SIGMOID; e.out0 = ZG;
+          } else if (g == 2) {
+            op.W = p.Wrnn[l][3]; e.bias = p.brnn[l][3]; e.act = ACT_NONE; e.out0 = HN;
+            op.K = D; op.in = c.bufA + static_cast<size_t>(D) * RT;
+          } else {
+            op.W = p.Wrnn[l][2]; e.bias = p.brnn[l][2]; e.mode = EPI_GRU_NEW;
+            e.rg = RG; e.zg = ZG; e.hn = HN; e.hprev = c.bufA + static_cast<size_t>(D) * RT;
+            e.out0 = c.bufB; e.out1 = c.Y; e.ld1 = R; e.off1 = l * RT;
+            op.K = D;
+          }
+          do_gemm = true;
+          if (++g == gemms_per_layer) { g = 0; if (++l == LL) ph = PH_REG; }
+          break;
+        }
+        case PH_REG: {
+          // pose head on the top layer's output (bufB, [D][RT]): Linear(D,128) + LeakyReLU(0.1)
+          op.W = p.Wreg0; op.K = D; op.N = kRegHidden; op.in = c.bufB; op.ld = RT; op.nrb = 1;
+          op.epi.mode = EPI_STORE; op.epi.bias = p.breg0; op.epi.act = ACT_LEAKY01;
+          op.epi.out0 = c.bufA; op.epi.ld0 = RT; op.epi.off0 = 0;
+          op.epi.out1 = nullptr; op.epi.ld1 = 0; op.epi.off1 = 0;
+          do_gemm = true;
+          ph = PH_REG_OUT;
+          break;
+        }
+        case PH_REG_OUT:
+          pose_out<RT>(c, i);
+          __syncthreads();
+          ph = (++i < p.S) ? PH_INTERVAL : PH_TILE_END;
+          break;
+        default:
+          ph = PH_TILE_END;
+          break;
+      }
+      if (do_gemm) tile_gemm<RT>(c.ring, c.pos, c.th, op.W, op.K, op.N, op.in, op.ld, op.nrb, op.epi);
     }
+
     // ---- final hidden state and status
     if (!c.th.producer) {
       for (int e = c.th.ctid; e < prm.D * R; e += ncons) {
         const int r = e / prm.D, d = e - r * prm.D;
-        const int l = r / RT, b = tile * RT + (r % RT);
-        if (b < prm.B) prm.hT[(static_cast<size_t>(l) * prm.B + b) * prm.D + d] = c.Y[static_cast<size_t>(d) * R + r];
+        const int l2 = r / RT, b = tile * RT + (r % RT);
+        if (b < prm.B) prm.hT[(static_cast<size_t>(l2) * prm.B + b) * prm.D + d] = c.Y[static_cast<size_t>(d) * R + r];
       }
       if (prm.status && c.th.ctid < RT) {
         const int b = tile * RT + c.th.ctid;
-        int st = 0;
-        for (int l = 0; l < LL; ++l) st = max(st, rs.status[l * RT + c.th.ctid]);
-        if (b < prm.B) prm.status[b] = st;
+        int stt = 0;
+        for (int l2 = 0; l2 < LL; ++l2) stt = max(stt, rs.status[l2 * RT + c.th.ctid]);
+        if (b < prm.B) prm.status[b] = stt;
       }
     }
     __syncthreads();

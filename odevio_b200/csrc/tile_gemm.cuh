@@ -100,12 +100,13 @@ __device__ __forceinline__ void run_epilogue(const Epilogue& e, int n, int rb, c
   }
 }
 
-// Consumer body, compiled once per (RT, P) and shared by every call site.  Returns the
-// advanced ring position packed as stage | phase << 8.
+// Consumer body.  Inlined into its (single) call site: as an ABI (__noinline__) function ptxas
+// serialised every LDS behind the previous step's FFMAs; inlined it double-buffers the operand
+// registers.  Returns the advanced ring position packed as stage | phase << 8.
 // Operands are addressed as offsets from the dynamic shared-memory base so the compiler emits
 // LDS (shared-space) loads in the hot loop instead of generic LD.
 template <int RT, int P>
-__device__ __noinline__ uint32_t gemm_body(WeightRing ring, uint32_t pos_packed, uint32_t in_off,
+__device__ __forceinline__ uint32_t gemm_body(WeightRing ring, uint32_t pos_packed, uint32_t in_off,
                                            int ld, int K, int N, int rb, int cg, int tpb, int lane,
                                            const Epilogue* __restrict__ epi) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -123,27 +124,42 @@ __device__ __noinline__ uint32_t gemm_body(WeightRing ring, uint32_t pos_packed,
     for (int r = 0; r < RT; ++r) { acc[pp][0][r] = 0.f; acc[pp][1][r] = 0.f; }
   }
   const int nch = K / KC;
+  // Software-pipelined over k with two operand register sets: the loads of step kk+1 are issued
+  // before the FFMAs of step kk, so the ~30-cycle LDS latency hides behind 16*P FFMAs instead of
+  // being exposed twice per step (ncu: short_scoreboard was the top stall without this).
+  float xa[RT], xb[RT];
+  float2 wa[P], wb[P];
+  auto load_operands = [&](const float* __restrict__ xp, const float* __restrict__ ws, int kk,
+                           float (&x)[RT], float2 (&w)[P]) {
+#pragma unroll
+    for (int q = 0; q < RT / 4; ++q) {
+      const float4 v = ld4(xp + kk * ld + 4 * q);
+      x[4 * q + 0] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int pp = 0; pp < P; ++pp) w[pp] = *reinterpret_cast<const float2*>(ws + kk * N + col[pp]);
+  };
+  auto fma_step = [&](const float (&x)[RT], const float2 (&w)[P]) {
+#pragma unroll
+    for (int pp = 0; pp < P; ++pp) {
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        acc[pp][0][r] = fmaf(x[r], w[pp].x, acc[pp][0][r]);
+        acc[pp][1][r] = fmaf(x[r], w[pp].y, acc[pp][1][r]);
+      }
+    }
+  };
   for (int ch = 0; ch < nch; ++ch) {
     mbar_wait(&ring.full[pos.stage], pos.phase);
     const float* __restrict__ ws = ring_buf + pos.stage * ring.stage_floats;
     const float* __restrict__ xp = inT + ch * KC * ld;
+    load_operands(xp, ws, 0, xa, wa);
 #pragma unroll
-    for (int kk = 0; kk < KC; ++kk) {
-      float x[RT];
-#pragma unroll
-      for (int q = 0; q < RT / 4; ++q) {
-        const float4 v = ld4(xp + kk * ld + 4 * q);
-        x[4 * q + 0] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
-      }
-#pragma unroll
-      for (int pp = 0; pp < P; ++pp) {
-        const float2 w = *reinterpret_cast<const float2*>(ws + kk * N + col[pp]);
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-          acc[pp][0][r] = fmaf(x[r], w.x, acc[pp][0][r]);
-          acc[pp][1][r] = fmaf(x[r], w.y, acc[pp][1][r]);
-        }
-      }
+    for (int kk = 0; kk < KC; kk += 2) {
+      load_operands(xp, ws, kk + 1, xb, wb);
+      fma_step(xa, wa);
+      if (kk + 2 < KC) load_operands(xp, ws, kk + 2, xa, wa);
+      fma_step(xb, wb);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&ring.empty[pos.stage]);
