@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libodevio_b200.so")
+LIB_PATH = os.environ.get("ODEVIO_LIB_PATH") or os.path.join(_HERE, "lib", "libodevio_b200.so")
 
 MAX_ODE_LINEARS = 6
 MAX_RNN_LAYERS = 4

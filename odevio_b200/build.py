@@ -50,40 +50,49 @@ def _fingerprint():
     return h.hexdigest()
 
 
-def build_library(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared object.  Returns its path."""
+def build_library(force=False, verbose=False, variant=None, defines=()):
+    """Compile every .cu under csrc/ into one shared object.  Returns its path.
+    `variant`/`defines` build a tuning variant (lib/libodevio_b200.<variant>.so) for A/B runs;
+    select it at run time with ODEVIO_LIB_PATH."""
     os.makedirs(LIBDIR, exist_ok=True)
+    if variant:
+        return _build(os.path.join(LIBDIR, f"libodevio_b200.{variant}.so"), variant, list(defines), verbose)
     stamp = os.path.join(LIBDIR, ".fingerprint")
     fp = _fingerprint()
     if not force and os.path.exists(LIBPATH) and os.path.exists(stamp):
         with open(stamp) as fh:
             if fh.read().strip() == fp:
                 return LIBPATH
+    path = _build(LIBPATH, "", [], verbose)
+    with open(stamp, "w") as fh:
+        fh.write(fp)
+    return path
+
+
+def _build(libpath, tag, defines, verbose):
     nvcc = _nvcc()
     objs = []
     log = []
     for src in sources():
-        obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
+        obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + (f".{tag}" if tag else "") + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:
             sys.stderr.write(log[-1])
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIBPATH] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-o", libpath] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
         sys.stderr.write(log[-1])
         raise RuntimeError("link failed")
-    with open(os.path.join(LIBDIR, "build.log"), "w") as fh:
+    with open(os.path.join(LIBDIR, f"build{'.' + tag if tag else ''}.log"), "w") as fh:
         fh.write("\n".join(log))
-    with open(stamp, "w") as fh:
-        fh.write(fp)
     if verbose:
         print("\n".join(log))
-    return LIBPATH
+    return libpath
 
 
 if __name__ == "__main__":

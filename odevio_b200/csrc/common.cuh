@@ -48,6 +48,34 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or
+// the hint (ns) elapses, instead of returning after the short default window.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+// Producer-side wait: parked in hardware so the lane does not steal issue slots from the two
+// consumer warps that share its scheduler (ncu: 828M polling TRYWAITs per launch without it).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (++spins > (1u << 20)) __trap();
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -74,6 +102,18 @@ __device__ __noinline__ float apply_act(float v, int act) {
     case ACT_LEAKY01: return v > 0.f ? v : 0.1f * v;          // regressor LeakyReLU(0.1)
     case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
     default: return v;
+  }
+}
+
+// 4-wide variant used by the GEMM epilogues: one ABI call per float4, the four transcendental
+// chains inside interleave (ncu: the scalar calls were ~11 % of the fused kernel's warp time).
+__device__ __noinline__ float4 apply_act4(float4 v, int act) {
+  switch (act) {
+    case ACT_TANH: return make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+    case ACT_RELU: return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    case ACT_NONE: return v;
+    default:
+      return make_float4(apply_act(v.x, act), apply_act(v.y, act), apply_act(v.z, act), apply_act(v.w, act));
   }
 }
 

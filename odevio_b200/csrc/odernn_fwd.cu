@@ -358,7 +358,7 @@ __device__ __forceinline__ void pose_out(Ctx<RT>& c, int i) {
 // One GEMM of the tile program.
 struct GemmOp {
   const float* W; int K; int N;
-  const float* in; int ld; int nrb;
+  const float* in; bool ode_layout;
   Epilogue epi;
 };
 
@@ -411,6 +411,7 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
   c.ring.nst = prm.nst;
   c.pos.stage = 0;
   c.pos.phase = 0;
+  c.pos.ready = 0;
   if (tid == 0) {
     for (int s = 0; s < prm.nst; ++s) {
       mbar_init(&c.ring.full[s], 1);
@@ -479,7 +480,7 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
         case PH_LAYER: {
           // ODEFunc layer j of stage st: lin -> lout (hidden) or -> K[st] (output layer, Tanh)
           op.W = p.Wode[j]; op.K = p.Kode[j]; op.N = p.Node[j];
-          op.in = lin; op.ld = R; op.nrb = LL;
+          op.in = lin; op.ode_layout = true;
           op.epi.mode = EPI_STORE; op.epi.bias = p.bode[j];
           op.epi.out1 = nullptr; op.epi.ld1 = 0; op.epi.off1 = 0;
           op.epi.ld0 = R; op.epi.off0 = 0;
@@ -519,7 +520,7 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
           Epilogue& e = op.epi;
           e.mode = EPI_STORE; e.ld0 = RT; e.off0 = 0; e.out1 = nullptr; e.ld1 = 0; e.off1 = 0;
           e.rg = e.zg = e.hn = e.hprev = nullptr;
-          op.N = D; op.ld = RT; op.nrb = 1; op.in = c.bufA; op.K = 2 * D;
+          op.N = D; op.ode_layout = false; op.in = c.bufA; op.K = 2 * D;
           if (p.rnn_type == 0) {
             op.W = p.Wrnn[l][0]; e.bias = p.brnn[l][0]; e.act = ACT_TANH;
             e.out0 = c.bufB; e.out1 = c.Y; e.ld1 = R; e.off1 = l * RT;
@@ -542,7 +543,7 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
         }
         case PH_REG: {
           // pose head on the top layer's output (bufB, [D][RT]): Linear(D,128) + LeakyReLU(0.1)
-          op.W = p.Wreg0; op.K = D; op.N = kRegHidden; op.in = c.bufB; op.ld = RT; op.nrb = 1;
+          op.W = p.Wreg0; op.K = D; op.N = kRegHidden; op.in = c.bufB; op.ode_layout = false;
           op.epi.mode = EPI_STORE; op.epi.bias = p.breg0; op.epi.act = ACT_LEAKY01;
           op.epi.out0 = c.bufA; op.epi.ld0 = RT; op.epi.off0 = 0;
           op.epi.out1 = nullptr; op.epi.ld1 = 0; op.epi.off1 = 0;
@@ -559,7 +560,7 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
           ph = PH_TILE_END;
           break;
       }
-      if (do_gemm) tile_gemm<RT>(c.ring, c.pos, c.th, op.W, op.K, op.N, op.in, op.ld, op.nrb, op.epi);
+      if (do_gemm) tile_gemm<RT, LL>(c.ring, c.pos, c.th, op.W, op.K, op.N, op.in, op.ode_layout, op.epi);
     }
 
     // ---- final hidden state and status

@@ -18,6 +18,15 @@
 namespace odevio {
 
 constexpr int KC = 8;           // k-rows per weight stage
+
+// tuning switches (A/B-tested on the B200, see profiles/)
+#ifndef ODEVIO_PRODUCER_WAIT
+#define ODEVIO_PRODUCER_WAIT 0      // 0 spin, 1 nanosleep back-off, 2 hardware-parked try_wait
+#endif
+#ifndef ODEVIO_EARLY_PROBE
+#define ODEVIO_EARLY_PROBE 0        // probe the next stage's full barrier one chunk ahead (no gain at 8-row
+                                    // tiles, -28 % at 16-row tiles on B200: profiles/r01_ab_tuning.md)
+#endif
 constexpr int MAX_STAGES = 4;
 constexpr int MAX_P = 4;        // column pairs per thread -> N <= 2 * MAX_P * threads_per_row_block
 
@@ -35,6 +44,7 @@ struct WeightRing {
 struct RingPos {
   uint32_t stage;
   uint32_t phase;
+  uint32_t ready;        // consumer hint: the full barrier at (stage, phase) was already seen complete
   __device__ __forceinline__ void advance(uint32_t nst) {
     if (++stage == nst) { stage = 0; phase ^= 1u; }
   }
@@ -67,7 +77,13 @@ __device__ __forceinline__ void pipe_produce(const WeightRing& ring, RingPos& po
   const uint32_t bytes = static_cast<uint32_t>(KC) * N * sizeof(float);
   const int nch = K / KC;
   for (int ch = 0; ch < nch; ++ch) {
+#if ODEVIO_PRODUCER_WAIT == 2
+    mbar_wait_parked(&ring.empty[pos.stage], pos.phase ^ 1u);
+#elif ODEVIO_PRODUCER_WAIT == 1
+    mbar_wait_backoff(&ring.empty[pos.stage], pos.phase ^ 1u);
+#else
     mbar_wait(&ring.empty[pos.stage], pos.phase ^ 1u);
+#endif
     mbar_arrive_expect_tx(&ring.full[pos.stage], bytes);
     tma_load_1d(ring.buf + static_cast<size_t>(pos.stage) * ring.stage_floats,
                 Wt + static_cast<size_t>(ch) * KC * N, bytes, &ring.full[pos.stage]);
@@ -81,7 +97,11 @@ __device__ __forceinline__ void run_epilogue(const Epilogue& e, int n, int rb, c
   float v[RT];
   if (e.mode == EPI_STORE) {
 #pragma unroll
-    for (int r = 0; r < RT; ++r) v[r] = apply_act(acc[r] + b, e.act);
+    for (int q = 0; q < RT / 4; ++q) {
+      const float4 a4 = apply_act4(make_float4(acc[4 * q] + b, acc[4 * q + 1] + b, acc[4 * q + 2] + b,
+                                               acc[4 * q + 3] + b), e.act);
+      v[4 * q] = a4.x; v[4 * q + 1] = a4.y; v[4 * q + 2] = a4.z; v[4 * q + 3] = a4.w;
+    }
   } else {
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
@@ -112,7 +132,7 @@ __device__ __forceinline__ uint32_t gemm_body(WeightRing ring, uint32_t pos_pack
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const float* __restrict__ inT = reinterpret_cast<const float*>(smem_raw + in_off);
   const float* __restrict__ ring_buf = reinterpret_cast<const float*>(smem_raw + ring.buf_off);
-  RingPos pos{pos_packed & 0xffu, pos_packed >> 8};
+  RingPos pos{pos_packed & 0xffu, (pos_packed >> 8) & 1u, (pos_packed >> 16) & 1u};
   float acc[P][2][RT];
   int col[P];
   const int npairs = N >> 1;
@@ -149,10 +169,19 @@ __device__ __forceinline__ uint32_t gemm_body(WeightRing ring, uint32_t pos_pack
       }
     }
   };
+  bool ready = pos.ready != 0;
   for (int ch = 0; ch < nch; ++ch) {
-    mbar_wait(&ring.full[pos.stage], pos.phase);
+    if (!ready) mbar_wait(&ring.full[pos.stage], pos.phase);
     const float* __restrict__ ws = ring_buf + pos.stage * ring.stage_floats;
     const float* __restrict__ xp = inT + ch * KC * ld;
+    const uint32_t cur = pos.stage;
+    pos.advance(ring.nst);
+#if ODEVIO_EARLY_PROBE
+    // probe the NEXT stage's barrier now; its ~90-cycle predicate latency hides behind this chunk
+    ready = mbar_try_wait(&ring.full[pos.stage], pos.phase);
+#else
+    ready = false;
+#endif
     load_operands(xp, ws, 0, xa, wa);
 #pragma unroll
     for (int kk = 0; kk < KC; kk += 2) {
@@ -162,9 +191,9 @@ __device__ __forceinline__ uint32_t gemm_body(WeightRing ring, uint32_t pos_pack
       fma_step(xb, wb);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ring.empty[pos.stage]);
-    pos.advance(ring.nst);
+    if (lane == 0) mbar_arrive(&ring.empty[cur]);
   }
+  pos.ready = ready ? 1u : 0u;
   const Epilogue e = *epi;
 #pragma unroll
   for (int pp = 0; pp < P; ++pp) {
@@ -174,29 +203,33 @@ __device__ __forceinline__ uint32_t gemm_body(WeightRing ring, uint32_t pos_pack
       run_epilogue<RT>(e, 2 * q + 1, rb, acc[pp][1]);
     }
   }
-  return pos.stage | (pos.phase << 8);
+  return pos.stage | (pos.phase << 8) | (pos.ready << 16);
 }
 
 // All threads of the CTA call this with identical arguments.
-//   Wt: packed [K][N] (K % KC == 0, N even, N <= 2*MAX_P*tpb), inT: shared T-layout, nrb row
-//   blocks of RT rows (row block rb starts at inT + rb*RT), ncons % nrb == 0.
+//   Wt: packed [K][N] (K % KC == 0, N even, N <= 2*MAX_P*tpb), inT: shared T-layout.
+//   ode_layout: vector-field geometry (LL row blocks of RT rows, row block rb starts at inT + rb*RT,
+//   row stride RT*LL, 128 threads per row block) vs jump geometry (one row block, stride RT).
 // Ends with a consumer-wide named barrier so the epilogue's stores are visible to the next phase.
-template <int RT>
+template <int RT, int LL>
 __device__ __forceinline__ void tile_gemm(const WeightRing& ring, RingPos& pos, const TileThread& th,
                                           const float* __restrict__ Wt, int K, int N,
-                                          const float* inT, int ld, int nrb, const Epilogue& epi) {
+                                          const float* inT, bool ode_layout, const Epilogue& epi) {
   if (th.producer) {
     if (th.lane == 0) pipe_produce(ring, pos, Wt, K, N);
     __syncwarp();
     return;
   }
-  const int tpb = th.ncons / nrb;
+  constexpr int ncons = 128 * LL;
+  const int nrb = ode_layout ? LL : 1;
+  const int ld = ode_layout ? RT * LL : RT;
+  const int tpb = ncons / nrb;
   const int rb = th.ctid / tpb;
   const int cg = th.ctid - rb * tpb;
   const int P = ((N >> 1) + tpb - 1) / tpb;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t in_rb = static_cast<uint32_t>(reinterpret_cast<const unsigned char*>(inT + rb * RT) - smem_raw);
-  const uint32_t pk = pos.stage | (pos.phase << 8);
+  const uint32_t pk = pos.stage | (pos.phase << 8) | (pos.ready << 16);
   uint32_t nk;
   switch (P) {
     case 1: nk = gemm_body<RT, 1>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
@@ -205,8 +238,9 @@ __device__ __forceinline__ void tile_gemm(const WeightRing& ring, RingPos& pos, 
     default: nk = gemm_body<RT, 4>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
   }
   pos.stage = nk & 0xffu;
-  pos.phase = nk >> 8;
-  named_bar_sync(1, th.ncons);
+  pos.phase = (nk >> 8) & 1u;
+  pos.ready = (nk >> 16) & 1u;
+  named_bar_sync(1, ncons);
 }
 
 }  // namespace odevio

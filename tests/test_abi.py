@@ -1,0 +1,85 @@
+"""The C-ABI library loads on a machine without a GPU and exports every symbol include/odevio.h
+declares; argument validation returns error codes without touching a device."""
+
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "odevio.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from odevio_b200.build import build_library
+    build_library()
+    from odevio_b200 import _lib
+    return _lib.load()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"ODEVIO_API[^;(]*?\b(odevio_\w+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = declared_symbols()
+    for must in ("odevio_version", "odevio_odernn_forward", "odevio_odernn_workspace_bytes",
+                 "odevio_odernn_default_cfg", "odevio_error_string"):
+        assert must in names
+
+
+def test_every_declared_symbol_is_exported(lib):
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/odevio.h but not exported"
+
+
+def test_struct_layout_matches_header(lib):
+    from odevio_b200 import _lib
+    cfg = _lib.default_odernn_cfg()
+    assert C.sizeof(_lib.OdeRnnCfg) == 30 * 4       # 24 ints + 6 floats, see include/odevio.h
+    assert (cfg.B, cfg.S, cfg.D, cfg.H, cfg.n_hidden, cfg.L) == (1, 10, 768, 512, 3, 2)
+    assert abs(cfg.atol - 1e-6) < 1e-12 and abs(cfg.rtol - 1e-2) < 1e-9 and abs(cfg.dt0 - 1e-4) < 1e-11
+    assert (cfg.accept_strict, cfg.floor_factor, cfg.endpoint_dense, cfg.exact_landing) == (1, 0, 0, 1)
+    assert lib.odevio_version() == 1
+
+
+def test_workspace_and_validation_without_gpu(lib):
+    from odevio_b200 import _lib
+    cfg = _lib.default_odernn_cfg()
+    cfg.B = 1024
+    assert lib.odevio_odernn_workspace_bytes(C.byref(cfg)) > 0
+    bad = _lib.default_odernn_cfg()
+    bad.D = 770                                  # not a multiple of 8
+    assert lib.odevio_odernn_workspace_bytes(C.byref(bad)) == 0
+    bad = _lib.default_odernn_cfg()
+    bad.solver = 17
+    assert lib.odevio_odernn_workspace_bytes(C.byref(bad)) == 0
+    w = _lib.OdeRnnWeights()
+    rc = lib.odevio_odernn_forward(C.byref(cfg), C.byref(w), None, None, 768, None, None, None, None, None,
+                                   None, None, 0, None)
+    assert rc == -1                              # ODEVIO_E_NULL, before any device work
+    assert b"NULL" in lib.odevio_error_string(rc)
+
+
+def test_module_fails_loudly_without_cuda():
+    import torch
+    import odevio_b200
+    from oracle.pose_odernn import default_opt
+    m = odevio_b200.PoseODERNN(default_opt())
+    fv, fi, ts = torch.zeros(2, 10, 512), torch.zeros(2, 10, 256), torch.zeros(2, 11)
+    with torch.no_grad(), pytest.raises(odevio_b200.OdevioError):
+        m(fv, fi, ts)
+
+
+def test_reference_menu_errors():
+    import odevio_b200
+    from oracle.pose_odernn import default_opt
+    with pytest.raises(ValueError):
+        odevio_b200.PoseODERNN(default_opt(ode_solver="bosh3"))
+    with pytest.raises(ValueError):
+        odevio_b200.PoseODERNN(default_opt(ode_rnn_type="lstm"))
+    with pytest.raises(ValueError):
+        odevio_b200.ODEFunc(8, 8, 2, "gelu")
