@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define ODEVIO_ABI_VERSION 1
+#define ODEVIO_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define ODEVIO_API __attribute__((visibility("default")))
@@ -69,7 +69,8 @@ enum {
   ODEVIO_SOLVER_EULER = 3, ODEVIO_SOLVER_RK4 = 4, ODEVIO_SOLVER_RK4_38 = 5
 };
 /* per-row status codes written to `status` */
-enum { ODEVIO_STATUS_OK = 0, ODEVIO_STATUS_MAX_STEPS = 1, ODEVIO_STATUS_INFINITE_NORM = 2 };
+enum { ODEVIO_STATUS_OK = 0, ODEVIO_STATUS_MAX_STEPS = 1, ODEVIO_STATUS_INFINITE_NORM = 2,
+       ODEVIO_STATUS_CKPT_OVERFLOW = 3 /* training: more solver iterations than cfg.ckpt_loops */ };
 /* arithmetic mode of the vector-field GEMMs */
 enum { ODEVIO_PRECISION_FP32 = 0 };
 
@@ -96,13 +97,16 @@ typedef struct odevio_odernn_cfg {
                                  torchode); 0: y1, its exact-arithmetic value (default) */
   int32_t max_steps;          /* per-interval guard; rows still running get STATUS_MAX_STEPS */
   int32_t precision;          /* ODEVIO_PRECISION_* */
-  int32_t save_checkpoints;   /* 1: record what odevio_odernn_backward needs in `ckpt` */
+  int32_t save_checkpoints;   /* 1: record what odevio_odernn_backward needs in `ckpt` (training;
+                                 tanh-RNN jump, rows_per_tile 4 or 8, endpoint_dense = 0) */
   int32_t rows_per_tile;      /* 0 = auto; else 4, 8 or 16 sequences per CTA */
   int32_t exact_landing;      /* 1 (default): a step clamped to the remaining interval ends exactly at
                                  t_end; 0: literal fp32 t + (t_end - t), may need a 1-ulp extra step */
   int32_t trace_steps;        /* T >= 0: additionally record (dt, error ratio) of the first T steps of
                                  every solve; the stats row then has 2 + 2*T int32 (floats as bits) */
-  int32_t reserved[5];
+  int32_t ckpt_loops;         /* training: stored solver iterations per interval and tile (0 = 16, or
+                                 `substeps` for the fixed-step solvers); overflow -> STATUS_CKPT_OVERFLOW */
+  int32_t reserved[4];
 } odevio_odernn_cfg;
 
 /* PyTorch-layout parameters ([out, in] row-major), exactly the reference's state_dict tensors */
@@ -118,6 +122,20 @@ typedef struct odevio_odernn_weights {
   const float* reg_w1;  /* regressor.2.weight [6, 128] */
   const float* reg_b1;  /* regressor.2.bias   [6]      */
 } odevio_odernn_weights;
+
+/* Gradient outputs of odevio_odernn_backward: same shapes as odevio_odernn_weights (overwritten). */
+typedef struct odevio_odernn_grads {
+  float* ode_w[ODEVIO_MAX_ODE_LINEARS];
+  float* ode_b[ODEVIO_MAX_ODE_LINEARS];
+  float* rnn_w_ih[ODEVIO_MAX_RNN_LAYERS];
+  float* rnn_w_hh[ODEVIO_MAX_RNN_LAYERS];
+  float* rnn_b_ih[ODEVIO_MAX_RNN_LAYERS];
+  float* rnn_b_hh[ODEVIO_MAX_RNN_LAYERS];
+  float* reg_w0;
+  float* reg_b0;
+  float* reg_w1;
+  float* reg_b1;
+} odevio_odernn_grads;
 
 /* ABI version of the loaded library (== ODEVIO_ABI_VERSION of the header it was built from). */
 ODEVIO_API int32_t odevio_version(void);
@@ -142,13 +160,50 @@ ODEVIO_API size_t odevio_odernn_workspace_bytes(const odevio_odernn_cfg* cfg);
  *   stats  [S,L,B,2+2T] int32 or NULL: (n_steps, n_accepted, then T x (dt, ratio) as float bits,
  *                                  T = cfg->trace_steps) per interval / layer / row; zero-fill it
  *   status [B] int32 or NULL:       worst ODEVIO_STATUS_* seen by the row
+ *   ckpt: NULL, or (cfg.save_checkpoints = 1) >= odevio_odernn_ckpt_bytes(cfg), 256-byte aligned
  *   workspace: >= odevio_odernn_workspace_bytes(cfg), 256-byte aligned
  */
 ODEVIO_API int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_weights* w,
                               const float* fv, const float* fi, int32_t Dv,
                               const float* ts, const float* h0,
                               float* pose, float* hT, int32_t* stats, int32_t* status,
+                              void* ckpt, size_t ckpt_bytes,
                               void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Launch geometry chosen for cfg: out[0] = sequences per tile (RT), out[1] = rows per tile
+ * (RT * L), out[2] = number of tiles, out[3] = vector-field evaluations recorded per stored
+ * solver iteration (stages entering y1), out[4] = stored iterations per interval (ckpt_loops
+ * resolved), out[5] = CTAs launched; out[6..7] reserved.  out must hold 8 int32 (HOST).
+ */
+ODEVIO_API int32_t odevio_odernn_geometry(const odevio_odernn_cfg* cfg, int32_t* out);
+
+/*
+ * Training (replaces loss.backward() through PoseODERNN.forward, reference
+ * scripts/train_model.py:78 -- torchode's AutoDiffAdjoint is plain autograd through the solver loop).
+ *
+ * 1. forward with cfg.save_checkpoints = 1 and a `ckpt` buffer of odevio_odernn_ckpt_bytes(cfg)
+ *    bytes (256-byte aligned).  Its head is int32 nloops[ntiles * S]: the number of stored solver
+ *    iterations of every (tile, interval).
+ * 2. the caller turns nloops into rec_base[ntiles * S] (int64, DEVICE) = exclusive prefix sum of
+ *    nloops * out[3] * out[1] and ode_rows = the total (this is the one host read of the step).
+ * 3. odevio_odernn_backward with a workspace of odevio_odernn_backward_workspace_bytes(cfg, ode_rows).
+ *
+ * Discretise-then-optimise with the accepted step sizes treated as constants.
+ *   grad_pose [B,S,6], grad_hT [L,B,D] or NULL (zero)      incoming gradients
+ *   g                                                     parameter gradients (overwritten)
+ *   grad_fused [B,S,D] or NULL                            gradient of the fused features cat(fv, fi)
+ *   grad_h0 [L,B,D] or NULL                               gradient of the initial hidden state
+ */
+ODEVIO_API size_t odevio_odernn_ckpt_bytes(const odevio_odernn_cfg* cfg);
+ODEVIO_API size_t odevio_odernn_backward_workspace_bytes(const odevio_odernn_cfg* cfg, int64_t ode_rows);
+ODEVIO_API int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn_weights* w,
+                               const float* fv, const float* fi, int32_t Dv,
+                               const void* ckpt, size_t ckpt_bytes,
+                               const int64_t* rec_base, int64_t ode_rows,
+                               const float* grad_pose, const float* grad_hT,
+                               const odevio_odernn_grads* g, float* grad_fused, float* grad_h0,
+                               void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Diagnostics (no reference counterpart): launch a dense FFMA loop on `blocks` CTAs of 512 threads

@@ -30,7 +30,7 @@ class OdeRnnCfg(C.Structure):
         ("accept_strict", C.c_int32), ("floor_factor", C.c_int32), ("endpoint_dense", C.c_int32),
         ("max_steps", C.c_int32), ("precision", C.c_int32), ("save_checkpoints", C.c_int32),
         ("rows_per_tile", C.c_int32), ("exact_landing", C.c_int32), ("trace_steps", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("ckpt_loops", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -46,6 +46,11 @@ class OdeRnnWeights(C.Structure):
     ]
 
 
+class OdeRnnGrads(C.Structure):
+    _fields_ = OdeRnnWeights._fields_
+
+
+ABI_VERSION = 2
 _lib = None
 
 
@@ -73,10 +78,20 @@ def load():
     lib.odevio_odernn_forward.restype = C.c_int32
     lib.odevio_odernn_forward.argtypes = [
         C.POINTER(OdeRnnCfg), C.POINTER(OdeRnnWeights),
-        _FP, _FP, C.c_int32, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_size_t, _FP]
+        _FP, _FP, C.c_int32, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_size_t, _FP, C.c_size_t, _FP]
+    lib.odevio_odernn_geometry.restype = C.c_int32
+    lib.odevio_odernn_geometry.argtypes = [C.POINTER(OdeRnnCfg), C.POINTER(C.c_int32)]
+    lib.odevio_odernn_ckpt_bytes.restype = C.c_size_t
+    lib.odevio_odernn_ckpt_bytes.argtypes = [C.POINTER(OdeRnnCfg)]
+    lib.odevio_odernn_backward_workspace_bytes.restype = C.c_size_t
+    lib.odevio_odernn_backward_workspace_bytes.argtypes = [C.POINTER(OdeRnnCfg), C.c_int64]
+    lib.odevio_odernn_backward.restype = C.c_int32
+    lib.odevio_odernn_backward.argtypes = [
+        C.POINTER(OdeRnnCfg), C.POINTER(OdeRnnWeights), _FP, _FP, C.c_int32, _FP, C.c_size_t,
+        _FP, C.c_int64, _FP, _FP, C.POINTER(OdeRnnGrads), _FP, _FP, _FP, C.c_size_t, _FP]
     lib.odevio_microbench_ffma.restype = C.c_int32
     lib.odevio_microbench_ffma.argtypes = [C.c_int32, C.c_int32, _FP, C.POINTER(C.c_double), _FP]
-    if lib.odevio_version() != 1:
+    if lib.odevio_version() != ABI_VERSION:
         raise OdevioError("libodevio_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
@@ -97,7 +112,7 @@ def dptr(t, name="tensor"):
         raise OdevioError(f"{name} must be a CUDA tensor (odevio_b200 has no CPU path)")
     if not t.is_contiguous():
         raise OdevioError(f"{name} must be contiguous")
-    if t.dtype not in (torch.float32, torch.int32, torch.uint8):
+    if t.dtype not in (torch.float32, torch.int32, torch.int64, torch.uint8):
         raise OdevioError(f"{name} must be float32/int32, got {t.dtype}")
     return C.c_void_p(t.data_ptr())
 

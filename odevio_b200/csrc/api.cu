@@ -14,6 +14,12 @@ cudaError_t transpose_pack(const float* src, int N, int K, float* dst, int ldN, 
 cudaError_t bias_sum(const float* a, const float* b, float* dst, int n, cudaStream_t stream);
 cudaError_t launch_odernn_fwd(const FwdParams& prm, int rows_per_tile, int grid, size_t smem_bytes,
                               cudaStream_t stream);
+cudaError_t launch_odernn_bwd(const BwdParams& prm, int rows_per_tile, int grid, size_t smem_bytes,
+                              cudaStream_t stream);
+int wgrad_splits(long long M, int N, int K, int nsm);
+cudaError_t wgrad_linear(const float* G, int ldg, const float* A, int lda, long long M, int N, int K,
+                         float* dW0, float* dW1, int k_split, float* db0, float* db1, float* part, int nsm,
+                         cudaStream_t stream);
 
 namespace {
 
@@ -108,7 +114,8 @@ int sm_count() {
 
 // Everything derived from cfg: launch geometry, shared-memory carve-up, workspace offsets.
 struct OdePlan {
-  int RT, R, ncons, threads, ntiles, grid, nst, G;
+  int RT, R, ncons, threads, ntiles, grid, nst, G, nsm, CK;
+  size_t ckpt_head_bytes, ckpt_floats_per_tile;
   size_t bufA_floats, bufB_floats, stage_floats, smem_bytes;
   size_t off_Wode[kMaxLinears];                 // float offsets into the workspace
   size_t off_Wrnn[kMaxRnnLayers][4], off_brnn[kMaxRnnLayers][4];
@@ -168,6 +175,13 @@ int plan_odernn(const odevio_odernn_cfg& c, OdePlan& pl) {
     return true;
   };
   int rt = c.rows_per_tile;
+  if (c.save_checkpoints) {
+    // training: the backward kernel exists for 4- and 8-row tiles and the tanh-RNN jump
+    if (c.rnn_type != ODEVIO_RNN_TANH || c.endpoint_dense) return ODEVIO_E_ENUM;
+    if (c.ckpt_loops < 0 || c.ckpt_loops > 4096) return ODEVIO_E_SHAPE;
+    if (rt == 16) return ODEVIO_E_SHAPE;
+    if (rt == 0) rt = fit(8) ? 8 : 4;
+  }
   if (rt == 0) {
     // Tile height: 16-row tiles amortise the weight stream better (~1.6x the time of an 8-row
     // tile for 2x the rows) but halve the CTA count and need <= 3 column pairs per thread to
@@ -202,7 +216,86 @@ int plan_odernn(const odevio_odernn_cfg& c, OdePlan& pl) {
   pl.scratch_floats_per_cta = align_up(static_cast<size_t>(kMaxStages + 2) * c.D * pl.R, 64);
   pl.off_scratch = take(pl.scratch_floats_per_cta * pl.grid);
   pl.total_bytes = off * sizeof(float);
+  pl.nsm = nsm;
+  pl.CK = c.ckpt_loops > 0 ? c.ckpt_loops : (fixed ? c.substeps : 16);
+  pl.ckpt_head_bytes = align_up(static_cast<size_t>(pl.ntiles) * c.S * sizeof(int32_t), 256);
+  pl.ckpt_floats_per_tile = align_up(static_cast<size_t>(c.S) * ckpt_interval_floats(c.D, pl.R, pl.CK), 64);
   return 0;
+}
+
+// Backward: stages entering y1, shared-memory carve-up, workspace layout for `ode_rows` record rows.
+struct BwdPlan {
+  int ns, nst;
+  size_t buf_floats, stage_floats, smem_bytes;
+  size_t off_Wode[kMaxLinears], off_Wreg0;
+  size_t off_scratch, scratch_floats_per_cta;
+  size_t off_recA_ode[kMaxLinears], off_recG_ode[kMaxLinears];
+  size_t off_recA_rnn[kMaxRnnLayers], off_recG_rnn[kMaxRnnLayers];
+  size_t off_recA_reg0, off_recG_reg0, off_recA_reg1, off_recG_reg1;
+  size_t off_part, part_floats;
+  long long jump_rows;
+  size_t total_bytes;
+};
+
+int plan_odernn_bwd(const odevio_odernn_cfg& c, const OdePlan& pl, long long ode_rows, BwdPlan& bp) {
+  if (ode_rows < 0) return ODEVIO_E_SHAPE;
+  DevTableau tb;
+  if (!make_tableau(c.solver, tb)) return ODEVIO_E_ENUM;
+  bp.ns = tb.ssal ? tb.n_stages - 1 : tb.n_stages;
+  const int NL = c.n_hidden + 1;
+  const size_t maxdh = static_cast<size_t>(c.D > c.H ? c.D : c.H);
+  bp.buf_floats = maxdh * pl.R;
+  bp.stage_floats = pl.stage_floats;
+  const size_t fixed_bytes = (2 * bp.buf_floats + 2 * static_cast<size_t>(pl.R)) * sizeof(float) + 8 +
+                             2 * kMaxStagesRing * 8 + 128;
+  if (fixed_bytes + 2 * bp.stage_floats * sizeof(float) > kSmemLimit) return ODEVIO_E_SHAPE;
+  size_t nst = (kSmemLimit - fixed_bytes) / (bp.stage_floats * sizeof(float));
+  if (nst > kMaxStagesRing) nst = kMaxStagesRing;
+  bp.nst = static_cast<int>(nst);
+  bp.smem_bytes = fixed_bytes + nst * bp.stage_floats * sizeof(float);
+
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = align_up(off + n, 64); return o; };
+  for (int j = 0; j < NL; ++j) bp.off_Wode[j] = take(static_cast<size_t>(pl.Kode[j]) * pl.Node[j]);
+  bp.off_Wreg0 = take(static_cast<size_t>(c.D) * kRegHidden);
+  const size_t arr = static_cast<size_t>(c.D) * pl.R, harr = static_cast<size_t>(c.H) * pl.R;
+  bp.scratch_floats_per_cta = align_up((2 * kMaxStages + 1) * arr + static_cast<size_t>(kMaxStages) * (NL - 1) * harr, 64);
+  bp.off_scratch = take(bp.scratch_floats_per_cta * pl.grid);
+  const size_t M = static_cast<size_t>(ode_rows);
+  for (int j = 0; j < NL; ++j) {
+    bp.off_recA_ode[j] = take(M * pl.Kode[j]);
+    bp.off_recG_ode[j] = take(M * pl.Node[j]);
+  }
+  bp.jump_rows = static_cast<long long>(pl.ntiles) * c.S * pl.RT;
+  const size_t MJ = static_cast<size_t>(bp.jump_rows);
+  for (int l = 0; l < c.L; ++l) {
+    bp.off_recA_rnn[l] = take(MJ * 2 * c.D);
+    bp.off_recG_rnn[l] = take(MJ * c.D);
+  }
+  bp.off_recA_reg0 = take(MJ * c.D);
+  bp.off_recG_reg0 = take(MJ * kRegHidden);
+  bp.off_recA_reg1 = take(MJ * kRegHidden);
+  bp.off_recG_reg1 = take(MJ * 8);
+  // split-M partial buffer: the largest Linear's partials
+  size_t part = 0;
+  auto need = [&](long long m, int n, int k) {
+    size_t v = static_cast<size_t>(wgrad_splits(m, n, k, pl.nsm)) * n * k;
+    if (v < static_cast<size_t>(256) * n) v = static_cast<size_t>(256) * n;
+    if (v > part) part = v;
+  };
+  for (int j = 0; j < NL; ++j) need(ode_rows, pl.Node[j], pl.Kode[j]);
+  need(bp.jump_rows, c.D, 2 * c.D);
+  need(bp.jump_rows, kRegHidden, c.D);
+  need(bp.jump_rows, kPoseDim, kRegHidden);
+  bp.part_floats = part;
+  bp.off_part = take(part);
+  bp.total_bytes = off * sizeof(float);
+  return 0;
+}
+
+size_t ckpt_total_bytes(const odevio_odernn_cfg& c, const OdePlan& pl) {
+  (void)c;
+  return pl.ckpt_head_bytes + static_cast<size_t>(pl.ntiles) * pl.ckpt_floats_per_tile * sizeof(float);
 }
 
 #define ODEVIO_CUDA_TRY(expr)                                   \
@@ -243,6 +336,7 @@ void odevio_odernn_default_cfg(odevio_odernn_cfg* cfg) {
   cfg->accept_strict = 1; cfg->floor_factor = 0; cfg->endpoint_dense = 0; cfg->exact_landing = 1;
   cfg->max_steps = 100000;
   cfg->precision = ODEVIO_PRECISION_FP32;
+  cfg->ckpt_loops = 0;
 }
 
 size_t odevio_odernn_workspace_bytes(const odevio_odernn_cfg* cfg) {
@@ -256,14 +350,18 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
                               const float* fv, const float* fi, int32_t Dv,
                               const float* ts, const float* h0,
                               float* pose, float* hT, int32_t* stats, int32_t* status,
+                              void* ckpt, size_t ckpt_bytes,
                               void* workspace, size_t workspace_bytes, void* stream_) {
   if (!cfg || !w || !fv || !ts || !pose || !hT || !workspace) return ODEVIO_E_NULL;
+  if (cfg->save_checkpoints && !ckpt) return ODEVIO_E_NULL;
   const odevio_odernn_cfg& c = *cfg;
   OdePlan pl;
   const int rc = plan_odernn(c, pl);
   if (rc != 0) return rc;
   if (Dv <= 0 || Dv > c.D || (Dv < c.D && !fi) || (Dv == c.D && fi)) return ODEVIO_E_SHAPE;
   if (workspace_bytes < pl.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ODEVIO_E_WORKSPACE;
+  if (c.save_checkpoints && (ckpt_bytes < ckpt_total_bytes(c, pl) || (reinterpret_cast<uintptr_t>(ckpt) & 255)))
+    return ODEVIO_E_WORKSPACE;
   const int NL = c.n_hidden + 1;
   for (int j = 0; j < NL; ++j) if (!w->ode_w[j] || !w->ode_b[j]) return ODEVIO_E_NULL;
   for (int l = 0; l < c.L; ++l)
@@ -332,7 +430,123 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
   p.bufA_floats = static_cast<int>(pl.bufA_floats); p.bufB_floats = static_cast<int>(pl.bufB_floats);
   p.stage_floats = static_cast<int>(pl.stage_floats);
 
+  if (c.save_checkpoints) {
+    p.nloops = static_cast<int*>(ckpt);
+    p.ckpt = reinterpret_cast<float*>(static_cast<unsigned char*>(ckpt) + pl.ckpt_head_bytes);
+    p.ckpt_floats_per_tile = pl.ckpt_floats_per_tile;
+    p.CK = pl.CK;
+  }
+
   ODEVIO_CUDA_TRY(launch_odernn_fwd(p, pl.RT, pl.grid, pl.smem_bytes, stream));
+  return 0;
+}
+
+int32_t odevio_odernn_geometry(const odevio_odernn_cfg* cfg, int32_t* out) {
+  if (!cfg || !out) return ODEVIO_E_NULL;
+  OdePlan pl;
+  const int rc = plan_odernn(*cfg, pl);
+  if (rc != 0) return rc;
+  DevTableau tb;
+  if (!make_tableau(cfg->solver, tb)) return ODEVIO_E_ENUM;
+  out[0] = pl.RT; out[1] = pl.R; out[2] = pl.ntiles;
+  out[3] = tb.ssal ? tb.n_stages - 1 : tb.n_stages;
+  out[4] = pl.CK; out[5] = pl.grid; out[6] = 0; out[7] = 0;
+  return 0;
+}
+
+size_t odevio_odernn_ckpt_bytes(const odevio_odernn_cfg* cfg) {
+  if (!cfg) return 0;
+  OdePlan pl;
+  if (plan_odernn(*cfg, pl) != 0) return 0;
+  return ckpt_total_bytes(*cfg, pl);
+}
+
+size_t odevio_odernn_backward_workspace_bytes(const odevio_odernn_cfg* cfg, int64_t ode_rows) {
+  if (!cfg || !cfg->save_checkpoints) return 0;
+  OdePlan pl;
+  if (plan_odernn(*cfg, pl) != 0) return 0;
+  BwdPlan bp;
+  if (plan_odernn_bwd(*cfg, pl, ode_rows, bp) != 0) return 0;
+  return bp.total_bytes;
+}
+
+int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn_weights* w,
+                               const float* fv, const float* fi, int32_t Dv,
+                               const void* ckpt, size_t ckpt_bytes,
+                               const int64_t* rec_base, int64_t ode_rows,
+                               const float* grad_pose, const float* grad_hT,
+                               const odevio_odernn_grads* g, float* grad_fused, float* grad_h0,
+                               void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!cfg || !w || !fv || !ckpt || !rec_base || !grad_pose || !g || !workspace) return ODEVIO_E_NULL;
+  const odevio_odernn_cfg& c = *cfg;
+  if (!c.save_checkpoints) return ODEVIO_E_ENUM;
+  OdePlan pl;
+  int rc = plan_odernn(c, pl);
+  if (rc != 0) return rc;
+  BwdPlan bp;
+  rc = plan_odernn_bwd(c, pl, ode_rows, bp);
+  if (rc != 0) return rc;
+  if (Dv <= 0 || Dv > c.D || (Dv < c.D && !fi) || (Dv == c.D && fi)) return ODEVIO_E_SHAPE;
+  if (workspace_bytes < bp.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ODEVIO_E_WORKSPACE;
+  if (ckpt_bytes < ckpt_total_bytes(c, pl) || (reinterpret_cast<uintptr_t>(ckpt) & 255)) return ODEVIO_E_WORKSPACE;
+  const int NL = c.n_hidden + 1;
+  for (int j = 0; j < NL; ++j) if (!w->ode_w[j] || !w->ode_b[j] || !g->ode_w[j] || !g->ode_b[j]) return ODEVIO_E_NULL;
+  for (int l = 0; l < c.L; ++l)
+    if (!w->rnn_w_ih[l] || !w->rnn_w_hh[l] || !g->rnn_w_ih[l] || !g->rnn_w_hh[l] || !g->rnn_b_ih[l] || !g->rnn_b_hh[l])
+      return ODEVIO_E_NULL;
+  if (!w->reg_w0 || !w->reg_b0 || !w->reg_w1 || !g->reg_w0 || !g->reg_b0 || !g->reg_w1 || !g->reg_b1) return ODEVIO_E_NULL;
+
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* ws = static_cast<float*>(workspace);
+  const int D = c.D;
+  BwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = c.B; p.S = c.S; p.D = D; p.H = c.H; p.NL = NL; p.L = c.L;
+  p.act = c.activation; p.rnn_type = c.rnn_type;
+  if (!make_tableau(c.solver, p.tab)) return ODEVIO_E_ENUM;
+  p.ns = bp.ns;
+  for (int j = 0; j < NL; ++j) {
+    float* dst = ws + bp.off_Wode[j];
+    ODEVIO_CUDA_TRY(transpose_pack(w->ode_w[j], pl.Node[j], pl.Kode[j], dst, pl.Node[j], 0, 0, stream));
+    p.Wode[j] = dst; p.bode[j] = w->ode_b[j]; p.Kode[j] = pl.Kode[j]; p.Node[j] = pl.Node[j];
+    p.Wode_raw[j] = w->ode_w[j];
+    p.recA_ode[j] = ws + bp.off_recA_ode[j]; p.recG_ode[j] = ws + bp.off_recG_ode[j];
+  }
+  for (int l = 0; l < c.L; ++l) {
+    p.Wih_raw[l] = w->rnn_w_ih[l]; p.Whh_raw[l] = w->rnn_w_hh[l];
+    p.recA_rnn[l] = ws + bp.off_recA_rnn[l]; p.recG_rnn[l] = ws + bp.off_recG_rnn[l];
+  }
+  {
+    float* dst = ws + bp.off_Wreg0;
+    ODEVIO_CUDA_TRY(transpose_pack(w->reg_w0, kRegHidden, D, dst, kRegHidden, 0, 0, stream));
+    p.Wreg0 = dst; p.breg0 = w->reg_b0; p.Wreg0_raw = w->reg_w0; p.Wreg1 = w->reg_w1;
+  }
+  p.recA_reg0 = ws + bp.off_recA_reg0; p.recG_reg0 = ws + bp.off_recG_reg0;
+  p.recA_reg1 = ws + bp.off_recA_reg1; p.recG_reg1 = ws + bp.off_recG_reg1;
+  p.fv = fv; p.fi = fi; p.Dv = Dv;
+  p.gpose = grad_pose; p.ghT = grad_hT; p.gh0 = grad_h0; p.gfused = grad_fused;
+  p.nloops = static_cast<const int*>(ckpt);
+  p.ckpt = reinterpret_cast<const float*>(static_cast<const unsigned char*>(ckpt) + pl.ckpt_head_bytes);
+  p.ckpt_floats_per_tile = pl.ckpt_floats_per_tile; p.CK = pl.CK;
+  p.rec_base = reinterpret_cast<const long long*>(rec_base);
+  p.scratch = ws + bp.off_scratch; p.scratch_floats_per_cta = bp.scratch_floats_per_cta;
+  p.ntiles = pl.ntiles; p.nst = bp.nst;
+  p.buf_floats = static_cast<int>(bp.buf_floats); p.stage_floats = static_cast<int>(bp.stage_floats);
+
+  ODEVIO_CUDA_TRY(launch_odernn_bwd(p, pl.RT, pl.grid, bp.smem_bytes, stream));
+
+  // ---- deferred weight gradients: one dense GEMM per Linear over its record stream
+  float* part = ws + bp.off_part;
+  for (int j = 0; j < NL; ++j)
+    ODEVIO_CUDA_TRY(wgrad_linear(p.recG_ode[j], pl.Node[j], p.recA_ode[j], pl.Kode[j], ode_rows, pl.Node[j], pl.Kode[j],
+                                 g->ode_w[j], nullptr, 0, g->ode_b[j], nullptr, part, pl.nsm, stream));
+  for (int l = 0; l < c.L; ++l)
+    ODEVIO_CUDA_TRY(wgrad_linear(p.recG_rnn[l], D, p.recA_rnn[l], 2 * D, bp.jump_rows, D, 2 * D,
+                                 g->rnn_w_ih[l], g->rnn_w_hh[l], D, g->rnn_b_ih[l], g->rnn_b_hh[l], part, pl.nsm, stream));
+  ODEVIO_CUDA_TRY(wgrad_linear(p.recG_reg0, kRegHidden, p.recA_reg0, D, bp.jump_rows, kRegHidden, D,
+                               g->reg_w0, nullptr, 0, g->reg_b0, nullptr, part, pl.nsm, stream));
+  ODEVIO_CUDA_TRY(wgrad_linear(p.recG_reg1, 8, p.recA_reg1, kRegHidden, bp.jump_rows, kPoseDim, kRegHidden,
+                               g->reg_w1, nullptr, 0, g->reg_b1, nullptr, part, pl.nsm, stream));
   return 0;
 }
 

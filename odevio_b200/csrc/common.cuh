@@ -93,7 +93,7 @@ enum { ACT_TANH = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_SOFTPLUS = 3, ACT_NONE = 4
 // Deliberately NOT inlined: epilogues call it once per output element (a few dozen calls per
 // GEMM per thread), and inlining the tanh/exp/log1p bodies at every call site multiplied the
 // kernel's code size ~10x for no measurable gain.
-__device__ __noinline__ float apply_act(float v, int act) {
+static __device__ __noinline__ float apply_act(float v, int act) {
   switch (act) {
     case ACT_TANH: return tanhf(v);
     case ACT_RELU: return v > 0.f ? v : 0.f;
@@ -107,7 +107,7 @@ __device__ __noinline__ float apply_act(float v, int act) {
 
 // 4-wide variant used by the GEMM epilogues: one ABI call per float4, the four transcendental
 // chains inside interleave (ncu: the scalar calls were ~11 % of the fused kernel's warp time).
-__device__ __noinline__ float4 apply_act4(float4 v, int act) {
+static __device__ __noinline__ float4 apply_act4(float4 v, int act) {
   switch (act) {
     case ACT_TANH: return make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
     case ACT_RELU: return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));

@@ -1,0 +1,450 @@
+// Fused ODE-RNN regressor backward (discretise-then-optimise, step sizes constant).
+//
+// Replaces the arithmetic behind `loss.backward()` through (reference file:line)
+//   PoseODERNN.forward / evolve_state      src/models/PoseODERNN.py:88-123, :70-75
+//   torchode AutoDiffAdjoint (plain autograd through the solver loop), call site :58-60,74
+//   ODEFunc.forward                        src/models/ODEFunc.py:38-39
+//   nn.RNN single step                     src/models/PoseODERNN.py:114
+//   regressor head                         src/models/PoseODERNN.py:64-68,122
+// as driven by scripts/train_model.py:72-78.
+//
+// One persistent CTA per sequence tile, same geometry as the forward (R = RT x L rows, T-layout
+// [feature][R] tile arrays, weights streamed through the TMA ring of tile_gemm.cuh).  The forward
+// left, per interval, the tile state at the start of every solver iteration that accepted a step
+// (odernn_params.h: ckpt layout).  For every such iteration, in reverse:
+//   1. re-evaluate the step's stages k_j = f(z_j), keeping the hidden activations (per-CTA scratch);
+//   2. for j = ns-1 .. 0:  gk_j = dt (b_j gY + sum_{m>j} a_mj gz_m),  g = gk_j (1 - k_j^2),
+//      back through the MLP with the PyTorch-layout weights as K-major operand (W^T g needs no
+//      transposed copy), giving gz_j;  3. gY <- upd ? gY + sum_j gz_j : gY.
+// Weight gradients are NOT accumulated here: every Linear's (input row a, pre-activation gradient
+// row g) pair is appended to row-major record streams and reduced by wgrad.cu's dense GEMM.
+#include "odernn_params.h"
+#include "tile_gemm.cuh"
+
+namespace odevio {
+
+namespace {
+
+template <int RT>
+struct BCtx {
+  const BwdParams* prm;
+  TileThread th;
+  WeightRing ring;
+  RingPos pos;
+  float* bufA; float* bufB;
+  float* dt; int* upd;                 // shared [R]
+  float* K[kMaxStages]; float* GZ[kMaxStages]; float* GY; float* HS;   // per-CTA global scratch
+  int R, rq4, rq, tile;
+};
+
+__device__ __forceinline__ float4 mul4s(float4 a, float s) {
+  return make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
+}
+__device__ __forceinline__ float4 fma4s(float4 a, float s, float4 c) {
+  return make_float4(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z), fmaf(a.w, s, c.w));
+}
+
+// scatter a float4 (4 rows of feature d) into a row-major record stream
+__device__ __forceinline__ void rec_put4(float* rec, long long row0, int ld, int d, float4 v) {
+  float* p = rec + row0 * ld + d;
+  p[0] = v.x; p[ld] = v.y; p[2 * static_cast<size_t>(ld)] = v.z; p[3 * static_cast<size_t>(ld)] = v.w;
+}
+
+// z_j = y0 + dt * sum_{m<j} a_jm k_m  -> bufA (T-layout) and the layer-0 input record
+template <int RT>
+__device__ __forceinline__ void stage_input_b(BCtx<RT>& c, const float* Y0, int j, long long row0) {
+  if (c.th.producer) return;
+  const BwdParams& p = *c.prm;
+  const int nvec = p.D * c.rq4;
+  const float4 dt = ld4(c.dt + 4 * c.rq);
+  for (int e = c.th.ctid; e < nvec; e += c.th.ncons) {
+    const size_t off = static_cast<size_t>(e) * 4;
+    float4 y = ld4(Y0 + off);
+    if (j > 0) {
+      // same operation order as the forward (odernn_fwd.cu: wsum4 / axpy4) so z_j is bit-identical
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool any = false;
+      for (int m = 0; m < j; ++m) {
+        const float cj = p.tab.a[j][m];
+        if (cj == 0.f) continue;
+        const float4 k = ld4(c.K[m] + off);
+        if (!any) {
+          acc = make_float4(mul_(k.x, cj), mul_(k.y, cj), mul_(k.z, cj), mul_(k.w, cj));
+          any = true;
+        } else {
+          acc = make_float4(add_(acc.x, mul_(k.x, cj)), add_(acc.y, mul_(k.y, cj)),
+                            add_(acc.z, mul_(k.z, cj)), add_(acc.w, mul_(k.w, cj)));
+        }
+      }
+      if (any) y = make_float4(add_(y.x, mul_(dt.x, acc.x)), add_(y.y, mul_(dt.y, acc.y)),
+                               add_(y.z, mul_(dt.z, acc.z)), add_(y.w, mul_(dt.w, acc.w)));
+    }
+    st4(c.bufA + off, y);
+    const int d = e / c.rq4;
+    rec_put4(p.recA_ode[0], row0 + 4 * c.rq, p.D, d, y);
+  }
+  named_bar_sync(1, c.th.ncons);
+}
+
+// g = upd ? dt (b_j gY + sum_{m>j} a_mj gz_m) (1 - k_j^2) : 0   -> bufA and the last layer's G record
+template <int RT>
+__device__ __forceinline__ void stage_grad_b(BCtx<RT>& c, int j, long long row0) {
+  if (c.th.producer) return;
+  const BwdParams& p = *c.prm;
+  const int nvec = p.D * c.rq4;
+  const float4 dt = ld4(c.dt + 4 * c.rq);
+  const int4 up = *reinterpret_cast<const int4*>(c.upd + 4 * c.rq);
+  const int NLm1 = p.NL - 1;
+  for (int e = c.th.ctid; e < nvec; e += c.th.ncons) {
+    const size_t off = static_cast<size_t>(e) * 4;
+    float4 acc = mul4s(ld4(c.GY + off), p.tab.b[j]);
+    for (int m = j + 1; m < p.ns; ++m) {
+      const float a = p.tab.a[m][j];
+      if (a != 0.f) acc = fma4s(ld4(c.GZ[m] + off), a, acc);
+    }
+    const float4 k = ld4(c.K[j] + off);
+    float4 g;
+    g.x = up.x ? dt.x * acc.x * (1.f - k.x * k.x) : 0.f;
+    g.y = up.y ? dt.y * acc.y * (1.f - k.y * k.y) : 0.f;
+    g.z = up.z ? dt.z * acc.z * (1.f - k.z * k.z) : 0.f;
+    g.w = up.w ? dt.w * acc.w * (1.f - k.w * k.w) : 0.f;
+    st4(c.bufA + off, g);
+    const int d = e / c.rq4;
+    rec_put4(p.recG_ode[NLm1], row0 + 4 * c.rq, p.D, d, g);
+  }
+  named_bar_sync(1, c.th.ncons);
+}
+
+// gY <- upd ? gY + sum_j gz_j : gY
+template <int RT>
+__device__ __forceinline__ void iter_end_b(BCtx<RT>& c) {
+  if (c.th.producer) return;
+  const BwdParams& p = *c.prm;
+  const int nvec = p.D * c.rq4;
+  const int4 up = *reinterpret_cast<const int4*>(c.upd + 4 * c.rq);
+  for (int e = c.th.ctid; e < nvec; e += c.th.ncons) {
+    const size_t off = static_cast<size_t>(e) * 4;
+    const float4 g0 = ld4(c.GY + off);
+    float4 s = g0;
+    for (int j = 0; j < p.ns; ++j) {
+      const float4 z = ld4(c.GZ[j] + off);
+      s.x += z.x; s.y += z.y; s.z += z.z; s.w += z.w;
+    }
+    st4(c.GY + off, make_float4(up.x ? s.x : g0.x, up.y ? s.y : g0.y, up.z ? s.z : g0.z, up.w ? s.w : g0.w));
+  }
+  named_bar_sync(1, c.th.ncons);
+}
+
+struct GemmOpB {
+  const float* W; int K; int N;
+  const float* in; bool ode_layout;
+  Epilogue epi;
+};
+
+enum { BP_HEAD1 = 0, BP_HEAD2, BP_JUMP_A, BP_JUMP_B, BP_ITER, BP_RSTAGE, BP_RLAYER, BP_BSTAGE, BP_BLAYER,
+       BP_ITER_END, BP_TILE_END };
+
+}  // namespace
+
+template <int RT, int LL>
+__global__ void __launch_bounds__(128 * LL + 32, 1)
+odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BCtx<RT> c;
+  c.prm = &prm;
+  const BwdParams& p = prm;
+  const int tid = threadIdx.x;
+  constexpr int ncons = 128 * LL;
+  constexpr int R = RT * LL;
+  c.th.ncons = ncons;
+  c.th.lane = tid & 31;
+  c.th.producer = tid >= ncons;
+  c.th.ctid = c.th.producer ? 0 : tid;
+  c.R = R; c.rq4 = R / 4; c.rq = c.th.ctid % (R / 4);
+
+  float* sm = reinterpret_cast<float*>(smem_raw);
+  c.bufA = sm; sm += prm.buf_floats;
+  c.bufB = sm; sm += prm.buf_floats;
+  float* stages = sm; sm += static_cast<size_t>(prm.nst) * prm.stage_floats;
+  c.dt = sm; sm += R;
+  c.upd = reinterpret_cast<int*>(sm); sm += R;
+  uintptr_t bp = (reinterpret_cast<uintptr_t>(sm) + 7) & ~static_cast<uintptr_t>(7);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bp);
+  c.ring.buf = stages;
+  c.ring.buf_off = static_cast<uint32_t>(reinterpret_cast<unsigned char*>(stages) - smem_raw);
+  c.ring.full = bars;
+  c.ring.empty = bars + MAX_STAGES;
+  c.ring.stage_floats = prm.stage_floats;
+  c.ring.nst = prm.nst;
+  c.pos.stage = 0; c.pos.phase = 0; c.pos.ready = 0;
+  if (tid == 0) {
+    for (int s = 0; s < prm.nst; ++s) {
+      mbar_init(&c.ring.full[s], 1);
+      mbar_init(&c.ring.empty[s], ncons / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int D = prm.D, H = prm.H, NL = prm.NL, S = prm.S;
+  const size_t arr = static_cast<size_t>(D) * R;
+  const size_t harr = static_cast<size_t>(H) * R;
+  float* sc = prm.scratch + static_cast<size_t>(blockIdx.x) * prm.scratch_floats_per_cta;
+  for (int j = 0; j < kMaxStages; ++j) { c.K[j] = sc + j * arr; c.GZ[j] = sc + (kMaxStages + j) * arr; }
+  c.GY = sc + 2 * kMaxStages * arr;
+  c.HS = c.GY + arr;                       // HS[(j * (NL-1) + lam) * harr]
+  const size_t ivf = ckpt_interval_floats(D, R, prm.CK);
+
+  for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+    c.tile = tile;
+    const int nvalid = min(RT, prm.B - tile * RT);
+    const float* ck_tile = prm.ckpt + static_cast<size_t>(tile) * prm.ckpt_floats_per_tile;
+    // ---- gY <- grad of the final hidden state
+    if (!c.th.producer) {
+      for (int e = c.th.ctid; e < D * R; e += ncons) {
+        const int r = e / D, d = e - r * D;
+        const int l = r / RT, b = tile * RT + (r % RT);
+        float v = 0.f;
+        if (prm.ghT && b < prm.B) v = prm.ghT[(static_cast<size_t>(l) * prm.B + b) * D + d];
+        c.GY[static_cast<size_t>(d) * R + r] = v;
+      }
+    }
+    __syncthreads();
+
+    int ph = BP_HEAD1;
+    int i = S - 1, l = 0, it = 0, j = 0, lam = 0;
+    float* lin = c.bufA; float* lout = c.bufB;
+    const float* Y0 = nullptr;
+    long long row_it = 0;                 // first ODE-stream row of the current iteration
+    while (ph != BP_TILE_END) {
+      GemmOpB op{};
+      bool do_gemm = false;
+      const float* ck_iv = ck_tile + static_cast<size_t>(i) * ivf;
+      const float* Yend = ck_iv; const float* Ypost = ck_iv + arr;
+      const long long rowJ = (static_cast<long long>(tile) * S + i) * RT;     // jump / head stream row
+      switch (ph) {
+        case BP_HEAD1: {
+          // regressor hidden recomputed from the top layer's post-jump state
+          if (!c.th.producer) {
+            for (int e = c.th.ctid; e < D * RT; e += ncons) {
+              const int m = e / D, d = e - m * D;
+              const float v = Ypost[static_cast<size_t>(d) * R + (LL - 1) * RT + m];
+              c.bufB[d * RT + m] = v;
+              p.recA_reg0[(rowJ + m) * D + d] = v;
+            }
+            named_bar_sync(1, ncons);
+          }
+          op.W = p.Wreg0; op.K = D; op.N = kRegHidden; op.in = c.bufB; op.ode_layout = false;
+          op.epi.mode = EPI_STORE; op.epi.bias = p.breg0; op.epi.act = ACT_LEAKY01;
+          op.epi.out0 = c.bufA; op.epi.ld0 = RT;
+          op.epi.rec = p.recA_reg1; op.epi.rec_row0 = rowJ; op.epi.rec_ld = kRegHidden;
+          op.epi.rec_rstride = 1; op.epi.rec_valid = RT;
+          do_gemm = true;
+          ph = BP_HEAD2;
+          break;
+        }
+        case BP_HEAD2: {
+          if (!c.th.producer) {
+            for (int e = c.th.ctid; e < kRegHidden * RT; e += ncons) {
+              const int k = e / RT, m = e - k * RT;
+              const int b = tile * RT + m;
+              float ga = 0.f;
+              if (b < p.B) {
+                const float* gp = p.gpose + (static_cast<size_t>(b) * S + i) * kPoseDim;
+#pragma unroll
+                for (int o = 0; o < kPoseDim; ++o) ga = fmaf(p.Wreg1[o * kRegHidden + k], gp[o], ga);
+              }
+              const float a = c.bufA[k * RT + m];
+              const float gz = ga * (a > 0.f ? 1.f : 0.1f);
+              c.bufA[k * RT + m] = gz;
+              p.recG_reg0[(rowJ + m) * kRegHidden + k] = gz;
+            }
+            if (c.th.ctid < RT * 8) {
+              const int m = c.th.ctid / 8, o = c.th.ctid - m * 8;
+              const int b = tile * RT + m;
+              float v = 0.f;
+              if (b < p.B && o < kPoseDim) v = p.gpose[(static_cast<size_t>(b) * S + i) * kPoseDim + o];
+              p.recG_reg1[(rowJ + m) * 8 + o] = v;
+            }
+            named_bar_sync(1, ncons);
+          }
+          op.W = p.Wreg0_raw; op.K = kRegHidden; op.N = D; op.in = c.bufA; op.ode_layout = false;
+          op.epi.mode = EPI_ADD; op.epi.act = ACT_NONE;
+          op.epi.out0 = c.GY; op.epi.ld0 = R; op.epi.off0 = (LL - 1) * RT;
+          do_gemm = true;
+          l = LL - 1;
+          ph = BP_JUMP_A;
+          break;
+        }
+        case BP_JUMP_A: {
+          // dpre = gh' (1 - h'^2);  records of the jump Linear ([x ; h^-] -> h')
+          if (!c.th.producer) {
+            for (int e = c.th.ctid; e < D * RT; e += ncons) {
+              const int m = e / D, d = e - m * D;
+              const size_t o = static_cast<size_t>(d) * R + l * RT + m;
+              const float hp = Ypost[o];
+              const float dpre = c.GY[o] * (1.f - hp * hp);
+              c.bufA[d * RT + m] = dpre;
+              p.recG_rnn[l][(rowJ + m) * D + d] = dpre;
+              float x;
+              if (l == 0) {
+                const int b = tile * RT + m;
+                x = 0.f;
+                if (b < p.B) {
+                  const size_t row = static_cast<size_t>(b) * S + i;
+                  x = (d < p.Dv) ? p.fv[row * p.Dv + d] : p.fi[row * (D - p.Dv) + (d - p.Dv)];
+                }
+              } else {
+                x = Ypost[static_cast<size_t>(d) * R + (l - 1) * RT + m];
+              }
+              float* ra = p.recA_rnn[l] + (rowJ + m) * (2 * static_cast<size_t>(D));
+              ra[d] = x;
+              ra[D + d] = Yend[o];
+            }
+            named_bar_sync(1, ncons);
+          }
+          op.W = p.Whh_raw[l]; op.K = D; op.N = D; op.in = c.bufA; op.ode_layout = false;
+          op.epi.mode = EPI_STORE; op.epi.act = ACT_NONE;
+          op.epi.out0 = c.GY; op.epi.ld0 = R; op.epi.off0 = l * RT;      // gradient of the interval's end state
+          do_gemm = true;
+          ph = BP_JUMP_B;
+          break;
+        }
+        case BP_JUMP_B: {
+          op.W = p.Wih_raw[l]; op.K = D; op.N = D; op.in = c.bufA; op.ode_layout = false;
+          op.epi.act = ACT_NONE;
+          if (l > 0) {
+            op.epi.mode = EPI_ADD; op.epi.out0 = c.GY; op.epi.ld0 = R; op.epi.off0 = (l - 1) * RT;
+          } else {
+            op.epi.mode = EPI_STORE; op.epi.out0 = nullptr;
+            if (p.gfused) {
+              op.epi.rec = p.gfused; op.epi.rec_row0 = static_cast<long long>(tile) * RT * S + i;
+              op.epi.rec_ld = D; op.epi.rec_rstride = S; op.epi.rec_valid = nvalid;
+            }
+          }
+          do_gemm = (l > 0) || (p.gfused != nullptr);
+          if (--l < 0) { it = p.nloops[static_cast<size_t>(tile) * S + i] - 1; ph = BP_ITER; }
+          else ph = BP_JUMP_A;
+          break;
+        }
+        case BP_ITER: {
+          if (it < 0) {
+            ph = (--i >= 0) ? BP_HEAD1 : BP_TILE_END;
+            break;
+          }
+          const float* slot = ck_iv + 2 * arr + static_cast<size_t>(it) * (arr + 2 * R);
+          Y0 = slot;
+          __syncthreads();      // previous users of dt / upd are done
+          if (!c.th.producer && c.th.ctid < R) {
+            c.dt[c.th.ctid] = slot[arr + c.th.ctid];
+            c.upd[c.th.ctid] = reinterpret_cast<const int*>(slot + arr + R)[c.th.ctid];
+          }
+          __syncthreads();
+          row_it = p.rec_base[static_cast<size_t>(tile) * S + i] + static_cast<long long>(it) * p.ns * R;
+          j = 0;
+          ph = BP_RSTAGE;
+          break;
+        }
+        case BP_RSTAGE:
+          stage_input_b<RT>(c, Y0, j, row_it + static_cast<long long>(j) * R);
+          lam = 0; lin = c.bufA; lout = c.bufB;
+          ph = BP_RLAYER;
+          break;
+        case BP_RLAYER: {
+          op.W = p.Wode[lam]; op.K = p.Kode[lam]; op.N = p.Node[lam];
+          op.in = lin; op.ode_layout = true;
+          op.epi.mode = EPI_STORE; op.epi.bias = p.bode[lam]; op.epi.ld0 = R;
+          if (lam == NL - 1) {
+            op.epi.act = ACT_TANH; op.epi.out0 = c.K[j];
+          } else {
+            op.epi.act = p.act; op.epi.out0 = lout;
+            op.epi.out1 = c.HS + (static_cast<size_t>(j) * (NL - 1) + lam) * harr; op.epi.ld1 = R;
+            op.epi.rec = p.recA_ode[lam + 1]; op.epi.rec_row0 = row_it + static_cast<long long>(j) * R;
+            op.epi.rec_ld = H; op.epi.rec_rstride = 1; op.epi.rec_valid = RT;
+          }
+          do_gemm = true;
+          float* t = lin; lin = lout; lout = t;
+          if (++lam == NL) {
+            if (++j < p.ns) ph = BP_RSTAGE;
+            else { j = p.ns - 1; ph = BP_BSTAGE; }
+          }
+          break;
+        }
+        case BP_BSTAGE:
+          stage_grad_b<RT>(c, j, row_it + static_cast<long long>(j) * R);
+          lam = NL - 1; lin = c.bufA; lout = c.bufB;
+          ph = BP_BLAYER;
+          break;
+        case BP_BLAYER: {
+          // g_{lam-1} = (W_lam^T g_lam) * act'(h_{lam-1});  the PyTorch [out][in] weight is the K-major operand
+          op.W = p.Wode_raw[lam]; op.K = p.Node[lam]; op.N = p.Kode[lam];
+          op.in = lin; op.ode_layout = true; op.epi.ld0 = R;
+          if (lam > 0) {
+            op.epi.mode = EPI_MUL_DACT; op.epi.act = p.act;
+            op.epi.hs = c.HS + (static_cast<size_t>(j) * (NL - 1) + (lam - 1)) * harr; op.epi.ldh = R;
+            op.epi.out0 = lout;
+            op.epi.rec = p.recG_ode[lam - 1]; op.epi.rec_row0 = row_it + static_cast<long long>(j) * R;
+            op.epi.rec_ld = H; op.epi.rec_rstride = 1; op.epi.rec_valid = RT;
+          } else {
+            op.epi.mode = EPI_STORE; op.epi.act = ACT_NONE; op.epi.out0 = c.GZ[j];
+          }
+          do_gemm = true;
+          float* t = lin; lin = lout; lout = t;
+          if (--lam < 0) ph = (--j >= 0) ? BP_BSTAGE : BP_ITER_END;
+          break;
+        }
+        case BP_ITER_END:
+          iter_end_b<RT>(c);
+          --it;
+          ph = BP_ITER;
+          break;
+        default:
+          ph = BP_TILE_END;
+          break;
+      }
+      if (do_gemm) tile_gemm<RT, LL>(c.ring, c.pos, c.th, op.W, op.K, op.N, op.in, op.ode_layout, op.epi);
+    }
+
+    // ---- gradient of the initial hidden state
+    __syncthreads();
+    if (!c.th.producer && prm.gh0) {
+      for (int e = c.th.ctid; e < D * R; e += ncons) {
+        const int r = e / D, d = e - r * D;
+        const int l2 = r / RT, b = tile * RT + (r % RT);
+        if (b < prm.B) prm.gh0[(static_cast<size_t>(l2) * prm.B + b) * D + d] = c.GY[static_cast<size_t>(d) * R + r];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int RT, int LL>
+static cudaError_t launch_one_b(const BwdParams& prm, int grid, size_t smem_bytes, cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(odernn_bwd_kernel<RT, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem_bytes));
+  if (err != cudaSuccess) return err;
+  odernn_bwd_kernel<RT, LL><<<grid, 128 * LL + 32, smem_bytes, stream>>>(prm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_odernn_bwd(const BwdParams& prm, int rows_per_tile, int grid, size_t smem_bytes,
+                              cudaStream_t stream) {
+  if (rows_per_tile == 4) {
+    switch (prm.L) {
+      case 1: return launch_one_b<4, 1>(prm, grid, smem_bytes, stream);
+      case 2: return launch_one_b<4, 2>(prm, grid, smem_bytes, stream);
+      case 3: return launch_one_b<4, 3>(prm, grid, smem_bytes, stream);
+      case 4: return launch_one_b<4, 4>(prm, grid, smem_bytes, stream);
+    }
+  } else if (rows_per_tile == 8) {
+    switch (prm.L) {
+      case 1: return launch_one_b<8, 1>(prm, grid, smem_bytes, stream);
+      case 2: return launch_one_b<8, 2>(prm, grid, smem_bytes, stream);
+      case 3: return launch_one_b<8, 3>(prm, grid, smem_bytes, stream);
+      case 4: return launch_one_b<8, 4>(prm, grid, smem_bytes, stream);
+    }
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace odevio

@@ -355,6 +355,15 @@ __device__ __forceinline__ void pose_out(Ctx<RT>& c, int i) {
   }
 }
 
+// Training checkpoints: copy a T-layout tile array (consumers; same element->thread mapping as the
+// elementwise passes, so no barrier is needed against them).
+template <int RT>
+__device__ __forceinline__ void copy_tile(const Ctx<RT>& c, float* dst, const float* src) {
+  if (c.th.producer) return;
+  const int nvec = c.prm->D * c.rq4;
+  for (int e = c.th.ctid; e < nvec; e += c.th.ncons) st4(dst + static_cast<size_t>(e) * 4, ld4(src + static_cast<size_t>(e) * 4));
+}
+
 // One GEMM of the tile program.
 struct GemmOp {
   const float* W; int K; int N;
@@ -446,18 +455,22 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
     __syncthreads();
 
     int ph = PH_INTERVAL;
-    int i = 0, st = 0, j = 0, l = 0, g = 0, loops = 0, any_running = 0;
+    int i = 0, st = 0, j = 0, l = 0, g = 0, loops = 0, any_running = 0, nsaved = 0;
+    float* const ck_tile = prm.ckpt ? prm.ckpt + static_cast<size_t>(tile) * prm.ckpt_floats_per_tile : nullptr;
+    float* ck_iv = nullptr;
     bool have_k0 = false;
     float* lin = c.bufA;      // ping-pong buffers of the vector-field MLP
     float* lout = c.bufB;
     while (ph != PH_TILE_END) {
-      GemmOp op;
+      GemmOp op{};
       bool do_gemm = false;
       switch (ph) {
         case PH_INTERVAL: {
           const int run = interval_begin<RT>(c, i);
           any_running = __syncthreads_or(run);
           loops = 0; have_k0 = false;
+          nsaved = 0;
+          ck_iv = ck_tile ? ck_tile + static_cast<size_t>(i) * ckpt_interval_floats(D, R, p.CK) : nullptr;
           if (any_running) {
             ph = PH_STEP_BEGIN;
           } else {
@@ -497,8 +510,37 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
             error_pass<RT>(c);
             const int run = controller<RT>(c, loops, i);
             any_running = __syncthreads_or(run);
+            if (ck_iv) {
+              const int upd = (!c.th.producer && c.th.ctid < R) ? rs.upd[c.th.ctid] : 0;
+              if (__syncthreads_or(upd)) {            // iterations that reject every row leave no trace
+                if (nsaved < p.CK) {
+                  float* slot = ck_iv + 2 * arr + static_cast<size_t>(nsaved) * (arr + 2 * R);
+                  copy_tile<RT>(c, slot, c.Y);
+                  if (!c.th.producer && c.th.ctid < R) {
+                    slot[arr + c.th.ctid] = rs.dtstep[c.th.ctid];
+                    reinterpret_cast<int*>(slot + arr + R)[c.th.ctid] = rs.upd[c.th.ctid];
+                  }
+                  ++nsaved;
+                } else if (!c.th.producer && c.th.ctid < R) {
+                  rs.status[c.th.ctid] = max(rs.status[c.th.ctid], 3);     // checkpoint overflow
+                }
+              }
+            }
             commit_pass<RT>(c);
           } else {
+            if (ck_iv) {
+              if (nsaved < p.CK) {
+                float* slot = ck_iv + 2 * arr + static_cast<size_t>(nsaved) * (arr + 2 * R);
+                copy_tile<RT>(c, slot, c.Y);
+                if (!c.th.producer && c.th.ctid < R) {
+                  slot[arr + c.th.ctid] = rs.dt[c.th.ctid];
+                  reinterpret_cast<int*>(slot + arr + R)[c.th.ctid] = 1;
+                }
+                ++nsaved;
+              } else if (!c.th.producer && c.th.ctid < R) {
+                rs.status[c.th.ctid] = max(rs.status[c.th.ctid], 3);
+              }
+            }
             fixed_commit<RT>(c);
             if (!c.th.producer && c.th.ctid < R) { rs.nsteps[c.th.ctid] += 1; rs.nacc[c.th.ctid] += 1; }
             any_running = loops < p.substeps;
@@ -513,6 +555,10 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
           break;
         }
         case PH_JUMP: {
+          if (ck_iv && l == 0 && g == 0) {           // state at the end of the interval's solves
+            copy_tile<RT>(c, ck_iv, c.Y);
+            if (tid == 0) p.nloops[static_cast<size_t>(tile) * p.S + i] = nsaved;
+          }
           // RNN: one GEMM per layer on [x ; h] (K = 2D).  GRU: r, z (K = 2D), hn (h half), new gate
           // (x half) -- PyTorch gate order (r, z, n).
           if (g == 0) assemble_jump_input<RT>(c, i, l);
@@ -542,6 +588,7 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
           break;
         }
         case PH_REG: {
+          if (ck_iv) copy_tile<RT>(c, ck_iv + arr, c.Y);      // post-jump state
           // pose head on the top layer's output (bufB, [D][RT]): Linear(D,128) + LeakyReLU(0.1)
           op.W = p.Wreg0; op.K = D; op.N = kRegHidden; op.in = c.bufB; op.ode_layout = false;
           op.epi.mode = EPI_STORE; op.epi.bias = p.breg0; op.epi.act = ACT_LEAKY01;

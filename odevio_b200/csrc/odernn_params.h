@@ -54,6 +54,51 @@ struct FwdParams {
   // launch geometry
   int ntiles, nst;
   int bufA_floats, bufB_floats, stage_floats;
+  // training checkpoints (nullptr: inference).  Per tile, per interval i (T-layout arrays of D*R floats):
+  //   [Yend | Ypost | CK x (Y0 | dt[R] | upd[R])]; nloops[tile * S + i] = stored solver iterations
+  float* ckpt; int* nloops; size_t ckpt_floats_per_tile; int CK;
+};
+
+inline __host__ __device__ size_t ckpt_interval_floats(int D, int R, int CK) {
+  return static_cast<size_t>(2) * D * R + static_cast<size_t>(CK) * (static_cast<size_t>(D) * R + 2 * R);
+}
+
+// Backward kernel parameters (odernn_bwd.cu).
+struct BwdParams {
+  int B, S, D, H, NL, L;
+  int act, rnn_type;
+  DevTableau tab;
+  int ns;                                    // stages that enter y1 (n_stages - 1 for FSAL/SSAL tableaus)
+  // forward-packed (K-major) weights for the stage re-evaluation
+  const float* Wode[kMaxLinears];
+  const float* bode[kMaxLinears];
+  int Kode[kMaxLinears], Node[kMaxLinears];
+  // PyTorch-layout [out][in] weights: the K-major operand of the transposed products W^T g
+  const float* Wode_raw[kMaxLinears];
+  const float* Wih_raw[kMaxRnnLayers];
+  const float* Whh_raw[kMaxRnnLayers];
+  const float* Wreg0;      // packed [D][128]
+  const float* breg0;
+  const float* Wreg0_raw;  // [128][D]
+  const float* Wreg1;      // [6][128]
+  // io
+  const float* fv; const float* fi; int Dv;
+  const float* gpose;      // [B,S,6]
+  const float* ghT;        // [L,B,D] or nullptr
+  float* gh0;              // [L,B,D]
+  float* gfused;           // [B,S,D] or nullptr
+  // checkpoints written by the forward
+  const float* ckpt; const int* nloops; size_t ckpt_floats_per_tile; int CK;
+  // record streams (row-major) for the deferred weight-gradient GEMMs
+  const long long* rec_base;                 // [ntiles * S] first ODE-stream row of (tile, interval)
+  float* recA_ode[kMaxLinears]; float* recG_ode[kMaxLinears];     // [M][K_j], [M][N_j]
+  float* recA_rnn[kMaxRnnLayers]; float* recG_rnn[kMaxRnnLayers]; // [ntiles*S*RT][2D], [..][D]
+  float* recA_reg0; float* recG_reg0;        // [ntiles*S*RT][D], [..][128]
+  float* recA_reg1; float* recG_reg1;        // [ntiles*S*RT][128], [..][8] (6 used)
+  // per-CTA scratch: K[7], GZ[7], GY (D*R each), HS[7][NL-1] (H*R each)
+  float* scratch; size_t scratch_floats_per_cta;
+  int ntiles, nst;
+  int buf_floats, stage_floats;
 };
 
 }  // namespace odevio

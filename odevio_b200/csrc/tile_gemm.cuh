@@ -60,16 +60,36 @@ struct TileThread {
 
 // Epilogue description: v = act(acc + bias[n]) stored to up to two T-layout destinations, or the
 // GRU new-gate combination.
-enum { EPI_STORE = 0, EPI_GRU_NEW = 1 };
+//   EPI_STORE     v = act(acc + bias[n])
+//   EPI_GRU_NEW   n = tanh(acc + bias + hn * r);  h' = (hprev - n) * z + n   (ATen gru_cell order)
+//   EPI_MUL_DACT  v = acc * act'(hs[n])      backward through a hidden activation; act' is computed
+//                                            from the saved activation OUTPUT hs (T-layout)
+//   EPI_ADD       v = acc + out0[n]          accumulate into an existing T-layout gradient
+// Optionally the value is also appended to a row-major record stream (one row per tile row):
+//   rec[(rec_row0 + (rb * RT + r) * rec_rstride) * rec_ld + n]   for r < rec_valid.
+enum { EPI_STORE = 0, EPI_GRU_NEW = 1, EPI_MUL_DACT = 2, EPI_ADD = 3 };
 struct Epilogue {
   int mode;
   const float* bias;   // [N] or nullptr
   int act;
-  float* out0; int ld0; int off0;   // out0[n * ld0 + off0 + rb * RT + r]   (shared or global)
+  float* out0; int ld0; int off0;   // out0[n * ld0 + off0 + rb * RT + r]   (shared or global); may be null
   float* out1; int ld1; int off1;   // optional second destination
-  // EPI_GRU_NEW: n = tanh(acc + bias + hn * r);  h' = (hprev - n) * z + n   (ATen gru_cell order)
-  const float* rg; const float* zg; const float* hn; const float* hprev;   // [N][RT]
+  const float* rg; const float* zg; const float* hn; const float* hprev;   // EPI_GRU_NEW: [N][RT]
+  const float* hs; int ldh; int offh;                                       // EPI_MUL_DACT
+  float* rec; long long rec_row0; int rec_ld; int rec_rstride; int rec_valid;
 };
+
+// act'(x) expressed through the activation output h = act(x)
+__device__ __forceinline__ float dact_from_output(float h, int act) {
+  switch (act) {
+    case ACT_TANH: return 1.f - h * h;
+    case ACT_RELU: return h > 0.f ? 1.f : 0.f;
+    case ACT_LEAKY: return h > 0.f ? 1.f : 0.01f;
+    case ACT_SOFTPLUS: return 1.f - expf(-h);     // sigmoid(x) with h = log(1 + e^x)
+    case ACT_LEAKY01: return h > 0.f ? 1.f : 0.1f;
+    default: return 1.f;
+  }
+}
 
 // One lane of the producer warp: stream Wt[K][N] in KC-row chunks.
 __device__ __forceinline__ void pipe_produce(const WeightRing& ring, RingPos& pos,
@@ -102,17 +122,43 @@ __device__ __forceinline__ void run_epilogue(const Epilogue& e, int n, int rb, c
                                                acc[4 * q + 3] + b), e.act);
       v[4 * q] = a4.x; v[4 * q + 1] = a4.y; v[4 * q + 2] = a4.z; v[4 * q + 3] = a4.w;
     }
-  } else {
+  } else if (e.mode == EPI_GRU_NEW) {
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       const size_t o = static_cast<size_t>(n) * RT + r;
       const float ng = apply_act((acc[r] + b) + e.hn[o] * e.rg[o], ACT_TANH);
       v[r] = (e.hprev[o] - ng) * e.zg[o] + ng;
     }
-  }
-  float* p0 = e.out0 + static_cast<size_t>(n) * e.ld0 + e.off0 + rb * RT;
+  } else if (e.mode == EPI_MUL_DACT) {
+    const float* hp = e.hs + static_cast<size_t>(n) * e.ldh + e.offh + rb * RT;
 #pragma unroll
-  for (int q = 0; q < RT / 4; ++q) st4(p0 + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    for (int q = 0; q < RT / 4; ++q) {
+      const float4 h4 = ld4(hp + 4 * q);
+      v[4 * q] = acc[4 * q] * dact_from_output(h4.x, e.act);
+      v[4 * q + 1] = acc[4 * q + 1] * dact_from_output(h4.y, e.act);
+      v[4 * q + 2] = acc[4 * q + 2] * dact_from_output(h4.z, e.act);
+      v[4 * q + 3] = acc[4 * q + 3] * dact_from_output(h4.w, e.act);
+    }
+  } else {   // EPI_ADD
+    const float* op = e.out0 + static_cast<size_t>(n) * e.ld0 + e.off0 + rb * RT;
+#pragma unroll
+    for (int q = 0; q < RT / 4; ++q) {
+      const float4 o4 = ld4(op + 4 * q);
+      v[4 * q] = acc[4 * q] + o4.x; v[4 * q + 1] = acc[4 * q + 1] + o4.y;
+      v[4 * q + 2] = acc[4 * q + 2] + o4.z; v[4 * q + 3] = acc[4 * q + 3] + o4.w;
+    }
+  }
+  if (e.rec) {
+    float* rp = e.rec + (e.rec_row0 + static_cast<long long>(rb * RT) * e.rec_rstride) * e.rec_ld + n;
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+      if (r < e.rec_valid) rp[static_cast<long long>(r) * e.rec_rstride * e.rec_ld] = v[r];
+  }
+  if (e.out0) {
+    float* p0 = e.out0 + static_cast<size_t>(n) * e.ld0 + e.off0 + rb * RT;
+#pragma unroll
+    for (int q = 0; q < RT / 4; ++q) st4(p0 + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+  }
   if (e.out1) {
     float* p1 = e.out1 + static_cast<size_t>(n) * e.ld1 + e.off1 + rb * RT;
 #pragma unroll

@@ -22,6 +22,11 @@ defaults; ``getattr(opt, name, default)``):
   ode_endpoint="y1" | "dense", ode_exact_landing=True   ("dense"/False = literal fp32 torchode
                         arithmetic, which is ill-conditioned; see oracle/torchode_like.py)
   ode_rows_per_tile=0   (auto) | 4 | 8 | 16
+  ode_ckpt_loops=0      training: stored solver iterations per interval and tile (0 = 16)
+
+Training: with grad enabled, ``forward`` goes through ``odevio_b200.autograd`` -- the fused
+forward with checkpoints, then ``odevio_odernn_backward`` (discretise-then-optimise, step sizes
+constant; reference: autograd through torchode's AutoDiffAdjoint, scripts/train_model.py:78).
 """
 
 import ctypes as C
@@ -155,6 +160,7 @@ class PoseODERNN(nn.Module):
         self.rows_per_tile = int(getattr(opt, "ode_rows_per_tile", 0))
         self.collect_stats = bool(getattr(opt, "ode_collect_stats", True))
         self.trace_steps = int(getattr(opt, "ode_trace_steps", 0))   # diagnostic: (dt, ratio) of first T steps
+        self.ckpt_loops = int(getattr(opt, "ode_ckpt_loops", 0))     # training: stored solver iterations per interval (0 = 16)
         self.last_stats = None      # int32 [S, L, B, 2] = (n_steps, n_accepted) of the last forward
         self.last_trace = None      # float32 [S, L, B, T, 2] = (dt, error ratio) when trace_steps = T > 0
         self.last_status = None     # int32 [B]
@@ -222,32 +228,54 @@ class PoseODERNN(nn.Module):
         w.reg_b1 = ptr(self.regressor[2].bias, "regressor.2.bias")
         return w, keep
 
-    def forward(self, fv, fi, ts, prev=None, do_profile=False):
-        lib = _lib.load()
+    def _prepare_inputs(self, fv, fi, ts, prev):
+        """Reference pre-processing (PoseODERNN.py:93-100): fusion, ts - ts[:, :1] without prev."""
         if not fv.is_cuda:
             raise _lib.OdevioError("PoseODERNN.forward needs CUDA tensors: odevio_b200 has no CPU path")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            # training goes through the autograd wrapper once the fused backward is built
-            from .autograd import odernn_apply
-            return odernn_apply(self, fv, fi, ts, prev)
-        return self._forward_impl(fv, fi, ts, prev, do_profile)
-
-    @torch.no_grad()
-    def _forward_impl(self, fv, fi, ts, prev=None, do_profile=False):
-        lib = _lib.load()
-        B, S = fv.shape[0], fv.shape[1]
-        dev = fv.device
+        B = fv.shape[0]
         if self.fuse_method == "cat":
             fvc, fic, Dv = _f32c(fv, "fv"), _f32c(fi, "fi"), fv.shape[2]     # concat happens in-kernel
         else:
             fvc, fic, Dv = _f32c(self.fuse(fv, fi), "fused"), None, self.f_len
         ts = _f32c(ts, "ts")
-        ts_in = (ts - ts[:, :1]) if prev is None else ts                       # PoseODERNN.py:100
-        ts_in = ts_in.contiguous()
+        ts_in = ((ts - ts[:, :1]) if prev is None else ts).contiguous()        # PoseODERNN.py:100
         h0 = None if prev is None else _f32c(prev, "prev")
         if h0 is not None and tuple(h0.shape) != (self.rnn_num_layers, B, self.f_len):
             raise _lib.OdevioError(f"prev must be [L,B,D]={self.rnn_num_layers, B, self.f_len}, got {tuple(h0.shape)}")
+        return fvc, fic, Dv, ts_in, h0
+
+    def forward(self, fv, fi, ts, prev=None, do_profile=False):
+        _lib.load()
+        fvc, fic, Dv, ts_in, h0 = self._prepare_inputs(fv, fi, ts, prev)
+        needs_grad = torch.is_grad_enabled() and (
+            any(p.requires_grad for p in self.parameters()) or fvc.requires_grad
+            or (fic is not None and fic.requires_grad) or (h0 is not None and h0.requires_grad))
+        if needs_grad:
+            from .autograd import odernn_apply                    # fused discretise-then-optimise backward
+            return odernn_apply(self, fvc, fic, Dv, ts_in, h0)
+        with torch.no_grad():
+            pose, hT, _ = self._launch(fvc, fic, Dv, ts_in, h0, save_ckpt=False, do_profile=do_profile)
+        return pose, hT
+
+    def _launch(self, fvc, fic, Dv, ts_in, h0, save_ckpt=False, do_profile=False):
+        """One odevio_odernn_forward call.  Returns (pose, hT, ctx) where ctx carries what the
+        backward needs (cfg, checkpoint buffer) when save_ckpt is set."""
+        lib = _lib.load()
+        B, S = fvc.shape[0], fvc.shape[1]
+        dev = fvc.device
         cfg = self._cfg(B, S)
+        ckpt, ckpt_bytes = None, 0
+        if save_ckpt:
+            cfg.save_checkpoints = 1
+            cfg.ckpt_loops = self.ckpt_loops
+            if cfg.rows_per_tile == 16:
+                cfg.rows_per_tile = 8
+            ckpt_bytes = lib.odevio_odernn_ckpt_bytes(C.byref(cfg))
+            if ckpt_bytes == 0:
+                raise _lib.OdevioError("training through the fused path supports the tanh-RNN jump, "
+                                       "ode_endpoint='y1' and rows_per_tile in {0, 4, 8} "
+                                       f"(rnn={self.rnn_type}, endpoint={self.endpoint})")
+            ckpt = torch.empty(ckpt_bytes, dtype=torch.uint8, device=dev)
         nbytes = lib.odevio_odernn_workspace_bytes(C.byref(cfg))
         if nbytes == 0:
             raise _lib.OdevioError("unsupported PoseODERNN configuration for the fused kernel "
@@ -267,7 +295,8 @@ class PoseODERNN(nn.Module):
             rc = lib.odevio_odernn_forward(
                 C.byref(cfg), C.byref(w), _lib.dptr(fvc, "fv"), _lib.dptr(fic, "fi"), Dv,
                 _lib.dptr(ts_in, "ts"), _lib.dptr(h0, "prev"), _lib.dptr(pose), _lib.dptr(hT),
-                _lib.dptr(stats), _lib.dptr(status), _lib.dptr(ws), nbytes, C.c_void_p(stream))
+                _lib.dptr(stats), _lib.dptr(status), _lib.dptr(ckpt), ckpt_bytes,
+                _lib.dptr(ws), nbytes, C.c_void_p(stream))
         if do_profile:
             torch.cuda.nvtx.range_pop()
         _lib.check(rc)
@@ -276,7 +305,7 @@ class PoseODERNN(nn.Module):
         self.last_stats = None if stats is None else stats[..., :2]
         self.last_trace = (stats[..., 2:].contiguous().view(torch.float32).view(S, self.rnn_num_layers, B, T, 2)
                            if T else None)
-        return pose, hT
+        return pose, hT, (cfg, ckpt, ckpt_bytes)
 
     def check_status(self):
         """Synchronising check of the last forward's per-row solver status."""
@@ -284,5 +313,6 @@ class PoseODERNN(nn.Module):
             return
         bad = int(self.last_status.max().item())
         if bad != 0:
-            what = {1: "max_steps reached", 2: "non-finite error norm"}.get(bad, str(bad))
+            what = {1: "max_steps reached", 2: "non-finite error norm",
+                    3: "more solver iterations per interval than ode_ckpt_loops (training checkpoints)"}.get(bad, str(bad))
             raise RuntimeError(f"ODE solve failed for some rows: {what}")

@@ -51,7 +51,8 @@ class OraclePoseODERNN(nn.Module):
                                       floor_factor_after_accept=getattr(opt, "ode_floor_factor", False),
                                       endpoint=getattr(opt, "ode_endpoint", "y1"),
                                       exact_landing=getattr(opt, "ode_exact_landing", True),
-                                      max_steps=getattr(opt, "ode_max_steps", 100000))
+                                      max_steps=getattr(opt, "ode_max_steps", 100000),
+                                      detach_dt=getattr(opt, "ode_detach_dt", False))
         self.dt0 = getattr(opt, "ode_dt0", 1e-4)
         self.substeps = getattr(opt, "ode_substeps", 1)
         self.trace_steps = getattr(opt, "ode_trace_steps", 0)

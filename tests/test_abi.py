@@ -43,7 +43,7 @@ def test_struct_layout_matches_header(lib):
     assert (cfg.B, cfg.S, cfg.D, cfg.H, cfg.n_hidden, cfg.L) == (1, 10, 768, 512, 3, 2)
     assert abs(cfg.atol - 1e-6) < 1e-12 and abs(cfg.rtol - 1e-2) < 1e-9 and abs(cfg.dt0 - 1e-4) < 1e-11
     assert (cfg.accept_strict, cfg.floor_factor, cfg.endpoint_dense, cfg.exact_landing) == (1, 0, 0, 1)
-    assert lib.odevio_version() == 1
+    assert lib.odevio_version() == _lib.ABI_VERSION == 2
 
 
 def test_workspace_and_validation_without_gpu(lib):
@@ -59,9 +59,34 @@ def test_workspace_and_validation_without_gpu(lib):
     assert lib.odevio_odernn_workspace_bytes(C.byref(bad)) == 0
     w = _lib.OdeRnnWeights()
     rc = lib.odevio_odernn_forward(C.byref(cfg), C.byref(w), None, None, 768, None, None, None, None, None,
-                                   None, None, 0, None)
+                                   None, None, 0, None, 0, None)
     assert rc == -1                              # ODEVIO_E_NULL, before any device work
     assert b"NULL" in lib.odevio_error_string(rc)
+
+
+def test_training_geometry_and_sizes_without_gpu(lib):
+    """Checkpoint / backward-workspace planning is pure host arithmetic."""
+    from odevio_b200 import _lib
+    cfg = _lib.default_odernn_cfg()
+    cfg.B, cfg.save_checkpoints = 100, 1
+    geo = (C.c_int32 * 8)()
+    assert lib.odevio_odernn_geometry(C.byref(cfg), geo) == 0
+    RT, R, ntiles, ns, CK = geo[0], geo[1], geo[2], geo[3], geo[4]
+    assert (RT, R, ntiles, ns, CK) == (8, 16, 13, 6, 16)          # dopri5: 6 stages enter y1 (FSAL)
+    per_iv = 2 * 768 * R + CK * (768 * R + 2 * R)
+    assert lib.odevio_odernn_ckpt_bytes(C.byref(cfg)) >= ntiles * 10 * per_iv * 4
+    small = lib.odevio_odernn_backward_workspace_bytes(C.byref(cfg), 0)
+    big = lib.odevio_odernn_backward_workspace_bytes(C.byref(cfg), 10000)
+    assert small > 0 and big - small >= 10000 * 4 * (768 + 512 + 512 + 512 + 512 + 768)
+    cfg.rnn_type = 1                                               # GRU training is not built
+    assert lib.odevio_odernn_ckpt_bytes(C.byref(cfg)) == 0
+    cfg.rnn_type, cfg.solver = 0, 4                                # rk4: 4 stages, substeps iterations
+    cfg.substeps = 2
+    assert lib.odevio_odernn_geometry(C.byref(cfg), geo) == 0 and (geo[3], geo[4]) == (4, 2)
+    g = _lib.OdeRnnGrads()
+    rc = lib.odevio_odernn_backward(C.byref(cfg), C.byref(_lib.OdeRnnWeights()), None, None, 768, None, 0,
+                                    None, 0, None, None, C.byref(g), None, None, None, 0, None)
+    assert rc == -1
 
 
 def test_module_fails_loudly_without_cuda():
