@@ -82,7 +82,7 @@ def test_backward_prev_and_hidden_grad(cuda_device):
 
 
 @pytest.mark.parametrize("over", [
-    dict(ode_solver="tsit5"), dict(ode_solver="heun", ode_rtol=1e-1),
+    dict(ode_solver="tsit5"), dict(ode_solver="heun", ode_rtol=1e-1, ode_ckpt_loops=512),
     dict(ode_activation_fn="softplus"), dict(ode_activation_fn="relu"), dict(ode_activation_fn="leaky_relu"),
     dict(rnn_num_layers=3, ode_hidden_dim=256, ode_fn_num_layers=2),
     dict(rnn_num_layers=1, ode_hidden_dim=1024, ode_fn_num_layers=1),
