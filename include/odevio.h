@@ -205,6 +205,67 @@ ODEVIO_API int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const od
                                const odevio_odernn_grads* g, float* grad_fused, float* grad_h0,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ Neural CDE (PoseCDE) ---- */
+
+/* cde solver menu: torchdiffeq names reachable through src/models/PoseCDE.py:72,101 */
+enum { ODEVIO_CDE_SOLVER_DOPRI5 = 0, ODEVIO_CDE_SOLVER_RK4 = 1 /* torchdiffeq fixed-grid 3/8 rule */ };
+/* control path: the reference's rectilinear linear interpolation (PoseCDE.py:94-95) or the
+ * north_star cubic path (Hermite cubics with backward differences on the integer knot grid) */
+enum { ODEVIO_CDE_INTERP_LINEAR = 0, ODEVIO_CDE_INTERP_CUBIC = 1 };
+
+typedef struct odevio_cde_cfg {
+  int32_t B;            /* sequences */
+  int32_t S;            /* output times (= seq_len - 1), <= 64 */
+  int32_t So;           /* observations in the control path (>= 2; = S in training, grows with the
+                           eval-mode history of PoseCDE.py:88-92) */
+  int32_t Hc;           /* cde_hidden_dim; the fused feature width must equal it (PoseCDE.py:47,62) */
+  int32_t n_layers;     /* cde_fn_num_layers: Hc->Hc Linears before the final Hc -> Hc*(Hc+1) */
+  int32_t activation;   /* ODEVIO_ACT_* */
+  int32_t solver;       /* ODEVIO_CDE_SOLVER_* */
+  int32_t interp;       /* ODEVIO_CDE_INTERP_* */
+  float atol;           /* reference 1e-6 (PoseCDE.py:101) */
+  float rtol;           /* reference 1e-4 */
+  double step_size;     /* rk4: > 0 = fixed grid spacing with linear output interpolation, 0 = output times */
+  int32_t max_steps;    /* dopri5 guard (status 1 when hit) */
+  int32_t rows_per_tile;/* 0 = auto; 8 or 16 */
+  int32_t reserved[6];
+} odevio_cde_cfg;
+
+typedef struct odevio_cde_weights {
+  const float* cde_w[ODEVIO_MAX_ODE_LINEARS];  /* cde_func.net.{0,2,..}.weight; the last is [Hc*(Hc+1), Hc] */
+  const float* cde_b[ODEVIO_MAX_ODE_LINEARS];
+  const float* init_w;  /* initial.0.weight [Hc, Hc+1] */
+  const float* init_b;
+  const float* reg_w0;  /* regressor.0.weight [128, Hc] */
+  const float* reg_b0;
+  const float* reg_w1;  /* regressor.2.weight [6, 128] */
+  const float* reg_b1;
+} odevio_cde_weights;
+
+ODEVIO_API void odevio_cde_default_cfg(odevio_cde_cfg* cfg);
+ODEVIO_API size_t odevio_cde_workspace_bytes(const odevio_cde_cfg* cfg);
+
+/*
+ * Fused PoseCDE forward (replaces src/models/PoseCDE.py:76-103 incl. torchcde / torchdiffeq).
+ *   tobs [B,So]                     channel 0 of the observations (the timestamps the reference
+ *                                   concatenates in front of the fused features, PoseCDE.py:83-85)
+ *   fv [B,So,Dv], fi [B,So,Hc-Dv]   fused features (fi = NULL and Dv = Hc when already fused)
+ *   tout [S] float64 (DEVICE)       output times in the integration variable: the reference passes
+ *                                   batch row 0's times in seconds (PoseCDE.py:101); the cubic mode
+ *                                   integrates over the knot grid
+ *   z0_in [B,Hc] or NULL            NULL: z0 = initial(X(knot 0)) (PoseCDE.py:96)
+ *   pose [B,S,6], z0_out [B,Hc]     outputs (the reference returns z0, PoseCDE.py:103)
+ *   hidden [B,S,Hc] or NULL         optional: the integrated hidden states
+ *   stats int32[4] or NULL          n_steps, n_accepted, n_f_evals, status (ODEVIO_STATUS_*)
+ * Launches cooperatively (one grid-wide reduction per solver step: torchdiffeq's batch-joint
+ * step control); the whole grid must be resident, which the workspace planner guarantees.
+ */
+ODEVIO_API int32_t odevio_cde_forward(const odevio_cde_cfg* cfg, const odevio_cde_weights* w,
+                                      const float* tobs, const float* fv, const float* fi, int32_t Dv,
+                                      const double* tout, const float* z0_in,
+                                      float* pose, float* z0_out, float* hidden, int32_t* stats,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+
 /*
  * Diagnostics (no reference counterpart): launch a dense FFMA loop on `blocks` CTAs of 512 threads
  * and report the FLOPs it performs in *flops_out (HOST); time it with events around the call to

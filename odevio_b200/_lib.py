@@ -46,6 +46,27 @@ class OdeRnnWeights(C.Structure):
     ]
 
 
+class CdeCfg(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("S", C.c_int32), ("So", C.c_int32), ("Hc", C.c_int32),
+        ("n_layers", C.c_int32), ("activation", C.c_int32), ("solver", C.c_int32), ("interp", C.c_int32),
+        ("atol", C.c_float), ("rtol", C.c_float), ("step_size", C.c_double),
+        ("max_steps", C.c_int32), ("rows_per_tile", C.c_int32), ("reserved", C.c_int32 * 6),
+    ]
+
+
+class CdeWeights(C.Structure):
+    _fields_ = [
+        ("cde_w", _FP * MAX_ODE_LINEARS), ("cde_b", _FP * MAX_ODE_LINEARS),
+        ("init_w", _FP), ("init_b", _FP),
+        ("reg_w0", _FP), ("reg_b0", _FP), ("reg_w1", _FP), ("reg_b1", _FP),
+    ]
+
+
+CDE_SOLVER = {"dopri5": 0, "rk4": 1}
+CDE_INTERP = {"linear": 0, "cubic": 1}
+
+
 class OdeRnnGrads(C.Structure):
     _fields_ = OdeRnnWeights._fields_
 
@@ -89,6 +110,14 @@ def load():
     lib.odevio_odernn_backward.argtypes = [
         C.POINTER(OdeRnnCfg), C.POINTER(OdeRnnWeights), _FP, _FP, C.c_int32, _FP, C.c_size_t,
         _FP, C.c_int64, _FP, _FP, C.POINTER(OdeRnnGrads), _FP, _FP, _FP, C.c_size_t, _FP]
+    lib.odevio_cde_default_cfg.restype = None
+    lib.odevio_cde_default_cfg.argtypes = [C.POINTER(CdeCfg)]
+    lib.odevio_cde_workspace_bytes.restype = C.c_size_t
+    lib.odevio_cde_workspace_bytes.argtypes = [C.POINTER(CdeCfg)]
+    lib.odevio_cde_forward.restype = C.c_int32
+    lib.odevio_cde_forward.argtypes = [
+        C.POINTER(CdeCfg), C.POINTER(CdeWeights), _FP, _FP, _FP, C.c_int32, _FP, _FP,
+        _FP, _FP, _FP, _FP, _FP, C.c_size_t, _FP]
     lib.odevio_microbench_ffma.restype = C.c_int32
     lib.odevio_microbench_ffma.argtypes = [C.c_int32, C.c_int32, _FP, C.POINTER(C.c_double), _FP]
     if lib.odevio_version() != ABI_VERSION:
@@ -112,9 +141,15 @@ def dptr(t, name="tensor"):
         raise OdevioError(f"{name} must be a CUDA tensor (odevio_b200 has no CPU path)")
     if not t.is_contiguous():
         raise OdevioError(f"{name} must be contiguous")
-    if t.dtype not in (torch.float32, torch.int32, torch.int64, torch.uint8):
+    if t.dtype not in (torch.float32, torch.float64, torch.int32, torch.int64, torch.uint8):
         raise OdevioError(f"{name} must be float32/int32, got {t.dtype}")
     return C.c_void_p(t.data_ptr())
+
+
+def default_cde_cfg():
+    cfg = CdeCfg()
+    load().odevio_cde_default_cfg(C.byref(cfg))
+    return cfg
 
 
 def default_odernn_cfg():

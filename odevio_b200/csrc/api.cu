@@ -6,6 +6,7 @@
 
 #include "../../include/odevio.h"
 #include "odernn_params.h"
+#include "cde_params.h"
 
 namespace odevio {
 
@@ -16,6 +17,10 @@ cudaError_t launch_odernn_fwd(const FwdParams& prm, int rows_per_tile, int grid,
                               cudaStream_t stream);
 cudaError_t launch_odernn_bwd(const BwdParams& prm, int rows_per_tile, int grid, size_t smem_bytes,
                               cudaStream_t stream);
+cudaError_t launch_cde_fwd(const CdeParams& prm, const DevTableau& tab, int RT, int LL, int grid,
+                           size_t smem_bytes, cudaStream_t stream);
+cudaError_t cde_pack_final(const float* W, const float* b, int Hc, int C, int Gc, int ngroups, float* Wp,
+                           float* bp, cudaStream_t stream);
 int wgrad_splits(long long M, int N, int K, int nsm);
 cudaError_t wgrad_linear(const float* G, int ldg, const float* A, int lda, long long M, int N, int K,
                          float* dW0, float* dW1, int k_split, float* db0, float* db1, float* part, int nsm,
@@ -298,6 +303,70 @@ size_t ckpt_total_bytes(const odevio_odernn_cfg& c, const OdePlan& pl) {
   return pl.ckpt_head_bytes + static_cast<size_t>(pl.ntiles) * pl.ckpt_floats_per_tile * sizeof(float);
 }
 
+// ------------------------------------------------------------------ CDE planning
+struct CdePlan {
+  int RT, LL, R, ntiles, grid, nst, C, Cpad, Gc, ngroups, Ng, nsm;
+  size_t buf_floats, staging_floats, stage_floats, smem_bytes;
+  size_t off_Wmlp[kMaxLinears], off_Wfin, off_bfin, off_Winit, off_Wreg0;
+  size_t off_scratch, scratch_floats_per_tile, off_red, off_bar;
+  size_t total_bytes;
+};
+
+int plan_cde(const odevio_cde_cfg& c, CdePlan& pl) {
+  if (c.B <= 0 || c.S < 1 || c.S > kCdeMaxOut || c.So < 2 || c.So < c.S) return ODEVIO_E_SHAPE;
+  if (c.Hc < 8 || c.Hc % 8 || c.Hc > 1024) return ODEVIO_E_SHAPE;
+  if (c.n_layers < 1 || c.n_layers + 1 > ODEVIO_MAX_ODE_LINEARS) return ODEVIO_E_SHAPE;
+  if (c.activation < 0 || c.activation > ODEVIO_ACT_SOFTPLUS) return ODEVIO_E_ENUM;
+  if (c.solver != ODEVIO_CDE_SOLVER_DOPRI5 && c.solver != ODEVIO_CDE_SOLVER_RK4) return ODEVIO_E_ENUM;
+  if (c.interp != ODEVIO_CDE_INTERP_LINEAR && c.interp != ODEVIO_CDE_INTERP_CUBIC) return ODEVIO_E_ENUM;
+  if (c.rows_per_tile != 0 && c.rows_per_tile != 8 && c.rows_per_tile != 16) return ODEVIO_E_SHAPE;
+  if (c.solver == ODEVIO_CDE_SOLVER_DOPRI5 && c.max_steps < 1) return ODEVIO_E_SHAPE;
+  if (c.step_size < 0.0) return ODEVIO_E_SHAPE;
+  const int nsm = sm_count();
+  pl.nsm = nsm;
+  pl.C = c.Hc + 1;
+  pl.Cpad = (pl.C + 7) / 8 * 8;
+  pl.Gc = 1024 / c.Hc; if (pl.Gc < 1) pl.Gc = 1; if (pl.Gc > pl.C) pl.Gc = pl.C;
+  pl.ngroups = (pl.C + pl.Gc - 1) / pl.Gc;
+  pl.Ng = pl.Gc * c.Hc;
+  int nmax = pl.Ng > kRegHidden ? pl.Ng : kRegHidden;
+  pl.stage_floats = static_cast<size_t>(kStageK) * nmax;
+  auto fit = [&](int R) -> bool {
+    size_t rows = static_cast<size_t>(c.Hc > pl.Cpad ? c.Hc : pl.Cpad);
+    if (rows < static_cast<size_t>(kRegHidden)) rows = kRegHidden;
+    pl.buf_floats = rows * R;
+    pl.staging_floats = static_cast<size_t>(pl.Ng) * R;
+    const size_t fixed_bytes = (2 * pl.buf_floats + pl.staging_floats + static_cast<size_t>(pl.Cpad) * R +
+                                static_cast<size_t>(c.Hc) * R) * sizeof(float) + 16 + 72 * sizeof(double) +
+                               2 * kMaxStagesRing * 8 + 128;
+    if (fixed_bytes + 2 * pl.stage_floats * sizeof(float) > kSmemLimit) return false;
+    size_t nst = (kSmemLimit - fixed_bytes) / (pl.stage_floats * sizeof(float));
+    if (nst > kMaxStagesRing) nst = kMaxStagesRing;
+    pl.nst = static_cast<int>(nst);
+    pl.smem_bytes = fixed_bytes + nst * pl.stage_floats * sizeof(float);
+    return true;
+  };
+  int R = c.rows_per_tile;
+  if (R == 0) R = (c.B <= 8 * nsm) ? 8 : 16;         // more CTAs while the batch fits one wave
+  if (!fit(R)) { if (R == 16 && fit(8)) R = 8; else return ODEVIO_E_SHAPE; }
+  pl.R = R; pl.RT = 8; pl.LL = R / 8;
+  pl.ntiles = (c.B + R - 1) / R;
+  pl.grid = pl.ntiles < nsm ? pl.ntiles : nsm;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = align_up(off + n, 64); return o; };
+  for (int j = 0; j < c.n_layers; ++j) pl.off_Wmlp[j] = take(static_cast<size_t>(c.Hc) * c.Hc);
+  pl.off_Wfin = take(static_cast<size_t>(pl.ngroups) * c.Hc * pl.Ng);
+  pl.off_bfin = take(static_cast<size_t>(pl.ngroups) * pl.Ng);
+  pl.off_Winit = take(static_cast<size_t>(pl.Cpad) * c.Hc);
+  pl.off_Wreg0 = take(static_cast<size_t>(c.Hc) * kRegHidden);
+  pl.scratch_floats_per_tile = align_up(static_cast<size_t>(2 + kMaxStages) * c.Hc * R, 64);
+  pl.off_scratch = take(pl.scratch_floats_per_tile * pl.ntiles);
+  pl.off_red = take(static_cast<size_t>(2) * pl.grid * 2 * 2);      // doubles as float pairs
+  pl.off_bar = take(64);
+  pl.total_bytes = off * sizeof(float);
+  return 0;
+}
+
 #define ODEVIO_CUDA_TRY(expr)                                   \
   do {                                                          \
     cudaError_t _e = (expr);                                    \
@@ -547,6 +616,72 @@ int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn
                                g->reg_w0, nullptr, 0, g->reg_b0, nullptr, part, pl.nsm, stream));
   ODEVIO_CUDA_TRY(wgrad_linear(p.recG_reg1, 8, p.recA_reg1, kRegHidden, bp.jump_rows, kPoseDim, kRegHidden,
                                g->reg_w1, nullptr, 0, g->reg_b1, nullptr, part, pl.nsm, stream));
+  return 0;
+}
+
+void odevio_cde_default_cfg(odevio_cde_cfg* cfg) {
+  if (!cfg) return;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->B = 1; cfg->S = 10; cfg->So = 10; cfg->Hc = 128; cfg->n_layers = 3;     // scripts/config.py:74-78
+  cfg->activation = ODEVIO_ACT_TANH; cfg->solver = ODEVIO_CDE_SOLVER_DOPRI5; cfg->interp = ODEVIO_CDE_INTERP_LINEAR;
+  cfg->atol = 1e-6f; cfg->rtol = 1e-4f;                                         // PoseCDE.py:101
+  cfg->step_size = 0.0; cfg->max_steps = 100000; cfg->rows_per_tile = 0;
+}
+
+size_t odevio_cde_workspace_bytes(const odevio_cde_cfg* cfg) {
+  if (!cfg) return 0;
+  CdePlan pl;
+  if (plan_cde(*cfg, pl) != 0) return 0;
+  return pl.total_bytes;
+}
+
+int32_t odevio_cde_forward(const odevio_cde_cfg* cfg, const odevio_cde_weights* w,
+                           const float* tobs, const float* fv, const float* fi, int32_t Dv,
+                           const double* tout, const float* z0_in,
+                           float* pose, float* z0_out, float* hidden, int32_t* stats,
+                           void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!cfg || !w || !tobs || !fv || !tout || !pose || !z0_out || !workspace) return ODEVIO_E_NULL;
+  const odevio_cde_cfg& c = *cfg;
+  CdePlan pl;
+  const int rc = plan_cde(c, pl);
+  if (rc != 0) return rc;
+  if (Dv <= 0 || Dv > c.Hc || (Dv < c.Hc && !fi) || (Dv == c.Hc && fi)) return ODEVIO_E_SHAPE;
+  if (workspace_bytes < pl.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ODEVIO_E_WORKSPACE;
+  for (int j = 0; j <= c.n_layers; ++j) if (!w->cde_w[j] || !w->cde_b[j]) return ODEVIO_E_NULL;
+  if (!w->init_w || !w->init_b || !w->reg_w0 || !w->reg_b0 || !w->reg_w1 || !w->reg_b1) return ODEVIO_E_NULL;
+
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* ws = static_cast<float*>(workspace);
+  CdeParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = c.B; p.S = c.S; p.So = c.So; p.Hc = c.Hc; p.C = pl.C; p.Cpad = pl.Cpad; p.NM = c.n_layers;
+  p.act = c.activation; p.solver = c.solver; p.interp = c.interp;
+  p.atol = c.atol; p.rtol = c.rtol; p.step_size = c.step_size; p.max_steps = c.max_steps;
+  for (int j = 0; j < c.n_layers; ++j) {
+    float* dst = ws + pl.off_Wmlp[j];
+    ODEVIO_CUDA_TRY(transpose_pack(w->cde_w[j], c.Hc, c.Hc, dst, c.Hc, 0, 0, stream));
+    p.Wmlp[j] = dst; p.bmlp[j] = w->cde_b[j];
+  }
+  ODEVIO_CUDA_TRY(cde_pack_final(w->cde_w[c.n_layers], w->cde_b[c.n_layers], c.Hc, pl.C, pl.Gc, pl.ngroups,
+                                 ws + pl.off_Wfin, ws + pl.off_bfin, stream));
+  p.Wfin = ws + pl.off_Wfin; p.bfin = ws + pl.off_bfin; p.Gc = pl.Gc; p.ngroups = pl.ngroups; p.Ng = pl.Ng;
+  ODEVIO_CUDA_TRY(cudaMemsetAsync(ws + pl.off_Winit, 0, sizeof(float) * pl.Cpad * c.Hc, stream));
+  ODEVIO_CUDA_TRY(transpose_pack(w->init_w, c.Hc, pl.C, ws + pl.off_Winit, c.Hc, 0, 0, stream));
+  p.Winit = ws + pl.off_Winit; p.binit = w->init_b;
+  ODEVIO_CUDA_TRY(transpose_pack(w->reg_w0, kRegHidden, c.Hc, ws + pl.off_Wreg0, kRegHidden, 0, 0, stream));
+  p.Wreg0 = ws + pl.off_Wreg0; p.breg0 = w->reg_b0; p.Wreg1 = w->reg_w1; p.breg1 = w->reg_b1;
+  p.tobs = tobs; p.fv = fv; p.fi = fi; p.Dv = Dv; p.tout = tout; p.z0_in = z0_in;
+  p.pose = pose; p.z0_out = z0_out; p.hout = hidden; p.stats = stats;
+  p.scratch = ws + pl.off_scratch; p.scratch_floats_per_tile = pl.scratch_floats_per_tile;
+  p.red = reinterpret_cast<double*>(ws + pl.off_red);
+  p.bar = reinterpret_cast<unsigned int*>(ws + pl.off_bar);
+  ODEVIO_CUDA_TRY(cudaMemsetAsync(p.bar, 0, 256, stream));
+  p.ntiles = pl.ntiles; p.nst = pl.nst;
+  p.buf_floats = static_cast<int>(pl.buf_floats); p.stage_floats = static_cast<int>(pl.stage_floats);
+  p.staging_floats = static_cast<int>(pl.staging_floats);
+  DevTableau tab;
+  if (!make_tableau(ODEVIO_SOLVER_DOPRI5, tab)) return ODEVIO_E_ENUM;
+  ODEVIO_CUDA_TRY(launch_cde_fwd(p, tab, pl.RT, pl.LL, pl.grid, pl.smem_bytes, stream));
   return 0;
 }
 

@@ -1,0 +1,791 @@
+// Fused Neural-CDE regressor forward: ONE cooperative persistent kernel integrates
+//   dz/dt = g(z) . dX/dt(t)
+// for the whole batch with torchdiffeq's BATCH-JOINT step control, evaluates the control path's
+// derivative inside the vector field (no coefficient tensor is ever materialised), and applies
+// the pose head at every output time.
+//
+// Replaces the arithmetic behind (reference file:line)
+//   PoseCDE.forward                                  src/models/PoseCDE.py:76-103
+//   torchcde linear_interpolation_coeffs(rectilinear=0) / LinearInterpolation / cdeint  (:94-101)
+//   torchdiffeq odeint dopri5 | rk4 underneath       (semantics: oracle/torchdiffeq_like.py)
+//   CDEFunc.forward                                  src/models/ODEFunc.py:81-84
+//   initial / regressor heads                        src/models/PoseCDE.py:58-61,67-71,96,102
+// plus the north_star cubic control path (Hermite cubics with backward differences).
+//
+// Geometry: tile = R = RT x LL sequences (LL row blocks of RT rows, 128 consumer threads each);
+// tiles are distributed round-robin over the CTAs and every tile's state (z, y1, k0..k6, T-layout
+// [Hc][R]) lives in L2-resident global scratch.  The final Linear Hc -> Hc*C of CDEFunc is
+// processed in channel groups: one tile_gemm of N = Gc*Hc columns into a shared-memory staging
+// buffer (tanh in the epilogue), then a fixed-order contraction with dX/dt -- the [B,Hc,C] tensor
+// never leaves the SM.  Channel groups whose dX/dt is identically zero (rectilinear segments move
+// either the time channel or the values) are skipped: 0 * tanh(.) adds an exact zero.
+// One grid-wide reduction per solver step gives the joint RMS error ratio; time-like scalars are
+// float64 and are recomputed identically by every CTA.
+#include "cde_params.h"
+#include "tile_gemm.cuh"
+
+namespace odevio {
+
+namespace {
+
+__constant__ float kDpC[7] = {0.0f, 0.2f, 0.3f, 0.8f, static_cast<float>(8.0 / 9.0), 1.0f, 1.0f};
+
+struct TileArrays { float* Z; float* Y1; float* K[kMaxStages]; };
+
+template <int RT>
+struct CCtx {
+  const CdeParams* prm;
+  TileThread th;
+  WeightRing ring;
+  RingPos pos;
+  float* bufA; float* bufB; float* staging; float* dXs; float* dz;
+  double* redsm;            // shared scratch for block reductions
+  unsigned int bar_target;
+  unsigned int red_count;
+  int R, rq4, rq;
+};
+
+__device__ __forceinline__ TileArrays tile_arrays(const CdeParams& p, int tile, int R) {
+  TileArrays t;
+  const size_t arr = static_cast<size_t>(p.Hc) * R;
+  float* base = p.scratch + static_cast<size_t>(tile) * p.scratch_floats_per_tile;
+  t.Z = base; t.Y1 = base + arr;
+  for (int j = 0; j < kMaxStages; ++j) t.K[j] = base + (2 + j) * arr;
+  return t;
+}
+
+// ---- grid-wide sum of two doubles (deterministic: fixed tree in the block, CTA order across) ----
+template <int RT>
+__device__ __forceinline__ void grid_reduce2(CCtx<RT>& c, double a, double b, double& sa, double& sb) {
+  const CdeParams& p = *c.prm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_down_sync(0xffffffffu, a, o);
+    b += __shfl_down_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) { c.redsm[2 * warp] = a; c.redsm[2 * warp + 1] = b; }
+  __syncthreads();
+  const int slot = c.red_count & 1;
+  double* mine = p.red + (static_cast<size_t>(slot) * gridDim.x + blockIdx.x) * 2;
+  if (tid == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int w = 0; w < nwarps; ++w) { ta += c.redsm[2 * w]; tb += c.redsm[2 * w + 1]; }
+    __stcg(mine, ta); __stcg(mine + 1, tb);
+    __threadfence();
+    atomicAdd(p.bar, 1u);
+    const unsigned int target = c.bar_target + gridDim.x;
+    unsigned int spins = 0;
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.bar) : "memory");
+      if (v >= target) break;
+      if (++spins > (1u << 27)) __trap();       // a lost CTA must not hang the GPU
+    }
+    __threadfence();
+    double ga = 0.0, gb = 0.0;
+    const double* all = p.red + static_cast<size_t>(slot) * gridDim.x * 2;
+    for (unsigned int g = 0; g < gridDim.x; ++g) { ga += __ldcg(all + 2 * g); gb += __ldcg(all + 2 * g + 1); }
+    c.redsm[64] = ga; c.redsm[65] = gb;
+  }
+  c.bar_target += gridDim.x;
+  c.red_count += 1;
+  __syncthreads();
+  sa = c.redsm[64]; sb = c.redsm[65];
+  __syncthreads();
+}
+
+// torchcde _interpret_t on the integer knot grid 0..nk-1 (bucketize right=False)
+__device__ __forceinline__ int segment_index(float t, int nk) {
+  int cnt = static_cast<int>(ceilf(t));          // knots strictly below t
+  cnt = max(0, min(cnt, nk));
+  return max(0, min(cnt - 1, nk - 2));
+}
+
+__device__ __forceinline__ float obs_value(const CdeParams& p, int b, int o, int ch) {
+  // channel 0 = time, channels 1.. = fused features cat(fv, fi)
+  if (ch == 0) return p.tobs[static_cast<size_t>(b) * p.So + o];
+  const int f = ch - 1;
+  const size_t row = static_cast<size_t>(b) * p.So + o;
+  return (f < p.Dv) ? p.fv[row * p.Dv + f] : p.fi[row * (p.Hc - p.Dv) + (f - p.Dv)];
+}
+
+// dX/dt(t) of the tile's rows -> dXs [Cpad][R]; returns nothing (consumers, ends with barrier)
+template <int RT>
+__device__ __forceinline__ void control_derivative(CCtx<RT>& c, int tile, float t) {
+  if (c.th.producer) return;
+  const CdeParams& p = *c.prm;
+  const int R = c.R;
+  const int nk = p.interp == CDE_INTERP_LINEAR ? 2 * p.So - 1 : p.So;
+  const int seg = segment_index(t, nk);
+  const float s = sub_(t, static_cast<float>(seg));
+  for (int e = c.th.ctid; e < p.Cpad * R; e += c.th.ncons) {
+    const int r = e / p.Cpad, ch = e - r * p.Cpad;          // coalesced along channels
+    const int b = tile * R + r;
+    float v = 0.f;
+    if (b < p.B && ch < p.C) {
+      if (p.interp == CDE_INTERP_LINEAR) {
+        const int m = seg >> 1;
+        if ((seg & 1) == 0) {                                 // time moves, values held
+          if (ch == 0) v = sub_(obs_value(p, b, m + 1, 0), obs_value(p, b, m, 0));
+        } else if (ch > 0) {                                  // values move, time held
+          v = sub_(obs_value(p, b, m + 1, ch), obs_value(p, b, m, ch));
+        }
+      } else {
+        const float x0 = obs_value(p, b, seg, ch), x1 = obs_value(p, b, seg + 1, ch);
+        const float d = sub_(x1, x0);
+        const float m = seg == 0 ? d : sub_(x0, obs_value(p, b, seg - 1, ch));
+        // m + (d - m) * ((4 - 3 s) * s)     (oracle/torchcde_like.py: HermiteCubicBackward.derivative)
+        v = add_(m, mul_(sub_(d, m), mul_(sub_(4.0f, mul_(3.0f, s)), s)));
+      }
+    }
+    c.dXs[ch * R + r] = v;
+  }
+  named_bar_sync(1, c.th.ncons);
+}
+
+// recipes for the argument of a vector-field evaluation / an output value, all -> bufA [Hc][R]
+enum { RC_Z = 0, RC_HAIRER, RC_STAGE, RC_RK4_1, RC_RK4_2, RC_RK4_3,
+       RC_INTERP, RC_Y1, RC_LERP };
+
+struct Recipe {
+  int kind; int stage; float dt_s; float x; const DevTableau* tab;
+};
+
+template <int RT>
+__device__ __forceinline__ void build_vector(CCtx<RT>& c, const TileArrays& T, const Recipe& rc, bool save_y1) {
+  if (c.th.producer) return;
+  const CdeParams& p = *c.prm;
+  const int nvec = p.Hc * c.rq4;
+  const float dt = rc.dt_s;
+  for (int e = c.th.ctid; e < nvec; e += c.th.ncons) {
+    const size_t off = static_cast<size_t>(e) * 4;
+    const float4 y4 = ld4(T.Z + off);
+    float y[4] = {y4.x, y4.y, y4.z, y4.w};
+    float out[4];
+    float k[kMaxStages][4];
+    auto ldk = [&](int j) { const float4 v = ld4(T.K[j] + off); k[j][0] = v.x; k[j][1] = v.y; k[j][2] = v.z; k[j][3] = v.w; };
+    switch (rc.kind) {
+      case RC_Z:
+        for (int q = 0; q < 4; ++q) out[q] = y[q];
+        break;
+      case RC_HAIRER:
+        ldk(0);
+        for (int q = 0; q < 4; ++q) out[q] = add_(y[q], mul_(dt, k[0][q]));
+        break;
+      case RC_STAGE: {
+        // y + sum_j k_j * fl(a_ij * dt), left to right, skipping exact zeros (torchdiffeq k.matmul(beta*dt))
+        const int i = rc.stage;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        bool any = false;
+        for (int j = 0; j < i; ++j) {
+          const float a = rc.tab->a[i][j];
+          if (a == 0.f) continue;
+          ldk(j);
+          const float w = mul_(a, dt);
+          for (int q = 0; q < 4; ++q) acc[q] = any ? add_(acc[q], mul_(k[j][q], w)) : mul_(k[j][q], w);
+          any = true;
+        }
+        for (int q = 0; q < 4; ++q) out[q] = any ? add_(y[q], acc[q]) : y[q];
+        break;
+      }
+      case RC_RK4_1:      // y + dt * k1 * (1/3)
+        ldk(0);
+        for (int q = 0; q < 4; ++q) out[q] = add_(y[q], mul_(mul_(dt, k[0][q]), static_cast<float>(1.0 / 3.0)));
+        break;
+      case RC_RK4_2:      // y + dt * (k2 - k1 * (1/3))
+        ldk(0); ldk(1);
+        for (int q = 0; q < 4; ++q)
+          out[q] = add_(y[q], mul_(dt, sub_(k[1][q], mul_(k[0][q], static_cast<float>(1.0 / 3.0)))));
+        break;
+      case RC_RK4_3:      // y + dt * (k1 - k2 + k3)
+        ldk(0); ldk(1); ldk(2);
+        for (int q = 0; q < 4; ++q) out[q] = add_(y[q], mul_(dt, add_(sub_(k[0][q], k[1][q]), k[2][q])));
+        break;
+      case RC_Y1: {
+        const float4 v = ld4(T.Y1 + off);
+        out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+        break;
+      }
+      case RC_LERP: {     // y + w * (y1 - y)
+        const float4 v = ld4(T.Y1 + off);
+        const float y1[4] = {v.x, v.y, v.z, v.w};
+        for (int q = 0; q < 4; ++q) out[q] = add_(y[q], mul_(rc.x, sub_(y1[q], y[q])));
+        break;
+      }
+      default: {          // RC_INTERP: quartic dense output of the accepted step (oracle interp_fit / interp_evaluate)
+        const float4 v = ld4(T.Y1 + off);
+        const float y1[4] = {v.x, v.y, v.z, v.w};
+        float ym[4] = {0.f, 0.f, 0.f, 0.f};
+        bool any = false;
+        for (int j = 0; j < rc.tab->n_stages; ++j) {
+          const float bm = rc.tab->bmid[j];
+          if (bm == 0.f) { if (j == 0 || j == rc.tab->n_stages - 1) ldk(j); continue; }
+          ldk(j);
+          const float w = mul_(bm, dt);
+          for (int q = 0; q < 4; ++q) ym[q] = any ? add_(ym[q], mul_(k[j][q], w)) : mul_(k[j][q], w);
+          any = true;
+        }
+        const int last = rc.tab->n_stages - 1;
+        const float x = rc.x;
+        for (int q = 0; q < 4; ++q) {
+          const float f0 = k[0][q], f1 = k[last][q], y0 = y[q], ymid = add_(y0, ym[q]);
+          const float a = add_(sub_(mul_(mul_(2.0f, dt), sub_(f1, f0)), mul_(8.0f, add_(y1[q], y0))), mul_(16.0f, ymid));
+          const float b = sub_(add_(add_(mul_(dt, sub_(mul_(5.0f, f0), mul_(3.0f, f1))), mul_(18.0f, y0)),
+                                    mul_(14.0f, y1[q])), mul_(32.0f, ymid));
+          const float cc = add_(sub_(sub_(mul_(dt, sub_(f1, mul_(4.0f, f0))), mul_(11.0f, y0)), mul_(5.0f, y1[q])),
+                                mul_(16.0f, ymid));
+          const float d = mul_(dt, f0);
+          float total = add_(y0, mul_(x, d));
+          float xp = x;
+          xp = mul_(xp, x); total = add_(total, mul_(xp, cc));
+          xp = mul_(xp, x); total = add_(total, mul_(xp, b));
+          xp = mul_(xp, x); total = add_(total, mul_(xp, a));
+          out[q] = total;
+        }
+        break;
+      }
+    }
+    const float4 o4 = make_float4(out[0], out[1], out[2], out[3]);
+    st4(c.bufA + off, o4);
+    if (save_y1) st4(T.Y1 + off, o4);
+  }
+  named_bar_sync(1, c.th.ncons);
+}
+
+// dz[h][r] (+)= sum_{c_local} staging[(c_local*Hc + h)][r] * dX[g*Gc + c_local][r], fixed order
+template <int RT>
+__device__ __forceinline__ void contract_group(CCtx<RT>& c, int g, bool first) {
+  if (c.th.producer) return;
+  const CdeParams& p = *c.prm;
+  const int R = c.R;
+  const int nvec = p.Hc * c.rq4;
+  const int c0 = g * p.Gc;
+  const int nc = min(p.Gc, p.C - c0);
+  for (int e = c.th.ctid; e < nvec; e += c.th.ncons) {
+    const size_t off = static_cast<size_t>(e) * 4;
+    const int q4 = 4 * (e % c.rq4);
+    float4 acc = first ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(c.dz + off);
+    for (int cl = 0; cl < nc; ++cl) {
+      const float4 s = ld4(c.staging + static_cast<size_t>(cl) * p.Hc * R + off);
+      const float4 dx = ld4(c.dXs + (c0 + cl) * R + q4);
+      acc.x = add_(acc.x, mul_(s.x, dx.x)); acc.y = add_(acc.y, mul_(s.y, dx.y));
+      acc.z = add_(acc.z, mul_(s.z, dx.z)); acc.w = add_(acc.w, mul_(s.w, dx.w));
+    }
+    st4(c.dz + off, acc);
+  }
+  named_bar_sync(1, c.th.ncons);
+}
+
+template <int RT>
+__device__ __forceinline__ void store_tile(CCtx<RT>& c, float* dst, const float* src_smem) {
+  if (c.th.producer) return;
+  const int nvec = c.prm->Hc * c.rq4;
+  for (int e = c.th.ctid; e < nvec; e += c.th.ncons) st4(dst + static_cast<size_t>(e) * 4, ld4(src_smem + static_cast<size_t>(e) * 4));
+  named_bar_sync(1, c.th.ncons);
+}
+
+struct GemmOpC {
+  const float* W; int K; int N;
+  const float* in; bool ode_layout;
+  Epilogue epi;
+};
+
+// program counters of the solve
+enum { PC_INIT = 0, PC_POSE0, PC_F0, PC_HAIRER_A, PC_HAIRER_B, PC_STEP_BEGIN, PC_STAGE, PC_STEP_END,
+       PC_OUTPUTS, PC_COMMIT, PC_AFTER_JUMP, PC_RK4_END, PC_END,
+       // sub-machines
+       PC_EVAL, PC_POSE, PC_INITZ };
+
+}  // namespace
+
+template <int RT, int LL>
+__global__ void __launch_bounds__(128 * LL + 32, 1)
+cde_fwd_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ DevTableau tab) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  CCtx<RT> c;
+  c.prm = &prm;
+  const CdeParams& p = prm;
+  const int tid = threadIdx.x;
+  constexpr int ncons = 128 * LL;
+  constexpr int R = RT * LL;
+  c.th.ncons = ncons;
+  c.th.lane = tid & 31;
+  c.th.producer = tid >= ncons;
+  c.th.ctid = c.th.producer ? 0 : tid;
+  c.R = R; c.rq4 = R / 4; c.rq = c.th.ctid % (R / 4);
+  c.bar_target = 0; c.red_count = 0;
+
+  float* sm = reinterpret_cast<float*>(smem_raw);
+  c.bufA = sm; sm += prm.buf_floats;
+  c.bufB = sm; sm += prm.buf_floats;
+  c.staging = sm; sm += prm.staging_floats;
+  c.dXs = sm; sm += prm.Cpad * R;
+  c.dz = sm; sm += prm.Hc * R;
+  float* stages = sm; sm += static_cast<size_t>(prm.nst) * prm.stage_floats;
+  uintptr_t bp = (reinterpret_cast<uintptr_t>(sm) + 15) & ~static_cast<uintptr_t>(15);
+  c.redsm = reinterpret_cast<double*>(bp);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(c.redsm + 72);
+  c.ring.buf = stages;
+  c.ring.buf_off = static_cast<uint32_t>(reinterpret_cast<unsigned char*>(stages) - smem_raw);
+  c.ring.full = bars;
+  c.ring.empty = bars + MAX_STAGES;
+  c.ring.stage_floats = prm.stage_floats;
+  c.ring.nst = prm.nst;
+  c.pos.stage = 0; c.pos.phase = 0; c.pos.ready = 0;
+  if (tid == 0) {
+    for (int s = 0; s < prm.nst; ++s) {
+      mbar_init(&c.ring.full[s], 1);
+      mbar_init(&c.ring.empty[s], ncons / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int Hc = prm.Hc, S = prm.S;
+  const int my_tiles = (prm.ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int nk = prm.interp == CDE_INTERP_LINEAR ? 2 * prm.So - 1 : prm.So;
+  const bool adaptive = prm.solver == CDE_SOLVER_DOPRI5;
+  const double elems = static_cast<double>(prm.B) * Hc;
+
+  // ---- solver scalars: identical in every thread of every CTA
+  double t_cur = prm.tout[0], dt = 0.0, step = 0.0, t_b = 0.0, h0 = 0.0, d1 = 0.0;
+  float dt_s = 0.f, ta_s = 0.f, tb_s = 0.f;
+  int on_jump = 0, next_jump = 0, i_out = 1, st = 0;
+  int n_steps = 0, n_acc = 0, n_f = 0, status = 0;
+  {
+    long long cnt = static_cast<long long>(floor(t_cur)) + 1;       // bisect_right(knots, t0)
+    if (cnt < 0) cnt = 0;
+    if (cnt > nk) cnt = nk;
+    next_jump = static_cast<int>(cnt < nk - 1 ? cnt : nk - 1);
+  }
+  // fixed-grid rk4 bookkeeping
+  int grid_n = 0, grid_i = 0;
+  if (!adaptive) {
+    if (prm.step_size > 0.0) grid_n = static_cast<int>(ceil((prm.tout[S - 1] - prm.tout[0]) / prm.step_size + 1.0));
+    else grid_n = S;
+  }
+  auto grid_time = [&](int k) -> double {
+    if (prm.step_size > 0.0) return k == grid_n - 1 ? prm.tout[S - 1] : prm.tout[0] + prm.step_size * k;
+    return prm.tout[k];
+  };
+
+  // ---- sub-machine registers
+  int pc = PC_INITZ, ret = PC_POSE0;
+  int tk = 0;                       // index into this CTA's tile list
+  int ev_phase = 0, ev_layer = 0, ev_group = 0, ev_out = 0, ev_perturb = 0, ev_save_y1 = 0;
+  float ev_t = 0.f;
+  Recipe ev_rc{RC_Z, 0, 0.f, 0.f, &tab};
+  Recipe po_rc{RC_Z, 0, 0.f, 0.f, &tab};
+  int po_phase = 0, po_i = 0;
+  float* lin = c.bufA; float* lout = c.bufB;
+  bool first_group = true;
+
+  auto start_eval = [&](int kind, int stage, float dts, float t, int perturb, int out, int save_y1, int back) {
+    ev_rc.kind = kind; ev_rc.stage = stage; ev_rc.dt_s = dts;
+    ev_t = t; ev_perturb = perturb; ev_out = out; ev_save_y1 = save_y1;
+    tk = 0; ev_phase = 0; ret = back; pc = PC_EVAL; ++n_f;
+  };
+  auto start_pose = [&](int kind, float dts, float x, int i, int back) {
+    po_rc.kind = kind; po_rc.dt_s = dts; po_rc.x = x; po_i = i;
+    tk = 0; po_phase = 0; ret = back; pc = PC_POSE;
+  };
+
+  while (pc != PC_END) {
+    GemmOpC op{};
+    bool do_gemm = false;
+    const int tile = static_cast<int>(blockIdx.x) + tk * static_cast<int>(gridDim.x);
+    switch (pc) {
+      // ================================================================ z0
+      case PC_INITZ: {
+        if (tk >= my_tiles) { tk = 0; pc = ret; break; }
+        const TileArrays T = tile_arrays(p, tile, R);
+        if (p.z0_in) {
+          if (!c.th.producer) {
+            for (int e = c.th.ctid; e < Hc * R; e += ncons) {
+              const int r = e / Hc, h = e - r * Hc;
+              const int b = tile * R + r;
+              T.Z[static_cast<size_t>(h) * R + r] = b < p.B ? p.z0_in[static_cast<size_t>(b) * Hc + h] : 0.f;
+            }
+            named_bar_sync(1, ncons);
+          }
+          ++tk;
+        } else {
+          // z0 = tanh(W_init . X(knot 0) + b) with X(knot 0) = (t_0, x_0)      (PoseCDE.py:96)
+          if (!c.th.producer) {
+            for (int e = c.th.ctid; e < p.Cpad * R; e += ncons) {
+              const int r = e / p.Cpad, ch = e - r * p.Cpad;
+              const int b = tile * R + r;
+              c.bufA[ch * R + r] = (b < p.B && ch < p.C) ? obs_value(p, b, 0, ch) : 0.f;
+            }
+            named_bar_sync(1, ncons);
+          }
+          op.W = p.Winit; op.K = p.Cpad; op.N = Hc; op.in = c.bufA; op.ode_layout = true;
+          op.epi.mode = EPI_STORE; op.epi.bias = p.binit; op.epi.act = ACT_TANH;
+          op.epi.out0 = T.Z; op.epi.ld0 = R;
+          do_gemm = true;
+          ++tk;
+        }
+        break;
+      }
+      // ================================================================ vector-field evaluation of all my tiles
+      case PC_EVAL: {
+        if (tk >= my_tiles) { tk = 0; pc = ret; break; }
+        const TileArrays T = tile_arrays(p, tile, R);
+        if (ev_phase == 0) {
+          build_vector<RT>(c, T, ev_rc, ev_save_y1 != 0);
+          float tt = ev_t;
+          if (ev_perturb > 0) tt = nextafterf(tt, tt + 1.0f);
+          else if (ev_perturb < 0) tt = nextafterf(tt, tt - 1.0f);
+          control_derivative<RT>(c, tile, tt);
+          // rectilinear: even segments move only the time channel -> only group 0 is live
+          ev_layer = 0; lin = c.bufA; lout = c.bufB; ev_phase = 1;
+          ev_group = 0; first_group = true;
+          break;
+        }
+        if (ev_phase == 1) {            // Hc -> Hc layers
+          op.W = p.Wmlp[ev_layer]; op.K = Hc; op.N = Hc; op.in = lin; op.ode_layout = true;
+          op.epi.mode = EPI_STORE; op.epi.bias = p.bmlp[ev_layer]; op.epi.act = p.act;
+          op.epi.out0 = lout; op.epi.ld0 = R;
+          do_gemm = true;
+          float* t = lin; lin = lout; lout = t;
+          if (++ev_layer == p.NM) ev_phase = 2;
+          break;
+        }
+        if (ev_phase == 2) {            // final Linear, one channel group per GEMM, tanh in the epilogue
+          float tt = ev_t;
+          if (ev_perturb > 0) tt = nextafterf(tt, tt + 1.0f);
+          else if (ev_perturb < 0) tt = nextafterf(tt, tt - 1.0f);
+          const bool time_only = p.interp == CDE_INTERP_LINEAR && (segment_index(tt, nk) & 1) == 0;
+          if (ev_group >= p.ngroups || (time_only && ev_group >= 1)) {
+            store_tile<RT>(c, T.K[ev_out], c.dz);
+            ++tk; ev_phase = 0;
+            break;
+          }
+          op.W = p.Wfin + static_cast<size_t>(ev_group) * Hc * p.Ng; op.K = Hc; op.N = p.Ng;
+          op.in = lin; op.ode_layout = true;
+          op.epi.mode = EPI_STORE; op.epi.bias = p.bfin + static_cast<size_t>(ev_group) * p.Ng; op.epi.act = ACT_TANH;
+          op.epi.out0 = c.staging; op.epi.ld0 = R;
+          do_gemm = true;
+          ev_phase = 3;
+          break;
+        }
+        // ev_phase == 3: contraction of the staged group with dX/dt
+        contract_group<RT>(c, ev_group, first_group);
+        first_group = false;
+        ++ev_group;
+        ev_phase = 2;
+        break;
+      }
+      // ================================================================ output i: hidden state -> pose head
+      case PC_POSE: {
+        if (tk >= my_tiles) { tk = 0; pc = ret; break; }
+        const TileArrays T = tile_arrays(p, tile, R);
+        if (po_phase == 0) {
+          build_vector<RT>(c, T, po_rc, false);
+          if (!c.th.producer) {
+            for (int e = c.th.ctid; e < Hc * R; e += ncons) {
+              const int r = e / Hc, h = e - r * Hc;
+              const int b = tile * R + r;
+              if (b < p.B) {
+                const float v = c.bufA[h * R + r];
+                if (p.hout) p.hout[(static_cast<size_t>(b) * S + po_i) * Hc + h] = v;
+                if (po_i == 0) p.z0_out[static_cast<size_t>(b) * Hc + h] = v;
+              }
+            }
+          }
+          op.W = p.Wreg0; op.K = Hc; op.N = kRegHidden; op.in = c.bufA; op.ode_layout = true;
+          op.epi.mode = EPI_STORE; op.epi.bias = p.breg0; op.epi.act = ACT_LEAKY01;
+          op.epi.out0 = c.bufB; op.epi.ld0 = R;
+          do_gemm = true;
+          po_phase = 1;
+          break;
+        }
+        if (!c.th.producer) {
+          for (int e = c.th.ctid; e < R * kPoseDim; e += ncons) {
+            const int r = e / kPoseDim, o = e - r * kPoseDim;
+            const int b = tile * R + r;
+            float acc = 0.f;
+            for (int k = 0; k < kRegHidden; ++k) acc = fmaf(c.bufB[k * R + r], p.Wreg1[o * kRegHidden + k], acc);
+            if (b < p.B) p.pose[(static_cast<size_t>(b) * S + po_i) * kPoseDim + o] = acc + p.breg1[o];
+          }
+          named_bar_sync(1, ncons);
+        }
+        ++tk; po_phase = 0;
+        break;
+      }
+      // ================================================================ main program
+      case PC_POSE0:
+        start_pose(RC_Z, 0.f, 0.f, 0, PC_F0);
+        break;
+      case PC_F0:
+        if (S == 1) { pc = PC_END; break; }
+        if (adaptive) {
+          start_eval(RC_Z, 0, 0.f, static_cast<float>(t_cur), 0, 0, 0, PC_HAIRER_A);
+        } else {
+          grid_i = 0;
+          pc = PC_STEP_BEGIN;
+        }
+        break;
+      case PC_HAIRER_A: {
+        // d0 = rms(y0 / scale), d1 = rms(f0 / scale), scale = atol + |y0| rtol  (joint over the batch)
+        double a = 0.0, b2 = 0.0;
+        if (!c.th.producer) {
+          for (int k2 = 0; k2 < my_tiles; ++k2) {
+            const int tl = static_cast<int>(blockIdx.x) + k2 * static_cast<int>(gridDim.x);
+            const TileArrays T = tile_arrays(p, tl, R);
+            for (int e = c.th.ctid; e < Hc * R; e += ncons) {
+              const int r = e % R;
+              if (tl * R + r >= p.B) continue;
+              const float y = T.Z[e], f = T.K[0][e];
+              const float sc = add_(p.atol, mul_(fabsf(y), p.rtol));
+              const float q0 = __fdiv_rn(y, sc), q1 = __fdiv_rn(f, sc);
+              a += static_cast<double>(q0) * q0; b2 += static_cast<double>(q1) * q1;
+            }
+          }
+        }
+        double sa, sb;
+        grid_reduce2<RT>(c, a, b2, sa, sb);
+        const double d0 = sqrt(sa / elems);
+        d1 = sqrt(sb / elems);
+        h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        start_eval(RC_HAIRER, 0, static_cast<float>(h0), static_cast<float>(t_cur + h0), 0, 1, 0, PC_HAIRER_B);
+        break;
+      }
+      case PC_HAIRER_B: {
+        double a = 0.0;
+        if (!c.th.producer) {
+          for (int k2 = 0; k2 < my_tiles; ++k2) {
+            const int tl = static_cast<int>(blockIdx.x) + k2 * static_cast<int>(gridDim.x);
+            const TileArrays T = tile_arrays(p, tl, R);
+            for (int e = c.th.ctid; e < Hc * R; e += ncons) {
+              const int r = e % R;
+              if (tl * R + r >= p.B) continue;
+              const float sc = add_(p.atol, mul_(fabsf(T.Z[e]), p.rtol));
+              const float q = __fdiv_rn(sub_(T.K[1][e], T.K[0][e]), sc);
+              a += static_cast<double>(q) * q;
+            }
+          }
+        }
+        double sa, sb;
+        grid_reduce2<RT>(c, a, 0.0, sa, sb);
+        const double d2 = sqrt(sa / elems) / h0;
+        double h1;
+        if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+        else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);       // order + 1 with order = 4
+        dt = fmin(100.0 * h0, h1);
+        pc = PC_STEP_BEGIN;
+        break;
+      }
+      case PC_STEP_BEGIN: {
+        if (adaptive) {
+          if (i_out >= S) { pc = PC_END; break; }
+          if (n_steps >= p.max_steps) { status = 1; pc = PC_END; break; }
+          step = dt; t_b = t_cur + dt; on_jump = 0;
+          const double nj = static_cast<double>(next_jump);
+          if (t_cur < nj && nj < t_cur + step) { on_jump = 1; step = nj - t_cur; t_b = nj; }
+          dt_s = static_cast<float>(step); ta_s = static_cast<float>(t_cur); tb_s = static_cast<float>(t_b);
+          st = 1;
+          pc = PC_STAGE;
+        } else {
+          if (grid_i >= grid_n - 1 || i_out >= S) { pc = PC_END; break; }
+          t_cur = grid_time(grid_i); t_b = grid_time(grid_i + 1);
+          dt_s = static_cast<float>(t_b - t_cur); ta_s = static_cast<float>(t_cur); tb_s = static_cast<float>(t_b);
+          st = 0;
+          pc = PC_STAGE;
+        }
+        break;
+      }
+      case PC_STAGE: {
+        if (adaptive) {
+          if (st >= tab.n_stages) { pc = PC_STEP_END; break; }
+          const bool last = kDpC[st] == 1.0f;
+          const float ts = last ? tb_s : add_(ta_s, mul_(kDpC[st], dt_s));
+          const int s_now = st++;
+          // dopri5: y1 is the argument of the last stage
+          start_eval(RC_STAGE, s_now, dt_s, ts, last ? -1 : 0, s_now, s_now == tab.n_stages - 1, PC_STAGE);
+        } else {
+          // 3/8 rule (oracle rk4_38_step)
+          if (st >= 4) { pc = PC_RK4_END; break; }
+          const float third = static_cast<float>(1.0 / 3.0);
+          const int s_now = st++;
+          if (s_now == 0) start_eval(RC_Z, 0, dt_s, ta_s, 0, 0, 0, PC_STAGE);
+          else if (s_now == 1) start_eval(RC_RK4_1, 0, dt_s, add_(ta_s, mul_(dt_s, third)), 0, 1, 0, PC_STAGE);
+          else if (s_now == 2) start_eval(RC_RK4_2, 0, dt_s, add_(ta_s, mul_(dt_s, mul_(2.0f, third))), 0, 2, 0, PC_STAGE);
+          else start_eval(RC_RK4_3, 0, dt_s, tb_s, -1, 3, 0, PC_STAGE);
+        }
+        break;
+      }
+      case PC_STEP_END: {
+        // err = sum_j k_j * fl(e_j dt); ratio = rms(err / (atol + rtol max(|y0|, |y1|))) over the whole batch
+        double a = 0.0;
+        if (!c.th.producer) {
+          for (int k2 = 0; k2 < my_tiles; ++k2) {
+            const int tl = static_cast<int>(blockIdx.x) + k2 * static_cast<int>(gridDim.x);
+            const TileArrays T = tile_arrays(p, tl, R);
+            for (int e = c.th.ctid; e < Hc * R; e += ncons) {
+              const int r = e % R;
+              if (tl * R + r >= p.B) continue;
+              float err = 0.f;
+              bool any = false;
+              for (int j = 0; j < tab.n_stages; ++j) {
+                const float ej = tab.e[j];
+                if (ej == 0.f) continue;
+                const float term = mul_(T.K[j][e], mul_(ej, dt_s));
+                err = any ? add_(err, term) : term;
+                any = true;
+              }
+              const float tol = add_(p.atol, mul_(p.rtol, fmaxf(fabsf(T.Z[e]), fabsf(T.Y1[e]))));
+              const float q = __fdiv_rn(err, tol);
+              a += static_cast<double>(q) * q;
+            }
+          }
+        }
+        double sa, sb;
+        grid_reduce2<RT>(c, a, 0.0, sa, sb);
+        const double ratio = sqrt(sa / elems);
+        ++n_steps;
+        if (!(ratio == ratio) || isinf(ratio)) { status = 2; pc = PC_END; break; }
+        const bool accept = ratio <= 1.0;
+        // next step size (torchdiffeq _optimal_step_size)
+        if (ratio == 0.0) dt = step * 10.0;
+        else {
+          const double dfactor = ratio < 1.0 ? 1.0 : 0.2;
+          dt = step * fmin(10.0, fmax(0.9 / pow(ratio, 0.2), dfactor));
+        }
+        if (accept) { ++n_acc; pc = PC_OUTPUTS; }
+        else pc = PC_STEP_BEGIN;
+        break;
+      }
+      case PC_OUTPUTS: {
+        // every requested time inside the accepted step (t_cur, t_b] comes from its dense output
+        if (i_out < S && !(p.tout[i_out] > t_b)) {
+          const float x = static_cast<float>((p.tout[i_out] - t_cur) / (t_b - t_cur));
+          const int i = i_out++;
+          start_pose(RC_INTERP, dt_s, x, i, PC_OUTPUTS);
+        } else {
+          pc = PC_COMMIT;
+        }
+        break;
+      }
+      case PC_COMMIT: {
+        // z <- y1, k0 <- k6 (FSAL)
+        if (!c.th.producer) {
+          for (int k2 = 0; k2 < my_tiles; ++k2) {
+            const int tl = static_cast<int>(blockIdx.x) + k2 * static_cast<int>(gridDim.x);
+            const TileArrays T = tile_arrays(p, tl, R);
+            const int nvec = Hc * c.rq4;
+            for (int e = c.th.ctid; e < nvec; e += ncons) {
+              const size_t off = static_cast<size_t>(e) * 4;
+              st4(T.Z + off, ld4(T.Y1 + off));
+              st4(T.K[0] + off, ld4(T.K[tab.n_stages - 1] + off));
+            }
+          }
+          named_bar_sync(1, ncons);
+        }
+        t_cur = t_b;
+        if (on_jump) {
+          if (next_jump != nk - 1) ++next_jump;
+          start_eval(RC_Z, 0, 0.f, tb_s, +1, 0, 0, PC_STEP_BEGIN);     // vector field just after the knot
+        } else {
+          pc = PC_STEP_BEGIN;
+        }
+        break;
+      }
+      case PC_RK4_END: {
+        // y1 = y + dt (k1 + 3 (k2 + k3) + k4) * 0.125 -> Y1; outputs on / inside the grid interval
+        if (!c.th.producer) {
+          for (int k2 = 0; k2 < my_tiles; ++k2) {
+            const int tl = static_cast<int>(blockIdx.x) + k2 * static_cast<int>(gridDim.x);
+            const TileArrays T = tile_arrays(p, tl, R);
+            for (int e = c.th.ctid; e < Hc * R; e += ncons) {
+              const float k1 = T.K[0][e], k2v = T.K[1][e], k3 = T.K[2][e], k4 = T.K[3][e];
+              const float s = add_(add_(k1, mul_(3.0f, add_(k2v, k3))), k4);
+              T.Y1[e] = add_(T.Z[e], mul_(mul_(dt_s, s), 0.125f));
+            }
+          }
+          named_bar_sync(1, ncons);
+        }
+        ++n_steps; ++n_acc;
+        pc = PC_AFTER_JUMP;      // reused as the rk4 output loop
+        break;
+      }
+      case PC_AFTER_JUMP: {
+        if (i_out < S && !(t_b < p.tout[i_out])) {
+          const int i = i_out++;
+          if (t_b == p.tout[i]) start_pose(RC_Y1, dt_s, 0.f, i, PC_AFTER_JUMP);
+          else start_pose(RC_LERP, dt_s, static_cast<float>((p.tout[i] - t_cur) / (t_b - t_cur)), i, PC_AFTER_JUMP);
+        } else {
+          if (!c.th.producer) {
+            for (int k2 = 0; k2 < my_tiles; ++k2) {
+              const int tl = static_cast<int>(blockIdx.x) + k2 * static_cast<int>(gridDim.x);
+              const TileArrays T = tile_arrays(p, tl, R);
+              const int nvec = Hc * c.rq4;
+              for (int e = c.th.ctid; e < nvec; e += ncons) {
+                const size_t off = static_cast<size_t>(e) * 4;
+                st4(T.Z + off, ld4(T.Y1 + off));
+              }
+            }
+            named_bar_sync(1, ncons);
+          }
+          ++grid_i;
+          pc = PC_STEP_BEGIN;
+        }
+        break;
+      }
+      default:
+        pc = PC_END;
+        break;
+    }
+    if (do_gemm) tile_gemm<RT, LL>(c.ring, c.pos, c.th, op.W, op.K, op.N, op.in, op.ode_layout, op.epi);
+  }
+
+  if (blockIdx.x == 0 && tid == 0 && prm.stats) {
+    prm.stats[0] = n_steps; prm.stats[1] = n_acc; prm.stats[2] = n_f; prm.stats[3] = status;
+  }
+}
+
+template <int RT, int LL>
+static cudaError_t launch_cde(const CdeParams& prm, const DevTableau& tab, int grid, size_t smem_bytes,
+                              cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(cde_fwd_kernel<RT, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem_bytes));
+  if (err != cudaSuccess) return err;
+  // cooperative launch: the grid-wide reductions need every CTA resident
+  void* args[] = {const_cast<CdeParams*>(&prm), const_cast<DevTableau*>(&tab)};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(cde_fwd_kernel<RT, LL>), dim3(grid),
+                                     dim3(128 * LL + 32), args, smem_bytes, stream);
+}
+
+cudaError_t launch_cde_fwd(const CdeParams& prm, const DevTableau& tab, int RT, int LL, int grid,
+                           size_t smem_bytes, cudaStream_t stream) {
+  if (RT == 8 && LL == 1) return launch_cde<8, 1>(prm, tab, grid, smem_bytes, stream);
+  if (RT == 8 && LL == 2) return launch_cde<8, 2>(prm, tab, grid, smem_bytes, stream);
+  if (RT == 4 && LL == 1) return launch_cde<4, 1>(prm, tab, grid, smem_bytes, stream);
+  return cudaErrorInvalidValue;
+}
+
+// ---- weight packing of the final Linear: W [Hc*C][Hc] (row h*C + c) -> groups [g][k][c_local*Hc + h]
+__global__ void cde_pack_final_kernel(const float* __restrict__ W, const float* __restrict__ b, int Hc, int C,
+                                      int Gc, int ngroups, float* __restrict__ Wp, float* __restrict__ bp) {
+  const int Ng = Gc * Hc;
+  const size_t total = static_cast<size_t>(ngroups) * Hc * Ng;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i % Ng);
+    const int k = static_cast<int>((i / Ng) % Hc);
+    const int g = static_cast<int>(i / (static_cast<size_t>(Ng) * Hc));
+    const int cl = n / Hc, h = n - cl * Hc;
+    const int ch = g * Gc + cl;
+    Wp[i] = ch < C ? W[(static_cast<size_t>(h) * C + ch) * Hc + k] : 0.f;
+    if (k == 0) bp[static_cast<size_t>(g) * Ng + n] = ch < C ? b[static_cast<size_t>(h) * C + ch] : 0.f;
+  }
+}
+
+cudaError_t cde_pack_final(const float* W, const float* b, int Hc, int C, int Gc, int ngroups, float* Wp,
+                           float* bp, cudaStream_t stream) {
+  cde_pack_final_kernel<<<592, 256, 0, stream>>>(W, b, Hc, C, Gc, ngroups, Wp, bp);
+  return cudaGetLastError();
+}
+
+}  // namespace odevio

@@ -316,3 +316,160 @@ class PoseODERNN(nn.Module):
             what = {1: "max_steps reached", 2: "non-finite error norm",
                     3: "more solver iterations per interval than ode_ckpt_loops (training checkpoints)"}.get(bad, str(bad))
             raise RuntimeError(f"ODE solve failed for some rows: {what}")
+
+
+class PoseCDE(nn.Module):
+    """Neural-CDE pose regressor (reference src/models/PoseCDE.py:41-112); ``forward`` launches the
+    fused cooperative sm_100a kernel (``odevio_cde_forward``).
+
+    Same constructor namespace, attributes and state_dict keys as the reference: ``fuse``,
+    ``reduction_net`` (constructed, never used -- PoseCDE.py:53-57 -- so the fused feature width must
+    equal ``cde_hidden_dim``), ``initial``, ``cde_func``, ``regressor``; eval-mode ``history`` growth
+    and absolute eval timestamps (PoseCDE.py:81,88-92) are reproduced.  Returns ``(poses, z0)``.
+
+    Optional ``opt`` attributes (reference values are the defaults): ``cde_interp`` "linear"
+    (rectilinear, integrated over batch row 0's times in seconds) | "cubic" (north_star: Hermite
+    cubics with backward differences, integrated over the knot grid), ``cde_atol`` 1e-6,
+    ``cde_rtol`` 1e-4 (PoseCDE.py:101), ``cde_step_size`` (fixed-grid rk4), ``cde_max_steps``,
+    ``cde_rows_per_tile``.  The reference's ``adjoint`` flag only changes how gradients are computed;
+    the fused backward for the CDE path is not built yet, so ``forward`` under autograd raises.
+    """
+
+    SOLVERS = ("dopri5", "rk4")
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.adjoint = getattr(opt, "adjoint", False)
+        self.f_len = opt.v_f_len + opt.i_f_len
+        self.input_dim = opt.cde_hidden_dim + 1
+        self.cde_hidden_dim = opt.cde_hidden_dim
+        self.cde_num_layers = getattr(opt, "cde_num_layers", 3)        # unused, as in the reference
+        self.cde_fn_num_layers = opt.cde_fn_num_layers
+        self.fuse_method = opt.fuse_method
+        self.fuse = FusionModule(self.f_len, opt.fuse_method)
+        self.reduction_net = nn.Sequential(nn.Linear(self.f_len, self.f_len // 2), nn.LeakyReLU(0.1, inplace=True),
+                                           nn.Linear(self.f_len // 2, opt.cde_hidden_dim))
+        self.initial = nn.Sequential(nn.Linear(opt.cde_hidden_dim + 1, opt.cde_hidden_dim), nn.Tanh())
+        self.cde_func = CDEFunc(feature_dim=self.input_dim, hidden_dim=opt.cde_hidden_dim,
+                                num_hidden_layers=opt.cde_fn_num_layers, activation=opt.cde_activation_fn)
+        self.regressor = nn.Sequential(nn.Linear(self.cde_hidden_dim, 128), nn.LeakyReLU(0.1, inplace=True),
+                                       nn.Linear(128, 6))
+        if opt.cde_solver not in self.SOLVERS:
+            raise ValueError(f"Solver {opt.cde_solver} not supported")
+        self.solver = opt.cde_solver
+        self.interp = getattr(opt, "cde_interp", "linear")
+        if self.interp not in _lib.CDE_INTERP:
+            raise ValueError(f"control path {self.interp} not supported")
+        self.atol = float(getattr(opt, "cde_atol", 1e-6))
+        self.rtol = float(getattr(opt, "cde_rtol", 1e-4))
+        self.step_size = getattr(opt, "cde_step_size", None)
+        self.max_steps = int(getattr(opt, "cde_max_steps", 100000))
+        self.rows_per_tile = int(getattr(opt, "cde_rows_per_tile", 0))
+        self.history = None          # (tobs [B,n], fv [B,n,.], fi [B,n,.] | None) in eval mode
+        self.last_stats = None       # int32 [4]: n_steps, n_accepted, n_f_evals, status
+        self.last_hidden = None      # [B,S,Hc]
+
+    def get_reduction_net_params(self):
+        return self.reduction_net.parameters()
+
+    def get_regressor_params(self):
+        return self.regressor.parameters()
+
+    def get_other_params(self):
+        return [p for n, p in self.named_parameters() if not n.startswith("regressor")]
+
+    def forward(self, fv, fi, ts, prev=None, do_profile=False):
+        lib = _lib.load()
+        if not fv.is_cuda:
+            raise _lib.OdevioError("PoseCDE.forward needs CUDA tensors: odevio_b200 has no CPU path")
+        if self.f_len != self.cde_hidden_dim:
+            raise _lib.OdevioError(f"PoseCDE needs v_f_len + i_f_len == cde_hidden_dim (reduction_net is unused in "
+                                   f"the reference, PoseCDE.py:53-57,62): {self.f_len} != {self.cde_hidden_dim}")
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or fv.requires_grad):
+            raise _lib.OdevioError("odevio_b200: the fused backward of the CDE path is not built; run PoseCDE "
+                                   "under torch.no_grad()")
+        B, S = fv.shape[0], fv.shape[1]
+        dev = fv.device
+        if self.fuse_method == "cat":
+            fvc, fic, Dv = _f32c(fv, "fv"), _f32c(fi, "fi"), fv.shape[2]
+        else:
+            fvc, fic, Dv = _f32c(self.fuse(fv, fi), "fused"), None, self.f_len
+        ts = _f32c(ts, "ts")
+        ts_diff = (ts - ts[:, :1]) if self.training else ts                       # PoseCDE.py:81
+        tobs = ts_diff[:, 1:].contiguous()
+        if not self.training:                                                     # PoseCDE.py:88-92
+            if prev is not None and self.history is not None:
+                h_t, h_v, h_i = self.history
+                tobs = torch.cat([h_t, tobs], 1).contiguous()
+                fvc = torch.cat([h_v, fvc], 1).contiguous()
+                fic = None if fic is None else torch.cat([h_i, fic], 1).contiguous()
+            self.history = (tobs, fvc, fic)
+        else:
+            self.history = None
+        So = tobs.shape[1]
+        if self.interp == "linear":
+            tout = ts_diff[0, 1:].double().contiguous()       # batch row 0's times, seconds (PoseCDE.py:101)
+        else:
+            tout = torch.arange(So - S, So, dtype=torch.float64, device=dev)
+        z0_in = None if prev is None else _f32c(prev, "prev")
+        if z0_in is not None and tuple(z0_in.shape) != (B, self.cde_hidden_dim):
+            raise _lib.OdevioError(f"prev must be [B,Hc]={B, self.cde_hidden_dim}, got {tuple(z0_in.shape)}")
+
+        cfg = _lib.default_cde_cfg()
+        cfg.B, cfg.S, cfg.So, cfg.Hc = B, S, So, self.cde_hidden_dim
+        cfg.n_layers = self.cde_fn_num_layers
+        cfg.activation = _lib.ACT[self.cde_func.activation]
+        cfg.solver, cfg.interp = _lib.CDE_SOLVER[self.solver], _lib.CDE_INTERP[self.interp]
+        cfg.atol, cfg.rtol = self.atol, self.rtol
+        step = self.step_size
+        if step is None and self.solver == "rk4" and self.interp == "linear":
+            step = 1.0            # torchcde injects min(diff(grid_points)) for fixed-grid solvers (SURVEY.md A.2)
+        cfg.step_size = float(step or 0.0)
+        cfg.max_steps, cfg.rows_per_tile = self.max_steps, self.rows_per_tile
+        nbytes = lib.odevio_cde_workspace_bytes(C.byref(cfg))
+        if nbytes == 0:
+            raise _lib.OdevioError(f"unsupported PoseCDE configuration for the fused kernel (Hc={cfg.Hc}, "
+                                   f"n={cfg.n_layers}, S={S}, So={So})")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        pose = torch.empty(B, S, 6, dtype=torch.float32, device=dev)
+        z0 = torch.empty(B, self.cde_hidden_dim, dtype=torch.float32, device=dev)
+        hidden = torch.empty(B, S, self.cde_hidden_dim, dtype=torch.float32, device=dev)
+        stats = torch.zeros(4, dtype=torch.int32, device=dev)
+        w = _lib.CdeWeights()
+        keep = []
+
+        def ptr(p, name):
+            t = _f32c(p.detach(), name)
+            keep.append(t)
+            return _lib.dptr(t, name)
+
+        for j, lin in enumerate(self.cde_func.linears()):
+            w.cde_w[j] = ptr(lin.weight, f"cde_func.net.{2 * j}.weight")
+            w.cde_b[j] = ptr(lin.bias, f"cde_func.net.{2 * j}.bias")
+        w.init_w, w.init_b = ptr(self.initial[0].weight, "initial.0.weight"), ptr(self.initial[0].bias, "initial.0.bias")
+        w.reg_w0, w.reg_b0 = ptr(self.regressor[0].weight, "regressor.0.weight"), ptr(self.regressor[0].bias, "regressor.0.bias")
+        w.reg_w1, w.reg_b1 = ptr(self.regressor[2].weight, "regressor.2.weight"), ptr(self.regressor[2].bias, "regressor.2.bias")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if do_profile:
+            torch.cuda.nvtx.range_push("cdeint")
+        with torch.cuda.device(dev):
+            rc = lib.odevio_cde_forward(
+                C.byref(cfg), C.byref(w), _lib.dptr(tobs, "tobs"), _lib.dptr(fvc, "fv"), _lib.dptr(fic, "fi"), Dv,
+                _lib.dptr(tout, "tout"), _lib.dptr(z0_in, "prev"), _lib.dptr(pose), _lib.dptr(z0),
+                _lib.dptr(hidden), _lib.dptr(stats), _lib.dptr(ws), nbytes, C.c_void_p(stream))
+        if do_profile:
+            torch.cuda.nvtx.range_pop()
+        _lib.check(rc)
+        del keep
+        self.last_stats, self.last_hidden = stats, hidden
+        return pose, z0                                                          # PoseCDE.py:103 returns z0
+
+    def check_status(self):
+        """Synchronising check of the last forward's solver status."""
+        if self.last_stats is None:
+            return
+        bad = int(self.last_stats[3].item())
+        if bad != 0:
+            what = {1: "max_steps reached", 2: "non-finite error norm"}.get(bad, str(bad))
+            raise RuntimeError(f"CDE solve failed: {what}")
