@@ -13,6 +13,7 @@ Run HERE (the authoring container), where /root/reference is mounted:
                         reproduce them)
      odernn_<case>.pt   oracle PoseODERNN forward on seeded weights / inputs / timestamps:
                         pose, h, n_steps, n_accepted
+     cde_<case>.pt      oracle PoseCDE forward: pose, z0, n_steps, n_accepted, n_f_evals
 /root/reference does not exist on the GPU box; nothing at test time reads it.
 """
 
@@ -112,6 +113,46 @@ def make_odernn_goldens():
         print("wrote", f"odernn_{name}.pt")
 
 
+CDE_CASES = {
+    # name: (opt overrides, B, S, irregular, feature scale)
+    "linear_dopri5_ref": (dict(cde_solver="dopri5", cde_interp="linear"), 6, 6, False, 0.2),
+    "linear_dopri5_knots": (dict(cde_solver="dopri5", cde_interp="linear"), 5, 6, True, 0.2),
+    "cubic_dopri5": (dict(cde_solver="dopri5", cde_interp="cubic", cde_rtol=1e-3), 6, 5, True, 0.2),
+    "cubic_rk4_step": (dict(cde_solver="rk4", cde_interp="cubic", cde_step_size=0.25), 6, 5, True, 0.2),
+    "linear_rk4": (dict(cde_solver="rk4", cde_interp="linear"), 6, 6, True, 0.2),
+}
+CDE_SMALL = dict(v_f_len=16, i_f_len=16, cde_hidden_dim=32, cde_fn_num_layers=2)
+
+
+def make_cde_goldens():
+    from oracle.modules import deepvio_initialization
+    from oracle.pose_cde import OraclePoseCDE
+    from oracle.pose_odernn import default_opt
+    from odevio_b200 import synth
+    for name, (over, B, S, irregular, scale) in CDE_CASES.items():
+        opt_kw = dict(CDE_SMALL, **over)
+        torch.manual_seed(4321)
+        m = OraclePoseCDE(default_opt(**opt_kw))
+        deepvio_initialization(m)
+        g = torch.Generator().manual_seed(98)
+        for n, p in m.named_parameters():
+            if n.endswith("bias"):
+                p.data.normal_(0, 0.05, generator=g)
+        m.train()                                             # relative timestamps (PoseCDE.py:81)
+        fv, fi = synth.features(B, S, 16, 16, seed=4)
+        fv, fi = fv * scale, fi * scale
+        ts = synth.timestamps(B, S, irregular=irregular, seed=4)
+        if name == "linear_dopri5_knots":
+            ts = ts * 4.0                                     # row 0 crosses several integer knots
+        with torch.no_grad():
+            pose, z0 = m(fv, fi, ts)
+        st = m.last_stats
+        torch.save(dict(opt=opt_kw, state={k: v.clone() for k, v in m.state_dict().items()}, fv=fv, fi=fi, ts=ts,
+                        pose=pose, z0=z0, n_steps=st["n_steps"], n_accepted=st["n_accepted"], n_f_evals=st["n_f_evals"]),
+                   os.path.join(OUT, f"cde_{name}.pt"))
+        print("wrote", f"cde_{name}.pt", st["n_steps"], st["n_accepted"], st["n_f_evals"])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if not os.path.isdir(REF):
@@ -119,3 +160,4 @@ if __name__ == "__main__":
     sys.path.insert(0, ROOT)
     check_against_reference()
     make_odernn_goldens()
+    make_cde_goldens()

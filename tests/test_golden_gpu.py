@@ -42,3 +42,24 @@ def test_kernel_reproduces_odernn_golden(cuda_device, path):
     else:
         mism = ((steps[..., 0] != fx["n_steps"]) | (steps[..., 1] != fx["n_accepted"])).float().mean().item()
         assert mism <= 0.5, mism          # knife-edge ramp-up decisions in interval 0 only
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "cde_*.pt"))),
+                         ids=lambda p: os.path.basename(p)[4:-3])
+def test_kernel_reproduces_cde_golden(cuda_device, path):
+    import odevio_b200
+    fx = torch.load(path)
+    mod = odevio_b200.PoseCDE(default_opt(**fx["opt"]))
+    mod.load_state_dict(fx["state"])
+    mod = mod.to(cuda_device).train()
+    dev = cuda_device
+    with torch.no_grad():
+        pose, z0 = mod(fx["fv"].to(dev), fx["fi"].to(dev), fx["ts"].to(dev))
+    mod.check_status()
+    name = os.path.basename(path)[4:-3]
+    tol = 1e-5 if "rk4" in name or "linear" in name else 1e-4     # adaptive cubic: solver-tolerance scale
+    assert (pose.cpu() - fx["pose"]).abs().max() <= tol * fx["pose"].abs().max()
+    assert (z0.cpu() - fx["z0"]).abs().max() <= 1e-5 * fx["z0"].abs().max()
+    st = mod.last_stats.cpu().tolist()
+    if "cubic_dopri5" not in name:
+        assert tuple(st[:3]) == (fx["n_steps"], fx["n_accepted"], fx["n_f_evals"])
