@@ -335,8 +335,129 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def _device_setup(local_rank, world):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the odevio_b200 path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    return dev
+
+
+def run_train(args, rank, world, local_rank):
+    """BASELINE configs[3]: PoseODERNN training step (forward + fused backward + NCCL gradient
+    all-reduce + clip + Adam), global batch 4096 sharded over the ranks (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    import odevio_b200
+    from odevio_b200 import distributed as D, synth
+    dev = _device_setup(local_rank, world)
+    w = WORKLOAD
+    GB, S = args.train_batch, w["S"]
+    a, b = D.shard_rows(GB, rank, world)
+    model = odevio_b200.PoseODERNN(make_opt())
+    init_like_deepvio(model, seed=0)
+    model = model.to(dev).train()
+    opt = D.make_optimizer(model, lr=1e-4)
+    fv, fi = synth.features(GB, S, w["v_f_len"], w["i_f_len"], seed=0)
+    ts = synth.timestamps(GB, S, irregular=True, seed=0)
+    gts = 0.01 * torch.randn(GB, S, 6, generator=torch.Generator().manual_seed(1))
+    fv, fi, ts, gts = (t[a:b].to(dev) for t in (fv, fi, ts, gts))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 1)):
+        D.train_step(model, opt, fv, fi, ts, gts, world_size=world)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = D.train_step(model, opt, fv, fi, ts, gts, world_size=world)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        per = ms.item() / args.steps
+        print(json.dumps({
+            "metric": "training_" + METRIC, "value": GB * S / (per * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": per, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "PoseODERNN training step (fwd + fused bwd + grad all-reduce + clip + Adam), "
+                                   f"global batch {GB} sharded over {world} GPU(s), dopri5 rtol=1e-3, BASELINE configs[3]",
+                       "global_batch": GB, "loss": float(loss)},
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_cde(args, rank, world, local_rank):
+    """BASELINE configs[2]: PoseCDE forward, B=1024, Hc = F = 128, cubic control path (and the
+    reference's rectilinear-linear path), dopri5 atol=1e-6 rtol=1e-4.  Replicas only for N > 1
+    (the batch-joint controller is not shard-invariant)."""
+    import torch
+    import odevio_b200
+    from types import SimpleNamespace
+    from odevio_b200 import synth
+    dev = _device_setup(local_rank, 1)
+    B, S, Hc = 1024, 10, 128
+    out = {}
+    for interp in ("cubic", "linear"):
+        opt = SimpleNamespace(v_f_len=Hc // 2, i_f_len=Hc // 2, fuse_method="cat", cde_hidden_dim=Hc,
+                              cde_fn_num_layers=3, cde_num_layers=3, cde_activation_fn="tanh", cde_solver="dopri5",
+                              adjoint=False, cde_interp=interp)
+        model = odevio_b200.PoseCDE(opt)
+        torch.manual_seed(0)
+        for m in model.modules():
+            if isinstance(m, torch.nn.Linear):
+                torch.nn.init.kaiming_normal_(m.weight.data); m.bias.data.zero_()
+        model = model.to(dev).train()
+        fv, fi = synth.features(B, S, Hc // 2, Hc // 2, seed=rank)
+        ts = synth.timestamps(B, S, irregular=True, seed=rank)
+        fv, fi, ts = (0.2 * fv).to(dev), (0.2 * fi).to(dev), ts.to(dev)
+        with torch.no_grad():
+            for _ in range(max(args.warmup, 3)):
+                model(fv, fi, ts)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                model(fv, fi, ts)
+            e1.record()
+            torch.cuda.synchronize(dev)
+        per = e0.elapsed_time(e1) / args.steps
+        st = model.last_stats.tolist()
+        C = Hc + 1
+        flops = st[2] * B * 2.0 * (3 * Hc * Hc + Hc * Hc * C + Hc * C)          # SURVEY.md 8d, per vf eval
+        out[interp] = {"ms_per_step": per, "seq_steps_per_s": B * S / (per * 1e-3), "solver_steps": st[0],
+                       "accepted": st[1], "vf_evals": st[2], "status": st[3],
+                       # nominal = every channel of the final Linear counted; the rectilinear path's
+                       # time-only segments legitimately skip all but one channel group
+                       ("algorithmic_tflops" if interp == "cubic" else "nominal_tflops_incl_skipped_channels"):
+                           flops / (per * 1e-3) / 1e12}
+    if rank == 0:
+        print(json.dumps({"metric": "cde_" + METRIC, "value": out["cubic"]["seq_steps_per_s"], "unit": UNIT,
+                          "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": out["cubic"]["ms_per_step"], "higher_is_better": True, "scaling": "replicas only",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "PoseCDE forward, B=1024, S=10, Hc=F=128, n=3, dopri5 atol=1e-6 "
+                                                 "rtol=1e-4, cubic (north_star) control path; 'linear' = reference "
+                                                 "rectilinear path; BASELINE configs[2]"},
+                          "detail": out}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="odernn_fwd", choices=["odernn_fwd", "odernn_train", "cde"],
+                    help="odernn_fwd = the headline (BASELINE configs[1]); the others are extra measurements")
+    ap.add_argument("--train-batch", type=int, default=4096)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -351,7 +472,12 @@ def main():
         return
     if world == 1 and args.gpus > 1:
         raise SystemExit("bench.py: for --gpus N > 1 launch with torch.distributed.run (one rank per GPU)")
-    run_ours(args, rank, world, local_rank)
+    if args.workload == "odernn_train":
+        run_train(args, rank, world, local_rank)
+    elif args.workload == "cde":
+        run_cde(args, rank, world, local_rank)
+    else:
+        run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -57,7 +57,9 @@ def test_kernel_reproduces_cde_golden(cuda_device, path):
         pose, z0 = mod(fx["fv"].to(dev), fx["fi"].to(dev), fx["ts"].to(dev))
     mod.check_status()
     name = os.path.basename(path)[4:-3]
-    tol = 1e-5 if "rk4" in name or "linear" in name else 1e-4     # adaptive cubic: solver-tolerance scale
+    # adaptive cubic (rtol = 1e-3): step sizes depend continuously on the error ratio, so fp32 rounding
+    # moves the solution at the solver-tolerance scale (tests/test_cde_gpu.py: conditioning())
+    tol = 1e-5 if "rk4" in name or "linear" in name else 1e-3
     assert (pose.cpu() - fx["pose"]).abs().max() <= tol * fx["pose"].abs().max()
     assert (z0.cpu() - fx["z0"]).abs().max() <= 1e-5 * fx["z0"].abs().max()
     st = mod.last_stats.cpu().tolist()
