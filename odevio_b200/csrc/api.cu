@@ -22,6 +22,11 @@ cudaError_t launch_cde_fwd(const CdeParams& prm, const DevTableau& tab, int RT, 
 cudaError_t cde_pack_final(const float* W, const float* b, int Hc, int C, int Gc, int ngroups, float* Wp,
                            float* bp, cudaStream_t stream);
 int wgrad_splits(long long M, int N, int K, int nsm);
+int wgrad_tc_bn(int K);
+int wgrad_tc_splits(long long nblocks, int N, int K, int nsm);
+cudaError_t wgrad_linear_tc(const float* Ghi, const float* Glo, const float* Ahi, const float* Alo,
+                            long long nblocks, int N, int K, int R, float* dW, float* db, float* part, int nsm,
+                            cudaStream_t stream);
 cudaError_t wgrad_linear(const float* G, int ldg, const float* A, int lda, long long M, int N, int K,
                          float* dW0, float* dW1, int k_split, float* db0, float* db1, float* part, int nsm,
                          cudaStream_t stream);
@@ -234,7 +239,7 @@ struct BwdPlan {
   size_t buf_floats, stage_floats, smem_bytes;
   size_t off_Wode[kMaxLinears], off_Wreg0;
   size_t off_scratch, scratch_floats_per_cta;
-  size_t off_recA_ode[kMaxLinears], off_recG_ode[kMaxLinears];
+  size_t off_recA_ode[kMaxLinears], off_recG_ode[kMaxLinears], off_recA_ode_lo[kMaxLinears], off_recG_ode_lo[kMaxLinears];
   size_t off_recA_rnn[kMaxRnnLayers], off_recG_rnn[kMaxRnnLayers];
   size_t off_recA_reg0, off_recG_reg0, off_recA_reg1, off_recG_reg1;
   size_t off_part, part_floats;
@@ -243,7 +248,9 @@ struct BwdPlan {
 };
 
 int plan_odernn_bwd(const odevio_odernn_cfg& c, const OdePlan& pl, long long ode_rows, BwdPlan& bp) {
-  if (ode_rows < 0) return ODEVIO_E_SHAPE;
+  if (ode_rows < 0 || ode_rows % pl.R) return ODEVIO_E_SHAPE;
+  // the ODEFunc weight gradients run on tcgen05 (wgrad_tc.cu): 128-row output tiles, 8-row k-steps
+  if (pl.R % 8 || pl.R > 32 || c.D % 128 || c.H % 128) return ODEVIO_E_SHAPE;
   DevTableau tb;
   if (!make_tableau(c.solver, tb)) return ODEVIO_E_ENUM;
   bp.ns = tb.ssal ? tb.n_stages - 1 : tb.n_stages;
@@ -269,7 +276,9 @@ int plan_odernn_bwd(const odevio_odernn_cfg& c, const OdePlan& pl, long long ode
   const size_t M = static_cast<size_t>(ode_rows);
   for (int j = 0; j < NL; ++j) {
     bp.off_recA_ode[j] = take(M * pl.Kode[j]);
+    bp.off_recA_ode_lo[j] = take(M * pl.Kode[j]);
     bp.off_recG_ode[j] = take(M * pl.Node[j]);
+    bp.off_recG_ode_lo[j] = take(M * pl.Node[j]);
   }
   bp.jump_rows = static_cast<long long>(pl.ntiles) * c.S * pl.RT;
   const size_t MJ = static_cast<size_t>(bp.jump_rows);
@@ -288,7 +297,11 @@ int plan_odernn_bwd(const odevio_odernn_cfg& c, const OdePlan& pl, long long ode
     if (v < static_cast<size_t>(256) * n) v = static_cast<size_t>(256) * n;
     if (v > part) part = v;
   };
-  for (int j = 0; j < NL; ++j) need(ode_rows, pl.Node[j], pl.Kode[j]);
+  for (int j = 0; j < NL; ++j) {
+    size_t v = static_cast<size_t>(wgrad_tc_splits(ode_rows / pl.R, pl.Node[j], pl.Kode[j], pl.nsm)) * pl.Node[j] * pl.Kode[j];
+    if (v < static_cast<size_t>(256) * pl.Node[j]) v = static_cast<size_t>(256) * pl.Node[j];
+    if (v > part) part = v;
+  }
   need(bp.jump_rows, c.D, 2 * c.D);
   need(bp.jump_rows, kRegHidden, c.D);
   need(bp.jump_rows, kPoseDim, kRegHidden);
@@ -580,6 +593,7 @@ int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn
     p.Wode[j] = dst; p.bode[j] = w->ode_b[j]; p.Kode[j] = pl.Kode[j]; p.Node[j] = pl.Node[j];
     p.Wode_raw[j] = w->ode_w[j];
     p.recA_ode[j] = ws + bp.off_recA_ode[j]; p.recG_ode[j] = ws + bp.off_recG_ode[j];
+    p.recA_ode_lo[j] = ws + bp.off_recA_ode_lo[j]; p.recG_ode_lo[j] = ws + bp.off_recG_ode_lo[j];
   }
   for (int l = 0; l < c.L; ++l) {
     p.Wih_raw[l] = w->rnn_w_ih[l]; p.Whh_raw[l] = w->rnn_w_hh[l];
@@ -606,9 +620,9 @@ int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn
 
   // ---- deferred weight gradients: one dense GEMM per Linear over its record stream
   float* part = ws + bp.off_part;
-  for (int j = 0; j < NL; ++j)
-    ODEVIO_CUDA_TRY(wgrad_linear(p.recG_ode[j], pl.Node[j], p.recA_ode[j], pl.Kode[j], ode_rows, pl.Node[j], pl.Kode[j],
-                                 g->ode_w[j], nullptr, 0, g->ode_b[j], nullptr, part, pl.nsm, stream));
+  for (int j = 0; j < NL; ++j)       // ODEFunc Linears: tcgen05 3xTF32 GEMMs over the block-format streams
+    ODEVIO_CUDA_TRY(wgrad_linear_tc(p.recG_ode[j], p.recG_ode_lo[j], p.recA_ode[j], p.recA_ode_lo[j], ode_rows / pl.R,
+                                    pl.Node[j], pl.Kode[j], pl.R, g->ode_w[j], g->ode_b[j], part, pl.nsm, stream));
   for (int l = 0; l < c.L; ++l)
     ODEVIO_CUDA_TRY(wgrad_linear(p.recG_rnn[l], D, p.recA_rnn[l], 2 * D, bp.jump_rows, D, 2 * D,
                                  g->rnn_w_ih[l], g->rnn_w_hh[l], D, g->rnn_b_ih[l], g->rnn_b_hh[l], part, pl.nsm, stream));

@@ -44,10 +44,12 @@ __device__ __forceinline__ float4 fma4s(float4 a, float s, float4 c) {
   return make_float4(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z), fmaf(a.w, s, c.w));
 }
 
-// scatter a float4 (4 rows of feature d) into a row-major record stream
-__device__ __forceinline__ void rec_put4(float* rec, long long row0, int ld, int d, float4 v) {
-  float* p = rec + row0 * ld + d;
-  p[0] = v.x; p[ld] = v.y; p[2 * static_cast<size_t>(ld)] = v.z; p[3 * static_cast<size_t>(ld)] = v.w;
+// one float4 (rows 4q .. 4q+3 of feature d) into block `blk` of a tcgen05 operand stream (hi / lo)
+__device__ __forceinline__ void rec_put4(float* hi, float* lo, long long blk, int F, int R, int d, int q, float4 v) {
+  const size_t o = static_cast<size_t>(blk) * F * R + rec_block_offset(d, 4 * q, R);
+  const float4 h4 = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  st4(hi + o, h4);
+  st4(lo + o, make_float4(v.x - h4.x, v.y - h4.y, v.z - h4.z, v.w - h4.w));
 }
 
 // z_j = y0 + dt * sum_{m<j} a_jm k_m  -> bufA (T-layout) and the layer-0 input record
@@ -81,7 +83,7 @@ __device__ __forceinline__ void stage_input_b(BCtx<RT>& c, const float* Y0, int 
     }
     st4(c.bufA + off, y);
     const int d = e / c.rq4;
-    rec_put4(p.recA_ode[0], row0 + 4 * c.rq, p.D, d, y);
+    rec_put4(p.recA_ode[0], p.recA_ode_lo[0], row0, p.D, c.R, d, c.rq, y);
   }
   named_bar_sync(1, c.th.ncons);
 }
@@ -110,7 +112,7 @@ __device__ __forceinline__ void stage_grad_b(BCtx<RT>& c, int j, long long row0)
     g.w = up.w ? dt.w * acc.w * (1.f - k.w * k.w) : 0.f;
     st4(c.bufA + off, g);
     const int d = e / c.rq4;
-    rec_put4(p.recG_ode[NLm1], row0 + 4 * c.rq, p.D, d, g);
+    rec_put4(p.recG_ode[NLm1], p.recG_ode_lo[NLm1], row0, p.D, c.R, d, c.rq, g);
   }
   named_bar_sync(1, c.th.ncons);
 }
@@ -215,7 +217,7 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
     int i = S - 1, l = 0, it = 0, j = 0, lam = 0;
     float* lin = c.bufA; float* lout = c.bufB;
     const float* Y0 = nullptr;
-    long long row_it = 0;                 // first ODE-stream row of the current iteration
+    long long row_it = 0;                 // first ODE-stream block of the current iteration (one block per stage)
     while (ph != BP_TILE_END) {
       GemmOpB op{};
       bool do_gemm = false;
@@ -340,13 +342,13 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
             c.upd[c.th.ctid] = reinterpret_cast<const int*>(slot + arr + R)[c.th.ctid];
           }
           __syncthreads();
-          row_it = p.rec_base[static_cast<size_t>(tile) * S + i] + static_cast<long long>(it) * p.ns * R;
+          row_it = p.rec_base[static_cast<size_t>(tile) * S + i] / R + static_cast<long long>(it) * p.ns;
           j = 0;
           ph = BP_RSTAGE;
           break;
         }
         case BP_RSTAGE:
-          stage_input_b<RT>(c, Y0, j, row_it + static_cast<long long>(j) * R);
+          stage_input_b<RT>(c, Y0, j, row_it + j);
           lam = 0; lin = c.bufA; lout = c.bufB;
           ph = BP_RLAYER;
           break;
@@ -359,8 +361,8 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
           } else {
             op.epi.act = p.act; op.epi.out0 = lout;
             op.epi.out1 = c.HS + (static_cast<size_t>(j) * (NL - 1) + lam) * harr; op.epi.ld1 = R;
-            op.epi.rec = p.recA_ode[lam + 1]; op.epi.rec_row0 = row_it + static_cast<long long>(j) * R;
-            op.epi.rec_ld = H; op.epi.rec_rstride = 1; op.epi.rec_valid = RT;
+            op.epi.rec = p.recA_ode[lam + 1]; op.epi.rec_lo = p.recA_ode_lo[lam + 1];
+            op.epi.rec_row0 = row_it + j; op.epi.rec_ld = H; op.epi.rec_rstride = R; op.epi.rec_valid = RT;
           }
           do_gemm = true;
           float* t = lin; lin = lout; lout = t;
@@ -371,7 +373,7 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
           break;
         }
         case BP_BSTAGE:
-          stage_grad_b<RT>(c, j, row_it + static_cast<long long>(j) * R);
+          stage_grad_b<RT>(c, j, row_it + j);
           lam = NL - 1; lin = c.bufA; lout = c.bufB;
           ph = BP_BLAYER;
           break;
@@ -383,8 +385,8 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
             op.epi.mode = EPI_MUL_DACT; op.epi.act = p.act;
             op.epi.hs = c.HS + (static_cast<size_t>(j) * (NL - 1) + (lam - 1)) * harr; op.epi.ldh = R;
             op.epi.out0 = lout;
-            op.epi.rec = p.recG_ode[lam - 1]; op.epi.rec_row0 = row_it + static_cast<long long>(j) * R;
-            op.epi.rec_ld = H; op.epi.rec_rstride = 1; op.epi.rec_valid = RT;
+            op.epi.rec = p.recG_ode[lam - 1]; op.epi.rec_lo = p.recG_ode_lo[lam - 1];
+            op.epi.rec_row0 = row_it + j; op.epi.rec_ld = H; op.epi.rec_rstride = R; op.epi.rec_valid = RT;
           } else {
             op.epi.mode = EPI_STORE; op.epi.act = ACT_NONE; op.epi.out0 = c.GZ[j];
           }

@@ -90,8 +90,10 @@ struct BwdParams {
   // checkpoints written by the forward
   const float* ckpt; const int* nloops; size_t ckpt_floats_per_tile; int CK;
   // record streams (row-major) for the deferred weight-gradient GEMMs
-  const long long* rec_base;                 // [ntiles * S] first ODE-stream row of (tile, interval)
-  float* recA_ode[kMaxLinears]; float* recG_ode[kMaxLinears];     // [M][K_j], [M][N_j]
+  // ODE-layer streams: tcgen05 operand blocks of R rows (tile_gemm.cuh: rec_block_offset), hi / lo parts
+  const long long* rec_base;                 // [ntiles * S] first ODE-stream row of (tile, interval); block = row / R
+  float* recA_ode[kMaxLinears]; float* recG_ode[kMaxLinears];     // hi: [blocks][K_j * R], [blocks][N_j * R]
+  float* recA_ode_lo[kMaxLinears]; float* recG_ode_lo[kMaxLinears];
   float* recA_rnn[kMaxRnnLayers]; float* recG_rnn[kMaxRnnLayers]; // [ntiles*S*RT][2D], [..][D]
   float* recA_reg0; float* recG_reg0;        // [ntiles*S*RT][D], [..][128]
   float* recA_reg1; float* recG_reg1;        // [ntiles*S*RT][128], [..][8] (6 used)

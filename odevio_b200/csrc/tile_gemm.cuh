@@ -65,8 +65,12 @@ struct TileThread {
 //   EPI_MUL_DACT  v = acc * act'(hs[n])      backward through a hidden activation; act' is computed
 //                                            from the saved activation OUTPUT hs (T-layout)
 //   EPI_ADD       v = acc + out0[n]          accumulate into an existing T-layout gradient
-// Optionally the value is also appended to a row-major record stream (one row per tile row):
-//   rec[(rec_row0 + (rb * RT + r) * rec_rstride) * rec_ld + n]   for r < rec_valid.
+// Optionally the value is also appended to a record stream:
+//   rec_lo == nullptr: row-major, one row per tile row,
+//       rec[(rec_row0 + (rb * RT + r) * rec_rstride) * rec_ld + n]   for r < rec_valid;
+//   rec_lo != nullptr: tcgen05 operand blocks (wgrad_tc.cu) -- block rec_row0 holds the tile's R rows of
+//       all rec_ld features as K-major core matrices [feature/8][R/4][8][4], split into a
+//       TF32-exact high part (rec) and the residual (rec_lo).
 enum { EPI_STORE = 0, EPI_GRU_NEW = 1, EPI_MUL_DACT = 2, EPI_ADD = 3 };
 struct Epilogue {
   int mode;
@@ -76,8 +80,16 @@ struct Epilogue {
   float* out1; int ld1; int off1;   // optional second destination
   const float* rg; const float* zg; const float* hn; const float* hprev;   // EPI_GRU_NEW: [N][RT]
   const float* hs; int ldh; int offh;                                       // EPI_MUL_DACT
-  float* rec; long long rec_row0; int rec_ld; int rec_rstride; int rec_valid;
+  float* rec; float* rec_lo; long long rec_row0; int rec_ld; int rec_rstride; int rec_valid;
 };
+
+// TF32-exact high part of x (low 13 mantissa bits cleared); x - hi is exact in fp32.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// float offset of (feature f, tile row r) inside a record block of R rows (see Epilogue)
+__device__ __forceinline__ size_t rec_block_offset(int f, int r, int R) {
+  return ((static_cast<size_t>(f >> 3) * (R >> 2) + (r >> 2)) * 8 + (f & 7)) * 4 + (r & 3);
+}
 
 // act'(x) expressed through the activation output h = act(x)
 __device__ __forceinline__ float dact_from_output(float h, int act) {
@@ -148,7 +160,18 @@ __device__ __forceinline__ void run_epilogue(const Epilogue& e, int n, int rb, c
       v[4 * q + 2] = acc[4 * q + 2] + o4.z; v[4 * q + 3] = acc[4 * q + 3] + o4.w;
     }
   }
-  if (e.rec) {
+  if (e.rec && e.rec_lo) {
+    // block format: R = rec_rstride rows per block; this thread holds rows rb*RT .. rb*RT + RT - 1 of feature n
+    const int R = e.rec_rstride;
+    const size_t blk = static_cast<size_t>(e.rec_row0) * e.rec_ld * R;
+#pragma unroll
+    for (int q = 0; q < RT / 4; ++q) {
+      const size_t o = blk + rec_block_offset(n, rb * RT + 4 * q, R);
+      const float4 h4 = make_float4(tf32_hi(v[4 * q]), tf32_hi(v[4 * q + 1]), tf32_hi(v[4 * q + 2]), tf32_hi(v[4 * q + 3]));
+      st4(e.rec + o, h4);
+      st4(e.rec_lo + o, make_float4(v[4 * q] - h4.x, v[4 * q + 1] - h4.y, v[4 * q + 2] - h4.z, v[4 * q + 3] - h4.w));
+    }
+  } else if (e.rec) {
     float* rp = e.rec + (e.rec_row0 + static_cast<long long>(rb * RT) * e.rec_rstride) * e.rec_ld + n;
 #pragma unroll
     for (int r = 0; r < RT; ++r)
