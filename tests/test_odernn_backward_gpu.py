@@ -40,7 +40,7 @@ def _grads(model, fv, fi, ts, gts, prev, hT_weight):
     return loss.item(), out, pose.detach().cpu()
 
 
-def _compare(dev, B, S, prev=False, hT_weight=0.0, tol=GRAD_RTOL, **over):
+def _compare(dev, B, S, prev=False, hT_weight=0.0, tol=GRAD_RTOL, conditioning=False, **over):
     ref, mod = make_pair(dev, bias_std=0.05, ode_detach_dt=True, **over)
     ref.train(); mod.train()
     fv, fi, ts = inputs(B, S, irregular=True, seed=2, offset=17.0 if prev else 0.0)
@@ -54,8 +54,17 @@ def _compare(dev, B, S, prev=False, hT_weight=0.0, tol=GRAD_RTOL, **over):
     assert rel_err(p_gpu, p_ref) <= 1e-4
     assert set(g_gpu) == set(g_ref), set(g_ref) ^ set(g_gpu)
     errs = {k: rel_err(g_gpu[k], g_ref[k]) for k in g_ref}
-    worst = max(errs, key=errs.get)
-    assert errs[worst] <= tol, (worst, errs)
+    tols = {k: tol for k in g_ref}
+    if conditioning:
+        # non-smooth vector fields under adaptive stepping: the ORACLE's own fp32 and fp64 gradients
+        # differ by percents (kinks + noise-regime step sizes); widen to 4 x that measured spread
+        import copy
+        ref64 = copy.deepcopy(ref).double()
+        _, g64, _ = _grads(ref64, fv.double(), fi.double(), ts.double(), gts.double(),
+                           None if pv is None else pv.double(), hT_weight)
+        tols = {k: max(tol, 4 * rel_err(g_ref[k].double(), g64[k])) for k in g_ref}
+    worst = max(errs, key=lambda k: errs[k] / tols[k])
+    assert errs[worst] <= tols[worst], (worst, errs[worst], tols[worst], errs)
     return ref, errs, (fv, fi, ts, gts, pv)
 
 
@@ -83,13 +92,21 @@ def test_backward_prev_and_hidden_grad(cuda_device):
 
 @pytest.mark.parametrize("over", [
     dict(ode_solver="tsit5"), dict(ode_solver="heun", ode_rtol=1e-1, ode_ckpt_loops=512),
-    dict(ode_activation_fn="softplus"), dict(ode_activation_fn="relu"), dict(ode_activation_fn="leaky_relu"),
+    dict(ode_activation_fn="softplus"),
+    dict(ode_activation_fn="relu", ode_solver="rk4"), dict(ode_activation_fn="leaky_relu", ode_solver="rk4"),
     dict(rnn_num_layers=3, ode_hidden_dim=256, ode_fn_num_layers=2),
     dict(rnn_num_layers=1, ode_hidden_dim=1024, ode_fn_num_layers=1),
     dict(ode_rows_per_tile=4),
 ])
 def test_backward_variants(cuda_device, over):
     _compare(cuda_device, 6, 3, **over)
+
+
+@pytest.mark.parametrize("act", ["relu", "leaky_relu"])
+def test_backward_nonsmooth_adaptive(cuda_device, act):
+    """ReLU-type fields with dopri5: gradients are only pinned to the oracle's own fp32/fp64 spread
+    (measured in the test: ~7 % for relu at these sizes); fixed-step rk4 above is exact."""
+    _compare(cuda_device, 6, 3, conditioning=True, ode_activation_fn=act)
 
 
 def test_backward_soft_fusion(cuda_device):

@@ -16,6 +16,9 @@ def case(name, B, S, **over):
     l_ref, g_ref, p_ref = _grads(ref, fv, fi, ts, gts, None, 0.0)
     l_gpu, g_gpu, p_gpu = _grads(mod, fv.to(dev), fi.to(dev), ts.to(dev), gts.to(dev), None, 0.0)
     print(f"[{name}] loss ref {l_ref:.6f} gpu {l_gpu:.6f} pose_err {rel_err(p_gpu, p_ref):.2e} status {int(mod.last_status.max())}")
+    st = mod.last_stats.cpu().long()
+    neq = (st[..., 0] != ref.last_stats["n_steps"]) | (st[..., 1] != ref.last_stats["n_accepted"])
+    print(f"   step-count mismatches {int(neq.sum())}/{neq.numel()}  mean steps {st[...,0].float().mean():.2f}")
     for k in g_ref:
         print(f"   {k:28s} rel_err {rel_err(g_gpu[k], g_ref[k]):.3e}  |ref| {g_ref[k].abs().max():.3e}")
 
@@ -42,5 +45,9 @@ cases = sys.argv[1:] or ["parity"]
 if "parity" in cases:
     case("rk4 B=8 S=2", 8, 2, ode_solver="rk4")
     case("dopri5 B=8 S=3", 8, 3, ode_solver="dopri5", ode_rtol=1e-3)
+if "relu" in cases:
+    case("relu rk4 B=6 S=3", 6, 3, ode_solver="rk4", ode_activation_fn="relu")
+    case("relu dopri5 B=6 S=3", 6, 3, ode_activation_fn="relu")
+    case("leaky dopri5 B=6 S=3", 6, 3, ode_activation_fn="leaky_relu")
 if "timing" in cases:
     timing(1024, ode_rtol=1e-3)
