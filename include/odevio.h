@@ -266,6 +266,24 @@ ODEVIO_API int32_t odevio_cde_forward(const odevio_cde_cfg* cfg, const odevio_cd
                                       float* pose, float* z0_out, float* hidden, int32_t* stats,
                                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------- ODEFunc.forward (tensor cores) ---- */
+
+/*
+ * Batched evaluation of the vector field, out = tanh(W_n a(... a(W_0 x + b_0) ...) + b_n), replacing
+ * ODEFunc.forward (reference src/models/ODEFunc.py:38-39) for callers that evaluate the field
+ * directly.  Runs on tcgen05 (kind::tf32 with the 3xTF32 hi/lo split: fp32-level accuracy, fp32
+ * accumulation in TMEM); a 128-row tile is split by output columns over a cluster of 8 CTAs.
+ *   weights[j] [out_j, in_j], biases[j] [out_j]  (HOST arrays of n_hidden + 1 DEVICE pointers,
+ *                                                 ode_func.net.{0,2,..})
+ *   x [M, D], out [M, D]
+ * Supported: D / 8 and H / 8 multiples of 32 in [32, 128] (D, H in {256, 512, 768, 1024}).
+ */
+ODEVIO_API size_t odevio_odefunc_workspace_bytes(int32_t M, int32_t D, int32_t H, int32_t n_hidden);
+ODEVIO_API int32_t odevio_odefunc_forward(int32_t M, int32_t D, int32_t H, int32_t n_hidden, int32_t activation,
+                                          const float* const* weights, const float* const* biases,
+                                          const float* x, float* out,
+                                          void* workspace, size_t workspace_bytes, void* stream);
+
 /*
  * Diagnostics (no reference counterpart): launch a dense FFMA loop on `blocks` CTAs of 512 threads
  * and report the FLOPs it performs in *flops_out (HOST); time it with events around the call to

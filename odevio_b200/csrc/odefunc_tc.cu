@@ -1,0 +1,384 @@
+// ODEFunc.forward on the 5th-generation tensor cores: batched evaluation of the vector field
+//   f(x) = tanh(W_n a(... a(W_0 x + b_0) ...) + b_n)            reference src/models/ODEFunc.py:38-39
+// for M rows, fp32-accurate through the 3xTF32 split (tcgen05.mma.kind::tf32, fp32 accumulators
+// in TMEM).  This is the tensor-core building block of the solver kernels: a 128-row tile is
+// owned by a CLUSTER of 8 CTAs, CTA c computing output columns [c N/8, (c+1) N/8) of every Linear,
+// so that 16 tiles (B = 1024 sequences x 2 rnn layers) already occupy 128 SMs.
+//
+// Per layer and CTA:
+//   * the layer input (128 x K, written by the previous layer's epilogues of all 8 CTAs) and the
+//     CTA's weight slice stream L2 -> shared memory in K-chunks of 32 through a bulk-TMA / mbarrier
+//     ring; both are stored in global memory directly in the tensor core's canonical K-major
+//     no-swizzle image (8 x 16 B core matrices) as a TF32-exact high part plus the exact residual;
+//   * one elected thread issues, per 8-wide k-step, D += A_hi W_hi + A_lo W_hi + A_hi W_lo;
+//   * four epilogue warps (thread = row) read the accumulators with tcgen05.ld, add the bias, apply
+//     the activation and write their 128 x N/8 slice of the next layer's operand (hi / lo) -- or
+//     the fp32 result of the last layer -- followed by a cluster barrier.
+// Activations therefore cross CTAs through L2 (8 KB .. 48 KB per CTA and layer), not DSMEM, whose
+// ~20 B/clk/SM would cost more than the MMAs (B300_MICROARCH.md, CGA/DSMEM table).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/odevio.h"
+#include "common.cuh"
+
+namespace odevio {
+
+namespace {
+
+constexpr int FT_ROWS = 128;          // rows per tile = MMA M
+constexpr int FT_NC = 8;              // CTAs per cluster = column slices
+constexpr int FT_KCH = 32;            // k per ring stage
+constexpr int FT_MAX_LAYERS = ODEVIO_MAX_ODE_LINEARS;
+constexpr int FT_MAX_STAGES = 4;
+constexpr int FT_THREADS = 192;       // warps 0-3 epilogue (thread = row), warp 4 TMA producer, warp 5 MMA issuer
+
+struct FtParams {
+  int M, NL, act;
+  int K[FT_MAX_LAYERS], N[FT_MAX_LAYERS];      // layer shapes (N % 256 == 0 or N/8 in {32, 64, 96, 128}, K % 32 == 0)
+  const float* Whi[FT_MAX_LAYERS];             // packed [c][K/32][Nc/8][8][8][4]
+  const float* Wlo[FT_MAX_LAYERS];
+  const float* bias[FT_MAX_LAYERS];
+  const float* x;                              // [M][K[0]]
+  float* out;                                  // [M][N[NL-1]]
+  float* xa;                                   // per cluster: 2 buffers x (hi, lo) x 128 x Kmax floats
+  size_t xa_buf_floats;                        // 128 * Kmax
+  int ntiles, nst;
+  uint32_t stage_bytes;                        // 2 * (128 + Ncmax) * 32 * 4
+};
+
+__device__ __forceinline__ uint64_t ft_desc(uint32_t saddr) {
+  // K-major, no swizzle: LBO (k core matrices) = 128 B, SBO (8-row groups) = 8 * 128 B; version 1
+  return static_cast<uint64_t>((saddr >> 4) & 0x3fffu) | (static_cast<uint64_t>(128u >> 4) << 16) |
+         (static_cast<uint64_t>(1024u >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void ft_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void ft_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// accumulators for the hi*hi products (K segments); one more holds the cross terms: (nseg + 1) * Nc <= 512
+__device__ __forceinline__ int ft_nseg(int Nc) { const int n = 512 / Nc - 1; return n > 4 ? 4 : n; }
+__device__ __forceinline__ float ft_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// float offset of (row r, feature k) in a 128-row operand buffer: [k/32][r/8][(k%32)/4][r%8][k%4]
+__device__ __forceinline__ size_t xa_offset(int r, int k) {
+  return ((static_cast<size_t>(k >> 5) * 16 + (r >> 3)) * 8 + ((k & 31) >> 2)) * 32 + (r & 7) * 4 + (k & 3);
+}
+
+// thread = row: 32 consecutive features (one k-chunk) -> hi / lo operand images
+__device__ __forceinline__ void store_chunk(float* hi, float* lo, int r, int k0, const float (&v)[32]) {
+  const size_t base = xa_offset(r, k0);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 h = make_float4(ft_hi(v[4 * q]), ft_hi(v[4 * q + 1]), ft_hi(v[4 * q + 2]), ft_hi(v[4 * q + 3]));
+    *reinterpret_cast<float4*>(hi + base + q * 32) = h;
+    *reinterpret_cast<float4*>(lo + base + q * 32) =
+        make_float4(v[4 * q] - h.x, v[4 * q + 1] - h.y, v[4 * q + 2] - h.z, v[4 * q + 3] - h.w);
+  }
+}
+
+__global__ void __cluster_dims__(FT_NC, 1, 1) __launch_bounds__(FT_THREADS, 1)
+odefunc_tc_kernel(const __grid_constant__ FtParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full_bar[FT_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[FT_MAX_STAGES];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int cluster_id = blockIdx.x / FT_NC, nclusters = gridDim.x / FT_NC;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.nst; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_slot;
+
+  float* xa_cluster = p.xa + static_cast<size_t>(cluster_id) * 4 * p.xa_buf_floats;
+  uint32_t ring_stage = 0, ring_phase = 0;       // producer / MMA thread keep identical copies
+  uint32_t accum_phase = 0;
+
+  for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
+    const int row0 = tile * FT_ROWS;
+    // ---- layer-0 operand: this CTA converts its K/8 feature slice of the tile's rows
+    if (warp < 4) {
+      const int r = tid, K0 = p.K[0], ks = K0 / FT_NC;
+      float* hi = xa_cluster; float* lo = xa_cluster + p.xa_buf_floats;
+      for (int kc = 0; kc < ks; kc += 32) {
+        const int k0 = static_cast<int>(crank) * ks + kc;
+        float v[32];
+        if (row0 + r < p.M) {
+          const float4* src = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(row0 + r) * K0 + k0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { const float4 t = src[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = 0.f;
+        }
+        store_chunk(hi, lo, r, k0, v);
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy stores -> visible to the bulk-copy (async) proxy
+    }
+    __syncwarp();
+    cluster_sync_all();
+
+    for (int l = 0; l < p.NL; ++l) {
+      const int K = p.K[l], N = p.N[l], Nc = N / FT_NC, nch = K / FT_KCH;
+      const float* a_hi = xa_cluster + static_cast<size_t>(l & 1) * 2 * p.xa_buf_floats;
+      const float* a_lo = a_hi + p.xa_buf_floats;
+      float* nx_hi = xa_cluster + static_cast<size_t>((l + 1) & 1) * 2 * p.xa_buf_floats;
+      float* nx_lo = nx_hi + p.xa_buf_floats;
+      const uint32_t a_bytes = FT_ROWS * FT_KCH * 4, w_bytes = static_cast<uint32_t>(Nc) * FT_KCH * 4;
+
+      if (warp == 4 && lane == 0) {
+        // ===== TMA producer
+        const float* whi = p.Whi[l] + static_cast<size_t>(crank) * Nc * K;
+        const float* wlo = p.Wlo[l] + static_cast<size_t>(crank) * Nc * K;
+        for (int ch = 0; ch < nch; ++ch) {
+          mbar_wait(&empty_bar[ring_stage], ring_phase ^ 1u);
+          unsigned char* dst = smem + static_cast<size_t>(ring_stage) * p.stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[ring_stage], 2 * (a_bytes + w_bytes));
+          tma_load_1d(dst, a_hi + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &full_bar[ring_stage]);
+          tma_load_1d(dst + a_bytes, a_lo + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &full_bar[ring_stage]);
+          tma_load_1d(dst + 2 * a_bytes, whi + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &full_bar[ring_stage]);
+          tma_load_1d(dst + 2 * a_bytes + w_bytes, wlo + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &full_bar[ring_stage]);
+          if (++ring_stage == static_cast<uint32_t>(p.nst)) { ring_stage = 0; ring_phase ^= 1u; }
+        }
+      } else if (warp == 5 && lane == 0) {
+        // ===== MMA issuer: D[128 x Nc] = sum_k A[128 x k] W[Nc x k]^T, 3xTF32
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(Nc >> 3) << 17) |
+                               (static_cast<uint32_t>(FT_ROWS >> 4) << 24);
+        // The tensor core accumulates with truncation, so a long chain into ONE accumulator drifts by
+        // ~n * 2^-24 (measured: 2.6e-5 after 288 accumulations).  The K range is therefore split over
+        // `nseg` accumulators for the hi*hi products plus one for the (2^-11 smaller) cross terms; the
+        // epilogue adds them in fp32 with round-to-nearest.
+        const int nseg = ft_nseg(Nc);
+        uint32_t corr_started = 0;
+        for (int ch = 0; ch < nch; ++ch) {
+          mbar_wait(&full_bar[ring_stage], ring_phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t base = smem_u32(smem + static_cast<size_t>(ring_stage) * p.stage_bytes);
+          const uint32_t sa_hi = base, sa_lo = base + a_bytes, sw_hi = base + 2 * a_bytes, sw_lo = sw_hi + w_bytes;
+          const int seg = ch * nseg / nch;
+          const bool seg_first = ch == (seg * nch + nseg - 1) / nseg;
+          const uint32_t d_main = tmem_d + static_cast<uint32_t>(seg * Nc), d_corr = tmem_d + static_cast<uint32_t>(nseg * Nc);
+#pragma unroll
+          for (int ks = 0; ks < FT_KCH / 8; ++ks) {
+            const uint32_t o = ks * 256;
+            ft_mma(d_main, ft_desc(sa_hi + o), ft_desc(sw_hi + o), idesc, (seg_first && ks == 0) ? 0u : 1u);
+            ft_mma(d_corr, ft_desc(sa_lo + o), ft_desc(sw_hi + o), idesc, corr_started);
+            corr_started = 1;
+            ft_mma(d_corr, ft_desc(sa_hi + o), ft_desc(sw_lo + o), idesc, 1);
+          }
+          ft_commit(&empty_bar[ring_stage]);
+          if (++ring_stage == static_cast<uint32_t>(p.nst)) { ring_stage = 0; ring_phase ^= 1u; }
+        }
+        ft_commit(&accum_bar);
+      } else if (warp < 4) {
+        // ===== epilogue warps: thread = row
+        mbar_wait(&accum_bar, accum_phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int r = tid;
+        const bool last = l == p.NL - 1;
+        const int act = last ? ACT_TANH : p.act;
+        const int nseg = ft_nseg(Nc);
+        for (int c0 = 0; c0 < Nc; c0 += 32) {
+          float accv[32];
+#pragma unroll
+          for (int q = 0; q < 32; ++q) accv[q] = 0.f;
+          uint32_t u[32];
+          for (int sgm = nseg; sgm >= 0; --sgm) {        // cross terms first (smallest), then the K segments
+          const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(sgm * Nc + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+                "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+                "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < 32; ++q) accv[q] += __uint_as_float(u[q]);
+          }
+          const int n0 = static_cast<int>(crank) * Nc + c0;
+          float v[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4*>(p.bias[l] + n0 + 4 * q);
+            const float4 a4 = apply_act4(make_float4(accv[4 * q] + b4.x, accv[4 * q + 1] + b4.y,
+                                                     accv[4 * q + 2] + b4.z, accv[4 * q + 3] + b4.w), act);
+            v[4 * q] = a4.x; v[4 * q + 1] = a4.y; v[4 * q + 2] = a4.z; v[4 * q + 3] = a4.w;
+          }
+          if (last) {
+            if (row0 + r < p.M) {
+              float4* dst = reinterpret_cast<float4*>(p.out + static_cast<size_t>(row0 + r) * N + n0);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          } else {
+            store_chunk(nx_hi, nx_lo, r, n0, v);
+          }
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      }
+      accum_phase ^= 1u;
+      __syncwarp();
+      // every CTA's slice of the next operand is written (and this CTA's accumulator drained)
+      cluster_sync_all();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
+  }
+}
+
+// W [N][K] (PyTorch) -> [c][K/32][Nc/8][8 kq][8 n][4 k] hi / lo
+__global__ void ft_pack_weight_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ hi, float* __restrict__ lo) {
+  const int Nc = N / FT_NC;
+  const size_t total = static_cast<size_t>(N) * K;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<size_t>(n) * K);
+    const int c = n / Nc, nl = n - c * Nc;
+    const size_t o = static_cast<size_t>(c) * Nc * K +
+                     ((static_cast<size_t>(k >> 5) * (Nc >> 3) + (nl >> 3)) * 8 + ((k & 31) >> 2)) * 32 + (nl & 7) * 4 + (k & 3);
+    const float w = W[i];
+    const float h = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+    hi[o] = h; lo[o] = w - h;
+  }
+}
+
+struct FtPlan {
+  int NL, ntiles, nclusters, nst, kmax, ncmax;
+  size_t off_whi[FT_MAX_LAYERS], off_wlo[FT_MAX_LAYERS], off_xa, xa_buf_floats, total_bytes, smem_bytes;
+  uint32_t stage_bytes;
+  int K[FT_MAX_LAYERS], N[FT_MAX_LAYERS];
+};
+
+int ft_plan(int M, int D, int H, int n_hidden, FtPlan& pl) {
+  if (M <= 0 || n_hidden < 1 || n_hidden + 1 > FT_MAX_LAYERS) return ODEVIO_E_SHAPE;
+  // column slices of 32 .. 128 (TMEM 128 columns, tcgen05.ld in 32-column chunks), k-chunks of 32
+  auto ok = [](int n) { const int nc = n / FT_NC; return n % FT_NC == 0 && nc % 32 == 0 && nc >= 32 && nc <= 128; };
+  if (!ok(D) || !ok(H)) return ODEVIO_E_SHAPE;
+  pl.NL = n_hidden + 1;
+  pl.kmax = D > H ? D : H;
+  pl.ncmax = pl.kmax / FT_NC;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = (off + n + 63) / 64 * 64; return o; };
+  for (int l = 0; l < pl.NL; ++l) {
+    pl.K[l] = l == 0 ? D : H;
+    pl.N[l] = l == pl.NL - 1 ? D : H;
+    pl.off_whi[l] = take(static_cast<size_t>(pl.K[l]) * pl.N[l]);
+    pl.off_wlo[l] = take(static_cast<size_t>(pl.K[l]) * pl.N[l]);
+  }
+  int dev = 0, nsm = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) {
+    cudaGetLastError();
+    nsm = 148;
+  }
+  pl.ntiles = (M + FT_ROWS - 1) / FT_ROWS;
+  pl.nclusters = nsm / FT_NC;
+  if (pl.nclusters > pl.ntiles) pl.nclusters = pl.ntiles;
+  pl.xa_buf_floats = static_cast<size_t>(FT_ROWS) * pl.kmax;
+  pl.off_xa = take(static_cast<size_t>(pl.nclusters) * 4 * pl.xa_buf_floats);
+  pl.total_bytes = off * sizeof(float);
+  pl.stage_bytes = 2u * (FT_ROWS + pl.ncmax) * FT_KCH * 4u;
+  pl.nst = static_cast<int>((220u * 1024u) / pl.stage_bytes);
+  if (pl.nst > FT_MAX_STAGES) pl.nst = FT_MAX_STAGES;
+  if (pl.nst < 2) return ODEVIO_E_SHAPE;
+  pl.smem_bytes = static_cast<size_t>(pl.nst) * pl.stage_bytes + 1024;
+  return 0;
+}
+
+}  // namespace
+}  // namespace odevio
+
+using namespace odevio;
+
+extern "C" {
+
+size_t odevio_odefunc_workspace_bytes(int32_t M, int32_t D, int32_t H, int32_t n_hidden) {
+  FtPlan pl;
+  if (ft_plan(M, D, H, n_hidden, pl) != 0) return 0;
+  return pl.total_bytes;
+}
+
+int32_t odevio_odefunc_forward(int32_t M, int32_t D, int32_t H, int32_t n_hidden, int32_t activation,
+                               const float* const* weights, const float* const* biases,
+                               const float* x, float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!weights || !biases || !x || !out || !workspace) return ODEVIO_E_NULL;
+  if (activation < 0 || activation > ODEVIO_ACT_SOFTPLUS) return ODEVIO_E_ENUM;
+  FtPlan pl;
+  const int rc = ft_plan(M, D, H, n_hidden, pl);
+  if (rc != 0) return rc;
+  if (workspace_bytes < pl.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ODEVIO_E_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* ws = static_cast<float*>(workspace);
+  FtParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.NL = pl.NL; p.act = activation;
+  for (int l = 0; l < pl.NL; ++l) {
+    if (!weights[l] || !biases[l]) return ODEVIO_E_NULL;
+    p.K[l] = pl.K[l]; p.N[l] = pl.N[l];
+    ft_pack_weight_kernel<<<296, 256, 0, stream>>>(weights[l], pl.N[l], pl.K[l], ws + pl.off_whi[l], ws + pl.off_wlo[l]);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int32_t>(e);
+    p.Whi[l] = ws + pl.off_whi[l]; p.Wlo[l] = ws + pl.off_wlo[l]; p.bias[l] = biases[l];
+  }
+  p.x = x; p.out = out; p.xa = ws + pl.off_xa; p.xa_buf_floats = pl.xa_buf_floats;
+  p.ntiles = pl.ntiles; p.nst = pl.nst; p.stage_bytes = pl.stage_bytes;
+  cudaError_t e = cudaFuncSetAttribute(odefunc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(pl.smem_bytes));
+  if (e != cudaSuccess) return static_cast<int32_t>(e);
+  {
+    // clusters of 8 must sit inside one GPC: launch no more clusters than can be co-resident
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(pl.nclusters * FT_NC); lc.blockDim = dim3(FT_THREADS); lc.dynamicSmemBytes = pl.smem_bytes;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = FT_NC; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    lc.attrs = &at; lc.numAttrs = 1;
+    int maxc = 0;
+    if (cudaOccupancyMaxActiveClusters(&maxc, odefunc_tc_kernel, &lc) == cudaSuccess && maxc > 0) {
+      if (pl.nclusters > maxc) pl.nclusters = maxc;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  odefunc_tc_kernel<<<pl.nclusters * FT_NC, FT_THREADS, pl.smem_bytes, stream>>>(p);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int32_t>(e);
+}
+
+}  // extern "C"

@@ -72,7 +72,8 @@ wgrad_tc_kernel(const float* __restrict__ Ghi, const float* __restrict__ Glo,
   const uint32_t g_tile_bytes = static_cast<uint32_t>(TC_BM) * R * 4;      // 128 features x R rows
   const uint32_t a_tile_bytes = static_cast<uint32_t>(BN) * R * 4;
   const uint32_t stage_bytes = 2 * (g_tile_bytes + a_tile_bytes);
-  const uint32_t tmem_cols = BN <= 32 ? 32u : BN <= 64 ? 64u : BN <= 128 ? 128u : 256u;
+  // two accumulators of BN columns: hi*hi products | cross terms (see the note at the MMA issue loop)
+  const uint32_t tmem_cols = 2 * BN <= 64 ? 64u : 2 * BN <= 128 ? 128u : 2 * BN <= 256 ? 256u : 512u;
 
   if (tid == 0) {
     for (int s = 0; s < nst; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -112,6 +113,11 @@ wgrad_tc_kernel(const float* __restrict__ Ghi, const float* __restrict__ Glo,
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                            (static_cast<uint32_t>(TC_BM >> 4) << 24);
     const uint32_t lbo = 128, sbo = static_cast<uint32_t>(R >> 2) * 128;
+    // The tensor core accumulates with truncation (measured in odefunc_tc.cu: ~n * 2^-24 drift after n
+    // accumulations into one accumulator), so (a) the hi*hi products and the 2^-11 smaller cross terms
+    // go to separate accumulators, added in fp32 in the epilogue, and (b) a CTA only reduces
+    // kBlocksPerSplit blocks -- longer reductions are split-M partials summed by the reduce kernel.
+    const uint32_t d_main = tmem_d, d_corr = tmem_d + static_cast<uint32_t>(BN);
     uint32_t stage = 0, phase = 0, acc = 0;
     for (int b = 0; b < nb; ++b) {
       mbar_wait(&full_bar[stage], phase);
@@ -123,10 +129,10 @@ wgrad_tc_kernel(const float* __restrict__ Ghi, const float* __restrict__ Glo,
         const uint32_t o = static_cast<uint32_t>(ks) * 256;
         const uint64_t dgh = smem_desc_kmajor(g_hi + o, lbo, sbo), dgl = smem_desc_kmajor(g_lo + o, lbo, sbo);
         const uint64_t dah = smem_desc_kmajor(a_hi + o, lbo, sbo), dal = smem_desc_kmajor(a_lo + o, lbo, sbo);
-        umma_tf32(tmem_d, dgh, dah, idesc, acc);
+        umma_tf32(d_main, dgh, dah, idesc, acc);
+        umma_tf32(d_corr, dgl, dah, idesc, acc);
         acc = 1;
-        umma_tf32(tmem_d, dgl, dah, idesc, 1);
-        umma_tf32(tmem_d, dgh, dal, idesc, 1);
+        umma_tf32(d_corr, dgh, dal, idesc, 1);
       }
       umma_commit(&empty_bar[stage]);                  // frees the slot when these MMAs have read it
       if (++stage == static_cast<uint32_t>(nst)) { stage = 0; phase ^= 1u; }
@@ -143,7 +149,11 @@ wgrad_tc_kernel(const float* __restrict__ Ghi, const float* __restrict__ Glo,
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
-      const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(c0);
+      float sum[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) sum[q] = 0.f;
+      for (int part_i = 1; part_i >= 0; --part_i) {          // cross terms first, then the main accumulator
+      const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(part_i * BN + c0);
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -155,13 +165,14 @@ wgrad_tc_kernel(const float* __restrict__ Ghi, const float* __restrict__ Glo,
           : "r"(taddr)
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int q = 0; q < 32; ++q) sum[q] += __uint_as_float(v[q]);
+      }
       if (n < N) {
         float* row = out + static_cast<size_t>(n) * K + k0 + c0;
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(row + 4 * q) =
-              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                          __uint_as_float(v[4 * q + 3]));
+          *reinterpret_cast<float4*>(row + 4 * q) = make_float4(sum[4 * q], sum[4 * q + 1], sum[4 * q + 2], sum[4 * q + 3]);
       }
     }
   } else if (n < N) {
@@ -213,14 +224,15 @@ int wgrad_tc_bn(int K) {
   return 0;
 }
 
+// Blocks one CTA reduces: bounds the accumulation chain (2 * R/8 MMAs per block into the main
+// accumulator) so that the tensor core's truncating accumulate stays below ~5e-6 relative.
+constexpr long long kBlocksPerSplit = 48;
+
 int wgrad_tc_splits(long long nblocks, int N, int K, int nsm) {
-  const int bn = wgrad_tc_bn(K);
-  if (!bn) return 0;
-  const long long tiles = static_cast<long long>(N / TC_BM) * (K / bn);
-  long long s = (2LL * nsm + tiles - 1) / tiles;
-  if (s > nblocks) s = nblocks;
+  (void)N; (void)nsm;
+  if (!wgrad_tc_bn(K)) return 0;
+  long long s = (nblocks + kBlocksPerSplit - 1) / kBlocksPerSplit;
   if (s < 1) s = 1;
-  if (s > 256) s = 256;
   return static_cast<int>(s);
 }
 
@@ -237,7 +249,7 @@ cudaError_t wgrad_linear_tc(const float* Ghi, const float* Glo, const float* Ahi
     return cudaMemsetAsync(db, 0, sizeof(float) * N, stream);
   }
   const int splits = wgrad_tc_splits(nblocks, N, K, nsm);
-  const long long bps = (nblocks + splits - 1) / splits;
+  const long long bps = kBlocksPerSplit;
   const size_t stage_bytes = static_cast<size_t>(2) * (TC_BM + bn) * R * 4;
   int nst = static_cast<int>((200 * 1024) / stage_bytes);
   if (nst > TC_MAX_STAGES) nst = TC_MAX_STAGES;

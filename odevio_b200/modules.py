@@ -72,9 +72,35 @@ class ODEFunc(nn.Module):
         return [m for m in self.net if isinstance(m, nn.Linear)]
 
     def forward(self, t, x):
-        # Single evaluations are not on the fused path (the solver kernels read the weights
-        # directly); kept for interface compatibility with callers that probe the field.
-        return self.net(x)
+        """f(t, x) for callers that evaluate the field directly (ODEFunc.py:38-39; `t` is ignored).
+        Runs the tcgen05 3xTF32 kernel behind ``odevio_odefunc_forward``; the fused solver kernels
+        read the weights themselves and never come through here.  No CPU / autograd path."""
+        lib = _lib.load()
+        if not x.is_cuda:
+            raise _lib.OdevioError("ODEFunc.forward needs a CUDA tensor: odevio_b200 has no CPU path")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise _lib.OdevioError("ODEFunc.forward is inference-only; gradients flow through PoseODERNN's fused backward")
+        shape = x.shape
+        x2 = _f32c(x.reshape(-1, self.feature_dim), "x")
+        M = x2.shape[0]
+        nbytes = lib.odevio_odefunc_workspace_bytes(M, self.feature_dim, self.hidden_dim, self.num_hidden_layers)
+        if nbytes == 0:
+            raise _lib.OdevioError(f"ODEFunc.forward: unsupported shape for the tensor-core kernel "
+                                   f"(D={self.feature_dim}, H={self.hidden_dim}; need multiples of 256 up to 1024)")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        out = torch.empty_like(x2)
+        lins = self.linears()
+        keep = [(_f32c(l.weight.detach(), "weight"), _f32c(l.bias.detach(), "bias")) for l in lins]
+        wp = (C.c_void_p * len(lins))(*[t[0].data_ptr() for t in keep])
+        bp = (C.c_void_p * len(lins))(*[t[1].data_ptr() for t in keep])
+        with torch.cuda.device(x.device):
+            rc = lib.odevio_odefunc_forward(M, self.feature_dim, self.hidden_dim, self.num_hidden_layers,
+                                            _lib.ACT[self.activation], wp, bp, _lib.dptr(x2), _lib.dptr(out),
+                                            _lib.dptr(ws), nbytes,
+                                            C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+        _lib.check(rc)
+        del keep
+        return out.reshape(shape)
 
 
 class CDEFunc(nn.Module):

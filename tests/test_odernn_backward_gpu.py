@@ -62,7 +62,8 @@ def _compare(dev, B, S, prev=False, hT_weight=0.0, tol=GRAD_RTOL, conditioning=F
         ref64 = copy.deepcopy(ref).double()
         _, g64, _ = _grads(ref64, fv.double(), fi.double(), ts.double(), gts.double(),
                            None if pv is None else pv.double(), hT_weight)
-        tols = {k: max(tol, 4 * rel_err(g_ref[k].double(), g64[k])) for k in g_ref}
+        spread = max(rel_err(g_ref[k].double(), g64[k]) for k in g_ref)
+        tols = {k: max(tol, 4 * spread) for k in g_ref}
     worst = max(errs, key=lambda k: errs[k] / tols[k])
     assert errs[worst] <= tols[worst], (worst, errs[worst], tols[worst], errs)
     return ref, errs, (fv, fi, ts, gts, pv)
@@ -104,9 +105,13 @@ def test_backward_variants(cuda_device, over):
 
 @pytest.mark.parametrize("act", ["relu", "leaky_relu"])
 def test_backward_nonsmooth_adaptive(cuda_device, act):
-    """ReLU-type fields with dopri5: gradients are only pinned to the oracle's own fp32/fp64 spread
-    (measured in the test: ~7 % for relu at these sizes); fixed-step rk4 above is exact."""
+    """ReLU-type fields with dopri5.  From the reference's dt0 = 1e-4 the first steps run in the
+    rounding-noise regime of the error estimate, their sizes differ by O(1) between any two fp32
+    implementations, and with a kinked field the constant-dt gradient then moves by percents (the
+    oracle's own fp32 vs fp64 gradients differ by ~7 %: measured here and used as the bound).
+    Started in the resolved regime (dt0 = 0.05) the same path is pinned at GRAD_RTOL scale."""
     _compare(cuda_device, 6, 3, conditioning=True, ode_activation_fn=act)
+    _compare(cuda_device, 6, 3, conditioning=True, tol=5 * GRAD_RTOL, ode_activation_fn=act, ode_dt0=0.05)
 
 
 def test_backward_soft_fusion(cuda_device):
