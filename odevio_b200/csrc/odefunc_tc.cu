@@ -25,7 +25,16 @@
 
 namespace odevio {
 
+// development timeline (clock64 of cluster 0 / CTA 0, first tile): [layer][event]
+__device__ long long g_ft_dbg[64];
+
 namespace {
+
+#ifdef ODEVIO_FT_TIMELINE
+#define FT_STAMP(idx) do { if (blockIdx.x == 0 && tile == 0) g_ft_dbg[idx] = clock64(); } while (0)
+#else
+#define FT_STAMP(idx) do { } while (0)
+#endif
 
 constexpr int FT_ROWS = 128;          // rows per tile = MMA M
 constexpr int FT_NC = 8;              // CTAs per cluster = column slices
@@ -65,6 +74,21 @@ __device__ __forceinline__ void ft_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// commit -> arrive on the same-offset mbarrier of every CTA in the cluster (ring slot freed cluster-wide)
+__device__ __forceinline__ void ft_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+// 1-D bulk copy global -> the same shared-memory offset of every CTA in `mask`, completing tx bytes on
+// the same-offset mbarrier of each destination CTA
+__device__ __forceinline__ void tma_load_1d_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                                      uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -103,7 +127,8 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
   const int cluster_id = blockIdx.x / FT_NC, nclusters = gridDim.x / FT_NC;
 
   if (tid == 0) {
-    for (int s = 0; s < p.nst; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    // a ring slot is refilled by multicasts from all 8 CTAs, so it is free only when all 8 MMA issuers released it
+    for (int s = 0; s < p.nst; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], FT_NC); }
     mbar_init(&accum_bar, 1);
     fence_barrier_init();
   }
@@ -143,7 +168,9 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
       asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy stores -> visible to the bulk-copy (async) proxy
     }
     __syncwarp();
+    if (tid == 0) FT_STAMP(0);
     cluster_sync_all();
+    if (tid == 0) FT_STAMP(1);
 
     for (int l = 0; l < p.NL; ++l) {
       const int K = p.K[l], N = p.N[l], Nc = N / FT_NC, nch = K / FT_KCH;
@@ -161,8 +188,12 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
           mbar_wait(&empty_bar[ring_stage], ring_phase ^ 1u);
           unsigned char* dst = smem + static_cast<size_t>(ring_stage) * p.stage_bytes;
           mbar_arrive_expect_tx(&full_bar[ring_stage], 2 * (a_bytes + w_bytes));
-          tma_load_1d(dst, a_hi + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &full_bar[ring_stage]);
-          tma_load_1d(dst + a_bytes, a_lo + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &full_bar[ring_stage]);
+          // the A chunk is common to the cluster: every CTA fetches 1/8 of it (two 8-row groups) and
+          // multicasts it to all 8 -> L2 is read once per cluster instead of 8 times
+          const uint32_t a_sl = a_bytes / FT_NC;
+          const size_t a_src = static_cast<size_t>(ch) * FT_ROWS * FT_KCH + static_cast<size_t>(crank) * (a_sl / 4);
+          tma_load_1d_multicast(dst + crank * a_sl, a_hi + a_src, a_sl, &full_bar[ring_stage], 0xff);
+          tma_load_1d_multicast(dst + a_bytes + crank * a_sl, a_lo + a_src, a_sl, &full_bar[ring_stage], 0xff);
           tma_load_1d(dst + 2 * a_bytes, whi + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &full_bar[ring_stage]);
           tma_load_1d(dst + 2 * a_bytes + w_bytes, wlo + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &full_bar[ring_stage]);
           if (++ring_stage == static_cast<uint32_t>(p.nst)) { ring_stage = 0; ring_phase ^= 1u; }
@@ -179,6 +210,7 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
         uint32_t corr_started = 0;
         for (int ch = 0; ch < nch; ++ch) {
           mbar_wait(&full_bar[ring_stage], ring_phase);
+          if (ch == 0) FT_STAMP(8 + l * 8 + 0);          // first chunk landed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t base = smem_u32(smem + static_cast<size_t>(ring_stage) * p.stage_bytes);
           const uint32_t sa_hi = base, sa_lo = base + a_bytes, sw_hi = base + 2 * a_bytes, sw_lo = sw_hi + w_bytes;
@@ -193,13 +225,15 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
             corr_started = 1;
             ft_mma(d_corr, ft_desc(sa_hi + o), ft_desc(sw_lo + o), idesc, 1);
           }
-          ft_commit(&empty_bar[ring_stage]);
+          ft_commit_multicast(&empty_bar[ring_stage], 0xff);
           if (++ring_stage == static_cast<uint32_t>(p.nst)) { ring_stage = 0; ring_phase ^= 1u; }
         }
         ft_commit(&accum_bar);
+        FT_STAMP(8 + l * 8 + 1);                         // all MMAs issued
       } else if (warp < 4) {
         // ===== epilogue warps: thread = row
         mbar_wait(&accum_bar, accum_phase);
+        if (tid == 0) FT_STAMP(8 + l * 8 + 2);           // accumulators complete
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int r = tid;
         const bool last = l == p.NL - 1;
@@ -247,17 +281,20 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
         }
         asm volatile("fence.proxy.async;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (tid == 0) FT_STAMP(8 + l * 8 + 3);           // epilogue done
       }
       accum_phase ^= 1u;
       __syncwarp();
       // every CTA's slice of the next operand is written (and this CTA's accumulator drained)
       cluster_sync_all();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (tid == 0) FT_STAMP(8 + l * 8 + 4);             // cluster barrier passed
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();          // no CTA may leave while peers can still multicast into it / arrive on its barriers
   if (warp == 5) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
   }
@@ -327,6 +364,11 @@ int ft_plan(int M, int D, int H, int n_hidden, FtPlan& pl) {
 using namespace odevio;
 
 extern "C" {
+
+// development only: copy the kernel's timeline stamps (64 x int64) to the host
+ODEVIO_API int32_t odevio_debug_odefunc_timeline(long long* host_dst) {
+  return static_cast<int32_t>(cudaMemcpyFromSymbol(host_dst, g_ft_dbg, sizeof(long long) * 64));
+}
 
 size_t odevio_odefunc_workspace_bytes(int32_t M, int32_t D, int32_t H, int32_t n_hidden) {
   FtPlan pl;
