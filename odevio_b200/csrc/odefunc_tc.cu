@@ -41,17 +41,20 @@ constexpr int FT_NC = 8;              // CTAs per cluster = column slices
 constexpr int FT_KCH = 32;            // k per ring stage
 constexpr int FT_MAX_LAYERS = ODEVIO_MAX_ODE_LINEARS;
 constexpr int FT_MAX_STAGES = 4;
-constexpr int FT_THREADS = 192;       // warps 0-3 epilogue (thread = row), warp 4 TMA producer, warp 5 MMA issuer
+// warps 0-7 epilogue (thread = row, two column halves), warps 8-11 hi/lo splitter, warp 12 TMA producer,
+// warp 13 MMA issuer
+constexpr int FT_EPI_WARPS = 8, FT_SPLIT_WARPS = 4;
+constexpr int FT_WARP_SPLIT = FT_EPI_WARPS, FT_WARP_TMA = FT_EPI_WARPS + FT_SPLIT_WARPS, FT_WARP_MMA = FT_WARP_TMA + 1;
+constexpr int FT_THREADS = 32 * (FT_WARP_MMA + 1);
 
 struct FtParams {
   int M, NL, act;
   int K[FT_MAX_LAYERS], N[FT_MAX_LAYERS];      // layer shapes (N % 256 == 0 or N/8 in {32, 64, 96, 128}, K % 32 == 0)
-  const float* Whi[FT_MAX_LAYERS];             // packed [c][K/32][Nc/8][8][8][4]
-  const float* Wlo[FT_MAX_LAYERS];
+  const float* Wp[FT_MAX_LAYERS];              // fp32, packed [c][K/32][Nc/8][8][8][4]
   const float* bias[FT_MAX_LAYERS];
   const float* x;                              // [M][K[0]]
   float* out;                                  // [M][N[NL-1]]
-  float* xa;                                   // per cluster: 2 buffers x (hi, lo) x 128 x Kmax floats
+  float* xa;                                   // per cluster: 2 buffers x 128 x Kmax floats (fp32 operand image)
   size_t xa_buf_floats;                        // 128 * Kmax
   int ntiles, nst;
   uint32_t stage_bytes;                        // 2 * (128 + Ncmax) * 32 * 4
@@ -89,6 +92,17 @@ __device__ __forceinline__ void tma_load_1d_multicast(void* dst_smem, const void
       ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
       : "memory");
 }
+// one lane of a converged warp (operands stay warp-uniform -> uniform registers, no per-lane waterfall)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -101,16 +115,13 @@ __device__ __forceinline__ size_t xa_offset(int r, int k) {
   return ((static_cast<size_t>(k >> 5) * 16 + (r >> 3)) * 8 + ((k & 31) >> 2)) * 32 + (r & 7) * 4 + (k & 3);
 }
 
-// thread = row: 32 consecutive features (one k-chunk) -> hi / lo operand images
-__device__ __forceinline__ void store_chunk(float* hi, float* lo, int r, int k0, const float (&v)[32]) {
+// thread = row: 32 consecutive features (one k-chunk) -> fp32 operand image (the hi / lo parts are
+// produced in shared memory by the splitter warps: one copy crosses L2 and the SM boundary, not two)
+__device__ __forceinline__ void store_chunk(float* dst, int r, int k0, const float (&v)[32]) {
   const size_t base = xa_offset(r, k0);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 h = make_float4(ft_hi(v[4 * q]), ft_hi(v[4 * q + 1]), ft_hi(v[4 * q + 2]), ft_hi(v[4 * q + 3]));
-    *reinterpret_cast<float4*>(hi + base + q * 32) = h;
-    *reinterpret_cast<float4*>(lo + base + q * 32) =
-        make_float4(v[4 * q] - h.x, v[4 * q + 1] - h.y, v[4 * q + 2] - h.z, v[4 * q + 3] - h.w);
-  }
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(dst + base + q * 32) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
 __global__ void __cluster_dims__(FT_NC, 1, 1) __launch_bounds__(FT_THREADS, 1)
@@ -118,6 +129,7 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[FT_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[FT_MAX_STAGES];
+  __shared__ __align__(8) uint64_t ready_bar[FT_MAX_STAGES];     // splitter -> MMA issuer
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
 
@@ -128,11 +140,16 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
 
   if (tid == 0) {
     // a ring slot is refilled by multicasts from all 8 CTAs, so it is free only when all 8 MMA issuers released it
-    for (int s = 0; s < p.nst; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], FT_NC); }
+    for (int s = 0; s < p.nst; ++s) {
+#ifndef ODEVIO_FT_MULTICAST
+#define ODEVIO_FT_MULTICAST 1
+#endif
+      mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ODEVIO_FT_MULTICAST ? FT_NC : 1); mbar_init(&ready_bar[s], FT_SPLIT_WARPS);
+    }
     mbar_init(&accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == FT_WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -142,7 +159,7 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_slot;
 
-  float* xa_cluster = p.xa + static_cast<size_t>(cluster_id) * 4 * p.xa_buf_floats;
+  float* xa_cluster = p.xa + static_cast<size_t>(cluster_id) * 2 * p.xa_buf_floats;
   uint32_t ring_stage = 0, ring_phase = 0;       // producer / MMA thread keep identical copies
   uint32_t accum_phase = 0;
 
@@ -151,7 +168,7 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
     // ---- layer-0 operand: this CTA converts its K/8 feature slice of the tile's rows
     if (warp < 4) {
       const int r = tid, K0 = p.K[0], ks = K0 / FT_NC;
-      float* hi = xa_cluster; float* lo = xa_cluster + p.xa_buf_floats;
+      float* dst0 = xa_cluster;
       for (int kc = 0; kc < ks; kc += 32) {
         const int k0 = static_cast<int>(crank) * ks + kc;
         float v[32];
@@ -163,7 +180,7 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] = 0.f;
         }
-        store_chunk(hi, lo, r, k0, v);
+        store_chunk(dst0, r, k0, v);
       }
       asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy stores -> visible to the bulk-copy (async) proxy
     }
@@ -174,32 +191,60 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
 
     for (int l = 0; l < p.NL; ++l) {
       const int K = p.K[l], N = p.N[l], Nc = N / FT_NC, nch = K / FT_KCH;
-      const float* a_hi = xa_cluster + static_cast<size_t>(l & 1) * 2 * p.xa_buf_floats;
-      const float* a_lo = a_hi + p.xa_buf_floats;
-      float* nx_hi = xa_cluster + static_cast<size_t>((l + 1) & 1) * 2 * p.xa_buf_floats;
-      float* nx_lo = nx_hi + p.xa_buf_floats;
+      const float* a_src_buf = xa_cluster + static_cast<size_t>(l & 1) * p.xa_buf_floats;
+      float* nx = xa_cluster + static_cast<size_t>((l + 1) & 1) * p.xa_buf_floats;
       const uint32_t a_bytes = FT_ROWS * FT_KCH * 4, w_bytes = static_cast<uint32_t>(Nc) * FT_KCH * 4;
 
-      if (warp == 4 && lane == 0) {
-        // ===== TMA producer
-        const float* whi = p.Whi[l] + static_cast<size_t>(crank) * Nc * K;
-        const float* wlo = p.Wlo[l] + static_cast<size_t>(crank) * Nc * K;
+      if (warp == FT_WARP_TMA && lane == 0) {
+        // ===== TMA producer: ONE fp32 copy of the A chunk (multicast) and of the weight chunk per stage
+        const float* wsrc = p.Wp[l] + static_cast<size_t>(crank) * Nc * K;
         for (int ch = 0; ch < nch; ++ch) {
           mbar_wait(&empty_bar[ring_stage], ring_phase ^ 1u);
           unsigned char* dst = smem + static_cast<size_t>(ring_stage) * p.stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[ring_stage], 2 * (a_bytes + w_bytes));
+          mbar_arrive_expect_tx(&full_bar[ring_stage], a_bytes + w_bytes);
           // the A chunk is common to the cluster: every CTA fetches 1/8 of it (two 8-row groups) and
           // multicasts it to all 8 -> L2 is read once per cluster instead of 8 times
           const uint32_t a_sl = a_bytes / FT_NC;
           const size_t a_src = static_cast<size_t>(ch) * FT_ROWS * FT_KCH + static_cast<size_t>(crank) * (a_sl / 4);
-          tma_load_1d_multicast(dst + crank * a_sl, a_hi + a_src, a_sl, &full_bar[ring_stage], 0xff);
-          tma_load_1d_multicast(dst + a_bytes + crank * a_sl, a_lo + a_src, a_sl, &full_bar[ring_stage], 0xff);
-          tma_load_1d(dst + 2 * a_bytes, whi + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &full_bar[ring_stage]);
-          tma_load_1d(dst + 2 * a_bytes + w_bytes, wlo + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &full_bar[ring_stage]);
+#if ODEVIO_FT_MULTICAST
+          tma_load_1d_multicast(dst + crank * a_sl, a_src_buf + a_src, a_sl, &full_bar[ring_stage], 0xff);
+#else
+          (void)a_sl; (void)a_src;
+          tma_load_1d(dst, a_src_buf + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &full_bar[ring_stage]);
+#endif
+          tma_load_1d(dst + 2 * a_bytes, wsrc + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &full_bar[ring_stage]);
           if (++ring_stage == static_cast<uint32_t>(p.nst)) { ring_stage = 0; ring_phase ^= 1u; }
         }
-      } else if (warp == 5 && lane == 0) {
-        // ===== MMA issuer: D[128 x Nc] = sum_k A[128 x k] W[Nc x k]^T, 3xTF32
+      } else if (warp >= FT_WARP_SPLIT && warp < FT_WARP_TMA) {
+        // ===== splitter: x -> (TF32-exact high part in place, exact residual next to it)
+        const int st = tid - 32 * FT_WARP_SPLIT;                     // 0 .. 127
+        const int a_vec = FT_ROWS * FT_KCH / 4, w_vec = Nc * FT_KCH / 4;
+        for (int ch = 0; ch < nch; ++ch) {
+          mbar_wait(&full_bar[ring_stage], ring_phase);
+          unsigned char* base = smem + static_cast<size_t>(ring_stage) * p.stage_bytes;
+          float4* ahi = reinterpret_cast<float4*>(base); float4* alo = reinterpret_cast<float4*>(base + a_bytes);
+          float4* whi = reinterpret_cast<float4*>(base + 2 * a_bytes); float4* wlo = reinterpret_cast<float4*>(base + 2 * a_bytes + w_bytes);
+#pragma unroll 4
+          for (int e = st; e < a_vec; e += 32 * FT_SPLIT_WARPS) {
+            const float4 x = ahi[e];
+            const float4 h = make_float4(ft_hi(x.x), ft_hi(x.y), ft_hi(x.z), ft_hi(x.w));
+            ahi[e] = h; alo[e] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+          }
+#pragma unroll 2
+          for (int e = st; e < w_vec; e += 32 * FT_SPLIT_WARPS) {
+            const float4 x = whi[e];
+            const float4 h = make_float4(ft_hi(x.x), ft_hi(x.y), ft_hi(x.z), ft_hi(x.w));
+            whi[e] = h; wlo[e] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready_bar[ring_stage]);
+          if (++ring_stage == static_cast<uint32_t>(p.nst)) { ring_stage = 0; ring_phase ^= 1u; }
+        }
+      } else if (warp == FT_WARP_MMA) {
+        // ===== MMA issuer: D[128 x Nc] = sum_k A[128 x k] W[Nc x k]^T, 3xTF32.  The WHOLE warp runs the loop
+        // with warp-uniform operands and one elected lane issues: with a single active lane ptxas moves
+        // every descriptor through an ELECT / R2UR.BROADCAST waterfall (~120 clk per MMA, measured).
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(Nc >> 3) << 17) |
                                (static_cast<uint32_t>(FT_ROWS >> 4) << 24);
         // The tensor core accumulates with truncation, so a long chain into ONE accumulator drifts by
@@ -207,45 +252,63 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
         // `nseg` accumulators for the hi*hi products plus one for the (2^-11 smaller) cross terms; the
         // epilogue adds them in fp32 with round-to-nearest.
         const int nseg = ft_nseg(Nc);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
         uint32_t corr_started = 0;
         for (int ch = 0; ch < nch; ++ch) {
-          mbar_wait(&full_bar[ring_stage], ring_phase);
-          if (ch == 0) FT_STAMP(8 + l * 8 + 0);          // first chunk landed
+          mbar_wait(&ready_bar[ring_stage], ring_phase);
+          if (ch == 0 && lane == 0) FT_STAMP(8 + l * 8 + 0);          // first chunk landed and split
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t base = smem_u32(smem + static_cast<size_t>(ring_stage) * p.stage_bytes);
           const uint32_t sa_hi = base, sa_lo = base + a_bytes, sw_hi = base + 2 * a_bytes, sw_lo = sw_hi + w_bytes;
           const int seg = ch * nseg / nch;
           const bool seg_first = ch == (seg * nch + nseg - 1) / nseg;
-          const uint32_t d_main = tmem_d + static_cast<uint32_t>(seg * Nc), d_corr = tmem_d + static_cast<uint32_t>(nseg * Nc);
+          const uint32_t d_main = tmem_u + static_cast<uint32_t>(seg * Nc), d_corr = tmem_u + static_cast<uint32_t>(nseg * Nc);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < FT_KCH / 8; ++ks) {
-            const uint32_t o = ks * 256;
-            ft_mma(d_main, ft_desc(sa_hi + o), ft_desc(sw_hi + o), idesc, (seg_first && ks == 0) ? 0u : 1u);
-            ft_mma(d_corr, ft_desc(sa_lo + o), ft_desc(sw_hi + o), idesc, corr_started);
-            corr_started = 1;
-            ft_mma(d_corr, ft_desc(sa_hi + o), ft_desc(sw_lo + o), idesc, 1);
+            for (int ks = 0; ks < FT_KCH / 8; ++ks) {
+              const uint32_t o = ks * 256;
+#ifndef ODEVIO_FT_DBG_MMA
+#define ODEVIO_FT_DBG_MMA 3
+#endif
+#if ODEVIO_FT_DBG_MMA >= 1
+              ft_mma(d_main, ft_desc(sa_hi + o), ft_desc(sw_hi + o), idesc, (seg_first && ks == 0) ? 0u : 1u);
+#endif
+#if ODEVIO_FT_DBG_MMA >= 3
+              ft_mma(d_corr, ft_desc(sa_lo + o), ft_desc(sw_hi + o), idesc, (corr_started | ks) ? 1u : 0u);
+              ft_mma(d_corr, ft_desc(sa_hi + o), ft_desc(sw_lo + o), idesc, 1);
+#endif
+            }
+#if ODEVIO_FT_MULTICAST
+            ft_commit_multicast(&empty_bar[ring_stage], 0xff);
+#else
+            ft_commit(&empty_bar[ring_stage]);
+#endif
           }
-          ft_commit_multicast(&empty_bar[ring_stage], 0xff);
+          corr_started = 1;
+          __syncwarp();
           if (++ring_stage == static_cast<uint32_t>(p.nst)) { ring_stage = 0; ring_phase ^= 1u; }
         }
-        ft_commit(&accum_bar);
-        FT_STAMP(8 + l * 8 + 1);                         // all MMAs issued
-      } else if (warp < 4) {
-        // ===== epilogue warps: thread = row
+        if (elect_one()) ft_commit(&accum_bar);
+        __syncwarp();
+        if (lane == 0) FT_STAMP(8 + l * 8 + 1);                         // all MMAs issued
+      } else if (warp < FT_EPI_WARPS) {
+        // ===== epilogue warps: thread = row; warps w and w + 4 share TMEM lane quarter w and split the columns
         mbar_wait(&accum_bar, accum_phase);
         if (tid == 0) FT_STAMP(8 + l * 8 + 2);           // accumulators complete
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int r = tid;
+        const int r = tid & 127;
+        const int half = tid >> 7, nchunks = Nc / 32;
+        const int cbeg = half == 0 ? 0 : (nchunks + 1) / 2, cend = half == 0 ? (nchunks + 1) / 2 : nchunks;
         const bool last = l == p.NL - 1;
         const int act = last ? ACT_TANH : p.act;
         const int nseg = ft_nseg(Nc);
-        for (int c0 = 0; c0 < Nc; c0 += 32) {
+        for (int c0 = 32 * cbeg; c0 < 32 * cend; c0 += 32) {
           float accv[32];
 #pragma unroll
           for (int q = 0; q < 32; ++q) accv[q] = 0.f;
           uint32_t u[32];
           for (int sgm = nseg; sgm >= 0; --sgm) {        // cross terms first (smallest), then the K segments
-          const uint32_t taddr = tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(sgm * Nc + c0);
+          const uint32_t taddr = tmem_d + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(sgm * Nc + c0);
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -276,7 +339,7 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
               for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
           } else {
-            store_chunk(nx_hi, nx_lo, r, n0, v);
+            store_chunk(nx, r, n0, v);
           }
         }
         asm volatile("fence.proxy.async;" ::: "memory");
@@ -295,13 +358,13 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncwarp();
   cluster_sync_all();          // no CTA may leave while peers can still multicast into it / arrive on its barriers
-  if (warp == 5) {
+  if (warp == FT_WARP_MMA) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
   }
 }
 
-// W [N][K] (PyTorch) -> [c][K/32][Nc/8][8 kq][8 n][4 k] hi / lo
-__global__ void ft_pack_weight_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ hi, float* __restrict__ lo) {
+// W [N][K] (PyTorch) -> fp32 operand image [c][K/32][Nc/8][8 kq][8 n][4 k]
+__global__ void ft_pack_weight_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ dst) {
   const int Nc = N / FT_NC;
   const size_t total = static_cast<size_t>(N) * K;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -310,15 +373,13 @@ __global__ void ft_pack_weight_kernel(const float* __restrict__ W, int N, int K,
     const int c = n / Nc, nl = n - c * Nc;
     const size_t o = static_cast<size_t>(c) * Nc * K +
                      ((static_cast<size_t>(k >> 5) * (Nc >> 3) + (nl >> 3)) * 8 + ((k & 31) >> 2)) * 32 + (nl & 7) * 4 + (k & 3);
-    const float w = W[i];
-    const float h = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
-    hi[o] = h; lo[o] = w - h;
+    dst[o] = W[i];
   }
 }
 
 struct FtPlan {
   int NL, ntiles, nclusters, nst, kmax, ncmax;
-  size_t off_whi[FT_MAX_LAYERS], off_wlo[FT_MAX_LAYERS], off_xa, xa_buf_floats, total_bytes, smem_bytes;
+  size_t off_w[FT_MAX_LAYERS], off_xa, xa_buf_floats, total_bytes, smem_bytes;
   uint32_t stage_bytes;
   int K[FT_MAX_LAYERS], N[FT_MAX_LAYERS];
 };
@@ -336,8 +397,7 @@ int ft_plan(int M, int D, int H, int n_hidden, FtPlan& pl) {
   for (int l = 0; l < pl.NL; ++l) {
     pl.K[l] = l == 0 ? D : H;
     pl.N[l] = l == pl.NL - 1 ? D : H;
-    pl.off_whi[l] = take(static_cast<size_t>(pl.K[l]) * pl.N[l]);
-    pl.off_wlo[l] = take(static_cast<size_t>(pl.K[l]) * pl.N[l]);
+    pl.off_w[l] = take(static_cast<size_t>(pl.K[l]) * pl.N[l]);
   }
   int dev = 0, nsm = 148;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) {
@@ -348,7 +408,7 @@ int ft_plan(int M, int D, int H, int n_hidden, FtPlan& pl) {
   pl.nclusters = nsm / FT_NC;
   if (pl.nclusters > pl.ntiles) pl.nclusters = pl.ntiles;
   pl.xa_buf_floats = static_cast<size_t>(FT_ROWS) * pl.kmax;
-  pl.off_xa = take(static_cast<size_t>(pl.nclusters) * 4 * pl.xa_buf_floats);
+  pl.off_xa = take(static_cast<size_t>(pl.nclusters) * 2 * pl.xa_buf_floats);
   pl.total_bytes = off * sizeof(float);
   pl.stage_bytes = 2u * (FT_ROWS + pl.ncmax) * FT_KCH * 4u;
   pl.nst = static_cast<int>((220u * 1024u) / pl.stage_bytes);
@@ -393,10 +453,10 @@ int32_t odevio_odefunc_forward(int32_t M, int32_t D, int32_t H, int32_t n_hidden
   for (int l = 0; l < pl.NL; ++l) {
     if (!weights[l] || !biases[l]) return ODEVIO_E_NULL;
     p.K[l] = pl.K[l]; p.N[l] = pl.N[l];
-    ft_pack_weight_kernel<<<296, 256, 0, stream>>>(weights[l], pl.N[l], pl.K[l], ws + pl.off_whi[l], ws + pl.off_wlo[l]);
+    ft_pack_weight_kernel<<<296, 256, 0, stream>>>(weights[l], pl.N[l], pl.K[l], ws + pl.off_w[l]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int32_t>(e);
-    p.Whi[l] = ws + pl.off_whi[l]; p.Wlo[l] = ws + pl.off_wlo[l]; p.bias[l] = biases[l];
+    p.Wp[l] = ws + pl.off_w[l]; p.bias[l] = biases[l];
   }
   p.x = x; p.out = out; p.xa = ws + pl.off_xa; p.xa_buf_floats = pl.xa_buf_floats;
   p.ntiles = pl.ntiles; p.nst = pl.nst; p.stage_bytes = pl.stage_bytes;

@@ -2,7 +2,7 @@
 import os, sys, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["ODEVIO_LIB_PATH"] = os.path.join(ROOT, "odevio_b200", "lib", "libodevio_b200.timeline.so")
+os.environ["ODEVIO_LIB_PATH"] = os.path.join(ROOT, "odevio_b200", "lib", "libodevio_b200.%s.so" % os.environ.get("FT_VARIANT", "timeline"))
 import torch, odevio_b200
 from odevio_b200 import _lib
 dev = torch.device("cuda:0")
