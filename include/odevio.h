@@ -98,7 +98,8 @@ typedef struct odevio_odernn_cfg {
   int32_t max_steps;          /* per-interval guard; rows still running get STATUS_MAX_STEPS */
   int32_t precision;          /* ODEVIO_PRECISION_* */
   int32_t save_checkpoints;   /* 1: record what odevio_odernn_backward needs in `ckpt` (training;
-                                 tanh-RNN jump, rows_per_tile 4 or 8, endpoint_dense = 0) */
+                                 rows_per_tile 4 or 8 with rows_per_tile * L a multiple of 8,
+                                 endpoint_dense = 0, D and H multiples of 128) */
   int32_t rows_per_tile;      /* 0 = auto; else 4, 8 or 16 sequences per CTA */
   int32_t exact_landing;      /* 1 (default): a step clamped to the remaining interval ends exactly at
                                  t_end; 0: literal fp32 t + (t_end - t), may need a 1-ulp extra step */

@@ -186,8 +186,8 @@ int plan_odernn(const odevio_odernn_cfg& c, OdePlan& pl) {
   };
   int rt = c.rows_per_tile;
   if (c.save_checkpoints) {
-    // training: the backward kernel exists for 4- and 8-row tiles and the tanh-RNN jump
-    if (c.rnn_type != ODEVIO_RNN_TANH || c.endpoint_dense) return ODEVIO_E_ENUM;
+    // training: the backward kernel exists for 4- and 8-row tiles and the y1 end-point rule
+    if (c.endpoint_dense) return ODEVIO_E_ENUM;
     if (c.ckpt_loops < 0 || c.ckpt_loops > 4096) return ODEVIO_E_SHAPE;
     if (rt == 16) return ODEVIO_E_SHAPE;
     if (rt == 0) rt = fit(8) ? 8 : 4;
@@ -242,6 +242,9 @@ struct BwdPlan {
   size_t off_recA_ode[kMaxLinears], off_recG_ode[kMaxLinears], off_recA_ode_lo[kMaxLinears], off_recG_ode_lo[kMaxLinears];
   size_t off_recA_rnn[kMaxRnnLayers], off_recG_rnn[kMaxRnnLayers];
   size_t off_recA_reg0, off_recG_reg0, off_recA_reg1, off_recG_reg1;
+  size_t off_Wrnn[kMaxRnnLayers][4], off_brnn[kMaxRnnLayers][4];      // GRU: gate re-evaluation weights
+  int Rb;
+  int GW;                                                              // G-record width per jump row: D (rnn) | 6D (gru)
   size_t off_part, part_floats;
   long long jump_rows;
   size_t total_bytes;
@@ -250,13 +253,15 @@ struct BwdPlan {
 int plan_odernn_bwd(const odevio_odernn_cfg& c, const OdePlan& pl, long long ode_rows, BwdPlan& bp) {
   if (ode_rows < 0 || ode_rows % pl.R) return ODEVIO_E_SHAPE;
   // the ODEFunc weight gradients run on tcgen05 (wgrad_tc.cu): 128-row output tiles, 8-row k-steps
-  if (pl.R % 8 || pl.R > 32 || c.D % 128 || c.H % 128) return ODEVIO_E_SHAPE;
+  if (pl.R % 4 || pl.R > 32 || c.D % 128 || c.H % 128) return ODEVIO_E_SHAPE;
+  bp.Rb = (pl.R + 7) / 8 * 8;                     // record block rows (8-row k-steps); padding rows are zero
   DevTableau tb;
   if (!make_tableau(c.solver, tb)) return ODEVIO_E_ENUM;
   bp.ns = tb.ssal ? tb.n_stages - 1 : tb.n_stages;
   const int NL = c.n_hidden + 1;
   const size_t maxdh = static_cast<size_t>(c.D > c.H ? c.D : c.H);
   bp.buf_floats = maxdh * pl.R;
+  if (bp.buf_floats < static_cast<size_t>(2) * c.D * pl.RT) bp.buf_floats = static_cast<size_t>(2) * c.D * pl.RT;
   bp.stage_floats = pl.stage_floats;
   const size_t fixed_bytes = (2 * bp.buf_floats + 2 * static_cast<size_t>(pl.R)) * sizeof(float) + 8 +
                              2 * kMaxStagesRing * 8 + 128;
@@ -270,10 +275,20 @@ int plan_odernn_bwd(const odevio_odernn_cfg& c, const OdePlan& pl, long long ode
   auto take = [&](size_t n) { size_t o = off; off = align_up(off + n, 64); return o; };
   for (int j = 0; j < NL; ++j) bp.off_Wode[j] = take(static_cast<size_t>(pl.Kode[j]) * pl.Node[j]);
   bp.off_Wreg0 = take(static_cast<size_t>(c.D) * kRegHidden);
+  const bool gru = c.rnn_type == ODEVIO_RNN_GRU;
+  bp.GW = gru ? 6 * c.D : c.D;
+  if (gru) {
+    const size_t DDg = static_cast<size_t>(c.D) * c.D;
+    for (int l = 0; l < c.L; ++l) {
+      bp.off_Wrnn[l][0] = take(2 * DDg); bp.off_Wrnn[l][1] = take(2 * DDg);
+      bp.off_Wrnn[l][2] = take(DDg); bp.off_Wrnn[l][3] = take(DDg);
+      for (int g = 0; g < 4; ++g) bp.off_brnn[l][g] = take(c.D);
+    }
+  }
   const size_t arr = static_cast<size_t>(c.D) * pl.R, harr = static_cast<size_t>(c.H) * pl.R;
   bp.scratch_floats_per_cta = align_up((2 * kMaxStages + 1) * arr + static_cast<size_t>(kMaxStages) * (NL - 1) * harr, 64);
   bp.off_scratch = take(bp.scratch_floats_per_cta * pl.grid);
-  const size_t M = static_cast<size_t>(ode_rows);
+  const size_t M = static_cast<size_t>(ode_rows / pl.R) * bp.Rb;
   for (int j = 0; j < NL; ++j) {
     bp.off_recA_ode[j] = take(M * pl.Kode[j]);
     bp.off_recA_ode_lo[j] = take(M * pl.Kode[j]);
@@ -284,7 +299,7 @@ int plan_odernn_bwd(const odevio_odernn_cfg& c, const OdePlan& pl, long long ode
   const size_t MJ = static_cast<size_t>(bp.jump_rows);
   for (int l = 0; l < c.L; ++l) {
     bp.off_recA_rnn[l] = take(MJ * 2 * c.D);
-    bp.off_recG_rnn[l] = take(MJ * c.D);
+    bp.off_recG_rnn[l] = take(MJ * bp.GW);
   }
   bp.off_recA_reg0 = take(MJ * c.D);
   bp.off_recG_reg0 = take(MJ * kRegHidden);
@@ -299,10 +314,11 @@ int plan_odernn_bwd(const odevio_odernn_cfg& c, const OdePlan& pl, long long ode
   };
   for (int j = 0; j < NL; ++j) {
     size_t v = static_cast<size_t>(wgrad_tc_splits(ode_rows / pl.R, pl.Node[j], pl.Kode[j], pl.nsm)) * pl.Node[j] * pl.Kode[j];
+    (void)M;
     if (v < static_cast<size_t>(256) * pl.Node[j]) v = static_cast<size_t>(256) * pl.Node[j];
     if (v > part) part = v;
   }
-  need(bp.jump_rows, c.D, 2 * c.D);
+  if (gru) need(bp.jump_rows, 3 * c.D, c.D); else need(bp.jump_rows, c.D, 2 * c.D);
   need(bp.jump_rows, kRegHidden, c.D);
   need(bp.jump_rows, kPoseDim, kRegHidden);
   bp.part_floats = part;
@@ -595,9 +611,29 @@ int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn
     p.recA_ode[j] = ws + bp.off_recA_ode[j]; p.recG_ode[j] = ws + bp.off_recG_ode[j];
     p.recA_ode_lo[j] = ws + bp.off_recA_ode_lo[j]; p.recG_ode_lo[j] = ws + bp.off_recG_ode_lo[j];
   }
+  const size_t DDb = static_cast<size_t>(D) * D;
   for (int l = 0; l < c.L; ++l) {
     p.Wih_raw[l] = w->rnn_w_ih[l]; p.Whh_raw[l] = w->rnn_w_hh[l];
     p.recA_rnn[l] = ws + bp.off_recA_rnn[l]; p.recG_rnn[l] = ws + bp.off_recG_rnn[l];
+    if (c.rnn_type == ODEVIO_RNN_GRU) {
+      if (!w->rnn_b_ih[l] || !w->rnn_b_hh[l]) return ODEVIO_E_NULL;
+      float* wr = ws + bp.off_Wrnn[l][0]; float* wz = ws + bp.off_Wrnn[l][1];
+      float* wi = ws + bp.off_Wrnn[l][2]; float* wh = ws + bp.off_Wrnn[l][3];
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l], D, D, wr, D, 0, 0, stream));
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_hh[l], D, D, wr, D, D, 0, stream));
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l] + DDb, D, D, wz, D, 0, 0, stream));
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_hh[l] + DDb, D, D, wz, D, D, 0, stream));
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l] + 2 * DDb, D, D, wi, D, 0, 0, stream));
+      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_hh[l] + 2 * DDb, D, D, wh, D, 0, 0, stream));
+      float* br = ws + bp.off_brnn[l][0]; float* bz = ws + bp.off_brnn[l][1];
+      float* bi = ws + bp.off_brnn[l][2]; float* bh = ws + bp.off_brnn[l][3];
+      ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_ih[l], w->rnn_b_hh[l], br, D, stream));
+      ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_ih[l] + D, w->rnn_b_hh[l] + D, bz, D, stream));
+      ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_ih[l] + 2 * D, nullptr, bi, D, stream));
+      ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_hh[l] + 2 * D, nullptr, bh, D, stream));
+      p.Wrnn[l][0] = wr; p.Wrnn[l][1] = wz; p.Wrnn[l][2] = wi; p.Wrnn[l][3] = wh;
+      p.brnn[l][0] = br; p.brnn[l][1] = bz; p.brnn[l][2] = bi; p.brnn[l][3] = bh;
+    }
   }
   {
     float* dst = ws + bp.off_Wreg0;
@@ -612,6 +648,17 @@ int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn
   p.ckpt = reinterpret_cast<const float*>(static_cast<const unsigned char*>(ckpt) + pl.ckpt_head_bytes);
   p.ckpt_floats_per_tile = pl.ckpt_floats_per_tile; p.CK = pl.CK;
   p.rec_base = reinterpret_cast<const long long*>(rec_base);
+  p.Rb = bp.Rb;
+  if (bp.Rb != pl.R) {
+    // padding rows of every record block must read as zero in the weight-gradient GEMMs
+    const size_t Mb = static_cast<size_t>(ode_rows / pl.R) * bp.Rb;
+    for (int j = 0; j < NL; ++j) {
+      ODEVIO_CUDA_TRY(cudaMemsetAsync(p.recA_ode[j], 0, sizeof(float) * Mb * pl.Kode[j], stream));
+      ODEVIO_CUDA_TRY(cudaMemsetAsync(p.recA_ode_lo[j], 0, sizeof(float) * Mb * pl.Kode[j], stream));
+      ODEVIO_CUDA_TRY(cudaMemsetAsync(p.recG_ode[j], 0, sizeof(float) * Mb * pl.Node[j], stream));
+      ODEVIO_CUDA_TRY(cudaMemsetAsync(p.recG_ode_lo[j], 0, sizeof(float) * Mb * pl.Node[j], stream));
+    }
+  }
   p.scratch = ws + bp.off_scratch; p.scratch_floats_per_cta = bp.scratch_floats_per_cta;
   p.ntiles = pl.ntiles; p.nst = bp.nst;
   p.buf_floats = static_cast<int>(bp.buf_floats); p.stage_floats = static_cast<int>(bp.stage_floats);
@@ -622,10 +669,19 @@ int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn
   float* part = ws + bp.off_part;
   for (int j = 0; j < NL; ++j)       // ODEFunc Linears: tcgen05 3xTF32 GEMMs over the block-format streams
     ODEVIO_CUDA_TRY(wgrad_linear_tc(p.recG_ode[j], p.recG_ode_lo[j], p.recA_ode[j], p.recA_ode_lo[j], ode_rows / pl.R,
-                                    pl.Node[j], pl.Kode[j], pl.R, g->ode_w[j], g->ode_b[j], part, pl.nsm, stream));
-  for (int l = 0; l < c.L; ++l)
-    ODEVIO_CUDA_TRY(wgrad_linear(p.recG_rnn[l], D, p.recA_rnn[l], 2 * D, bp.jump_rows, D, 2 * D,
-                                 g->rnn_w_ih[l], g->rnn_w_hh[l], D, g->rnn_b_ih[l], g->rnn_b_hh[l], part, pl.nsm, stream));
+                                    pl.Node[j], pl.Kode[j], bp.Rb, g->ode_w[j], g->ode_b[j], part, pl.nsm, stream));
+  for (int l = 0; l < c.L; ++l) {
+    if (c.rnn_type == ODEVIO_RNN_GRU) {
+      // records: A = [x | h] (ld 2D), G = [G_ih | G_hh] (ld 6D); weight_ih / weight_hh are [3D][D]
+      ODEVIO_CUDA_TRY(wgrad_linear(p.recG_rnn[l], 6 * D, p.recA_rnn[l], 2 * D, bp.jump_rows, 3 * D, D,
+                                   g->rnn_w_ih[l], nullptr, 0, g->rnn_b_ih[l], nullptr, part, pl.nsm, stream));
+      ODEVIO_CUDA_TRY(wgrad_linear(p.recG_rnn[l] + 3 * D, 6 * D, p.recA_rnn[l] + D, 2 * D, bp.jump_rows, 3 * D, D,
+                                   g->rnn_w_hh[l], nullptr, 0, g->rnn_b_hh[l], nullptr, part, pl.nsm, stream));
+    } else {
+      ODEVIO_CUDA_TRY(wgrad_linear(p.recG_rnn[l], D, p.recA_rnn[l], 2 * D, bp.jump_rows, D, 2 * D,
+                                   g->rnn_w_ih[l], g->rnn_w_hh[l], D, g->rnn_b_ih[l], g->rnn_b_hh[l], part, pl.nsm, stream));
+    }
+  }
   ODEVIO_CUDA_TRY(wgrad_linear(p.recG_reg0, kRegHidden, p.recA_reg0, D, bp.jump_rows, kRegHidden, D,
                                g->reg_w0, nullptr, 0, g->reg_b0, nullptr, part, pl.nsm, stream));
   ODEVIO_CUDA_TRY(wgrad_linear(p.recG_reg1, 8, p.recA_reg1, kRegHidden, bp.jump_rows, kPoseDim, kRegHidden,

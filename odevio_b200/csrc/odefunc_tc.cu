@@ -92,17 +92,6 @@ __device__ __forceinline__ void tma_load_1d_multicast(void* dst_smem, const void
       ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
       : "memory");
 }
-// one lane of a converged warp (operands stay warp-uniform -> uniform registers, no per-lane waterfall)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-      "elect.sync rx|px, %1;\n\t"
-      "@px mov.s32 %0, 1;\n\t}"
-      : "+r"(pred)
-      : "r"(0xffffffffu));
-  return pred != 0;
-}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }

@@ -83,7 +83,7 @@ __device__ __forceinline__ void stage_input_b(BCtx<RT>& c, const float* Y0, int 
     }
     st4(c.bufA + off, y);
     const int d = e / c.rq4;
-    rec_put4(p.recA_ode[0], p.recA_ode_lo[0], row0, p.D, c.R, d, c.rq, y);
+    rec_put4(p.recA_ode[0], p.recA_ode_lo[0], row0, p.D, p.Rb, d, c.rq, y);
   }
   named_bar_sync(1, c.th.ncons);
 }
@@ -112,7 +112,7 @@ __device__ __forceinline__ void stage_grad_b(BCtx<RT>& c, int j, long long row0)
     g.w = up.w ? dt.w * acc.w * (1.f - k.w * k.w) : 0.f;
     st4(c.bufA + off, g);
     const int d = e / c.rq4;
-    rec_put4(p.recG_ode[NLm1], p.recG_ode_lo[NLm1], row0, p.D, c.R, d, c.rq, g);
+    rec_put4(p.recG_ode[NLm1], p.recG_ode_lo[NLm1], row0, p.D, p.Rb, d, c.rq, g);
   }
   named_bar_sync(1, c.th.ncons);
 }
@@ -143,7 +143,7 @@ struct GemmOpB {
   Epilogue epi;
 };
 
-enum { BP_HEAD1 = 0, BP_HEAD2, BP_JUMP_A, BP_JUMP_B, BP_ITER, BP_RSTAGE, BP_RLAYER, BP_BSTAGE, BP_BLAYER,
+enum { BP_HEAD1 = 0, BP_HEAD2, BP_JUMP_A, BP_JUMP_B, BP_GRU_GATES, BP_GRU_ELEM, BP_GRU_BWD, BP_ITER, BP_RSTAGE, BP_RLAYER, BP_BSTAGE, BP_BLAYER,
        BP_ITER_END, BP_TILE_END };
 
 }  // namespace
@@ -214,7 +214,7 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
     __syncthreads();
 
     int ph = BP_HEAD1;
-    int i = S - 1, l = 0, it = 0, j = 0, lam = 0;
+    int i = S - 1, l = 0, it = 0, j = 0, lam = 0, gg = 0;
     float* lin = c.bufA; float* lout = c.bufB;
     const float* Y0 = nullptr;
     long long row_it = 0;                 // first ODE-stream block of the current iteration (one block per stage)
@@ -275,7 +275,8 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
           op.epi.out0 = c.GY; op.epi.ld0 = R; op.epi.off0 = (LL - 1) * RT;
           do_gemm = true;
           l = LL - 1;
-          ph = BP_JUMP_A;
+          gg = 0;
+          ph = p.rnn_type == 0 ? BP_JUMP_A : BP_GRU_GATES;
           break;
         }
         case BP_JUMP_A: {
@@ -329,6 +330,111 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
           else ph = BP_JUMP_A;
           break;
         }
+        // ---------------------------------------------------------------- GRU jump backward
+        case BP_GRU_GATES: {
+          // re-evaluate the gates of layer l: r, z (K = 2D on [x ; h]), hn = W_hn h + b_hn, n = tanh(W_in x + b_in + r hn)
+          float* RG = c.K[1]; float* ZG = c.K[2]; float* HN = c.K[3]; float* NG = c.K[4];     // [D][RT] scratch
+          if (gg == 0 && !c.th.producer) {
+            for (int e = c.th.ctid; e < D * RT; e += ncons) {
+              const int m = e / D, d = e - m * D;
+              float x;
+              if (l == 0) {
+                const int b = tile * RT + m;
+                x = 0.f;
+                if (b < p.B) {
+                  const size_t row = static_cast<size_t>(b) * S + i;
+                  x = (d < p.Dv) ? p.fv[row * p.Dv + d] : p.fi[row * (D - p.Dv) + (d - p.Dv)];
+                }
+              } else {
+                x = Ypost[static_cast<size_t>(d) * R + (l - 1) * RT + m];
+              }
+              const float h = Yend[static_cast<size_t>(d) * R + l * RT + m];
+              c.bufA[d * RT + m] = x;
+              c.bufA[(D + d) * RT + m] = h;
+              float* ra = p.recA_rnn[l] + (rowJ + m) * (2 * static_cast<size_t>(D));
+              ra[d] = x; ra[D + d] = h;
+            }
+            named_bar_sync(1, ncons);
+          }
+          Epilogue& e = op.epi;
+          e.mode = EPI_STORE; e.ld0 = RT;
+          op.N = D; op.ode_layout = false; op.in = c.bufA; op.K = 2 * D;
+          if (gg == 0) { op.W = p.Wrnn[l][0]; e.bias = p.brnn[l][0]; e.act = ACT_SIGMOID; e.out0 = RG; }
+          else if (gg == 1) { op.W = p.Wrnn[l][1]; e.bias = p.brnn[l][1]; e.act = ACT_SIGMOID; e.out0 = ZG; }
+          else if (gg == 2) {
+            op.W = p.Wrnn[l][3]; e.bias = p.brnn[l][3]; e.act = ACT_NONE; e.out0 = HN;
+            op.K = D; op.in = c.bufA + static_cast<size_t>(D) * RT;
+          } else {
+            op.W = p.Wrnn[l][2]; e.bias = p.brnn[l][2]; e.mode = EPI_GRU_N; e.rg = RG; e.hn = HN; e.out0 = NG;
+            op.K = D;
+          }
+          do_gemm = true;
+          if (++gg == 4) { gg = 0; ph = BP_GRU_ELEM; }
+          break;
+        }
+        case BP_GRU_ELEM: {
+          // h' = (1 - z) n + z h:  dn = g (1 - z), dz = g (h - n), dh += g z;  n = tanh(a_n + r hn):
+          // dn_pre = dn (1 - n^2), dr = dn_pre hn, d(hn) = dn_pre r;  r, z sigmoid
+          if (!c.th.producer) {
+            const float* RG = c.K[1]; const float* ZG = c.K[2]; const float* HN = c.K[3]; const float* NG = c.K[4];
+            const size_t DR = static_cast<size_t>(D) * RT;
+            for (int e = c.th.ctid; e < D * RT; e += ncons) {
+              const int m = e / D, d = e - m * D;
+              const size_t o = static_cast<size_t>(d) * R + l * RT + m;     // tile arrays
+              const size_t q = static_cast<size_t>(d) * RT + m;             // [D][RT] scratch
+              const float g = c.GY[o], h = Yend[o];
+              const float r = RG[q], z = ZG[q], hn = HN[q], n = NG[q];
+              const float dn_pre = g * (1.f - z) * (1.f - n * n);
+              const float dz_pre = g * (h - n) * z * (1.f - z);
+              const float dr_pre = dn_pre * hn * r * (1.f - r);
+              const float dhn = dn_pre * r;
+              c.GY[o] = g * z;                                              // direct path h -> h'
+              c.bufA[q] = dr_pre; c.bufA[DR + q] = dz_pre; c.bufB[q] = dn_pre; c.bufB[DR + q] = dhn;
+              float* rg = p.recG_rnn[l] + (rowJ + m) * (6 * static_cast<size_t>(D));
+              rg[d] = dr_pre; rg[D + d] = dz_pre; rg[2 * D + d] = dn_pre;               // G_ih
+              rg[3 * D + d] = dr_pre; rg[4 * D + d] = dz_pre; rg[5 * D + d] = dhn;       // G_hh
+            }
+            named_bar_sync(1, ncons);
+          }
+          gg = 0;
+          ph = BP_GRU_BWD;
+          break;
+        }
+        case BP_GRU_BWD: {
+          // dh += W_hh^T [dr_pre; dz_pre; dn_pre r],  dx = W_ih^T [dr_pre; dz_pre; dn_pre]; gate g uses rows g*D.. of
+          // the PyTorch [3D][D] weight as the K-major operand
+          const size_t DR = static_cast<size_t>(D) * RT, DD = static_cast<size_t>(D) * D;
+          const int gate = gg % 3;
+          const bool hh = gg < 3;
+          op.K = D; op.N = D; op.ode_layout = false; op.epi.act = ACT_NONE; op.epi.ld0 = R;
+          if (hh) {
+            op.W = p.Whh_raw[l] + gate * DD;
+            op.in = gate == 0 ? c.bufA : gate == 1 ? c.bufA + DR : c.bufB + DR;
+            op.epi.mode = EPI_ADD; op.epi.out0 = c.GY; op.epi.off0 = l * RT;
+            do_gemm = true;
+          } else {
+            op.W = p.Wih_raw[l] + gate * DD;
+            op.in = gate == 0 ? c.bufA : gate == 1 ? c.bufA + DR : c.bufB;
+            if (l > 0) {
+              op.epi.mode = EPI_ADD; op.epi.out0 = c.GY; op.epi.off0 = (l - 1) * RT;
+              do_gemm = true;
+            } else if (p.gfused) {
+              // accumulate the three gate contributions in scratch, emit the rows with the last one
+              op.epi.mode = gate == 0 ? EPI_STORE : EPI_ADD; op.epi.out0 = c.K[5]; op.epi.ld0 = RT; op.epi.off0 = 0;
+              if (gate == 2) {
+                op.epi.rec = p.gfused; op.epi.rec_row0 = static_cast<long long>(tile) * RT * S + i;
+                op.epi.rec_ld = D; op.epi.rec_rstride = S; op.epi.rec_valid = nvalid;
+              }
+              do_gemm = true;
+            }
+          }
+          if (++gg == 6) {
+            gg = 0;
+            if (--l < 0) { it = p.nloops[static_cast<size_t>(tile) * S + i] - 1; ph = BP_ITER; }
+            else ph = BP_GRU_GATES;
+          }
+          break;
+        }
         case BP_ITER: {
           if (it < 0) {
             ph = (--i >= 0) ? BP_HEAD1 : BP_TILE_END;
@@ -362,7 +468,7 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
             op.epi.act = p.act; op.epi.out0 = lout;
             op.epi.out1 = c.HS + (static_cast<size_t>(j) * (NL - 1) + lam) * harr; op.epi.ld1 = R;
             op.epi.rec = p.recA_ode[lam + 1]; op.epi.rec_lo = p.recA_ode_lo[lam + 1];
-            op.epi.rec_row0 = row_it + j; op.epi.rec_ld = H; op.epi.rec_rstride = R; op.epi.rec_valid = RT;
+            op.epi.rec_row0 = row_it + j; op.epi.rec_ld = H; op.epi.rec_rstride = p.Rb; op.epi.rec_valid = RT;
           }
           do_gemm = true;
           float* t = lin; lin = lout; lout = t;
@@ -386,7 +492,7 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
             op.epi.hs = c.HS + (static_cast<size_t>(j) * (NL - 1) + (lam - 1)) * harr; op.epi.ldh = R;
             op.epi.out0 = lout;
             op.epi.rec = p.recG_ode[lam - 1]; op.epi.rec_lo = p.recG_ode_lo[lam - 1];
-            op.epi.rec_row0 = row_it + j; op.epi.rec_ld = H; op.epi.rec_rstride = R; op.epi.rec_valid = RT;
+            op.epi.rec_row0 = row_it + j; op.epi.rec_ld = H; op.epi.rec_rstride = p.Rb; op.epi.rec_valid = RT;
           } else {
             op.epi.mode = EPI_STORE; op.epi.act = ACT_NONE; op.epi.out0 = c.GZ[j];
           }

@@ -75,8 +75,11 @@ struct BwdParams {
   int Kode[kMaxLinears], Node[kMaxLinears];
   // PyTorch-layout [out][in] weights: the K-major operand of the transposed products W^T g
   const float* Wode_raw[kMaxLinears];
-  const float* Wih_raw[kMaxRnnLayers];
+  const float* Wih_raw[kMaxRnnLayers];       // rnn.weight_ih_l{k}: [G*D][D], G = 1 | 3 (gates r, z, n)
   const float* Whh_raw[kMaxRnnLayers];
+  // GRU only: forward-packed gate weights / biases for the gate re-evaluation (same packing as FwdParams)
+  const float* Wrnn[kMaxRnnLayers][4];
+  const float* brnn[kMaxRnnLayers][4];
   const float* Wreg0;      // packed [D][128]
   const float* breg0;
   const float* Wreg0_raw;  // [128][D]
@@ -92,9 +95,10 @@ struct BwdParams {
   // record streams (row-major) for the deferred weight-gradient GEMMs
   // ODE-layer streams: tcgen05 operand blocks of R rows (tile_gemm.cuh: rec_block_offset), hi / lo parts
   const long long* rec_base;                 // [ntiles * S] first ODE-stream row of (tile, interval); block = row / R
+  int Rb;                                    // rows per record block = R rounded up to 8 (padding rows stay zero)
   float* recA_ode[kMaxLinears]; float* recG_ode[kMaxLinears];     // hi: [blocks][K_j * R], [blocks][N_j * R]
   float* recA_ode_lo[kMaxLinears]; float* recG_ode_lo[kMaxLinears];
-  float* recA_rnn[kMaxRnnLayers]; float* recG_rnn[kMaxRnnLayers]; // [ntiles*S*RT][2D], [..][D]
+  float* recA_rnn[kMaxRnnLayers]; float* recG_rnn[kMaxRnnLayers]; // [ntiles*S*RT][2D], [..][D] (GRU: [..][6D] = [G_ih | G_hh])
   float* recA_reg0; float* recG_reg0;        // [ntiles*S*RT][D], [..][128]
   float* recA_reg1; float* recG_reg1;        // [ntiles*S*RT][128], [..][8] (6 used)
   // per-CTA scratch: K[7], GZ[7], GY (D*R each), HS[7][NL-1] (H*R each)

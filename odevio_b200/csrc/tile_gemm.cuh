@@ -71,7 +71,8 @@ struct TileThread {
 //   rec_lo != nullptr: tcgen05 operand blocks (wgrad_tc.cu) -- block rec_row0 holds the tile's R rows of
 //       all rec_ld features as K-major core matrices [feature/8][R/4][8][4], split into a
 //       TF32-exact high part (rec) and the residual (rec_lo).
-enum { EPI_STORE = 0, EPI_GRU_NEW = 1, EPI_MUL_DACT = 2, EPI_ADD = 3 };
+//   EPI_GRU_N     v = tanh(acc + bias + hn * r)                 the GRU new gate alone (backward recompute)
+enum { EPI_STORE = 0, EPI_GRU_NEW = 1, EPI_MUL_DACT = 2, EPI_ADD = 3, EPI_GRU_N = 4 };
 struct Epilogue {
   int mode;
   const float* bias;   // [N] or nullptr
@@ -140,6 +141,12 @@ __device__ __forceinline__ void run_epilogue(const Epilogue& e, int n, int rb, c
       const size_t o = static_cast<size_t>(n) * RT + r;
       const float ng = apply_act((acc[r] + b) + e.hn[o] * e.rg[o], ACT_TANH);
       v[r] = (e.hprev[o] - ng) * e.zg[o] + ng;
+    }
+  } else if (e.mode == EPI_GRU_N) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const size_t o = static_cast<size_t>(n) * RT + r;
+      v[r] = apply_act((acc[r] + b) + e.hn[o] * e.rg[o], ACT_TANH);
     }
   } else if (e.mode == EPI_MUL_DACT) {
     const float* hp = e.hs + static_cast<size_t>(n) * e.ldh + e.offh + rb * RT;

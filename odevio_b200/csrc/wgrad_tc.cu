@@ -107,8 +107,9 @@ wgrad_tc_kernel(const float* __restrict__ Ghi, const float* __restrict__ Glo,
       tma_load_1d(dst + 2 * g_tile_bytes + a_tile_bytes, Alo + blk * a_blk + a_off, a_tile_bytes, &full_bar[stage]);
       if (++stage == static_cast<uint32_t>(nst)) { stage = 0; phase ^= 1u; }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer
+  } else if (warp == 1) {
+    // ===== MMA issuer: the whole warp runs the loop with warp-uniform operands, one elected lane issues
+    // (a single active lane makes ptxas move every descriptor through an ELECT / R2UR waterfall)
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, K-major both, N >> 3, M >> 4
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
                            (static_cast<uint32_t>(TC_BM >> 4) << 24);
@@ -117,7 +118,8 @@ wgrad_tc_kernel(const float* __restrict__ Ghi, const float* __restrict__ Glo,
     // accumulations into one accumulator), so (a) the hi*hi products and the 2^-11 smaller cross terms
     // go to separate accumulators, added in fp32 in the epilogue, and (b) a CTA only reduces
     // kBlocksPerSplit blocks -- longer reductions are split-M partials summed by the reduce kernel.
-    const uint32_t d_main = tmem_d, d_corr = tmem_d + static_cast<uint32_t>(BN);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
+    const uint32_t d_main = tmem_u, d_corr = tmem_u + static_cast<uint32_t>(BN);
     uint32_t stage = 0, phase = 0, acc = 0;
     for (int b = 0; b < nb; ++b) {
       mbar_wait(&full_bar[stage], phase);
@@ -125,19 +127,24 @@ wgrad_tc_kernel(const float* __restrict__ Ghi, const float* __restrict__ Glo,
       const uint32_t base = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
       const uint32_t g_hi = base, g_lo = base + g_tile_bytes;
       const uint32_t a_hi = base + 2 * g_tile_bytes, a_lo = a_hi + a_tile_bytes;
-      for (int ks = 0; ks < (R >> 3); ++ks) {          // 8 rows (2 core matrices along K) per tf32 MMA
-        const uint32_t o = static_cast<uint32_t>(ks) * 256;
-        const uint64_t dgh = smem_desc_kmajor(g_hi + o, lbo, sbo), dgl = smem_desc_kmajor(g_lo + o, lbo, sbo);
-        const uint64_t dah = smem_desc_kmajor(a_hi + o, lbo, sbo), dal = smem_desc_kmajor(a_lo + o, lbo, sbo);
-        umma_tf32(d_main, dgh, dah, idesc, acc);
-        umma_tf32(d_corr, dgl, dah, idesc, acc);
-        acc = 1;
-        umma_tf32(d_corr, dgh, dal, idesc, 1);
+      if (elect_one()) {
+        for (int ks = 0; ks < (R >> 3); ++ks) {        // 8 rows (2 core matrices along K) per tf32 MMA
+          const uint32_t o = static_cast<uint32_t>(ks) * 256;
+          const uint64_t dgh = smem_desc_kmajor(g_hi + o, lbo, sbo), dgl = smem_desc_kmajor(g_lo + o, lbo, sbo);
+          const uint64_t dah = smem_desc_kmajor(a_hi + o, lbo, sbo), dal = smem_desc_kmajor(a_lo + o, lbo, sbo);
+          const uint32_t a0 = (acc | static_cast<uint32_t>(ks)) ? 1u : 0u;
+          umma_tf32(d_main, dgh, dah, idesc, a0);
+          umma_tf32(d_corr, dgl, dah, idesc, a0);
+          umma_tf32(d_corr, dgh, dal, idesc, 1);
+        }
+        umma_commit(&empty_bar[stage]);                // frees the slot when these MMAs have read it
       }
-      umma_commit(&empty_bar[stage]);                  // frees the slot when these MMAs have read it
+      acc = 1;
+      __syncwarp();
       if (++stage == static_cast<uint32_t>(nst)) { stage = 0; phase ^= 1u; }
     }
-    umma_commit(&accum_bar);                           // accumulator complete
+    if (elect_one()) umma_commit(&accum_bar);          // accumulator complete
+    __syncwarp();
   }
   __syncwarp();
 

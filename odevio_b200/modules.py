@@ -298,9 +298,9 @@ class PoseODERNN(nn.Module):
                 cfg.rows_per_tile = 8
             ckpt_bytes = lib.odevio_odernn_ckpt_bytes(C.byref(cfg))
             if ckpt_bytes == 0:
-                raise _lib.OdevioError("training through the fused path supports the tanh-RNN jump, "
-                                       "ode_endpoint='y1' and rows_per_tile in {0, 4, 8} "
-                                       f"(rnn={self.rnn_type}, endpoint={self.endpoint})")
+                raise _lib.OdevioError("training through the fused path needs ode_endpoint='y1', rows_per_tile in "
+                                       "{0, 4, 8} and D, H multiples of 128 "
+                                       f"(endpoint={self.endpoint}, D={cfg.D}, H={cfg.H})")
             ckpt = torch.empty(ckpt_bytes, dtype=torch.uint8, device=dev)
         nbytes = lib.odevio_odernn_workspace_bytes(C.byref(cfg))
         if nbytes == 0:

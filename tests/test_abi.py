@@ -78,8 +78,11 @@ def test_training_geometry_and_sizes_without_gpu(lib):
     small = lib.odevio_odernn_backward_workspace_bytes(C.byref(cfg), 0)
     big = lib.odevio_odernn_backward_workspace_bytes(C.byref(cfg), 10000)
     assert small > 0 and big - small >= 10000 * 4 * (768 + 512 + 512 + 512 + 512 + 768)
-    cfg.rnn_type = 1                                               # GRU training is not built
+    cfg.rnn_type = 1                                               # GRU: wider G records for the jump
+    assert lib.odevio_odernn_backward_workspace_bytes(C.byref(cfg), 0) > small
+    cfg.endpoint_dense = 1                                         # literal dense end point: no backward
     assert lib.odevio_odernn_ckpt_bytes(C.byref(cfg)) == 0
+    cfg.endpoint_dense = 0
     cfg.rnn_type, cfg.solver = 0, 4                                # rk4: 4 stages, substeps iterations
     cfg.substeps = 2
     assert lib.odevio_odernn_geometry(C.byref(cfg), geo) == 0 and (geo[3], geo[4]) == (4, 2)

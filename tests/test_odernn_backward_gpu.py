@@ -123,10 +123,13 @@ def test_backward_batch_not_multiple_of_tile(cuda_device):
     _compare(cuda_device, 11, 2)
 
 
-def test_gru_training_raises(cuda_device):
-    ref, mod = make_pair(cuda_device, ode_rnn_type="gru")
-    fv, fi, ts = inputs(4, 2)
-    import odevio_b200
-    with pytest.raises(odevio_b200.OdevioError):
-        mod.train()
-        mod(fv.to(cuda_device), fi.to(cuda_device), ts.to(cuda_device))
+def test_backward_gru(cuda_device):
+    """GRU jump (reference menu, PoseODERNN.py:139-148): gate re-evaluation + backward in the kernel."""
+    _compare(cuda_device, 6, 3, ode_rnn_type="gru")
+    _compare(cuda_device, 5, 2, ode_rnn_type="gru", rnn_num_layers=3, ode_solver="rk4", prev=True, hT_weight=0.5)
+
+
+def test_backward_shipped_run_config(cuda_device):
+    """The reference's shipped ODE-RNN run (scripts/run_training.sh:9-24): L=3, H=1024, n=2, soft fusion."""
+    _compare(cuda_device, 5, 2, tol=2 * GRAD_RTOL, rnn_num_layers=3, ode_hidden_dim=1024, ode_fn_num_layers=2,
+             fuse_method="soft")
