@@ -38,9 +38,12 @@ namespace {
 
 constexpr int FT_ROWS = 128;          // rows per tile = MMA M
 constexpr int FT_NC = 8;              // CTAs per cluster = column slices
-constexpr int FT_KCH = 32;            // k per ring stage
+constexpr int FT_KCH = 16;            // k per ring stage (two 8-wide tf32 k-steps)
+constexpr int FT_RAW_STAGES = 8;      // fp32 chunks in flight (bulk TMA -> splitter); 4 when shared memory is short
+constexpr int FT_OP_STAGES = 4;       // split hi/lo operand stages (splitter -> tensor core) == splitter warps:
+                                      // chunk g uses raw stage g % nraw and operand stage g % 4, both always served by
+                                      // splitter warp g % 4, so every parity wait is at most one phase behind
 constexpr int FT_MAX_LAYERS = ODEVIO_MAX_ODE_LINEARS;
-constexpr int FT_MAX_STAGES = 4;
 // warps 0-7 epilogue (thread = row, two column halves), warps 8-11 hi/lo splitter, warp 12 TMA producer,
 // warp 13 MMA issuer
 constexpr int FT_EPI_WARPS = 8, FT_SPLIT_WARPS = 4;
@@ -56,14 +59,15 @@ struct FtParams {
   float* out;                                  // [M][N[NL-1]]
   float* xa;                                   // per cluster: 2 buffers x 128 x Kmax floats (fp32 operand image)
   size_t xa_buf_floats;                        // 128 * Kmax
-  int ntiles, nst;
-  uint32_t stage_bytes;                        // 2 * (128 + Ncmax) * 32 * 4
+  int ntiles, nraw;
+  uint32_t raw_stage_bytes;                    // (128 + Ncmax) * 16 * 4: one fp32 A chunk + one fp32 W chunk
+  uint32_t op_stage_bytes;                     // 2 * raw: hi and lo images
 };
 
 __device__ __forceinline__ uint64_t ft_desc(uint32_t saddr) {
-  // K-major, no swizzle: LBO (k core matrices) = 128 B, SBO (8-row groups) = 8 * 128 B; version 1
+  // K-major, no swizzle: LBO (k core matrices) = 128 B, SBO (8-row groups) = (KCH / 4) * 128 B; version 1
   return static_cast<uint64_t>((saddr >> 4) & 0x3fffu) | (static_cast<uint64_t>(128u >> 4) << 16) |
-         (static_cast<uint64_t>(1024u >> 4) << 32) | (1ull << 46);
+         (static_cast<uint64_t>((FT_KCH / 4 * 128u) >> 4) << 32) | (1ull << 46);
 }
 __device__ __forceinline__ void ft_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -99,26 +103,26 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ int ft_nseg(int Nc) { const int n = 512 / Nc - 1; return n > 4 ? 4 : n; }
 __device__ __forceinline__ float ft_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-// float offset of (row r, feature k) in a 128-row operand buffer: [k/32][r/8][(k%32)/4][r%8][k%4]
+// float offset of (row r, feature k) in a 128-row operand buffer: [k/KCH][r/8][(k%KCH)/4][r%8][k%4]
 __device__ __forceinline__ size_t xa_offset(int r, int k) {
-  return ((static_cast<size_t>(k >> 5) * 16 + (r >> 3)) * 8 + ((k & 31) >> 2)) * 32 + (r & 7) * 4 + (k & 3);
+  return ((static_cast<size_t>(k / FT_KCH) * 16 + (r >> 3)) * (FT_KCH / 4) + ((k % FT_KCH) >> 2)) * 32 + (r & 7) * 4 + (k & 3);
 }
 
 // thread = row: 32 consecutive features (one k-chunk) -> fp32 operand image (the hi / lo parts are
 // produced in shared memory by the splitter warps: one copy crosses L2 and the SM boundary, not two)
 __device__ __forceinline__ void store_chunk(float* dst, int r, int k0, const float (&v)[32]) {
-  const size_t base = xa_offset(r, k0);
 #pragma unroll
   for (int q = 0; q < 8; ++q)
-    *reinterpret_cast<float4*>(dst + base + q * 32) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    *reinterpret_cast<float4*>(dst + xa_offset(r, k0 + 4 * q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
 __global__ void __cluster_dims__(FT_NC, 1, 1) __launch_bounds__(FT_THREADS, 1)
 odefunc_tc_kernel(const __grid_constant__ FtParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full_bar[FT_MAX_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[FT_MAX_STAGES];
-  __shared__ __align__(8) uint64_t ready_bar[FT_MAX_STAGES];     // splitter -> MMA issuer
+  __shared__ __align__(8) uint64_t raw_full[FT_RAW_STAGES];      // bulk TMA -> splitter
+  __shared__ __align__(8) uint64_t raw_empty[FT_RAW_STAGES];     // splitter -> producer
+  __shared__ __align__(8) uint64_t op_ready[FT_OP_STAGES];       // splitter -> MMA issuer
+  __shared__ __align__(8) uint64_t op_empty[FT_OP_STAGES];       // tcgen05.commit -> splitter
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
 
@@ -128,13 +132,8 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
   const int cluster_id = blockIdx.x / FT_NC, nclusters = gridDim.x / FT_NC;
 
   if (tid == 0) {
-    // a ring slot is refilled by multicasts from all 8 CTAs, so it is free only when all 8 MMA issuers released it
-    for (int s = 0; s < p.nst; ++s) {
-#ifndef ODEVIO_FT_MULTICAST
-#define ODEVIO_FT_MULTICAST 1
-#endif
-      mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ODEVIO_FT_MULTICAST ? FT_NC : 1); mbar_init(&ready_bar[s], FT_SPLIT_WARPS);
-    }
+    for (int i = 0; i < FT_RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 1); }
+    for (int i = 0; i < FT_OP_STAGES; ++i) { mbar_init(&op_ready[i], 1); mbar_init(&op_empty[i], 1); }
     mbar_init(&accum_bar, 1);
     fence_barrier_init();
   }
@@ -149,7 +148,10 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
   const uint32_t tmem_d = tmem_slot;
 
   float* xa_cluster = p.xa + static_cast<size_t>(cluster_id) * 2 * p.xa_buf_floats;
-  uint32_t ring_stage = 0, ring_phase = 0;       // producer / MMA thread keep identical copies
+  uint32_t g0 = 0;                // chunks issued so far (all roles count identically): chunk g uses raw stage
+                                  // g % RAW, operand stage g % OP, barrier parity (g / stages) & 1
+  const uint32_t nraw = static_cast<uint32_t>(p.nraw);
+  unsigned char* const op_base = smem + static_cast<size_t>(nraw) * p.raw_stage_bytes;
   uint32_t accum_phase = 0;
 
   for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
@@ -184,51 +186,53 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
       float* nx = xa_cluster + static_cast<size_t>((l + 1) & 1) * p.xa_buf_floats;
       const uint32_t a_bytes = FT_ROWS * FT_KCH * 4, w_bytes = static_cast<uint32_t>(Nc) * FT_KCH * 4;
 
-      if (warp == FT_WARP_TMA && lane == 0) {
-        // ===== TMA producer: ONE fp32 copy of the A chunk (multicast) and of the weight chunk per stage
+      if (warp == FT_WARP_TMA) {
+        // ===== TMA producer: ONE fp32 copy of the A chunk and of the weight chunk per raw stage.  Whole warp,
+        // warp-uniform operands, one elected lane issues (a lone active lane costs an R2UR waterfall per copy).
         const float* wsrc = p.Wp[l] + static_cast<size_t>(crank) * Nc * K;
         for (int ch = 0; ch < nch; ++ch) {
-          mbar_wait(&empty_bar[ring_stage], ring_phase ^ 1u);
-          unsigned char* dst = smem + static_cast<size_t>(ring_stage) * p.stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[ring_stage], a_bytes + w_bytes);
-          // the A chunk is common to the cluster: every CTA fetches 1/8 of it (two 8-row groups) and
-          // multicasts it to all 8 -> L2 is read once per cluster instead of 8 times
-          const uint32_t a_sl = a_bytes / FT_NC;
-          const size_t a_src = static_cast<size_t>(ch) * FT_ROWS * FT_KCH + static_cast<size_t>(crank) * (a_sl / 4);
-#if ODEVIO_FT_MULTICAST
-          tma_load_1d_multicast(dst + crank * a_sl, a_src_buf + a_src, a_sl, &full_bar[ring_stage], 0xff);
-#else
-          (void)a_sl; (void)a_src;
-          tma_load_1d(dst, a_src_buf + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &full_bar[ring_stage]);
-#endif
-          tma_load_1d(dst + 2 * a_bytes, wsrc + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &full_bar[ring_stage]);
-          if (++ring_stage == static_cast<uint32_t>(p.nst)) { ring_stage = 0; ring_phase ^= 1u; }
+          const uint32_t g = g0 + ch, rs = g % nraw, rph = (g / nraw) & 1u;
+          mbar_wait(&raw_empty[rs], rph ^ 1u);
+          unsigned char* dst = smem + static_cast<size_t>(rs) * p.raw_stage_bytes;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&raw_full[rs], a_bytes + w_bytes);
+            tma_load_1d(dst, a_src_buf + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &raw_full[rs]);
+            tma_load_1d(dst + a_bytes, wsrc + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &raw_full[rs]);
+          }
+          __syncwarp();
         }
       } else if (warp >= FT_WARP_SPLIT && warp < FT_WARP_TMA) {
-        // ===== splitter: x -> (TF32-exact high part in place, exact residual next to it)
-        const int st = tid - 32 * FT_WARP_SPLIT;                     // 0 .. 127
+        // ===== splitter: raw fp32 chunk -> operand stage (TF32-exact high part | exact residual).  Every warp
+        // owns every 4th chunk by itself, so four chunks are in the split stage at once: one chunk costs
+        // ~1 k clk of latency (two barrier waits, LDS -> STS, fence.proxy.async), which bounded the kernel
+        // when all four warps worked on the same chunk.
+        const int sw = warp - FT_WARP_SPLIT;
         const int a_vec = FT_ROWS * FT_KCH / 4, w_vec = Nc * FT_KCH / 4;
-        for (int ch = 0; ch < nch; ++ch) {
-          mbar_wait(&full_bar[ring_stage], ring_phase);
-          unsigned char* base = smem + static_cast<size_t>(ring_stage) * p.stage_bytes;
-          float4* ahi = reinterpret_cast<float4*>(base); float4* alo = reinterpret_cast<float4*>(base + a_bytes);
-          float4* whi = reinterpret_cast<float4*>(base + 2 * a_bytes); float4* wlo = reinterpret_cast<float4*>(base + 2 * a_bytes + w_bytes);
-#pragma unroll 4
-          for (int e = st; e < a_vec; e += 32 * FT_SPLIT_WARPS) {
-            const float4 x = ahi[e];
+        for (int ch = sw; ch < nch; ch += FT_SPLIT_WARPS) {
+          const uint32_t g = g0 + ch, rs = g % nraw, rph = (g / nraw) & 1u;
+          const uint32_t os = g % FT_OP_STAGES, oph = (g / FT_OP_STAGES) & 1u;
+          mbar_wait(&raw_full[rs], rph);
+          mbar_wait(&op_empty[os], oph ^ 1u);
+          const unsigned char* raw = smem + static_cast<size_t>(rs) * p.raw_stage_bytes;
+          unsigned char* ob = op_base + static_cast<size_t>(os) * p.op_stage_bytes;
+          const float4* ra = reinterpret_cast<const float4*>(raw); const float4* rw = reinterpret_cast<const float4*>(raw + a_bytes);
+          float4* ahi = reinterpret_cast<float4*>(ob); float4* alo = reinterpret_cast<float4*>(ob + a_bytes);
+          float4* whi = reinterpret_cast<float4*>(ob + 2 * a_bytes); float4* wlo = reinterpret_cast<float4*>(ob + 2 * a_bytes + w_bytes);
+#pragma unroll 8
+          for (int e = lane; e < a_vec; e += 32) {
+            const float4 x = ra[e];
             const float4 h = make_float4(ft_hi(x.x), ft_hi(x.y), ft_hi(x.z), ft_hi(x.w));
             ahi[e] = h; alo[e] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
           }
-#pragma unroll 2
-          for (int e = st; e < w_vec; e += 32 * FT_SPLIT_WARPS) {
-            const float4 x = whi[e];
+#pragma unroll 4
+          for (int e = lane; e < w_vec; e += 32) {
+            const float4 x = rw[e];
             const float4 h = make_float4(ft_hi(x.x), ft_hi(x.y), ft_hi(x.z), ft_hi(x.w));
             whi[e] = h; wlo[e] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core (async proxy)
           __syncwarp();
-          if (lane == 0) mbar_arrive(&ready_bar[ring_stage]);
-          if (++ring_stage == static_cast<uint32_t>(p.nst)) { ring_stage = 0; ring_phase ^= 1u; }
+          if (lane == 0) { mbar_arrive(&op_ready[os]); mbar_arrive(&raw_empty[rs]); }
         }
       } else if (warp == FT_WARP_MMA) {
         // ===== MMA issuer: D[128 x Nc] = sum_k A[128 x k] W[Nc x k]^T, 3xTF32.  The WHOLE warp runs the loop
@@ -244,10 +248,11 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
         uint32_t corr_started = 0;
         for (int ch = 0; ch < nch; ++ch) {
-          mbar_wait(&ready_bar[ring_stage], ring_phase);
+          const uint32_t g = g0 + ch, os = g % FT_OP_STAGES, oph = (g / FT_OP_STAGES) & 1u;
+          mbar_wait(&op_ready[os], oph);
           if (ch == 0 && lane == 0) FT_STAMP(8 + l * 8 + 0);          // first chunk landed and split
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t base = smem_u32(smem + static_cast<size_t>(ring_stage) * p.stage_bytes);
+          const uint32_t base = smem_u32(op_base + static_cast<size_t>(os) * p.op_stage_bytes);
           const uint32_t sa_hi = base, sa_lo = base + a_bytes, sw_hi = base + 2 * a_bytes, sw_lo = sw_hi + w_bytes;
           const int seg = ch * nseg / nch;
           const bool seg_first = ch == (seg * nch + nseg - 1) / nseg;
@@ -256,26 +261,14 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
 #pragma unroll
             for (int ks = 0; ks < FT_KCH / 8; ++ks) {
               const uint32_t o = ks * 256;
-#ifndef ODEVIO_FT_DBG_MMA
-#define ODEVIO_FT_DBG_MMA 3
-#endif
-#if ODEVIO_FT_DBG_MMA >= 1
               ft_mma(d_main, ft_desc(sa_hi + o), ft_desc(sw_hi + o), idesc, (seg_first && ks == 0) ? 0u : 1u);
-#endif
-#if ODEVIO_FT_DBG_MMA >= 3
               ft_mma(d_corr, ft_desc(sa_lo + o), ft_desc(sw_hi + o), idesc, (corr_started | ks) ? 1u : 0u);
               ft_mma(d_corr, ft_desc(sa_hi + o), ft_desc(sw_lo + o), idesc, 1);
-#endif
             }
-#if ODEVIO_FT_MULTICAST
-            ft_commit_multicast(&empty_bar[ring_stage], 0xff);
-#else
-            ft_commit(&empty_bar[ring_stage]);
-#endif
+            ft_commit(&op_empty[os]);
           }
           corr_started = 1;
           __syncwarp();
-          if (++ring_stage == static_cast<uint32_t>(p.nst)) { ring_stage = 0; ring_phase ^= 1u; }
         }
         if (elect_one()) ft_commit(&accum_bar);
         __syncwarp();
@@ -336,6 +329,7 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
         if (tid == 0) FT_STAMP(8 + l * 8 + 3);           // epilogue done
       }
       accum_phase ^= 1u;
+      g0 += static_cast<uint32_t>(nch);
       __syncwarp();
       // every CTA's slice of the next operand is written (and this CTA's accumulator drained)
       cluster_sync_all();
@@ -352,7 +346,7 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
   }
 }
 
-// W [N][K] (PyTorch) -> fp32 operand image [c][K/32][Nc/8][8 kq][8 n][4 k]
+// W [N][K] (PyTorch) -> fp32 operand image [c][K/KCH][Nc/8][KCH/4 kq][8 n][4 k]
 __global__ void ft_pack_weight_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ dst) {
   const int Nc = N / FT_NC;
   const size_t total = static_cast<size_t>(N) * K;
@@ -361,15 +355,16 @@ __global__ void ft_pack_weight_kernel(const float* __restrict__ W, int N, int K,
     const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<size_t>(n) * K);
     const int c = n / Nc, nl = n - c * Nc;
     const size_t o = static_cast<size_t>(c) * Nc * K +
-                     ((static_cast<size_t>(k >> 5) * (Nc >> 3) + (nl >> 3)) * 8 + ((k & 31) >> 2)) * 32 + (nl & 7) * 4 + (k & 3);
+                     ((static_cast<size_t>(k / FT_KCH) * (Nc >> 3) + (nl >> 3)) * (FT_KCH / 4) + ((k % FT_KCH) >> 2)) * 32 +
+                     (nl & 7) * 4 + (k & 3);
     dst[o] = W[i];
   }
 }
 
 struct FtPlan {
-  int NL, ntiles, nclusters, nst, kmax, ncmax;
+  int NL, ntiles, nclusters, kmax, ncmax, nraw;
   size_t off_w[FT_MAX_LAYERS], off_xa, xa_buf_floats, total_bytes, smem_bytes;
-  uint32_t stage_bytes;
+  uint32_t raw_stage_bytes, op_stage_bytes;
   int K[FT_MAX_LAYERS], N[FT_MAX_LAYERS];
 };
 
@@ -399,11 +394,15 @@ int ft_plan(int M, int D, int H, int n_hidden, FtPlan& pl) {
   pl.xa_buf_floats = static_cast<size_t>(FT_ROWS) * pl.kmax;
   pl.off_xa = take(static_cast<size_t>(pl.nclusters) * 2 * pl.xa_buf_floats);
   pl.total_bytes = off * sizeof(float);
-  pl.stage_bytes = 2u * (FT_ROWS + pl.ncmax) * FT_KCH * 4u;
-  pl.nst = static_cast<int>((220u * 1024u) / pl.stage_bytes);
-  if (pl.nst > FT_MAX_STAGES) pl.nst = FT_MAX_STAGES;
-  if (pl.nst < 2) return ODEVIO_E_SHAPE;
-  pl.smem_bytes = static_cast<size_t>(pl.nst) * pl.stage_bytes + 1024;
+  pl.raw_stage_bytes = static_cast<uint32_t>(FT_ROWS + pl.ncmax) * FT_KCH * 4u;
+  pl.op_stage_bytes = 2u * pl.raw_stage_bytes;
+  pl.nraw = FT_RAW_STAGES;
+  pl.smem_bytes = static_cast<size_t>(pl.nraw) * pl.raw_stage_bytes + static_cast<size_t>(FT_OP_STAGES) * pl.op_stage_bytes + 1024;
+  if (pl.smem_bytes > 227u * 1024u) {
+    pl.nraw = 4;
+    pl.smem_bytes = static_cast<size_t>(pl.nraw) * pl.raw_stage_bytes + static_cast<size_t>(FT_OP_STAGES) * pl.op_stage_bytes + 1024;
+  }
+  if (pl.smem_bytes > 227u * 1024u) return ODEVIO_E_SHAPE;
   return 0;
 }
 
@@ -448,7 +447,7 @@ int32_t odevio_odefunc_forward(int32_t M, int32_t D, int32_t H, int32_t n_hidden
     p.Wp[l] = ws + pl.off_w[l]; p.bias[l] = biases[l];
   }
   p.x = x; p.out = out; p.xa = ws + pl.off_xa; p.xa_buf_floats = pl.xa_buf_floats;
-  p.ntiles = pl.ntiles; p.nst = pl.nst; p.stage_bytes = pl.stage_bytes;
+  p.ntiles = pl.ntiles; p.nraw = pl.nraw; p.raw_stage_bytes = pl.raw_stage_bytes; p.op_stage_bytes = pl.op_stage_bytes;
   cudaError_t e = cudaFuncSetAttribute(odefunc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(pl.smem_bytes));
   if (e != cudaSuccess) return static_cast<int32_t>(e);
