@@ -37,8 +37,12 @@ namespace {
 #endif
 
 constexpr int FT_ROWS = 128;          // rows per tile = MMA M
-constexpr int FT_NC = 8;              // CTAs per cluster = column slices
-constexpr int FT_KCH = 16;            // k per ring stage (two 8-wide tf32 k-steps)
+// cluster size NC (column slices per 128-row tile) and k per ring stage KCH are template parameters:
+//   <8, 16>  few tiles (B ~ 1024): 8 CTAs per tile keep 128 SMs busy, N = 64 / 96 per MMA
+//   <4, 16>  many tiles: N = 128 / 192 / 256 per MMA amortises the ~125 clk A-operand read of every MMA
+// FT_SPLIT: true = one fp32 operand copy crosses L2, hi/lo produced in shared memory by the splitter warps;
+//           false = the epilogues write hi and lo images (twice the bytes, no split stage: wide slices do not
+//           leave shared memory for a separate operand ring)
 constexpr int FT_RAW_STAGES = 8;      // fp32 chunks in flight (bulk TMA -> splitter); 4 when shared memory is short
 constexpr int FT_OP_STAGES = 4;       // split hi/lo operand stages (splitter -> tensor core) == splitter warps:
                                       // chunk g uses raw stage g % nraw and operand stage g % 4, both always served by
@@ -53,7 +57,8 @@ constexpr int FT_THREADS = 32 * (FT_WARP_MMA + 1);
 struct FtParams {
   int M, NL, act;
   int K[FT_MAX_LAYERS], N[FT_MAX_LAYERS];      // layer shapes (N % 256 == 0 or N/8 in {32, 64, 96, 128}, K % 32 == 0)
-  const float* Wp[FT_MAX_LAYERS];              // fp32, packed [c][K/32][Nc/8][8][8][4]
+  const float* Wp[FT_MAX_LAYERS];              // packed [c][K/KCH][Nc/8][KCH/4][8][4]: fp32 (FT_SPLIT) or TF32-exact high part
+  const float* Wlo[FT_MAX_LAYERS];             // residual (only !FT_SPLIT)
   const float* bias[FT_MAX_LAYERS];
   const float* x;                              // [M][K[0]]
   float* out;                                  // [M][N[NL-1]]
@@ -64,10 +69,11 @@ struct FtParams {
   uint32_t op_stage_bytes;                     // 2 * raw: hi and lo images
 };
 
+template <int KCH>
 __device__ __forceinline__ uint64_t ft_desc(uint32_t saddr) {
   // K-major, no swizzle: LBO (k core matrices) = 128 B, SBO (8-row groups) = (KCH / 4) * 128 B; version 1
   return static_cast<uint64_t>((saddr >> 4) & 0x3fffu) | (static_cast<uint64_t>(128u >> 4) << 16) |
-         (static_cast<uint64_t>((FT_KCH / 4 * 128u) >> 4) << 32) | (1ull << 46);
+         (static_cast<uint64_t>((KCH / 4 * 128u) >> 4) << 32) | (1ull << 46);
 }
 __device__ __forceinline__ void ft_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -100,23 +106,37 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // accumulators for the hi*hi products (K segments); one more holds the cross terms: (nseg + 1) * Nc <= 512
-__device__ __forceinline__ int ft_nseg(int Nc) { const int n = 512 / Nc - 1; return n > 4 ? 4 : n; }
+__device__ __forceinline__ int ft_nseg(int Nc) { const int n = 512 / Nc - 1; return n > 4 ? 4 : (n < 1 ? 1 : n); }
 __device__ __forceinline__ float ft_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // float offset of (row r, feature k) in a 128-row operand buffer: [k/KCH][r/8][(k%KCH)/4][r%8][k%4]
+template <int KCH>
 __device__ __forceinline__ size_t xa_offset(int r, int k) {
-  return ((static_cast<size_t>(k / FT_KCH) * 16 + (r >> 3)) * (FT_KCH / 4) + ((k % FT_KCH) >> 2)) * 32 + (r & 7) * 4 + (k & 3);
+  return ((static_cast<size_t>(k / KCH) * 16 + (r >> 3)) * (KCH / 4) + ((k % KCH) >> 2)) * 32 + (r & 7) * 4 + (k & 3);
 }
 
 // thread = row: 32 consecutive features (one k-chunk) -> fp32 operand image (the hi / lo parts are
 // produced in shared memory by the splitter warps: one copy crosses L2 and the SM boundary, not two)
+template <int KCH>
 __device__ __forceinline__ void store_chunk(float* dst, int r, int k0, const float (&v)[32]) {
 #pragma unroll
   for (int q = 0; q < 8; ++q)
-    *reinterpret_cast<float4*>(dst + xa_offset(r, k0 + 4 * q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    *reinterpret_cast<float4*>(dst + xa_offset<KCH>(r, k0 + 4 * q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
-__global__ void __cluster_dims__(FT_NC, 1, 1) __launch_bounds__(FT_THREADS, 1)
+template <int KCH>
+__device__ __forceinline__ void store_chunk_hilo(float* hi, float* lo, int r, int k0, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const size_t o = xa_offset<KCH>(r, k0 + 4 * q);
+    const float4 h = make_float4(ft_hi(v[4 * q]), ft_hi(v[4 * q + 1]), ft_hi(v[4 * q + 2]), ft_hi(v[4 * q + 3]));
+    *reinterpret_cast<float4*>(hi + o) = h;
+    *reinterpret_cast<float4*>(lo + o) = make_float4(v[4 * q] - h.x, v[4 * q + 1] - h.y, v[4 * q + 2] - h.z, v[4 * q + 3] - h.w);
+  }
+}
+
+template <int FT_NC, int FT_KCH, bool FT_SPLIT>
+__global__ void __launch_bounds__(FT_THREADS, 1)
 odefunc_tc_kernel(const __grid_constant__ FtParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t raw_full[FT_RAW_STAGES];      // bulk TMA -> splitter
@@ -147,7 +167,7 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_slot;
 
-  float* xa_cluster = p.xa + static_cast<size_t>(cluster_id) * 2 * p.xa_buf_floats;
+  float* xa_cluster = p.xa + static_cast<size_t>(cluster_id) * 4 * p.xa_buf_floats;   // [ping-pong][hi|lo]
   uint32_t g0 = 0;                // chunks issued so far (all roles count identically): chunk g uses raw stage
                                   // g % RAW, operand stage g % OP, barrier parity (g / stages) & 1
   const uint32_t nraw = static_cast<uint32_t>(p.nraw);
@@ -171,7 +191,8 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] = 0.f;
         }
-        store_chunk(dst0, r, k0, v);
+        if (FT_SPLIT) store_chunk<FT_KCH>(dst0, r, k0, v);
+        else store_chunk_hilo<FT_KCH>(dst0, dst0 + p.xa_buf_floats, r, k0, v);
       }
       asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy stores -> visible to the bulk-copy (async) proxy
     }
@@ -182,8 +203,8 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
 
     for (int l = 0; l < p.NL; ++l) {
       const int K = p.K[l], N = p.N[l], Nc = N / FT_NC, nch = K / FT_KCH;
-      const float* a_src_buf = xa_cluster + static_cast<size_t>(l & 1) * p.xa_buf_floats;
-      float* nx = xa_cluster + static_cast<size_t>((l + 1) & 1) * p.xa_buf_floats;
+      const float* a_src_buf = xa_cluster + static_cast<size_t>(l & 1) * 2 * p.xa_buf_floats;
+      float* nx = xa_cluster + static_cast<size_t>((l + 1) & 1) * 2 * p.xa_buf_floats;
       const uint32_t a_bytes = FT_ROWS * FT_KCH * 4, w_bytes = static_cast<uint32_t>(Nc) * FT_KCH * 4;
 
       if (warp == FT_WARP_TMA) {
@@ -195,13 +216,22 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
           mbar_wait(&raw_empty[rs], rph ^ 1u);
           unsigned char* dst = smem + static_cast<size_t>(rs) * p.raw_stage_bytes;
           if (elect_one()) {
-            mbar_arrive_expect_tx(&raw_full[rs], a_bytes + w_bytes);
-            tma_load_1d(dst, a_src_buf + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &raw_full[rs]);
-            tma_load_1d(dst + a_bytes, wsrc + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &raw_full[rs]);
+            if (FT_SPLIT) {
+              mbar_arrive_expect_tx(&raw_full[rs], a_bytes + w_bytes);
+              tma_load_1d(dst, a_src_buf + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &raw_full[rs]);
+              tma_load_1d(dst + a_bytes, wsrc + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &raw_full[rs]);
+            } else {       // stage = [A_hi | A_lo | W_hi | W_lo], consumed by the MMA issuer directly
+              const float* wlo = p.Wlo[l] + static_cast<size_t>(crank) * Nc * K;
+              mbar_arrive_expect_tx(&raw_full[rs], 2 * (a_bytes + w_bytes));
+              tma_load_1d(dst, a_src_buf + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &raw_full[rs]);
+              tma_load_1d(dst + a_bytes, a_src_buf + p.xa_buf_floats + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &raw_full[rs]);
+              tma_load_1d(dst + 2 * a_bytes, wsrc + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &raw_full[rs]);
+              tma_load_1d(dst + 2 * a_bytes + w_bytes, wlo + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &raw_full[rs]);
+            }
           }
           __syncwarp();
         }
-      } else if (warp >= FT_WARP_SPLIT && warp < FT_WARP_TMA) {
+      } else if (FT_SPLIT && warp >= FT_WARP_SPLIT && warp < FT_WARP_TMA) {
         // ===== splitter: raw fp32 chunk -> operand stage (TF32-exact high part | exact residual).  Every warp
         // owns every 4th chunk by itself, so four chunks are in the split stage at once: one chunk costs
         // ~1 k clk of latency (two barrier waits, LDS -> STS, fence.proxy.async), which bounded the kernel
@@ -248,11 +278,15 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
         uint32_t corr_started = 0;
         for (int ch = 0; ch < nch; ++ch) {
-          const uint32_t g = g0 + ch, os = g % FT_OP_STAGES, oph = (g / FT_OP_STAGES) & 1u;
-          mbar_wait(&op_ready[os], oph);
+          const uint32_t g = g0 + ch;
+          const uint32_t os = FT_SPLIT ? g % FT_OP_STAGES : g % nraw, oph = FT_SPLIT ? (g / FT_OP_STAGES) & 1u : (g / nraw) & 1u;
+          uint64_t* wait_bar = FT_SPLIT ? &op_ready[os] : &raw_full[os];
+          uint64_t* free_bar = FT_SPLIT ? &op_empty[os] : &raw_empty[os];
+          mbar_wait(wait_bar, oph);
           if (ch == 0 && lane == 0) FT_STAMP(8 + l * 8 + 0);          // first chunk landed and split
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t base = smem_u32(op_base + static_cast<size_t>(os) * p.op_stage_bytes);
+          const uint32_t base = FT_SPLIT ? smem_u32(op_base + static_cast<size_t>(os) * p.op_stage_bytes)
+                                         : smem_u32(smem + static_cast<size_t>(os) * p.raw_stage_bytes);
           const uint32_t sa_hi = base, sa_lo = base + a_bytes, sw_hi = base + 2 * a_bytes, sw_lo = sw_hi + w_bytes;
           const int seg = ch * nseg / nch;
           const bool seg_first = ch == (seg * nch + nseg - 1) / nseg;
@@ -261,11 +295,11 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
 #pragma unroll
             for (int ks = 0; ks < FT_KCH / 8; ++ks) {
               const uint32_t o = ks * 256;
-              ft_mma(d_main, ft_desc(sa_hi + o), ft_desc(sw_hi + o), idesc, (seg_first && ks == 0) ? 0u : 1u);
-              ft_mma(d_corr, ft_desc(sa_lo + o), ft_desc(sw_hi + o), idesc, (corr_started | ks) ? 1u : 0u);
-              ft_mma(d_corr, ft_desc(sa_hi + o), ft_desc(sw_lo + o), idesc, 1);
+              ft_mma(d_main, ft_desc<FT_KCH>(sa_hi + o), ft_desc<FT_KCH>(sw_hi + o), idesc, (seg_first && ks == 0) ? 0u : 1u);
+              ft_mma(d_corr, ft_desc<FT_KCH>(sa_lo + o), ft_desc<FT_KCH>(sw_hi + o), idesc, (corr_started | ks) ? 1u : 0u);
+              ft_mma(d_corr, ft_desc<FT_KCH>(sa_hi + o), ft_desc<FT_KCH>(sw_lo + o), idesc, 1);
             }
-            ft_commit(&op_empty[os]);
+            ft_commit(free_bar);
           }
           corr_started = 1;
           __syncwarp();
@@ -321,7 +355,8 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
               for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
           } else {
-            store_chunk(nx, r, n0, v);
+            if (FT_SPLIT) store_chunk<FT_KCH>(nx, r, n0, v);
+            else store_chunk_hilo<FT_KCH>(nx, nx + p.xa_buf_floats, r, n0, v);
           }
         }
         asm volatile("fence.proxy.async;" ::: "memory");
@@ -347,63 +382,104 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
 }
 
 // W [N][K] (PyTorch) -> fp32 operand image [c][K/KCH][Nc/8][KCH/4 kq][8 n][4 k]
-__global__ void ft_pack_weight_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ dst) {
-  const int Nc = N / FT_NC;
+__global__ void ft_pack_weight_kernel(const float* __restrict__ W, int N, int K, int NC, int KCH, float* __restrict__ dst,
+                                      float* __restrict__ dst_lo) {
+  const int Nc = N / NC;
   const size_t total = static_cast<size_t>(N) * K;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<size_t>(n) * K);
     const int c = n / Nc, nl = n - c * Nc;
     const size_t o = static_cast<size_t>(c) * Nc * K +
-                     ((static_cast<size_t>(k / FT_KCH) * (Nc >> 3) + (nl >> 3)) * (FT_KCH / 4) + ((k % FT_KCH) >> 2)) * 32 +
+                     ((static_cast<size_t>(k / KCH) * (Nc >> 3) + (nl >> 3)) * (KCH / 4) + ((k % KCH) >> 2)) * 32 +
                      (nl & 7) * 4 + (k & 3);
-    dst[o] = W[i];
+    const float w = W[i];
+    if (dst_lo) { const float h = __uint_as_float(__float_as_uint(w) & 0xffffe000u); dst[o] = h; dst_lo[o] = w - h; }
+    else dst[o] = w;
   }
 }
 
 struct FtPlan {
-  int NL, ntiles, nclusters, kmax, ncmax, nraw;
-  size_t off_w[FT_MAX_LAYERS], off_xa, xa_buf_floats, total_bytes, smem_bytes;
+  int NL, ntiles, nclusters, kmax, ncmax, nraw, NC, KCH, split;
+  size_t off_w[FT_MAX_LAYERS], off_wlo[FT_MAX_LAYERS], off_xa, xa_buf_floats, total_bytes, smem_bytes;
   uint32_t raw_stage_bytes, op_stage_bytes;
   int K[FT_MAX_LAYERS], N[FT_MAX_LAYERS];
 };
 
 int ft_plan(int M, int D, int H, int n_hidden, FtPlan& pl) {
   if (M <= 0 || n_hidden < 1 || n_hidden + 1 > FT_MAX_LAYERS) return ODEVIO_E_SHAPE;
-  // column slices of 32 .. 128 (TMEM 128 columns, tcgen05.ld in 32-column chunks), k-chunks of 32
-  auto ok = [](int n) { const int nc = n / FT_NC; return n % FT_NC == 0 && nc % 32 == 0 && nc >= 32 && nc <= 128; };
-  if (!ok(D) || !ok(H)) return ODEVIO_E_SHAPE;
-  pl.NL = n_hidden + 1;
-  pl.kmax = D > H ? D : H;
-  pl.ncmax = pl.kmax / FT_NC;
-  size_t off = 0;
-  auto take = [&](size_t n) { size_t o = off; off = (off + n + 63) / 64 * 64; return o; };
-  for (int l = 0; l < pl.NL; ++l) {
-    pl.K[l] = l == 0 ? D : H;
-    pl.N[l] = l == pl.NL - 1 ? D : H;
-    pl.off_w[l] = take(static_cast<size_t>(pl.K[l]) * pl.N[l]);
-  }
   int dev = 0, nsm = 148;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) {
     cudaGetLastError();
     nsm = 148;
   }
   pl.ntiles = (M + FT_ROWS - 1) / FT_ROWS;
-  pl.nclusters = nsm / FT_NC;
+  // column slices of 32 .. 256 (one MMA, <= 512 TMEM columns with two accumulators), tcgen05.ld in 32-column chunks
+  auto ok = [](int n, int nc_) { const int nc = n / nc_; return n % nc_ == 0 && nc % 32 == 0 && nc >= 32 && nc <= 256; };
+  // few tiles: 8 CTAs per tile (latency, SM count); many tiles: 4 CTAs per tile (wider MMAs, fewer A re-reads)
+  const bool wide = pl.ntiles > nsm / 8 && ok(D, 4) && ok(H, 4);
+  pl.NC = wide ? 4 : 8;
+  pl.KCH = 16;
+  pl.split = wide ? 0 : 1;
+  if (!ok(D, pl.NC) || !ok(H, pl.NC) || D / pl.NC > 128 * (wide ? 2 : 1) || H / pl.NC > 128 * (wide ? 2 : 1)) return ODEVIO_E_SHAPE;
+  pl.NL = n_hidden + 1;
+  pl.kmax = D > H ? D : H;
+  pl.ncmax = pl.kmax / pl.NC;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = (off + n + 63) / 64 * 64; return o; };
+  for (int l = 0; l < pl.NL; ++l) {
+    pl.K[l] = l == 0 ? D : H;
+    pl.N[l] = l == pl.NL - 1 ? D : H;
+    pl.off_w[l] = take(static_cast<size_t>(pl.K[l]) * pl.N[l]);
+    pl.off_wlo[l] = take(static_cast<size_t>(pl.K[l]) * pl.N[l]);
+  }
+  pl.nclusters = nsm / pl.NC;
   if (pl.nclusters > pl.ntiles) pl.nclusters = pl.ntiles;
   pl.xa_buf_floats = static_cast<size_t>(FT_ROWS) * pl.kmax;
-  pl.off_xa = take(static_cast<size_t>(pl.nclusters) * 2 * pl.xa_buf_floats);
+  pl.off_xa = take(static_cast<size_t>(pl.nclusters) * 4 * pl.xa_buf_floats);
   pl.total_bytes = off * sizeof(float);
-  pl.raw_stage_bytes = static_cast<uint32_t>(FT_ROWS + pl.ncmax) * FT_KCH * 4u;
-  pl.op_stage_bytes = 2u * pl.raw_stage_bytes;
-  pl.nraw = FT_RAW_STAGES;
-  pl.smem_bytes = static_cast<size_t>(pl.nraw) * pl.raw_stage_bytes + static_cast<size_t>(FT_OP_STAGES) * pl.op_stage_bytes + 1024;
-  if (pl.smem_bytes > 227u * 1024u) {
-    pl.nraw = 4;
+  if (pl.split) {
+    pl.raw_stage_bytes = static_cast<uint32_t>(FT_ROWS + pl.ncmax) * pl.KCH * 4u;
+    pl.op_stage_bytes = 2u * pl.raw_stage_bytes;
+    pl.nraw = FT_RAW_STAGES;
     pl.smem_bytes = static_cast<size_t>(pl.nraw) * pl.raw_stage_bytes + static_cast<size_t>(FT_OP_STAGES) * pl.op_stage_bytes + 1024;
+    if (pl.smem_bytes > 227u * 1024u) {
+      pl.nraw = 4;
+      pl.smem_bytes = static_cast<size_t>(pl.nraw) * pl.raw_stage_bytes + static_cast<size_t>(FT_OP_STAGES) * pl.op_stage_bytes + 1024;
+    }
+  } else {
+    pl.raw_stage_bytes = 2u * static_cast<uint32_t>(FT_ROWS + pl.ncmax) * pl.KCH * 4u;      // hi + lo images
+    pl.op_stage_bytes = 0;
+    pl.nraw = static_cast<int>((224u * 1024u) / pl.raw_stage_bytes);
+    if (pl.nraw > FT_RAW_STAGES) pl.nraw = FT_RAW_STAGES;
+    pl.smem_bytes = static_cast<size_t>(pl.nraw) * pl.raw_stage_bytes + 1024;
+    if (pl.nraw < 2) return ODEVIO_E_SHAPE;
   }
   if (pl.smem_bytes > 227u * 1024u) return ODEVIO_E_SHAPE;
   return 0;
+}
+
+template <int NC, int KCH, bool SPLIT>
+cudaError_t ft_launch(const FtParams& p, FtPlan& pl, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(odefunc_tc_kernel<NC, KCH, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(pl.smem_bytes));
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.blockDim = dim3(FT_THREADS); lc.dynamicSmemBytes = pl.smem_bytes; lc.stream = stream;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = NC; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  lc.attrs = &at; lc.numAttrs = 1;
+  // clusters must sit inside one GPC: launch no more clusters than can be co-resident
+  lc.gridDim = dim3(pl.nclusters * NC);
+  int maxc = 0;
+  if (cudaOccupancyMaxActiveClusters(&maxc, odefunc_tc_kernel<NC, KCH, SPLIT>, &lc) == cudaSuccess && maxc > 0) {
+    if (pl.nclusters > maxc) pl.nclusters = maxc;
+  } else {
+    cudaGetLastError();
+  }
+  lc.gridDim = dim3(pl.nclusters * NC);
+  return cudaLaunchKernelEx(&lc, odefunc_tc_kernel<NC, KCH, SPLIT>, p);
 }
 
 }  // namespace
@@ -441,32 +517,16 @@ int32_t odevio_odefunc_forward(int32_t M, int32_t D, int32_t H, int32_t n_hidden
   for (int l = 0; l < pl.NL; ++l) {
     if (!weights[l] || !biases[l]) return ODEVIO_E_NULL;
     p.K[l] = pl.K[l]; p.N[l] = pl.N[l];
-    ft_pack_weight_kernel<<<296, 256, 0, stream>>>(weights[l], pl.N[l], pl.K[l], ws + pl.off_w[l]);
+    ft_pack_weight_kernel<<<296, 256, 0, stream>>>(weights[l], pl.N[l], pl.K[l], pl.NC, pl.KCH, ws + pl.off_w[l],
+                                                   pl.split ? nullptr : ws + pl.off_wlo[l]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int32_t>(e);
-    p.Wp[l] = ws + pl.off_w[l]; p.bias[l] = biases[l];
+    p.Wp[l] = ws + pl.off_w[l]; p.Wlo[l] = ws + pl.off_wlo[l]; p.bias[l] = biases[l];
   }
   p.x = x; p.out = out; p.xa = ws + pl.off_xa; p.xa_buf_floats = pl.xa_buf_floats;
   p.ntiles = pl.ntiles; p.nraw = pl.nraw; p.raw_stage_bytes = pl.raw_stage_bytes; p.op_stage_bytes = pl.op_stage_bytes;
-  cudaError_t e = cudaFuncSetAttribute(odefunc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(pl.smem_bytes));
+  cudaError_t e = pl.NC == 8 ? ft_launch<8, 16, true>(p, pl, stream) : ft_launch<4, 16, false>(p, pl, stream);
   if (e != cudaSuccess) return static_cast<int32_t>(e);
-  {
-    // clusters of 8 must sit inside one GPC: launch no more clusters than can be co-resident
-    cudaLaunchConfig_t lc;
-    memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3(pl.nclusters * FT_NC); lc.blockDim = dim3(FT_THREADS); lc.dynamicSmemBytes = pl.smem_bytes;
-    cudaLaunchAttribute at;
-    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = FT_NC; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-    lc.attrs = &at; lc.numAttrs = 1;
-    int maxc = 0;
-    if (cudaOccupancyMaxActiveClusters(&maxc, odefunc_tc_kernel, &lc) == cudaSuccess && maxc > 0) {
-      if (pl.nclusters > maxc) pl.nclusters = maxc;
-    } else {
-      cudaGetLastError();
-    }
-  }
-  odefunc_tc_kernel<<<pl.nclusters * FT_NC, FT_THREADS, pl.smem_bytes, stream>>>(p);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int32_t>(e);
 }
