@@ -286,6 +286,18 @@ ODEVIO_API int32_t odevio_odefunc_forward(int32_t M, int32_t D, int32_t H, int32
                                           void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Generic MLP evaluation on CUDA cores (fp32 FMA) for the module interfaces that are called
+ * directly and are not on a fused path: CDEFunc.forward (reference src/models/ODEFunc.py:81-84,
+ * the caller views the [M, Hc*C] result as [M, Hc, C]) and ODEFunc.forward for shapes the
+ * tensor-core kernel does not cover.  dims[n_linears + 1] and acts[n_linears] (ODEVIO_ACT_* or
+ * 4 = identity) are HOST arrays; weights[j] [dims[j+1], dims[j]] / biases[j] are HOST arrays of
+ * DEVICE pointers; x [M, dims[0]], out [M, dims[n_linears]].
+ */
+ODEVIO_API int32_t odevio_mlp_forward(int32_t M, int32_t n_linears, const int32_t* dims, const int32_t* acts,
+                                      const float* const* weights, const float* const* biases,
+                                      const float* x, float* out, void* stream);
+
+/*
  * Diagnostics (no reference counterpart): launch a dense FFMA loop on `blocks` CTAs of 512 threads
  * and report the FLOPs it performs in *flops_out (HOST); time it with events around the call to
  * obtain this GPU's fp32 FMA peak, the roofline denominator of ODEVIO_PRECISION_FP32.

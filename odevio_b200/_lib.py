@@ -122,6 +122,9 @@ def load():
     lib.odevio_odefunc_workspace_bytes.argtypes = [C.c_int32] * 4
     lib.odevio_odefunc_forward.restype = C.c_int32
     lib.odevio_odefunc_forward.argtypes = [C.c_int32] * 5 + [C.POINTER(_FP), C.POINTER(_FP), _FP, _FP, _FP, C.c_size_t, _FP]
+    lib.odevio_mlp_forward.restype = C.c_int32
+    lib.odevio_mlp_forward.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                       C.POINTER(_FP), C.POINTER(_FP), _FP, _FP, _FP]
     lib.odevio_microbench_ffma.restype = C.c_int32
     lib.odevio_microbench_ffma.argtypes = [C.c_int32, C.c_int32, _FP, C.POINTER(C.c_double), _FP]
     if lib.odevio_version() != ABI_VERSION:

@@ -57,6 +57,29 @@ def _vector_field_net(sizes, activation):
     return nn.Sequential(*layers)
 
 
+def _mlp_forward_kernel(net, x2, last_act):
+    """Evaluate an nn.Sequential of Linear/activation pairs with odevio_mlp_forward (CUDA cores)."""
+    lib = _lib.load()
+    lins = [m for m in net if isinstance(m, nn.Linear)]
+    acts = [m for m in net if not isinstance(m, nn.Linear)]
+    names = {nn.Tanh: 0, nn.ReLU: 1, nn.LeakyReLU: 2, nn.Softplus: 3}
+    act_ids = [names[type(a)] for a in acts]
+    assert len(act_ids) == len(lins) and act_ids[-1] == last_act
+    dims = [lins[0].in_features] + [l.out_features for l in lins]
+    keep = [(_f32c(l.weight.detach(), "weight"), _f32c(l.bias.detach(), "bias")) for l in lins]
+    out = torch.empty(x2.shape[0], dims[-1], dtype=torch.float32, device=x2.device)
+    n = len(lins)
+    with torch.cuda.device(x2.device):
+        rc = lib.odevio_mlp_forward(x2.shape[0], n, (C.c_int32 * (n + 1))(*dims), (C.c_int32 * n)(*act_ids),
+                                    (C.c_void_p * n)(*[t[0].data_ptr() for t in keep]),
+                                    (C.c_void_p * n)(*[t[1].data_ptr() for t in keep]),
+                                    _lib.dptr(x2), _lib.dptr(out),
+                                    C.c_void_p(torch.cuda.current_stream(x2.device).cuda_stream))
+    _lib.check(rc)
+    del keep
+    return out
+
+
 class ODEFunc(nn.Module):
     """Parameter container for the autonomous vector field
     f(t, x) = tanh(W_n a(... a(W_0 x + b_0) ...) + b_n)  (keys ``net.{0,2,..}.{weight,bias}``)."""
@@ -85,8 +108,8 @@ class ODEFunc(nn.Module):
         M = x2.shape[0]
         nbytes = lib.odevio_odefunc_workspace_bytes(M, self.feature_dim, self.hidden_dim, self.num_hidden_layers)
         if nbytes == 0:
-            raise _lib.OdevioError(f"ODEFunc.forward: unsupported shape for the tensor-core kernel "
-                                   f"(D={self.feature_dim}, H={self.hidden_dim}; need multiples of 256 up to 1024)")
+            # shapes outside the tensor-core kernel's tiling (D, H multiples of 256 up to 1024): CUDA-core kernel
+            return _mlp_forward_kernel(self.net, x2, 0).reshape(shape)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         out = torch.empty_like(x2)
         lins = self.linears()
@@ -117,7 +140,16 @@ class CDEFunc(nn.Module):
         return [m for m in self.net if isinstance(m, nn.Linear)]
 
     def forward(self, t, z):
-        return self.net(z).view(z.size(0), self.hidden_dim, self.feature_dim)
+        """g(t, z) -> [B, hidden, channels] for callers that evaluate the field directly
+        (ODEFunc.py:81-84); the fused CDE kernel never materialises this tensor.  Runs
+        ``odevio_mlp_forward``; no CPU / autograd path."""
+        _lib.load()
+        if not z.is_cuda:
+            raise _lib.OdevioError("CDEFunc.forward needs a CUDA tensor: odevio_b200 has no CPU path")
+        if torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise _lib.OdevioError("CDEFunc.forward is inference-only (the fused CDE backward is not built)")
+        out = _mlp_forward_kernel(self.net, _f32c(z.reshape(-1, self.hidden_dim), "z"), 0)
+        return out.view(z.size(0), self.hidden_dim, self.feature_dim)
 
 
 class FusionModule(nn.Module):

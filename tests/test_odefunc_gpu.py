@@ -36,10 +36,29 @@ def test_odefunc_tensor_core_matches_fp64(cuda_device, D, H, n, act, M):
     assert err <= 1e-5, err
 
 
-def test_odefunc_fails_loudly(cuda_device):
+def test_vector_fields_match_reference_class_outputs(cuda_device):
+    """ODEFunc / CDEFunc called directly (odevio_mlp_forward for these small shapes) reproduce the outputs
+    recorded from the reference's own classes (tests/golden/vector_fields.pt, src/models/ODEFunc.py)."""
+    import os
     import odevio_b200
-    f = odevio_b200.ODEFunc(32, 16, 2, "tanh")
+    vf = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vector_fields.pt"))
+    for act in ("tanh", "relu", "leaky_relu", "softplus"):
+        fx = vf[act]
+        f = odevio_b200.ODEFunc(32, 16, 3, act)
+        f.load_state_dict(fx["ode_state"])
+        g = odevio_b200.CDEFunc(9, 8, 2, act)
+        g.load_state_dict(fx["cde_state"])
+        with torch.no_grad():
+            y = f.to(cuda_device)(None, fx["x"].to(cuda_device)).cpu()
+            out = g.to(cuda_device)(None, fx["z"].to(cuda_device)).cpu()
+        assert out.shape == (5, 8, 9)
+        assert torch.allclose(y, fx["y"], rtol=2e-6, atol=2e-7)
+        assert torch.allclose(out, fx["g"], rtol=2e-6, atol=2e-7)
+
+
+def test_vector_fields_fail_loudly_on_cpu():
+    import odevio_b200
     with pytest.raises(odevio_b200.OdevioError):          # CPU tensor: no CPU path
-        f(None, torch.zeros(4, 32))
-    with pytest.raises(odevio_b200.OdevioError), torch.no_grad():   # unsupported shape: no silent fallback
-        f.to(cuda_device)(None, torch.zeros(4, 32, device=cuda_device))
+        odevio_b200.ODEFunc(32, 16, 2, "tanh")(None, torch.zeros(4, 32))
+    with pytest.raises(odevio_b200.OdevioError):
+        odevio_b200.CDEFunc(9, 8, 2, "tanh")(None, torch.zeros(4, 8))
