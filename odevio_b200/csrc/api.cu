@@ -314,7 +314,6 @@ int plan_odernn_bwd(const odevio_odernn_cfg& c, const OdePlan& pl, long long ode
   };
   for (int j = 0; j < NL; ++j) {
     size_t v = static_cast<size_t>(wgrad_tc_splits(ode_rows / pl.R, pl.Node[j], pl.Kode[j], pl.nsm)) * pl.Node[j] * pl.Kode[j];
-    (void)M;
     if (v < static_cast<size_t>(256) * pl.Node[j]) v = static_cast<size_t>(256) * pl.Node[j];
     if (v > part) part = v;
   }

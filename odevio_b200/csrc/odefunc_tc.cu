@@ -15,7 +15,10 @@
 //     the activation and write their 128 x N/8 slice of the next layer's operand (hi / lo) -- or
 //     the fp32 result of the last layer -- followed by a cluster barrier.
 // Activations therefore cross CTAs through L2 (8 KB .. 48 KB per CTA and layer), not DSMEM, whose
-// ~20 B/clk/SM would cost more than the MMAs (B300_MICROARCH.md, CGA/DSMEM table).
+// ~20 B/clk/SM would cost more than the MMAs (B300_MICROARCH.md, CGA/DSMEM table).  Multicasting the
+// shared A chunks (cp.async.bulk ... .multicast::cluster with cluster-wide slot release) was measured
+// and removed: it cut L2 reads 2.3x and changed nothing -- the bound is the per-MMA A-operand read
+// from shared memory.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -86,21 +89,6 @@ __device__ __forceinline__ void ft_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
 __device__ __forceinline__ void ft_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
-}
-// commit -> arrive on the same-offset mbarrier of every CTA in the cluster (ring slot freed cluster-wide)
-__device__ __forceinline__ void ft_commit_multicast(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(mask)
-               : "memory");
-}
-// 1-D bulk copy global -> the same shared-memory offset of every CTA in `mask`, completing tx bytes on
-// the same-offset mbarrier of each destination CTA
-__device__ __forceinline__ void tma_load_1d_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes,
-                                                      uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-      ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-      : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
