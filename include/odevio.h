@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define ODEVIO_ABI_VERSION 2
+#define ODEVIO_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define ODEVIO_API __attribute__((visibility("default")))
@@ -122,6 +122,11 @@ typedef struct odevio_odernn_weights {
   const float* reg_b0;  /* regressor.0.bias   [128]    */
   const float* reg_w1;  /* regressor.2.weight [6, 128] */
   const float* reg_b1;  /* regressor.2.bias   [6]      */
+  /* FusionModule "soft" (src/models/FusionModule.py:20-23): fused = cat * (W cat + b), evaluated in the
+   * forward kernel when both are non-NULL (fv / fi are then the RAW features); NULL = "cat".
+   * odevio_odernn_backward ignores them: in training the host applies the fusion (autograd). */
+  const float* fuse_w;  /* fuse.net.0.weight [D, D] or NULL */
+  const float* fuse_b;  /* fuse.net.0.bias   [D]    or NULL */
 } odevio_odernn_weights;
 
 /* Gradient outputs of odevio_odernn_backward: same shapes as odevio_odernn_weights (overwritten). */

@@ -43,6 +43,7 @@ class OdeRnnWeights(C.Structure):
         ("rnn_w_ih", _FP * MAX_RNN_LAYERS), ("rnn_w_hh", _FP * MAX_RNN_LAYERS),
         ("rnn_b_ih", _FP * MAX_RNN_LAYERS), ("rnn_b_hh", _FP * MAX_RNN_LAYERS),
         ("reg_w0", _FP), ("reg_b0", _FP), ("reg_w1", _FP), ("reg_b1", _FP),
+        ("fuse_w", _FP), ("fuse_b", _FP),
     ]
 
 
@@ -71,7 +72,7 @@ class OdeRnnGrads(C.Structure):
     _fields_ = OdeRnnWeights._fields_
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 

@@ -129,7 +129,7 @@ struct OdePlan {
   size_t bufA_floats, bufB_floats, stage_floats, smem_bytes;
   size_t off_Wode[kMaxLinears];                 // float offsets into the workspace
   size_t off_Wrnn[kMaxRnnLayers][4], off_brnn[kMaxRnnLayers][4];
-  size_t off_Wreg0;
+  size_t off_Wreg0, off_Wfuse;
   size_t off_scratch, scratch_floats_per_cta;
   size_t total_bytes;
   int Kode[kMaxLinears], Node[kMaxLinears];
@@ -223,6 +223,7 @@ int plan_odernn(const odevio_odernn_cfg& c, OdePlan& pl) {
     }
   }
   pl.off_Wreg0 = take(static_cast<size_t>(c.D) * kRegHidden);
+  pl.off_Wfuse = take(DD);
   pl.scratch_floats_per_cta = align_up(static_cast<size_t>(kMaxStages + 2) * c.D * pl.R, 64);
   pl.off_scratch = take(pl.scratch_floats_per_cta * pl.grid);
   pl.total_bytes = off * sizeof(float);
@@ -519,6 +520,13 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
     float* dst = ws + pl.off_Wreg0;
     ODEVIO_CUDA_TRY(transpose_pack(w->reg_w0, kRegHidden, D, dst, kRegHidden, 0, 0, stream));
     p.Wreg0 = dst; p.breg0 = w->reg_b0; p.Wreg1 = w->reg_w1; p.breg1 = w->reg_b1;
+  }
+  if (w->fuse_w && w->fuse_b) {
+    float* dst = ws + pl.off_Wfuse;
+    ODEVIO_CUDA_TRY(transpose_pack(w->fuse_w, D, D, dst, D, 0, 0, stream));
+    p.Wfuse = dst; p.bfuse = w->fuse_b;
+  } else if (w->fuse_w || w->fuse_b) {
+    return ODEVIO_E_NULL;
   }
   p.fv = fv; p.fi = fi; p.Dv = Dv; p.ts = ts; p.h0 = h0;
   p.pose = pose; p.hT = hT; p.stats = stats; p.status = status;

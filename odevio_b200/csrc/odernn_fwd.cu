@@ -319,7 +319,10 @@ __device__ __forceinline__ void assemble_jump_input(Ctx<RT>& c, int i, int l) {
   const FwdParams& p = *c.prm;
   const int D = p.D;
   const TileThread& th = c.th;
-  if (l == 0) {
+  if (l == 0 && p.Wfuse) {
+    // 'soft' fusion: PH_FUSE left cat * Linear(cat) in scratch K[4] ([D][RT])
+    for (int e = th.ctid; e < D * RT / 4; e += th.ncons) st4(c.bufA + 4 * e, ld4(c.K[4] + 4 * e));
+  } else if (l == 0) {
     for (int e = th.ctid; e < D * RT; e += th.ncons) {
       const int m = e / D, k = e - m * D;          // coalesced along k
       const int b = c.tile * RT + m;
@@ -375,7 +378,7 @@ struct GemmOp {
 // (inlined) tile_gemm call site: every GEMM of the path -- ODEFunc layers of every RK stage, the
 // RNN/GRU jump, the pose head -- is issued from there, so the hot loop is compiled once per
 // column-pair count and scheduled by ptxas as straight-line kernel code.
-enum { PH_INTERVAL = 0, PH_STEP_BEGIN, PH_STAGE, PH_LAYER, PH_STEP_END, PH_JUMP, PH_REG, PH_REG_OUT, PH_TILE_END };
+enum { PH_INTERVAL = 0, PH_STEP_BEGIN, PH_STAGE, PH_LAYER, PH_STEP_END, PH_FUSE, PH_JUMP, PH_REG, PH_REG_OUT, PH_TILE_END };
 
 }  // namespace
 
@@ -475,7 +478,7 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
             ph = PH_STEP_BEGIN;
           } else {
             write_stats<RT>(c, i);
-            l = 0; g = 0; ph = PH_JUMP;
+            l = 0; g = 0; ph = p.Wfuse ? PH_FUSE : PH_JUMP;
           }
           break;
         }
@@ -550,8 +553,31 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
           } else {
             write_stats<RT>(c, i);
             __syncthreads();
-            l = 0; g = 0; ph = PH_JUMP;
+            l = 0; g = 0; ph = p.Wfuse ? PH_FUSE : PH_JUMP;
           }
+          break;
+        }
+        case PH_FUSE: {
+          // FusionModule 'soft' (src/models/FusionModule.py:20-23): x <- cat(fv, fi) * (W_f cat + b_f), in the kernel
+          if (!c.th.producer) {
+            for (int e = c.th.ctid; e < D * RT; e += ncons) {
+              const int m = e / D, k = e - m * D;
+              const int b = tile * RT + m;
+              float v = 0.f;
+              if (b < p.B) {
+                const size_t row = static_cast<size_t>(b) * p.S + i;
+                v = (k < p.Dv) ? p.fv[row * p.Dv + k] : p.fi[row * (D - p.Dv) + (k - p.Dv)];
+              }
+              c.bufA[k * RT + m] = v;
+            }
+            named_bar_sync(1, ncons);
+          }
+          op.W = p.Wfuse; op.K = D; op.N = D; op.in = c.bufA; op.ode_layout = false;
+          op.epi.mode = EPI_MUL_IN; op.epi.bias = p.bfuse; op.epi.act = ACT_NONE;
+          op.epi.hs = c.bufA; op.epi.ldh = RT; op.epi.offh = 0;
+          op.epi.out0 = c.K[4]; op.epi.ld0 = RT; op.epi.off0 = 0;
+          do_gemm = true;
+          ph = PH_JUMP;
           break;
         }
         case PH_JUMP: {

@@ -45,6 +45,8 @@ struct FwdParams {
   const float* breg0;  // [128]
   const float* Wreg1;  // [6][128]  (PyTorch layout, used directly)
   const float* breg1;  // [6]
+  const float* Wfuse;  // FusionModule 'soft': packed [D][D] or nullptr ('cat')
+  const float* bfuse;  // [D]
   // io
   const float* fv; const float* fi; int Dv;
   const float* ts; const float* h0;

@@ -72,7 +72,8 @@ struct TileThread {
 //       all rec_ld features as K-major core matrices [feature/8][R/4][8][4], split into a
 //       TF32-exact high part (rec) and the residual (rec_lo).
 //   EPI_GRU_N     v = tanh(acc + bias + hn * r)                 the GRU new gate alone (backward recompute)
-enum { EPI_STORE = 0, EPI_GRU_NEW = 1, EPI_MUL_DACT = 2, EPI_ADD = 3, EPI_GRU_N = 4 };
+//   EPI_MUL_IN    v = (acc + bias) * hs[n]                      FusionModule 'soft': cat * Linear(cat)
+enum { EPI_STORE = 0, EPI_GRU_NEW = 1, EPI_MUL_DACT = 2, EPI_ADD = 3, EPI_GRU_N = 4, EPI_MUL_IN = 5 };
 struct Epilogue {
   int mode;
   const float* bias;   // [N] or nullptr
@@ -147,6 +148,14 @@ __device__ __forceinline__ void run_epilogue(const Epilogue& e, int n, int rb, c
     for (int r = 0; r < RT; ++r) {
       const size_t o = static_cast<size_t>(n) * RT + r;
       v[r] = apply_act((acc[r] + b) + e.hn[o] * e.rg[o], ACT_TANH);
+    }
+  } else if (e.mode == EPI_MUL_IN) {
+    const float* hp = e.hs + static_cast<size_t>(n) * e.ldh + e.offh + rb * RT;
+#pragma unroll
+    for (int q = 0; q < RT / 4; ++q) {
+      const float4 h4 = ld4(hp + 4 * q);
+      v[4 * q] = (acc[4 * q] + b) * h4.x; v[4 * q + 1] = (acc[4 * q + 1] + b) * h4.y;
+      v[4 * q + 2] = (acc[4 * q + 2] + b) * h4.z; v[4 * q + 3] = (acc[4 * q + 3] + b) * h4.w;
     }
   } else if (e.mode == EPI_MUL_DACT) {
     const float* hp = e.hs + static_cast<size_t>(n) * e.ldh + e.offh + rb * RT;

@@ -153,9 +153,10 @@ class CDEFunc(nn.Module):
 
 
 class FusionModule(nn.Module):
-    """cat / soft / hard fusion (FusionModule.py:17-29).  "cat" is folded into the kernel's
-    feature load (no concatenated tensor is materialised); "soft"/"hard" are one Linear upstream
-    of the path and stay in PyTorch."""
+    """cat / soft / hard fusion (FusionModule.py:17-29).  Inside PoseODERNN, "cat" is folded into
+    the kernel's feature load (no concatenated tensor is materialised) and "soft" runs in the
+    kernel prologue of every jump for inference; while training "soft" stays this torch op so that
+    autograd carries its gradient, and "hard" (Gumbel noise from torch's RNG) always does."""
 
     def __init__(self, feature_dim, fuse_method):
         super().__init__()
@@ -263,7 +264,7 @@ class PoseODERNN(nn.Module):
         cfg.trace_steps = self.trace_steps
         return cfg
 
-    def _weights(self):
+    def _weights(self, fuse_in_kernel=False):
         w = _lib.OdeRnnWeights()
         keep = []
 
@@ -284,6 +285,9 @@ class PoseODERNN(nn.Module):
         w.reg_b0 = ptr(self.regressor[0].bias, "regressor.0.bias")
         w.reg_w1 = ptr(self.regressor[2].weight, "regressor.2.weight")
         w.reg_b1 = ptr(self.regressor[2].bias, "regressor.2.bias")
+        if fuse_in_kernel:
+            w.fuse_w = ptr(self.fuse.net[0].weight, "fuse.net.0.weight")
+            w.fuse_b = ptr(self.fuse.net[0].bias, "fuse.net.0.bias")
         return w, keep
 
     def _prepare_inputs(self, fv, fi, ts, prev):
@@ -291,8 +295,10 @@ class PoseODERNN(nn.Module):
         if not fv.is_cuda:
             raise _lib.OdevioError("PoseODERNN.forward needs CUDA tensors: odevio_b200 has no CPU path")
         B = fv.shape[0]
-        if self.fuse_method == "cat":
-            fvc, fic, Dv = _f32c(fv, "fv"), _f32c(fi, "fi"), fv.shape[2]     # concat happens in-kernel
+        if self.fuse_method == "cat" or (self.fuse_method == "soft" and not self._fuse_in_torch()):
+            # "cat" is folded into the kernel's feature load; "soft" (cat * Linear(cat)) runs in the
+            # kernel prologue of every jump when no gradient is needed (the raw features go in)
+            fvc, fic, Dv = _f32c(fv, "fv"), _f32c(fi, "fi"), fv.shape[2]
         else:
             fvc, fic, Dv = _f32c(self.fuse(fv, fi), "fused"), None, self.f_len
         ts = _f32c(ts, "ts")
@@ -301,6 +307,11 @@ class PoseODERNN(nn.Module):
         if h0 is not None and tuple(h0.shape) != (self.rnn_num_layers, B, self.f_len):
             raise _lib.OdevioError(f"prev must be [L,B,D]={self.rnn_num_layers, B, self.f_len}, got {tuple(h0.shape)}")
         return fvc, fic, Dv, ts_in, h0
+
+    def _fuse_in_torch(self):
+        """'soft' fusion stays a torch op (autograd) while training; 'hard' (Gumbel noise) always."""
+        return self.fuse_method == "hard" or (
+            torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()))
 
     def forward(self, fv, fi, ts, prev=None, do_profile=False):
         _lib.load()
@@ -345,7 +356,7 @@ class PoseODERNN(nn.Module):
         stats = (torch.zeros(S, self.rnn_num_layers, B, 2 + 2 * T, dtype=torch.int32, device=dev)
                  if (self.collect_stats or T) else None)
         status = torch.zeros(B, dtype=torch.int32, device=dev)
-        w, keep = self._weights()
+        w, keep = self._weights(fuse_in_kernel=(self.fuse_method == "soft" and fic is not None))
         stream = torch.cuda.current_stream(dev).cuda_stream
         if do_profile:
             torch.cuda.nvtx.range_push("odeint")                               # PoseODERNN.py:103-104

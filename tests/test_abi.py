@@ -43,7 +43,7 @@ def test_struct_layout_matches_header(lib):
     assert (cfg.B, cfg.S, cfg.D, cfg.H, cfg.n_hidden, cfg.L) == (1, 10, 768, 512, 3, 2)
     assert abs(cfg.atol - 1e-6) < 1e-12 and abs(cfg.rtol - 1e-2) < 1e-9 and abs(cfg.dt0 - 1e-4) < 1e-11
     assert (cfg.accept_strict, cfg.floor_factor, cfg.endpoint_dense, cfg.exact_landing) == (1, 0, 0, 1)
-    assert lib.odevio_version() == _lib.ABI_VERSION == 2
+    assert lib.odevio_version() == _lib.ABI_VERSION == 3
 
 
 def test_workspace_and_validation_without_gpu(lib):
