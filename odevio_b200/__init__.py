@@ -8,5 +8,6 @@ C ABI underneath: include/odevio.h  ->  odevio_b200/lib/libodevio_b200.so (build
 
 from .modules import PoseODERNN, PoseCDE, ODEFunc, CDEFunc, FusionModule  # noqa: F401
 from ._lib import OdevioError, LIB_PATH  # noqa: F401
+from .streaming import StreamingPoseODERNN  # noqa: F401
 
-__all__ = ["PoseODERNN", "PoseCDE", "ODEFunc", "CDEFunc", "FusionModule", "OdevioError", "LIB_PATH"]
+__all__ = ["PoseODERNN", "PoseCDE", "ODEFunc", "CDEFunc", "FusionModule", "OdevioError", "LIB_PATH", "StreamingPoseODERNN"]
