@@ -41,7 +41,9 @@ namespace {
 
 constexpr int FT_ROWS = 128;          // rows per tile = MMA M
 // cluster size NC (column slices per 128-row tile) and k per ring stage KCH are template parameters:
-//   <8, 16>  few tiles (B ~ 1024): 8 CTAs per tile keep 128 SMs busy, N = 64 / 96 per MMA
+//   <8, 8>   few tiles (B ~ 1024): 8 CTAs per tile keep 128 SMs busy; per layer they form an nN x nK grid
+//            (2 x 4 / 4 x 2 at the default shapes) so that every MMA is 192..256 columns wide, the k-split
+//            partials are reduced through L2
 //   <4, 16>  many tiles: N = 128 / 192 / 256 per MMA amortises the ~125 clk A-operand read of every MMA
 // FT_SPLIT: true = one fp32 operand copy crosses L2, hi/lo produced in shared memory by the splitter warps;
 //           false = the epilogues write hi and lo images (twice the bytes, no split stage: wide slices do not
@@ -59,7 +61,11 @@ constexpr int FT_THREADS = 32 * (FT_WARP_MMA + 1);
 
 struct FtParams {
   int M, NL, act;
-  int K[FT_MAX_LAYERS], N[FT_MAX_LAYERS];      // layer shapes (N % 256 == 0 or N/8 in {32, 64, 96, 128}, K % 32 == 0)
+  int K[FT_MAX_LAYERS], N[FT_MAX_LAYERS];      // layer shapes
+  int nN[FT_MAX_LAYERS], nK[FT_MAX_LAYERS];    // the cluster's CTAs form an nN x nK grid per layer: CTA (cn, ck) computes
+                                               // output columns slice cn over the k range ck; nK > 1: partials reduced through L2
+  float* part;                                 // per cluster: [nK*nN][Nsl][128] fp32 partial sums, column-major (nK > 1)
+  size_t part_floats;                          // per cluster
   const float* Wp[FT_MAX_LAYERS];              // packed [c][K/KCH][Nc/8][KCH/4][8][4]: fp32 (FT_SPLIT) or TF32-exact high part
   const float* Wlo[FT_MAX_LAYERS];             // residual (only !FT_SPLIT)
   const float* bias[FT_MAX_LAYERS];
@@ -190,7 +196,10 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
     if (tid == 0) FT_STAMP(1);
 
     for (int l = 0; l < p.NL; ++l) {
-      const int K = p.K[l], N = p.N[l], Nc = N / FT_NC, nch = K / FT_KCH;
+      // CTA (cn, ck) of the layer's nN x nK grid: Nc output columns starting at cn * Nc, k range [ck * Ksl, (ck + 1) * Ksl)
+      const int K = p.K[l], N = p.N[l], nN = p.nN[l], nK = p.nK[l];
+      const int cn = static_cast<int>(crank) % nN, ck = static_cast<int>(crank) / nN;
+      const int Nc = N / nN, Ksl = K / nK, nch = Ksl / FT_KCH, ch0 = ck * nch;
       const float* a_src_buf = xa_cluster + static_cast<size_t>(l & 1) * 2 * p.xa_buf_floats;
       float* nx = xa_cluster + static_cast<size_t>((l + 1) & 1) * 2 * p.xa_buf_floats;
       const uint32_t a_bytes = FT_ROWS * FT_KCH * 4, w_bytes = static_cast<uint32_t>(Nc) * FT_KCH * 4;
@@ -198,7 +207,8 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
       if (warp == FT_WARP_TMA) {
         // ===== TMA producer: ONE fp32 copy of the A chunk and of the weight chunk per raw stage.  Whole warp,
         // warp-uniform operands, one elected lane issues (a lone active lane costs an R2UR waterfall per copy).
-        const float* wsrc = p.Wp[l] + static_cast<size_t>(crank) * Nc * K;
+        const float* wsrc = p.Wp[l] + static_cast<size_t>(cn) * Nc * K + static_cast<size_t>(ch0) * Nc * FT_KCH;
+        const float* asrc = a_src_buf + static_cast<size_t>(ch0) * FT_ROWS * FT_KCH;
         for (int ch = 0; ch < nch; ++ch) {
           const uint32_t g = g0 + ch, rs = g % nraw, rph = (g / nraw) & 1u;
           mbar_wait(&raw_empty[rs], rph ^ 1u);
@@ -206,13 +216,13 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
           if (elect_one()) {
             if (FT_SPLIT) {
               mbar_arrive_expect_tx(&raw_full[rs], a_bytes + w_bytes);
-              tma_load_1d(dst, a_src_buf + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &raw_full[rs]);
+              tma_load_1d(dst, asrc + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &raw_full[rs]);
               tma_load_1d(dst + a_bytes, wsrc + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &raw_full[rs]);
             } else {       // stage = [A_hi | A_lo | W_hi | W_lo], consumed by the MMA issuer directly
-              const float* wlo = p.Wlo[l] + static_cast<size_t>(crank) * Nc * K;
+              const float* wlo = p.Wlo[l] + static_cast<size_t>(cn) * Nc * K + static_cast<size_t>(ch0) * Nc * FT_KCH;
               mbar_arrive_expect_tx(&raw_full[rs], 2 * (a_bytes + w_bytes));
-              tma_load_1d(dst, a_src_buf + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &raw_full[rs]);
-              tma_load_1d(dst + a_bytes, a_src_buf + p.xa_buf_floats + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &raw_full[rs]);
+              tma_load_1d(dst, asrc + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &raw_full[rs]);
+              tma_load_1d(dst + a_bytes, asrc + p.xa_buf_floats + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &raw_full[rs]);
               tma_load_1d(dst + 2 * a_bytes, wsrc + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &raw_full[rs]);
               tma_load_1d(dst + 2 * a_bytes + w_bytes, wlo + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &raw_full[rs]);
             }
@@ -327,7 +337,16 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) accv[q] += __uint_as_float(u[q]);
           }
-          const int n0 = static_cast<int>(crank) * Nc + c0;
+          if (nK > 1) {
+            // k-split layer: fp32 partial sums of this CTA's k range -> L2; reduced after the cluster barrier
+            // column-major [slice][col][row]: the 32 rows of a warp are contiguous -> coalesced both ways
+            float* dstp = p.part + static_cast<size_t>(cluster_id) * p.part_floats +
+                          (static_cast<size_t>(ck * nN + cn) * Nc + c0) * FT_ROWS + r;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) __stcg(dstp + static_cast<size_t>(q) * FT_ROWS, accv[q]);
+            continue;
+          }
+          const int n0 = cn * Nc + c0;
           float v[32];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -354,6 +373,49 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
       accum_phase ^= 1u;
       g0 += static_cast<uint32_t>(nch);
       __syncwarp();
+      if (nK > 1) {
+        // every CTA's partial is in L2: CTA (cn, ck) finishes columns [ck * Nc / nK, (ck + 1) * Nc / nK) of slice cn,
+        // summing the nK partials in a fixed order (deterministic), then bias + activation + operand store
+        cluster_sync_all();
+        if (warp < FT_EPI_WARPS) {
+          const int r = tid & 127, half = tid >> 7;
+          const int ncols = Nc / nK, nchunks = ncols / 32;
+          const int cbeg = half == 0 ? 0 : (nchunks + 1) / 2, cend = half == 0 ? (nchunks + 1) / 2 : nchunks;
+          const bool last = l == p.NL - 1;
+          const int act = last ? ACT_TANH : p.act;
+          const float* pb = p.part + static_cast<size_t>(cluster_id) * p.part_floats;
+          for (int cc = cbeg; cc < cend; ++cc) {
+            const int c0 = ck * ncols + 32 * cc;                      // column inside slice cn
+            const int n0 = cn * Nc + c0;
+            float v[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = 0.f;
+            for (int kk = 0; kk < nK; ++kk) {
+              const float* src = pb + (static_cast<size_t>(kk * nN + cn) * Nc + c0) * FT_ROWS + r;
+#pragma unroll
+              for (int q = 0; q < 32; ++q) v[q] += __ldcg(src + static_cast<size_t>(q) * FT_ROWS);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = *reinterpret_cast<const float4*>(p.bias[l] + n0 + 4 * q);
+              const float4 a4 = apply_act4(make_float4(v[4 * q] + b4.x, v[4 * q + 1] + b4.y, v[4 * q + 2] + b4.z, v[4 * q + 3] + b4.w), act);
+              v[4 * q] = a4.x; v[4 * q + 1] = a4.y; v[4 * q + 2] = a4.z; v[4 * q + 3] = a4.w;
+            }
+            if (last) {
+              if (row0 + r < p.M) {
+                float4* dst = reinterpret_cast<float4*>(p.out + static_cast<size_t>(row0 + r) * N + n0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              }
+            } else {
+              if (FT_SPLIT) store_chunk<FT_KCH>(nx, r, n0, v);
+              else store_chunk_hilo<FT_KCH>(nx, nx + p.xa_buf_floats, r, n0, v);
+            }
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        __syncwarp();
+      }
       // every CTA's slice of the next operand is written (and this CTA's accumulator drained)
       cluster_sync_all();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -389,6 +451,8 @@ __global__ void ft_pack_weight_kernel(const float* __restrict__ W, int N, int K,
 
 struct FtPlan {
   int NL, ntiles, nclusters, kmax, ncmax, nraw, NC, KCH, split;
+  int nN[FT_MAX_LAYERS], nK[FT_MAX_LAYERS];
+  size_t off_part, part_floats;
   size_t off_w[FT_MAX_LAYERS], off_wlo[FT_MAX_LAYERS], off_xa, xa_buf_floats, total_bytes, smem_bytes;
   uint32_t raw_stage_bytes, op_stage_bytes;
   int K[FT_MAX_LAYERS], N[FT_MAX_LAYERS];
@@ -407,24 +471,47 @@ int ft_plan(int M, int D, int H, int n_hidden, FtPlan& pl) {
   // few tiles: 8 CTAs per tile (latency, SM count); many tiles: 4 CTAs per tile (wider MMAs, fewer A re-reads)
   const bool wide = pl.ntiles > nsm / 8 && ok(D, 4) && ok(H, 4);
   pl.NC = wide ? 4 : 8;
-  pl.KCH = 16;
+  pl.KCH = wide ? 16 : 8;
   pl.split = wide ? 0 : 1;
-  if (!ok(D, pl.NC) || !ok(H, pl.NC) || D / pl.NC > 128 * (wide ? 2 : 1) || H / pl.NC > 128 * (wide ? 2 : 1)) return ODEVIO_E_SHAPE;
   pl.NL = n_hidden + 1;
   pl.kmax = D > H ? D : H;
-  pl.ncmax = pl.kmax / pl.NC;
+  if (D % 64 || H % 64 || (D / pl.NC) % 32) return ODEVIO_E_SHAPE;     // per-CTA input-conversion slices of 32 features
+  pl.ncmax = 0;
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off = (off + n + 63) / 64 * 64; return o; };
   for (int l = 0; l < pl.NL; ++l) {
-    pl.K[l] = l == 0 ? D : H;
-    pl.N[l] = l == pl.NL - 1 ? D : H;
-    pl.off_w[l] = take(static_cast<size_t>(pl.K[l]) * pl.N[l]);
-    pl.off_wlo[l] = take(static_cast<size_t>(pl.K[l]) * pl.N[l]);
+    const int K = l == 0 ? D : H, N = l == pl.NL - 1 ? D : H;
+    pl.K[l] = K; pl.N[l] = N;
+    if (wide) {
+      pl.nN[l] = 4; pl.nK[l] = 1;
+    } else {
+      // 8 CTAs as an nN x nK grid with >= 192-column MMAs where the shape allows (the A-operand read of an
+      // SS-mode MMA costs ~125 clk regardless of N): widest slice whose count divides the cluster
+      pl.nN[l] = 0;
+      const int cand[] = {256, 192, 128, 96, 64, 32};
+      for (int ci = 0; ci < 6 && !pl.nN[l]; ++ci) {
+        const int nsl = cand[ci];
+        if (N % nsl) continue;
+        const int nn = N / nsl;
+        if (nn > 8 || 8 % nn) continue;
+        const int nk = 8 / nn;
+        if (K % (nk * pl.KCH) || (nsl / nk) % 32) continue;
+        pl.nN[l] = nn; pl.nK[l] = nk;
+      }
+      if (!pl.nN[l]) return ODEVIO_E_SHAPE;
+    }
+    const int nsl = N / pl.nN[l];
+    if (nsl % 32 || nsl < 32 || nsl > 256 || K % pl.KCH) return ODEVIO_E_SHAPE;
+    if (nsl > pl.ncmax) pl.ncmax = nsl;
+    pl.off_w[l] = take(static_cast<size_t>(K) * N);
+    pl.off_wlo[l] = take(static_cast<size_t>(K) * N);
   }
   pl.nclusters = nsm / pl.NC;
   if (pl.nclusters > pl.ntiles) pl.nclusters = pl.ntiles;
   pl.xa_buf_floats = static_cast<size_t>(FT_ROWS) * pl.kmax;
   pl.off_xa = take(static_cast<size_t>(pl.nclusters) * 4 * pl.xa_buf_floats);
+  pl.part_floats = static_cast<size_t>(8) * FT_ROWS * 256;
+  pl.off_part = take(wide ? 64 : static_cast<size_t>(pl.nclusters) * pl.part_floats);
   pl.total_bytes = off * sizeof(float);
   if (pl.split) {
     pl.raw_stage_bytes = static_cast<uint32_t>(FT_ROWS + pl.ncmax) * pl.KCH * 4u;
@@ -504,16 +591,17 @@ int32_t odevio_odefunc_forward(int32_t M, int32_t D, int32_t H, int32_t n_hidden
   p.M = M; p.NL = pl.NL; p.act = activation;
   for (int l = 0; l < pl.NL; ++l) {
     if (!weights[l] || !biases[l]) return ODEVIO_E_NULL;
-    p.K[l] = pl.K[l]; p.N[l] = pl.N[l];
-    ft_pack_weight_kernel<<<296, 256, 0, stream>>>(weights[l], pl.N[l], pl.K[l], pl.NC, pl.KCH, ws + pl.off_w[l],
+    p.K[l] = pl.K[l]; p.N[l] = pl.N[l]; p.nN[l] = pl.nN[l]; p.nK[l] = pl.nK[l];
+    ft_pack_weight_kernel<<<296, 256, 0, stream>>>(weights[l], pl.N[l], pl.K[l], pl.nN[l], pl.KCH, ws + pl.off_w[l],
                                                    pl.split ? nullptr : ws + pl.off_wlo[l]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int32_t>(e);
     p.Wp[l] = ws + pl.off_w[l]; p.Wlo[l] = ws + pl.off_wlo[l]; p.bias[l] = biases[l];
   }
   p.x = x; p.out = out; p.xa = ws + pl.off_xa; p.xa_buf_floats = pl.xa_buf_floats;
+  p.part = ws + pl.off_part; p.part_floats = pl.part_floats;
   p.ntiles = pl.ntiles; p.nraw = pl.nraw; p.raw_stage_bytes = pl.raw_stage_bytes; p.op_stage_bytes = pl.op_stage_bytes;
-  cudaError_t e = pl.NC == 8 ? ft_launch<8, 16, true>(p, pl, stream) : ft_launch<4, 16, false>(p, pl, stream);
+  cudaError_t e = pl.NC == 8 ? ft_launch<8, 8, true>(p, pl, stream) : ft_launch<4, 16, false>(p, pl, stream);
   if (e != cudaSuccess) return static_cast<int32_t>(e);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int32_t>(e);
