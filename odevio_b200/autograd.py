@@ -67,8 +67,14 @@ class _OdeRnnFunction(torch.autograd.Function):
         nbytes = lib.odevio_odernn_backward_workspace_bytes(C.byref(cfg), ode_rows)
         if nbytes == 0:
             raise _lib.OdevioError("odevio_odernn_backward: unsupported configuration")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-
+        # The record streams dominate (tens of GB at B = 4096).  The buffer is kept on the module and reused
+        # across steps: handed back to torch's caching allocator it gets split by the next forward's small
+        # allocations and the following request of ~the same size no longer fits (measured: OOM / retry stalls).
+        ws = getattr(module, "_bwd_workspace", None)
+        if ws is None or ws.device != dev or ws.numel() < nbytes:
+            module._bwd_workspace = ws = None
+            gran = 1 << 30 if nbytes >= (8 << 30) else 1 << 26
+            module._bwd_workspace = ws = torch.empty((nbytes + gran - 1) // gran * gran, dtype=torch.uint8, device=dev)
         w = _lib.OdeRnnWeights()
         g = _lib.OdeRnnGrads()
         grads = [torch.empty_like(p) for p in params]
@@ -98,7 +104,7 @@ class _OdeRnnFunction(torch.autograd.Function):
                 C.byref(cfg), C.byref(w), _lib.dptr(fvc), _lib.dptr(fic), ctx.Dv,
                 _lib.dptr(ctx.ckpt), ctx.ckpt_bytes, _lib.dptr(rec_base), ode_rows,
                 _lib.dptr(gpose), _lib.dptr(ghT_c), C.byref(g), _lib.dptr(gfused), _lib.dptr(gh0),
-                _lib.dptr(ws), nbytes, C.c_void_p(stream))
+                _lib.dptr(ws), ws.numel(), C.c_void_p(stream))
         _lib.check(rc)
         gfv = gfi = None
         if gfused is not None:

@@ -50,4 +50,4 @@ if "relu" in cases:
     case("relu dopri5 B=6 S=3", 6, 3, ode_activation_fn="relu")
     case("leaky dopri5 B=6 S=3", 6, 3, ode_activation_fn="leaky_relu")
 if "timing" in cases:
-    timing(1024, ode_rtol=1e-3)
+    timing(int(os.environ.get("PROBE_B", "1024")), iters=3, ode_rtol=1e-3)
