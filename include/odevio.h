@@ -107,7 +107,10 @@ typedef struct odevio_odernn_cfg {
                                  every solve; the stats row then has 2 + 2*T int32 (floats as bits) */
   int32_t ckpt_loops;         /* training: stored solver iterations per interval and tile (0 = 16, or
                                  `substeps` for the fixed-step solvers); overflow -> STATUS_CKPT_OVERFLOW */
-  int32_t reserved[4];
+  int32_t evolve_only;        /* 1: PoseODERNN.evolve_state (src/models/PoseODERNN.py:70-75): only the ODE solves of the
+                                 S intervals, no jump, no pose head; hT returns the evolved states ([L,B,D]), pose is
+                                 not written (may be NULL) and fv / fi are not read */
+  int32_t reserved[3];
 } odevio_odernn_cfg;
 
 /* PyTorch-layout parameters ([out, in] row-major), exactly the reference's state_dict tensors */

@@ -450,21 +450,24 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
                               float* pose, float* hT, int32_t* stats, int32_t* status,
                               void* ckpt, size_t ckpt_bytes,
                               void* workspace, size_t workspace_bytes, void* stream_) {
-  if (!cfg || !w || !fv || !ts || !pose || !hT || !workspace) return ODEVIO_E_NULL;
-  if (cfg->save_checkpoints && !ckpt) return ODEVIO_E_NULL;
+  if (!cfg || !w || !ts || !hT || !workspace) return ODEVIO_E_NULL;
+  if (!cfg->evolve_only && (!fv || !pose)) return ODEVIO_E_NULL;
+  if (cfg->save_checkpoints && (!ckpt || cfg->evolve_only)) return ODEVIO_E_NULL;
   const odevio_odernn_cfg& c = *cfg;
   OdePlan pl;
   const int rc = plan_odernn(c, pl);
   if (rc != 0) return rc;
-  if (Dv <= 0 || Dv > c.D || (Dv < c.D && !fi) || (Dv == c.D && fi)) return ODEVIO_E_SHAPE;
+  if (!c.evolve_only && (Dv <= 0 || Dv > c.D || (Dv < c.D && !fi) || (Dv == c.D && fi))) return ODEVIO_E_SHAPE;
   if (workspace_bytes < pl.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ODEVIO_E_WORKSPACE;
   if (c.save_checkpoints && (ckpt_bytes < ckpt_total_bytes(c, pl) || (reinterpret_cast<uintptr_t>(ckpt) & 255)))
     return ODEVIO_E_WORKSPACE;
   const int NL = c.n_hidden + 1;
   for (int j = 0; j < NL; ++j) if (!w->ode_w[j] || !w->ode_b[j]) return ODEVIO_E_NULL;
-  for (int l = 0; l < c.L; ++l)
-    if (!w->rnn_w_ih[l] || !w->rnn_w_hh[l] || !w->rnn_b_ih[l] || !w->rnn_b_hh[l]) return ODEVIO_E_NULL;
-  if (!w->reg_w0 || !w->reg_b0 || !w->reg_w1 || !w->reg_b1) return ODEVIO_E_NULL;
+  if (!c.evolve_only) {
+    for (int l = 0; l < c.L; ++l)
+      if (!w->rnn_w_ih[l] || !w->rnn_w_hh[l] || !w->rnn_b_ih[l] || !w->rnn_b_hh[l]) return ODEVIO_E_NULL;
+    if (!w->reg_w0 || !w->reg_b0 || !w->reg_w1 || !w->reg_b1) return ODEVIO_E_NULL;
+  }
 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   float* ws = static_cast<float*>(workspace);
@@ -479,6 +482,7 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
   p.atol = c.atol; p.rtol = c.rtol; p.dt0 = c.dt0; p.safety = c.safety; p.fmin = c.factor_min; p.fmax = c.factor_max;
   p.accept_strict = c.accept_strict; p.floor_factor = c.floor_factor; p.endpoint_dense = c.endpoint_dense;
   p.max_steps = c.max_steps; p.exact_landing = c.exact_landing; p.trace_steps = c.trace_steps;
+  p.evolve_only = c.evolve_only ? 1 : 0;
   if (!make_tableau(c.solver, p.tab)) return ODEVIO_E_ENUM;
 
   // ---- pre-pack weights into the workspace
@@ -488,7 +492,7 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
     p.Wode[j] = dst; p.bode[j] = w->ode_b[j]; p.Kode[j] = pl.Kode[j]; p.Node[j] = pl.Node[j];
   }
   const size_t DD = static_cast<size_t>(D) * D;
-  for (int l = 0; l < c.L; ++l) {
+  for (int l = 0; l < (c.evolve_only ? 0 : c.L); ++l) {
     if (pl.G == 1) {
       float* dst = ws + pl.off_Wrnn[l][0];
       ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l], D, D, dst, D, 0, 0, stream));
@@ -516,12 +520,14 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
       p.brnn[l][0] = br; p.brnn[l][1] = bz; p.brnn[l][2] = bi; p.brnn[l][3] = bh;
     }
   }
-  {
+  if (!c.evolve_only) {
     float* dst = ws + pl.off_Wreg0;
     ODEVIO_CUDA_TRY(transpose_pack(w->reg_w0, kRegHidden, D, dst, kRegHidden, 0, 0, stream));
     p.Wreg0 = dst; p.breg0 = w->reg_b0; p.Wreg1 = w->reg_w1; p.breg1 = w->reg_b1;
   }
-  if (w->fuse_w && w->fuse_b) {
+  if (c.evolve_only) {
+    // no fusion / jump / head weights are read
+  } else if (w->fuse_w && w->fuse_b) {
     float* dst = ws + pl.off_Wfuse;
     ODEVIO_CUDA_TRY(transpose_pack(w->fuse_w, D, D, dst, D, 0, 0, stream));
     p.Wfuse = dst; p.bfuse = w->fuse_b;

@@ -478,7 +478,7 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
             ph = PH_STEP_BEGIN;
           } else {
             write_stats<RT>(c, i);
-            l = 0; g = 0; ph = p.Wfuse ? PH_FUSE : PH_JUMP;
+            l = 0; g = 0; ph = p.evolve_only ? ((++i < p.S) ? PH_INTERVAL : PH_TILE_END) : (p.Wfuse ? PH_FUSE : PH_JUMP);
           }
           break;
         }
@@ -553,7 +553,7 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
           } else {
             write_stats<RT>(c, i);
             __syncthreads();
-            l = 0; g = 0; ph = p.Wfuse ? PH_FUSE : PH_JUMP;
+            l = 0; g = 0; ph = p.evolve_only ? ((++i < p.S) ? PH_INTERVAL : PH_TILE_END) : (p.Wfuse ? PH_FUSE : PH_JUMP);
           }
           break;
         }

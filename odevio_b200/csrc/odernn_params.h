@@ -32,6 +32,7 @@ struct FwdParams {
   // controller
   float atol, rtol, dt0, safety, fmin, fmax;
   int accept_strict, floor_factor, endpoint_dense, max_steps, exact_landing, trace_steps;
+  int evolve_only;           // PoseODERNN.evolve_state: ODE solves only (no jump / head)
   DevTableau tab;
   // packed weights (K-major [K][N]) and biases
   const float* Wode[kMaxLinears];

@@ -376,6 +376,50 @@ class PoseODERNN(nn.Module):
                            if T else None)
         return pose, hT, (cfg, ckpt, ckpt_bytes)
 
+    def evolve_state(self, state, ts):
+        """``PoseODERNN.evolve_state`` (reference PoseODERNN.py:70-75): the IVP ``y' = ODEFunc(y)`` from
+        ``ts[:, 0]`` to ``ts[:, -1]`` for one layer's hidden state ``[B, D]`` (intermediate columns of
+        ``ts`` are solved as consecutive intervals; the reference passes two).  Runs the fused kernel
+        with ``evolve_only = 1``: solver loop only, no jump, no pose head.  Inference only."""
+        lib = _lib.load()
+        if not state.is_cuda:
+            raise _lib.OdevioError("PoseODERNN.evolve_state needs CUDA tensors: odevio_b200 has no CPU path")
+        y0 = _f32c(state.detach(), "state")
+        tsc = _f32c(ts.detach(), "ts")
+        if y0.dim() != 2 or y0.shape[1] != self.f_len or tsc.dim() != 2 or tsc.shape[0] != y0.shape[0] or tsc.shape[1] < 2:
+            raise _lib.OdevioError(f"evolve_state expects state [B,{self.f_len}] and ts [B,>=2], got "
+                                   f"{tuple(state.shape)}, {tuple(ts.shape)}")
+        B, S = y0.shape[0], tsc.shape[1] - 1
+        dev = y0.device
+        cfg = self._cfg(B, S)
+        cfg.L = 1
+        cfg.evolve_only = 1
+        nbytes = lib.odevio_odernn_workspace_bytes(C.byref(cfg))
+        if nbytes == 0:
+            raise _lib.OdevioError("unsupported configuration for the fused kernel")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty(1, B, self.f_len, dtype=torch.float32, device=dev)
+        T = self.trace_steps
+        stats = torch.zeros(S, 1, B, 2 + 2 * T, dtype=torch.int32, device=dev) if (self.collect_stats or T) else None
+        status = torch.zeros(B, dtype=torch.int32, device=dev)
+        w, keep = self._weights()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = lib.odevio_odernn_forward(
+                C.byref(cfg), C.byref(w), None, None, 0, _lib.dptr(tsc, "ts"), _lib.dptr(y0.unsqueeze(0), "state"),
+                None, _lib.dptr(out), _lib.dptr(stats), _lib.dptr(status), None, 0,
+                _lib.dptr(ws), nbytes, C.c_void_p(stream))
+        _lib.check(rc)
+        del keep
+        self.last_status = status
+        self.last_stats = None if stats is None else stats[..., :2]
+        return out[0]
+
+    def update_method(self):
+        """Reference PoseODERNN.update_method (PoseODERNN.py:77-86): switch to Euler with a fixed-step
+        controller (one step of ``ode_substeps`` per interval)."""
+        self.ode_solver = self._set_solver("euler")
+
     def check_status(self):
         """Synchronising check of the last forward's per-row solver status."""
         if self.last_status is None:

@@ -182,3 +182,29 @@ def test_controller_trace_matches_oracle(cuda_device):
     # interval >= 1 (state away from 0): ramp-up is noise-free on both sides
     ramp = tg[1:, :, :, :2, 0]
     assert torch.allclose(ramp, tr[1:, :, :, :2, 0], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("solver", ["dopri5", "rk4"])
+def test_evolve_state(cuda_device, solver):
+    """PoseODERNN.evolve_state (reference PoseODERNN.py:70-75): one IVP per row, no jump / head
+    (kernel flag evolve_only).  Also checks that two chained calls equal one call over three
+    time columns (consecutive intervals restart the controller at dt0, like the reference loop)."""
+    ref, mod = make_pair(cuda_device, ode_solver=solver, ode_rtol=1e-3, bias_std=0.05)
+    g = torch.Generator().manual_seed(11)
+    B = 37                                              # ragged: not a multiple of any tile
+    state = 0.5 * torch.randn(B, mod.f_len, generator=g)
+    t0 = torch.rand(B, generator=g)
+    ts = torch.stack([t0, t0 + 0.1 + 0.3 * torch.rand(B, generator=g)], 1)
+    with torch.no_grad():
+        want = ref.evolve_state(state, ts)
+        got = mod.evolve_state(state.to(cuda_device), ts.to(cuda_device))
+    mod.check_status()
+    err = ((got.cpu() - want["y_end"]).abs().max() / want["y_end"].abs().max()).item()
+    assert err <= STATE_RTOL, err
+    ns = mod.last_stats[0, 0, :, 0].cpu().long()
+    assert (ns == want["n_steps"]).float().mean().item() >= 0.97, (ns, want["n_steps"])
+    ts3 = torch.cat([ts, ts[:, 1:] + 0.2], 1)
+    with torch.no_grad():
+        both = mod.evolve_state(state.to(cuda_device), ts3.to(cuda_device))
+        second = mod.evolve_state(got, ts3[:, 1:].to(cuda_device))
+    assert torch.equal(both, second)
