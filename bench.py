@@ -44,6 +44,9 @@ def workload_name(b=None):
             f"H={w['H']}, n={w['n']}, L={w['L']} nn.RNN, random-init (DeepVIO rule), BASELINE configs[1]")
 
 
+PRECISION = "fp32"       # set by --precision: "fp32" (FFMA kernel) | "tf32x3" (tensor-core solver, fp32-accurate)
+
+
 def make_opt():
     from types import SimpleNamespace
     w = WORKLOAD
@@ -51,7 +54,7 @@ def make_opt():
                            ode_hidden_dim=w["H"], ode_fn_num_layers=w["n"], ode_activation_fn="tanh",
                            ode_solver=w["solver"], ode_rnn_type=w["rnn"], rnn_num_layers=w["L"],
                            rnn_hidden_dim=1024, rnn_dropout_out=0.0, ode_rtol=w["rtol"], ode_atol=w["atol"],
-                           ode_dt0=w["dt0"])
+                           ode_dt0=w["dt0"], ode_precision=PRECISION)
 
 
 def init_like_deepvio(model, seed=0):
@@ -462,7 +465,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=PRECISION, choices=["fp32", "tf32x3"],
+                    help="odernn_fwd: CUDA-core FFMA kernel, or the tcgen05 3xTF32 solver kernel (fp32-accurate)")
     args = ap.parse_args()
+    globals()["PRECISION"] = args.precision
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -72,7 +72,11 @@ enum {
 enum { ODEVIO_STATUS_OK = 0, ODEVIO_STATUS_MAX_STEPS = 1, ODEVIO_STATUS_INFINITE_NORM = 2,
        ODEVIO_STATUS_CKPT_OVERFLOW = 3 /* training: more solver iterations than cfg.ckpt_loops */ };
 /* arithmetic mode of the vector-field GEMMs */
-enum { ODEVIO_PRECISION_FP32 = 0 };
+enum { ODEVIO_PRECISION_FP32 = 0,    /* CUDA-core FFMA, one persistent kernel per forward */
+       ODEVIO_PRECISION_TF32X3 = 1   /* ODEFunc GEMMs on tcgen05 as 3xTF32 (hi/lo split, fp32-accurate: <= 1e-5 on poses);
+                                        per interval one cluster kernel runs the whole solver loop of every 128-row
+                                        tile (odernn_tc.cu), then the FMA kernel runs the jump + head.  Inference only
+                                        (save_checkpoints = 0), endpoint_dense = 0, trace_steps = 0; D, H multiples of 64 */ };
 
 typedef struct odevio_odernn_cfg {
   int32_t B;            /* sequences */

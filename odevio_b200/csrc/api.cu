@@ -6,6 +6,7 @@
 
 #include "../../include/odevio.h"
 #include "odernn_params.h"
+#include "odernn_tc.h"
 #include "cde_params.h"
 
 namespace odevio {
@@ -143,7 +144,9 @@ int plan_odernn(const odevio_odernn_cfg& c, OdePlan& pl) {
   if (c.activation < 0 || c.activation > ODEVIO_ACT_SOFTPLUS) return ODEVIO_E_ENUM;
   if (c.rnn_type != ODEVIO_RNN_TANH && c.rnn_type != ODEVIO_RNN_GRU) return ODEVIO_E_ENUM;
   if (c.solver < 0 || c.solver > ODEVIO_SOLVER_RK4_38) return ODEVIO_E_ENUM;
-  if (c.precision != ODEVIO_PRECISION_FP32) return ODEVIO_E_ENUM;
+  if (c.precision != ODEVIO_PRECISION_FP32 && c.precision != ODEVIO_PRECISION_TF32X3) return ODEVIO_E_ENUM;
+  // tensor-core solver (odernn_tc.cu): inference, end point rule y1, no step trace
+  if (c.precision == ODEVIO_PRECISION_TF32X3 && (c.save_checkpoints || c.endpoint_dense || c.trace_steps)) return ODEVIO_E_ENUM;
   if (c.rows_per_tile != 0 && c.rows_per_tile != 4 && c.rows_per_tile != 8 && c.rows_per_tile != 16) return ODEVIO_E_SHAPE;
   const bool fixed = c.solver == ODEVIO_SOLVER_RK4 || c.solver == ODEVIO_SOLVER_RK4_38;
   if (fixed && c.substeps < 1) return ODEVIO_E_SHAPE;
@@ -441,6 +444,10 @@ size_t odevio_odernn_workspace_bytes(const odevio_odernn_cfg* cfg) {
   if (!cfg) return 0;
   OdePlan pl;
   if (plan_odernn(*cfg, pl) != 0) return 0;
+  if (cfg->precision == ODEVIO_PRECISION_TF32X3) {
+    const size_t tcb = odernn_tc_workspace_bytes(*cfg);
+    return tcb ? align_up(pl.total_bytes, 256) + tcb : 0;
+  }
   return pl.total_bytes;
 }
 
@@ -483,6 +490,7 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
   p.accept_strict = c.accept_strict; p.floor_factor = c.floor_factor; p.endpoint_dense = c.endpoint_dense;
   p.max_steps = c.max_steps; p.exact_landing = c.exact_landing; p.trace_steps = c.trace_steps;
   p.evolve_only = c.evolve_only ? 1 : 0;
+  p.skip_evolve = 0; p.S_io = c.S; p.i_off = 0;
   if (!make_tableau(c.solver, p.tab)) return ODEVIO_E_ENUM;
 
   // ---- pre-pack weights into the workspace
@@ -548,6 +556,30 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
     p.CK = pl.CK;
   }
 
+  if (c.precision == ODEVIO_PRECISION_TF32X3) {
+    // Per interval: the cluster kernel evolves all L*B rows of the state in place on the tensor cores, then the FMA
+    // kernel runs the interval's jump + head (skip_evolve).  Same stream, no host synchronisation.
+    const size_t tc_off = align_up(pl.total_bytes, 256);
+    if (workspace_bytes <= tc_off) return ODEVIO_E_WORKSPACE;
+    TcEvolve tc;
+    const int prc = tc.prepare(c, p.tab, p.adaptive != 0, w->ode_w, w->ode_b, static_cast<unsigned char*>(workspace) + tc_off,
+                               workspace_bytes - tc_off, stream);
+    if (prc != 0) return prc;
+    const size_t state_bytes = static_cast<size_t>(c.L) * c.B * D * sizeof(float);
+    if (h0) { if (h0 != hT) ODEVIO_CUDA_TRY(cudaMemcpyAsync(hT, h0, state_bytes, cudaMemcpyDeviceToDevice, stream)); }
+    else ODEVIO_CUDA_TRY(cudaMemsetAsync(hT, 0, state_bytes, stream));
+    if (status) ODEVIO_CUDA_TRY(cudaMemsetAsync(status, 0, static_cast<size_t>(c.B) * sizeof(int32_t), stream));
+    p.S = 1; p.skip_evolve = 1; p.S_io = c.S; p.stats = nullptr; p.status = nullptr; p.h0 = hT; p.hT = hT; p.ts = nullptr;
+    for (int i = 0; i < c.S; ++i) {
+      const int erc = tc.evolve(hT, ts, c.S + 1, i, stats, status, stream);
+      if (erc != 0) return erc;
+      if (!c.evolve_only) {
+        p.i_off = i;
+        ODEVIO_CUDA_TRY(launch_odernn_fwd(p, pl.RT, pl.grid, pl.smem_bytes, stream));
+      }
+    }
+    return 0;
+  }
   ODEVIO_CUDA_TRY(launch_odernn_fwd(p, pl.RT, pl.grid, pl.smem_bytes, stream));
   return 0;
 }

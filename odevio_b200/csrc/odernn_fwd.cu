@@ -278,7 +278,7 @@ __device__ __forceinline__ int interval_begin(Ctx<RT>& c, int i) {
     const int r = c.th.ctid;
     const int b = c.tile * RT + (r % RT);
     float t0 = 0.f, t1 = 0.f;
-    if (b < p.B) {
+    if (b < p.B && !p.skip_evolve) {
       t0 = p.ts[static_cast<size_t>(b) * (p.S + 1) + i];
       t1 = p.ts[static_cast<size_t>(b) * (p.S + 1) + i + 1];
     }
@@ -294,6 +294,7 @@ __device__ __forceinline__ int interval_begin(Ctx<RT>& c, int i) {
       run = 1;
     }
     rs.dtstep[r] = rs.dt[r];
+    if (p.skip_evolve) run = 0;          // jump + head only: the tensor-core solver kernel evolved the state (odernn_tc.cu)
     rs.run[r] = run; rs.noteval[r] = run;
   }
   return run;
@@ -328,7 +329,7 @@ __device__ __forceinline__ void assemble_jump_input(Ctx<RT>& c, int i, int l) {
       const int b = c.tile * RT + m;
       float v = 0.f;
       if (b < p.B) {
-        const size_t row = static_cast<size_t>(b) * p.S + i;
+        const size_t row = static_cast<size_t>(b) * p.S_io + p.i_off + i;
         v = (k < p.Dv) ? p.fv[row * p.Dv + k] : p.fi[row * (D - p.Dv) + (k - p.Dv)];
       }
       c.bufA[k * RT + m] = v;
@@ -354,7 +355,7 @@ __device__ __forceinline__ void pose_out(Ctx<RT>& c, int i) {
     const int b = c.tile * RT + m;
     float acc = 0.f;
     for (int k = 0; k < kRegHidden; ++k) acc = fmaf(c.bufA[k * RT + m], p.Wreg1[o * kRegHidden + k], acc);
-    if (b < p.B) p.pose[(static_cast<size_t>(b) * p.S + i) * kPoseDim + o] = acc + p.breg1[o];
+    if (b < p.B) p.pose[(static_cast<size_t>(b) * p.S_io + p.i_off + i) * kPoseDim + o] = acc + p.breg1[o];
   }
 }
 
@@ -565,7 +566,7 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
               const int b = tile * RT + m;
               float v = 0.f;
               if (b < p.B) {
-                const size_t row = static_cast<size_t>(b) * p.S + i;
+                const size_t row = static_cast<size_t>(b) * p.S_io + p.i_off + i;
                 v = (k < p.Dv) ? p.fv[row * p.Dv + k] : p.fi[row * (D - p.Dv) + (k - p.Dv)];
               }
               c.bufA[k * RT + m] = v;

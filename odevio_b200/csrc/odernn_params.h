@@ -33,6 +33,8 @@ struct FwdParams {
   float atol, rtol, dt0, safety, fmin, fmax;
   int accept_strict, floor_factor, endpoint_dense, max_steps, exact_landing, trace_steps;
   int evolve_only;           // PoseODERNN.evolve_state: ODE solves only (no jump / head)
+  int skip_evolve;           // jump + head only (the state was evolved by the tensor-core solver kernel); ts is not read
+  int S_io, i_off;           // features / poses of interval i live at row b * S_io + i_off + i (S_io = S, i_off = 0 normally)
   DevTableau tab;
   // packed weights (K-major [K][N]) and biases
   const float* Wode[kMaxLinears];

@@ -1,0 +1,468 @@
+// Tensor-core ODE solver: PoseODERNN.evolve_state (reference src/models/PoseODERNN.py:70-75) for every
+// (sequence, rnn layer) row of one observation interval, with the ODEFunc GEMMs on tcgen05 (3xTF32,
+// fp32-accurate -- ft_layer.cuh) and the whole solver loop of a 128-row tile inside ONE cluster of 8 CTAs:
+// stage combines, Butcher tableau, per-row error norm, per-row step-size controller (torchode semantics as
+// restated in oracle/torchode_like.py), FSAL -- no host round trip between solver steps.
+//
+//   row g = l * B + b of the [L, B, D] hidden state; a tile = 128 consecutive rows; the cluster's CTAs split every
+//   Linear as an nN x nK grid (ft_layer) and every elementwise pass by FEATURE slice: CTA c owns the `own_nf`
+//   features it finalises in the last Linear, for all 128 rows, thread = row.
+//   * stage vectors K0..K6, Y, Y1 of the tile: per-cluster L2-resident scratch, feature-major [D][128] so that
+//     thread = row accesses are coalesced; every element is only ever touched by its owning CTA;
+//   * stage argument y + dt * sum_j a_ij k_j -> written straight into the tensor core's operand image of layer 0
+//     (fp32, split hi/lo in shared memory by the splitter warps), fence.proxy.async + cluster barrier;
+//   * error norm: thread-local sum over the CTA's features, one 128-float exchange per CTA through L2, summed in
+//     CTA order by every CTA -> all 8 CTAs take identical controller decisions (each keeps the full row state in
+//     shared memory), so the number of cluster barriers is the same everywhere.
+// The jump (nn.RNN / nn.GRU step) and the pose head of the interval run in the FMA kernel with skip_evolve = 1
+// (odernn_fwd.cu): M = B rows there, too few for the tensor core to matter (5 % of the FLOPs).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/odevio.h"
+#include "common.cuh"
+#include "ft_layer.cuh"
+#include "odernn_params.h"
+#include "odernn_tc.h"
+
+namespace odevio {
+
+namespace {
+
+constexpr int TC_NC = 8, TC_KCH = 8;
+constexpr int TC_UNIT = 16;          // features per elementwise unit (thread = row, 4 float4 of the operand image)
+
+struct TcParams {
+  int M, B, L, D, NL, act;
+  int K[FT_MAX_LAYERS], N[FT_MAX_LAYERS], nN[FT_MAX_LAYERS], nK[FT_MAX_LAYERS];
+  const float* Wp[FT_MAX_LAYERS];
+  const float* bias[FT_MAX_LAYERS];
+  float* part; size_t part_floats;
+  float* xa; size_t xa_buf_floats;
+  int ntiles, nraw;
+  uint32_t raw_stage_bytes, op_stage_bytes;
+  // solver
+  DevTableau tab;
+  int adaptive, substeps;
+  float atol, rtol, dt0, safety, fmin, fmax;
+  int accept_strict, floor_factor, max_steps, exact_landing;
+  float* Y;                 // [M][D] row-major hidden state, evolved in place
+  const float* ts; int ts_ld, interval;      // row b: ts[b * ts_ld + interval] -> ts[.. + 1]
+  int* stats;               // [S][L][B][2] (n_steps, n_accepted) or nullptr
+  int* status;              // [B], max over layers
+  float* state; size_t state_floats;         // per cluster: (kMaxStages + 2) x [D][128] + [8][128] norm partials
+};
+
+struct TcRows {      // per-row solver state, replicated in every CTA of the cluster (shared memory)
+  float t[FT_ROWS], dt[FT_ROWS], tend[FT_ROWS], tmin[FT_ROWS], tmax[FT_ROWS];
+  int run[FT_ROWS], upd[FT_ROWS], nsteps[FT_ROWS], nacc[FT_ROWS], status[FT_ROWS];
+  float psum[2][FT_ROWS];
+};
+
+// acc = c0*k0 + c1*k1 + ... left to right, skipping exact zeros (oracle/_weighted_sum; same order as
+// odernn_fwd.cu:wsum4).  The loads of all n stage vectors are issued before the arithmetic chain.
+__device__ __forceinline__ float wsum1(float* const* Kst, const float* coef, int n, size_t off, bool& any) {
+  float k[kMaxStages];
+#pragma unroll
+  for (int j = 0; j < kMaxStages; ++j) k[j] = (j < n && coef[j] != 0.f) ? __ldcg(Kst[j] + off) : 0.f;
+  float acc = 0.f;
+  any = false;
+#pragma unroll
+  for (int j = 0; j < kMaxStages; ++j) {
+    if (j < n && coef[j] != 0.f) {
+      acc = any ? add_(acc, mul_(k[j], coef[j])) : mul_(k[j], coef[j]);
+      any = true;
+    }
+  }
+  return acc;
+}
+
+template <int NC, int KCH>
+__global__ void __launch_bounds__(FT_THREADS, 1)
+odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t raw_full[FT_RAW_STAGES];
+  __shared__ __align__(8) uint64_t raw_empty[FT_RAW_STAGES];
+  __shared__ __align__(8) uint64_t op_ready[FT_OP_STAGES];
+  __shared__ __align__(8) uint64_t op_empty[FT_OP_STAGES];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ TcRows rs;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int cluster_id = blockIdx.x / NC, nclusters = gridDim.x / NC;
+  const DevTableau& tb = p.tab;
+
+  if (tid == 0) {
+    for (int i = 0; i < FT_RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 1); }
+    for (int i = 0; i < FT_OP_STAGES; ++i) { mbar_init(&op_ready[i], 1); mbar_init(&op_empty[i], 1); }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == FT_WARP_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_slot;
+
+  float* xa_cluster = p.xa + static_cast<size_t>(cluster_id) * 4 * p.xa_buf_floats;
+  FtCtx c;
+  c.smem = smem; c.op_base = smem + static_cast<size_t>(p.nraw) * p.raw_stage_bytes;
+  c.raw_full = raw_full; c.raw_empty = raw_empty; c.op_ready = op_ready; c.op_empty = op_empty; c.accum_bar = &accum_bar;
+  c.tmem_d = tmem_d; c.crank = crank; c.nraw = static_cast<uint32_t>(p.nraw);
+  c.raw_stage_bytes = p.raw_stage_bytes; c.op_stage_bytes = p.op_stage_bytes; c.xa_buf_floats = p.xa_buf_floats;
+  c.part = p.part + static_cast<size_t>(cluster_id) * p.part_floats;
+  c.g0 = 0; c.accum_phase = 0; c.tile = 0;
+
+  // ---- feature slice owned by this CTA in every elementwise pass = the columns it finalises in the last Linear
+  const int D = p.D;
+  int own_f0, own_nf;
+  {
+    const int l = p.NL - 1, nN = p.nN[l], nK = p.nK[l];
+    const int cn = static_cast<int>(crank) % nN, ck = static_cast<int>(crank) / nN;
+    const int Nc = p.N[l] / nN;
+    own_nf = Nc / nK;
+    own_f0 = cn * Nc + ck * own_nf;
+  }
+  const int nunits = own_nf / TC_UNIT;
+  const size_t arr = static_cast<size_t>(D) * FT_ROWS;
+  float* const st_base = p.state + static_cast<size_t>(cluster_id) * p.state_floats;
+  float* Kst[kMaxStages];
+#pragma unroll
+  for (int j = 0; j < kMaxStages; ++j) Kst[j] = st_base + j * arr;
+  float* const Yc = st_base + kMaxStages * arr;
+  float* const Y1 = Yc + arr;
+  float* const normpart = Y1 + arr;          // [NC][128]
+
+  const bool epi = warp < FT_EPI_WARPS;
+  const int r = tid & (FT_ROWS - 1), half = (tid >> 7) & 1;
+  const int ns = tb.n_stages;
+
+  for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
+    c.tile = tile;
+    const int row0 = tile * FT_ROWS;
+    const int g = row0 + r;                        // global row of this thread (epilogue warps)
+    const bool valid = g < p.M;
+    const int b = valid ? g % p.B : 0, lyr = valid ? g / p.B : 0;
+
+    // ---- load the tile's state (row-major [M][D]) into the feature-major scratch, own slice
+    if (epi) {
+      for (int u = half; u < nunits; u += 2) {
+        const int f0 = own_f0 + TC_UNIT * u;
+        float v[TC_UNIT];
+        if (valid) {
+          const float4* src = reinterpret_cast<const float4*>(p.Y + static_cast<size_t>(g) * D + f0);
+#pragma unroll
+          for (int q = 0; q < TC_UNIT / 4; ++q) { const float4 t4 = src[q]; v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w; }
+        } else {
+#pragma unroll
+          for (int q = 0; q < TC_UNIT; ++q) v[q] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < TC_UNIT; ++q) __stcg(Yc + static_cast<size_t>(f0 + q) * FT_ROWS + r, v[q]);
+      }
+    }
+    // ---- per-row solver state (PoseODERNN.py:70-75; odernn_fwd.cu:interval_begin)
+    int run = 0;
+    if (tid < FT_ROWS) {
+      float t0 = 0.f, t1 = 0.f;
+      if (valid) {
+        t0 = p.ts[static_cast<size_t>(b) * p.ts_ld + p.interval];
+        t1 = p.ts[static_cast<size_t>(b) * p.ts_ld + p.interval + 1];
+      }
+      rs.t[r] = t0; rs.tend[r] = t1;
+      rs.tmin[r] = fminf(t0, t1); rs.tmax[r] = fmaxf(t0, t1);
+      rs.nsteps[r] = 0; rs.nacc[r] = 0; rs.upd[r] = 0; rs.status[r] = 0;
+      if (p.adaptive) {
+        rs.dt[r] = fminf(fmaxf(p.dt0, sub_(rs.tmin[r], t0)), sub_(rs.tmax[r], t0));
+        run = (valid && t0 < t1) ? 1 : 0;
+      } else {
+        rs.dt[r] = __fdiv_rn(sub_(t1, t0), static_cast<float>(p.substeps));
+        run = valid ? 1 : 0;
+      }
+      rs.run[r] = run;
+    }
+    int any_running = __syncthreads_or(run);
+    int loops = 0;
+    bool have_k0 = false;
+
+    while (any_running) {
+      ++loops;
+      for (int st = (tb.fsal && have_k0) ? 1 : 0; st < ns; ++st) {
+        // ---- stage argument -> layer-0 operand image (own feature slice, all 128 rows)
+        if (epi) {
+          const float dt = rs.dt[r];
+          for (int u = half; u < nunits; u += 2) {
+            const int f0 = own_f0 + TC_UNIT * u;
+            float v[TC_UNIT];
+#pragma unroll
+            for (int q = 0; q < TC_UNIT; ++q) {
+              const size_t off = static_cast<size_t>(f0 + q) * FT_ROWS + r;
+              float y = __ldcg(Yc + off);
+              if (st > 0) {
+                bool any;
+                const float acc = wsum1(Kst, tb.a[st], st, off, any);
+                if (any) y = add_(y, mul_(dt, acc));
+              }
+              v[q] = y;
+            }
+#pragma unroll
+            for (int q = 0; q < TC_UNIT / 4; ++q)
+              *reinterpret_cast<float4*>(xa_cluster + xa_offset<KCH>(r, f0 + 4 * q)) =
+                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores -> bulk-copy (async) proxy of all CTAs
+        }
+        __syncwarp();
+        cluster_sync_all();
+        // ---- ODEFunc (src/models/ODEFunc.py:38-39) on the tensor cores; last Linear (+ Tanh) -> K[st]
+        for (int l = 0; l < p.NL; ++l) {
+          FtLayer Ld;
+          Ld.K = p.K[l]; Ld.N = p.N[l]; Ld.nN = p.nN[l]; Ld.nK = p.nK[l]; Ld.stamp = l;
+          const bool last = l == p.NL - 1;
+          Ld.act = last ? ACT_TANH : p.act;
+          Ld.out_mode = last ? FT_OUT_FEATURE_MAJOR : FT_OUT_OPERAND;
+          Ld.Wp = p.Wp[l]; Ld.Wlo = nullptr; Ld.bias = p.bias[l];
+          Ld.a_src = xa_cluster + static_cast<size_t>(l & 1) * 2 * p.xa_buf_floats;
+          Ld.nx = xa_cluster + static_cast<size_t>((l + 1) & 1) * 2 * p.xa_buf_floats;
+          Ld.out = Kst[st]; Ld.M = p.M; Ld.row0 = row0;
+          ft_layer<NC, KCH, true>(c, Ld);
+        }
+      }
+      have_k0 = true;
+
+      if (p.adaptive) {
+        // ---- y1, embedded error, this CTA's share of the per-row error norm (odernn_fwd.cu:error_pass)
+        if (epi) {
+          const float dt = rs.dt[r];
+          float sum = 0.f;
+          for (int u = half; u < nunits; u += 2) {
+            const int f0 = own_f0 + TC_UNIT * u;
+#pragma unroll 4
+            for (int q = 0; q < TC_UNIT; ++q) {
+              const size_t off = static_cast<size_t>(f0 + q) * FT_ROWS + r;
+              const float y0 = __ldcg(Yc + off);
+              bool any;
+              float acc = tb.ssal ? wsum1(Kst, tb.a[ns - 1], ns - 1, off, any) : wsum1(Kst, tb.b, ns, off, any);
+              const float y1 = any ? add_(y0, mul_(dt, acc)) : y0;
+              __stcg(Y1 + off, y1);
+              if (tb.has_err) {
+                acc = wsum1(Kst, tb.e, ns, off, any);
+                const float e = mul_(dt, acc);
+                const float bound = add_(p.atol, mul_(p.rtol, fmaxf(fabsf(y0), fabsf(y1))));
+                const float q2 = __fdiv_rn(e, bound);
+                sum = fmaf(q2, q2, sum);
+              }
+            }
+          }
+          rs.psum[half][r] = sum;
+          named_bar_sync(1, FT_EPI_WARPS * 32);
+          if (tid < FT_ROWS) __stcg(normpart + static_cast<size_t>(crank) * FT_ROWS + r, add_(rs.psum[0][r], rs.psum[1][r]));
+        }
+        __syncwarp();
+        cluster_sync_all();
+        // ---- per-row controller, identical in every CTA (odernn_fwd.cu:controller; torchode IntegralController)
+        run = 0;
+        if (tid < FT_ROWS) {
+          run = rs.run[r];
+          const float dt = rs.dt[r];
+          float t = rs.t[r];
+          const float tend = rs.tend[r];
+          bool accept = true, finite = true;
+          float dt_next = dt;
+          if (tb.has_err) {
+            float total = 0.f;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) total = add_(total, __ldcg(normpart + k * FT_ROWS + r));
+            const float ratio = sqrtf(__fdiv_rn(total, static_cast<float>(D)));
+            finite = isfinite(ratio);
+            accept = p.accept_strict ? (ratio < 1.0f) : (ratio <= 1.0f);
+            float factor = mul_(p.safety, powf(ratio, tb.exponent));
+            factor = fminf(fmaxf(factor, p.fmin), p.fmax);
+            if (p.floor_factor && accept) factor = fmaxf(factor, 1.0f);
+            dt_next = mul_(dt, factor);
+          }
+          const int upd = (accept && run) ? 1 : 0;
+          rs.nsteps[r] += run;
+          rs.nacc[r] += upd;
+          const bool lands = p.exact_landing && dt >= sub_(tend, t);
+          t = upd ? (lands ? tend : add_(t, dt)) : t;
+          rs.upd[r] = upd;
+          if (run && !finite) rs.status[r] = max(rs.status[r], 2);
+          run = (run && t < tend && finite) ? 1 : 0;
+          if (run && loops >= p.max_steps) { rs.status[r] = max(rs.status[r], 1); run = 0; }
+          float dtn = run ? dt_next : dt;
+          dtn = fminf(fmaxf(dtn, sub_(rs.tmin[r], t)), sub_(rs.tmax[r], t));
+          rs.t[r] = t;
+          rs.dt[r] = dtn;
+          rs.run[r] = run;
+        }
+        any_running = __syncthreads_or(run);
+        // ---- commit: accepted rows take y1; FSAL carry (end point rule "y1": exact landing makes y1 the value at t_end)
+        if (epi && rs.upd[r]) {
+          for (int u = half; u < nunits; u += 2) {
+            const int f0 = own_f0 + TC_UNIT * u;
+#pragma unroll
+            for (int q = 0; q < TC_UNIT; ++q) {
+              const size_t off = static_cast<size_t>(f0 + q) * FT_ROWS + r;
+              __stcg(Yc + off, __ldcg(Y1 + off));
+              if (tb.fsal) __stcg(Kst[0] + off, __ldcg(Kst[ns - 1] + off));
+            }
+          }
+        }
+      } else {
+        // ---- fixed step: Y <- y0 + dt * sum b_j k_j for every row (odernn_fwd.cu:fixed_commit)
+        if (epi) {
+          const float dt = rs.dt[r];
+          for (int u = half; u < nunits; u += 2) {
+            const int f0 = own_f0 + TC_UNIT * u;
+#pragma unroll 4
+            for (int q = 0; q < TC_UNIT; ++q) {
+              const size_t off = static_cast<size_t>(f0 + q) * FT_ROWS + r;
+              const float y0 = __ldcg(Yc + off);
+              bool any;
+              const float acc = wsum1(Kst, tb.b, ns, off, any);
+              __stcg(Yc + off, any ? add_(y0, mul_(dt, acc)) : y0);
+            }
+          }
+          if (tid < FT_ROWS && valid) { rs.nsteps[r] += 1; rs.nacc[r] += 1; }
+        }
+        any_running = loops < p.substeps;
+      }
+    }
+
+    // ---- evolved state back to [M][D]; stats / status of the interval
+    __syncthreads();
+    if (epi && valid) {
+      for (int u = half; u < nunits; u += 2) {
+        const int f0 = own_f0 + TC_UNIT * u;
+        float v[TC_UNIT];
+#pragma unroll
+        for (int q = 0; q < TC_UNIT; ++q) v[q] = __ldcg(Yc + static_cast<size_t>(f0 + q) * FT_ROWS + r);
+        float4* dst = reinterpret_cast<float4*>(p.Y + static_cast<size_t>(g) * D + f0);
+#pragma unroll
+        for (int q = 0; q < TC_UNIT / 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      if (crank == 0 && tid < FT_ROWS) {
+        if (p.stats) {
+          int* sp = p.stats + ((static_cast<size_t>(p.interval) * p.L + lyr) * p.B + b) * 2;
+          sp[0] = rs.nsteps[r]; sp[1] = rs.nacc[r];
+        }
+        if (p.status && rs.status[r]) atomicMax(p.status + b, rs.status[r]);
+      }
+    }
+    __syncthreads();
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  cluster_sync_all();
+  if (warp == FT_WARP_MMA) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ host side
+
+struct TcEvolve::Impl {
+  FtPlan pl;
+  TcParams prm;
+  size_t state_floats, off_state, total_bytes;
+};
+
+static int tc_plan(const odevio_odernn_cfg& c, FtPlan& pl, size_t& off_state, size_t& state_floats, size_t& total_bytes) {
+  const long long M = static_cast<long long>(c.L) * c.B;
+  if (M <= 0 || M > 0x7fffffffLL) return ODEVIO_E_SHAPE;
+  const int rc = ft_plan(static_cast<int>(M), c.D, c.H, c.n_hidden, pl, /*force_split=*/true);
+  if (rc != 0) return rc;
+  // elementwise units of 16 features inside the slice every CTA finalises in the last Linear
+  const int l = pl.NL - 1;
+  const int own_nf = pl.N[l] / pl.nN[l] / pl.nK[l];
+  if (own_nf % TC_UNIT || c.D % 4) return ODEVIO_E_SHAPE;
+  // the solver kernel must co-reside: one cluster per tile or a persistent loop over tiles (nclusters from occupancy)
+  state_floats = (static_cast<size_t>(kMaxStages + 2) * c.D + TC_NC) * FT_ROWS;
+  state_floats = (state_floats + 63) / 64 * 64;
+  off_state = (pl.total_bytes / sizeof(float) + 63) / 64 * 64;
+  total_bytes = (off_state + state_floats * static_cast<size_t>(pl.nclusters)) * sizeof(float);
+  return 0;
+}
+
+size_t odernn_tc_workspace_bytes(const odevio_odernn_cfg& c) {
+  FtPlan pl;
+  size_t off_state, state_floats, total;
+  if (tc_plan(c, pl, off_state, state_floats, total) != 0) return 0;
+  return total;
+}
+
+TcEvolve::TcEvolve() : impl(nullptr) {}
+TcEvolve::~TcEvolve() { delete impl; }
+
+int TcEvolve::prepare(const odevio_odernn_cfg& c, const DevTableau& tab, bool adaptive, const float* const* ode_w,
+                      const float* const* ode_b, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  delete impl;
+  impl = new Impl();
+  int rc = tc_plan(c, impl->pl, impl->off_state, impl->state_floats, impl->total_bytes);
+  if (rc != 0) return rc;
+  if (workspace_bytes < impl->total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ODEVIO_E_WORKSPACE;
+  FtPlan& pl = impl->pl;
+  float* ws = static_cast<float*>(workspace);
+  TcParams& p = impl->prm;
+  memset(&p, 0, sizeof(p));
+  p.M = c.L * c.B; p.B = c.B; p.L = c.L; p.D = c.D; p.NL = pl.NL; p.act = c.activation;
+  for (int l = 0; l < pl.NL; ++l) {
+    if (!ode_w[l] || !ode_b[l]) return ODEVIO_E_NULL;
+    p.K[l] = pl.K[l]; p.N[l] = pl.N[l]; p.nN[l] = pl.nN[l]; p.nK[l] = pl.nK[l];
+    ft_pack_weight_kernel<<<296, 256, 0, stream>>>(ode_w[l], pl.N[l], pl.K[l], pl.nN[l], pl.KCH, ws + pl.off_w[l], nullptr);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    p.Wp[l] = ws + pl.off_w[l]; p.bias[l] = ode_b[l];
+  }
+  p.xa = ws + pl.off_xa; p.xa_buf_floats = pl.xa_buf_floats;
+  p.part = ws + pl.off_part; p.part_floats = pl.part_floats;
+  p.ntiles = pl.ntiles; p.nraw = pl.nraw; p.raw_stage_bytes = pl.raw_stage_bytes; p.op_stage_bytes = pl.op_stage_bytes;
+  p.tab = tab; p.adaptive = adaptive ? 1 : 0; p.substeps = c.substeps;
+  p.atol = c.atol; p.rtol = c.rtol; p.dt0 = c.dt0; p.safety = c.safety; p.fmin = c.factor_min; p.fmax = c.factor_max;
+  p.accept_strict = c.accept_strict; p.floor_factor = c.floor_factor; p.max_steps = c.max_steps; p.exact_landing = c.exact_landing;
+  p.state = ws + impl->off_state; p.state_floats = impl->state_floats;
+  return 0;
+}
+
+int TcEvolve::evolve(float* Y, const float* ts, int ts_ld, int interval, int* stats, int* status, cudaStream_t stream) {
+  if (!impl) return ODEVIO_E_NULL;
+  TcParams p = impl->prm;
+  FtPlan& pl = impl->pl;
+  p.Y = Y; p.ts = ts; p.ts_ld = ts_ld; p.interval = interval; p.stats = stats; p.status = status;
+  auto kern = odernn_tc_evolve_kernel<TC_NC, TC_KCH>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem_bytes));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.blockDim = dim3(FT_THREADS); lc.dynamicSmemBytes = pl.smem_bytes; lc.stream = stream;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = TC_NC; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  lc.attrs = &at; lc.numAttrs = 1;
+  int nclusters = pl.nclusters;
+  lc.gridDim = dim3(nclusters * TC_NC);
+  int maxc = 0;
+  if (cudaOccupancyMaxActiveClusters(&maxc, kern, &lc) == cudaSuccess && maxc > 0) {
+    if (nclusters > maxc) nclusters = maxc;
+  } else {
+    cudaGetLastError();
+  }
+  lc.gridDim = dim3(nclusters * TC_NC);
+  e = cudaLaunchKernelEx(&lc, kern, p);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+}  // namespace odevio

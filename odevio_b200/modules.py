@@ -220,6 +220,10 @@ class PoseODERNN(nn.Module):
         self.collect_stats = bool(getattr(opt, "ode_collect_stats", True))
         self.trace_steps = int(getattr(opt, "ode_trace_steps", 0))   # diagnostic: (dt, ratio) of first T steps
         self.ckpt_loops = int(getattr(opt, "ode_ckpt_loops", 0))     # training: stored solver iterations per interval (0 = 16)
+        # "fp32": CUDA-core FFMA kernel; "tf32x3": ODEFunc GEMMs on tcgen05 (3xTF32, fp32-accurate), inference only
+        self.precision = getattr(opt, "ode_precision", "fp32")
+        if self.precision not in _lib.PRECISION:
+            raise ValueError(f"Precision {self.precision} not supported")
         self.last_stats = None      # int32 [S, L, B, 2] = (n_steps, n_accepted) of the last forward
         self.last_trace = None      # float32 [S, L, B, T, 2] = (dt, error ratio) when trace_steps = T > 0
         self.last_status = None     # int32 [B]
@@ -262,6 +266,7 @@ class PoseODERNN(nn.Module):
         cfg.max_steps = self.max_steps
         cfg.rows_per_tile = self.rows_per_tile
         cfg.trace_steps = self.trace_steps
+        cfg.precision = _lib.PRECISION[self.precision]
         return cfg
 
     def _weights(self, fuse_in_kernel=False):
@@ -335,6 +340,7 @@ class PoseODERNN(nn.Module):
         cfg = self._cfg(B, S)
         ckpt, ckpt_bytes = None, 0
         if save_ckpt:
+            cfg.precision = _lib.PRECISION["fp32"]          # training runs the FMA kernels (checkpointed forward + fused backward)
             cfg.save_checkpoints = 1
             cfg.ckpt_loops = self.ckpt_loops
             if cfg.rows_per_tile == 16:
