@@ -44,7 +44,7 @@ def workload_name(b=None):
             f"H={w['H']}, n={w['n']}, L={w['L']} nn.RNN, random-init (DeepVIO rule), BASELINE configs[1]")
 
 
-PRECISION = "fp32"       # set by --precision: "fp32" (FFMA kernel) | "tf32x3" (tensor-core solver, fp32-accurate)
+PRECISION = "tf32x3"     # set by --precision: "tf32x3" (tensor-core solver, 3xTF32 = fp32-accurate; default) | "fp32" (FFMA kernel)
 
 
 def make_opt():
@@ -264,6 +264,22 @@ def run_ours(args, rank, world, local_rank):
         stats = model.last_stats.clone()
         status = int(model.last_status.max().item())
 
+        # ---- dominant kernel's average launch duration, live: CUDA events around every solver launch on its stream
+        tc_kernel_ms, tc_launches, tc_geo = None, 0, None
+        if PRECISION == "tf32x3":
+            import ctypes as C
+            lib.odevio_debug_tc_timing(1, None, None)
+            for _ in range(args.steps):
+                flush.fill_(1)
+                model(fv, fi, ts)
+            torch.cuda.synchronize(dev)
+            tot, cnt = C.c_float(0), C.c_int32(0)
+            lib.odevio_debug_tc_timing(-1, C.byref(tot), C.byref(cnt))
+            lib.odevio_debug_tc_timing(0, None, None)
+            geo = (C.c_int32 * 3)()
+            lib.odevio_debug_tc_geometry(geo)
+            tc_kernel_ms, tc_launches, tc_geo = tot.value, cnt.value, list(geo)
+
         # ---- end to end through the public API from pinned host buffers
         pose_h = torch.empty(B, S, 6, dtype=torch.float32).pin_memory()
         for _ in range(2):
@@ -298,19 +314,51 @@ def run_ours(args, rank, world, local_rank):
         prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(prof):
             with open(prof) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_launch")
-        roofline = {
-            "bound": "tensor", "kernel": "odernn_fwd_kernel<8,2>",
-            "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved_tf / peaks["bf16_tflops_sustained"], "peak_source": peak_src + ", sustained bf16",
-            "traffic": traffic,
-            "algorithmic_flops_per_launch": flops, "vector_field_evals_per_launch": evals,
-            "note": "fp32 parity mode runs the GEMMs on CUDA-core FFMA, so the pipe that bounds it is fp32 FMA "
-                    "(fma_fp32 below, peak measured live by odevio_microbench_ffma); the tensor-pipe fraction is "
-                    "reported against the measured bf16 peak as the contract asks",
-            "fma_fp32": {"achieved": achieved_tf, "peak": fma_peak,
-                         "frac": (achieved_tf / fma_peak) if fma_peak else None, "unit": "TFLOP/s"},
-        }
+                traffic = json.load(fh).get("dram_bytes_per_launch_tc" if PRECISION == "tf32x3" else "dram_bytes_per_launch")
+        n_side = 0
+        if PRECISION == "tf32x3":
+            # the cluster kernel integrates rows g = l * B + b < tc_rows of every interval; the rest (side launch) is FFMA
+            D_, H_, n_ = w["v_f_len"] + w["i_f_len"], w["H"], w["n"]
+            f_ode = 2 * (D_ * H_ + (n_ - 1) * H_ * H_ + H_ * D_)
+            tc_rows = tc_geo[2]
+            n_side = 1 if tc_rows < w["L"] * B else 0
+            st_rows = stats.cpu()[..., 0].reshape(S, w["L"] * B)[:, :tc_rows].double()
+            tc_evals = (6.0 * st_rows + (st_rows > 0).double()).sum().item()
+            per_launch_ms = tc_kernel_ms / tc_launches
+            tc_flops_per_launch = tc_evals * f_ode / S
+            tc_achieved = tc_flops_per_launch / (per_launch_ms * 1e-3) / 1e12
+            tf32x3_peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0
+            roofline = {
+                "bound": "tensor", "kernel": "odernn_tc_evolve_kernel<8,8>",
+                "achieved": tc_achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": tc_achieved / peaks["bf16_tflops_sustained"], "peak_source": peak_src + ", sustained bf16",
+                "traffic": traffic,
+                "algorithmic_flops_per_launch": tc_flops_per_launch, "launch_ms": per_launch_ms,
+                "launches_per_step": S, "kernel_share_of_step": tc_kernel_ms / args.steps / ms_per_step,
+                "clusters": tc_geo[0], "max_coresident_clusters": tc_geo[1], "rows_in_cluster_kernel": tc_rows,
+                "rows_in_ffma_side_launch": w["L"] * B - tc_rows,
+                "whole_step": {"achieved": achieved_tf, "algorithmic_flops": flops, "vector_field_evals": evals},
+                "tensor_3xtf32": {"achieved": tc_achieved, "peak": tf32x3_peak, "frac": tc_achieved / tf32x3_peak,
+                                  "unit": "TFLOP/s",
+                                  "note": "fp32 parity needs 3 TF32 MMAs per product (hi*hi, lo*hi, hi*lo) and TF32 runs at half "
+                                          "the bf16 rate: the fp32-accurate tensor ceiling is bf16 peak / 6"},
+                "note": "launch duration measured live with CUDA events around every solver launch on its stream "
+                        "(odevio_debug_tc_timing) in extra un-profiled forwards after the timed region; latency-bound: "
+                        "15 clusters x 8 CTAs each walk one 128-row tile through ~36 dependent ODEFunc evaluations per launch",
+            }
+        else:
+            roofline = {
+                "bound": "tensor", "kernel": "odernn_fwd_kernel<8,2>",
+                "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved_tf / peaks["bf16_tflops_sustained"], "peak_source": peak_src + ", sustained bf16",
+                "traffic": traffic,
+                "algorithmic_flops_per_launch": flops, "vector_field_evals_per_launch": evals,
+                "note": "fp32 parity mode runs the GEMMs on CUDA-core FFMA, so the pipe that bounds it is fp32 FMA "
+                        "(fma_fp32 below, peak measured live by odevio_microbench_ffma); the tensor-pipe fraction is "
+                        "reported against the measured bf16 peak as the contract asks",
+                "fma_fp32": {"achieved": achieved_tf, "peak": fma_peak,
+                             "frac": (achieved_tf / fma_peak) if fma_peak else None, "unit": "TFLOP/s"},
+            }
         n_prepack = (w["n"] + 1) + w["L"] * 3 + 1
         cpu_rate, cpu_sec, cpu_threads = cpu_oracle_rate(steps=5, warmup=1, B=CPU_SAMPLE_B) if world == 1 else (None, None, None)
         line = {
@@ -320,12 +368,16 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": workload_name(), "global_batch": world * B,
                        "parallelism": f"independent sequences sharded over {world} GPU(s), no data-path collective",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-                       "mean_solver_steps_per_interval": stats[..., 0].float().mean().item()},
+                       "mean_solver_steps_per_interval": stats[..., 0].float().mean().item(),
+                       "precision": PRECISION + (" (ODEFunc GEMMs on tcgen05 as 3xTF32, fp32-accurate; jump/head and the "
+                                                 "rows beyond the co-resident clusters on FFMA)" if PRECISION == "tf32x3" else
+                                                 " (CUDA-core FFMA)")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": fv_h.numel() * 4 + fi_h.numel() * 4 + ts_h.numel() * 4,
                     "d2h_bytes_per_step": pose_h.numel() * 4, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": (n_prepack + 1) * args.steps,
+            "gpu_launches": ((n_prepack + 1) if PRECISION == "fp32" else
+                             (n_prepack + (w["n"] + 1) + S * (2 + n_side))) * args.steps,
             "roofline": roofline,
         }
         if cpu_rate is not None:

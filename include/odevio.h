@@ -317,6 +317,17 @@ ODEVIO_API int32_t odevio_mlp_forward(int32_t M, int32_t n_linears, const int32_
 ODEVIO_API int32_t odevio_microbench_ffma(int32_t iters, int32_t blocks, float* sink, double* flops_out,
                                           void* stream);
 
+/* Diagnostics: out[0] = clusters launched, out[1] = co-resident cluster maximum (cudaOccupancyMaxActiveClusters),
+ * out[2] = rows taken by the cluster kernel (the rest ran in the FMA side launch) of the last ODEVIO_PRECISION_TF32X3
+ * solver launch of this process.  out: int32[3] (HOST). */
+ODEVIO_API int32_t odevio_debug_tc_geometry(int32_t* out);
+/* Development (-DODEVIO_FT_TIMELINE builds): 64 clock64 stamps of cluster 0 / CTA 0 / tile 0 of the last solver iteration. */
+ODEVIO_API int32_t odevio_debug_tc_timeline(long long* host_dst);
+/* Measurement hook: enable = 1 / 0 switches CUDA-event timing of every ODEVIO_PRECISION_TF32X3 solver launch on / off
+ * (events on the launching stream); enable = -1 synchronises and returns the summed kernel duration (ms, HOST) and
+ * the number of launches since the last read in *total_ms / *launches.  Not thread-safe; used by bench.py. */
+ODEVIO_API int32_t odevio_debug_tc_timing(int32_t enable, float* total_ms, int32_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

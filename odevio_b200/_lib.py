@@ -127,6 +127,10 @@ def load():
     lib.odevio_mlp_forward.restype = C.c_int32
     lib.odevio_mlp_forward.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                        C.POINTER(_FP), C.POINTER(_FP), _FP, _FP, _FP]
+    lib.odevio_debug_tc_geometry.restype = C.c_int32
+    lib.odevio_debug_tc_geometry.argtypes = [C.POINTER(C.c_int32)]
+    lib.odevio_debug_tc_timing.restype = C.c_int32
+    lib.odevio_debug_tc_timing.argtypes = [C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.odevio_microbench_ffma.restype = C.c_int32
     lib.odevio_microbench_ffma.argtypes = [C.c_int32, C.c_int32, _FP, C.POINTER(C.c_double), _FP]
     if lib.odevio_version() != ABI_VERSION:

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/odevio.h"
 #include "odernn_params.h"
 #include "odernn_tc.h"
@@ -405,6 +407,32 @@ int plan_cde(const odevio_cde_cfg& c, CdePlan& pl) {
     if (_e != cudaSuccess) return static_cast<int32_t>(_e);     \
   } while (0)
 
+// ---- tensor-core mode: rows the cluster kernel cannot take in full rounds run concurrently in the FMA kernel
+constexpr int kSideRT = 8;      // sequences (= rows, L = 1) per CTA of the side launch
+size_t tc_side_scratch_bytes(const odevio_odernn_cfg& c, int nsm) {
+  return align_up(static_cast<size_t>(kMaxStages + 2) * c.D * kSideRT, 64) * sizeof(float) * static_cast<size_t>(nsm);
+}
+
+// Helper stream + fork/join events per device, created on first use (the only persistent objects of the library).
+struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+int side_stream(SideStream** out) {
+  static std::mutex mu;
+  static SideStream table[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (dev < 0 || dev >= 64) return ODEVIO_E_DEVICE;
+  std::lock_guard<std::mutex> lock(mu);
+  SideStream& t = table[dev];
+  if (!t.stream) {
+    if ((e = cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking)) != cudaSuccess) return static_cast<int>(e);
+    if ((e = cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming)) != cudaSuccess) return static_cast<int>(e);
+    if ((e = cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming)) != cudaSuccess) return static_cast<int>(e);
+  }
+  *out = &t;
+  return 0;
+}
+
 }  // namespace
 }  // namespace odevio
 
@@ -446,7 +474,7 @@ size_t odevio_odernn_workspace_bytes(const odevio_odernn_cfg* cfg) {
   if (plan_odernn(*cfg, pl) != 0) return 0;
   if (cfg->precision == ODEVIO_PRECISION_TF32X3) {
     const size_t tcb = odernn_tc_workspace_bytes(*cfg);
-    return tcb ? align_up(pl.total_bytes, 256) + tcb : 0;
+    return tcb ? align_up(pl.total_bytes, 256) + align_up(tcb, 256) + tc_side_scratch_bytes(*cfg, pl.nsm) : 0;
   }
   return pl.total_bytes;
 }
@@ -491,6 +519,7 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
   p.max_steps = c.max_steps; p.exact_landing = c.exact_landing; p.trace_steps = c.trace_steps;
   p.evolve_only = c.evolve_only ? 1 : 0;
   p.skip_evolve = 0; p.S_io = c.S; p.i_off = 0;
+  p.full_B = 0; p.full_L = 0; p.row_off = 0; p.ts_ld = c.S + 1;
   if (!make_tableau(c.solver, p.tab)) return ODEVIO_E_ENUM;
 
   // ---- pre-pack weights into the workspace
@@ -560,19 +589,68 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
     // Per interval: the cluster kernel evolves all L*B rows of the state in place on the tensor cores, then the FMA
     // kernel runs the interval's jump + head (skip_evolve).  Same stream, no host synchronisation.
     const size_t tc_off = align_up(pl.total_bytes, 256);
-    if (workspace_bytes <= tc_off) return ODEVIO_E_WORKSPACE;
+    const size_t tc_bytes = align_up(odernn_tc_workspace_bytes(c), 256);
+    const size_t side_bytes = tc_side_scratch_bytes(c, pl.nsm);
+    if (tc_bytes == 0) return ODEVIO_E_SHAPE;
+    if (workspace_bytes < tc_off + tc_bytes + side_bytes) return ODEVIO_E_WORKSPACE;
     TcEvolve tc;
     const int prc = tc.prepare(c, p.tab, p.adaptive != 0, w->ode_w, w->ode_b, static_cast<unsigned char*>(workspace) + tc_off,
-                               workspace_bytes - tc_off, stream);
+                               tc_bytes, stream);
     if (prc != 0) return prc;
     const size_t state_bytes = static_cast<size_t>(c.L) * c.B * D * sizeof(float);
     if (h0) { if (h0 != hT) ODEVIO_CUDA_TRY(cudaMemcpyAsync(hT, h0, state_bytes, cudaMemcpyDeviceToDevice, stream)); }
     else ODEVIO_CUDA_TRY(cudaMemsetAsync(hT, 0, state_bytes, stream));
     if (status) ODEVIO_CUDA_TRY(cudaMemsetAsync(status, 0, static_cast<size_t>(c.B) * sizeof(int32_t), stream));
+
+    // Row split.  A B200 holds 15-16 clusters of 8 CTAs at once; every further 128-row tile would cost a whole extra
+    // round of the latency-bound cluster kernel.  The cluster kernel therefore takes full rounds only, and a remainder
+    // that fits one wave of the FMA kernel on the SMs the clusters leave idle runs there, concurrently (helper stream).
+    const int M = c.L * c.B;
+    const int ntiles_tc = (M + 127) / 128, maxc = tc.max_clusters();
+    int tc_rows = M, side_rows = 0;
+    if (maxc > 0 && ntiles_tc > maxc && ntiles_tc % maxc != 0) {
+      const int full_rows = (ntiles_tc / maxc) * maxc * 128;
+      const int idle_sms = pl.nsm - maxc * 8;
+      if (M - full_rows <= idle_sms * kSideRT) { tc_rows = full_rows; side_rows = M - full_rows; }
+    }
+    FwdParams ps = p;          // side launch: evolve_only on rows [tc_rows, M) as an L = 1 problem
+    OdePlan pls;
+    SideStream* side = nullptr;
+    if (side_rows > 0) {
+      odevio_odernn_cfg cs = c;
+      // 8-row tiles; when the rows allow it as 2 row blocks of 4 (an "L = 2" problem of side_rows / 2 sequences): 256
+      // consumer threads per CTA instead of 128 (measured: 46.9 vs 50.1 ms per configs[1] forward)
+      const bool two = side_rows % 8 == 0;
+      cs.L = two ? 2 : 1; cs.B = two ? side_rows / 2 : side_rows; cs.rows_per_tile = two ? 4 : kSideRT;
+      cs.S = 1; cs.evolve_only = 1; cs.precision = ODEVIO_PRECISION_FP32;
+      const int src = plan_odernn(cs, pls);
+      if (src != 0) return src;
+      const int ssrc = side_stream(&side);
+      if (ssrc != 0) return ssrc;
+      ps.B = cs.B; ps.L = cs.L; ps.S = 1; ps.evolve_only = 1; ps.skip_evolve = 0;
+      ps.full_B = c.B; ps.full_L = c.L; ps.row_off = tc_rows; ps.ts_ld = c.S + 1; ps.ts = ts;
+      ps.h0 = hT + static_cast<size_t>(tc_rows) * D; ps.hT = hT + static_cast<size_t>(tc_rows) * D;
+      ps.stats = stats; ps.status = status; ps.pose = nullptr; ps.fv = nullptr; ps.fi = nullptr; ps.Wfuse = nullptr;
+      ps.scratch = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + tc_off + tc_bytes);
+      ps.scratch_floats_per_cta = pls.scratch_floats_per_cta;
+      ps.ntiles = pls.ntiles; ps.nst = pls.nst;
+      ps.bufA_floats = static_cast<int>(pls.bufA_floats); ps.bufB_floats = static_cast<int>(pls.bufB_floats);
+      ps.stage_floats = static_cast<int>(pls.stage_floats);
+    }
     p.S = 1; p.skip_evolve = 1; p.S_io = c.S; p.stats = nullptr; p.status = nullptr; p.h0 = hT; p.hT = hT; p.ts = nullptr;
     for (int i = 0; i < c.S; ++i) {
-      const int erc = tc.evolve(hT, ts, c.S + 1, i, stats, status, stream);
+      if (side) {
+        ODEVIO_CUDA_TRY(cudaEventRecord(side->fork, stream));
+        ODEVIO_CUDA_TRY(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      }
+      const int erc = tc.evolve(hT, tc_rows, ts, c.S + 1, i, stats, status, stream);      // clusters first: they need whole GPCs
       if (erc != 0) return erc;
+      if (side) {
+        ps.i_off = i;
+        ODEVIO_CUDA_TRY(launch_odernn_fwd(ps, pls.RT, pls.grid, pls.smem_bytes, side->stream));
+        ODEVIO_CUDA_TRY(cudaEventRecord(side->join, side->stream));
+        ODEVIO_CUDA_TRY(cudaStreamWaitEvent(stream, side->join, 0));
+      }
       if (!c.evolve_only) {
         p.i_off = i;
         ODEVIO_CUDA_TRY(launch_odernn_fwd(p, pl.RT, pl.grid, pl.smem_bytes, stream));
@@ -582,6 +660,28 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
   }
   ODEVIO_CUDA_TRY(launch_odernn_fwd(p, pl.RT, pl.grid, pl.smem_bytes, stream));
   return 0;
+}
+
+// development only: out[0] = clusters launched, out[1] = co-resident maximum, out[2] = rows of the last tensor-core solver launch
+int32_t odevio_debug_tc_geometry(int32_t* out) {
+  if (!out) return ODEVIO_E_NULL;
+  int a = 0, b = 0, r = 0;
+  odernn_tc_last_geometry(&a, &b, &r);
+  out[0] = a; out[1] = b; out[2] = r;
+  return 0;
+}
+
+int32_t odevio_debug_tc_timeline(long long* host_dst) {
+  return host_dst ? odernn_tc_debug_timeline(host_dst) : ODEVIO_E_NULL;
+}
+
+int32_t odevio_debug_tc_timing(int32_t enable, float* total_ms, int32_t* launches) {
+  if (enable >= 0) { odernn_tc_timing_enable(enable != 0); return 0; }
+  if (!total_ms || !launches) return ODEVIO_E_NULL;
+  int n = 0;
+  const int rc = odernn_tc_timing_read(total_ms, &n);
+  *launches = n;
+  return rc;
 }
 
 int32_t odevio_odernn_geometry(const odevio_odernn_cfg* cfg, int32_t* out) {

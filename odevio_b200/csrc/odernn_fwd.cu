@@ -43,6 +43,14 @@ struct Ctx {
   int tile;     // current tile index
 };
 
+// (layer, sequence) of local row (l, b) in the addressing of ts / stats / status (see FwdParams::full_B)
+__device__ __forceinline__ void global_ids(const FwdParams& p, int l, int b, int& ll, int& bb) {
+  if (p.full_B > 0) {
+    const long long gr = static_cast<long long>(p.row_off) + static_cast<long long>(l) * p.B + b;
+    ll = static_cast<int>(gr / p.full_B); bb = static_cast<int>(gr - static_cast<long long>(ll) * p.full_B);
+  } else { ll = l; bb = b; }
+}
+
 // ---- elementwise helpers over T-layout [D][R]; one float4 = 4 rows of one feature ---------
 
 __device__ __forceinline__ float4 wsum4(const float* const* K, const float* coef, int n, size_t off,
@@ -279,8 +287,10 @@ __device__ __forceinline__ int interval_begin(Ctx<RT>& c, int i) {
     const int b = c.tile * RT + (r % RT);
     float t0 = 0.f, t1 = 0.f;
     if (b < p.B && !p.skip_evolve) {
-      t0 = p.ts[static_cast<size_t>(b) * (p.S + 1) + i];
-      t1 = p.ts[static_cast<size_t>(b) * (p.S + 1) + i + 1];
+      int ll, bb;
+      global_ids(p, r / RT, b, ll, bb);
+      t0 = p.ts[static_cast<size_t>(bb) * p.ts_ld + p.i_off + i];
+      t1 = p.ts[static_cast<size_t>(bb) * p.ts_ld + p.i_off + i + 1];
     }
     rs.t[r] = t0; rs.tend[r] = t1;
     rs.tmin[r] = fminf(t0, t1); rs.tmax[r] = fmaxf(t0, t1);
@@ -308,7 +318,10 @@ __device__ __forceinline__ void write_stats(Ctx<RT>& c, int i) {
   const int r = c.th.ctid;
   const int l = r / RT, b = c.tile * RT + (r % RT);
   if (b < p.B) {
-    int* sp = p.stats + ((static_cast<size_t>(i) * p.L + l) * p.B + b) * (2 + 2 * p.trace_steps);
+    int ll, bb;
+    global_ids(p, l, b, ll, bb);
+    const int LL_ = p.full_B > 0 ? p.full_L : p.L, BB_ = p.full_B > 0 ? p.full_B : p.B;
+    int* sp = p.stats + ((static_cast<size_t>(i + (p.full_B > 0 ? p.i_off : 0)) * LL_ + ll) * BB_ + bb) * (2 + 2 * p.trace_steps);
     sp[0] = c.rs.nsteps[r]; sp[1] = c.rs.nacc[r];
   }
 }
@@ -648,7 +661,15 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
         const int b = tile * RT + c.th.ctid;
         int stt = 0;
         for (int l2 = 0; l2 < LL; ++l2) stt = max(stt, rs.status[l2 * RT + c.th.ctid]);
-        if (b < prm.B) prm.status[b] = stt;
+        if (b < prm.B) {
+          if (prm.full_B > 0) {
+            int ll, bb;
+            global_ids(prm, 0, b, ll, bb);
+            if (stt) atomicMax(prm.status + bb, stt);     // several (layer) rows of a sequence may live in different launches
+          } else {
+            prm.status[b] = stt;
+          }
+        }
       }
     }
     __syncthreads();

@@ -30,6 +30,12 @@ namespace odevio {
 
 namespace {
 
+#ifdef ODEVIO_FT_TIMELINE
+#define TC_STAMP(idx) do { if (blockIdx.x == 0 && tile == 0 && threadIdx.x == 0) g_ft_dbg[idx] = clock64(); } while (0)
+#else
+#define TC_STAMP(idx) do { } while (0)
+#endif
+
 constexpr int TC_NC = 8, TC_KCH = 8;
 constexpr int TC_UNIT = 16;          // features per elementwise unit (thread = row, 4 float4 of the operand image)
 
@@ -60,23 +66,142 @@ struct TcRows {      // per-row solver state, replicated in every CTA of the clu
   float psum[2][FT_ROWS];
 };
 
-// acc = c0*k0 + c1*k1 + ... left to right, skipping exact zeros (oracle/_weighted_sum; same order as
-// odernn_fwd.cu:wsum4).  The loads of all n stage vectors are issued before the arithmetic chain.
-__device__ __forceinline__ float wsum1(float* const* Kst, const float* coef, int n, size_t off, bool& any) {
-  float k[kMaxStages];
+// ---- elementwise passes: thread = row, groups of TC_GRP consecutive features of the CTA's slice.
+// All loads of a group (TC_GRP x (1 + N) coalesced 128-byte warp requests) are issued before any arithmetic and the
+// arithmetic is branch-free: one L2 round trip per group instead of one per element (measured: 55 k -> see DESIGN).
+// Weighted sums run left to right over j = 0..N-1 in the oracle's order (oracle/_weighted_sum, odernn_fwd.cu:wsum4);
+// the oracle skips exactly-zero coefficients, here they contribute an exact +-0 (identical for finite stage values).
+constexpr int TC_GRP = 8;
+
+struct TcSlice {            // what a thread needs to walk its share of the CTA's feature slice
+  float* base;              // per-cluster stage vectors: K[j] = base + j * arr, Y = base + 7 * arr, Y1 = base + 8 * arr
+  size_t arr;
+  int own_f0, ngroups, half, r;
+};
+
+template <int N>
+__device__ __forceinline__ void tc_load_k(const TcSlice& sl, size_t off, float (&k)[N > 0 ? N : 1][TC_GRP]) {
 #pragma unroll
-  for (int j = 0; j < kMaxStages; ++j) k[j] = (j < n && coef[j] != 0.f) ? __ldcg(Kst[j] + off) : 0.f;
-  float acc = 0.f;
-  any = false;
+  for (int j = 0; j < N; ++j)
 #pragma unroll
-  for (int j = 0; j < kMaxStages; ++j) {
-    if (j < n && coef[j] != 0.f) {
-      acc = any ? add_(acc, mul_(k[j], coef[j])) : mul_(k[j], coef[j]);
-      any = true;
-    }
-  }
+    for (int q = 0; q < TC_GRP; ++q) k[j][q] = __ldcg(sl.base + j * sl.arr + off + static_cast<size_t>(q) * FT_ROWS);
+}
+template <int N>
+__device__ __forceinline__ float tc_wsum(const float (&k)[N > 0 ? N : 1][TC_GRP], int q, const float (&cf)[kMaxStages]) {
+  float acc = mul_(k[0][q], cf[0]);
+#pragma unroll
+  for (int j = 1; j < N; ++j) acc = add_(acc, mul_(k[j][q], cf[j]));
   return acc;
 }
+
+// stage argument y + dt * sum_{j<N} a_j k_j  ->  fp32 operand image of layer 0 (N = stage index)
+template <int N, int KCH>
+__device__ __forceinline__ void tc_stage_input(const TcSlice& sl, const float* coef, float dt, float* xa) {
+  float cf[kMaxStages];
+#pragma unroll
+  for (int j = 0; j < kMaxStages; ++j) cf[j] = j < N ? coef[j] : 0.f;
+  const float* Y = sl.base + kMaxStages * sl.arr;
+  for (int grp = sl.half; grp < sl.ngroups; grp += 2) {
+    const int f0 = sl.own_f0 + TC_GRP * grp;
+    const size_t off = static_cast<size_t>(f0) * FT_ROWS + sl.r;
+    float y[TC_GRP], k[N > 0 ? N : 1][TC_GRP];
+#pragma unroll
+    for (int q = 0; q < TC_GRP; ++q) y[q] = __ldcg(Y + off + static_cast<size_t>(q) * FT_ROWS);
+    tc_load_k<N>(sl, off, k);
+    if (N > 0) {
+#pragma unroll
+      for (int q = 0; q < TC_GRP; ++q) y[q] = add_(y[q], mul_(dt, tc_wsum<N>(k, q, cf)));
+    }
+#pragma unroll
+    for (int q = 0; q < TC_GRP / 4; ++q)
+      *reinterpret_cast<float4*>(xa + xa_offset<KCH>(sl.r, f0 + 4 * q)) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+  }
+}
+
+// y1 -> Y1 and this thread's share of sum_d (err_d / bound_d)^2 (odernn_fwd.cu:error_pass); NS = tableau stages.
+// The stage vectors are loaded once and feed both weighted sums.
+template <int NS>
+__device__ __forceinline__ float tc_error_pass(const TcSlice& sl, const DevTableau& tb, float dt, float atol, float rtol) {
+  float cy[kMaxStages], ce[kMaxStages];
+#pragma unroll
+  for (int j = 0; j < kMaxStages; ++j) {
+    cy[j] = j < NS ? (tb.ssal ? (j < NS - 1 ? tb.a[NS - 1][j] : 0.f) : tb.b[j]) : 0.f;
+    ce[j] = j < NS ? tb.e[j] : 0.f;
+  }
+  const float* Y = sl.base + kMaxStages * sl.arr;
+  float* Y1 = sl.base + (kMaxStages + 1) * sl.arr;
+  float sum = 0.f;
+  for (int grp = sl.half; grp < sl.ngroups; grp += 2) {
+    const size_t off = static_cast<size_t>(sl.own_f0 + TC_GRP * grp) * FT_ROWS + sl.r;
+    float y0[TC_GRP], k[NS][TC_GRP];
+#pragma unroll
+    for (int q = 0; q < TC_GRP; ++q) y0[q] = __ldcg(Y + off + static_cast<size_t>(q) * FT_ROWS);
+    tc_load_k<NS>(sl, off, k);
+#pragma unroll
+    for (int q = 0; q < TC_GRP; ++q) {
+      const float y1 = add_(y0[q], mul_(dt, tc_wsum<NS>(k, q, cy)));
+      __stcg(Y1 + off + static_cast<size_t>(q) * FT_ROWS, y1);
+      if (tb.has_err) {
+        const float e = mul_(dt, tc_wsum<NS>(k, q, ce));
+        const float bound = add_(atol, mul_(rtol, fmaxf(fabsf(y0[q]), fabsf(y1))));
+        const float q2 = __fdiv_rn(e, bound);
+        sum = fmaf(q2, q2, sum);
+      }
+    }
+  }
+  return sum;
+}
+
+// fixed step: Y <- y0 + dt * sum b_j k_j (odernn_fwd.cu:fixed_commit)
+template <int NS>
+__device__ __forceinline__ void tc_fixed_commit(const TcSlice& sl, const DevTableau& tb, float dt) {
+  float cb[kMaxStages];
+#pragma unroll
+  for (int j = 0; j < kMaxStages; ++j) cb[j] = j < NS ? tb.b[j] : 0.f;
+  float* Y = sl.base + kMaxStages * sl.arr;
+  for (int grp = sl.half; grp < sl.ngroups; grp += 2) {
+    const size_t off = static_cast<size_t>(sl.own_f0 + TC_GRP * grp) * FT_ROWS + sl.r;
+    float y0[TC_GRP], k[NS][TC_GRP];
+#pragma unroll
+    for (int q = 0; q < TC_GRP; ++q) y0[q] = __ldcg(Y + off + static_cast<size_t>(q) * FT_ROWS);
+    tc_load_k<NS>(sl, off, k);
+#pragma unroll
+    for (int q = 0; q < TC_GRP; ++q)
+      __stcg(Y + off + static_cast<size_t>(q) * FT_ROWS, add_(y0[q], mul_(dt, tc_wsum<NS>(k, q, cb))));
+  }
+}
+
+// accepted rows: Y <- Y1, FSAL carry K0 <- K[ns-1]
+__device__ __forceinline__ void tc_commit(const TcSlice& sl, int ns, int fsal) {
+  float* Y = sl.base + kMaxStages * sl.arr;
+  const float* Y1 = sl.base + (kMaxStages + 1) * sl.arr;
+  const float* Kl = sl.base + static_cast<size_t>(ns - 1) * sl.arr;
+  for (int grp = sl.half; grp < sl.ngroups; grp += 2) {
+    const size_t off = static_cast<size_t>(sl.own_f0 + TC_GRP * grp) * FT_ROWS + sl.r;
+    float a[TC_GRP], b[TC_GRP];
+#pragma unroll
+    for (int q = 0; q < TC_GRP; ++q) {
+      a[q] = __ldcg(Y1 + off + static_cast<size_t>(q) * FT_ROWS);
+      b[q] = fsal ? __ldcg(Kl + off + static_cast<size_t>(q) * FT_ROWS) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < TC_GRP; ++q) {
+      __stcg(Y + off + static_cast<size_t>(q) * FT_ROWS, a[q]);
+      if (fsal) __stcg(sl.base + off + static_cast<size_t>(q) * FT_ROWS, b[q]);
+    }
+  }
+}
+
+#define TC_DISPATCH_STAGES(n, CALL)                                                                                 \
+  switch (n) {                                                                                                      \
+    case 1: { constexpr int NSV = 1; CALL; break; }                                                                 \
+    case 2: { constexpr int NSV = 2; CALL; break; }                                                                 \
+    case 3: { constexpr int NSV = 3; CALL; break; }                                                                 \
+    case 4: { constexpr int NSV = 4; CALL; break; }                                                                 \
+    case 5: { constexpr int NSV = 5; CALL; break; }                                                                 \
+    case 6: { constexpr int NSV = 6; CALL; break; }                                                                 \
+    default: { constexpr int NSV = 7; CALL; break; }                                                                \
+  }
 
 template <int NC, int KCH>
 __global__ void __launch_bounds__(FT_THREADS, 1)
@@ -134,15 +259,14 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
   const int nunits = own_nf / TC_UNIT;
   const size_t arr = static_cast<size_t>(D) * FT_ROWS;
   float* const st_base = p.state + static_cast<size_t>(cluster_id) * p.state_floats;
-  float* Kst[kMaxStages];
-#pragma unroll
-  for (int j = 0; j < kMaxStages; ++j) Kst[j] = st_base + j * arr;
   float* const Yc = st_base + kMaxStages * arr;
   float* const Y1 = Yc + arr;
   float* const normpart = Y1 + arr;          // [NC][128]
 
   const bool epi = warp < FT_EPI_WARPS;
   const int r = tid & (FT_ROWS - 1), half = (tid >> 7) & 1;
+  TcSlice sl;
+  sl.base = st_base; sl.arr = arr; sl.own_f0 = own_f0; sl.ngroups = own_nf / TC_GRP; sl.half = half; sl.r = r;
   const int ns = tb.n_stages;
 
   for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
@@ -195,33 +319,21 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
 
     while (any_running) {
       ++loops;
+      TC_STAMP(40);
       for (int st = (tb.fsal && have_k0) ? 1 : 0; st < ns; ++st) {
         // ---- stage argument -> layer-0 operand image (own feature slice, all 128 rows)
+        TC_STAMP(41);
         if (epi) {
           const float dt = rs.dt[r];
-          for (int u = half; u < nunits; u += 2) {
-            const int f0 = own_f0 + TC_UNIT * u;
-            float v[TC_UNIT];
-#pragma unroll
-            for (int q = 0; q < TC_UNIT; ++q) {
-              const size_t off = static_cast<size_t>(f0 + q) * FT_ROWS + r;
-              float y = __ldcg(Yc + off);
-              if (st > 0) {
-                bool any;
-                const float acc = wsum1(Kst, tb.a[st], st, off, any);
-                if (any) y = add_(y, mul_(dt, acc));
-              }
-              v[q] = y;
-            }
-#pragma unroll
-            for (int q = 0; q < TC_UNIT / 4; ++q)
-              *reinterpret_cast<float4*>(xa_cluster + xa_offset<KCH>(r, f0 + 4 * q)) =
-                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          }
+          if (st == 0) tc_stage_input<0, KCH>(sl, tb.a[0], dt, xa_cluster);
+          else TC_DISPATCH_STAGES(st, (tc_stage_input<(NSV < kMaxStages ? NSV : kMaxStages - 1), KCH>(sl, tb.a[st], dt, xa_cluster)))
+          TC_STAMP(42);
           asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores -> bulk-copy (async) proxy of all CTAs
+          TC_STAMP(43);
         }
         __syncwarp();
         cluster_sync_all();
+        TC_STAMP(44);
         // ---- ODEFunc (src/models/ODEFunc.py:38-39) on the tensor cores; last Linear (+ Tanh) -> K[st]
         for (int l = 0; l < p.NL; ++l) {
           FtLayer Ld;
@@ -232,9 +344,11 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
           Ld.Wp = p.Wp[l]; Ld.Wlo = nullptr; Ld.bias = p.bias[l];
           Ld.a_src = xa_cluster + static_cast<size_t>(l & 1) * 2 * p.xa_buf_floats;
           Ld.nx = xa_cluster + static_cast<size_t>((l + 1) & 1) * 2 * p.xa_buf_floats;
-          Ld.out = Kst[st]; Ld.M = p.M; Ld.row0 = row0;
+          Ld.out = st_base + static_cast<size_t>(st) * arr; Ld.M = p.M; Ld.row0 = row0;
           ft_layer<NC, KCH, true>(c, Ld);
+          TC_STAMP(52 + l);
         }
+        TC_STAMP(45);
       }
       have_k0 = true;
 
@@ -243,31 +357,16 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
         if (epi) {
           const float dt = rs.dt[r];
           float sum = 0.f;
-          for (int u = half; u < nunits; u += 2) {
-            const int f0 = own_f0 + TC_UNIT * u;
-#pragma unroll 4
-            for (int q = 0; q < TC_UNIT; ++q) {
-              const size_t off = static_cast<size_t>(f0 + q) * FT_ROWS + r;
-              const float y0 = __ldcg(Yc + off);
-              bool any;
-              float acc = tb.ssal ? wsum1(Kst, tb.a[ns - 1], ns - 1, off, any) : wsum1(Kst, tb.b, ns, off, any);
-              const float y1 = any ? add_(y0, mul_(dt, acc)) : y0;
-              __stcg(Y1 + off, y1);
-              if (tb.has_err) {
-                acc = wsum1(Kst, tb.e, ns, off, any);
-                const float e = mul_(dt, acc);
-                const float bound = add_(p.atol, mul_(p.rtol, fmaxf(fabsf(y0), fabsf(y1))));
-                const float q2 = __fdiv_rn(e, bound);
-                sum = fmaf(q2, q2, sum);
-              }
-            }
-          }
+          TC_DISPATCH_STAGES(ns, (sum = tc_error_pass<NSV>(sl, tb, dt, p.atol, p.rtol)))
           rs.psum[half][r] = sum;
+          TC_STAMP(46);
           named_bar_sync(1, FT_EPI_WARPS * 32);
           if (tid < FT_ROWS) __stcg(normpart + static_cast<size_t>(crank) * FT_ROWS + r, add_(rs.psum[0][r], rs.psum[1][r]));
         }
         __syncwarp();
+        TC_STAMP(47);
         cluster_sync_all();
+        TC_STAMP(48);
         // ---- per-row controller, identical in every CTA (odernn_fwd.cu:controller; torchode IntegralController)
         run = 0;
         if (tid < FT_ROWS) {
@@ -305,33 +404,15 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
           rs.run[r] = run;
         }
         any_running = __syncthreads_or(run);
+        TC_STAMP(49);
         // ---- commit: accepted rows take y1; FSAL carry (end point rule "y1": exact landing makes y1 the value at t_end)
-        if (epi && rs.upd[r]) {
-          for (int u = half; u < nunits; u += 2) {
-            const int f0 = own_f0 + TC_UNIT * u;
-#pragma unroll
-            for (int q = 0; q < TC_UNIT; ++q) {
-              const size_t off = static_cast<size_t>(f0 + q) * FT_ROWS + r;
-              __stcg(Yc + off, __ldcg(Y1 + off));
-              if (tb.fsal) __stcg(Kst[0] + off, __ldcg(Kst[ns - 1] + off));
-            }
-          }
-        }
+        if (epi && rs.upd[r]) tc_commit(sl, ns, tb.fsal);
+        TC_STAMP(50);
       } else {
         // ---- fixed step: Y <- y0 + dt * sum b_j k_j for every row (odernn_fwd.cu:fixed_commit)
         if (epi) {
           const float dt = rs.dt[r];
-          for (int u = half; u < nunits; u += 2) {
-            const int f0 = own_f0 + TC_UNIT * u;
-#pragma unroll 4
-            for (int q = 0; q < TC_UNIT; ++q) {
-              const size_t off = static_cast<size_t>(f0 + q) * FT_ROWS + r;
-              const float y0 = __ldcg(Yc + off);
-              bool any;
-              const float acc = wsum1(Kst, tb.b, ns, off, any);
-              __stcg(Yc + off, any ? add_(y0, mul_(dt, acc)) : y0);
-            }
-          }
+          TC_DISPATCH_STAGES(ns, (tc_fixed_commit<NSV>(sl, tb, dt)))
           if (tid < FT_ROWS && valid) { rs.nsteps[r] += 1; rs.nacc[r] += 1; }
         }
         any_running = loops < p.substeps;
@@ -373,10 +454,48 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
 
 // ------------------------------------------------------------------------------------------ host side
 
+static int g_tc_last_clusters = 0, g_tc_last_max_clusters = 0, g_tc_last_rows = 0;      // development: geometry of the last launch
+
+// Measurement hook (bench.py): CUDA events around every solver launch on its own stream, so that the kernel's
+// average launch duration is measured live, un-profiled, inside a normal forward (roofline.achieved).
+constexpr int kTimingSlots = 512;
+static bool g_tc_timing = false;
+static int g_tc_timing_n = 0;
+static cudaEvent_t g_tc_ev[kTimingSlots][2];
+static bool g_tc_ev_made = false;
+void odernn_tc_timing_enable(bool on) {
+  g_tc_timing = on; g_tc_timing_n = 0;
+  if (on && !g_tc_ev_made) {
+    for (int i = 0; i < kTimingSlots; ++i) { cudaEventCreate(&g_tc_ev[i][0]); cudaEventCreate(&g_tc_ev[i][1]); }
+    g_tc_ev_made = true;
+  }
+}
+int odernn_tc_timing_read(float* total_ms, int* launches) {
+  float tot = 0.f;
+  for (int i = 0; i < g_tc_timing_n; ++i) {
+    cudaError_t e = cudaEventSynchronize(g_tc_ev[i][1]);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, g_tc_ev[i][0], g_tc_ev[i][1]);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    tot += ms;
+  }
+  *total_ms = tot; *launches = g_tc_timing_n;
+  g_tc_timing_n = 0;
+  return 0;
+}
+int odernn_tc_debug_timeline(long long* host_dst) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_dst, g_ft_dbg, sizeof(long long) * 64));
+}
+void odernn_tc_last_geometry(int* clusters, int* max_clusters, int* rows) {
+  *clusters = g_tc_last_clusters; *max_clusters = g_tc_last_max_clusters; *rows = g_tc_last_rows;
+}
+
 struct TcEvolve::Impl {
   FtPlan pl;
   TcParams prm;
   size_t state_floats, off_state, total_bytes;
+  int maxc = 0;
 };
 
 static int tc_plan(const odevio_odernn_cfg& c, FtPlan& pl, size_t& off_state, size_t& state_floats, size_t& total_bytes) {
@@ -436,31 +555,52 @@ int TcEvolve::prepare(const odevio_odernn_cfg& c, const DevTableau& tab, bool ad
   return 0;
 }
 
-int TcEvolve::evolve(float* Y, const float* ts, int ts_ld, int interval, int* stats, int* status, cudaStream_t stream) {
+static cudaError_t tc_launch_config(const FtPlan& pl, cudaLaunchConfig_t& lc, cudaLaunchAttribute& at, int nclusters,
+                                    cudaStream_t stream) {
+  auto kern = odernn_tc_evolve_kernel<TC_NC, TC_KCH>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem_bytes));
+  if (e != cudaSuccess) return e;
+  memset(&lc, 0, sizeof(lc));
+  lc.blockDim = dim3(FT_THREADS); lc.dynamicSmemBytes = pl.smem_bytes; lc.stream = stream;
+  at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = TC_NC; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  lc.attrs = &at; lc.numAttrs = 1;
+  lc.gridDim = dim3(nclusters * TC_NC);
+  return cudaSuccess;
+}
+
+int TcEvolve::max_clusters() {
+  if (!impl) return 0;
+  if (impl->maxc > 0) return impl->maxc;
+  cudaLaunchConfig_t lc; cudaLaunchAttribute at;
+  if (tc_launch_config(impl->pl, lc, at, impl->pl.nclusters, nullptr) != cudaSuccess) { cudaGetLastError(); return impl->pl.nclusters; }
+  int maxc = 0;
+  if (cudaOccupancyMaxActiveClusters(&maxc, odernn_tc_evolve_kernel<TC_NC, TC_KCH>, &lc) != cudaSuccess || maxc <= 0) {
+    cudaGetLastError();
+    maxc = impl->pl.nclusters;
+  }
+  if (maxc > impl->pl.nclusters) maxc = impl->pl.nclusters;       // scratch is sized for pl.nclusters
+  impl->maxc = maxc;
+  return maxc;
+}
+
+int TcEvolve::evolve(float* Y, int rows, const float* ts, int ts_ld, int interval, int* stats, int* status, cudaStream_t stream) {
   if (!impl) return ODEVIO_E_NULL;
   TcParams p = impl->prm;
   FtPlan& pl = impl->pl;
+  if (rows <= 0 || rows > p.M) return ODEVIO_E_SHAPE;
+  p.M = rows; p.ntiles = (rows + FT_ROWS - 1) / FT_ROWS;
   p.Y = Y; p.ts = ts; p.ts_ld = ts_ld; p.interval = interval; p.stats = stats; p.status = status;
-  auto kern = odernn_tc_evolve_kernel<TC_NC, TC_KCH>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem_bytes));
+  int nclusters = max_clusters();
+  if (nclusters > p.ntiles) nclusters = p.ntiles;
+  cudaLaunchConfig_t lc; cudaLaunchAttribute at;
+  cudaError_t e = tc_launch_config(pl, lc, at, nclusters, stream);
   if (e != cudaSuccess) return static_cast<int>(e);
-  cudaLaunchConfig_t lc;
-  memset(&lc, 0, sizeof(lc));
-  lc.blockDim = dim3(FT_THREADS); lc.dynamicSmemBytes = pl.smem_bytes; lc.stream = stream;
-  cudaLaunchAttribute at;
-  at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = TC_NC; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-  lc.attrs = &at; lc.numAttrs = 1;
-  int nclusters = pl.nclusters;
-  lc.gridDim = dim3(nclusters * TC_NC);
-  int maxc = 0;
-  if (cudaOccupancyMaxActiveClusters(&maxc, kern, &lc) == cudaSuccess && maxc > 0) {
-    if (nclusters > maxc) nclusters = maxc;
-  } else {
-    cudaGetLastError();
-  }
-  lc.gridDim = dim3(nclusters * TC_NC);
-  e = cudaLaunchKernelEx(&lc, kern, p);
+  g_tc_last_clusters = nclusters; g_tc_last_max_clusters = impl->maxc; g_tc_last_rows = rows;
+  const bool timed = g_tc_timing && g_tc_timing_n < kTimingSlots;
+  if (timed) cudaEventRecord(g_tc_ev[g_tc_timing_n][0], stream);
+  e = cudaLaunchKernelEx(&lc, odernn_tc_evolve_kernel<TC_NC, TC_KCH>, p);
   if (e != cudaSuccess) return static_cast<int>(e);
+  if (timed) { cudaEventRecord(g_tc_ev[g_tc_timing_n][1], stream); ++g_tc_timing_n; }
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }

@@ -14,6 +14,17 @@ namespace odevio {
 // workspace bytes of the solver (packed weight images, operand buffers, per-cluster stage vectors); 0 = unsupported shape
 size_t odernn_tc_workspace_bytes(const odevio_odernn_cfg& c);
 
+// development: clusters launched / co-resident maximum (cudaOccupancyMaxActiveClusters) / rows of the last evolve launch
+void odernn_tc_last_geometry(int* clusters, int* max_clusters, int* rows);
+
+// measurement hook: CUDA events around every solver launch (bench.py's live kernel duration); read() synchronises,
+// returns the summed duration and the number of launches since enable / the last read
+void odernn_tc_timing_enable(bool on);
+int odernn_tc_timing_read(float* total_ms, int* launches);
+
+// development (-DODEVIO_FT_TIMELINE builds): clock64 stamps of cluster 0 / CTA 0 / tile 0, last solver iteration
+int odernn_tc_debug_timeline(long long* host_dst);
+
 class TcEvolve {
  public:
   TcEvolve();
@@ -23,8 +34,11 @@ class TcEvolve {
   // packs the ODEFunc weights (PyTorch [out][in] layout) into the workspace; returns 0 or an ODEVIO_E_* / CUDA code
   int prepare(const odevio_odernn_cfg& c, const DevTableau& tab, bool adaptive, const float* const* ode_w,
               const float* const* ode_b, void* workspace, size_t workspace_bytes, cudaStream_t stream);
-  // evolves Y[L*B][D] in place over interval `interval` (row b: ts[b * ts_ld + interval] -> [.. + 1])
-  int evolve(float* Y, const float* ts, int ts_ld, int interval, int* stats, int* status, cudaStream_t stream);
+  // clusters of 8 CTAs that can be co-resident on this GPU (cudaOccupancyMaxActiveClusters; 15-16 on B200)
+  int max_clusters();
+  // evolves rows [0, rows) of Y[L*B][D] in place over interval `interval` (row g = l * B + b:
+  // ts[b * ts_ld + interval] -> ts[.. + 1]); rows beyond `rows` are left to the caller
+  int evolve(float* Y, int rows, const float* ts, int ts_ld, int interval, int* stats, int* status, cudaStream_t stream);
 
  private:
   struct Impl;
