@@ -321,8 +321,17 @@ def run_ours(args, rank, world, local_rank):
             D_, H_, n_ = w["v_f_len"] + w["i_f_len"], w["H"], w["n"]
             f_ode = 2 * (D_ * H_ + (n_ - 1) * H_ * H_ + H_ * D_)
             tc_rows = tc_geo[2]
-            n_side = 1 if tc_rows < w["L"] * B else 0
-            st_rows = stats.cpu()[..., 0].reshape(S, w["L"] * B)[:, :tc_rows].double()
+            n_side_seq = B - tc_rows // w["L"]
+            n_side = 1 if n_side_seq > 0 else 0
+            st_all = stats.cpu()[..., 0].double()                       # [S, L, B]
+            in_tc = torch.ones(S, B, dtype=torch.bool)
+            if n_side_seq > 0:
+                # the library's per-interval rule (tc_select_kernel): the n_side sequences with the shortest interval
+                # (ties by index) run in the FFMA side launch
+                gaps = (ts_h[:, 1:] - ts_h[:, :-1]).float()
+                for i in range(S):
+                    in_tc[i, torch.argsort(gaps[:, i], stable=True)[:n_side_seq]] = False
+            st_rows = st_all * in_tc[:, None, :]
             tc_evals = (6.0 * st_rows + (st_rows > 0).double()).sum().item()
             per_launch_ms = tc_kernel_ms / tc_launches
             tc_flops_per_launch = tc_evals * f_ode / S

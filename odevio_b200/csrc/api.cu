@@ -409,8 +409,12 @@ int plan_cde(const odevio_cde_cfg& c, CdePlan& pl) {
 
 // ---- tensor-core mode: rows the cluster kernel cannot take in full rounds run concurrently in the FMA kernel
 constexpr int kSideRT = 8;      // sequences (= rows, L = 1) per CTA of the side launch
-size_t tc_side_scratch_bytes(const odevio_odernn_cfg& c, int nsm) {
-  return align_up(static_cast<size_t>(kMaxStages + 2) * c.D * kSideRT, 64) * sizeof(float) * static_cast<size_t>(nsm);
+size_t tc_side_scratch_bytes(const odevio_odernn_cfg& c, int nsm) {      // <= 8 rows per CTA, <= nsm CTAs
+  return align_up(align_up(static_cast<size_t>(kMaxStages + 2) * c.D * 8, 64) * sizeof(float) * static_cast<size_t>(nsm), 256);
+}
+
+size_t tc_seq_table_bytes(const odevio_odernn_cfg& c) {
+  return align_up(static_cast<size_t>(c.S) * c.B * sizeof(int32_t), 256);
 }
 
 // Helper stream + fork/join events per device, created on first use (the only persistent objects of the library).
@@ -474,7 +478,8 @@ size_t odevio_odernn_workspace_bytes(const odevio_odernn_cfg* cfg) {
   if (plan_odernn(*cfg, pl) != 0) return 0;
   if (cfg->precision == ODEVIO_PRECISION_TF32X3) {
     const size_t tcb = odernn_tc_workspace_bytes(*cfg);
-    return tcb ? align_up(pl.total_bytes, 256) + align_up(tcb, 256) + tc_side_scratch_bytes(*cfg, pl.nsm) : 0;
+    return tcb ? align_up(pl.total_bytes, 256) + align_up(tcb, 256) + tc_side_scratch_bytes(*cfg, pl.nsm) +
+                     tc_seq_table_bytes(*cfg) : 0;
   }
   return pl.total_bytes;
 }
@@ -519,7 +524,7 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
   p.max_steps = c.max_steps; p.exact_landing = c.exact_landing; p.trace_steps = c.trace_steps;
   p.evolve_only = c.evolve_only ? 1 : 0;
   p.skip_evolve = 0; p.S_io = c.S; p.i_off = 0;
-  p.full_B = 0; p.full_L = 0; p.row_off = 0; p.ts_ld = c.S + 1;
+  p.full_B = 0; p.full_L = 0; p.row_off = 0; p.ts_ld = c.S + 1; p.seq = nullptr;
   if (!make_tableau(c.solver, p.tab)) return ODEVIO_E_ENUM;
 
   // ---- pre-pack weights into the workspace
@@ -592,7 +597,7 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
     const size_t tc_bytes = align_up(odernn_tc_workspace_bytes(c), 256);
     const size_t side_bytes = tc_side_scratch_bytes(c, pl.nsm);
     if (tc_bytes == 0) return ODEVIO_E_SHAPE;
-    if (workspace_bytes < tc_off + tc_bytes + side_bytes) return ODEVIO_E_WORKSPACE;
+    if (workspace_bytes < tc_off + tc_bytes + side_bytes + tc_seq_table_bytes(c)) return ODEVIO_E_WORKSPACE;
     TcEvolve tc;
     const int prc = tc.prepare(c, p.tab, p.adaptive != 0, w->ode_w, w->ode_b, static_cast<unsigned char*>(workspace) + tc_off,
                                tc_bytes, stream);
@@ -603,33 +608,39 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
     if (status) ODEVIO_CUDA_TRY(cudaMemsetAsync(status, 0, static_cast<size_t>(c.B) * sizeof(int32_t), stream));
 
     // Row split.  A B200 holds 15-16 clusters of 8 CTAs at once; every further 128-row tile would cost a whole extra
-    // round of the latency-bound cluster kernel.  The cluster kernel therefore takes full rounds only, and a remainder
-    // that fits one wave of the FMA kernel on the SMs the clusters leave idle runs there, concurrently (helper stream).
+    // round of the latency-bound cluster kernel.  The cluster kernel therefore takes full rounds only (all L layer rows
+    // of Bsub sequences), and when the other sequences fit one wave of the FFMA kernel on the SMs the clusters leave idle
+    // they run there, concurrently (helper stream).  The FFMA tiles are slower per evaluation, so per interval they get
+    // the sequences with the SHORTEST interval -- the fewest solver steps (tc_select_kernel).
     const int M = c.L * c.B;
     const int ntiles_tc = (M + 127) / 128, maxc = tc.max_clusters();
-    int tc_rows = M, side_rows = 0;
-    if (maxc > 0 && ntiles_tc > maxc && ntiles_tc % maxc != 0) {
+    int Bsub = c.B, n_side = 0;
+    const int side_rt = c.L >= 2 ? 4 : kSideRT;
+    if (maxc > 0 && ntiles_tc > maxc && ntiles_tc % maxc != 0 && c.B <= 8192) {
       const int full_rows = (ntiles_tc / maxc) * maxc * 128;
       const int idle_sms = pl.nsm - maxc * 8;
-      if (M - full_rows <= idle_sms * kSideRT) { tc_rows = full_rows; side_rows = M - full_rows; }
+      if (full_rows % c.L == 0) {
+        const int bs = full_rows / c.L, ns_ = c.B - bs;
+        if (ns_ > 0 && (ns_ + side_rt - 1) / side_rt <= idle_sms && side_rt * c.L <= 8) { Bsub = bs; n_side = ns_; }
+      }
     }
-    FwdParams ps = p;          // side launch: evolve_only on rows [tc_rows, M) as an L = 1 problem
+    FwdParams ps = p;          // side launch: evolve_only on the last n_side sequences of the per-interval order
     OdePlan pls;
     SideStream* side = nullptr;
-    if (side_rows > 0) {
+    int* seq = nullptr;
+    if (n_side > 0) {
       odevio_odernn_cfg cs = c;
-      // 8-row tiles; when the rows allow it as 2 row blocks of 4 (an "L = 2" problem of side_rows / 2 sequences): 256
-      // consumer threads per CTA instead of 128 (measured: 46.9 vs 50.1 ms per configs[1] forward)
-      const bool two = side_rows % 8 == 0;
-      cs.L = two ? 2 : 1; cs.B = two ? side_rows / 2 : side_rows; cs.rows_per_tile = two ? 4 : kSideRT;
-      cs.S = 1; cs.evolve_only = 1; cs.precision = ODEVIO_PRECISION_FP32;
+      cs.B = n_side; cs.S = 1; cs.evolve_only = 1; cs.rows_per_tile = side_rt; cs.precision = ODEVIO_PRECISION_FP32;
       const int src = plan_odernn(cs, pls);
       if (src != 0) return src;
       const int ssrc = side_stream(&side);
       if (ssrc != 0) return ssrc;
-      ps.B = cs.B; ps.L = cs.L; ps.S = 1; ps.evolve_only = 1; ps.skip_evolve = 0;
-      ps.full_B = c.B; ps.full_L = c.L; ps.row_off = tc_rows; ps.ts_ld = c.S + 1; ps.ts = ts;
-      ps.h0 = hT + static_cast<size_t>(tc_rows) * D; ps.hT = hT + static_cast<size_t>(tc_rows) * D;
+      seq = reinterpret_cast<int*>(static_cast<unsigned char*>(workspace) + tc_off + tc_bytes + side_bytes);
+      const int selrc = odernn_tc_select(ts, c.B, c.S, n_side, seq, stream);
+      if (selrc != 0) return selrc;
+      ps.B = n_side; ps.S = 1; ps.evolve_only = 1; ps.skip_evolve = 0;
+      ps.full_B = c.B; ps.full_L = c.L; ps.row_off = Bsub; ps.ts_ld = c.S + 1; ps.ts = ts;
+      ps.h0 = hT; ps.hT = hT;
       ps.stats = stats; ps.status = status; ps.pose = nullptr; ps.fv = nullptr; ps.fi = nullptr; ps.Wfuse = nullptr;
       ps.scratch = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + tc_off + tc_bytes);
       ps.scratch_floats_per_cta = pls.scratch_floats_per_cta;
@@ -643,10 +654,11 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
         ODEVIO_CUDA_TRY(cudaEventRecord(side->fork, stream));
         ODEVIO_CUDA_TRY(cudaStreamWaitEvent(side->stream, side->fork, 0));
       }
-      const int erc = tc.evolve(hT, tc_rows, ts, c.S + 1, i, stats, status, stream);      // clusters first: they need whole GPCs
+      const int* seq_i = seq ? seq + static_cast<size_t>(i) * c.B : nullptr;
+      const int erc = tc.evolve(hT, Bsub, seq_i, ts, c.S + 1, i, stats, status, stream);   // clusters first: they need whole GPCs
       if (erc != 0) return erc;
       if (side) {
-        ps.i_off = i;
+        ps.i_off = i; ps.seq = seq_i;
         ODEVIO_CUDA_TRY(launch_odernn_fwd(ps, pls.RT, pls.grid, pls.smem_bytes, side->stream));
         ODEVIO_CUDA_TRY(cudaEventRecord(side->join, side->stream));
         ODEVIO_CUDA_TRY(cudaStreamWaitEvent(stream, side->join, 0));

@@ -43,12 +43,10 @@ struct Ctx {
   int tile;     // current tile index
 };
 
-// (layer, sequence) of local row (l, b) in the addressing of ts / stats / status (see FwdParams::full_B)
+// (layer, sequence) of local row (l, b) in the addressing of state / ts / stats / status (see FwdParams::full_B)
 __device__ __forceinline__ void global_ids(const FwdParams& p, int l, int b, int& ll, int& bb) {
-  if (p.full_B > 0) {
-    const long long gr = static_cast<long long>(p.row_off) + static_cast<long long>(l) * p.B + b;
-    ll = static_cast<int>(gr / p.full_B); bb = static_cast<int>(gr - static_cast<long long>(ll) * p.full_B);
-  } else { ll = l; bb = b; }
+  ll = l;
+  bb = (p.full_B > 0) ? p.seq[p.row_off + b] : b;
 }
 
 // ---- elementwise helpers over T-layout [D][R]; one float4 = 4 rows of one feature ---------
@@ -464,7 +462,11 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
         const int r = e / prm.D, d = e - r * prm.D;      // coalesced along d
         const int l = r / RT, b = tile * RT + (r % RT);
         float v = 0.f;
-        if (prm.h0 && b < prm.B) v = prm.h0[(static_cast<size_t>(l) * prm.B + b) * prm.D + d];
+        if (prm.h0 && b < prm.B) {
+          int ll, bb;
+          global_ids(prm, l, b, ll, bb);
+          v = prm.h0[(static_cast<size_t>(ll) * (prm.full_B > 0 ? prm.full_B : prm.B) + bb) * prm.D + d];
+        }
         c.Y[static_cast<size_t>(d) * R + r] = v;
       }
       if (c.th.ctid < R) rs.status[c.th.ctid] = 0;
@@ -655,7 +657,11 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
       for (int e = c.th.ctid; e < prm.D * R; e += ncons) {
         const int r = e / prm.D, d = e - r * prm.D;
         const int l2 = r / RT, b = tile * RT + (r % RT);
-        if (b < prm.B) prm.hT[(static_cast<size_t>(l2) * prm.B + b) * prm.D + d] = c.Y[static_cast<size_t>(d) * R + r];
+        if (b < prm.B) {
+          int ll, bb;
+          global_ids(prm, l2, b, ll, bb);
+          prm.hT[(static_cast<size_t>(ll) * (prm.full_B > 0 ? prm.full_B : prm.B) + bb) * prm.D + d] = c.Y[static_cast<size_t>(d) * R + r];
+        }
       }
       if (prm.status && c.th.ctid < RT) {
         const int b = tile * RT + c.th.ctid;

@@ -35,10 +35,12 @@ struct FwdParams {
   int evolve_only;           // PoseODERNN.evolve_state: ODE solves only (no jump / head)
   int skip_evolve;           // jump + head only (the state was evolved by the tensor-core solver kernel); ts is not read
   int S_io, i_off;           // features / poses of interval i live at row b * S_io + i_off + i (S_io = S, i_off = 0 normally)
-  // sub-launch on a row range of a larger [full_L, full_B] problem (tensor-core mode: the rows the cluster kernel
-  // leaves to the FMA kernel): local row l * B + b is global row row_off + l * B + b = ll * full_B + bb; timestamps,
-  // stats and status are addressed with (ll, bb).  full_B = 0: plain launch.
+  // sub-launch on part of the sequences of a larger [full_L = L, full_B] problem (tensor-core mode: the sequences the
+  // cluster kernel leaves to the FFMA kernel): local sequence b is sequence bb = seq[row_off + b] of the full problem;
+  // hidden state (h0 / hT are the FULL [L, full_B, D] arrays), timestamps, stats and status are addressed with bb.
+  // full_B = 0: plain launch.
   int full_B, full_L, row_off, ts_ld;
+  const int* seq;
   DevTableau tab;
   // packed weights (K-major [K][N]) and biases
   const float* Wode[kMaxLinears];

@@ -53,7 +53,9 @@ struct TcParams {
   int adaptive, substeps;
   float atol, rtol, dt0, safety, fmin, fmax;
   int accept_strict, floor_factor, max_steps, exact_landing;
-  float* Y;                 // [M][D] row-major hidden state, evolved in place
+  float* Y;                 // [L*B][D] row-major hidden state, evolved in place
+  const int* seq; int Bsub; // this launch integrates the L * Bsub rows (l, j), j < Bsub, of sequences b = seq[j] (seq == nullptr:
+                            // b = j); kernel row g = l * Bsub + j lives at state row l * B + b.  M = L * Bsub.
   const float* ts; int ts_ld, interval;      // row b: ts[b * ts_ld + interval] -> ts[.. + 1]
   int* stats;               // [S][L][B][2] (n_steps, n_accepted) or nullptr
   int* status;              // [B], max over layers
@@ -274,7 +276,9 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
     const int row0 = tile * FT_ROWS;
     const int g = row0 + r;                        // global row of this thread (epilogue warps)
     const bool valid = g < p.M;
-    const int b = valid ? g % p.B : 0, lyr = valid ? g / p.B : 0;
+    const int lyr = valid ? g / p.Bsub : 0, jseq = valid ? g - lyr * p.Bsub : 0;
+    const int b = valid ? (p.seq ? p.seq[jseq] : jseq) : 0;
+    const size_t grow = static_cast<size_t>(lyr) * p.B + b;      // state row of this thread's kernel row
 
     // ---- load the tile's state (row-major [M][D]) into the feature-major scratch, own slice
     if (epi) {
@@ -282,7 +286,7 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
         const int f0 = own_f0 + TC_UNIT * u;
         float v[TC_UNIT];
         if (valid) {
-          const float4* src = reinterpret_cast<const float4*>(p.Y + static_cast<size_t>(g) * D + f0);
+          const float4* src = reinterpret_cast<const float4*>(p.Y + grow * D + f0);
 #pragma unroll
           for (int q = 0; q < TC_UNIT / 4; ++q) { const float4 t4 = src[q]; v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w; }
         } else {
@@ -427,7 +431,7 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
         float v[TC_UNIT];
 #pragma unroll
         for (int q = 0; q < TC_UNIT; ++q) v[q] = __ldcg(Yc + static_cast<size_t>(f0 + q) * FT_ROWS + r);
-        float4* dst = reinterpret_cast<float4*>(p.Y + static_cast<size_t>(g) * D + f0);
+        float4* dst = reinterpret_cast<float4*>(p.Y + grow * D + f0);
 #pragma unroll
         for (int q = 0; q < TC_UNIT / 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
@@ -453,6 +457,42 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ host side
+
+// ---- per-interval sequence order for the row split (api.cu): seq[i][0 .. B - n_side) = the sequences the cluster
+// kernel integrates (increasing index), seq[i][B - n_side .. B) = the n_side sequences with the SHORTEST interval i
+// (ties by index): they need the fewest solver steps and go to the slower FFMA side launch.  One CTA per interval,
+// rank by counting (B <= 8192: ~10 us at B = 1024).
+__global__ void tc_select_kernel(const float* __restrict__ ts, int B, int S, int n_side, int* __restrict__ seq) {
+  extern __shared__ unsigned char sel_smem[];
+  float* dt = reinterpret_cast<float*>(sel_smem);
+  int* side = reinterpret_cast<int*>(dt + B);
+  const int i = blockIdx.x;
+  for (int b = threadIdx.x; b < B; b += blockDim.x)
+    dt[b] = ts[static_cast<size_t>(b) * (S + 1) + i + 1] - ts[static_cast<size_t>(b) * (S + 1) + i];
+  __syncthreads();
+  int* out = seq + static_cast<size_t>(i) * B;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float d = dt[b];
+    int rank = 0;
+    for (int o = 0; o < B; ++o) { const float e = dt[o]; rank += (e < d || (e == d && o < b)) ? 1 : 0; }
+    side[b] = rank < n_side ? 1 : 0;
+    if (rank < n_side) out[B - n_side + rank] = b;
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    if (side[b]) continue;
+    int before = 0;
+    for (int o = 0; o < b; ++o) before += side[o];
+    out[b - before] = b;
+  }
+}
+
+int odernn_tc_select(const float* ts, int B, int S, int n_side, int* seq, cudaStream_t stream) {
+  if (B > 8192 || n_side <= 0 || n_side >= B) return ODEVIO_E_SHAPE;
+  tc_select_kernel<<<S, 1024, static_cast<size_t>(B) * 8, stream>>>(ts, B, S, n_side, seq);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
 
 static int g_tc_last_clusters = 0, g_tc_last_max_clusters = 0, g_tc_last_rows = 0;      // development: geometry of the last launch
 
@@ -583,12 +623,15 @@ int TcEvolve::max_clusters() {
   return maxc;
 }
 
-int TcEvolve::evolve(float* Y, int rows, const float* ts, int ts_ld, int interval, int* stats, int* status, cudaStream_t stream) {
+int TcEvolve::evolve(float* Y, int Bsub, const int* seq, const float* ts, int ts_ld, int interval, int* stats, int* status,
+                     cudaStream_t stream) {
   if (!impl) return ODEVIO_E_NULL;
   TcParams p = impl->prm;
   FtPlan& pl = impl->pl;
-  if (rows <= 0 || rows > p.M) return ODEVIO_E_SHAPE;
+  if (Bsub <= 0 || Bsub > p.B) return ODEVIO_E_SHAPE;
+  const int rows = p.L * Bsub;
   p.M = rows; p.ntiles = (rows + FT_ROWS - 1) / FT_ROWS;
+  p.Bsub = Bsub; p.seq = seq;
   p.Y = Y; p.ts = ts; p.ts_ld = ts_ld; p.interval = interval; p.stats = stats; p.status = status;
   int nclusters = max_clusters();
   if (nclusters > p.ntiles) nclusters = p.ntiles;

@@ -25,6 +25,10 @@ int odernn_tc_timing_read(float* total_ms, int* launches);
 // development (-DODEVIO_FT_TIMELINE builds): clock64 stamps of cluster 0 / CTA 0 / tile 0, last solver iteration
 int odernn_tc_debug_timeline(long long* host_dst);
 
+// seq[S][B] (device): per interval the sequences in increasing index order, except that the n_side sequences with the
+// shortest interval are moved to the tail (the FFMA side launch takes the tail).  B <= 8192.
+int odernn_tc_select(const float* ts, int B, int S, int n_side, int* seq, cudaStream_t stream);
+
 class TcEvolve {
  public:
   TcEvolve();
@@ -36,9 +40,10 @@ class TcEvolve {
               const float* const* ode_b, void* workspace, size_t workspace_bytes, cudaStream_t stream);
   // clusters of 8 CTAs that can be co-resident on this GPU (cudaOccupancyMaxActiveClusters; 15-16 on B200)
   int max_clusters();
-  // evolves rows [0, rows) of Y[L*B][D] in place over interval `interval` (row g = l * B + b:
-  // ts[b * ts_ld + interval] -> ts[.. + 1]); rows beyond `rows` are left to the caller
-  int evolve(float* Y, int rows, const float* ts, int ts_ld, int interval, int* stats, int* status, cudaStream_t stream);
+  // evolves, in place over interval `interval`, the L * Bsub rows (l, b = seq[j]), j < Bsub, of Y[L][B][D]
+  // (seq == nullptr: b = j); row b integrates ts[b * ts_ld + interval] -> ts[.. + 1].  Other rows are left to the caller.
+  int evolve(float* Y, int Bsub, const int* seq, const float* ts, int ts_ld, int interval, int* stats, int* status,
+             cudaStream_t stream);
 
  private:
   struct Impl;
