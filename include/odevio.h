@@ -310,6 +310,24 @@ ODEVIO_API int32_t odevio_mlp_forward(int32_t M, int32_t n_linears, const int32_
                                       const float* x, float* out, void* stream);
 
 /*
+ * InertialEncoder.forward (reference src/models/Encoder.py:39-74), inference mode: raw IMU rows imu [B, 10*S + 1, 6]
+ * -> windows of 11 samples (stride 10) -> 3 x {Conv1d(k=3, pad=1) + BatchNorm1d(running statistics) + LeakyReLU(0.1)}
+ * (6 -> 64 -> 128 -> 256) -> Linear(256 * 11, i_f_len) -> out [B, S, i_f_len], the `fi` input of the regressors.
+ * Weights are the reference's state_dict tensors (encoder_conv.{0,4,8}.{weight [C_out, C_in, 3], bias},
+ * encoder_conv.{1,5,9}.{weight, bias, running_mean, running_var}, proj.{weight [i_f_len, 2816], bias}), DEVICE pointers.
+ */
+typedef struct odevio_imu_encoder_weights {
+  const float* conv_w[3]; const float* conv_b[3];
+  const float* bn_weight[3]; const float* bn_bias[3]; const float* bn_mean[3]; const float* bn_var[3];
+  float bn_eps;                 /* nn.BatchNorm1d default 1e-5 */
+  const float* proj_w; const float* proj_b;
+} odevio_imu_encoder_weights;
+ODEVIO_API size_t odevio_imu_encoder_workspace_bytes(int32_t i_f_len);
+ODEVIO_API int32_t odevio_imu_encoder_forward(int32_t B, int32_t S, int32_t i_f_len, const odevio_imu_encoder_weights* w,
+                                              const float* imu, float* out,
+                                              void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Diagnostics (no reference counterpart): launch a dense FFMA loop on `blocks` CTAs of 512 threads
  * and report the FLOPs it performs in *flops_out (HOST); time it with events around the call to
  * obtain this GPU's fp32 FMA peak, the roofline denominator of ODEVIO_PRECISION_FP32.

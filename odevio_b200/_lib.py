@@ -73,6 +73,15 @@ class OdeRnnGrads(C.Structure):
     _fields_ = OdeRnnWeights._fields_
 
 
+class ImuEncoderWeights(C.Structure):
+    """odevio_imu_encoder_weights (include/odevio.h)."""
+    _fields_ = [
+        ("conv_w", C.c_void_p * 3), ("conv_b", C.c_void_p * 3),
+        ("bn_weight", C.c_void_p * 3), ("bn_bias", C.c_void_p * 3), ("bn_mean", C.c_void_p * 3), ("bn_var", C.c_void_p * 3),
+        ("bn_eps", C.c_float), ("proj_w", C.c_void_p), ("proj_b", C.c_void_p),
+    ]
+
+
 ABI_VERSION = 3
 _lib = None
 
@@ -127,6 +136,11 @@ def load():
     lib.odevio_mlp_forward.restype = C.c_int32
     lib.odevio_mlp_forward.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                        C.POINTER(_FP), C.POINTER(_FP), _FP, _FP, _FP]
+    lib.odevio_imu_encoder_workspace_bytes.restype = C.c_size_t
+    lib.odevio_imu_encoder_workspace_bytes.argtypes = [C.c_int32]
+    lib.odevio_imu_encoder_forward.restype = C.c_int32
+    lib.odevio_imu_encoder_forward.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(ImuEncoderWeights), _FP, _FP,
+                                               _FP, C.c_size_t, _FP]
     lib.odevio_debug_tc_geometry.restype = C.c_int32
     lib.odevio_debug_tc_geometry.argtypes = [C.POINTER(C.c_int32)]
     lib.odevio_debug_tc_timing.restype = C.c_int32

@@ -8,6 +8,7 @@ drop-in and reference checkpoints load:
   * :class:`CDEFunc`      -- reference src/models/ODEFunc.py:44-84
   * :class:`FusionModule` -- reference src/models/FusionModule.py:8-29
   * :class:`PoseODERNN`   -- reference src/models/PoseODERNN.py:39-154
+  * :class:`InertialEncoder` -- reference src/models/Encoder.py:39-74 (the step upstream of the regressors)
 
 The modules only *hold* parameters (ordinary ``nn.Parameter``) and pack pointers; all of the
 path's arithmetic runs in the sm_100a kernels behind the C ABI (``include/odevio.h``).  There
@@ -182,6 +183,64 @@ def _f32c(t, name):
     if t.dtype != torch.float32:
         raise _lib.OdevioError(f"{name} must be float32 (the path computes in fp32), got {t.dtype}")
     return t.contiguous()
+
+
+class InertialEncoder(nn.Module):
+    """IMU encoder (reference src/models/Encoder.py:39-74), the step immediately upstream of the regressors: raw IMU rows
+    ``[B, 10*S + 1, 6]`` -> ``fi [B, S, i_f_len]``.  Same construction order, module types and state_dict keys as the
+    reference (``encoder_conv.{0..11}``, ``proj``), so its checkpoints load; ``forward`` launches ``odevio_imu_encoder_forward``
+    (one kernel: windowing, 3 x Conv1d+BatchNorm+LeakyReLU, projection).  Inference only: in training mode BatchNorm
+    uses batch statistics and Dropout is active, for which there is no kernel -- ``forward`` raises."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.seq_len = opt.seq_len
+        drop = getattr(opt, "imu_dropout", 0.0)
+        self.encoder_conv = nn.Sequential(
+            nn.Conv1d(6, 64, kernel_size=3, padding=1), nn.BatchNorm1d(64), nn.LeakyReLU(0.1, inplace=True), nn.Dropout(drop),
+            nn.Conv1d(64, 128, kernel_size=3, padding=1), nn.BatchNorm1d(128), nn.LeakyReLU(0.1, inplace=True), nn.Dropout(drop),
+            nn.Conv1d(128, 256, kernel_size=3, padding=1), nn.BatchNorm1d(256), nn.LeakyReLU(0.1, inplace=True), nn.Dropout(drop),
+        )
+        self.proj = nn.Linear(256 * 1 * 11, opt.i_f_len)
+        self.i_f_len = opt.i_f_len
+
+    def forward(self, x):
+        lib = _lib.load()
+        if not x.is_cuda:
+            raise _lib.OdevioError("InertialEncoder.forward needs a CUDA tensor: odevio_b200 has no CPU path")
+        if self.training or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+                             and x.requires_grad):
+            raise _lib.OdevioError("InertialEncoder.forward is inference-only (eval mode: running BatchNorm statistics, "
+                                   "no Dropout); the reference trains it with the encoders, which are out of scope")
+        if x.dim() != 3 or x.shape[2] != 6 or x.shape[1] < 11:
+            raise _lib.OdevioError(f"imu must be [B, 10*S + 1, 6], got {tuple(x.shape)}")
+        B, S = x.shape[0], (x.shape[1] - 1) // 10                                   # Encoder.py:61
+        xs = _f32c(x[:, :10 * S + 1].detach(), "imu")
+        keep = []
+
+        def ptr(t):
+            t = _f32c(t.detach(), "weight")
+            keep.append(t)
+            return t.data_ptr()
+
+        w = _lib.ImuEncoderWeights()
+        for k in range(3):
+            conv, bn = self.encoder_conv[4 * k], self.encoder_conv[4 * k + 1]
+            w.conv_w[k], w.conv_b[k] = ptr(conv.weight), ptr(conv.bias)
+            w.bn_weight[k], w.bn_bias[k] = ptr(bn.weight), ptr(bn.bias)
+            w.bn_mean[k], w.bn_var[k] = ptr(bn.running_mean), ptr(bn.running_var)
+        w.bn_eps = self.encoder_conv[1].eps
+        w.proj_w, w.proj_b = ptr(self.proj.weight), ptr(self.proj.bias)
+        nbytes = lib.odevio_imu_encoder_workspace_bytes(self.i_f_len)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        out = torch.empty(B, S, self.i_f_len, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.odevio_imu_encoder_forward(B, S, self.i_f_len, C.byref(w), _lib.dptr(xs), _lib.dptr(out),
+                                                _lib.dptr(ws), nbytes,
+                                                C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+        _lib.check(rc)
+        del keep
+        return out
 
 
 class PoseODERNN(nn.Module):
