@@ -618,7 +618,7 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
     const int side_rt = c.L >= 2 ? 4 : kSideRT;
     if (maxc > 0 && ntiles_tc > maxc && ntiles_tc % maxc != 0 && c.B <= 8192) {
       const int full_rows = (ntiles_tc / maxc) * maxc * 128;
-      const int idle_sms = pl.nsm - maxc * 8;
+      const int idle_sms = pl.nsm - maxc * tc.cluster_size();
       if (full_rows % c.L == 0) {
         const int bs = full_rows / c.L, ns_ = c.B - bs;
         if (ns_ > 0 && (ns_ + side_rt - 1) / side_rt <= idle_sms && side_rt * c.L <= 8) { Bsub = bs; n_side = ns_; }

@@ -384,7 +384,8 @@ struct FtPlan {
   int K[FT_MAX_LAYERS], N[FT_MAX_LAYERS];
 };
 
-int ft_plan(int M, int D, int H, int n_hidden, FtPlan& pl, bool force_split = false) {
+// mode: 0 = by tile count (ODEFunc.forward), 1 = clusters of 8 / split operands, 2 = clusters of 4 / pre-split wide MMAs
+int ft_plan(int M, int D, int H, int n_hidden, FtPlan& pl, int mode = 0) {
   if (M <= 0 || n_hidden < 1 || n_hidden + 1 > FT_MAX_LAYERS) return ODEVIO_E_SHAPE;
   int dev = 0, nsm = 148;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) {
@@ -395,7 +396,8 @@ int ft_plan(int M, int D, int H, int n_hidden, FtPlan& pl, bool force_split = fa
   // column slices of 32 .. 256 (one MMA, <= 512 TMEM columns with two accumulators), tcgen05.ld in 32-column chunks
   auto ok = [](int n, int nc_) { const int nc = n / nc_; return n % nc_ == 0 && nc % 32 == 0 && nc >= 32 && nc <= 256; };
   // few tiles: 8 CTAs per tile (latency, SM count); many tiles: 4 CTAs per tile (wider MMAs, fewer A re-reads)
-  const bool wide = !force_split && pl.ntiles > nsm / 8 && ok(D, 4) && ok(H, 4);
+  if (mode == 2 && !(ok(D, 4) && ok(H, 4))) return ODEVIO_E_SHAPE;
+  const bool wide = mode != 1 && (mode == 2 || pl.ntiles > nsm / 8) && ok(D, 4) && ok(H, 4);
   pl.NC = wide ? 4 : 8;
   pl.KCH = wide ? 16 : 8;
   pl.split = wide ? 0 : 1;

@@ -36,13 +36,16 @@ namespace {
 #define TC_STAMP(idx) do { } while (0)
 #endif
 
-constexpr int TC_NC = 8, TC_KCH = 8;
+// two instantiations (ft_layer.cuh): <8, 8, split> up to 16 tiles (latency: 8 CTAs per tile), <4, 16, pre-split> beyond
+// (throughput: 37 co-resident clusters, 128..256-column MMAs, no k-split reduce)
+constexpr int TC_MAX_NC = 8;
 constexpr int TC_UNIT = 16;          // features per elementwise unit (thread = row, 4 float4 of the operand image)
 
 struct TcParams {
   int M, B, L, D, NL, act;
   int K[FT_MAX_LAYERS], N[FT_MAX_LAYERS], nN[FT_MAX_LAYERS], nK[FT_MAX_LAYERS];
   const float* Wp[FT_MAX_LAYERS];
+  const float* Wlo[FT_MAX_LAYERS];   // residual image (pre-split mode only)
   const float* bias[FT_MAX_LAYERS];
   float* part; size_t part_floats;
   float* xa; size_t xa_buf_floats;
@@ -59,7 +62,7 @@ struct TcParams {
   const float* ts; int ts_ld, interval;      // row b: ts[b * ts_ld + interval] -> ts[.. + 1]
   int* stats;               // [S][L][B][2] (n_steps, n_accepted) or nullptr
   int* status;              // [B], max over layers
-  float* state; size_t state_floats;         // per cluster: (kMaxStages + 2) x [D][128] + [8][128] norm partials
+  float* state; size_t state_floats;         // per cluster: (kMaxStages + 2) x [D][128] + [TC_MAX_NC][128] norm partials
 };
 
 struct TcRows {      // per-row solver state, replicated in every CTA of the cluster (shared memory)
@@ -97,8 +100,8 @@ __device__ __forceinline__ float tc_wsum(const float (&k)[N > 0 ? N : 1][TC_GRP]
 }
 
 // stage argument y + dt * sum_{j<N} a_j k_j  ->  fp32 operand image of layer 0 (N = stage index)
-template <int N, int KCH>
-__device__ __forceinline__ void tc_stage_input(const TcSlice& sl, const float* coef, float dt, float* xa) {
+template <int N, int KCH, bool SPLIT>
+__device__ __forceinline__ void tc_stage_input(const TcSlice& sl, const float* coef, float dt, float* xa, size_t lo_off) {
   float cf[kMaxStages];
 #pragma unroll
   for (int j = 0; j < kMaxStages; ++j) cf[j] = j < N ? coef[j] : 0.f;
@@ -115,8 +118,17 @@ __device__ __forceinline__ void tc_stage_input(const TcSlice& sl, const float* c
       for (int q = 0; q < TC_GRP; ++q) y[q] = add_(y[q], mul_(dt, tc_wsum<N>(k, q, cf)));
     }
 #pragma unroll
-    for (int q = 0; q < TC_GRP / 4; ++q)
-      *reinterpret_cast<float4*>(xa + xa_offset<KCH>(sl.r, f0 + 4 * q)) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+    for (int q = 0; q < TC_GRP / 4; ++q) {
+      const size_t o = xa_offset<KCH>(sl.r, f0 + 4 * q);
+      if (SPLIT) {           // one fp32 image, split into hi / lo in shared memory by the splitter warps
+        *reinterpret_cast<float4*>(xa + o) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+      } else {               // pre-split operand images (TF32-exact high part | exact residual)
+        const float4 h = make_float4(ft_hi(y[4 * q]), ft_hi(y[4 * q + 1]), ft_hi(y[4 * q + 2]), ft_hi(y[4 * q + 3]));
+        *reinterpret_cast<float4*>(xa + o) = h;
+        *reinterpret_cast<float4*>(xa + lo_off + o) =
+            make_float4(y[4 * q] - h.x, y[4 * q + 1] - h.y, y[4 * q + 2] - h.z, y[4 * q + 3] - h.w);
+      }
+    }
   }
 }
 
@@ -205,7 +217,7 @@ __device__ __forceinline__ void tc_commit(const TcSlice& sl, int ns, int fsal) {
     default: { constexpr int NSV = 7; CALL; break; }                                                                \
   }
 
-template <int NC, int KCH>
+template <int NC, int KCH, bool SPLIT>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -329,8 +341,8 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
         TC_STAMP(41);
         if (epi) {
           const float dt = rs.dt[r];
-          if (st == 0) tc_stage_input<0, KCH>(sl, tb.a[0], dt, xa_cluster);
-          else TC_DISPATCH_STAGES(st, (tc_stage_input<(NSV < kMaxStages ? NSV : kMaxStages - 1), KCH>(sl, tb.a[st], dt, xa_cluster)))
+          if (st == 0) tc_stage_input<0, KCH, SPLIT>(sl, tb.a[0], dt, xa_cluster, p.xa_buf_floats);
+          else TC_DISPATCH_STAGES(st, (tc_stage_input<(NSV < kMaxStages ? NSV : kMaxStages - 1), KCH, SPLIT>(sl, tb.a[st], dt, xa_cluster, p.xa_buf_floats)))
           TC_STAMP(42);
           asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores -> bulk-copy (async) proxy of all CTAs
           TC_STAMP(43);
@@ -345,11 +357,11 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
           const bool last = l == p.NL - 1;
           Ld.act = last ? ACT_TANH : p.act;
           Ld.out_mode = last ? FT_OUT_FEATURE_MAJOR : FT_OUT_OPERAND;
-          Ld.Wp = p.Wp[l]; Ld.Wlo = nullptr; Ld.bias = p.bias[l];
+          Ld.Wp = p.Wp[l]; Ld.Wlo = p.Wlo[l]; Ld.bias = p.bias[l];
           Ld.a_src = xa_cluster + static_cast<size_t>(l & 1) * 2 * p.xa_buf_floats;
           Ld.nx = xa_cluster + static_cast<size_t>((l + 1) & 1) * 2 * p.xa_buf_floats;
           Ld.out = st_base + static_cast<size_t>(st) * arr; Ld.M = p.M; Ld.row0 = row0;
-          ft_layer<NC, KCH, true>(c, Ld);
+          ft_layer<NC, KCH, SPLIT>(c, Ld);
           TC_STAMP(52 + l);
         }
         TC_STAMP(45);
@@ -541,14 +553,22 @@ struct TcEvolve::Impl {
 static int tc_plan(const odevio_odernn_cfg& c, FtPlan& pl, size_t& off_state, size_t& state_floats, size_t& total_bytes) {
   const long long M = static_cast<long long>(c.L) * c.B;
   if (M <= 0 || M > 0x7fffffffLL) return ODEVIO_E_SHAPE;
-  const int rc = ft_plan(static_cast<int>(M), c.D, c.H, c.n_hidden, pl, /*force_split=*/true);
+  // up to 16 tiles (configs[1]: 2048 rows): latency matters, 8 CTAs per tile; beyond: clusters of 4 with wide pre-split MMAs
+  const int ntiles = static_cast<int>((M + FT_ROWS - 1) / FT_ROWS);
+  // (shapes one instantiation cannot slice -- e.g. H = 128 with 8 CTAs -- take the other one)
+  const int first = ntiles <= 16 ? 1 : 2;
+  int rc = ODEVIO_E_SHAPE;
+  for (int attempt = 0; attempt < 2 && rc != 0; ++attempt) {
+    rc = ft_plan(static_cast<int>(M), c.D, c.H, c.n_hidden, pl, attempt == 0 ? first : 3 - first);
+    if (rc == 0) {
+      // elementwise groups of 8 features inside the slice every CTA finalises in the last Linear, two thread halves
+      const int l = pl.NL - 1;
+      const int own_nf = pl.N[l] / pl.nN[l] / pl.nK[l];
+      if (own_nf % (2 * TC_GRP) || c.D % 4) rc = ODEVIO_E_SHAPE;
+    }
+  }
   if (rc != 0) return rc;
-  // elementwise units of 16 features inside the slice every CTA finalises in the last Linear
-  const int l = pl.NL - 1;
-  const int own_nf = pl.N[l] / pl.nN[l] / pl.nK[l];
-  if (own_nf % TC_UNIT || c.D % 4) return ODEVIO_E_SHAPE;
-  // the solver kernel must co-reside: one cluster per tile or a persistent loop over tiles (nclusters from occupancy)
-  state_floats = (static_cast<size_t>(kMaxStages + 2) * c.D + TC_NC) * FT_ROWS;
+  state_floats = (static_cast<size_t>(kMaxStages + 2) * c.D + TC_MAX_NC) * FT_ROWS;
   state_floats = (state_floats + 63) / 64 * 64;
   off_state = (pl.total_bytes / sizeof(float) + 63) / 64 * 64;
   total_bytes = (off_state + state_floats * static_cast<size_t>(pl.nclusters)) * sizeof(float);
@@ -580,10 +600,11 @@ int TcEvolve::prepare(const odevio_odernn_cfg& c, const DevTableau& tab, bool ad
   for (int l = 0; l < pl.NL; ++l) {
     if (!ode_w[l] || !ode_b[l]) return ODEVIO_E_NULL;
     p.K[l] = pl.K[l]; p.N[l] = pl.N[l]; p.nN[l] = pl.nN[l]; p.nK[l] = pl.nK[l];
-    ft_pack_weight_kernel<<<296, 256, 0, stream>>>(ode_w[l], pl.N[l], pl.K[l], pl.nN[l], pl.KCH, ws + pl.off_w[l], nullptr);
+    ft_pack_weight_kernel<<<296, 256, 0, stream>>>(ode_w[l], pl.N[l], pl.K[l], pl.nN[l], pl.KCH, ws + pl.off_w[l],
+                                                   pl.split ? nullptr : ws + pl.off_wlo[l]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
-    p.Wp[l] = ws + pl.off_w[l]; p.bias[l] = ode_b[l];
+    p.Wp[l] = ws + pl.off_w[l]; p.Wlo[l] = ws + pl.off_wlo[l]; p.bias[l] = ode_b[l];
   }
   p.xa = ws + pl.off_xa; p.xa_buf_floats = pl.xa_buf_floats;
   p.part = ws + pl.off_part; p.part_floats = pl.part_floats;
@@ -595,18 +616,24 @@ int TcEvolve::prepare(const odevio_odernn_cfg& c, const DevTableau& tab, bool ad
   return 0;
 }
 
+typedef void (*TcKernel)(TcParams);
+static TcKernel tc_kernel_of(const FtPlan& pl) {
+  return pl.NC == 8 ? static_cast<TcKernel>(odernn_tc_evolve_kernel<8, 8, true>)
+                    : static_cast<TcKernel>(odernn_tc_evolve_kernel<4, 16, false>);
+}
 static cudaError_t tc_launch_config(const FtPlan& pl, cudaLaunchConfig_t& lc, cudaLaunchAttribute& at, int nclusters,
                                     cudaStream_t stream) {
-  auto kern = odernn_tc_evolve_kernel<TC_NC, TC_KCH>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem_bytes));
+  cudaError_t e = cudaFuncSetAttribute(tc_kernel_of(pl), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem_bytes));
   if (e != cudaSuccess) return e;
   memset(&lc, 0, sizeof(lc));
   lc.blockDim = dim3(FT_THREADS); lc.dynamicSmemBytes = pl.smem_bytes; lc.stream = stream;
-  at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = TC_NC; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = pl.NC; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
   lc.attrs = &at; lc.numAttrs = 1;
-  lc.gridDim = dim3(nclusters * TC_NC);
+  lc.gridDim = dim3(nclusters * pl.NC);
   return cudaSuccess;
 }
+
+int TcEvolve::cluster_size() const { return impl ? impl->pl.NC : 0; }
 
 int TcEvolve::max_clusters() {
   if (!impl) return 0;
@@ -614,7 +641,7 @@ int TcEvolve::max_clusters() {
   cudaLaunchConfig_t lc; cudaLaunchAttribute at;
   if (tc_launch_config(impl->pl, lc, at, impl->pl.nclusters, nullptr) != cudaSuccess) { cudaGetLastError(); return impl->pl.nclusters; }
   int maxc = 0;
-  if (cudaOccupancyMaxActiveClusters(&maxc, odernn_tc_evolve_kernel<TC_NC, TC_KCH>, &lc) != cudaSuccess || maxc <= 0) {
+  if (cudaOccupancyMaxActiveClusters(&maxc, tc_kernel_of(impl->pl), &lc) != cudaSuccess || maxc <= 0) {
     cudaGetLastError();
     maxc = impl->pl.nclusters;
   }
@@ -641,7 +668,7 @@ int TcEvolve::evolve(float* Y, int Bsub, const int* seq, const float* ts, int ts
   g_tc_last_clusters = nclusters; g_tc_last_max_clusters = impl->maxc; g_tc_last_rows = rows;
   const bool timed = g_tc_timing && g_tc_timing_n < kTimingSlots;
   if (timed) cudaEventRecord(g_tc_ev[g_tc_timing_n][0], stream);
-  e = cudaLaunchKernelEx(&lc, odernn_tc_evolve_kernel<TC_NC, TC_KCH>, p);
+  e = cudaLaunchKernelEx(&lc, tc_kernel_of(pl), p);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (timed) { cudaEventRecord(g_tc_ev[g_tc_timing_n][1], stream); ++g_tc_timing_n; }
   e = cudaGetLastError();

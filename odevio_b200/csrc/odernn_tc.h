@@ -40,6 +40,7 @@ class TcEvolve {
               const float* const* ode_b, void* workspace, size_t workspace_bytes, cudaStream_t stream);
   // clusters of 8 CTAs that can be co-resident on this GPU (cudaOccupancyMaxActiveClusters; 15-16 on B200)
   int max_clusters();
+  int cluster_size() const;          // 8 (up to 16 tiles) or 4 (beyond)
   // evolves, in place over interval `interval`, the L * Bsub rows (l, b = seq[j]), j < Bsub, of Y[L][B][D]
   // (seq == nullptr: b = j); row b integrates ts[b * ts_ld + interval] -> ts[.. + 1].  Other rows are left to the caller.
   int evolve(float* Y, int Bsub, const int* seq, const float* ts, int ts_ld, int interval, int* stats, int* status,

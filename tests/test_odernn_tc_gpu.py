@@ -63,11 +63,12 @@ def test_tc_prev_state_and_gru(cuda_device):
     _check(out)
 
 
-@pytest.mark.parametrize("B", [1024, 1200])
+@pytest.mark.parametrize("B", [1024, 1200, 2600])
 def test_tc_full_size_rows_match_oracle_subset(cuda_device, B):
     """configs[1] at full size on the tensor-core path.  B = 1024 -> 2048 rows = 16 tiles: on a GPU that holds 15
-    clusters the last 128 rows run concurrently in the FMA kernel (side launch); B = 1200 -> 19 tiles: the cluster
-    kernel's persistent loop takes a second round.  The oracle runs a random subset of rows (rows are independent);
+    clusters 64 sequences per interval run concurrently in the FMA kernel (side launch); B = 1200 -> 19 tiles: the
+    clusters-of-4 pre-split instantiation, one round; B = 2600 -> 41 tiles > 37 co-resident clusters of 4: its
+    persistent loop takes a second round.  The oracle runs a random subset of rows (rows are independent);
     same criterion as tests/test_full_size_gpu.py.  Also: the rows agree with the fp32 FMA kernel to 1e-5 wherever
     both kernels took the same accept/reject history."""
     import odevio_b200

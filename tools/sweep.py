@@ -17,10 +17,11 @@ from bench import init_like_deepvio
 from types import SimpleNamespace
 
 
-def point(dev, B, H, solver, S=10, L=2, n=3, reps=2):
+def point(dev, B, H, solver, S=10, L=2, n=3, reps=2, precision="tf32x3"):
     opt = SimpleNamespace(v_f_len=512, i_f_len=256, fuse_method="cat", ode_hidden_dim=H, ode_fn_num_layers=n,
                           ode_activation_fn="tanh", ode_solver=solver, ode_rnn_type="rnn", rnn_num_layers=L,
-                          rnn_hidden_dim=1024, rnn_dropout_out=0.0, ode_rtol=1e-3, ode_atol=1e-6, ode_dt0=1e-4)
+                          rnn_hidden_dim=1024, rnn_dropout_out=0.0, ode_rtol=1e-3, ode_atol=1e-6, ode_dt0=1e-4,
+                          ode_precision=precision)
     model = odevio_b200.PoseODERNN(opt)
     init_like_deepvio(model, seed=0)
     model = model.to(dev).eval()
@@ -43,7 +44,7 @@ def point(dev, B, H, solver, S=10, L=2, n=3, reps=2):
     evals = (4.0 * st.sum().item()) if solver == "rk4" else (6.0 * st + (st > 0).double()).sum().item()
     flops = evals * f_ode + B * S * (L * 4 * D * D + 2 * (D * 128 + 128 * 6))
     assert int(model.last_status.max().item()) == 0
-    return {"B": B, "H": H, "solver": solver, "ms_per_forward": ms, "seq_steps_per_s": B * S / (ms * 1e-3),
+    return {"B": B, "H": H, "solver": solver, "precision": precision, "ms_per_forward": ms, "seq_steps_per_s": B * S / (ms * 1e-3),
             "algorithmic_tflops": flops / (ms * 1e-3) / 1e12, "mean_steps_per_interval": st.mean().item()}
 
 
@@ -51,6 +52,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep_fwd.json"))
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3"],
+                    help="tf32x3: tensor-core solver (clusters of 8 up to 16 tiles, clusters of 4 beyond); fp32: FFMA kernel")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     Bs = [256, 4096] if args.quick else [256, 1024, 4096, 16384, 65536]
@@ -59,7 +62,11 @@ def main():
     for solver in ("rk4", "dopri5"):
         for H in Hs:
             for B in Bs:
-                r = point(dev, B, H, solver)
+                try:
+                    r = point(dev, B, H, solver, precision=args.precision)
+                except odevio_b200.OdevioError as err:       # shape outside the tcgen05 tiling: FFMA kernel
+                    r = point(dev, B, H, solver, precision="fp32")
+                    r["note"] = f"{args.precision} unsupported here ({err}); FFMA kernel"
                 rows.append(r)
                 print(json.dumps(r), flush=True)
     with open(args.out, "w") as fh:
