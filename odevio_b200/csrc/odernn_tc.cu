@@ -501,8 +501,11 @@ __global__ void tc_select_kernel(const float* __restrict__ ts, int B, int S, int
 
 int odernn_tc_select(const float* ts, int B, int S, int n_side, int* seq, cudaStream_t stream) {
   if (B > 8192 || n_side <= 0 || n_side >= B) return ODEVIO_E_SHAPE;
-  tc_select_kernel<<<S, 1024, static_cast<size_t>(B) * 8, stream>>>(ts, B, S, n_side, seq);
-  const cudaError_t e = cudaGetLastError();
+  const size_t smem = static_cast<size_t>(B) * 8;
+  cudaError_t e = cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  tc_select_kernel<<<S, 1024, smem, stream>>>(ts, B, S, n_side, seq);
+  e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }
 
