@@ -328,6 +328,25 @@ ODEVIO_API int32_t odevio_imu_encoder_forward(int32_t B, int32_t S, int32_t i_f_
                                               void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Training-loop glue downstream of odevio_odernn_backward.
+ * odevio_pose_loss: reference scripts/train_model.py:72-76 -- loss3[0] = w_angle * MSE(pose[:, :3], gts[:, :3]) +
+ *   MSE(pose[:, 3:], gts[:, 3:]) (w_angle = 100), loss3[1] = the angle MSE, loss3[2] = the translation MSE (DEVICE
+ *   float[3]); grad_pose (may be NULL) = grad_scale * d loss3[0] / d pose.  pose, gts, grad_pose: [n_rows, 6].
+ * odevio_adam_step: torch.nn.utils.clip_grad_norm_(max_norm) (scripts/train_model.py:83-85; max_norm <= 0: none)
+ *   followed by one torch.optim.Adam step (src/utils/utils.py:150-157: L2 weight decay, no amsgrad) on a flat fp32
+ *   bucket of n values -- the bucket of the NCCL gradient all-reduce.  step = 1, 2, ... ; norm_coef (DEVICE float[2],
+ *   required with max_norm > 0) receives the total gradient norm and the clip coefficient.  All four arrays 16-byte
+ *   aligned.  No host synchronisation.
+ * workspace: odevio_train_glue_workspace_bytes() bytes, 16-byte aligned.
+ */
+ODEVIO_API size_t odevio_train_glue_workspace_bytes(void);
+ODEVIO_API int32_t odevio_pose_loss(int64_t n_rows, const float* pose, const float* gts, float w_angle, float grad_scale,
+                                    float* loss3, float* grad_pose, void* workspace, size_t workspace_bytes, void* stream);
+ODEVIO_API int32_t odevio_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                    int32_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                    float max_norm, float* norm_coef, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Diagnostics (no reference counterpart): launch a dense FFMA loop on `blocks` CTAs of 512 threads
  * and report the FLOPs it performs in *flops_out (HOST); time it with events around the call to
  * obtain this GPU's fp32 FMA peak, the roofline denominator of ODEVIO_PRECISION_FP32.

@@ -141,6 +141,12 @@ def load():
     lib.odevio_imu_encoder_forward.restype = C.c_int32
     lib.odevio_imu_encoder_forward.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(ImuEncoderWeights), _FP, _FP,
                                                _FP, C.c_size_t, _FP]
+    lib.odevio_train_glue_workspace_bytes.restype = C.c_size_t
+    lib.odevio_train_glue_workspace_bytes.argtypes = []
+    lib.odevio_pose_loss.restype = C.c_int32
+    lib.odevio_pose_loss.argtypes = [C.c_int64, _FP, _FP, C.c_float, C.c_float, _FP, _FP, _FP, C.c_size_t, _FP]
+    lib.odevio_adam_step.restype = C.c_int32
+    lib.odevio_adam_step.argtypes = [C.c_int64, _FP, _FP, _FP, _FP, C.c_int32] + [C.c_float] * 6 + [_FP, _FP, C.c_size_t, _FP]
     lib.odevio_debug_tc_geometry.restype = C.c_int32
     lib.odevio_debug_tc_geometry.argtypes = [C.POINTER(C.c_int32)]
     lib.odevio_debug_tc_timing.restype = C.c_int32

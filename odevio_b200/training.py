@@ -1,0 +1,143 @@
+"""Training-loop glue of the regressor path on the device.
+
+Reference: scripts/train_model.py:69-86 (loss = 100 * MSE(angles) + MSE(translations), backward, global-norm clip 5,
+optimizer.step) and src/utils/utils.py:143-157 (Adam over the two ``Pose_net`` parameter groups, lr, betas (0.9, 0.999),
+eps 1e-8, weight_decay 5e-5).  Here:
+
+* :func:`fused_pose_loss` -- loss value(s) and d loss / d poses in ONE kernel (``odevio_pose_loss``), as an autograd
+  function so it drops into the reference's ``loss.backward()``;
+* :class:`FusedPoseNetAdam` -- the ``Pose_net`` parameters live as views of one flat fp32 buffer (state_dict keys and
+  shapes unchanged, reference checkpoints still load with ``load_state_dict``); the gradients are gathered into the flat
+  bucket that the NCCL all-reduce needs anyway, and ``odevio_adam_step`` runs clip + Adam on that bucket in three
+  launches with the clip coefficient kept on the device -- the optimiser step is the all-reduce's epilogue;
+* :func:`fused_train_step` -- forward (fused kernels), loss, backward (fused kernels), all-reduce, clip + Adam.
+
+No CPU path: CUDA tensors only (the reference-equivalent torch ops remain in ``odevio_b200.distributed`` and are what the
+tests compare against -- torch.optim.Adam / clip_grad_norm_ / mse_loss are the reference's own dependencies).
+"""
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .distributed import pose_net_params
+
+
+def _workspace(dev):
+    lib = _lib.load()
+    n = lib.odevio_train_glue_workspace_bytes()
+    return torch.empty(n, dtype=torch.uint8, device=dev), n
+
+
+class _PoseLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, poses, gts, w_angle):
+        lib = _lib.load()
+        if not poses.is_cuda:
+            raise _lib.OdevioError("fused_pose_loss needs CUDA tensors: odevio_b200 has no CPU path")
+        p = poses.detach().to(torch.float32).contiguous()
+        g = gts.detach().to(torch.float32).contiguous()
+        if p.shape != g.shape or p.shape[-1] != 6:
+            raise _lib.OdevioError(f"poses / gts must both be [..., 6], got {tuple(p.shape)} / {tuple(g.shape)}")
+        n_rows = p.numel() // 6
+        loss3 = torch.empty(3, dtype=torch.float32, device=p.device)
+        grad = torch.empty_like(p) if poses.requires_grad else None
+        ws, nbytes = _workspace(p.device)
+        with torch.cuda.device(p.device):
+            rc = lib.odevio_pose_loss(n_rows, _lib.dptr(p), _lib.dptr(g), float(w_angle), 1.0, _lib.dptr(loss3),
+                                      _lib.dptr(grad), _lib.dptr(ws), nbytes,
+                                      C.c_void_p(torch.cuda.current_stream(p.device).cuda_stream))
+        _lib.check(rc)
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(loss3)
+        return loss3[0].clone(), loss3
+    
+    @staticmethod
+    def backward(ctx, gout, _g3):
+        (grad,) = ctx.saved_tensors
+        return (None if grad is None else grad * gout), None, None
+
+
+def fused_pose_loss(poses, gts, w_angle=100.0, with_parts=False):
+    """scripts/train_model.py:72-76.  Returns the scalar loss (differentiable w.r.t. ``poses``); with ``with_parts`` also the
+    device tensor [loss, angle_mse, translation_mse] the reference logs (:91)."""
+    loss, loss3 = _PoseLoss.apply(poses, gts, w_angle)
+    return (loss, loss3) if with_parts else loss
+
+
+class FusedPoseNetAdam:
+    """Adam (+ global-norm clip) over the reference's ``Pose_net`` parameter set on one flat bucket.
+
+    ``params``: the regressor group then the other parameters (utils/utils.py:143-147), as ``pose_net_params(model)``
+    returns them.  Both reference groups share lr / weight_decay (utils.py:150-157), so one bucket is exact."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-5, max_norm=5.0):
+        self.params = [p for p in pose_net_params(model) if p.requires_grad]
+        if not self.params or not self.params[0].is_cuda:
+            raise _lib.OdevioError("FusedPoseNetAdam needs the model on a CUDA device: odevio_b200 has no CPU path")
+        dev = self.params[0].device
+        # every parameter starts on a 256-byte boundary of the bucket (the kernels' bulk-TMA / 128-bit accesses assume the
+        # alignment of a fresh allocation); the padding stays exactly zero under clip + Adam (g = 0, wd * 0 = 0)
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 63) // 64 * 64
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):      # parameters become views of the flat buffer (keys / shapes unchanged)
+                n = p.numel()
+                self.flat[o:o + n].copy_(p.data.reshape(-1))
+                p.data = self.flat[o:o + n].view_as(p.data)
+        self.grads = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.norm_coef = torch.zeros(2, dtype=torch.float32, device=dev)      # [total grad norm, clip coefficient]
+        self.step_count = 0
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self._ws, self._ws_bytes = _workspace(dev)
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def gather_grads(self, weight=1.0):
+        """p.grad of every parameter -> the flat bucket (scaled); missing gradients count as zero."""
+        for p, o in zip(self.params, self.offsets):
+            dst = self.grads[o:o + p.numel()]
+            if p.grad is None:
+                dst.zero_()
+            else:
+                dst.copy_(p.grad.reshape(-1))
+        if weight != 1.0:
+            self.grads.mul_(weight)
+        return self.grads
+
+    def step(self):
+        """clip_grad_norm_(max_norm) + Adam on the bucket (three launches, no host synchronisation)."""
+        lib = _lib.load()
+        self.step_count += 1
+        dev = self.flat.device
+        with torch.cuda.device(dev):
+            rc = lib.odevio_adam_step(self.flat.numel(), _lib.dptr(self.flat), _lib.dptr(self.grads), _lib.dptr(self.exp_avg),
+                                      _lib.dptr(self.exp_avg_sq), self.step_count, self.lr, self.betas[0], self.betas[1],
+                                      self.eps, self.weight_decay, float(self.max_norm or 0.0), _lib.dptr(self.norm_coef),
+                                      _lib.dptr(self._ws), self._ws_bytes,
+                                      C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc)
+
+
+def fused_train_step(model, opt, fv, fi, ts, gts, world_size=1, group=None):
+    """One optimisation step on this rank's shard (scripts/train_model.py:69-86) with the glue on the device: fused forward
+    (checkpoints), fused loss + d loss / d poses, fused backward, ONE flat-bucket all-reduce, clip + Adam as its epilogue."""
+    opt.zero_grad()
+    poses, _ = model(fv, fi, ts, prev=None)
+    loss = fused_pose_loss(poses, gts)
+    loss.backward()
+    flat = opt.gather_grads(1.0 / world_size if world_size > 1 else 1.0)
+    if world_size > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    opt.step()
+    return loss.detach()

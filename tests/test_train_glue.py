@@ -1,0 +1,114 @@
+"""Training-loop glue: fused pose loss and flat-bucket clip + Adam against the reference's own
+dependencies -- torch.nn.functional.mse_loss, torch.nn.utils.clip_grad_norm_, torch.optim.Adam with the reference's
+hyper-parameters (scripts/train_model.py:72-86, src/utils/utils.py:150-157).  PINNED: torch IS what the reference runs."""
+
+import copy
+
+import pytest
+import torch
+
+from odevio_b200.distributed import make_optimizer, pose_loss, pose_net_params
+
+
+def test_flat_views_keep_state_dict_keys_and_values():
+    """Host logic (CPU): re-pointing the parameters at one flat buffer keeps names, shapes and values, and later
+    load_state_dict() writes through to the buffer (reference checkpoints keep loading)."""
+    from oracle.pose_odernn import OraclePoseODERNN, default_opt
+    torch.manual_seed(0)
+    m = OraclePoseODERNN(default_opt(v_f_len=24, i_f_len=8, ode_hidden_dim=16))
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    params = pose_net_params(m)
+    flat = torch.zeros(sum(p.numel() for p in params))
+    off = 0
+    for p in params:
+        n = p.numel()
+        flat[off:off + n].copy_(p.data.reshape(-1))
+        p.data = flat[off:off + n].view_as(p.data)
+        off += n
+    after = m.state_dict()
+    assert list(before) == list(after) and all(torch.equal(before[k], after[k]) for k in before)
+    m.load_state_dict({k: v + 1 for k, v in before.items()})
+    assert torch.equal(flat, torch.cat([(before[n] + 1).reshape(-1) for n, _ in
+                                        [(n, p) for grp in (True, False) for n, p in m.named_parameters()
+                                         if n.startswith("regressor") == grp]]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [(4, 3), (1024, 10), (333, 7)])
+def test_fused_pose_loss_matches_torch(cuda_device, n):
+    from odevio_b200.training import fused_pose_loss
+    g = torch.Generator().manual_seed(1)
+    poses = torch.randn(*n, 6, generator=g).to(cuda_device).requires_grad_(True)
+    gts = (0.1 * torch.randn(*n, 6, generator=g)).to(cuda_device)
+    loss, parts = fused_pose_loss(poses, gts, with_parts=True)
+    (3.0 * loss).backward()
+    p2 = poses.detach().clone().requires_grad_(True)
+    want = pose_loss(p2, gts)
+    (3.0 * want).backward()
+    assert abs(loss.item() - want.item()) <= 2e-6 * abs(want.item())
+    assert abs(parts[1].item() - torch.nn.functional.mse_loss(p2[..., :3], gts[..., :3]).item()) <= 2e-6 * parts[1].item()
+    assert ((poses.grad - p2.grad).abs().max() / p2.grad.abs().max()).item() <= 2e-6
+
+
+@pytest.mark.gpu
+def test_fused_adam_matches_torch_adam_with_clip(cuda_device):
+    """Five optimisation steps of the flat-bucket clip + Adam vs clip_grad_norm_ + torch.optim.Adam on identical
+    parameters and gradients; one step with a gradient norm above the clip threshold, the others below."""
+    import odevio_b200
+    from odevio_b200.training import FusedPoseNetAdam
+    from oracle.pose_odernn import default_opt
+    opt = default_opt()
+    torch.manual_seed(0)
+    a = odevio_b200.PoseODERNN(opt).to(cuda_device)
+    b = copy.deepcopy(a)
+    fused = FusedPoseNetAdam(a, lr=1e-3, weight_decay=5e-5, max_norm=5.0)
+    ref_opt = make_optimizer(b, lr=1e-3, weight_decay=5e-5)
+    keys = list(a.state_dict())
+    g = torch.Generator().manual_seed(3)
+    for step in range(5):
+        scale = 50.0 if step == 2 else 0.01                       # step 2 exceeds max_norm = 5
+        for pa, pb in zip(pose_net_params(a), pose_net_params(b)):
+            gr = (scale * torch.randn(pa.shape, generator=g) / pa.numel() ** 0.5).to(cuda_device)
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        fused.gather_grads()
+        fused.step()
+        norm = torch.nn.utils.clip_grad_norm_(pose_net_params(b), max_norm=5.0)
+        ref_opt.step()
+        assert abs(fused.norm_coef[0].item() - norm.item()) <= 1e-5 * norm.item()
+        assert (fused.norm_coef[1].item() < 1.0) == (norm.item() > 5.0)
+        for pa, pb in zip(pose_net_params(a), pose_net_params(b)):
+            assert ((pa - pb).abs().max() / pb.abs().max().clamp_min(1e-12)).item() <= 1e-5, step
+    assert list(a.state_dict()) == keys                            # checkpoint keys unchanged by the flat views
+
+
+@pytest.mark.gpu
+def test_fused_train_step_matches_reference_glue(cuda_device):
+    """Whole step: fused forward/backward + fused glue vs fused forward/backward + the torch glue of
+    odevio_b200.distributed.train_step (mse_loss, clip_grad_norm_, torch.optim.Adam): same loss, same parameters."""
+    import odevio_b200
+    from helpers import inputs
+    from odevio_b200.distributed import train_step
+    from odevio_b200.training import FusedPoseNetAdam, fused_train_step
+    from oracle.pose_odernn import default_opt
+    opt = default_opt(ode_solver="rk4")
+    torch.manual_seed(0)
+    a = odevio_b200.PoseODERNN(opt).to(cuda_device).train()
+    b = copy.deepcopy(a)
+    fused = FusedPoseNetAdam(a)
+    ref_opt = make_optimizer(b)
+    fv, fi, ts = (t.to(cuda_device) for t in inputs(16, S=4))
+    gts = (0.1 * torch.randn(16, 4, 6, generator=torch.Generator().manual_seed(2))).to(cuda_device)
+    p0 = [p.detach().clone() for p in pose_net_params(b)]
+    steps, lr = 3, 1e-3
+    for _ in range(steps):
+        la = fused_train_step(a, fused, fv, fi, ts, gts)
+        lb = train_step(b, ref_opt, fv, fi, ts, gts)
+        assert abs(la.item() - lb.item()) <= 1e-5 * abs(lb.item())
+    # Adam normalises every element's update to ~lr * sign(g): elements whose gradient is at the fp32 noise level of the
+    # backward (a cancellation residue ~1e-6 of the tensor's largest gradient; the two loss backwards round differently)
+    # legitimately move differently.  So: the update VECTORS agree in the L2 sense, no element is off by more than the
+    # steps could move it, and the identical-gradient test above pins the optimiser arithmetic itself to 1e-5.
+    da = torch.cat([(x.detach() - z).reshape(-1) for x, z in zip(pose_net_params(a), p0)])
+    db = torch.cat([(y.detach() - z).reshape(-1) for y, z in zip(pose_net_params(b), p0)])
+    assert ((da - db).norm() / db.norm()).item() <= 2e-2, ((da - db).norm() / db.norm()).item()
+    assert (da - db).abs().max().item() <= 2 * lr * steps
