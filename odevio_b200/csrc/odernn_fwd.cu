@@ -53,13 +53,22 @@ __device__ __forceinline__ void global_ids(const FwdParams& p, int l, int b, int
 
 __device__ __forceinline__ float4 wsum4(const float* const* K, const float* coef, int n, size_t off,
                                         bool& any) {
-  // acc = c0*k0 + c1*k1 + ... left to right, skipping exact zeros (oracle/_weighted_sum)
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // acc = c0*k0 + c1*k1 + ... left to right, skipping exact zeros (oracle/_weighted_sum).
+  // All stage vectors are loaded first (warp-uniform predicates, independent 128-bit loads): one L2 round trip per
+  // element instead of one per term -- the per-term load -> use chain was ~12 % of the kernel's warp time (ncu
+  // long_scoreboard), see DESIGN.md 4.6 for the same fix in the tensor-core solver.
+  static_assert(kMaxStages == 7, "wsum4 is written out for 7 stages");
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool u0 = 0 < n && coef[0] != 0.f, u1 = 1 < n && coef[1] != 0.f, u2 = 2 < n && coef[2] != 0.f,
+             u3 = 3 < n && coef[3] != 0.f, u4 = 4 < n && coef[4] != 0.f, u5 = 5 < n && coef[5] != 0.f,
+             u6 = 6 < n && coef[6] != 0.f;
+  const float4 k0 = u0 ? ld4(K[0] + off) : z4, k1 = u1 ? ld4(K[1] + off) : z4, k2 = u2 ? ld4(K[2] + off) : z4,
+               k3 = u3 ? ld4(K[3] + off) : z4, k4 = u4 ? ld4(K[4] + off) : z4, k5 = u5 ? ld4(K[5] + off) : z4,
+               k6 = u6 ? ld4(K[6] + off) : z4;
+  float4 acc = z4;
   any = false;
-  for (int j = 0; j < n; ++j) {
-    const float cj = coef[j];
-    if (cj == 0.f) continue;
-    const float4 k = ld4(K[j] + off);
+  auto term = [&](bool u, const float4& k, float cj) {
+    if (!u) return;
     if (!any) {
       acc = make_float4(mul_(k.x, cj), mul_(k.y, cj), mul_(k.z, cj), mul_(k.w, cj));
       any = true;
@@ -67,7 +76,9 @@ __device__ __forceinline__ float4 wsum4(const float* const* K, const float* coef
       acc = make_float4(add_(acc.x, mul_(k.x, cj)), add_(acc.y, mul_(k.y, cj)),
                         add_(acc.z, mul_(k.z, cj)), add_(acc.w, mul_(k.w, cj)));
     }
-  }
+  };
+  term(u0, k0, coef[0]); term(u1, k1, coef[1]); term(u2, k2, coef[2]); term(u3, k3, coef[3]);
+  term(u4, k4, coef[4]); term(u5, k5, coef[5]); term(u6, k6, coef[6]);
   return acc;
 }
 
