@@ -18,6 +18,7 @@
 // (odernn_fwd.cu): M = B rows there, too few for the tensor core to matter (5 % of the FLOPs).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/odevio.h"
@@ -559,7 +560,9 @@ static int tc_plan(const odevio_odernn_cfg& c, FtPlan& pl, size_t& off_state, si
   // up to 16 tiles (configs[1]: 2048 rows): latency matters, 8 CTAs per tile; beyond: clusters of 4 with wide pre-split MMAs
   const int ntiles = static_cast<int>((M + FT_ROWS - 1) / FT_ROWS);
   // (shapes one instantiation cannot slice -- e.g. H = 128 with 8 CTAs -- take the other one)
-  const int first = ntiles <= 16 ? 1 : 2;
+  // development override: ODEVIO_TC_MODE=1 (clusters of 8) / 2 (clusters of 4) regardless of the tile count
+  const char* force = getenv("ODEVIO_TC_MODE");
+  const int first = (force && (force[0] == '1' || force[0] == '2')) ? force[0] - '0' : (ntiles <= 16 ? 1 : 2);
   int rc = ODEVIO_E_SHAPE;
   for (int attempt = 0; attempt < 2 && rc != 0; ++attempt) {
     rc = ft_plan(static_cast<int>(M), c.D, c.H, c.n_hidden, pl, attempt == 0 ? first : 3 - first);
