@@ -332,6 +332,7 @@ cde_fwd_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ De
   c.ring.empty = bars + MAX_STAGES;
   c.ring.stage_floats = prm.stage_floats;
   c.ring.nst = prm.nst;
+  c.ring.kc = KC;
   c.pos.stage = 0; c.pos.phase = 0; c.pos.ready = 0;
   if (tid == 0) {
     for (int s = 0; s < prm.nst; ++s) {

@@ -178,6 +178,7 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
   c.ring.empty = bars + MAX_STAGES;
   c.ring.stage_floats = prm.stage_floats;
   c.ring.nst = prm.nst;
+  c.ring.kc = static_cast<uint32_t>(prm.kc);
   c.pos.stage = 0; c.pos.phase = 0; c.pos.ready = 0;
   if (tid == 0) {
     for (int s = 0; s < prm.nst; ++s) {
@@ -510,7 +511,7 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
           ph = BP_TILE_END;
           break;
       }
-      if (do_gemm) tile_gemm<RT, LL>(c.ring, c.pos, c.th, op.W, op.K, op.N, op.in, op.ode_layout, op.epi);
+      if (do_gemm) tile_gemm<RT, LL, true>(c.ring, c.pos, c.th, op.W, op.K, op.N, op.in, op.ode_layout, op.epi);
     }
 
     // ---- gradient of the initial hidden state

@@ -444,6 +444,7 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
   c.ring.empty = bars + MAX_STAGES;
   c.ring.stage_floats = prm.stage_floats;
   c.ring.nst = prm.nst;
+  c.ring.kc = static_cast<uint32_t>(prm.kc);
   c.pos.stage = 0;
   c.pos.phase = 0;
   c.pos.ready = 0;
@@ -660,7 +661,7 @@ odernn_fwd_kernel(const __grid_constant__ FwdParams prm) {
           ph = PH_TILE_END;
           break;
       }
-      if (do_gemm) tile_gemm<RT, LL>(c.ring, c.pos, c.th, op.W, op.K, op.N, op.in, op.ode_layout, op.epi);
+      if (do_gemm) tile_gemm<RT, LL, true>(c.ring, c.pos, c.th, op.W, op.K, op.N, op.in, op.ode_layout, op.epi);
     }
 
     // ---- final hidden state and status

@@ -65,6 +65,7 @@ struct FwdParams {
   // launch geometry
   int ntiles, nst;
   int bufA_floats, bufB_floats, stage_floats;
+  int kc;                    // k-rows per weight stage (8 or 16; divides D, H)
   // training checkpoints (nullptr: inference).  Per tile, per interval i (T-layout arrays of D*R floats):
   //   [Yend | Ypost | CK x (Y0 | dt[R] | upd[R])]; nloops[tile * S + i] = stored solver iterations
   float* ckpt; int* nloops; size_t ckpt_floats_per_tile; int CK;
@@ -116,6 +117,7 @@ struct BwdParams {
   float* scratch; size_t scratch_floats_per_cta;
   int ntiles, nst;
   int buf_floats, stage_floats;
+  int kc;                                    // k-rows per weight stage (8 or 16)
 };
 
 }  // namespace odevio

@@ -17,7 +17,9 @@
 
 namespace odevio {
 
-constexpr int KC = 8;           // k-rows per weight stage
+constexpr int KC = 8;           // k-rows per weight stage; kernels that opt in (tile_gemm<.., ALLOW16>) also run 16-row stages
+                                // (ring.kc = 16: half the mbarrier waits / arrives per k and a longer software pipeline:
+                                // measured +7 % on the forward, +5 % on the training step)
 
 // tuning switches (A/B-tested on the B200, see profiles/)
 #ifndef ODEVIO_PRODUCER_WAIT
@@ -38,6 +40,7 @@ struct WeightRing {
   uint64_t* empty;       // [nst] one arrive per consumer warp
   uint32_t stage_floats;
   uint32_t nst;
+  uint32_t kc;           // k-rows per stage: a multiple of KC that divides every K streamed through this ring
 };
 
 // Running position in the ring; every thread keeps its own copy, all in lock-step.
@@ -108,8 +111,8 @@ __device__ __forceinline__ float dact_from_output(float h, int act) {
 // One lane of the producer warp: stream Wt[K][N] in KC-row chunks.
 __device__ __forceinline__ void pipe_produce(const WeightRing& ring, RingPos& pos,
                                              const float* __restrict__ Wt, int K, int N) {
-  const uint32_t bytes = static_cast<uint32_t>(KC) * N * sizeof(float);
-  const int nch = K / KC;
+  const uint32_t bytes = ring.kc * static_cast<uint32_t>(N) * sizeof(float);
+  const int nch = K / static_cast<int>(ring.kc);
   for (int ch = 0; ch < nch; ++ch) {
 #if ODEVIO_PRODUCER_WAIT == 2
     mbar_wait_parked(&ring.empty[pos.stage], pos.phase ^ 1u);
@@ -120,7 +123,7 @@ __device__ __forceinline__ void pipe_produce(const WeightRing& ring, RingPos& po
 #endif
     mbar_arrive_expect_tx(&ring.full[pos.stage], bytes);
     tma_load_1d(ring.buf + static_cast<size_t>(pos.stage) * ring.stage_floats,
-                Wt + static_cast<size_t>(ch) * KC * N, bytes, &ring.full[pos.stage]);
+                Wt + static_cast<size_t>(ch) * ring.kc * N, bytes, &ring.full[pos.stage]);
     pos.advance(ring.nst);
   }
 }
@@ -210,7 +213,7 @@ __device__ __forceinline__ void run_epilogue(const Epilogue& e, int n, int rb, c
 // registers.  Returns the advanced ring position packed as stage | phase << 8.
 // Operands are addressed as offsets from the dynamic shared-memory base so the compiler emits
 // LDS (shared-space) loads in the hot loop instead of generic LD.
-template <int RT, int P>
+template <int RT, int P, int KCT>
 __device__ __forceinline__ uint32_t gemm_body(WeightRing ring, uint32_t pos_packed, uint32_t in_off,
                                            int ld, int K, int N, int rb, int cg, int tpb, int lane,
                                            const Epilogue* __restrict__ epi) {
@@ -228,7 +231,7 @@ __device__ __forceinline__ uint32_t gemm_body(WeightRing ring, uint32_t pos_pack
 #pragma unroll
     for (int r = 0; r < RT; ++r) { acc[pp][0][r] = 0.f; acc[pp][1][r] = 0.f; }
   }
-  const int nch = K / KC;
+  const int nch = K / KCT;
   // Software-pipelined over k with two operand register sets: the loads of step kk+1 are issued
   // before the FFMAs of step kk, so the ~30-cycle LDS latency hides behind 16*P FFMAs instead of
   // being exposed twice per step (ncu: short_scoreboard was the top stall without this).
@@ -258,7 +261,7 @@ __device__ __forceinline__ uint32_t gemm_body(WeightRing ring, uint32_t pos_pack
   for (int ch = 0; ch < nch; ++ch) {
     if (!ready) mbar_wait(&ring.full[pos.stage], pos.phase);
     const float* __restrict__ ws = ring_buf + pos.stage * ring.stage_floats;
-    const float* __restrict__ xp = inT + ch * KC * ld;
+    const float* __restrict__ xp = inT + ch * KCT * ld;
     const uint32_t cur = pos.stage;
     pos.advance(ring.nst);
 #if ODEVIO_EARLY_PROBE
@@ -269,10 +272,10 @@ __device__ __forceinline__ uint32_t gemm_body(WeightRing ring, uint32_t pos_pack
 #endif
     load_operands(xp, ws, 0, xa, wa);
 #pragma unroll
-    for (int kk = 0; kk < KC; kk += 2) {
+    for (int kk = 0; kk < KCT; kk += 2) {
       load_operands(xp, ws, kk + 1, xb, wb);
       fma_step(xa, wa);
-      if (kk + 2 < KC) load_operands(xp, ws, kk + 2, xa, wa);
+      if (kk + 2 < KCT) load_operands(xp, ws, kk + 2, xa, wa);
       fma_step(xb, wb);
     }
     __syncwarp();
@@ -296,7 +299,7 @@ __device__ __forceinline__ uint32_t gemm_body(WeightRing ring, uint32_t pos_pack
 //   ode_layout: vector-field geometry (LL row blocks of RT rows, row block rb starts at inT + rb*RT,
 //   row stride RT*LL, 128 threads per row block) vs jump geometry (one row block, stride RT).
 // Ends with a consumer-wide named barrier so the epilogue's stores are visible to the next phase.
-template <int RT, int LL>
+template <int RT, int LL, bool ALLOW16 = false>
 __device__ __forceinline__ void tile_gemm(const WeightRing& ring, RingPos& pos, const TileThread& th,
                                           const float* __restrict__ Wt, int K, int N,
                                           const float* inT, bool ode_layout, const Epilogue& epi) {
@@ -316,11 +319,20 @@ __device__ __forceinline__ void tile_gemm(const WeightRing& ring, RingPos& pos, 
   const uint32_t in_rb = static_cast<uint32_t>(reinterpret_cast<const unsigned char*>(inT + rb * RT) - smem_raw);
   const uint32_t pk = pos.stage | (pos.phase << 8) | (pos.ready << 16);
   uint32_t nk;
-  switch (P) {
-    case 1: nk = gemm_body<RT, 1>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
-    case 2: nk = gemm_body<RT, 2>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
-    case 3: nk = gemm_body<RT, 3>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
-    default: nk = gemm_body<RT, 4>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
+  if (ALLOW16 && ring.kc == 16) {      // 16-row stages (K % 16 == 0 guaranteed by the host plan)
+    switch (P) {
+      case 1: nk = gemm_body<RT, 1, 16>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
+      case 2: nk = gemm_body<RT, 2, 16>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
+      case 3: nk = gemm_body<RT, 3, 16>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
+      default: nk = gemm_body<RT, 4, 16>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
+    }
+  } else {
+    switch (P) {
+      case 1: nk = gemm_body<RT, 1, KC>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
+      case 2: nk = gemm_body<RT, 2, KC>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
+      case 3: nk = gemm_body<RT, 3, KC>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
+      default: nk = gemm_body<RT, 4, KC>(ring, pk, in_rb, ld, K, N, rb, cg, tpb, th.lane, &epi); break;
+    }
   }
   pos.stage = nk & 0xffu;
   pos.phase = (nk >> 8) & 1u;

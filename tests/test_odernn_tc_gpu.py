@@ -132,3 +132,30 @@ def test_tc_rejects_training_and_dense(cuda_device):
     with pytest.raises(Exception):
         with torch.no_grad():
             mod(fv, fi, ts)
+
+
+def test_tc_evolve_state_side_launch_l1(cuda_device):
+    """evolve_state is an L = 1 problem: 2048 rows = 16 tiles -> with 15 co-resident clusters the 128 shortest-interval
+    rows run in the FFMA side launch as 8-row `<8, 1>` tiles.  Fixed-step rk4 (no controller feedback), so every row must
+    agree with the FFMA-only kernel to fp32 parity, whichever kernel integrated it."""
+    import odevio_b200
+    from oracle.pose_odernn import default_opt
+    ref, mod = make_pair(cuda_device, ode_solver="rk4", ode_substeps=2, ode_precision="tf32x3", bias_std=0.05)
+    mod_f = odevio_b200.PoseODERNN(default_opt(ode_solver="rk4", ode_substeps=2))
+    mod_f.load_state_dict(ref.state_dict())
+    mod_f = mod_f.to(cuda_device).eval()
+    g = torch.Generator().manual_seed(4)
+    B = 2048
+    state = (0.5 * torch.randn(B, mod.f_len, generator=g)).to(cuda_device)
+    t0 = torch.rand(B, generator=g)
+    ts = torch.stack([t0, t0 + 0.05 + 0.3 * torch.rand(B, generator=g)], 1).to(cuda_device)
+    with torch.no_grad():
+        got = mod.evolve_state(state, ts)
+        want = mod_f.evolve_state(state, ts)
+    mod.check_status()
+    assert rel_err(got.cpu(), want.cpu()) <= STATE_RTOL
+    assert (mod.last_stats[0, 0, :, 0] == 2).all() and torch.equal(mod.last_stats, mod_f.last_stats)
+    rows = torch.randperm(B, generator=g)[:16]
+    with torch.no_grad():
+        o = ref.evolve_state(state.cpu()[rows], ts.cpu()[rows])
+    assert rel_err(got.cpu()[rows], o["y_end"]) <= STATE_RTOL
