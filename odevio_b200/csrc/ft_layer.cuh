@@ -93,6 +93,9 @@ __device__ __forceinline__ void store_chunk_hilo(float* hi, float* lo, int r, in
   }
 }
 
+// arrivals that complete op_ready[]: split mode = splitter warp + the producer's expect_tx for the weight images
+constexpr uint32_t ft_op_ready_arrivals(bool split) { return split ? 2u : 1u; }
+
 // where a layer's epilogue puts its result
 enum { FT_OUT_OPERAND = 0,         // next layer's operand image (L.nx)
        FT_OUT_ROWS = 1,            // fp32 row-major L.out[(row0 + r) * N + n], rows < M
@@ -138,13 +141,22 @@ __device__ __forceinline__ void ft_layer(FtCtx& c, const FtLayer& L) {
     const float* asrc = a_src_buf + static_cast<size_t>(ch0) * FT_ROWS * FT_KCH;
     for (int ch = 0; ch < nch; ++ch) {
       const uint32_t g = c.g0 + ch, rs = g % c.nraw, rph = (g / c.nraw) & 1u;
+      const uint32_t os_p = g % FT_OP_STAGES, oph_p = (g / FT_OP_STAGES) & 1u;
       mbar_wait(&c.raw_empty[rs], rph ^ 1u);
+      if (FT_SPLIT) mbar_wait(&c.op_empty[os_p], oph_p ^ 1u);     // the tensor core is done with the stage's previous chunk
       unsigned char* dst = c.smem + static_cast<size_t>(rs) * c.raw_stage_bytes;
       if (elect_one()) {
         if (FT_SPLIT) {
-          mbar_arrive_expect_tx(&c.raw_full[rs], a_bytes + w_bytes);
+          // the activation chunk goes to a raw stage (split hi / lo by a splitter warp); the weights are static, so their
+          // hi / lo images were split once on the host side of the launch and land straight in the operand stage:
+          // op_ready[os] completes on the splitter's arrive + this arrive + the weight bytes
+          unsigned char* ob = c.op_base + static_cast<size_t>(os_p) * c.op_stage_bytes;
+          const float* wlo = L.Wlo + static_cast<size_t>(cn) * Nc * K + static_cast<size_t>(ch0) * Nc * FT_KCH;
+          mbar_arrive_expect_tx(&c.raw_full[rs], a_bytes);
           tma_load_1d(dst, asrc + static_cast<size_t>(ch) * FT_ROWS * FT_KCH, a_bytes, &c.raw_full[rs]);
-          tma_load_1d(dst + a_bytes, wsrc + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &c.raw_full[rs]);
+          mbar_arrive_expect_tx(&c.op_ready[os_p], 2 * w_bytes);
+          tma_load_1d(ob + 2 * a_bytes, wsrc + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &c.op_ready[os_p]);
+          tma_load_1d(ob + 2 * a_bytes + w_bytes, wlo + static_cast<size_t>(ch) * Nc * FT_KCH, w_bytes, &c.op_ready[os_p]);
         } else {       // stage = [A_hi | A_lo | W_hi | W_lo], consumed by the MMA issuer directly
           const float* wlo = L.Wlo + static_cast<size_t>(cn) * Nc * K + static_cast<size_t>(ch0) * Nc * FT_KCH;
           mbar_arrive_expect_tx(&c.raw_full[rs], 2 * (a_bytes + w_bytes));
@@ -162,7 +174,7 @@ __device__ __forceinline__ void ft_layer(FtCtx& c, const FtLayer& L) {
     // ~1 k clk of latency (two barrier waits, LDS -> STS, fence.proxy.async), which bounded the kernel
     // when all four warps worked on the same chunk.
     const int sw = warp - FT_WARP_SPLIT;
-    const int a_vec = FT_ROWS * FT_KCH / 4, w_vec = Nc * FT_KCH / 4;
+    const int a_vec = FT_ROWS * FT_KCH / 4;
     for (int ch = sw; ch < nch; ch += FT_SPLIT_WARPS) {
       const uint32_t g = c.g0 + ch, rs = g % c.nraw, rph = (g / c.nraw) & 1u;
       const uint32_t os = g % FT_OP_STAGES, oph = (g / FT_OP_STAGES) & 1u;
@@ -170,20 +182,13 @@ __device__ __forceinline__ void ft_layer(FtCtx& c, const FtLayer& L) {
       mbar_wait(&c.op_empty[os], oph ^ 1u);
       const unsigned char* raw = c.smem + static_cast<size_t>(rs) * c.raw_stage_bytes;
       unsigned char* ob = c.op_base + static_cast<size_t>(os) * c.op_stage_bytes;
-      const float4* ra = reinterpret_cast<const float4*>(raw); const float4* rw = reinterpret_cast<const float4*>(raw + a_bytes);
+      const float4* ra = reinterpret_cast<const float4*>(raw);
       float4* ahi = reinterpret_cast<float4*>(ob); float4* alo = reinterpret_cast<float4*>(ob + a_bytes);
-      float4* whi = reinterpret_cast<float4*>(ob + 2 * a_bytes); float4* wlo = reinterpret_cast<float4*>(ob + 2 * a_bytes + w_bytes);
 #pragma unroll 8
       for (int e = lane; e < a_vec; e += 32) {
         const float4 x = ra[e];
         const float4 h = make_float4(ft_hi(x.x), ft_hi(x.y), ft_hi(x.z), ft_hi(x.w));
         ahi[e] = h; alo[e] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-      }
-#pragma unroll 4
-      for (int e = lane; e < w_vec; e += 32) {
-        const float4 x = rw[e];
-        const float4 h = make_float4(ft_hi(x.x), ft_hi(x.y), ft_hi(x.z), ft_hi(x.w));
-        whi[e] = h; wlo[e] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> tensor core (async proxy)
       __syncwarp();
@@ -442,8 +447,8 @@ int ft_plan(int M, int D, int H, int n_hidden, FtPlan& pl, int mode = 0) {
   pl.off_part = take(wide ? 64 : static_cast<size_t>(pl.nclusters) * pl.part_floats);
   pl.total_bytes = off * sizeof(float);
   if (pl.split) {
-    pl.raw_stage_bytes = static_cast<uint32_t>(FT_ROWS + pl.ncmax) * pl.KCH * 4u;
-    pl.op_stage_bytes = 2u * pl.raw_stage_bytes;
+    pl.raw_stage_bytes = static_cast<uint32_t>(FT_ROWS) * pl.KCH * 4u;                 // fp32 activation chunk
+    pl.op_stage_bytes = 2u * static_cast<uint32_t>(FT_ROWS + pl.ncmax) * pl.KCH * 4u;   // A hi | A lo | W hi | W lo
     pl.nraw = FT_RAW_STAGES;
     pl.smem_bytes = static_cast<size_t>(pl.nraw) * pl.raw_stage_bytes + static_cast<size_t>(FT_OP_STAGES) * pl.op_stage_bytes + 1024;
     if (pl.smem_bytes > 227u * 1024u) {

@@ -76,7 +76,7 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
 
   if (tid == 0) {
     for (int i = 0; i < FT_RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 1); }
-    for (int i = 0; i < FT_OP_STAGES; ++i) { mbar_init(&op_ready[i], 1); mbar_init(&op_empty[i], 1); }
+    for (int i = 0; i < FT_OP_STAGES; ++i) { mbar_init(&op_ready[i], ft_op_ready_arrivals(FT_SPLIT)); mbar_init(&op_empty[i], 1); }
     mbar_init(&accum_bar, 1);
     fence_barrier_init();
   }
@@ -210,7 +210,7 @@ int32_t odevio_odefunc_forward(int32_t M, int32_t D, int32_t H, int32_t n_hidden
     if (!weights[l] || !biases[l]) return ODEVIO_E_NULL;
     p.K[l] = pl.K[l]; p.N[l] = pl.N[l]; p.nN[l] = pl.nN[l]; p.nK[l] = pl.nK[l];
     ft_pack_weight_kernel<<<296, 256, 0, stream>>>(weights[l], pl.N[l], pl.K[l], pl.nN[l], pl.KCH, ws + pl.off_w[l],
-                                                   pl.split ? nullptr : ws + pl.off_wlo[l]);
+                                                   ws + pl.off_wlo[l]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int32_t>(e);
     p.Wp[l] = ws + pl.off_w[l]; p.Wlo[l] = ws + pl.off_wlo[l]; p.bias[l] = biases[l];

@@ -238,7 +238,7 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
 
   if (tid == 0) {
     for (int i = 0; i < FT_RAW_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 1); }
-    for (int i = 0; i < FT_OP_STAGES; ++i) { mbar_init(&op_ready[i], 1); mbar_init(&op_empty[i], 1); }
+    for (int i = 0; i < FT_OP_STAGES; ++i) { mbar_init(&op_ready[i], ft_op_ready_arrivals(SPLIT)); mbar_init(&op_empty[i], 1); }
     mbar_init(&accum_bar, 1);
     fence_barrier_init();
   }
@@ -607,7 +607,7 @@ int TcEvolve::prepare(const odevio_odernn_cfg& c, const DevTableau& tab, bool ad
     if (!ode_w[l] || !ode_b[l]) return ODEVIO_E_NULL;
     p.K[l] = pl.K[l]; p.N[l] = pl.N[l]; p.nN[l] = pl.nN[l]; p.nK[l] = pl.nK[l];
     ft_pack_weight_kernel<<<296, 256, 0, stream>>>(ode_w[l], pl.N[l], pl.K[l], pl.nN[l], pl.KCH, ws + pl.off_w[l],
-                                                   pl.split ? nullptr : ws + pl.off_wlo[l]);
+                                                   ws + pl.off_wlo[l]);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
     p.Wp[l] = ws + pl.off_w[l]; p.Wlo[l] = ws + pl.off_wlo[l]; p.bias[l] = ode_b[l];

@@ -1,6 +1,6 @@
 set -x
 cd /root/repo
-timeout 1800 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_tc_final.json 2> gpurun_out/bench_tc_final.err; cut -c1-250 gpurun_out/bench_tc_final.json
-timeout 600 python bench.py --steps 10 --warmup 3 --precision fp32 > gpurun_out/bench_fp32_final.json 2> gpurun_out/bench_fp32_final.err; cut -c1-250 gpurun_out/bench_fp32_final.json
-timeout 900 python bench.py --workload odernn_train --train-batch 4096 --steps 3 --warmup 1 > gpurun_out/bench_train_final.json 2> gpurun_out/bench_train_final.err; cut -c1-250 gpurun_out/bench_train_final.json
+timeout 300 python -m pytest tests/test_odefunc_gpu.py -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_odernn_tc_gpu.py -x -q 2>&1 | tail -3
+SUB=4 timeout 300 python tools/gpu_tc_timing.py 2>&1 | grep "tf32x3 rows=\(128\|1920\|2048\)"
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_tc_presplit.json 2> gpurun_out/bench_tc_presplit.err; cut -c1-250 gpurun_out/bench_tc_presplit.json
