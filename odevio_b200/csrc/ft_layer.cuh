@@ -31,9 +31,11 @@ constexpr int FT_ROWS = 128;          // rows per tile = MMA M
 //           false = the epilogues write hi and lo images (twice the bytes, no split stage: wide slices do not
 //           leave shared memory for a separate operand ring)
 constexpr int FT_RAW_STAGES = 8;      // fp32 chunks in flight (bulk TMA -> splitter); 4 when shared memory is short
-constexpr int FT_OP_STAGES = 4;       // split hi/lo operand stages (splitter -> tensor core) == splitter warps:
-                                      // chunk g uses raw stage g % nraw and operand stage g % 4, both always served by
-                                      // splitter warp g % 4, so every parity wait is at most one phase behind
+constexpr int FT_OP_STAGES = 8;       // operand stages (activations: splitter -> tensor core; weights: TMA -> tensor core), a
+                                      // multiple of the 4 splitter warps: chunk g uses raw stage g % nraw and operand stage
+                                      // g % 8, both always served by splitter warp g % 4, so every parity wait is at most one
+                                      // phase behind.  8 (was 4): the producer waits for the operand stage, so its run-ahead is
+                                      // the operand ring depth and must cover the ~1.4 k clk TMA landing latency
 constexpr int FT_MAX_LAYERS = ODEVIO_MAX_ODE_LINEARS;
 // warps 0-7 epilogue (thread = row, two column halves), warps 8-11 hi/lo splitter, warp 12 TMA producer,
 // warp 13 MMA issuer
@@ -451,7 +453,7 @@ int ft_plan(int M, int D, int H, int n_hidden, FtPlan& pl, int mode = 0) {
     pl.op_stage_bytes = 2u * static_cast<uint32_t>(FT_ROWS + pl.ncmax) * pl.KCH * 4u;   // A hi | A lo | W hi | W lo
     pl.nraw = FT_RAW_STAGES;
     pl.smem_bytes = static_cast<size_t>(pl.nraw) * pl.raw_stage_bytes + static_cast<size_t>(FT_OP_STAGES) * pl.op_stage_bytes + 1024;
-    if (pl.smem_bytes > 227u * 1024u) {
+    if (pl.smem_bytes > 218u * 1024u) {          // leave room for the kernels' static shared memory (row state, barriers)
       pl.nraw = 4;
       pl.smem_bytes = static_cast<size_t>(pl.nraw) * pl.raw_stage_bytes + static_cast<size_t>(FT_OP_STAGES) * pl.op_stage_bytes + 1024;
     }
