@@ -176,6 +176,53 @@ def test_joint_controller_depends_on_batch(cuda_device):
     assert a["stats"][0] != b["stats"][0] or not torch.equal(a["pose"][:4], b["pose"])
 
 
+@pytest.mark.parametrize("interp", ["linear", "cubic"])
+def test_configs2_full_size(cuda_device, interp):
+    """BASELINE configs[2] at FULL size: B = 1024, Hc = F = 128, n = 3, dopri5 atol=1e-6 rtol=1e-4, irregular
+    timestamps; reference rectilinear-linear path and north_star cubic path.  The batch-joint controller
+    cannot be checked on a row subset (one step size for the whole batch), so the CPU oracle integrates all
+    1024 sequences (~2 TFLOP for the cubic path: seconds).  Same criterion as the small cases: poses <= 1e-5
+    (widened only to 4x the oracle's own 2-8 ulp noise spread), identical (n_steps, n_accepted, n_f_evals)
+    whenever the noisy oracle members reproduce them."""
+    ref, mod = make_pair(cuda_device, Hc=128, cde_fn_num_layers=3, cde_interp=interp)
+    fv, fi, ts = data(1024, 10, 128, True)
+    hist = None
+    spread, stable = conditioning(ref, fv, fi, ts, None, hist, n_members=2)
+    with torch.no_grad():
+        p_ref, z_ref = ref(fv, fi, ts)
+        p, z = mod(fv.to(cuda_device), fi.to(cuda_device), ts.to(cuda_device))
+    torch.cuda.synchronize()
+    mod.check_status()
+    out = dict(pose_err=rel_err(p.cpu(), p_ref), z0_err=rel_err(z.cpu(), z_ref), spread=spread, stable=stable,
+               stats=mod.last_stats.cpu().tolist(),
+               ref_stats=(ref.last_stats["n_steps"], ref.last_stats["n_accepted"], ref.last_stats["n_f_evals"]))
+    print(f"configs[2] {interp}: pose_err {out['pose_err']:.3e} (oracle noise spread {spread:.3e}, stable={stable}), "
+          f"stats kernel {out['stats'][:3]} oracle {out['ref_stats']}")
+    check(out)
+
+
+def test_unit_variance_features_measured_spread(cuda_device):
+    """BASELINE's N(0,1) features (the other CDE tests and the bench scale them to 0.2, see data()).
+    With unit-variance features the random-init cubic CDE is ill-conditioned: this test MEASURES and prints
+    the oracle's own fp32-vs-fp64 pose gap and its 2-8 ulp noise spread, and holds the kernel to 4x the
+    larger of the two (never tighter than 1e-5) -- i.e. the kernel must be as close to the fp32 oracle as
+    the fp32 oracle is pinned by the reference semantics at this conditioning."""
+    ref, mod = make_pair(cuda_device, Hc=32, cde_fn_num_layers=2, cde_interp="cubic")
+    fv, fi, ts = data(12, 10, 32, True, scale=1.0)
+    spread, stable = conditioning(ref, fv, fi, ts, None, None)
+    ref64 = copy.deepcopy(ref).double()
+    with torch.no_grad():
+        p_ref, _ = ref(fv, fi, ts)
+        p64, _ = ref64(fv.double(), fi.double(), ts.double())
+        p, _ = mod(fv.to(cuda_device), fi.to(cuda_device), ts.to(cuda_device))
+    mod.check_status()
+    gap64 = rel_err(p_ref.double(), p64)
+    err = rel_err(p.cpu(), p_ref)
+    print(f"unit-variance features: kernel vs fp32 oracle {err:.3e}; oracle fp32 vs fp64 {gap64:.3e}; "
+          f"oracle 2-8 ulp noise spread {spread:.3e}; steps stable under noise: {stable}")
+    assert err <= max(POSE_RTOL, 4 * max(spread, gap64))
+
+
 def test_training_raises(cuda_device):
     import odevio_b200
     ref, mod = make_pair(cuda_device)

@@ -12,15 +12,26 @@ from oracle.pose_odernn import default_opt
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # fixed-step cases and the reference-default dopri5 case (zero biases, regular frames) are well
-# conditioned: strict north_star tolerance.  The others exercise noise-sensitive controller
-# decisions (tests/helpers.noise_ensemble) and are held to the solver-tolerance scale.
+# conditioned: strict north_star tolerance and identical step counts.  The others exercise noise-sensitive
+# controller decisions; they are held to the criterion of tests/test_odernn_gpu.py: identical
+# (n_steps, n_accepted) on every entry the ORACLE ITSELF reproduces under 2-32 ulp noise in its vector-field
+# evaluations (tests/helpers.noise_ensemble, rebuilt here from the fixture's weights), poses within 1e-5
+# widened only to 4x the oracle's own measured noise spread.
 STRICT = ("rk4_regular", "rk4_38_sub2", "dopri5_ref_defaults")
+
+
+def _oracle_from_fixture(fx):
+    from oracle.pose_odernn import OraclePoseODERNN
+    ref = OraclePoseODERNN(default_opt(**fx["opt"]))
+    ref.load_state_dict(fx["state"])
+    return ref.eval()
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "odernn_*.pt"))),
                          ids=lambda p: os.path.basename(p)[7:-3])
 def test_kernel_reproduces_odernn_golden(cuda_device, path):
     import odevio_b200
+    from helpers import noise_ensemble
     name = os.path.basename(path)[7:-3]
     fx = torch.load(path)
     mod = odevio_b200.PoseODERNN(default_opt(**fx["opt"]))
@@ -32,16 +43,22 @@ def test_kernel_reproduces_odernn_golden(cuda_device, path):
         steps = mod.last_stats.cpu()
         pose_c, h_c = mod(fx["fv"].to(dev), fx["fi"].to(dev), fx["ts_abs"].to(dev), prev=fx["prev"].to(dev))
     mod.check_status()
-    tol = 1e-5 if name in STRICT else 2e-4
     scale = fx["pose"].abs().max()
+    neq = (steps[..., 0] != fx["n_steps"]) | (steps[..., 1] != fx["n_accepted"])
+    if name in STRICT:
+        tol = tol_c = 1e-5
+        assert not bool(neq.any()), int(neq.sum())
+    else:
+        ref = _oracle_from_fixture(fx)
+        stable, spread_p, _ = noise_ensemble(ref, fx["fv"], fx["fi"], fx["ts"], n_members=6)
+        _, spread_c, _ = noise_ensemble(ref, fx["fv"], fx["fi"], fx["ts_abs"], prev=fx["prev"], n_members=6)
+        assert int((neq & stable).sum()) == 0, (int(neq.sum()), int((~stable).sum()), neq.numel())
+        tol, tol_c = max(1e-5, 4 * spread_p), max(1e-5, 4 * spread_c)
+        print(f"{name}: mismatching entries {int(neq.sum())}/{neq.numel()} (all among the {int((~stable).sum())} the oracle's "
+              f"noise ensemble leaves undetermined); pose tolerance {tol:.2e} / {tol_c:.2e}")
     assert (pose.cpu() - fx["pose"]).abs().max() <= tol * scale
     assert (h.cpu() - fx["h"]).abs().max() <= 5 * tol * fx["h"].abs().max()
-    assert (pose_c.cpu() - fx["pose_carry"]).abs().max() <= tol * scale
-    if name in STRICT:
-        assert torch.equal(steps[..., 0], fx["n_steps"]) and torch.equal(steps[..., 1], fx["n_accepted"])
-    else:
-        mism = ((steps[..., 0] != fx["n_steps"]) | (steps[..., 1] != fx["n_accepted"])).float().mean().item()
-        assert mism <= 0.5, mism          # knife-edge ramp-up decisions in interval 0 only
+    assert (pose_c.cpu() - fx["pose_carry"]).abs().max() <= tol_c * scale
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "cde_*.pt"))),
