@@ -73,10 +73,16 @@ enum { ODEVIO_STATUS_OK = 0, ODEVIO_STATUS_MAX_STEPS = 1, ODEVIO_STATUS_INFINITE
        ODEVIO_STATUS_CKPT_OVERFLOW = 3 /* training: more solver iterations than cfg.ckpt_loops */ };
 /* arithmetic mode of the vector-field GEMMs */
 enum { ODEVIO_PRECISION_FP32 = 0,    /* CUDA-core FFMA, one persistent kernel per forward */
-       ODEVIO_PRECISION_TF32X3 = 1   /* ODEFunc GEMMs on tcgen05 as 3xTF32 (hi/lo split, fp32-accurate: <= 1e-5 on poses);
+       ODEVIO_PRECISION_TF32X3 = 1,  /* ODEFunc GEMMs on tcgen05 as 3xTF32 (hi/lo split, fp32-accurate: <= 1e-5 on poses);
                                         per interval one cluster kernel runs the whole solver loop of every 128-row
                                         tile (odernn_tc.cu), then the FMA kernel runs the jump + head.  Inference only
-                                        (save_checkpoints = 0), endpoint_dense = 0, trace_steps = 0; D, H multiples of 64 */ };
+                                        (save_checkpoints = 0), endpoint_dense = 0, trace_steps = 0; D, H multiples of 64 */
+       ODEVIO_PRECISION_FP16X3 = 2   /* second-generation tensor-core solver (odernn_h3.cu): ODEFunc GEMMs on tcgen05 as
+                                        3xFP16 (x = hi + lo * 2^-11, products hi*hi + lo*hi + hi*lo, fp32 accumulate: the
+                                        same 2^-22 product accuracy as 3xTF32 at twice the MMA rate and half the operand
+                                        bytes), weights on the M side, clusters of 4 CTAs around 64-row tiles.  Same
+                                        restrictions as TF32X3; D / 4 and H / 4 multiples of 32 in [128, 256]
+                                        (D = 768, H in {512, 768, 1024}); |state|, |activation| < 65504 (fp16 range) */ };
 
 typedef struct odevio_odernn_cfg {
   int32_t B;            /* sequences */

@@ -17,7 +17,7 @@ MAX_RNN_LAYERS = 4
 ACT = {"tanh": 0, "relu": 1, "leaky_relu": 2, "softplus": 3}
 RNN = {"rnn": 0, "gru": 1}
 SOLVER = {"dopri5": 0, "tsit5": 1, "heun": 2, "euler": 3, "rk4": 4, "rk4_38": 5}
-PRECISION = {"fp32": 0, "tf32x3": 1}     # ODEVIO_PRECISION_*
+PRECISION = {"fp32": 0, "tf32x3": 1, "fp16x3": 2}     # ODEVIO_PRECISION_*
 STATUS_OK, STATUS_MAX_STEPS, STATUS_INFINITE_NORM = 0, 1, 2
 
 

@@ -9,6 +9,7 @@
 #include "../../include/odevio.h"
 #include "odernn_params.h"
 #include "odernn_tc.h"
+#include "odernn_h3.h"
 #include "cde_params.h"
 
 namespace odevio {
@@ -147,9 +148,10 @@ int plan_odernn(const odevio_odernn_cfg& c, OdePlan& pl) {
   if (c.activation < 0 || c.activation > ODEVIO_ACT_SOFTPLUS) return ODEVIO_E_ENUM;
   if (c.rnn_type != ODEVIO_RNN_TANH && c.rnn_type != ODEVIO_RNN_GRU) return ODEVIO_E_ENUM;
   if (c.solver < 0 || c.solver > ODEVIO_SOLVER_RK4_38) return ODEVIO_E_ENUM;
-  if (c.precision != ODEVIO_PRECISION_FP32 && c.precision != ODEVIO_PRECISION_TF32X3) return ODEVIO_E_ENUM;
-  // tensor-core solver (odernn_tc.cu): inference, end point rule y1, no step trace
-  if (c.precision == ODEVIO_PRECISION_TF32X3 && (c.save_checkpoints || c.endpoint_dense || c.trace_steps)) return ODEVIO_E_ENUM;
+  if (c.precision != ODEVIO_PRECISION_FP32 && c.precision != ODEVIO_PRECISION_TF32X3 && c.precision != ODEVIO_PRECISION_FP16X3)
+    return ODEVIO_E_ENUM;
+  // tensor-core solvers (odernn_tc.cu, odernn_h3.cu): inference, end point rule y1, no step trace
+  if (c.precision != ODEVIO_PRECISION_FP32 && (c.save_checkpoints || c.endpoint_dense || c.trace_steps)) return ODEVIO_E_ENUM;
   if (c.rows_per_tile != 0 && c.rows_per_tile != 4 && c.rows_per_tile != 8 && c.rows_per_tile != 16) return ODEVIO_E_SHAPE;
   const bool fixed = c.solver == ODEVIO_SOLVER_RK4 || c.solver == ODEVIO_SOLVER_RK4_38;
   if (fixed && c.substeps < 1) return ODEVIO_E_SHAPE;
@@ -417,6 +419,7 @@ int plan_cde(const odevio_cde_cfg& c, CdePlan& pl) {
   } while (0)
 
 // ---- tensor-core mode: rows the cluster kernel cannot take in full rounds run concurrently in the FMA kernel
+int g_last_precision = 0;       // development hooks: which solver the last forward used
 constexpr int kSideRT = 8;      // sequences (= rows, L = 1) per CTA of the side launch
 size_t tc_side_scratch_bytes(const odevio_odernn_cfg& c, int nsm) {      // <= 8 rows per CTA, <= nsm CTAs
   return align_up(align_up(static_cast<size_t>(kMaxStages + 2) * c.D * 8, 64) * sizeof(float) * static_cast<size_t>(nsm), 256);
@@ -489,6 +492,10 @@ size_t odevio_odernn_workspace_bytes(const odevio_odernn_cfg* cfg) {
     const size_t tcb = odernn_tc_workspace_bytes(*cfg);
     return tcb ? align_up(pl.total_bytes, 256) + align_up(tcb, 256) + tc_side_scratch_bytes(*cfg, pl.nsm) +
                      tc_seq_table_bytes(*cfg) : 0;
+  }
+  if (cfg->precision == ODEVIO_PRECISION_FP16X3) {
+    const size_t hb = odernn_h3_workspace_bytes(*cfg);
+    return hb ? align_up(pl.total_bytes, 1024) + align_up(hb, 1024) : 0;
   }
   return pl.total_bytes;
 }
@@ -599,6 +606,33 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
     p.CK = pl.CK;
   }
 
+  g_last_precision = c.precision;
+  if (c.precision == ODEVIO_PRECISION_FP16X3) {
+    // Per interval: the 3xFP16 cluster kernel (odernn_h3.cu) evolves ALL L*B rows of the state in place (32 clusters of 4
+    // take the 2048 rows of configs[1] in one round: no side launch), then the FMA kernel runs the jump + head.
+    const size_t h_off = align_up(pl.total_bytes, 1024);
+    const size_t h_bytes = align_up(odernn_h3_workspace_bytes(c), 1024);
+    if (h_bytes == 0) return ODEVIO_E_SHAPE;
+    if (workspace_bytes < h_off + h_bytes) return ODEVIO_E_WORKSPACE;
+    H3Evolve h3;
+    const int prc = h3.prepare(c, p.tab, p.adaptive != 0, w->ode_w, w->ode_b, static_cast<unsigned char*>(workspace) + h_off,
+                               h_bytes, stream);
+    if (prc != 0) return prc;
+    const size_t state_bytes = static_cast<size_t>(c.L) * c.B * D * sizeof(float);
+    if (h0) { if (h0 != hT) ODEVIO_CUDA_TRY(cudaMemcpyAsync(hT, h0, state_bytes, cudaMemcpyDeviceToDevice, stream)); }
+    else ODEVIO_CUDA_TRY(cudaMemsetAsync(hT, 0, state_bytes, stream));
+    if (status) ODEVIO_CUDA_TRY(cudaMemsetAsync(status, 0, static_cast<size_t>(c.B) * sizeof(int32_t), stream));
+    p.S = 1; p.skip_evolve = 1; p.S_io = c.S; p.stats = nullptr; p.status = nullptr; p.h0 = hT; p.hT = hT; p.ts = nullptr;
+    for (int i = 0; i < c.S; ++i) {
+      const int erc = h3.evolve(hT, c.B, nullptr, ts, c.S + 1, i, stats, status, stream);
+      if (erc != 0) return erc;
+      if (!c.evolve_only) {
+        p.i_off = i;
+        ODEVIO_CUDA_TRY(launch_odernn_fwd(p, pl.RT, pl.grid, pl.smem_bytes, stream));
+      }
+    }
+    return 0;
+  }
   if (c.precision == ODEVIO_PRECISION_TF32X3) {
     // Per interval: the cluster kernel evolves all L*B rows of the state in place on the tensor cores, then the FMA
     // kernel runs the interval's jump + head (skip_evolve).  Same stream, no host synchronisation.
@@ -688,6 +722,7 @@ int32_t odevio_debug_tc_geometry(int32_t* out) {
   if (!out) return ODEVIO_E_NULL;
   int a = 0, b = 0, r = 0;
   odernn_tc_last_geometry(&a, &b, &r);
+  if (g_last_precision == ODEVIO_PRECISION_FP16X3) odernn_h3_last_geometry(&a, &b, &r);
   out[0] = a; out[1] = b; out[2] = r;
   return 0;
 }
@@ -697,10 +732,10 @@ int32_t odevio_debug_tc_timeline(long long* host_dst) {
 }
 
 int32_t odevio_debug_tc_timing(int32_t enable, float* total_ms, int32_t* launches) {
-  if (enable >= 0) { odernn_tc_timing_enable(enable != 0); return 0; }
+  if (enable >= 0) { odernn_tc_timing_enable(enable != 0); odernn_h3_timing_enable(enable != 0); return 0; }
   if (!total_ms || !launches) return ODEVIO_E_NULL;
   int n = 0;
-  const int rc = odernn_tc_timing_read(total_ms, &n);
+  const int rc = g_last_precision == ODEVIO_PRECISION_FP16X3 ? odernn_h3_timing_read(total_ms, &n) : odernn_tc_timing_read(total_ms, &n);
   *launches = n;
   return rc;
 }

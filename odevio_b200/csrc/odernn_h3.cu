@@ -1,0 +1,925 @@
+// Tensor-core ODE solver, second generation (cfg.precision = ODEVIO_PRECISION_FP16X3): PoseODERNN.evolve_state
+// (reference src/models/PoseODERNN.py:70-75) for every (sequence, rnn layer) row of one observation interval, the
+// ODEFunc GEMMs (src/models/ODEFunc.py:38-39) on tcgen05 as 3xFP16 and the whole solver loop of a tile -- stage
+// combines, Butcher tableau, per-row error norm, per-row step-size controller (torchode semantics as restated in
+// oracle/torchode_like.py), FSAL -- inside ONE cluster of 4 CTAs, no host round trip between solver steps.
+//
+// What changed against odernn_tc.cu (3xTF32, clusters of 8 around 128-row tiles) and why -- every number below is from
+// profiles/r02_mma_tma_probe.md:
+//   * WEIGHTS ON THE M SIDE: D^T[feature][row] = W[feature][k] . X^T[k][row].  A CTA owns Fc = N_out / 4 output features
+//     (one or two 128-feature MMA tiles) of every Linear for the tile's NR = 64 rows; 2048 rows = 32 clusters = 128 SMs
+//     in ONE round (37 clusters of 4 are co-resident; only 15 clusters of 8 were, which forced a concurrent FFMA side
+//     launch), no k-split, no partial-sum reduce through L2.
+//   * 3xFP16 instead of 3xTF32: fp16 and tf32 both carry 11 significant bits, but kind::f16 takes K = 16 per MMA at the
+//     cost of a kind::tf32 K = 8 MMA and the operands are half the bytes.  x = hi + lo * 2^-11 with hi = fp16(x),
+//     lo = fp16((x - hi) * 2^11) (the scaling keeps the residual out of fp16's subnormal range); products hi*hi into
+//     the main accumulators, lo*hi + hi*lo into a separate one that the epilogue scales by 2^-11: relative product
+//     error <= 2^-22, the same as 3xTF32.  Operands must stay below 65504 in magnitude (tanh-bounded states and
+//     activations do; an overflow surfaces as a non-finite error norm -> ODEVIO_STATUS_INFINITE_NORM).
+//   * the accumulate of tcgen05.mma truncates (~n 2^-24 drift after n accumulations, measured in round 1): the K range
+//     is split over up to 4 main accumulators per tile, added in fp32 round-to-nearest by the epilogue.
+//   * 48 KB ring stages (32 KB of weights + 16 KB of activations = 64 k of a 128-feature tile, 12 MMAs = 576 clk): a
+//     ring iteration costs ~450 clk of serial mbarrier / bulk-copy instruction latency whatever the stage size, so small
+//     stages were the bound of the old kernel, not the L2 fabric.  Separate weight / activation rings with their own
+//     producer warps; the weight producer runs ahead into the next Linear while the epilogue and the cluster barrier of
+//     the current one are in flight (weights are static, activations are not).
+//   * no integer division in any role loop (the old MMA issuer spent ~125 clk per MMA on them).
+// Layouts: activations are exchanged between the CTAs of a cluster through L2 in the tensor core's canonical
+// MN-major / no-swizzle fp16 image [k-chunk][hi|lo][row/8][k/8][k%8][row%8] -- feature-major, so that epilogue
+// thread = feature writes 16-byte pieces; weights are pre-packed per CTA in the K-major image
+// [k-chunk][tile][hi|lo][feature/8][k/8][feature%8][k%8].  One 1-D bulk TMA copy per chunk and ring.
+// Stage vectors K0..K6, Y, Y1 of a tile: per-cluster L2-resident scratch, feature-major [D][NR] fp32; every element is
+// only ever touched by the CTA that owns its feature.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/odevio.h"
+#include "common.cuh"
+#include "odernn_h3.h"
+#include "odernn_params.h"
+
+namespace odevio {
+
+namespace {
+
+constexpr int H3_NC = 4;                  // CTAs per cluster = feature slices of every Linear
+constexpr int H3_MAXL = ODEVIO_MAX_ODE_LINEARS;
+constexpr int H3_EPI_WARPS = 8;           // warps 0-7: epilogue + elementwise solver passes
+constexpr int H3_WARP_WPROD = 8, H3_WARP_XPROD = 9, H3_WARP_MMA = 10;
+constexpr int H3_THREADS = 32 * 11;
+constexpr int H3_EPI_THREADS = 32 * H3_EPI_WARPS;
+constexpr int H3_WCHUNK = 32768;          // bytes of a weight stage: T tiles x (hi | lo) x 128 features x KCH k (KCH = 64 / T)
+constexpr int H3_NWS = 4, H3_NXS = 4;     // ring depths (powers of two)
+
+struct H3Layer {
+  int K, N;                 // input / output features
+  int Fc;                   // output features per CTA = N / 4, a multiple of 32 in [128, 256]
+  int T;                    // 128-feature MMA tiles per CTA: tile 0 = local features [0, 128), tile 1 = [Fc - 128, Fc)
+  int KCH;                  // k per ring chunk = 64 / T
+  int nch;                  // K / KCH
+  int nseg;                 // main accumulators per tile (K split; + 1 accumulator for the cross terms)
+  int act;
+  const unsigned char* Wimg; // [4 CTAs][nch][H3_WCHUNK]
+  const float* bias;
+};
+
+struct H3Params {
+  int M, B, L, D, NL;
+  H3Layer lay[H3_MAXL];
+  unsigned char* xa; size_t xa_buf_bytes;       // per cluster: 2 activation-image buffers of xa_buf_bytes
+  float* state; size_t state_floats;            // per cluster: (kMaxStages + 2) x [D][NR] + [4][NR] norm partials
+  int ntiles;
+  DevTableau tab;
+  int adaptive, substeps;
+  float atol, rtol, dt0, safety, fmin, fmax;
+  int accept_strict, floor_factor, max_steps, exact_landing;
+  float* Y;                  // [L*B][D] row-major hidden state, evolved in place
+  const int* seq; int Bsub;  // rows (l, j), j < Bsub, of sequences b = seq[j] (nullptr: b = j); kernel row g = l * Bsub + j
+  const float* ts; int ts_ld, interval;
+  int* stats; int* status;
+};
+
+template <int NR>
+struct H3Rows {      // per-row solver state, replicated in every CTA of the cluster
+  __align__(16) float dt[NR];
+  float t[NR], tend[NR], tmin[NR], tmax[NR];
+  int run[NR], upd[NR], nsteps[NR], nacc[NR], status[NR];
+  long long grow[NR];                 // state row of the tile's row (-1: beyond M)
+  int bidx[NR], lyr[NR];
+  float psum[H3_EPI_WARPS][NR];
+};
+
+struct H3Ctx {
+  unsigned char* wring; unsigned char* xring;
+  uint64_t* w_full; uint64_t* w_empty; uint64_t* x_full; uint64_t* x_empty; uint64_t* accum_bar;
+  uint32_t tmem, crank;
+  uint32_t wcount, xcount;   // chunks of all previous layers on each ring (identical in every role)
+  uint32_t accum_phase;
+  uint32_t w_ahead;          // weight producer: chunks of the coming layer already issued
+};
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint64_t h3_desc(uint32_t saddr, uint32_t hi_word) {
+  // no-swizzle canonical layouts, LBO = 128 B (k groups of 8), SBO in hi_word (8-row / 8-column groups), version 1
+  return (static_cast<uint64_t>(hi_word) << 32) | static_cast<uint64_t>(((saddr >> 4) & 0x3fffu) | ((128u >> 4) << 16));
+}
+__device__ __forceinline__ void h3_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void h3_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void h3_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void h3_tmem_ld32(uint32_t taddr, uint32_t (&u)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+        "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+        "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// x = hi + lo * 2^-11: hi = fp16(x), lo = fp16((x - hi) * 2^11)  (x - hi is exact in fp32)
+__device__ __forceinline__ void h3_split(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * 2048.0f);
+}
+__device__ __forceinline__ uint32_t h3_pack2(__half a, __half b) {
+  return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+}
+
+// byte offset of (feature k, row n0 = multiple of 4) in the activation image of a layer whose chunks hold KCH = 1 << kshift
+// k: [k / KCH][hi | lo][n / 8][(k % KCH) / 8][k % 8][n % 8] fp16
+template <int NR>
+__device__ __forceinline__ size_t h3_x_offset(int k, int n0, int kshift) {
+  const int KCH = 1 << kshift;
+  return (static_cast<size_t>(k >> kshift) * (4u * KCH * NR)) + static_cast<size_t>(n0 >> 3) * ((KCH >> 3) * 128u) +
+         static_cast<size_t>((k & (KCH - 1)) >> 3) * 128u + static_cast<size_t>(k & 7) * 16u + static_cast<size_t>(n0 & 7) * 2u;
+}
+
+// MMAs of one ring chunk: T tiles x (KCH / 16) k-steps x {hi*hi -> main accumulator of segment `seg`, lo*hi + hi*lo -> the
+// tile's cross-term accumulator}; KCH = 64 / T.  Weight stage [tile][hi | lo][feature/8][k/8][feature%8][k%8] (K-major A),
+// activation stage [hi | lo][row/8][k/8][k%8][row%8] (MN-major B); both no-swizzle with LBO = 128 B, SBO = (KCH / 8) * 128 B.
+template <int T, int NR>
+__device__ __forceinline__ void h3_issue_chunk(uint32_t tmem, uint32_t wbase, uint32_t xbase, uint32_t nseg, uint32_t seg,
+                                               bool acc_main, bool acc_cross) {
+  constexpr uint32_t KCH = 64u / T, KS = KCH / 16u;
+  constexpr uint32_t hi_word = (((KCH >> 3) * 128u) >> 4) | (1u << 14);        // SBO | descriptor version 1 (bit 46)
+  constexpr uint32_t tile_bytes = 128u * KCH * 2u, ximg_bytes = KCH * NR * 2u;
+  // instruction descriptor: D fp32, A / B fp16, A K-major, B MN-major, N = NR, M = 128
+  constexpr uint32_t idesc = (1u << 4) | (1u << 16) | (static_cast<uint32_t>(NR >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  const uint32_t acc_per_tile = (nseg + 1u) * NR;
+#pragma unroll
+  for (uint32_t t = 0; t < static_cast<uint32_t>(T); ++t) {
+    const uint32_t a_hi = wbase + t * 2u * tile_bytes, a_lo = a_hi + tile_bytes;
+    const uint32_t d_main = tmem + t * acc_per_tile + seg * NR, d_cross = tmem + t * acc_per_tile + nseg * NR;
+#pragma unroll
+    for (uint32_t ks = 0; ks < KS; ++ks) {
+      const uint32_t o = ks * 256u;
+      const uint64_t ah = h3_desc(a_hi + o, hi_word), al = h3_desc(a_lo + o, hi_word);
+      const uint64_t xh = h3_desc(xbase + o, hi_word), xl = h3_desc(xbase + ximg_bytes + o, hi_word);
+      h3_mma(d_main, ah, xh, idesc, (acc_main || ks) ? 1u : 0u);
+      h3_mma(d_cross, al, xh, idesc, (acc_cross || ks) ? 1u : 0u);
+      h3_mma(d_cross, ah, xl, idesc, 1u);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- one Linear
+// All threads of all 4 CTAs call this with identical arguments.  Reads the cluster's activation image `xsrc` (complete
+// and visible: the caller's previous step ended with a cluster barrier), writes act(W x + b) either into the activation
+// image `xdst` of the next Linear (chunks of 1 << xdst_kshift) or, `out` != nullptr, as fp32 [feature][NR] rows of a
+// stage vector.  Ends with a cluster barrier.  `next` (may be nullptr): the Linear that certainly follows -- its first
+// weight chunks are issued before the barrier.
+template <int NR>
+__device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Layer* next, const unsigned char* xsrc,
+                                         unsigned char* xdst, int xdst_kshift, float* out) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t XSTAGE = 4u * 64u * NR;                 // bytes of an activation stage (KCH = 64: hi | lo)
+  const int nch = L.nch;
+
+  if (warp == H3_WARP_WPROD) {
+    // ===== weight producer: one 32 KB bulk copy per chunk; whole warp, one elected lane issues
+    const unsigned char* src = L.Wimg + static_cast<size_t>(c.crank) * nch * H3_WCHUNK;
+    uint32_t g = c.wcount + c.w_ahead;
+    for (int ch = static_cast<int>(c.w_ahead); ch < nch; ++ch, ++g) {
+      const uint32_t s = g & (H3_NWS - 1), ph = (g / H3_NWS) & 1u;
+      mbar_wait(&c.w_empty[s], ph ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&c.w_full[s], H3_WCHUNK);
+        tma_load_1d(c.wring + s * H3_WCHUNK, src + static_cast<size_t>(ch) * H3_WCHUNK, H3_WCHUNK, &c.w_full[s]);
+      }
+      __syncwarp();
+    }
+    uint32_t pre = 0;
+    if (next) {
+      const unsigned char* nsrc = next->Wimg + static_cast<size_t>(c.crank) * next->nch * H3_WCHUNK;
+      pre = next->nch < H3_NWS ? next->nch : H3_NWS;
+      for (uint32_t ch = 0; ch < pre; ++ch, ++g) {
+        const uint32_t s = g & (H3_NWS - 1), ph = (g / H3_NWS) & 1u;
+        mbar_wait(&c.w_empty[s], ph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&c.w_full[s], H3_WCHUNK);
+          tma_load_1d(c.wring + s * H3_WCHUNK, nsrc + static_cast<size_t>(ch) * H3_WCHUNK, H3_WCHUNK, &c.w_full[s]);
+        }
+        __syncwarp();
+      }
+    }
+    c.w_ahead = pre;
+  } else if (warp == H3_WARP_XPROD) {
+    // ===== activation producer: one bulk copy (hi | lo images of KCH k x NR rows) per chunk
+    const uint32_t xcb = 4u * static_cast<uint32_t>(L.KCH) * NR;
+    uint32_t g = c.xcount;
+    for (int ch = 0; ch < nch; ++ch, ++g) {
+      const uint32_t s = g & (H3_NXS - 1), ph = (g / H3_NXS) & 1u;
+      mbar_wait(&c.x_empty[s], ph ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&c.x_full[s], xcb);
+        tma_load_1d(c.xring + s * XSTAGE, xsrc + static_cast<size_t>(ch) * xcb, xcb, &c.x_full[s]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == H3_WARP_MMA) {
+    // ===== MMA issuer: D^T[128 features x NR rows] += W[128 x 16] X^T[16 x NR], three products per k-step.  Whole warp
+    // with warp-uniform operands, one elected lane issues; the chunk body is fully unrolled (h3_issue_chunk) and there
+    // is no division anywhere in the loop.
+    const uint32_t nseg = static_cast<uint32_t>(L.nseg);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, c.tmem, 0);
+    // chunks per K segment (ceil): segment s takes chunks [s * cps, (s + 1) * cps)
+    uint32_t cps = 1;
+    while (cps * nseg < static_cast<uint32_t>(nch)) ++cps;
+    uint32_t seg = 0, in_seg = 0, gw = c.wcount, gx = c.xcount;
+    for (int ch = 0; ch < nch; ++ch, ++gw, ++gx) {
+      const uint32_t ws = gw & (H3_NWS - 1), wph = (gw / H3_NWS) & 1u;
+      const uint32_t xs = gx & (H3_NXS - 1), xph = (gx / H3_NXS) & 1u;
+      mbar_wait(&c.w_full[ws], wph);
+      mbar_wait(&c.x_full[xs], xph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t wbase = smem_u32(c.wring + ws * H3_WCHUNK), xbase = smem_u32(c.xring + xs * XSTAGE);
+      if (elect_one()) {
+        if (L.T == 1) h3_issue_chunk<1, NR>(tmem_u, wbase, xbase, nseg, seg, in_seg != 0, ch != 0);
+        else h3_issue_chunk<2, NR>(tmem_u, wbase, xbase, nseg, seg, in_seg != 0, ch != 0);
+        h3_commit(&c.w_empty[ws]);
+        h3_commit(&c.x_empty[xs]);
+      }
+      __syncwarp();
+      if (++in_seg == cps) { in_seg = 0; ++seg; }
+    }
+    if (elect_one()) h3_commit(c.accum_bar);
+    __syncwarp();
+  } else if (warp < H3_EPI_WARPS) {
+    // ===== epilogue: thread = output feature (TMEM lane); warps w and w + 4 share lane quarter w & 3 and split the rows
+    mbar_wait(c.accum_bar, c.accum_phase);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3, h = warp >> 2;
+    const int nseg = L.nseg, act = L.act;
+    for (int t = 0; t < L.T; ++t) {
+      const int m = 32 * q + lane;                                  // row of the MMA tile = TMEM lane
+      // tile 1 overlaps tile 0 when Fc < 256: only its upper Fc - 128 features are new (warp-uniform: Fc % 32 == 0)
+      if (t == 1 && 32 * q < 256 - L.Fc) continue;
+      const int fl = (t == 0 ? 0 : L.Fc - 128) + m;                 // feature inside the CTA's slice
+      const int f = static_cast<int>(c.crank) * L.Fc + fl;          // output feature of the Linear
+      const float bias = L.bias[f];
+      const uint32_t tbase = c.tmem + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(t * (nseg + 1) * NR);
+#pragma unroll 1
+      for (int cb = 0; cb < NR / 64; ++cb) {
+        const int col0 = h * (NR / 2) + 32 * cb;
+        uint32_t u[32];
+        float acc[32];
+        h3_tmem_ld32(tbase + static_cast<uint32_t>(nseg * NR + col0), u);              // cross terms first (smallest)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(u[i]) * (1.0f / 2048.0f);
+        for (int sgm = nseg - 1; sgm >= 0; --sgm) {
+          h3_tmem_ld32(tbase + static_cast<uint32_t>(sgm * NR + col0), u);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(u[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 a4 = apply_act4(make_float4(acc[4 * i] + bias, acc[4 * i + 1] + bias, acc[4 * i + 2] + bias, acc[4 * i + 3] + bias), act);
+          acc[4 * i] = a4.x; acc[4 * i + 1] = a4.y; acc[4 * i + 2] = a4.z; acc[4 * i + 3] = a4.w;
+        }
+        if (out) {
+          float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(f) * NR + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) __stcg(dst + i, make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]));
+        } else {
+          const size_t lo_off = static_cast<size_t>(2u * NR) << xdst_kshift;          // KCH * NR * 2 bytes
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __half hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h3_split(acc[8 * j + i], hi[i], lo[i]);
+            unsigned char* dst = xdst + h3_x_offset<NR>(f, col0 + 8 * j, xdst_kshift);
+            __stcg(reinterpret_cast<uint4*>(dst),
+                   make_uint4(h3_pack2(hi[0], hi[1]), h3_pack2(hi[2], hi[3]), h3_pack2(hi[4], hi[5]), h3_pack2(hi[6], hi[7])));
+            __stcg(reinterpret_cast<uint4*>(dst + lo_off),
+                   make_uint4(h3_pack2(lo[0], lo[1]), h3_pack2(lo[2], lo[3]), h3_pack2(lo[4], lo[5]), h3_pack2(lo[6], lo[7])));
+          }
+        }
+      }
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");             // generic-proxy global stores -> bulk copies of all 4 CTAs
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  c.accum_phase ^= 1u;
+  c.wcount += static_cast<uint32_t>(nch);
+  c.xcount += static_cast<uint32_t>(nch);
+  __syncwarp();
+  h3_cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------- elementwise passes
+// 256 threads walk the CTA's own feature slice [own_f0, own_f0 + own_nf) of the [D][NR] stage vectors: lane = (fs, g),
+// feature = own_f0 + 32 * it + 4 * warp + fs, rows 32 * m + 4 * g + {0..3} (m < NR / 32): every float4 load of 8 lanes
+// covers 128 contiguous bytes.  Weighted sums run left to right over j in the oracle's order (oracle/_weighted_sum); zero
+// coefficients contribute an exact +-0.
+template <int NR>
+struct H3Slice {
+  float* base; size_t arr;       // K[j] = base + j * arr, Y = base + 7 * arr, Y1 = base + 8 * arr
+  int own_f0, nit, warp, fs, g;
+};
+__device__ __forceinline__ float4 h3_ld4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void h3_st4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
+
+template <int N>
+__device__ __forceinline__ float4 h3_wsum(const float4 (&k)[N > 0 ? N : 1], const float (&cf)[kMaxStages]) {
+  float4 a = make_float4(mul_(k[0].x, cf[0]), mul_(k[0].y, cf[0]), mul_(k[0].z, cf[0]), mul_(k[0].w, cf[0]));
+#pragma unroll
+  for (int j = 1; j < N; ++j) {
+    a.x = add_(a.x, mul_(k[j].x, cf[j])); a.y = add_(a.y, mul_(k[j].y, cf[j]));
+    a.z = add_(a.z, mul_(k[j].z, cf[j])); a.w = add_(a.w, mul_(k[j].w, cf[j]));
+  }
+  return a;
+}
+
+// stage argument y + dt * sum_{j<N} a_j k_j -> fp16 hi / lo activation image of the first Linear
+template <int N, int NR>
+__device__ __forceinline__ void h3_stage_input(const H3Slice<NR>& sl, const float* coef, const float* dt_rows, unsigned char* xa,
+                                               int kshift) {
+  float cf[kMaxStages];
+#pragma unroll
+  for (int j = 0; j < kMaxStages; ++j) cf[j] = j < N ? coef[j] : 0.f;
+  const float* Y = sl.base + kMaxStages * sl.arr;
+  const size_t lo_off = static_cast<size_t>(2u * NR) << kshift;
+  for (int it = 0; it < sl.nit; ++it) {
+    const int f = sl.own_f0 + 32 * it + 4 * sl.warp + sl.fs;
+#pragma unroll
+    for (int m = 0; m < NR / 32; ++m) {
+      const int n0 = 32 * m + 4 * sl.g;
+      const size_t off = static_cast<size_t>(f) * NR + n0;
+      float4 y = h3_ld4(Y + off);
+      float4 k[N > 0 ? N : 1];
+#pragma unroll
+      for (int j = 0; j < N; ++j) k[j] = h3_ld4(sl.base + j * sl.arr + off);
+      if (N > 0) {
+        const float4 dt = *reinterpret_cast<const float4*>(dt_rows + n0);
+        const float4 s = h3_wsum<N>(k, cf);
+        y.x = add_(y.x, mul_(dt.x, s.x)); y.y = add_(y.y, mul_(dt.y, s.y));
+        y.z = add_(y.z, mul_(dt.z, s.z)); y.w = add_(y.w, mul_(dt.w, s.w));
+      }
+      __half hi[4], lo[4];
+      h3_split(y.x, hi[0], lo[0]); h3_split(y.y, hi[1], lo[1]); h3_split(y.z, hi[2], lo[2]); h3_split(y.w, hi[3], lo[3]);
+      unsigned char* dst = xa + h3_x_offset<NR>(f, n0, kshift);
+      __stcg(reinterpret_cast<uint2*>(dst), make_uint2(h3_pack2(hi[0], hi[1]), h3_pack2(hi[2], hi[3])));
+      __stcg(reinterpret_cast<uint2*>(dst + lo_off), make_uint2(h3_pack2(lo[0], lo[1]), h3_pack2(lo[2], lo[3])));
+    }
+  }
+}
+
+// y1 -> Y1 and this thread's share of sum_d (err_d / bound_d)^2 for its rows (odernn_fwd.cu:error_pass)
+template <int NS, int NR>
+__device__ __forceinline__ void h3_error_pass(const H3Slice<NR>& sl, const DevTableau& tb, const float* dt_rows, float atol, float rtol,
+                                              float (&sum)[NR / 32][4]) {
+  float cy[kMaxStages], ce[kMaxStages];
+#pragma unroll
+  for (int j = 0; j < kMaxStages; ++j) {
+    cy[j] = j < NS ? (tb.ssal ? (j < NS - 1 ? tb.a[NS - 1][j] : 0.f) : tb.b[j]) : 0.f;
+    ce[j] = j < NS ? tb.e[j] : 0.f;
+  }
+  const float* Y = sl.base + kMaxStages * sl.arr;
+  float* Y1 = sl.base + (kMaxStages + 1) * sl.arr;
+#pragma unroll
+  for (int m = 0; m < NR / 32; ++m) { sum[m][0] = 0.f; sum[m][1] = 0.f; sum[m][2] = 0.f; sum[m][3] = 0.f; }
+  for (int it = 0; it < sl.nit; ++it) {
+    const int f = sl.own_f0 + 32 * it + 4 * sl.warp + sl.fs;
+#pragma unroll
+    for (int m = 0; m < NR / 32; ++m) {
+      const int n0 = 32 * m + 4 * sl.g;
+      const size_t off = static_cast<size_t>(f) * NR + n0;
+      const float4 y0 = h3_ld4(Y + off);
+      float4 k[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) k[j] = h3_ld4(sl.base + j * sl.arr + off);
+      const float4 dt = *reinterpret_cast<const float4*>(dt_rows + n0);
+      const float4 sy = h3_wsum<NS>(k, cy);
+      const float4 y1 = make_float4(add_(y0.x, mul_(dt.x, sy.x)), add_(y0.y, mul_(dt.y, sy.y)), add_(y0.z, mul_(dt.z, sy.z)),
+                                    add_(y0.w, mul_(dt.w, sy.w)));
+      h3_st4(Y1 + off, y1);
+      if (tb.has_err) {
+        const float4 se = h3_wsum<NS>(k, ce);
+        const float e0 = mul_(dt.x, se.x), e1 = mul_(dt.y, se.y), e2 = mul_(dt.z, se.z), e3 = mul_(dt.w, se.w);
+        const float q0 = __fdiv_rn(e0, add_(atol, mul_(rtol, fmaxf(fabsf(y0.x), fabsf(y1.x)))));
+        const float q1 = __fdiv_rn(e1, add_(atol, mul_(rtol, fmaxf(fabsf(y0.y), fabsf(y1.y)))));
+        const float q2 = __fdiv_rn(e2, add_(atol, mul_(rtol, fmaxf(fabsf(y0.z), fabsf(y1.z)))));
+        const float q3 = __fdiv_rn(e3, add_(atol, mul_(rtol, fmaxf(fabsf(y0.w), fabsf(y1.w)))));
+        sum[m][0] = fmaf(q0, q0, sum[m][0]); sum[m][1] = fmaf(q1, q1, sum[m][1]);
+        sum[m][2] = fmaf(q2, q2, sum[m][2]); sum[m][3] = fmaf(q3, q3, sum[m][3]);
+      }
+    }
+  }
+}
+
+// fixed step: Y <- y0 + dt * sum b_j k_j (odernn_fwd.cu:fixed_commit)
+template <int NS, int NR>
+__device__ __forceinline__ void h3_fixed_commit(const H3Slice<NR>& sl, const DevTableau& tb, const float* dt_rows) {
+  float cb[kMaxStages];
+#pragma unroll
+  for (int j = 0; j < kMaxStages; ++j) cb[j] = j < NS ? tb.b[j] : 0.f;
+  float* Y = sl.base + kMaxStages * sl.arr;
+  for (int it = 0; it < sl.nit; ++it) {
+    const int f = sl.own_f0 + 32 * it + 4 * sl.warp + sl.fs;
+#pragma unroll
+    for (int m = 0; m < NR / 32; ++m) {
+      const int n0 = 32 * m + 4 * sl.g;
+      const size_t off = static_cast<size_t>(f) * NR + n0;
+      const float4 y0 = h3_ld4(Y + off);
+      float4 k[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) k[j] = h3_ld4(sl.base + j * sl.arr + off);
+      const float4 dt = *reinterpret_cast<const float4*>(dt_rows + n0);
+      const float4 s = h3_wsum<NS>(k, cb);
+      h3_st4(Y + off, make_float4(add_(y0.x, mul_(dt.x, s.x)), add_(y0.y, mul_(dt.y, s.y)), add_(y0.z, mul_(dt.z, s.z)),
+                                  add_(y0.w, mul_(dt.w, s.w))));
+    }
+  }
+}
+
+// accepted rows: Y <- Y1, FSAL carry K0 <- K[ns - 1]; other rows keep both
+template <int NR>
+__device__ __forceinline__ void h3_commit_rows(const H3Slice<NR>& sl, int ns, int fsal, const int* upd_rows) {
+  float* Y = sl.base + kMaxStages * sl.arr;
+  const float* Y1 = sl.base + (kMaxStages + 1) * sl.arr;
+  const float* Kl = sl.base + static_cast<size_t>(ns - 1) * sl.arr;
+  for (int it = 0; it < sl.nit; ++it) {
+    const int f = sl.own_f0 + 32 * it + 4 * sl.warp + sl.fs;
+#pragma unroll
+    for (int m = 0; m < NR / 32; ++m) {
+      const int n0 = 32 * m + 4 * sl.g;
+      const int4 u = *reinterpret_cast<const int4*>(upd_rows + n0);
+      if (!(u.x | u.y | u.z | u.w)) continue;
+      const size_t off = static_cast<size_t>(f) * NR + n0;
+      const float4 a = h3_ld4(Y1 + off), o = h3_ld4(Y + off);
+      h3_st4(Y + off, make_float4(u.x ? a.x : o.x, u.y ? a.y : o.y, u.z ? a.z : o.z, u.w ? a.w : o.w));
+      if (fsal) {
+        const float4 b = h3_ld4(Kl + off), o0 = h3_ld4(sl.base + off);
+        h3_st4(sl.base + off, make_float4(u.x ? b.x : o0.x, u.y ? b.y : o0.y, u.z ? b.z : o0.z, u.w ? b.w : o0.w));
+      }
+    }
+  }
+}
+
+#define H3_DISPATCH_STAGES(n, CALL)                                                                                 \
+  switch (n) {                                                                                                      \
+    case 1: { constexpr int NSV = 1; CALL; break; }                                                                 \
+    case 2: { constexpr int NSV = 2; CALL; break; }                                                                 \
+    case 3: { constexpr int NSV = 3; CALL; break; }                                                                 \
+    case 4: { constexpr int NSV = 4; CALL; break; }                                                                 \
+    case 5: { constexpr int NSV = 5; CALL; break; }                                                                 \
+    case 6: { constexpr int NSV = 6; CALL; break; }                                                                 \
+    default: { constexpr int NSV = 7; CALL; break; }                                                                \
+  }
+
+__device__ __forceinline__ int h3_log2(int v) { return 31 - __clz(v); }
+
+template <int NR>
+__global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_evolve_kernel(const __grid_constant__ H3Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t w_full[H3_NWS];
+  __shared__ __align__(8) uint64_t w_empty[H3_NWS];
+  __shared__ __align__(8) uint64_t x_full[H3_NXS];
+  __shared__ __align__(8) uint64_t x_empty[H3_NXS];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) H3Rows<NR> rs;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int cluster_id = blockIdx.x / H3_NC, nclusters = gridDim.x / H3_NC;
+  const DevTableau& tb = p.tab;
+
+  if (tid == 0) {
+    for (int i = 0; i < H3_NWS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < H3_NXS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == H3_WARP_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  H3Ctx c;
+  c.wring = smem; c.xring = smem + H3_NWS * H3_WCHUNK;
+  c.w_full = w_full; c.w_empty = w_empty; c.x_full = x_full; c.x_empty = x_empty; c.accum_bar = &accum_bar;
+  c.tmem = tmem_slot; c.crank = crank; c.wcount = 0; c.xcount = 0; c.accum_phase = 0; c.w_ahead = 0;
+
+  const int D = p.D, NL = p.NL;
+  const int own_nf = D / H3_NC, own_f0 = static_cast<int>(crank) * own_nf;
+  const size_t arr = static_cast<size_t>(D) * NR;
+  float* const st_base = p.state + static_cast<size_t>(cluster_id) * p.state_floats;
+  float* const Yc = st_base + kMaxStages * arr;
+  float* const normpart = st_base + (kMaxStages + 2) * arr;            // [4][NR]
+  unsigned char* const xa0 = p.xa + static_cast<size_t>(cluster_id) * 2 * p.xa_buf_bytes;
+  unsigned char* const xa1 = xa0 + p.xa_buf_bytes;
+
+  const bool epi = warp < H3_EPI_WARPS;
+  H3Slice<NR> sl;
+  sl.base = st_base; sl.arr = arr; sl.own_f0 = own_f0; sl.nit = own_nf / 32; sl.warp = warp; sl.fs = lane >> 3; sl.g = lane & 7;
+  const int ns = tb.n_stages;
+  const int kshift0 = h3_log2(p.lay[0].KCH);
+
+  for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
+    const int row0 = tile * NR;
+    // ---- per-row solver state (PoseODERNN.py:70-75; odernn_fwd.cu:interval_begin)
+    int run = 0;
+    if (tid < NR) {
+      const int r = tid, g = row0 + r;
+      const bool valid = g < p.M;
+      const int lyr = valid ? g / p.Bsub : 0, jseq = valid ? g - lyr * p.Bsub : 0;
+      const int b = valid ? (p.seq ? p.seq[jseq] : jseq) : 0;
+      rs.grow[r] = valid ? static_cast<long long>(lyr) * p.B + b : -1;
+      rs.bidx[r] = b; rs.lyr[r] = lyr;
+      float t0 = 0.f, t1 = 0.f;
+      if (valid) {
+        t0 = p.ts[static_cast<size_t>(b) * p.ts_ld + p.interval];
+        t1 = p.ts[static_cast<size_t>(b) * p.ts_ld + p.interval + 1];
+      }
+      rs.t[r] = t0; rs.tend[r] = t1;
+      rs.tmin[r] = fminf(t0, t1); rs.tmax[r] = fmaxf(t0, t1);
+      rs.nsteps[r] = 0; rs.nacc[r] = 0; rs.upd[r] = 0; rs.status[r] = 0;
+      if (p.adaptive) {
+        rs.dt[r] = fminf(fmaxf(p.dt0, sub_(rs.tmin[r], t0)), sub_(rs.tmax[r], t0));
+        run = (valid && t0 < t1) ? 1 : 0;
+      } else {
+        rs.dt[r] = __fdiv_rn(sub_(t1, t0), static_cast<float>(p.substeps));
+        run = valid ? 1 : 0;
+      }
+      rs.run[r] = run;
+    }
+    int any_running = __syncthreads_or(run);
+    // ---- the tile's state rows (row-major [M][D]) -> feature-major scratch, own feature slice
+    if (epi) {
+      const int nf4 = own_nf / 4;
+      for (int item = tid; item < NR * nf4; item += H3_EPI_THREADS) {
+        const int n = item / nf4, f4 = item - n * nf4;
+        const long long gr = rs.grow[n];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr >= 0) v = *reinterpret_cast<const float4*>(p.Y + static_cast<size_t>(gr) * D + own_f0 + 4 * f4);
+        float* dst = Yc + static_cast<size_t>(own_f0 + 4 * f4) * NR + n;
+        __stcg(dst, v.x); __stcg(dst + NR, v.y); __stcg(dst + 2 * NR, v.z); __stcg(dst + 3 * NR, v.w);
+      }
+      named_bar_sync(1, H3_EPI_THREADS);      // the elementwise passes walk the slice with another thread mapping
+    }
+    int loops = 0;
+    bool have_k0 = false;
+
+    while (any_running) {
+      ++loops;
+      for (int st = (tb.fsal && have_k0) ? 1 : 0; st < ns; ++st) {
+        // ---- stage argument -> activation image of the first Linear (own feature slice, all rows)
+        if (epi) {
+          if (st == 0) h3_stage_input<0, NR>(sl, tb.a[0], rs.dt, xa0, kshift0);
+          else H3_DISPATCH_STAGES(st, (h3_stage_input<(NSV < kMaxStages ? NSV : kMaxStages - 1), NR>(sl, tb.a[st], rs.dt, xa0, kshift0)))
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        __syncwarp();
+        h3_cluster_sync();
+        // ---- ODEFunc on the tensor cores; last Linear (+ Tanh) -> K[st]
+        for (int l = 0; l < NL; ++l) {
+          const bool last = l == NL - 1;
+          const H3Layer* next = !last ? &p.lay[l + 1] : (st + 1 < ns ? &p.lay[0] : nullptr);
+          h3_layer<NR>(c, p.lay[l], next, (l & 1) ? xa1 : xa0, (l & 1) ? xa0 : xa1, last ? 0 : h3_log2(p.lay[l + 1].KCH),
+                       last ? st_base + static_cast<size_t>(st) * arr : nullptr);
+        }
+      }
+      have_k0 = true;
+
+      if (p.adaptive) {
+        // ---- y1, embedded error, this CTA's share of the per-row error norm
+        if (epi) {
+          float sum[NR / 32][4];
+          H3_DISPATCH_STAGES(ns, (h3_error_pass<NSV, NR>(sl, tb, rs.dt, p.atol, p.rtol, sum)))
+#pragma unroll
+          for (int m = 0; m < NR / 32; ++m)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float v = sum[m][i];
+              v = add_(v, __shfl_xor_sync(0xffffffffu, v, 8));
+              v = add_(v, __shfl_xor_sync(0xffffffffu, v, 16));
+              if (sl.fs == 0) rs.psum[warp][32 * m + 4 * sl.g + i] = v;
+            }
+          named_bar_sync(1, H3_EPI_THREADS);
+          if (tid < NR) {
+            float tot = rs.psum[0][tid];
+#pragma unroll
+            for (int w = 1; w < H3_EPI_WARPS; ++w) tot = add_(tot, rs.psum[w][tid]);
+            __stcg(normpart + static_cast<size_t>(crank) * NR + tid, tot);
+          }
+        }
+        __syncwarp();
+        h3_cluster_sync();
+        // ---- per-row controller, identical in every CTA (odernn_fwd.cu:controller; torchode IntegralController)
+        run = 0;
+        if (tid < NR) {
+          const int r = tid;
+          run = rs.run[r];
+          const float dt = rs.dt[r];
+          float t = rs.t[r];
+          const float tend = rs.tend[r];
+          bool accept = true, finite = true;
+          float dt_next = dt;
+          if (tb.has_err) {
+            float total = 0.f;
+#pragma unroll
+            for (int k = 0; k < H3_NC; ++k) total = add_(total, __ldcg(normpart + k * NR + r));
+            const float ratio = sqrtf(__fdiv_rn(total, static_cast<float>(D)));
+            finite = isfinite(ratio);
+            accept = p.accept_strict ? (ratio < 1.0f) : (ratio <= 1.0f);
+            float factor = mul_(p.safety, powf(ratio, tb.exponent));
+            factor = fminf(fmaxf(factor, p.fmin), p.fmax);
+            if (p.floor_factor && accept) factor = fmaxf(factor, 1.0f);
+            dt_next = mul_(dt, factor);
+          }
+          const int upd = (accept && run) ? 1 : 0;
+          rs.nsteps[r] += run;
+          rs.nacc[r] += upd;
+          const bool lands = p.exact_landing && dt >= sub_(tend, t);
+          t = upd ? (lands ? tend : add_(t, dt)) : t;
+          rs.upd[r] = upd;
+          if (run && !finite) rs.status[r] = max(rs.status[r], 2);
+          run = (run && t < tend && finite) ? 1 : 0;
+          if (run && loops >= p.max_steps) { rs.status[r] = max(rs.status[r], 1); run = 0; }
+          float dtn = run ? dt_next : dt;
+          dtn = fminf(fmaxf(dtn, sub_(rs.tmin[r], t)), sub_(rs.tmax[r], t));
+          rs.t[r] = t;
+          rs.dt[r] = dtn;
+          rs.run[r] = run;
+        }
+        any_running = __syncthreads_or(run);
+        // ---- commit: accepted rows take y1; FSAL carry (end point rule "y1": exact landing makes y1 the value at t_end)
+        if (epi) h3_commit_rows<NR>(sl, ns, tb.fsal, rs.upd);
+      } else {
+        if (epi) {
+          H3_DISPATCH_STAGES(ns, (h3_fixed_commit<NSV, NR>(sl, tb, rs.dt)))
+          if (tid < NR && rs.grow[tid] >= 0) { rs.nsteps[tid] += 1; rs.nacc[tid] += 1; }
+        }
+        any_running = loops < p.substeps;
+      }
+      // the elementwise passes of the next iteration read what this one wrote with a different thread mapping only
+      // within the epilogue warps of this CTA
+      if (epi) named_bar_sync(1, H3_EPI_THREADS);
+    }
+
+    // ---- evolved state back to [M][D]; stats / status of the interval
+    __syncthreads();
+    if (epi) {
+      const int nf4 = own_nf / 4;
+      for (int item = tid; item < NR * nf4; item += H3_EPI_THREADS) {
+        const int n = item / nf4, f4 = item - n * nf4;
+        const long long gr = rs.grow[n];
+        if (gr < 0) continue;
+        const float* src = Yc + static_cast<size_t>(own_f0 + 4 * f4) * NR + n;
+        const float4 v = make_float4(__ldcg(src), __ldcg(src + NR), __ldcg(src + 2 * NR), __ldcg(src + 3 * NR));
+        *reinterpret_cast<float4*>(p.Y + static_cast<size_t>(gr) * D + own_f0 + 4 * f4) = v;
+      }
+      if (crank == 0 && tid < NR && rs.grow[tid] >= 0) {
+        if (p.stats) {
+          int* sp = p.stats + ((static_cast<size_t>(p.interval) * p.L + rs.lyr[tid]) * p.B + rs.bidx[tid]) * 2;
+          sp[0] = rs.nsteps[tid]; sp[1] = rs.nacc[tid];
+        }
+        if (p.status && rs.status[tid]) atomicMax(p.status + rs.bidx[tid], rs.status[tid]);
+      }
+    }
+    __syncthreads();
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  h3_cluster_sync();
+  if (warp == H3_WARP_MMA) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "r"(512u) : "memory");
+  }
+}
+
+// W [N][K] (PyTorch layout) -> per-CTA fp16 hi / lo operand images:
+// [cta][k-chunk][tile][hi | lo][feature / 8][k / 8][feature % 8][k % 8]; one thread per 16-byte piece (8 k of one feature)
+__global__ void h3_pack_weight_kernel(const float* __restrict__ W, int N, int K, int Fc, int T, int KCH, unsigned char* __restrict__ dst) {
+  const int nch = K / KCH, k8n = KCH / 8;
+  const size_t total = static_cast<size_t>(H3_NC) * nch * T * 128 * k8n;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    size_t r = i;
+    const int k8 = static_cast<int>(r % k8n); r /= k8n;
+    const int m = static_cast<int>(r % 128); r /= 128;
+    const int t = static_cast<int>(r % T); r /= T;
+    const int kc = static_cast<int>(r % nch); r /= nch;
+    const int cta = static_cast<int>(r);
+    const int f = cta * Fc + (t == 0 ? 0 : Fc - 128) + m;
+    const float* src = W + static_cast<size_t>(f) * K + static_cast<size_t>(kc) * KCH + 8 * k8;
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h3_split(src[e], hi[e], lo[e]);
+    const size_t tile_bytes = static_cast<size_t>(128) * KCH * 2;
+    unsigned char* o = dst + (static_cast<size_t>(cta) * nch + kc) * H3_WCHUNK + static_cast<size_t>(t) * 2 * tile_bytes +
+                       static_cast<size_t>(m >> 3) * (k8n * 128) + static_cast<size_t>(k8) * 128 + static_cast<size_t>(m & 7) * 16;
+    *reinterpret_cast<uint4*>(o) = make_uint4(h3_pack2(hi[0], hi[1]), h3_pack2(hi[2], hi[3]), h3_pack2(hi[4], hi[5]), h3_pack2(hi[6], hi[7]));
+    *reinterpret_cast<uint4*>(o + tile_bytes) =
+        make_uint4(h3_pack2(lo[0], lo[1]), h3_pack2(lo[2], lo[3]), h3_pack2(lo[4], lo[5]), h3_pack2(lo[6], lo[7]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct H3Plan {
+  int NL, NR, ntiles, nclusters;
+  int K[H3_MAXL], N[H3_MAXL], Fc[H3_MAXL], T[H3_MAXL], KCH[H3_MAXL], nch[H3_MAXL], nseg[H3_MAXL];
+  size_t off_w[H3_MAXL], off_xa, xa_buf_bytes, off_state, state_floats, total_bytes, smem_bytes;
+};
+
+int h3_plan(const odevio_odernn_cfg& c, H3Plan& pl) {
+  const long long M = static_cast<long long>(c.L) * c.B;
+  if (M <= 0 || M > 0x7fffffffLL || c.n_hidden < 1 || c.n_hidden + 1 > H3_MAXL) return ODEVIO_E_SHAPE;
+  int dev = 0, nsm = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) {
+    cudaGetLastError();
+    nsm = 148;
+  }
+  pl.NL = c.n_hidden + 1;
+  pl.NR = 64;
+  pl.ntiles = static_cast<int>((M + pl.NR - 1) / pl.NR);
+  pl.nclusters = nsm / H3_NC;
+  if (pl.nclusters > pl.ntiles) pl.nclusters = pl.ntiles;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = (off + n + 1023) / 1024 * 1024; return o; };
+  int kmax = 0;
+  for (int l = 0; l < pl.NL; ++l) {
+    const int K = l == 0 ? c.D : c.H, N = l == pl.NL - 1 ? c.D : c.H;
+    if (N % H3_NC) return ODEVIO_E_SHAPE;
+    const int Fc = N / H3_NC;
+    if (Fc < 128 || Fc > 256 || Fc % 32) return ODEVIO_E_SHAPE;
+    const int T = Fc > 128 ? 2 : 1, KCH = 64 / T;
+    if (K % KCH || K % 64) return ODEVIO_E_SHAPE;
+    pl.K[l] = K; pl.N[l] = N; pl.Fc[l] = Fc; pl.T[l] = T; pl.KCH[l] = KCH; pl.nch[l] = K / KCH;
+    int nseg = 512 / (T * pl.NR) - 1;
+    if (nseg > 4) nseg = 4;
+    if (nseg > pl.nch[l]) nseg = pl.nch[l];
+    if (nseg < 1) return ODEVIO_E_SHAPE;
+    pl.nseg[l] = nseg;
+    pl.off_w[l] = take(static_cast<size_t>(H3_NC) * pl.nch[l] * H3_WCHUNK);
+    if (K > kmax) kmax = K;
+  }
+  if ((c.D / H3_NC) % 32 || c.D % 16) return ODEVIO_E_SHAPE;
+  pl.xa_buf_bytes = (static_cast<size_t>(kmax) * pl.NR * 4 + 1023) / 1024 * 1024;       // hi + lo fp16 images of kmax x NR
+  pl.off_xa = take(static_cast<size_t>(pl.nclusters) * 2 * pl.xa_buf_bytes);
+  pl.state_floats = (static_cast<size_t>(kMaxStages + 2) * c.D + H3_NC) * pl.NR;
+  pl.state_floats = (pl.state_floats + 255) / 256 * 256;
+  pl.off_state = take(static_cast<size_t>(pl.nclusters) * pl.state_floats * sizeof(float));
+  pl.total_bytes = off;
+  pl.smem_bytes = static_cast<size_t>(H3_NWS) * H3_WCHUNK + static_cast<size_t>(H3_NXS) * 4 * 64 * pl.NR + 1024;
+  return 0;
+}
+
+typedef void (*H3Kernel)(H3Params);
+H3Kernel h3_kernel_of(const H3Plan&) { return static_cast<H3Kernel>(odernn_h3_evolve_kernel<64>); }
+
+cudaError_t h3_launch_config(const H3Plan& pl, cudaLaunchConfig_t& lc, cudaLaunchAttribute& at, int nclusters, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(h3_kernel_of(pl), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem_bytes));
+  if (e != cudaSuccess) return e;
+  memset(&lc, 0, sizeof(lc));
+  lc.blockDim = dim3(H3_THREADS); lc.dynamicSmemBytes = pl.smem_bytes; lc.stream = stream;
+  at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = H3_NC; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  lc.attrs = &at; lc.numAttrs = 1;
+  lc.gridDim = dim3(nclusters * H3_NC);
+  return cudaSuccess;
+}
+
+int g_h3_last_clusters = 0, g_h3_last_max_clusters = 0, g_h3_last_rows = 0;
+constexpr int kH3TimingSlots = 512;
+bool g_h3_timing = false;
+int g_h3_timing_n = 0;
+cudaEvent_t g_h3_ev[kH3TimingSlots][2];
+bool g_h3_ev_made = false;
+
+}  // namespace
+
+struct H3Evolve::Impl {
+  H3Plan pl;
+  H3Params prm;
+  int maxc = 0;
+};
+
+size_t odernn_h3_workspace_bytes(const odevio_odernn_cfg& c) {
+  H3Plan pl;
+  if (h3_plan(c, pl) != 0) return 0;
+  return pl.total_bytes;
+}
+
+void odernn_h3_last_geometry(int* clusters, int* max_clusters, int* rows) {
+  *clusters = g_h3_last_clusters; *max_clusters = g_h3_last_max_clusters; *rows = g_h3_last_rows;
+}
+void odernn_h3_timing_enable(bool on) {
+  g_h3_timing = on; g_h3_timing_n = 0;
+  if (on && !g_h3_ev_made) {
+    for (int i = 0; i < kH3TimingSlots; ++i) { cudaEventCreate(&g_h3_ev[i][0]); cudaEventCreate(&g_h3_ev[i][1]); }
+    g_h3_ev_made = true;
+  }
+}
+int odernn_h3_timing_read(float* total_ms, int* launches) {
+  float tot = 0.f;
+  for (int i = 0; i < g_h3_timing_n; ++i) {
+    cudaError_t e = cudaEventSynchronize(g_h3_ev[i][1]);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, g_h3_ev[i][0], g_h3_ev[i][1]);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    tot += ms;
+  }
+  *total_ms = tot; *launches = g_h3_timing_n;
+  g_h3_timing_n = 0;
+  return 0;
+}
+
+H3Evolve::H3Evolve() : impl(nullptr) {}
+H3Evolve::~H3Evolve() { delete impl; }
+
+int H3Evolve::prepare(const odevio_odernn_cfg& c, const DevTableau& tab, bool adaptive, const float* const* ode_w,
+                      const float* const* ode_b, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  delete impl;
+  impl = new Impl();
+  H3Plan& pl = impl->pl;
+  const int rc = h3_plan(c, pl);
+  if (rc != 0) return rc;
+  if (workspace_bytes < pl.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ODEVIO_E_WORKSPACE;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  H3Params& p = impl->prm;
+  memset(&p, 0, sizeof(p));
+  p.M = c.L * c.B; p.B = c.B; p.L = c.L; p.D = c.D; p.NL = pl.NL;
+  for (int l = 0; l < pl.NL; ++l) {
+    if (!ode_w[l] || !ode_b[l]) return ODEVIO_E_NULL;
+    H3Layer& y = p.lay[l];
+    y.K = pl.K[l]; y.N = pl.N[l]; y.Fc = pl.Fc[l]; y.T = pl.T[l]; y.KCH = pl.KCH[l]; y.nch = pl.nch[l]; y.nseg = pl.nseg[l];
+    y.act = l == pl.NL - 1 ? ACT_TANH : c.activation;
+    h3_pack_weight_kernel<<<296, 256, 0, stream>>>(ode_w[l], pl.N[l], pl.K[l], pl.Fc[l], pl.T[l], pl.KCH[l], ws + pl.off_w[l]);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    y.Wimg = ws + pl.off_w[l]; y.bias = ode_b[l];
+  }
+  p.xa = ws + pl.off_xa; p.xa_buf_bytes = pl.xa_buf_bytes;
+  p.state = reinterpret_cast<float*>(ws + pl.off_state); p.state_floats = pl.state_floats;
+  p.ntiles = pl.ntiles;
+  p.tab = tab; p.adaptive = adaptive ? 1 : 0; p.substeps = c.substeps;
+  p.atol = c.atol; p.rtol = c.rtol; p.dt0 = c.dt0; p.safety = c.safety; p.fmin = c.factor_min; p.fmax = c.factor_max;
+  p.accept_strict = c.accept_strict; p.floor_factor = c.floor_factor; p.max_steps = c.max_steps; p.exact_landing = c.exact_landing;
+  return 0;
+}
+
+int H3Evolve::max_clusters() {
+  if (!impl) return 0;
+  if (impl->maxc > 0) return impl->maxc;
+  cudaLaunchConfig_t lc; cudaLaunchAttribute at;
+  if (h3_launch_config(impl->pl, lc, at, impl->pl.nclusters, nullptr) != cudaSuccess) { cudaGetLastError(); return impl->pl.nclusters; }
+  int maxc = 0;
+  if (cudaOccupancyMaxActiveClusters(&maxc, h3_kernel_of(impl->pl), &lc) != cudaSuccess || maxc <= 0) {
+    cudaGetLastError();
+    maxc = impl->pl.nclusters;
+  }
+  if (maxc > impl->pl.nclusters) maxc = impl->pl.nclusters;       // scratch is sized for pl.nclusters
+  impl->maxc = maxc;
+  return maxc;
+}
+
+int H3Evolve::evolve(float* Y, int Bsub, const int* seq, const float* ts, int ts_ld, int interval, int* stats, int* status,
+                     cudaStream_t stream) {
+  if (!impl) return ODEVIO_E_NULL;
+  H3Params p = impl->prm;
+  H3Plan& pl = impl->pl;
+  if (Bsub <= 0 || Bsub > p.B) return ODEVIO_E_SHAPE;
+  const int rows = p.L * Bsub;
+  p.M = rows; p.ntiles = (rows + pl.NR - 1) / pl.NR;
+  p.Bsub = Bsub; p.seq = seq;
+  p.Y = Y; p.ts = ts; p.ts_ld = ts_ld; p.interval = interval; p.stats = stats; p.status = status;
+  int nclusters = max_clusters();
+  if (nclusters > p.ntiles) nclusters = p.ntiles;
+  cudaLaunchConfig_t lc; cudaLaunchAttribute at;
+  cudaError_t e = h3_launch_config(pl, lc, at, nclusters, stream);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  g_h3_last_clusters = nclusters; g_h3_last_max_clusters = impl->maxc; g_h3_last_rows = rows;
+  const bool timed = g_h3_timing && g_h3_timing_n < kH3TimingSlots;
+  if (timed) cudaEventRecord(g_h3_ev[g_h3_timing_n][0], stream);
+  e = cudaLaunchKernelEx(&lc, h3_kernel_of(pl), p);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (timed) { cudaEventRecord(g_h3_ev[g_h3_timing_n][1], stream); ++g_h3_timing_n; }
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+}  // namespace odevio

@@ -1,6 +1,6 @@
-"""GPU parity of the tensor-core solver path (cfg.precision = ODEVIO_PRECISION_TF32X3, odernn_tc.cu):
-per interval one cluster kernel evolves all L*B rows (3xTF32 ODEFunc GEMMs on tcgen05, solver loop in the
-cluster), then the FMA kernel runs the jump + head.  Same oracle, same tolerances as the fp32 FMA path
+"""GPU parity of the tensor-core solver paths (cfg.precision = ODEVIO_PRECISION_TF32X3: odernn_tc.cu;
+ODEVIO_PRECISION_FP16X3: odernn_h3.cu): per interval one cluster kernel evolves all L*B rows (3xTF32 / 3xFP16
+ODEFunc GEMMs on tcgen05, solver loop in the cluster), then the FMA kernel runs the jump + head.  Same oracle, same tolerances as the fp32 FMA path
 (tests/test_odernn_gpu.py): poses <= 1e-5 max-norm relative, identical step counts wherever the reference
 semantics determine them at fp32 precision."""
 
@@ -10,6 +10,10 @@ import torch
 from helpers import POSE_RTOL, STATE_RTOL, inputs, make_pair, rel_err, run_pair
 
 pytestmark = pytest.mark.gpu
+
+# both tensor-core solvers behind the same ABI switch: "tf32x3" = odernn_tc.cu (clusters of 8 / 4, 128-row tiles, 3xTF32),
+# "fp16x3" = odernn_h3.cu (clusters of 4, 64-row tiles, weights on the M side, 3xFP16; the bench default)
+PRECISIONS = ["tf32x3", "fp16x3"]
 
 
 def _summary(out):
@@ -24,38 +28,43 @@ def _check(out, slack=4.0):
     assert out["h_err"] <= max(STATE_RTOL, slack * out["spread_h"]), s
 
 
-def test_tc_rk4_config1(cuda_device):
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_tc_rk4_config1(cuda_device, prec):
     """BASELINE config 1 shape on the tensor-core path: fixed-step rk4, one (mostly padded) 128-row tile."""
-    ref, mod = make_pair(cuda_device, ode_solver="rk4", ode_precision="tf32x3")
+    ref, mod = make_pair(cuda_device, ode_solver="rk4", ode_precision=prec)
     out = run_pair(ref, mod, *inputs(16))
     _check(out)
     assert out["steps_equal"] and out["pose_err"] <= POSE_RTOL, _summary(out)
 
 
-def test_tc_rk4_substeps(cuda_device):
-    ref, mod = make_pair(cuda_device, ode_solver="rk4_38", ode_substeps=3, ode_precision="tf32x3", bias_std=0.05)
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_tc_rk4_substeps(cuda_device, prec):
+    ref, mod = make_pair(cuda_device, ode_solver="rk4_38", ode_substeps=3, ode_precision=prec, bias_std=0.05)
     out = run_pair(ref, mod, *inputs(24, S=4, irregular=True))
     _check(out)
     assert out["pose_err"] <= POSE_RTOL, _summary(out)
 
 
 @pytest.mark.parametrize("solver", ["dopri5", "tsit5", "heun"])
-def test_tc_adaptive_menu(cuda_device, solver):
-    ref, mod = make_pair(cuda_device, ode_solver=solver, ode_precision="tf32x3", bias_std=0.05)
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_tc_adaptive_menu(cuda_device, solver, prec):
+    ref, mod = make_pair(cuda_device, ode_solver=solver, ode_precision=prec, bias_std=0.05)
     out = run_pair(ref, mod, *inputs(16, irregular=True), ensemble=3)
     _check(out)
 
 
-def test_tc_dopri5_irregular_rtol_ragged(cuda_device):
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_tc_dopri5_irregular_rtol_ragged(cuda_device, prec):
     """BASELINE config 2 semantics; B = 100 -> 200 rows = one full and one ragged tile, the second tile
     starts inside layer 1 (row = l * B + b)."""
-    ref, mod = make_pair(cuda_device, ode_solver="dopri5", ode_rtol=1e-3, ode_precision="tf32x3", bias_std=0.05)
+    ref, mod = make_pair(cuda_device, ode_solver="dopri5", ode_rtol=1e-3, ode_precision=prec, bias_std=0.05)
     out = run_pair(ref, mod, *inputs(100, irregular=True, seed=3), ensemble=3)
     _check(out)
 
 
-def test_tc_prev_state_and_gru(cuda_device):
-    ref, mod = make_pair(cuda_device, ode_rnn_type="gru", ode_precision="tf32x3", bias_std=0.05)
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_tc_prev_state_and_gru(cuda_device, prec):
+    ref, mod = make_pair(cuda_device, ode_rnn_type="gru", ode_precision=prec, bias_std=0.05)
     fv, fi, ts = inputs(16, S=5, irregular=True, offset=37.5)
     g = torch.Generator().manual_seed(5)
     prev = 0.3 * torch.randn(2, 16, 768, generator=g)
@@ -64,7 +73,8 @@ def test_tc_prev_state_and_gru(cuda_device):
 
 
 @pytest.mark.parametrize("B", [1024, 1200, 2600])
-def test_tc_full_size_rows_match_oracle_subset(cuda_device, B):
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_tc_full_size_rows_match_oracle_subset(cuda_device, B, prec):
     """configs[1] at full size on the tensor-core path.  B = 1024 -> 2048 rows = 16 tiles: on a GPU that holds 15
     clusters 64 sequences per interval run concurrently in the FMA kernel (side launch); B = 1200 -> 19 tiles: the
     clusters-of-4 pre-split instantiation, one round; B = 2600 -> 41 tiles > 37 co-resident clusters of 4: its
@@ -74,7 +84,7 @@ def test_tc_full_size_rows_match_oracle_subset(cuda_device, B):
     import odevio_b200
     from helpers import noise_ensemble
     from oracle.pose_odernn import default_opt
-    ref, mod = make_pair(cuda_device, ode_solver="dopri5", ode_rtol=1e-3, ode_precision="tf32x3", bias_std=0.05)
+    ref, mod = make_pair(cuda_device, ode_solver="dopri5", ode_rtol=1e-3, ode_precision=prec, bias_std=0.05)
     fv, fi, ts = inputs(B, 10, irregular=True, seed=0)
     dev = cuda_device
     with torch.no_grad():
@@ -106,8 +116,9 @@ def test_tc_full_size_rows_match_oracle_subset(cuda_device, B):
     assert rel_err(p.cpu(), p_f.cpu()) <= 1e-3
 
 
-def test_tc_evolve_state(cuda_device):
-    ref, mod = make_pair(cuda_device, ode_solver="dopri5", ode_rtol=1e-3, ode_precision="tf32x3", bias_std=0.05)
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_tc_evolve_state(cuda_device, prec):
+    ref, mod = make_pair(cuda_device, ode_solver="dopri5", ode_rtol=1e-3, ode_precision=prec, bias_std=0.05)
     g = torch.Generator().manual_seed(11)
     B = 37
     state = 0.5 * torch.randn(B, mod.f_len, generator=g)
@@ -122,25 +133,27 @@ def test_tc_evolve_state(cuda_device):
     assert (ns == want["n_steps"]).float().mean().item() >= 0.97
 
 
-def test_tc_rejects_training_and_dense(cuda_device):
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_tc_rejects_training_and_dense(cuda_device, prec):
     """The tensor-core path is inference-only: training falls back to the FMA kernels (precision forced to fp32
     for the checkpointed forward), the dense end-point rule is refused with a clear error."""
     import odevio_b200
     from oracle.pose_odernn import default_opt
-    mod = odevio_b200.PoseODERNN(default_opt(ode_precision="tf32x3", ode_endpoint="dense")).to(cuda_device).eval()
+    mod = odevio_b200.PoseODERNN(default_opt(ode_precision=prec, ode_endpoint="dense")).to(cuda_device).eval()
     fv, fi, ts = (t.to(cuda_device) for t in inputs(4, S=2))
     with pytest.raises(Exception):
         with torch.no_grad():
             mod(fv, fi, ts)
 
 
-def test_tc_evolve_state_side_launch_l1(cuda_device):
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_tc_evolve_state_side_launch_l1(cuda_device, prec):
     """evolve_state is an L = 1 problem: 2048 rows = 16 tiles -> with 15 co-resident clusters the 128 shortest-interval
     rows run in the FFMA side launch as 8-row `<8, 1>` tiles.  Fixed-step rk4 (no controller feedback), so every row must
     agree with the FFMA-only kernel to fp32 parity, whichever kernel integrated it."""
     import odevio_b200
     from oracle.pose_odernn import default_opt
-    ref, mod = make_pair(cuda_device, ode_solver="rk4", ode_substeps=2, ode_precision="tf32x3", bias_std=0.05)
+    ref, mod = make_pair(cuda_device, ode_solver="rk4", ode_substeps=2, ode_precision=prec, bias_std=0.05)
     mod_f = odevio_b200.PoseODERNN(default_opt(ode_solver="rk4", ode_substeps=2))
     mod_f.load_state_dict(ref.state_dict())
     mod_f = mod_f.to(cuda_device).eval()
