@@ -352,24 +352,8 @@ ODEVIO_API int32_t odevio_adam_step(int64_t n, float* params, const float* grads
                                     int32_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
                                     float max_norm, float* norm_coef, void* workspace, size_t workspace_bytes, void* stream);
 
-/*
- * Diagnostics (no reference counterpart): launch a dense FFMA loop on `blocks` CTAs of 512 threads
- * and report the FLOPs it performs in *flops_out (HOST); time it with events around the call to
- * obtain this GPU's fp32 FMA peak, the roofline denominator of ODEVIO_PRECISION_FP32.
- */
-ODEVIO_API int32_t odevio_microbench_ffma(int32_t iters, int32_t blocks, float* sink, double* flops_out,
-                                          void* stream);
-
-/* Diagnostics: out[0] = clusters launched, out[1] = co-resident cluster maximum (cudaOccupancyMaxActiveClusters),
- * out[2] = rows taken by the cluster kernel (the rest ran in the FMA side launch) of the last ODEVIO_PRECISION_TF32X3
- * solver launch of this process.  out: int32[3] (HOST). */
-ODEVIO_API int32_t odevio_debug_tc_geometry(int32_t* out);
-/* Development (-DODEVIO_FT_TIMELINE builds): 64 clock64 stamps of cluster 0 / CTA 0 / tile 0 of the last solver iteration. */
-ODEVIO_API int32_t odevio_debug_tc_timeline(long long* host_dst);
-/* Measurement hook: enable = 1 / 0 switches CUDA-event timing of every ODEVIO_PRECISION_TF32X3 solver launch on / off
- * (events on the launching stream); enable = -1 synchronises and returns the summed kernel duration (ms, HOST) and
- * the number of launches since the last read in *total_ms / *launches.  Not thread-safe; used by bench.py. */
-ODEVIO_API int32_t odevio_debug_tc_timing(int32_t enable, float* total_ms, int32_t* launches);
+/* Diagnostics / measurement hooks (odevio_debug_*, odevio_microbench_ffma) are NOT part of the product ABI: they are
+ * declared in include/odevio_debug.h. */
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@
 #include <mutex>
 
 #include "../../include/odevio.h"
+#include "../../include/odevio_debug.h"
 #include "odernn_params.h"
 #include "odernn_tc.h"
 #include "odernn_h3.h"
@@ -729,6 +730,10 @@ int32_t odevio_debug_tc_geometry(int32_t* out) {
 
 int32_t odevio_debug_tc_timeline(long long* host_dst) {
   return host_dst ? odernn_tc_debug_timeline(host_dst) : ODEVIO_E_NULL;
+}
+
+int32_t odevio_debug_h3_timeline(long long* host_dst) {
+  return host_dst ? odernn_h3_debug_timeline(host_dst) : ODEVIO_E_NULL;
 }
 
 int32_t odevio_debug_tc_timing(int32_t enable, float* total_ms, int32_t* launches) {

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "../../include/odevio.h"
+#include "../../include/odevio_debug.h"
 
 namespace odevio {
 

@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include "../../include/odevio.h"
+#include "../../include/odevio_debug.h"
 #include "common.cuh"
 #include "ft_layer.cuh"
 

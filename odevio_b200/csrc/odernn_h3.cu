@@ -45,6 +45,20 @@ namespace odevio {
 
 namespace {
 
+// development timeline (-DODEVIO_H3_TIMELINE): clock64 stamps / wait sums of cluster 0 / CTA 0, last solver iteration
+__device__ long long g_h3_dbg[96];
+#ifdef ODEVIO_H3_TIMELINE
+#define H3_STAMP(idx) do { if (blockIdx.x == 0) g_h3_dbg[idx] = clock64(); } while (0)
+#define H3_ADD(idx, v) do { if (blockIdx.x == 0) g_h3_dbg[idx] += (v); } while (0)
+#define H3_SET(idx, v) do { if (blockIdx.x == 0) g_h3_dbg[idx] = (v); } while (0)
+#define H3_CLOCK() clock64()
+#else
+#define H3_STAMP(idx) do { } while (0)
+#define H3_ADD(idx, v) do { } while (0)
+#define H3_SET(idx, v) do { } while (0)
+#define H3_CLOCK() 0ll
+#endif
+
 constexpr int H3_NC = 4;                  // CTAs per cluster = feature slices of every Linear
 constexpr int H3_MAXL = ODEVIO_MAX_ODE_LINEARS;
 constexpr int H3_EPI_WARPS = 8;           // warps 0-7: epilogue + elementwise solver passes
@@ -188,8 +202,10 @@ __device__ __forceinline__ void h3_issue_chunk(uint32_t tmem, uint32_t wbase, ui
 // weight chunks are issued before the barrier.
 template <int NR>
 __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Layer* next, const unsigned char* xsrc,
-                                         unsigned char* xdst, int xdst_kshift, float* out) {
+                                         unsigned char* xdst, int xdst_kshift, float* out, int stamp = 0) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sb = 16 + 10 * stamp;          // timeline slots of this layer
+  (void)sb;
   constexpr uint32_t XSTAGE = 4u * 64u * NR;                 // bytes of an activation stage (KCH = 64: hi | lo)
   const int nch = L.nch;
 
@@ -247,8 +263,17 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
     for (int ch = 0; ch < nch; ++ch, ++gw, ++gx) {
       const uint32_t ws = gw & (H3_NWS - 1), wph = (gw / H3_NWS) & 1u;
       const uint32_t xs = gx & (H3_NXS - 1), xph = (gx / H3_NXS) & 1u;
+      const long long tw0 = H3_CLOCK();
       mbar_wait(&c.w_full[ws], wph);
+      const long long tw1 = H3_CLOCK();
       mbar_wait(&c.x_full[xs], xph);
+      const long long tw2 = H3_CLOCK();
+      if (lane == 0) {
+        if (ch == 0) { H3_STAMP(sb + 0); H3_SET(sb + 6, 0); H3_SET(sb + 7, 0); }
+        else { H3_ADD(sb + 6, tw1 - tw0); H3_ADD(sb + 7, tw2 - tw1); }     // starvation after the first chunk: W ring / X ring
+        if (ch == nch - 1) H3_STAMP(sb + 5);
+      }
+      (void)tw0; (void)tw1; (void)tw2;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t wbase = smem_u32(c.wring + ws * H3_WCHUNK), xbase = smem_u32(c.xring + xs * XSTAGE);
       if (elect_one()) {
@@ -262,9 +287,11 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
     }
     if (elect_one()) h3_commit(c.accum_bar);
     __syncwarp();
+    if (lane == 0) H3_STAMP(sb + 1);
   } else if (warp < H3_EPI_WARPS) {
     // ===== epilogue: thread = output feature (TMEM lane); warps w and w + 4 share lane quarter w & 3 and split the rows
     mbar_wait(c.accum_bar, c.accum_phase);
+    if (tid == 0) H3_STAMP(sb + 2);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3, h = warp >> 2;
     const int nseg = L.nseg, act = L.act;
@@ -316,6 +343,7 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
     }
     asm volatile("fence.proxy.async;" ::: "memory");             // generic-proxy global stores -> bulk copies of all 4 CTAs
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (tid == 0) H3_STAMP(sb + 3);
   }
   c.accum_phase ^= 1u;
   c.wcount += static_cast<uint32_t>(nch);
@@ -323,6 +351,7 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
   __syncwarp();
   h3_cluster_sync();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid == 0) H3_STAMP(sb + 4);
 }
 
 // ---------------------------------------------------------------------------------------------- elementwise passes
@@ -586,22 +615,27 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_evolve_kernel(const _
 
     while (any_running) {
       ++loops;
+      if (tid == 0) H3_STAMP(0);
       for (int st = (tb.fsal && have_k0) ? 1 : 0; st < ns; ++st) {
         // ---- stage argument -> activation image of the first Linear (own feature slice, all rows)
+        if (tid == 0) H3_STAMP(1);
         if (epi) {
           if (st == 0) h3_stage_input<0, NR>(sl, tb.a[0], rs.dt, xa0, kshift0);
           else H3_DISPATCH_STAGES(st, (h3_stage_input<(NSV < kMaxStages ? NSV : kMaxStages - 1), NR>(sl, tb.a[st], rs.dt, xa0, kshift0)))
           asm volatile("fence.proxy.async;" ::: "memory");
         }
+        if (tid == 0) H3_STAMP(2);
         __syncwarp();
         h3_cluster_sync();
+        if (tid == 0) H3_STAMP(3);
         // ---- ODEFunc on the tensor cores; last Linear (+ Tanh) -> K[st]
         for (int l = 0; l < NL; ++l) {
           const bool last = l == NL - 1;
           const H3Layer* next = !last ? &p.lay[l + 1] : (st + 1 < ns ? &p.lay[0] : nullptr);
           h3_layer<NR>(c, p.lay[l], next, (l & 1) ? xa1 : xa0, (l & 1) ? xa0 : xa1, last ? 0 : h3_log2(p.lay[l + 1].KCH),
-                       last ? st_base + static_cast<size_t>(st) * arr : nullptr);
+                       last ? st_base + static_cast<size_t>(st) * arr : nullptr, l);
         }
+        if (tid == 0) H3_STAMP(4);
       }
       have_k0 = true;
 
@@ -619,6 +653,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_evolve_kernel(const _
               v = add_(v, __shfl_xor_sync(0xffffffffu, v, 16));
               if (sl.fs == 0) rs.psum[warp][32 * m + 4 * sl.g + i] = v;
             }
+          if (tid == 0) H3_STAMP(5);
           named_bar_sync(1, H3_EPI_THREADS);
           if (tid < NR) {
             float tot = rs.psum[0][tid];
@@ -628,7 +663,9 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_evolve_kernel(const _
           }
         }
         __syncwarp();
+        if (tid == 0) H3_STAMP(6);
         h3_cluster_sync();
+        if (tid == 0) H3_STAMP(7);
         // ---- per-row controller, identical in every CTA (odernn_fwd.cu:controller; torchode IntegralController)
         run = 0;
         if (tid < NR) {
@@ -667,8 +704,10 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_evolve_kernel(const _
           rs.run[r] = run;
         }
         any_running = __syncthreads_or(run);
+        if (tid == 0) H3_STAMP(8);
         // ---- commit: accepted rows take y1; FSAL carry (end point rule "y1": exact landing makes y1 the value at t_end)
         if (epi) h3_commit_rows<NR>(sl, ns, tb.fsal, rs.upd);
+        if (tid == 0) H3_STAMP(9);
       } else {
         if (epi) {
           H3_DISPATCH_STAGES(ns, (h3_fixed_commit<NSV, NR>(sl, tb, rs.dt)))
@@ -825,6 +864,9 @@ size_t odernn_h3_workspace_bytes(const odevio_odernn_cfg& c) {
 
 void odernn_h3_last_geometry(int* clusters, int* max_clusters, int* rows) {
   *clusters = g_h3_last_clusters; *max_clusters = g_h3_last_max_clusters; *rows = g_h3_last_rows;
+}
+int odernn_h3_debug_timeline(long long* host_dst) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_dst, g_h3_dbg, sizeof(long long) * 96));
 }
 void odernn_h3_timing_enable(bool on) {
   g_h3_timing = on; g_h3_timing_n = 0;

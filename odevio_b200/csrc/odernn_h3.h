@@ -16,6 +16,8 @@ size_t odernn_h3_workspace_bytes(const odevio_odernn_cfg& c);
 void odernn_h3_last_geometry(int* clusters, int* max_clusters, int* rows);
 void odernn_h3_timing_enable(bool on);
 int odernn_h3_timing_read(float* total_ms, int* launches);
+// development (-DODEVIO_H3_TIMELINE builds): clock64 stamps of cluster 0 / CTA 0, last solver iteration
+int odernn_h3_debug_timeline(long long* host_dst);
 
 class H3Evolve {
  public:

@@ -9,6 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "odevio.h")
+DEBUG_HEADER = os.path.join(ROOT, "include", "odevio_debug.h")       # diagnostics: not part of the product ABI
 
 
 @pytest.fixture(scope="module")
@@ -19,8 +20,8 @@ def lib():
     return _lib.load()
 
 
-def declared_symbols():
-    src = open(HEADER).read()
+def declared_symbols(header=HEADER):
+    src = open(header).read()
     return sorted(set(re.findall(r"ODEVIO_API[^;(]*?\b(odevio_\w+)\s*\(", src)))
 
 
@@ -34,6 +35,14 @@ def test_header_declares_the_expected_entry_points():
 def test_every_declared_symbol_is_exported(lib):
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} declared in include/odevio.h but not exported"
+
+
+def test_debug_hooks_live_in_their_own_header(lib):
+    assert not [n for n in declared_symbols() if "debug" in n or "microbench" in n]
+    dbg = declared_symbols(DEBUG_HEADER)
+    assert dbg and all("debug" in n or "microbench" in n for n in dbg)
+    for name in dbg:
+        assert hasattr(lib, name), f"{name} declared in include/odevio_debug.h but not exported"
 
 
 def test_struct_layout_matches_header(lib):
