@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(B=1024, S=10, v_f_len=512, i_f_len=256, H=512, n=3, L=2, rnn="rnn",
                 solver="dopri5", rtol=1e-3, atol=1e-6, dt0=1e-4)
-CPU_SAMPLE_B = 256          # sequences of the same workload timed on the host per CPU step
+CPU_SAMPLE_B = 1024         # the reference arm and cpu_baseline run the SAME B = 1024 workload on the host cores
 METRIC = "integrated_sequence_steps_per_sec"
 UNIT = "sequence-steps/s"
 
@@ -44,7 +44,9 @@ def workload_name(b=None):
             f"H={w['H']}, n={w['n']}, L={w['L']} nn.RNN, random-init (DeepVIO rule), BASELINE configs[1]")
 
 
-PRECISION = "tf32x3"     # set by --precision: "tf32x3" (tensor-core solver, 3xTF32 = fp32-accurate; default) | "fp32" (FFMA kernel)
+# set by --precision: "fp16x3" (default: odernn_h3.cu, ONE tcgen05 cluster kernel per forward, 3xFP16 = fp32-accurate) |
+# "tf32x3" (round-1 tensor-core solver, per-interval launches) | "fp32" (CUDA-core FFMA kernel)
+PRECISION = "fp16x3"
 
 
 def make_opt():
@@ -128,7 +130,7 @@ class ClockSampler:
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rate(steps, warmup, B):
+def cpu_oracle_rate(steps, warmup, B, opt=None, irregular=True):
     """Oracle restatement of the reference CPU path on `B` sequences of the workload."""
     import torch
     from oracle.modules import deepvio_initialization
@@ -136,12 +138,12 @@ def cpu_oracle_rate(steps, warmup, B):
     from odevio_b200 import synth
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
-    ref = OraclePoseODERNN(make_opt())
+    ref = OraclePoseODERNN(opt or make_opt())
     deepvio_initialization(ref)
     ref.eval()
     w = WORKLOAD
     fv, fi = synth.features(B, w["S"], w["v_f_len"], w["i_f_len"], seed=0)
-    ts = synth.timestamps(B, w["S"], irregular=True, seed=0)
+    ts = synth.timestamps(B, w["S"], irregular=irregular, seed=0)
     times = []
     with torch.no_grad():
         for k in range(warmup + steps):
@@ -168,7 +170,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     rate, sec, threads = cpu_oracle_rate(args.steps, args.warmup, CPU_SAMPLE_B)
-    sample = (f"{CPU_SAMPLE_B} of the {WORKLOAD['B']} sequences per step, oracle restatement of the reference "
+    sample = (f"all {CPU_SAMPLE_B} sequences of the workload per step, oracle restatement of the reference "
               f"CPU regressor path (torchode unavailable offline), eager PyTorch fp32, {cpu_model()}")
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
@@ -266,7 +268,7 @@ def run_ours(args, rank, world, local_rank):
 
         # ---- dominant kernel's average launch duration, live: CUDA events around every solver launch on its stream
         tc_kernel_ms, tc_launches, tc_geo = None, 0, None
-        if PRECISION == "tf32x3":
+        if PRECISION in ("tf32x3", "fp16x3"):
             import ctypes as C
             lib.odevio_debug_tc_timing(1, None, None)
             for _ in range(args.steps):
@@ -299,6 +301,11 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = total_ms.item(), e2e_ms.item()
+    train_info = None
+    if args.train:
+        del flush
+        torch.cuda.empty_cache()
+        train_info = measure_train(args, rank, world, dev)
     if status != 0:
         raise SystemExit(f"bench.py: solver status {status} (non-finite norm / max_steps) -- result invalid")
 
@@ -314,9 +321,33 @@ def run_ours(args, rank, world, local_rank):
         prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(prof):
             with open(prof) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_launch_tc" if PRECISION == "tf32x3" else "dram_bytes_per_launch")
+                traffic = json.load(fh).get({"tf32x3": "dram_bytes_per_launch_tc", "fp16x3": "dram_bytes_per_launch_h3"}.get(
+                    PRECISION, "dram_bytes_per_launch"))
         n_side = 0
-        if PRECISION == "tf32x3":
+        if PRECISION == "fp16x3":
+            # ONE launch per forward: solver loops of all S intervals + rnn jump + pose head in odernn_h3_kernel
+            per_launch_ms = tc_kernel_ms / tc_launches
+            launches_per_step = tc_launches / args.steps
+            h3_achieved = flops / launches_per_step / (per_launch_ms * 1e-3) / 1e12
+            fp16x3_peak = peaks["bf16_tflops_sustained"] / 3.0
+            roofline = {
+                "bound": "tensor", "kernel": "odernn_h3_kernel<64>",
+                "achieved": h3_achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": h3_achieved / peaks["bf16_tflops_sustained"], "peak_source": peak_src + ", sustained bf16",
+                "traffic": traffic,
+                "algorithmic_flops_per_launch": flops / launches_per_step, "launch_ms": per_launch_ms,
+                "launches_per_step": launches_per_step, "kernel_share_of_step": tc_kernel_ms / args.steps / ms_per_step,
+                "clusters": tc_geo[0], "max_coresident_clusters": tc_geo[1], "rows": tc_geo[2],
+                "vector_field_evals_per_launch": evals / launches_per_step,
+                "tensor_3xfp16": {"achieved": h3_achieved, "peak": fp16x3_peak, "frac": h3_achieved / fp16x3_peak,
+                                  "unit": "TFLOP/s",
+                                  "note": "fp32 parity needs 3 fp16 MMAs per product (hi*hi, lo*hi, hi*lo): the fp32-accurate "
+                                          "tensor ceiling is the fp16/bf16 peak / 3"},
+                "note": "launch duration measured live with CUDA events around the solver launch on its stream "
+                        "(odevio_debug_tc_timing) in extra un-profiled forwards after the timed region; algorithmic FLOPs "
+                        "from the kernel's own step statistics (SURVEY.md 8d)",
+            }
+        elif PRECISION == "tf32x3":
             # the cluster kernel integrates rows g = l * B + b < tc_rows of every interval; the rest (side launch) is FFMA
             D_, H_, n_ = w["v_f_len"] + w["i_f_len"], w["H"], w["n"]
             f_ode = 2 * (D_ * H_ + (n_ - 1) * H_ * H_ + H_ * D_)
@@ -369,7 +400,7 @@ def run_ours(args, rank, world, local_rank):
                              "frac": (achieved_tf / fma_peak) if fma_peak else None, "unit": "TFLOP/s"},
             }
         n_prepack = (w["n"] + 1) + w["L"] * 3 + 1
-        cpu_rate, cpu_sec, cpu_threads = cpu_oracle_rate(steps=5, warmup=1, B=CPU_SAMPLE_B) if world == 1 else (None, None, None)
+        cpu_rate, cpu_sec, cpu_threads = cpu_oracle_rate(steps=4, warmup=1, B=CPU_SAMPLE_B) if world == 1 else (None, None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -378,25 +409,121 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": f"independent sequences sharded over {world} GPU(s), no data-path collective",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
                        "mean_solver_steps_per_interval": stats[..., 0].float().mean().item(),
-                       "precision": PRECISION + (" (ODEFunc GEMMs on tcgen05 as 3xTF32, fp32-accurate; jump/head and the "
-                                                 "rows beyond the co-resident clusters on FFMA)" if PRECISION == "tf32x3" else
-                                                 " (CUDA-core FFMA)")},
+                       "precision": PRECISION + {"tf32x3": " (ODEFunc GEMMs on tcgen05 as 3xTF32, fp32-accurate; jump/head and the "
+                                                           "rows beyond the co-resident clusters on FFMA)",
+                                                 "fp16x3": " (every GEMM of the forward on tcgen05 as 3xFP16, fp32-accurate; one "
+                                                           "cluster kernel per forward)"}.get(PRECISION, " (CUDA-core FFMA)")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": fv_h.numel() * 4 + fi_h.numel() * 4 + ts_h.numel() * 4,
                     "d2h_bytes_per_step": pose_h.numel() * 4, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": ((n_prepack + 1) if PRECISION == "fp32" else
-                             (n_prepack + (w["n"] + 1) + S * (2 + n_side))) * args.steps,
+            # kernels of this library launched inside the timed region (fp16x3: the weights are packed once, by the first
+            # warm-up forward -- cfg.weights_prepacked -- so a timed step is exactly one launch)
+            "gpu_launches": (args.steps if PRECISION == "fp16x3" else (n_prepack + 1) * args.steps if PRECISION == "fp32" else
+                             (n_prepack + (w["n"] + 1) + S * (2 + n_side)) * args.steps),
             "roofline": roofline,
         }
         if cpu_rate is not None:
             line["cpu_baseline"] = {
                 "value": cpu_rate, "unit": UNIT, "cores": cpu_threads, "kind": "port",
-                "sample": f"{CPU_SAMPLE_B} of the {B} sequences, 5 forwards after 1 warm-up ({cpu_sec:.2f} s each), "
+                "sample": f"all {CPU_SAMPLE_B} sequences of the workload, 4 forwards after 1 warm-up ({cpu_sec:.2f} s each), "
                           f"oracle restatement of the reference CPU regressor path, eager PyTorch fp32, {cpu_model()}"}
+            line["config0"] = config0_row(torch, odevio_b200, dev)
+        if args.train:
+            line["train"] = train_info
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def config0_row(torch, odevio_b200, dev):
+    """BASELINE configs[0]: PoseODERNN forward, fixed-step rk4, B = 16 x seq_len 11, regular timestamps -- the reference's
+    own CPU-runnable case: the CPU oracle port and this library (same --precision) side by side."""
+    import copy
+    from odevio_b200 import synth
+    w = WORKLOAD
+    opt = make_opt()
+    opt.ode_solver = "rk4"
+    cpu_rate, cpu_sec, threads = cpu_oracle_rate(steps=10, warmup=2, B=16, opt=copy.copy(opt), irregular=False)
+    model = odevio_b200.PoseODERNN(opt)
+    init_like_deepvio(model, seed=0)
+    model = model.to(dev).eval()
+    fv, fi = synth.features(16, w["S"], w["v_f_len"], w["i_f_len"], seed=0)
+    ts = synth.timestamps(16, w["S"], irregular=False, seed=0)
+    fv, fi, ts = fv.to(dev), fi.to(dev), ts.to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            model(fv, fi, ts)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            model(fv, fi, ts)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 10
+    return {"workload": "PoseODERNN forward, fixed-step rk4, B=16 x seq_len 11 (S=10), regular ts, BASELINE configs[0]",
+            "gpu_ms_per_step": ms, "gpu_value": 16 * w["S"] / (ms * 1e-3),
+            "cpu_ms_per_step": cpu_sec * 1e3, "cpu_value": cpu_rate, "cpu_cores": threads, "unit": UNIT,
+            "note": "one 64-row tile = 4 of 148 SMs busy: a latency measurement, not a throughput one"}
+
+
+def measure_train(args, rank, world, dev):
+    """BASELINE configs[3] next to the headline: PoseODERNN training step (forward with checkpoints + fused backward + ONE
+    NCCL all-reduce of the flat Pose_net gradient bucket + clip + Adam as its epilogue: training.fused_train_step),
+    global batch `--train-batch` strong-scaled over the ranks.  Collective on every rank; returns the dict rank 0 prints."""
+    import torch
+    import torch.distributed as dist
+    import odevio_b200
+    from odevio_b200 import distributed as D, synth, training
+    w = WORKLOAD
+    GB, S = args.train_batch, w["S"]
+    info = {"workload": f"PoseODERNN training step (fwd + fused bwd + NCCL grad all-reduce + clip + Adam), global batch {GB} "
+                        f"strong-scaled over {world} GPU(s), dopri5 rtol={w['rtol']:g}, BASELINE configs[3]",
+            "global_batch": GB, "scaling": "strong", "n_gpus": world}
+    try:
+        a, b = D.shard_rows(GB, rank, world)
+        opt_ns = make_opt()
+        model = odevio_b200.PoseODERNN(opt_ns)
+        init_like_deepvio(model, seed=0)
+        model = model.to(dev).train()
+        opt = training.FusedPoseNetAdam(model, lr=1e-4)
+        fv, fi = synth.features(GB, S, w["v_f_len"], w["i_f_len"], seed=0)
+        ts = synth.timestamps(GB, S, irregular=True, seed=0)
+        gts = 0.01 * torch.randn(GB, S, 6, generator=torch.Generator().manual_seed(1))
+        fv, fi, ts, gts = (t[a:b].to(dev) for t in (fv, fi, ts, gts))
+        torch.cuda.reset_peak_memory_stats(dev)
+        training.fused_train_step(model, opt, fv, fi, ts, gts, world_size=world)       # warm-up (allocations)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        steps = args.train_steps
+        evs = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = training.fused_train_step(model, opt, fv, fi, ts, gts, world_size=world, events=evs)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        phases = {}
+        for name, x0, x1 in evs:
+            phases[name] = phases.get(name, 0.0) + x0.elapsed_time(x1) / steps
+        vals = torch.tensor([e0.elapsed_time(e1) / steps, phases["allreduce"], phases["forward"], phases["loss_backward"],
+                             phases["clip_adam"], torch.cuda.max_memory_allocated(dev) / 1e9], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        per, ar, fw, bw, ad, mem = vals.tolist()
+        info.update({"ms_per_step": per, "value": GB * S / (per * 1e-3), "unit": UNIT, "steps": steps, "warmup": 1,
+                     "allreduce_ms": ar, "forward_ms": fw, "loss_backward_ms": bw, "clip_adam_ms": ad,
+                     "allreduce_bytes": opt.flat.numel() * 4, "peak_mem_gb": mem, "loss": float(loss),
+                     "timing": "CUDA events, max over ranks"})
+        del model, opt, fv, fi, ts, gts
+        torch.cuda.empty_cache()
+    except Exception as exc:                       # the headline line must still be printed
+        info["error"] = f"{type(exc).__name__}: {exc}"[:300]
+    return info
 
 
 def _device_setup(local_rank, world):
@@ -525,9 +652,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--train-steps", type=int, default=2)
+    ap.add_argument("--no-train", dest="train", action="store_false",
+                    help="odernn_fwd: skip the extra `train` object (configs[3] training step incl. the NCCL gradient all-reduce)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=PRECISION, choices=["fp32", "tf32x3"],
-                    help="odernn_fwd: CUDA-core FFMA kernel, or the tcgen05 3xTF32 solver kernel (fp32-accurate)")
+    ap.add_argument("--precision", default=PRECISION, choices=["fp32", "tf32x3", "fp16x3"],
+                    help="odernn_fwd: CUDA-core FFMA kernel, or a tcgen05 solver kernel (3xTF32 / 3xFP16, both fp32-accurate)")
     args = ap.parse_args()
     globals()["PRECISION"] = args.precision
     rank = int(os.environ.get("RANK", "0"))

@@ -120,7 +120,11 @@ typedef struct odevio_odernn_cfg {
   int32_t evolve_only;        /* 1: PoseODERNN.evolve_state (src/models/PoseODERNN.py:70-75): only the ODE solves of the
                                  S intervals, no jump, no pose head; hT returns the evolved states ([L,B,D]), pose is
                                  not written (may be NULL) and fv / fi are not read */
-  int32_t reserved[3];
+  int32_t weights_prepacked;  /* ODEVIO_PRECISION_FP16X3: 1 = the workspace still holds the packed weight images written by an
+                                 earlier odevio_odernn_forward call with the same cfg (apart from this flag), the same
+                                 workspace address and unchanged weights: the per-forward packing launches are skipped
+                                 ("prepare the weights once").  0: pack on every call (stateless) */
+  int32_t reserved[2];
 } odevio_odernn_cfg;
 
 /* PyTorch-layout parameters ([out, in] row-major), exactly the reference's state_dict tensors */

@@ -31,7 +31,8 @@ class OdeRnnCfg(C.Structure):
         ("accept_strict", C.c_int32), ("floor_factor", C.c_int32), ("endpoint_dense", C.c_int32),
         ("max_steps", C.c_int32), ("precision", C.c_int32), ("save_checkpoints", C.c_int32),
         ("rows_per_tile", C.c_int32), ("exact_landing", C.c_int32), ("trace_steps", C.c_int32),
-        ("ckpt_loops", C.c_int32), ("evolve_only", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("ckpt_loops", C.c_int32), ("evolve_only", C.c_int32), ("weights_prepacked", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 

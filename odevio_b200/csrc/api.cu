@@ -530,6 +530,26 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
   float* ws = static_cast<float*>(workspace);
   const int D = c.D;
 
+  if (c.precision == ODEVIO_PRECISION_FP16X3 && (c.evolve_only || (odernn_h3_can_fuse_jump(c) && !w->fuse_w && !w->fuse_b))) {
+    // ONE launch per forward (odernn_h3.cu): every cluster of 4 CTAs walks its 64-row tile through all S intervals --
+    // solver loops, rnn jump and pose head on tcgen05 -- without returning to the host (PoseODERNN.py:108-122).  None of
+    // the FMA kernel's packed weights is needed.
+    DevTableau tab;
+    if (!make_tableau(c.solver, tab)) return ODEVIO_E_ENUM;
+    const bool adaptive = !(c.solver == ODEVIO_SOLVER_RK4 || c.solver == ODEVIO_SOLVER_RK4_38);
+    const size_t h_off = align_up(pl.total_bytes, 1024);
+    const size_t h_bytes = align_up(odernn_h3_workspace_bytes(c), 1024);
+    if (h_bytes == 0) return ODEVIO_E_SHAPE;
+    if (workspace_bytes < h_off + h_bytes) return ODEVIO_E_WORKSPACE;
+    g_last_precision = c.precision;
+    H3Evolve h3;
+    const int prc = h3.prepare(c, tab, adaptive, w, !c.evolve_only, !c.weights_prepacked, static_cast<unsigned char*>(workspace) + h_off,
+                               h_bytes, stream);
+    if (prc != 0) return prc;
+    if (status) ODEVIO_CUDA_TRY(cudaMemsetAsync(status, 0, static_cast<size_t>(c.B) * sizeof(int32_t), stream));
+    return h3.run(h0, hT, ts, c.S + 1, 0, c.S, fv, fi, Dv, c.S, pose, stats, status, stream);
+  }
+
   FwdParams p;
   memset(&p, 0, sizeof(p));
   p.B = c.B; p.S = c.S; p.D = D; p.H = c.H; p.NL = NL; p.L = c.L;
@@ -610,27 +630,23 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
   g_last_precision = c.precision;
   if (c.precision == ODEVIO_PRECISION_FP16X3) {
     // Per interval: the 3xFP16 cluster kernel (odernn_h3.cu) evolves ALL L*B rows of the state in place (32 clusters of 4
-    // take the 2048 rows of configs[1] in one round: no side launch), then the FMA kernel runs the jump + head.
+    // take the 2048 rows of configs[1] in one round: no side launch), then the FMA kernel runs the jump + head.  (GRU,
+    // "soft" fusion in the kernel, L > 2; the other configurations returned above with ONE launch per forward.)
     const size_t h_off = align_up(pl.total_bytes, 1024);
     const size_t h_bytes = align_up(odernn_h3_workspace_bytes(c), 1024);
     if (h_bytes == 0) return ODEVIO_E_SHAPE;
     if (workspace_bytes < h_off + h_bytes) return ODEVIO_E_WORKSPACE;
     H3Evolve h3;
-    const int prc = h3.prepare(c, p.tab, p.adaptive != 0, w->ode_w, w->ode_b, static_cast<unsigned char*>(workspace) + h_off,
+    const int prc = h3.prepare(c, p.tab, p.adaptive != 0, w, false, !c.weights_prepacked, static_cast<unsigned char*>(workspace) + h_off,
                                h_bytes, stream);
     if (prc != 0) return prc;
-    const size_t state_bytes = static_cast<size_t>(c.L) * c.B * D * sizeof(float);
-    if (h0) { if (h0 != hT) ODEVIO_CUDA_TRY(cudaMemcpyAsync(hT, h0, state_bytes, cudaMemcpyDeviceToDevice, stream)); }
-    else ODEVIO_CUDA_TRY(cudaMemsetAsync(hT, 0, state_bytes, stream));
     if (status) ODEVIO_CUDA_TRY(cudaMemsetAsync(status, 0, static_cast<size_t>(c.B) * sizeof(int32_t), stream));
     p.S = 1; p.skip_evolve = 1; p.S_io = c.S; p.stats = nullptr; p.status = nullptr; p.h0 = hT; p.hT = hT; p.ts = nullptr;
     for (int i = 0; i < c.S; ++i) {
-      const int erc = h3.evolve(hT, c.B, nullptr, ts, c.S + 1, i, stats, status, stream);
+      const int erc = h3.run(i == 0 ? h0 : hT, hT, ts, c.S + 1, i, 1, nullptr, nullptr, 0, c.S, nullptr, stats, status, stream);
       if (erc != 0) return erc;
-      if (!c.evolve_only) {
-        p.i_off = i;
-        ODEVIO_CUDA_TRY(launch_odernn_fwd(p, pl.RT, pl.grid, pl.smem_bytes, stream));
-      }
+      p.i_off = i;
+      ODEVIO_CUDA_TRY(launch_odernn_fwd(p, pl.RT, pl.grid, pl.smem_bytes, stream));
     }
     return 0;
   }

@@ -70,29 +70,51 @@ constexpr int H3_NWS = 4, H3_NXS = 4;     // ring depths (powers of two)
 
 struct H3Layer {
   int K, N;                 // input / output features
-  int Fc;                   // output features per CTA = N / 4, a multiple of 32 in [128, 256]
+  int Fc;                   // output features per CTA = N / nctas, a multiple of 32 in [128, 256]
   int T;                    // 128-feature MMA tiles per CTA: tile 0 = local features [0, 128), tile 1 = [Fc - 128, Fc)
   int KCH;                  // k per ring chunk = 64 / T
   int nch;                  // K / KCH
   int nseg;                 // main accumulators per tile (K split; + 1 accumulator for the cross terms)
   int act;
-  const unsigned char* Wimg; // [4 CTAs][nch][H3_WCHUNK]
+  int nctas;                // CTAs of the cluster that take part (4; 1 for the pose head's 128-feature Linear)
+  const unsigned char* Wimg; // [nctas][nch][H3_WCHUNK]
   const float* bias;
+  const float* bias2;       // second bias added in the epilogue (rnn: b_ih + b_hh) or nullptr
+};
+
+// one call of the layer routine: which columns (rows of the tile) it computes and where the result goes
+struct H3Call {
+  const unsigned char* xsrc;   // activation image of the input (chunks of L.KCH k)
+  int col0, ncol;              // tile rows [col0, col0 + ncol) = the N side of the MMAs (ncol = 32 or 64)
+  float* out;                  // fp32 [feature][NR] destination (stage vector / state / head activations) or nullptr
+  unsigned char* xdst;         // activation image that receives act(W x + b) as fp16 hi / lo, or nullptr
+  int xdst_kshift;             // log2 of that image's chunk size
+  int xdst_colshift;           // the image row that receives tile row n is n + xdst_colshift
 };
 
 struct H3Params {
-  int M, B, L, D, NL;
+  int B, L, D, NL;
+  int SPT;                   // sequences per tile: row r of a tile = (layer r / SPT, sequence tile * SPT + r % SPT), SPT = NR / L;
+                             // 0 (L does not divide NR): kernel row g = l * B + b, a tile = 64 consecutive g
   H3Layer lay[H3_MAXL];
+  H3Layer jump[2];           // rnn jump of layer l: [W_ih | W_hh] (K = 2 D), tanh
+  H3Layer head;              // regressor.0 (D -> 128, LeakyReLU(0.1)); regressor.2 runs on the CUDA cores
   unsigned char* xa; size_t xa_buf_bytes;       // per cluster: 2 activation-image buffers of xa_buf_bytes
-  float* state; size_t state_floats;            // per cluster: (kMaxStages + 2) x [D][NR] + [4][NR] norm partials
+  unsigned char* xj; size_t xj_buf_bytes;       // per cluster: L jump-input images [x ; h] of 2 D x NR
+  float* state; size_t state_floats;            // per cluster: (kMaxStages + 2) x [D][NR] + [4][NR] norm partials + [128][NR] head
   int ntiles;
   DevTableau tab;
   int adaptive, substeps;
   float atol, rtol, dt0, safety, fmin, fmax;
   int accept_strict, floor_factor, max_steps, exact_landing;
-  float* Y;                  // [L*B][D] row-major hidden state, evolved in place
-  const int* seq; int Bsub;  // rows (l, j), j < Bsub, of sequences b = seq[j] (nullptr: b = j); kernel row g = l * Bsub + j
-  const float* ts; int ts_ld, interval;
+  const float* h0;           // [L][B][D] initial hidden state or nullptr (zeros); may alias hT
+  float* hT;                 // [L][B][D] final hidden state
+  const float* ts; int ts_ld;
+  int interval0, nI;         // observation intervals [interval0, interval0 + nI) are integrated by this launch
+  int do_jump;               // after every interval: rnn jump on the fused features + pose head (PoseODERNN.py:112-122)
+  const float* fv; const float* fi; int Dv, S_io;   // features of interval i: fv[(b * S_io + i) * Dv + k], fi[.. * (D - Dv) + k - Dv]
+  const float* reg_w1; const float* reg_b1;         // regressor.2: [6][128], [6]
+  float* pose;               // [B][S_io][6]
   int* stats; int* status;
 };
 
@@ -169,24 +191,28 @@ __device__ __forceinline__ size_t h3_x_offset(int k, int n0, int kshift) {
 // MMAs of one ring chunk: T tiles x (KCH / 16) k-steps x {hi*hi -> main accumulator of segment `seg`, lo*hi + hi*lo -> the
 // tile's cross-term accumulator}; KCH = 64 / T.  Weight stage [tile][hi | lo][feature/8][k/8][feature%8][k%8] (K-major A),
 // activation stage [hi | lo][row/8][k/8][k%8][row%8] (MN-major B); both no-swizzle with LBO = 128 B, SBO = (KCH / 8) * 128 B.
+// The N side is the tile rows [col0, col0 + ncol): the B descriptors start col0 / 8 row groups into the stage, the
+// accumulators of a tile are ncol columns apart.
 template <int T, int NR>
 __device__ __forceinline__ void h3_issue_chunk(uint32_t tmem, uint32_t wbase, uint32_t xbase, uint32_t nseg, uint32_t seg,
-                                               bool acc_main, bool acc_cross) {
+                                               bool acc_main, bool acc_cross, uint32_t col0, uint32_t ncol) {
   constexpr uint32_t KCH = 64u / T, KS = KCH / 16u;
-  constexpr uint32_t hi_word = (((KCH >> 3) * 128u) >> 4) | (1u << 14);        // SBO | descriptor version 1 (bit 46)
+  constexpr uint32_t sbo = (KCH >> 3) * 128u;
+  constexpr uint32_t hi_word = (sbo >> 4) | (1u << 14);                        // SBO | descriptor version 1 (bit 46)
   constexpr uint32_t tile_bytes = 128u * KCH * 2u, ximg_bytes = KCH * NR * 2u;
-  // instruction descriptor: D fp32, A / B fp16, A K-major, B MN-major, N = NR, M = 128
-  constexpr uint32_t idesc = (1u << 4) | (1u << 16) | (static_cast<uint32_t>(NR >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
-  const uint32_t acc_per_tile = (nseg + 1u) * NR;
+  // instruction descriptor: D fp32, A / B fp16, A K-major, B MN-major, N = ncol, M = 128
+  const uint32_t idesc = (1u << 4) | (1u << 16) | ((ncol >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  const uint32_t acc_per_tile = (nseg + 1u) * ncol;
+  const uint32_t xcol = xbase + (col0 >> 3) * sbo;
 #pragma unroll
   for (uint32_t t = 0; t < static_cast<uint32_t>(T); ++t) {
     const uint32_t a_hi = wbase + t * 2u * tile_bytes, a_lo = a_hi + tile_bytes;
-    const uint32_t d_main = tmem + t * acc_per_tile + seg * NR, d_cross = tmem + t * acc_per_tile + nseg * NR;
+    const uint32_t d_main = tmem + t * acc_per_tile + seg * ncol, d_cross = tmem + t * acc_per_tile + nseg * ncol;
 #pragma unroll
     for (uint32_t ks = 0; ks < KS; ++ks) {
       const uint32_t o = ks * 256u;
       const uint64_t ah = h3_desc(a_hi + o, hi_word), al = h3_desc(a_lo + o, hi_word);
-      const uint64_t xh = h3_desc(xbase + o, hi_word), xl = h3_desc(xbase + ximg_bytes + o, hi_word);
+      const uint64_t xh = h3_desc(xcol + o, hi_word), xl = h3_desc(xcol + ximg_bytes + o, hi_word);
       h3_mma(d_main, ah, xh, idesc, (acc_main || ks) ? 1u : 0u);
       h3_mma(d_cross, al, xh, idesc, (acc_cross || ks) ? 1u : 0u);
       h3_mma(d_cross, ah, xl, idesc, 1u);
@@ -195,35 +221,39 @@ __device__ __forceinline__ void h3_issue_chunk(uint32_t tmem, uint32_t wbase, ui
 }
 
 // ---------------------------------------------------------------------------------------------- one Linear
-// All threads of all 4 CTAs call this with identical arguments.  Reads the cluster's activation image `xsrc` (complete
-// and visible: the caller's previous step ended with a cluster barrier), writes act(W x + b) either into the activation
-// image `xdst` of the next Linear (chunks of 1 << xdst_kshift) or, `out` != nullptr, as fp32 [feature][NR] rows of a
-// stage vector.  Ends with a cluster barrier.  `next` (may be nullptr): the Linear that certainly follows -- its first
-// weight chunks are issued before the barrier.
+// All threads of all 4 CTAs call this with identical arguments.  Reads the cluster's activation image `cl.xsrc` (complete
+// and visible: the caller's previous step ended with a cluster barrier) and computes act(W x + b) for the tile rows
+// [cl.col0, cl.col0 + cl.ncol); the result goes to the activation image `cl.xdst` of a following Linear (fp16 hi / lo) and /
+// or to fp32 [feature][NR] rows at `cl.out`.  Ends with a cluster barrier.  CTAs with rank >= L.nctas only take part in
+// the barrier.  `next` (may be nullptr): the Linear that certainly follows -- its first weight chunks are issued before
+// the barrier.
 template <int NR>
-__device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Layer* next, const unsigned char* xsrc,
-                                         unsigned char* xdst, int xdst_kshift, float* out, int stamp = 0) {
+__device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Layer* next, const H3Call& cl, int stamp = 0) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sb = 16 + 10 * stamp;          // timeline slots of this layer
   (void)sb;
   constexpr uint32_t XSTAGE = 4u * 64u * NR;                 // bytes of an activation stage (KCH = 64: hi | lo)
   const int nch = L.nch;
+  const bool active = static_cast<int>(c.crank) < L.nctas;
+  const bool next_active = next != nullptr && static_cast<int>(c.crank) < next->nctas;
 
   if (warp == H3_WARP_WPROD) {
     // ===== weight producer: one 32 KB bulk copy per chunk; whole warp, one elected lane issues
-    const unsigned char* src = L.Wimg + static_cast<size_t>(c.crank) * nch * H3_WCHUNK;
     uint32_t g = c.wcount + c.w_ahead;
-    for (int ch = static_cast<int>(c.w_ahead); ch < nch; ++ch, ++g) {
-      const uint32_t s = g & (H3_NWS - 1), ph = (g / H3_NWS) & 1u;
-      mbar_wait(&c.w_empty[s], ph ^ 1u);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&c.w_full[s], H3_WCHUNK);
-        tma_load_1d(c.wring + s * H3_WCHUNK, src + static_cast<size_t>(ch) * H3_WCHUNK, H3_WCHUNK, &c.w_full[s]);
+    if (active) {
+      const unsigned char* src = L.Wimg + static_cast<size_t>(c.crank) * nch * H3_WCHUNK;
+      for (int ch = static_cast<int>(c.w_ahead); ch < nch; ++ch, ++g) {
+        const uint32_t s = g & (H3_NWS - 1), ph = (g / H3_NWS) & 1u;
+        mbar_wait(&c.w_empty[s], ph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&c.w_full[s], H3_WCHUNK);
+          tma_load_1d(c.wring + s * H3_WCHUNK, src + static_cast<size_t>(ch) * H3_WCHUNK, H3_WCHUNK, &c.w_full[s]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
     uint32_t pre = 0;
-    if (next) {
+    if (next_active) {
       const unsigned char* nsrc = next->Wimg + static_cast<size_t>(c.crank) * next->nch * H3_WCHUNK;
       pre = next->nch < H3_NWS ? next->nch : H3_NWS;
       for (uint32_t ch = 0; ch < pre; ++ch, ++g) {
@@ -239,80 +269,87 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
     c.w_ahead = pre;
   } else if (warp == H3_WARP_XPROD) {
     // ===== activation producer: one bulk copy (hi | lo images of KCH k x NR rows) per chunk
-    const uint32_t xcb = 4u * static_cast<uint32_t>(L.KCH) * NR;
-    uint32_t g = c.xcount;
-    for (int ch = 0; ch < nch; ++ch, ++g) {
-      const uint32_t s = g & (H3_NXS - 1), ph = (g / H3_NXS) & 1u;
-      mbar_wait(&c.x_empty[s], ph ^ 1u);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&c.x_full[s], xcb);
-        tma_load_1d(c.xring + s * XSTAGE, xsrc + static_cast<size_t>(ch) * xcb, xcb, &c.x_full[s]);
+    if (active) {
+      const uint32_t xcb = 4u * static_cast<uint32_t>(L.KCH) * NR;
+      uint32_t g = c.xcount;
+      for (int ch = 0; ch < nch; ++ch, ++g) {
+        const uint32_t s = g & (H3_NXS - 1), ph = (g / H3_NXS) & 1u;
+        mbar_wait(&c.x_empty[s], ph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&c.x_full[s], xcb);
+          tma_load_1d(c.xring + s * XSTAGE, cl.xsrc + static_cast<size_t>(ch) * xcb, xcb, &c.x_full[s]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == H3_WARP_MMA) {
-    // ===== MMA issuer: D^T[128 features x NR rows] += W[128 x 16] X^T[16 x NR], three products per k-step.  Whole warp
-    // with warp-uniform operands, one elected lane issues; the chunk body is fully unrolled (h3_issue_chunk) and there
-    // is no division anywhere in the loop.
-    const uint32_t nseg = static_cast<uint32_t>(L.nseg);
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, c.tmem, 0);
-    // chunks per K segment (ceil): segment s takes chunks [s * cps, (s + 1) * cps)
-    uint32_t cps = 1;
-    while (cps * nseg < static_cast<uint32_t>(nch)) ++cps;
-    uint32_t seg = 0, in_seg = 0, gw = c.wcount, gx = c.xcount;
-    for (int ch = 0; ch < nch; ++ch, ++gw, ++gx) {
-      const uint32_t ws = gw & (H3_NWS - 1), wph = (gw / H3_NWS) & 1u;
-      const uint32_t xs = gx & (H3_NXS - 1), xph = (gx / H3_NXS) & 1u;
-      const long long tw0 = H3_CLOCK();
-      mbar_wait(&c.w_full[ws], wph);
-      const long long tw1 = H3_CLOCK();
-      mbar_wait(&c.x_full[xs], xph);
-      const long long tw2 = H3_CLOCK();
-      if (lane == 0) {
-        if (ch == 0) { H3_STAMP(sb + 0); H3_SET(sb + 6, 0); H3_SET(sb + 7, 0); }
-        else { H3_ADD(sb + 6, tw1 - tw0); H3_ADD(sb + 7, tw2 - tw1); }     // starvation after the first chunk: W ring / X ring
-        if (ch == nch - 1) H3_STAMP(sb + 5);
+    // ===== MMA issuer: D^T[128 features x ncol rows] += W[128 x 16] X^T[16 x ncol], three products per k-step.  Whole
+    // warp with warp-uniform operands, one elected lane issues; the chunk body is fully unrolled (h3_issue_chunk) and
+    // there is no division anywhere in the loop.
+    if (active) {
+      const uint32_t nseg = static_cast<uint32_t>(L.nseg);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, c.tmem, 0);
+      const uint32_t col0 = static_cast<uint32_t>(cl.col0), ncol = static_cast<uint32_t>(cl.ncol);
+      // chunks per K segment (ceil): segment s takes chunks [s * cps, (s + 1) * cps)
+      uint32_t cps = 1;
+      while (cps * nseg < static_cast<uint32_t>(nch)) ++cps;
+      uint32_t seg = 0, in_seg = 0, gw = c.wcount, gx = c.xcount;
+      for (int ch = 0; ch < nch; ++ch, ++gw, ++gx) {
+        const uint32_t ws = gw & (H3_NWS - 1), wph = (gw / H3_NWS) & 1u;
+        const uint32_t xs = gx & (H3_NXS - 1), xph = (gx / H3_NXS) & 1u;
+        const long long tw0 = H3_CLOCK();
+        mbar_wait(&c.w_full[ws], wph);
+        const long long tw1 = H3_CLOCK();
+        mbar_wait(&c.x_full[xs], xph);
+        const long long tw2 = H3_CLOCK();
+        if (lane == 0) {
+          if (ch == 0) { H3_STAMP(sb + 0); H3_SET(sb + 6, 0); H3_SET(sb + 7, 0); }
+          else { H3_ADD(sb + 6, tw1 - tw0); H3_ADD(sb + 7, tw2 - tw1); }     // starvation after the first chunk: W ring / X ring
+          if (ch == nch - 1) H3_STAMP(sb + 5);
+        }
+        (void)tw0; (void)tw1; (void)tw2;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t wbase = smem_u32(c.wring + ws * H3_WCHUNK), xbase = smem_u32(c.xring + xs * XSTAGE);
+        if (elect_one()) {
+          if (L.T == 1) h3_issue_chunk<1, NR>(tmem_u, wbase, xbase, nseg, seg, in_seg != 0, ch != 0, col0, ncol);
+          else h3_issue_chunk<2, NR>(tmem_u, wbase, xbase, nseg, seg, in_seg != 0, ch != 0, col0, ncol);
+          h3_commit(&c.w_empty[ws]);
+          h3_commit(&c.x_empty[xs]);
+        }
+        __syncwarp();
+        if (++in_seg == cps) { in_seg = 0; ++seg; }
       }
-      (void)tw0; (void)tw1; (void)tw2;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t wbase = smem_u32(c.wring + ws * H3_WCHUNK), xbase = smem_u32(c.xring + xs * XSTAGE);
-      if (elect_one()) {
-        if (L.T == 1) h3_issue_chunk<1, NR>(tmem_u, wbase, xbase, nseg, seg, in_seg != 0, ch != 0);
-        else h3_issue_chunk<2, NR>(tmem_u, wbase, xbase, nseg, seg, in_seg != 0, ch != 0);
-        h3_commit(&c.w_empty[ws]);
-        h3_commit(&c.x_empty[xs]);
-      }
+      if (elect_one()) h3_commit(c.accum_bar);
       __syncwarp();
-      if (++in_seg == cps) { in_seg = 0; ++seg; }
+      if (lane == 0) H3_STAMP(sb + 1);
     }
-    if (elect_one()) h3_commit(c.accum_bar);
-    __syncwarp();
-    if (lane == 0) H3_STAMP(sb + 1);
-  } else if (warp < H3_EPI_WARPS) {
-    // ===== epilogue: thread = output feature (TMEM lane); warps w and w + 4 share lane quarter w & 3 and split the rows
+  } else if (warp < H3_EPI_WARPS && active) {
+    // ===== epilogue: thread = output feature (TMEM lane); warps w and w + 4 share lane quarter w & 3 and alternate over
+    // the 32-column blocks of the tile rows
     mbar_wait(c.accum_bar, c.accum_phase);
     if (tid == 0) H3_STAMP(sb + 2);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3, h = warp >> 2;
-    const int nseg = L.nseg, act = L.act;
+    const int nseg = L.nseg, act = L.act, ncol = cl.ncol;
     for (int t = 0; t < L.T; ++t) {
       const int m = 32 * q + lane;                                  // row of the MMA tile = TMEM lane
       // tile 1 overlaps tile 0 when Fc < 256: only its upper Fc - 128 features are new (warp-uniform: Fc % 32 == 0)
       if (t == 1 && 32 * q < 256 - L.Fc) continue;
       const int fl = (t == 0 ? 0 : L.Fc - 128) + m;                 // feature inside the CTA's slice
       const int f = static_cast<int>(c.crank) * L.Fc + fl;          // output feature of the Linear
-      const float bias = L.bias[f];
-      const uint32_t tbase = c.tmem + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(t * (nseg + 1) * NR);
+      const float bias = L.bias2 ? add_(L.bias[f], L.bias2[f]) : L.bias[f];
+      const uint32_t tbase = c.tmem + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(t * (nseg + 1) * ncol);
 #pragma unroll 1
-      for (int cb = 0; cb < NR / 64; ++cb) {
-        const int col0 = h * (NR / 2) + 32 * cb;
+      for (int cb = h; cb < (ncol >> 5); cb += 2) {
+        const int colb = 32 * cb;                                   // column inside the accumulators
+        const int col = cl.col0 + colb;                             // tile row
         uint32_t u[32];
         float acc[32];
-        h3_tmem_ld32(tbase + static_cast<uint32_t>(nseg * NR + col0), u);              // cross terms first (smallest)
+        h3_tmem_ld32(tbase + static_cast<uint32_t>(nseg * ncol + colb), u);             // cross terms first (smallest)
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(u[i]) * (1.0f / 2048.0f);
         for (int sgm = nseg - 1; sgm >= 0; --sgm) {
-          h3_tmem_ld32(tbase + static_cast<uint32_t>(sgm * NR + col0), u);
+          h3_tmem_ld32(tbase + static_cast<uint32_t>(sgm * ncol + colb), u);
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(u[i]);
         }
@@ -321,18 +358,19 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
           const float4 a4 = apply_act4(make_float4(acc[4 * i] + bias, acc[4 * i + 1] + bias, acc[4 * i + 2] + bias, acc[4 * i + 3] + bias), act);
           acc[4 * i] = a4.x; acc[4 * i + 1] = a4.y; acc[4 * i + 2] = a4.z; acc[4 * i + 3] = a4.w;
         }
-        if (out) {
-          float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(f) * NR + col0);
+        if (cl.out) {
+          float4* dst = reinterpret_cast<float4*>(cl.out + static_cast<size_t>(f) * NR + col);
 #pragma unroll
           for (int i = 0; i < 8; ++i) __stcg(dst + i, make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]));
-        } else {
-          const size_t lo_off = static_cast<size_t>(2u * NR) << xdst_kshift;          // KCH * NR * 2 bytes
+        }
+        if (cl.xdst) {
+          const size_t lo_off = static_cast<size_t>(2u * NR) << cl.xdst_kshift;       // KCH * NR * 2 bytes
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             __half hi[8], lo[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) h3_split(acc[8 * j + i], hi[i], lo[i]);
-            unsigned char* dst = xdst + h3_x_offset<NR>(f, col0 + 8 * j, xdst_kshift);
+            unsigned char* dst = cl.xdst + h3_x_offset<NR>(f, col + cl.xdst_colshift + 8 * j, cl.xdst_kshift);
             __stcg(reinterpret_cast<uint4*>(dst),
                    make_uint4(h3_pack2(hi[0], hi[1]), h3_pack2(hi[2], hi[3]), h3_pack2(hi[4], hi[5]), h3_pack2(hi[6], hi[7])));
             __stcg(reinterpret_cast<uint4*>(dst + lo_off),
@@ -345,9 +383,11 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     if (tid == 0) H3_STAMP(sb + 3);
   }
-  c.accum_phase ^= 1u;
-  c.wcount += static_cast<uint32_t>(nch);
-  c.xcount += static_cast<uint32_t>(nch);
+  if (active) {
+    c.accum_phase ^= 1u;
+    c.wcount += static_cast<uint32_t>(nch);
+    c.xcount += static_cast<uint32_t>(nch);
+  }
   __syncwarp();
   h3_cluster_sync();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -517,8 +557,53 @@ __device__ __forceinline__ void h3_commit_rows(const H3Slice<NR>& sl, int ns, in
 
 __device__ __forceinline__ int h3_log2(int v) { return 31 - __clz(v); }
 
+// Input images of the rnn jump (PoseODERNN.py:112-117): layer l's image holds [x ; h] for its tile rows, x = the fused
+// features of the interval (layer 0: cat(fv, fi), FusionModule "cat") or the new hidden state of layer l - 1 (written by
+// that jump's epilogue), h = the evolved state.  This pass writes, for the CTA's own feature slice, the h part of every
+// layer (k = D + f) and the feature part of layer 0 (k = f).
 template <int NR>
-__global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_evolve_kernel(const __grid_constant__ H3Params p) {
+__device__ __forceinline__ void h3_jump_input(const H3Params& p, const H3Rows<NR>& rs, const float* Yc, unsigned char* xj,
+                                              int own_f0, int own_nf, int interval, int tid) {
+  const int D = p.D, kshift = h3_log2(p.jump[0].KCH);
+  const size_t lo_off = static_cast<size_t>(2u * NR) << kshift;
+  // h part: task = (feature, group of 8 rows); 8 consecutive lanes cover the NR = 64 rows of one feature (256 B)
+  for (int task = tid; task < own_nf * (NR / 8); task += H3_EPI_THREADS) {
+    const int f = own_f0 + task / (NR / 8), n0 = 8 * (task % (NR / 8));
+    const float4 a = h3_ld4(Yc + static_cast<size_t>(f) * NR + n0), b = h3_ld4(Yc + static_cast<size_t>(f) * NR + n0 + 4);
+    __half hi[8], lo[8];
+    h3_split(a.x, hi[0], lo[0]); h3_split(a.y, hi[1], lo[1]); h3_split(a.z, hi[2], lo[2]); h3_split(a.w, hi[3], lo[3]);
+    h3_split(b.x, hi[4], lo[4]); h3_split(b.y, hi[5], lo[5]); h3_split(b.z, hi[6], lo[6]); h3_split(b.w, hi[7], lo[7]);
+    const int lyr = p.SPT ? n0 / p.SPT : 0;
+    unsigned char* dst = xj + static_cast<size_t>(lyr) * p.xj_buf_bytes + h3_x_offset<NR>(D + f, n0, kshift);
+    __stcg(reinterpret_cast<uint4*>(dst), make_uint4(h3_pack2(hi[0], hi[1]), h3_pack2(hi[2], hi[3]), h3_pack2(hi[4], hi[5]), h3_pack2(hi[6], hi[7])));
+    __stcg(reinterpret_cast<uint4*>(dst + lo_off),
+           make_uint4(h3_pack2(lo[0], lo[1]), h3_pack2(lo[2], lo[3]), h3_pack2(lo[4], lo[5]), h3_pack2(lo[6], lo[7])));
+  }
+  // feature part of layer 0 (tile rows [0, SPT)): task = (group of 8 sequences, feature); consecutive lanes read
+  // consecutive features of one sequence (coalesced) and write consecutive 16-byte pieces of the image
+  const int ngrp = p.SPT / 8;
+  for (int task = tid; task < own_nf * ngrp; task += H3_EPI_THREADS) {
+    const int grp = task / own_nf, f = own_f0 + task - grp * own_nf;
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int n = 8 * grp + e;
+      float v = 0.f;
+      if (rs.grow[n] >= 0) {
+        const size_t row = static_cast<size_t>(rs.bidx[n]) * p.S_io + interval;
+        v = f < p.Dv ? __ldg(p.fv + row * p.Dv + f) : __ldg(p.fi + row * (D - p.Dv) + (f - p.Dv));
+      }
+      h3_split(v, hi[e], lo[e]);
+    }
+    unsigned char* dst = xj + h3_x_offset<NR>(f, 8 * grp, kshift);
+    __stcg(reinterpret_cast<uint4*>(dst), make_uint4(h3_pack2(hi[0], hi[1]), h3_pack2(hi[2], hi[3]), h3_pack2(hi[4], hi[5]), h3_pack2(hi[6], hi[7])));
+    __stcg(reinterpret_cast<uint4*>(dst + lo_off),
+           make_uint4(h3_pack2(lo[0], lo[1]), h3_pack2(lo[2], lo[3]), h3_pack2(lo[4], lo[5]), h3_pack2(lo[6], lo[7])));
+  }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_constant__ H3Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t w_full[H3_NWS];
   __shared__ __align__(8) uint64_t w_empty[H3_NWS];
@@ -559,168 +644,232 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_evolve_kernel(const _
   float* const st_base = p.state + static_cast<size_t>(cluster_id) * p.state_floats;
   float* const Yc = st_base + kMaxStages * arr;
   float* const normpart = st_base + (kMaxStages + 2) * arr;            // [4][NR]
+  float* const headbuf = normpart + H3_NC * NR;                        // [128][NR] activations of regressor.0
   unsigned char* const xa0 = p.xa + static_cast<size_t>(cluster_id) * 2 * p.xa_buf_bytes;
   unsigned char* const xa1 = xa0 + p.xa_buf_bytes;
+  unsigned char* const xj = p.xj + static_cast<size_t>(cluster_id) * p.L * p.xj_buf_bytes;
 
   const bool epi = warp < H3_EPI_WARPS;
   H3Slice<NR> sl;
   sl.base = st_base; sl.arr = arr; sl.own_f0 = own_f0; sl.nit = own_nf / 32; sl.warp = warp; sl.fs = lane >> 3; sl.g = lane & 7;
   const int ns = tb.n_stages;
   const int kshift0 = h3_log2(p.lay[0].KCH);
+  const long long Mrows = static_cast<long long>(p.L) * p.B;
 
   for (int tile = cluster_id; tile < p.ntiles; tile += nclusters) {
-    const int row0 = tile * NR;
-    // ---- per-row solver state (PoseODERNN.py:70-75; odernn_fwd.cu:interval_begin)
-    int run = 0;
+    // ---- which (layer, sequence) each tile row is
     if (tid < NR) {
-      const int r = tid, g = row0 + r;
-      const bool valid = g < p.M;
-      const int lyr = valid ? g / p.Bsub : 0, jseq = valid ? g - lyr * p.Bsub : 0;
-      const int b = valid ? (p.seq ? p.seq[jseq] : jseq) : 0;
+      const int r = tid;
+      bool valid; int lyr, b;
+      if (p.SPT) { lyr = r / p.SPT; b = tile * p.SPT + (r - lyr * p.SPT); valid = b < p.B; }
+      else { const long long g = static_cast<long long>(tile) * NR + r; valid = g < Mrows; lyr = valid ? static_cast<int>(g / p.B) : 0; b = valid ? static_cast<int>(g - static_cast<long long>(lyr) * p.B) : 0; }
       rs.grow[r] = valid ? static_cast<long long>(lyr) * p.B + b : -1;
-      rs.bidx[r] = b; rs.lyr[r] = lyr;
-      float t0 = 0.f, t1 = 0.f;
-      if (valid) {
-        t0 = p.ts[static_cast<size_t>(b) * p.ts_ld + p.interval];
-        t1 = p.ts[static_cast<size_t>(b) * p.ts_ld + p.interval + 1];
-      }
-      rs.t[r] = t0; rs.tend[r] = t1;
-      rs.tmin[r] = fminf(t0, t1); rs.tmax[r] = fmaxf(t0, t1);
-      rs.nsteps[r] = 0; rs.nacc[r] = 0; rs.upd[r] = 0; rs.status[r] = 0;
-      if (p.adaptive) {
-        rs.dt[r] = fminf(fmaxf(p.dt0, sub_(rs.tmin[r], t0)), sub_(rs.tmax[r], t0));
-        run = (valid && t0 < t1) ? 1 : 0;
-      } else {
-        rs.dt[r] = __fdiv_rn(sub_(t1, t0), static_cast<float>(p.substeps));
-        run = valid ? 1 : 0;
-      }
-      rs.run[r] = run;
+      rs.bidx[r] = valid ? b : 0; rs.lyr[r] = lyr;
     }
-    int any_running = __syncthreads_or(run);
-    // ---- the tile's state rows (row-major [M][D]) -> feature-major scratch, own feature slice
+    __syncthreads();
+    // ---- the tile's state rows (row-major [L][B][D]; zeros without h0) -> feature-major scratch, own feature slice
     if (epi) {
       const int nf4 = own_nf / 4;
       for (int item = tid; item < NR * nf4; item += H3_EPI_THREADS) {
         const int n = item / nf4, f4 = item - n * nf4;
         const long long gr = rs.grow[n];
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gr >= 0) v = *reinterpret_cast<const float4*>(p.Y + static_cast<size_t>(gr) * D + own_f0 + 4 * f4);
+        if (gr >= 0 && p.h0) v = *reinterpret_cast<const float4*>(p.h0 + static_cast<size_t>(gr) * D + own_f0 + 4 * f4);
         float* dst = Yc + static_cast<size_t>(own_f0 + 4 * f4) * NR + n;
         __stcg(dst, v.x); __stcg(dst + NR, v.y); __stcg(dst + 2 * NR, v.z); __stcg(dst + 3 * NR, v.w);
       }
       named_bar_sync(1, H3_EPI_THREADS);      // the elementwise passes walk the slice with another thread mapping
     }
-    int loops = 0;
-    bool have_k0 = false;
 
-    while (any_running) {
-      ++loops;
-      if (tid == 0) H3_STAMP(0);
-      for (int st = (tb.fsal && have_k0) ? 1 : 0; st < ns; ++st) {
-        // ---- stage argument -> activation image of the first Linear (own feature slice, all rows)
-        if (tid == 0) H3_STAMP(1);
+    for (int ii = 0; ii < p.nI; ++ii) {
+      const int interval = p.interval0 + ii;
+      // ---- per-row solver state (PoseODERNN.py:70-75; odernn_fwd.cu:interval_begin)
+      int run = 0;
+      if (tid < NR) {
+        const int r = tid;
+        const bool valid = rs.grow[r] >= 0;
+        float t0 = 0.f, t1 = 0.f;
+        if (valid) {
+          t0 = p.ts[static_cast<size_t>(rs.bidx[r]) * p.ts_ld + interval];
+          t1 = p.ts[static_cast<size_t>(rs.bidx[r]) * p.ts_ld + interval + 1];
+        }
+        rs.t[r] = t0; rs.tend[r] = t1;
+        rs.tmin[r] = fminf(t0, t1); rs.tmax[r] = fmaxf(t0, t1);
+        rs.nsteps[r] = 0; rs.nacc[r] = 0; rs.upd[r] = 0; rs.status[r] = 0;
+        if (p.adaptive) {
+          rs.dt[r] = fminf(fmaxf(p.dt0, sub_(rs.tmin[r], t0)), sub_(rs.tmax[r], t0));
+          run = (valid && t0 < t1) ? 1 : 0;
+        } else {
+          rs.dt[r] = __fdiv_rn(sub_(t1, t0), static_cast<float>(p.substeps));
+          run = valid ? 1 : 0;
+        }
+        rs.run[r] = run;
+      }
+      int any_running = __syncthreads_or(run);
+      int loops = 0;
+      bool have_k0 = false;
+
+      while (any_running) {
+        ++loops;
+        if (tid == 0) H3_STAMP(0);
+        for (int st = (tb.fsal && have_k0) ? 1 : 0; st < ns; ++st) {
+          // ---- stage argument -> activation image of the first Linear (own feature slice, all rows)
+          if (tid == 0) H3_STAMP(1);
+          if (epi) {
+            if (st == 0) h3_stage_input<0, NR>(sl, tb.a[0], rs.dt, xa0, kshift0);
+            else H3_DISPATCH_STAGES(st, (h3_stage_input<(NSV < kMaxStages ? NSV : kMaxStages - 1), NR>(sl, tb.a[st], rs.dt, xa0, kshift0)))
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
+          if (tid == 0) H3_STAMP(2);
+          __syncwarp();
+          h3_cluster_sync();
+          if (tid == 0) H3_STAMP(3);
+          // ---- ODEFunc on the tensor cores; last Linear (+ Tanh) -> K[st]
+          for (int l = 0; l < NL; ++l) {
+            const bool last = l == NL - 1;
+            const H3Layer* next = !last ? &p.lay[l + 1] : (st + 1 < ns ? &p.lay[0] : nullptr);
+            H3Call cl;
+            cl.xsrc = (l & 1) ? xa1 : xa0; cl.col0 = 0; cl.ncol = NR;
+            cl.out = last ? st_base + static_cast<size_t>(st) * arr : nullptr;
+            cl.xdst = last ? nullptr : ((l & 1) ? xa0 : xa1);
+            cl.xdst_kshift = last ? 0 : h3_log2(p.lay[l + 1].KCH); cl.xdst_colshift = 0;
+            h3_layer<NR>(c, p.lay[l], next, cl, l);
+          }
+          if (tid == 0) H3_STAMP(4);
+        }
+        have_k0 = true;
+
+        if (p.adaptive) {
+          // ---- y1, embedded error, this CTA's share of the per-row error norm
+          if (epi) {
+            float sum[NR / 32][4];
+            H3_DISPATCH_STAGES(ns, (h3_error_pass<NSV, NR>(sl, tb, rs.dt, p.atol, p.rtol, sum)))
+#pragma unroll
+            for (int m = 0; m < NR / 32; ++m)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float v = sum[m][i];
+                v = add_(v, __shfl_xor_sync(0xffffffffu, v, 8));
+                v = add_(v, __shfl_xor_sync(0xffffffffu, v, 16));
+                if (sl.fs == 0) rs.psum[warp][32 * m + 4 * sl.g + i] = v;
+              }
+            if (tid == 0) H3_STAMP(5);
+            named_bar_sync(1, H3_EPI_THREADS);
+            if (tid < NR) {
+              float tot = rs.psum[0][tid];
+#pragma unroll
+              for (int w = 1; w < H3_EPI_WARPS; ++w) tot = add_(tot, rs.psum[w][tid]);
+              __stcg(normpart + static_cast<size_t>(crank) * NR + tid, tot);
+            }
+          }
+          __syncwarp();
+          if (tid == 0) H3_STAMP(6);
+          h3_cluster_sync();
+          if (tid == 0) H3_STAMP(7);
+          // ---- per-row controller, identical in every CTA (odernn_fwd.cu:controller; torchode IntegralController)
+          run = 0;
+          if (tid < NR) {
+            const int r = tid;
+            run = rs.run[r];
+            const float dt = rs.dt[r];
+            float t = rs.t[r];
+            const float tend = rs.tend[r];
+            bool accept = true, finite = true;
+            float dt_next = dt;
+            if (tb.has_err) {
+              float total = 0.f;
+#pragma unroll
+              for (int k = 0; k < H3_NC; ++k) total = add_(total, __ldcg(normpart + k * NR + r));
+              const float ratio = sqrtf(__fdiv_rn(total, static_cast<float>(D)));
+              finite = isfinite(ratio);
+              accept = p.accept_strict ? (ratio < 1.0f) : (ratio <= 1.0f);
+              float factor = mul_(p.safety, powf(ratio, tb.exponent));
+              factor = fminf(fmaxf(factor, p.fmin), p.fmax);
+              if (p.floor_factor && accept) factor = fmaxf(factor, 1.0f);
+              dt_next = mul_(dt, factor);
+            }
+            const int upd = (accept && run) ? 1 : 0;
+            rs.nsteps[r] += run;
+            rs.nacc[r] += upd;
+            const bool lands = p.exact_landing && dt >= sub_(tend, t);
+            t = upd ? (lands ? tend : add_(t, dt)) : t;
+            rs.upd[r] = upd;
+            if (run && !finite) rs.status[r] = max(rs.status[r], 2);
+            run = (run && t < tend && finite) ? 1 : 0;
+            if (run && loops >= p.max_steps) { rs.status[r] = max(rs.status[r], 1); run = 0; }
+            float dtn = run ? dt_next : dt;
+            dtn = fminf(fmaxf(dtn, sub_(rs.tmin[r], t)), sub_(rs.tmax[r], t));
+            rs.t[r] = t;
+            rs.dt[r] = dtn;
+            rs.run[r] = run;
+          }
+          any_running = __syncthreads_or(run);
+          if (tid == 0) H3_STAMP(8);
+          // ---- commit: accepted rows take y1; FSAL carry (end point rule "y1": exact landing makes y1 the value at t_end)
+          if (epi) h3_commit_rows<NR>(sl, ns, tb.fsal, rs.upd);
+          if (tid == 0) H3_STAMP(9);
+        } else {
+          if (epi) {
+            H3_DISPATCH_STAGES(ns, (h3_fixed_commit<NSV, NR>(sl, tb, rs.dt)))
+            if (tid < NR && rs.grow[tid] >= 0) { rs.nsteps[tid] += 1; rs.nacc[tid] += 1; }
+          }
+          any_running = loops < p.substeps;
+        }
+        // the elementwise passes of the next iteration read what this one wrote with a different thread mapping only
+        // within the epilogue warps of this CTA
+        if (epi) named_bar_sync(1, H3_EPI_THREADS);
+      }
+
+      // ---- stats / status of the interval
+      __syncthreads();
+      if (crank == 0 && tid < NR && rs.grow[tid] >= 0) {
+        if (p.stats) {
+          int* sp = p.stats + ((static_cast<size_t>(interval) * p.L + rs.lyr[tid]) * p.B + rs.bidx[tid]) * 2;
+          sp[0] = rs.nsteps[tid]; sp[1] = rs.nacc[tid];
+        }
+        if (p.status && rs.status[tid]) atomicMax(p.status + rs.bidx[tid], rs.status[tid]);
+      }
+
+      if (p.do_jump) {
+        // ---- rnn jump at the observation (PoseODERNN.py:112-117) and pose head (:119-122), all on this cluster
         if (epi) {
-          if (st == 0) h3_stage_input<0, NR>(sl, tb.a[0], rs.dt, xa0, kshift0);
-          else H3_DISPATCH_STAGES(st, (h3_stage_input<(NSV < kMaxStages ? NSV : kMaxStages - 1), NR>(sl, tb.a[st], rs.dt, xa0, kshift0)))
+          h3_jump_input<NR>(p, rs, Yc, xj, own_f0, own_nf, interval, tid);
           asm volatile("fence.proxy.async;" ::: "memory");
         }
-        if (tid == 0) H3_STAMP(2);
         __syncwarp();
         h3_cluster_sync();
-        if (tid == 0) H3_STAMP(3);
-        // ---- ODEFunc on the tensor cores; last Linear (+ Tanh) -> K[st]
-        for (int l = 0; l < NL; ++l) {
-          const bool last = l == NL - 1;
-          const H3Layer* next = !last ? &p.lay[l + 1] : (st + 1 < ns ? &p.lay[0] : nullptr);
-          h3_layer<NR>(c, p.lay[l], next, (l & 1) ? xa1 : xa0, (l & 1) ? xa0 : xa1, last ? 0 : h3_log2(p.lay[l + 1].KCH),
-                       last ? st_base + static_cast<size_t>(st) * arr : nullptr, l);
+        const int kshj = h3_log2(p.jump[0].KCH), kshh = h3_log2(p.head.KCH);
+        const int ncolj = p.SPT;                 // SPT = NR / L: each layer's rows are a block of SPT tile rows
+        for (int l = 0; l < p.L; ++l) {
+          const bool top = l == p.L - 1;
+          H3Call cl;
+          cl.xsrc = xj + static_cast<size_t>(l) * p.xj_buf_bytes; cl.col0 = l * ncolj; cl.ncol = ncolj;
+          cl.out = Yc;                            // the new hidden state of the layer's rows
+          // ... which is also the input x of the next layer's jump (same sequences, SPT rows further) / of the pose head
+          cl.xdst = top ? xa0 : xj + static_cast<size_t>(l + 1) * p.xj_buf_bytes;
+          cl.xdst_kshift = top ? kshh : kshj; cl.xdst_colshift = top ? 0 : ncolj;
+          h3_layer<NR>(c, p.jump[l], top ? &p.head : &p.jump[l + 1], cl, 0);
         }
-        if (tid == 0) H3_STAMP(4);
-      }
-      have_k0 = true;
-
-      if (p.adaptive) {
-        // ---- y1, embedded error, this CTA's share of the per-row error norm
-        if (epi) {
-          float sum[NR / 32][4];
-          H3_DISPATCH_STAGES(ns, (h3_error_pass<NSV, NR>(sl, tb, rs.dt, p.atol, p.rtol, sum)))
-#pragma unroll
-          for (int m = 0; m < NR / 32; ++m)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float v = sum[m][i];
-              v = add_(v, __shfl_xor_sync(0xffffffffu, v, 8));
-              v = add_(v, __shfl_xor_sync(0xffffffffu, v, 16));
-              if (sl.fs == 0) rs.psum[warp][32 * m + 4 * sl.g + i] = v;
-            }
-          if (tid == 0) H3_STAMP(5);
-          named_bar_sync(1, H3_EPI_THREADS);
-          if (tid < NR) {
-            float tot = rs.psum[0][tid];
-#pragma unroll
-            for (int w = 1; w < H3_EPI_WARPS; ++w) tot = add_(tot, rs.psum[w][tid]);
-            __stcg(normpart + static_cast<size_t>(crank) * NR + tid, tot);
+        {
+          H3Call cl;
+          cl.xsrc = xa0; cl.col0 = (p.L - 1) * ncolj; cl.ncol = ncolj;
+          cl.out = headbuf; cl.xdst = nullptr; cl.xdst_kshift = 0; cl.xdst_colshift = 0;
+          h3_layer<NR>(c, p.head, nullptr, cl, 0);
+        }
+        // regressor.2 (128 -> 6) on the CUDA cores: thread = (pose component, sequence of the tile)
+        if (crank == 0) {
+          for (int idx = tid; idx < kPoseDim * ncolj; idx += H3_THREADS) {
+            const int o = idx / ncolj, j = idx - o * ncolj, n = (p.L - 1) * ncolj + j;
+            if (rs.grow[n] < 0) continue;
+            float acc = 0.f;
+            for (int m = 0; m < kRegHidden; ++m) acc = fmaf(__ldg(p.reg_w1 + o * kRegHidden + m), __ldcg(headbuf + static_cast<size_t>(m) * NR + n), acc);
+            p.pose[(static_cast<size_t>(rs.bidx[n]) * p.S_io + interval) * kPoseDim + o] = add_(acc, __ldg(p.reg_b1 + o));
           }
         }
-        __syncwarp();
-        if (tid == 0) H3_STAMP(6);
-        h3_cluster_sync();
-        if (tid == 0) H3_STAMP(7);
-        // ---- per-row controller, identical in every CTA (odernn_fwd.cu:controller; torchode IntegralController)
-        run = 0;
-        if (tid < NR) {
-          const int r = tid;
-          run = rs.run[r];
-          const float dt = rs.dt[r];
-          float t = rs.t[r];
-          const float tend = rs.tend[r];
-          bool accept = true, finite = true;
-          float dt_next = dt;
-          if (tb.has_err) {
-            float total = 0.f;
-#pragma unroll
-            for (int k = 0; k < H3_NC; ++k) total = add_(total, __ldcg(normpart + k * NR + r));
-            const float ratio = sqrtf(__fdiv_rn(total, static_cast<float>(D)));
-            finite = isfinite(ratio);
-            accept = p.accept_strict ? (ratio < 1.0f) : (ratio <= 1.0f);
-            float factor = mul_(p.safety, powf(ratio, tb.exponent));
-            factor = fminf(fmaxf(factor, p.fmin), p.fmax);
-            if (p.floor_factor && accept) factor = fmaxf(factor, 1.0f);
-            dt_next = mul_(dt, factor);
-          }
-          const int upd = (accept && run) ? 1 : 0;
-          rs.nsteps[r] += run;
-          rs.nacc[r] += upd;
-          const bool lands = p.exact_landing && dt >= sub_(tend, t);
-          t = upd ? (lands ? tend : add_(t, dt)) : t;
-          rs.upd[r] = upd;
-          if (run && !finite) rs.status[r] = max(rs.status[r], 2);
-          run = (run && t < tend && finite) ? 1 : 0;
-          if (run && loops >= p.max_steps) { rs.status[r] = max(rs.status[r], 1); run = 0; }
-          float dtn = run ? dt_next : dt;
-          dtn = fminf(fmaxf(dtn, sub_(rs.tmin[r], t)), sub_(rs.tmax[r], t));
-          rs.t[r] = t;
-          rs.dt[r] = dtn;
-          rs.run[r] = run;
-        }
-        any_running = __syncthreads_or(run);
-        if (tid == 0) H3_STAMP(8);
-        // ---- commit: accepted rows take y1; FSAL carry (end point rule "y1": exact landing makes y1 the value at t_end)
-        if (epi) h3_commit_rows<NR>(sl, ns, tb.fsal, rs.upd);
-        if (tid == 0) H3_STAMP(9);
-      } else {
-        if (epi) {
-          H3_DISPATCH_STAGES(ns, (h3_fixed_commit<NSV, NR>(sl, tb, rs.dt)))
-          if (tid < NR && rs.grow[tid] >= 0) { rs.nsteps[tid] += 1; rs.nacc[tid] += 1; }
-        }
-        any_running = loops < p.substeps;
       }
-      // the elementwise passes of the next iteration read what this one wrote with a different thread mapping only
-      // within the epilogue warps of this CTA
-      if (epi) named_bar_sync(1, H3_EPI_THREADS);
     }
 
-    // ---- evolved state back to [M][D]; stats / status of the interval
+    // ---- final state back to [L][B][D]
     __syncthreads();
     if (epi) {
       const int nf4 = own_nf / 4;
@@ -730,14 +879,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_evolve_kernel(const _
         if (gr < 0) continue;
         const float* src = Yc + static_cast<size_t>(own_f0 + 4 * f4) * NR + n;
         const float4 v = make_float4(__ldcg(src), __ldcg(src + NR), __ldcg(src + 2 * NR), __ldcg(src + 3 * NR));
-        *reinterpret_cast<float4*>(p.Y + static_cast<size_t>(gr) * D + own_f0 + 4 * f4) = v;
-      }
-      if (crank == 0 && tid < NR && rs.grow[tid] >= 0) {
-        if (p.stats) {
-          int* sp = p.stats + ((static_cast<size_t>(p.interval) * p.L + rs.lyr[tid]) * p.B + rs.bidx[tid]) * 2;
-          sp[0] = rs.nsteps[tid]; sp[1] = rs.nacc[tid];
-        }
-        if (p.status && rs.status[tid]) atomicMax(p.status + rs.bidx[tid], rs.status[tid]);
+        *reinterpret_cast<float4*>(p.hT + static_cast<size_t>(gr) * D + own_f0 + 4 * f4) = v;
       }
     }
     __syncthreads();
@@ -751,11 +893,13 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_evolve_kernel(const _
   }
 }
 
-// W [N][K] (PyTorch layout) -> per-CTA fp16 hi / lo operand images:
-// [cta][k-chunk][tile][hi | lo][feature / 8][k / 8][feature % 8][k % 8]; one thread per 16-byte piece (8 k of one feature)
-__global__ void h3_pack_weight_kernel(const float* __restrict__ W, int N, int K, int Fc, int T, int KCH, unsigned char* __restrict__ dst) {
-  const int nch = K / KCH, k8n = KCH / 8;
-  const size_t total = static_cast<size_t>(H3_NC) * nch * T * 128 * k8n;
+// W [N][K1] (and W2 [N][K2], the columns K1 .. K1 + K2 of the concatenated operand; PyTorch layout) -> per-CTA fp16
+// hi / lo operand images [cta][k-chunk][tile][hi | lo][feature / 8][k / 8][feature % 8][k % 8]; one thread per 16-byte piece
+// (8 k of one feature; K1 is a multiple of 8)
+__global__ void h3_pack_weight_kernel(const float* __restrict__ W, int K1, const float* __restrict__ W2, int K2, int nctas, int Fc,
+                                      int T, int KCH, unsigned char* __restrict__ dst) {
+  const int nch = (K1 + K2) / KCH, k8n = KCH / 8;
+  const size_t total = static_cast<size_t>(nctas) * nch * T * 128 * k8n;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     size_t r = i;
     const int k8 = static_cast<int>(r % k8n); r /= k8n;
@@ -764,7 +908,8 @@ __global__ void h3_pack_weight_kernel(const float* __restrict__ W, int N, int K,
     const int kc = static_cast<int>(r % nch); r /= nch;
     const int cta = static_cast<int>(r);
     const int f = cta * Fc + (t == 0 ? 0 : Fc - 128) + m;
-    const float* src = W + static_cast<size_t>(f) * K + static_cast<size_t>(kc) * KCH + 8 * k8;
+    const int k = kc * KCH + 8 * k8;
+    const float* src = k < K1 ? W + static_cast<size_t>(f) * K1 + k : W2 + static_cast<size_t>(f) * K2 + (k - K1);
     __half hi[8], lo[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) h3_split(src[e], hi[e], lo[e]);
@@ -778,15 +923,36 @@ __global__ void h3_pack_weight_kernel(const float* __restrict__ W, int N, int K,
 }
 
 // ------------------------------------------------------------------------------------------ host side
+struct H3LayerPlan { int K, N, Fc, T, KCH, nch, nseg, nctas; size_t off_w; };
+
 struct H3Plan {
-  int NL, NR, ntiles, nclusters;
-  int K[H3_MAXL], N[H3_MAXL], Fc[H3_MAXL], T[H3_MAXL], KCH[H3_MAXL], nch[H3_MAXL], nseg[H3_MAXL];
-  size_t off_w[H3_MAXL], off_xa, xa_buf_bytes, off_state, state_floats, total_bytes, smem_bytes;
+  int NL, NR, SPT, ntiles, nclusters;
+  bool can_jump;                         // the rnn jump + pose head can run inside the cluster kernel
+  H3LayerPlan lay[H3_MAXL], jump[2], head;
+  size_t off_xa, xa_buf_bytes, off_xj, xj_buf_bytes, off_state, state_floats, total_bytes, smem_bytes;
 };
+
+// geometry of one Linear on the cluster: `nctas` CTAs x Fc features, MMAs over `ncol` tile rows
+int h3_plan_layer(int K, int N, int nctas, int ncol, H3LayerPlan& y) {
+  if (N % nctas) return ODEVIO_E_SHAPE;
+  const int Fc = N / nctas;
+  if (Fc < 128 || Fc > 256 || Fc % 32) return ODEVIO_E_SHAPE;
+  const int T = Fc > 128 ? 2 : 1, KCH = 64 / T;
+  if (K % 64) return ODEVIO_E_SHAPE;
+  y.K = K; y.N = N; y.Fc = Fc; y.T = T; y.KCH = KCH; y.nch = K / KCH; y.nctas = nctas;
+  // the accumulate of tcgen05.mma truncates: at most ~12 k-steps of 16 go into one accumulator
+  int nseg = (K / 16 + 11) / 12;
+  const int fit = 512 / (T * ncol) - 1;
+  if (nseg > fit) nseg = fit;
+  if (nseg > y.nch) nseg = y.nch;
+  if (nseg < 1) return ODEVIO_E_SHAPE;
+  y.nseg = nseg;
+  return 0;
+}
 
 int h3_plan(const odevio_odernn_cfg& c, H3Plan& pl) {
   const long long M = static_cast<long long>(c.L) * c.B;
-  if (M <= 0 || M > 0x7fffffffLL || c.n_hidden < 1 || c.n_hidden + 1 > H3_MAXL) return ODEVIO_E_SHAPE;
+  if (M <= 0 || M > 0x7fffffffLL || c.n_hidden < 1 || c.n_hidden + 1 > H3_MAXL || c.L < 1) return ODEVIO_E_SHAPE;
   int dev = 0, nsm = 148;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) {
     cudaGetLastError();
@@ -794,7 +960,8 @@ int h3_plan(const odevio_odernn_cfg& c, H3Plan& pl) {
   }
   pl.NL = c.n_hidden + 1;
   pl.NR = 64;
-  pl.ntiles = static_cast<int>((M + pl.NR - 1) / pl.NR);
+  pl.SPT = (pl.NR % c.L == 0 && (pl.NR / c.L) % 8 == 0) ? pl.NR / c.L : 0;
+  pl.ntiles = pl.SPT ? (c.B + pl.SPT - 1) / pl.SPT : static_cast<int>((M + pl.NR - 1) / pl.NR);
   pl.nclusters = nsm / H3_NC;
   if (pl.nclusters > pl.ntiles) pl.nclusters = pl.ntiles;
   size_t off = 0;
@@ -802,24 +969,29 @@ int h3_plan(const odevio_odernn_cfg& c, H3Plan& pl) {
   int kmax = 0;
   for (int l = 0; l < pl.NL; ++l) {
     const int K = l == 0 ? c.D : c.H, N = l == pl.NL - 1 ? c.D : c.H;
-    if (N % H3_NC) return ODEVIO_E_SHAPE;
-    const int Fc = N / H3_NC;
-    if (Fc < 128 || Fc > 256 || Fc % 32) return ODEVIO_E_SHAPE;
-    const int T = Fc > 128 ? 2 : 1, KCH = 64 / T;
-    if (K % KCH || K % 64) return ODEVIO_E_SHAPE;
-    pl.K[l] = K; pl.N[l] = N; pl.Fc[l] = Fc; pl.T[l] = T; pl.KCH[l] = KCH; pl.nch[l] = K / KCH;
-    int nseg = 512 / (T * pl.NR) - 1;
-    if (nseg > 4) nseg = 4;
-    if (nseg > pl.nch[l]) nseg = pl.nch[l];
-    if (nseg < 1) return ODEVIO_E_SHAPE;
-    pl.nseg[l] = nseg;
-    pl.off_w[l] = take(static_cast<size_t>(H3_NC) * pl.nch[l] * H3_WCHUNK);
+    const int rc = h3_plan_layer(K, N, H3_NC, pl.NR, pl.lay[l]);
+    if (rc != 0) return rc;
+    pl.lay[l].off_w = take(static_cast<size_t>(H3_NC) * pl.lay[l].nch * H3_WCHUNK);
     if (K > kmax) kmax = K;
   }
-  if ((c.D / H3_NC) % 32 || c.D % 16) return ODEVIO_E_SHAPE;
+  if ((c.D / H3_NC) % 32 || c.D % 64) return ODEVIO_E_SHAPE;
+  // jump + head inside the kernel: tanh rnn, 1 or 2 layers (MMAs over SPT = 64 / L rows: a multiple of 32)
+  pl.can_jump = !c.evolve_only && c.rnn_type == ODEVIO_RNN_TANH && pl.SPT >= 32;
+  if (pl.can_jump) {
+    for (int l = 0; l < c.L; ++l) {
+      if (h3_plan_layer(2 * c.D, c.D, H3_NC, pl.SPT, pl.jump[l]) != 0) { pl.can_jump = false; break; }
+      pl.jump[l].off_w = take(static_cast<size_t>(H3_NC) * pl.jump[l].nch * H3_WCHUNK);
+    }
+  }
+  if (pl.can_jump) {
+    if (h3_plan_layer(c.D, kRegHidden, 1, pl.SPT, pl.head) != 0) pl.can_jump = false;
+    else pl.head.off_w = take(static_cast<size_t>(pl.head.nch) * H3_WCHUNK);
+  }
   pl.xa_buf_bytes = (static_cast<size_t>(kmax) * pl.NR * 4 + 1023) / 1024 * 1024;       // hi + lo fp16 images of kmax x NR
   pl.off_xa = take(static_cast<size_t>(pl.nclusters) * 2 * pl.xa_buf_bytes);
-  pl.state_floats = (static_cast<size_t>(kMaxStages + 2) * c.D + H3_NC) * pl.NR;
+  pl.xj_buf_bytes = pl.can_jump ? static_cast<size_t>(2 * c.D) * pl.NR * 4 : 0;
+  pl.off_xj = take(static_cast<size_t>(pl.nclusters) * c.L * pl.xj_buf_bytes);
+  pl.state_floats = (static_cast<size_t>(kMaxStages + 2) * c.D + H3_NC + kRegHidden) * pl.NR;
   pl.state_floats = (pl.state_floats + 255) / 256 * 256;
   pl.off_state = take(static_cast<size_t>(pl.nclusters) * pl.state_floats * sizeof(float));
   pl.total_bytes = off;
@@ -828,7 +1000,7 @@ int h3_plan(const odevio_odernn_cfg& c, H3Plan& pl) {
 }
 
 typedef void (*H3Kernel)(H3Params);
-H3Kernel h3_kernel_of(const H3Plan&) { return static_cast<H3Kernel>(odernn_h3_evolve_kernel<64>); }
+H3Kernel h3_kernel_of(const H3Plan&) { return static_cast<H3Kernel>(odernn_h3_kernel<64>); }
 
 cudaError_t h3_launch_config(const H3Plan& pl, cudaLaunchConfig_t& lc, cudaLaunchAttribute& at, int nclusters, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(h3_kernel_of(pl), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem_bytes));
@@ -893,34 +1065,68 @@ int odernn_h3_timing_read(float* total_ms, int* launches) {
 H3Evolve::H3Evolve() : impl(nullptr) {}
 H3Evolve::~H3Evolve() { delete impl; }
 
-int H3Evolve::prepare(const odevio_odernn_cfg& c, const DevTableau& tab, bool adaptive, const float* const* ode_w,
-                      const float* const* ode_b, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+namespace {
+void h3_fill_layer(H3Layer& y, const H3LayerPlan& lp, int act, const unsigned char* ws, const float* bias, const float* bias2) {
+  y.K = lp.K; y.N = lp.N; y.Fc = lp.Fc; y.T = lp.T; y.KCH = lp.KCH; y.nch = lp.nch; y.nseg = lp.nseg; y.act = act;
+  y.nctas = lp.nctas; y.Wimg = ws + lp.off_w; y.bias = bias; y.bias2 = bias2;
+}
+cudaError_t h3_pack(const float* W, int K1, const float* W2, int K2, const H3LayerPlan& lp, unsigned char* ws, cudaStream_t stream) {
+  h3_pack_weight_kernel<<<296, 256, 0, stream>>>(W, K1, W2, K2, lp.nctas, lp.Fc, lp.T, lp.KCH, ws + lp.off_w);
+  return cudaGetLastError();
+}
+}  // namespace
+
+bool odernn_h3_can_fuse_jump(const odevio_odernn_cfg& c) {
+  H3Plan pl;
+  return h3_plan(c, pl) == 0 && pl.can_jump;
+}
+
+int H3Evolve::prepare(const odevio_odernn_cfg& c, const DevTableau& tab, bool adaptive, const odevio_odernn_weights* w, bool with_jump,
+                      bool pack_weights, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   delete impl;
   impl = new Impl();
   H3Plan& pl = impl->pl;
   const int rc = h3_plan(c, pl);
   if (rc != 0) return rc;
+  if (with_jump && !pl.can_jump) return ODEVIO_E_SHAPE;
   if (workspace_bytes < pl.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ODEVIO_E_WORKSPACE;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   H3Params& p = impl->prm;
   memset(&p, 0, sizeof(p));
-  p.M = c.L * c.B; p.B = c.B; p.L = c.L; p.D = c.D; p.NL = pl.NL;
+  p.B = c.B; p.L = c.L; p.D = c.D; p.NL = pl.NL; p.SPT = pl.SPT;
   for (int l = 0; l < pl.NL; ++l) {
-    if (!ode_w[l] || !ode_b[l]) return ODEVIO_E_NULL;
-    H3Layer& y = p.lay[l];
-    y.K = pl.K[l]; y.N = pl.N[l]; y.Fc = pl.Fc[l]; y.T = pl.T[l]; y.KCH = pl.KCH[l]; y.nch = pl.nch[l]; y.nseg = pl.nseg[l];
-    y.act = l == pl.NL - 1 ? ACT_TANH : c.activation;
-    h3_pack_weight_kernel<<<296, 256, 0, stream>>>(ode_w[l], pl.N[l], pl.K[l], pl.Fc[l], pl.T[l], pl.KCH[l], ws + pl.off_w[l]);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return static_cast<int>(e);
-    y.Wimg = ws + pl.off_w[l]; y.bias = ode_b[l];
+    if (!w->ode_w[l] || !w->ode_b[l]) return ODEVIO_E_NULL;
+    h3_fill_layer(p.lay[l], pl.lay[l], l == pl.NL - 1 ? ACT_TANH : c.activation, ws, w->ode_b[l], nullptr);
+    if (pack_weights) {
+      const cudaError_t e = h3_pack(w->ode_w[l], pl.lay[l].K, nullptr, 0, pl.lay[l], ws, stream);
+      if (e != cudaSuccess) return static_cast<int>(e);
+    }
+  }
+  if (with_jump) {
+    for (int l = 0; l < c.L; ++l) {
+      if (!w->rnn_w_ih[l] || !w->rnn_w_hh[l] || !w->rnn_b_ih[l] || !w->rnn_b_hh[l]) return ODEVIO_E_NULL;
+      h3_fill_layer(p.jump[l], pl.jump[l], ACT_TANH, ws, w->rnn_b_ih[l], w->rnn_b_hh[l]);
+      if (pack_weights) {
+        const cudaError_t e = h3_pack(w->rnn_w_ih[l], c.D, w->rnn_w_hh[l], c.D, pl.jump[l], ws, stream);
+        if (e != cudaSuccess) return static_cast<int>(e);
+      }
+    }
+    if (!w->reg_w0 || !w->reg_b0 || !w->reg_w1 || !w->reg_b1) return ODEVIO_E_NULL;
+    h3_fill_layer(p.head, pl.head, ACT_LEAKY01, ws, w->reg_b0, nullptr);
+    if (pack_weights) {
+      const cudaError_t e = h3_pack(w->reg_w0, c.D, nullptr, 0, pl.head, ws, stream);
+      if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    p.reg_w1 = w->reg_w1; p.reg_b1 = w->reg_b1;
   }
   p.xa = ws + pl.off_xa; p.xa_buf_bytes = pl.xa_buf_bytes;
+  p.xj = ws + pl.off_xj; p.xj_buf_bytes = pl.xj_buf_bytes;
   p.state = reinterpret_cast<float*>(ws + pl.off_state); p.state_floats = pl.state_floats;
   p.ntiles = pl.ntiles;
   p.tab = tab; p.adaptive = adaptive ? 1 : 0; p.substeps = c.substeps;
   p.atol = c.atol; p.rtol = c.rtol; p.dt0 = c.dt0; p.safety = c.safety; p.fmin = c.factor_min; p.fmax = c.factor_max;
   p.accept_strict = c.accept_strict; p.floor_factor = c.floor_factor; p.max_steps = c.max_steps; p.exact_landing = c.exact_landing;
+  p.do_jump = with_jump ? 1 : 0;
   return 0;
 }
 
@@ -939,22 +1145,21 @@ int H3Evolve::max_clusters() {
   return maxc;
 }
 
-int H3Evolve::evolve(float* Y, int Bsub, const int* seq, const float* ts, int ts_ld, int interval, int* stats, int* status,
-                     cudaStream_t stream) {
+int H3Evolve::run(const float* h0, float* hT, const float* ts, int ts_ld, int interval0, int n_intervals, const float* fv,
+                  const float* fi, int Dv, int S_io, float* pose, int* stats, int* status, cudaStream_t stream) {
   if (!impl) return ODEVIO_E_NULL;
   H3Params p = impl->prm;
   H3Plan& pl = impl->pl;
-  if (Bsub <= 0 || Bsub > p.B) return ODEVIO_E_SHAPE;
-  const int rows = p.L * Bsub;
-  p.M = rows; p.ntiles = (rows + pl.NR - 1) / pl.NR;
-  p.Bsub = Bsub; p.seq = seq;
-  p.Y = Y; p.ts = ts; p.ts_ld = ts_ld; p.interval = interval; p.stats = stats; p.status = status;
+  if (!hT || !ts || n_intervals < 1) return ODEVIO_E_NULL;
+  if (p.do_jump && (!fv || !pose || Dv <= 0 || Dv > p.D || (Dv < p.D && !fi))) return ODEVIO_E_NULL;
+  p.h0 = h0; p.hT = hT; p.ts = ts; p.ts_ld = ts_ld; p.interval0 = interval0; p.nI = n_intervals;
+  p.fv = fv; p.fi = fi; p.Dv = Dv; p.S_io = S_io; p.pose = pose; p.stats = stats; p.status = status;
   int nclusters = max_clusters();
   if (nclusters > p.ntiles) nclusters = p.ntiles;
   cudaLaunchConfig_t lc; cudaLaunchAttribute at;
   cudaError_t e = h3_launch_config(pl, lc, at, nclusters, stream);
   if (e != cudaSuccess) return static_cast<int>(e);
-  g_h3_last_clusters = nclusters; g_h3_last_max_clusters = impl->maxc; g_h3_last_rows = rows;
+  g_h3_last_clusters = nclusters; g_h3_last_max_clusters = impl->maxc; g_h3_last_rows = p.L * p.B;
   const bool timed = g_h3_timing && g_h3_timing_n < kH3TimingSlots;
   if (timed) cudaEventRecord(g_h3_ev[g_h3_timing_n][0], stream);
   e = cudaLaunchKernelEx(&lc, h3_kernel_of(pl), p);

@@ -286,6 +286,8 @@ class PoseODERNN(nn.Module):
         self.last_stats = None      # int32 [S, L, B, 2] = (n_steps, n_accepted) of the last forward
         self.last_trace = None      # float32 [S, L, B, T, 2] = (dt, error ratio) when trace_steps = T > 0
         self.last_status = None     # int32 [B]
+        self.last_prepacked = False # the last forward reused the packed weight images of an earlier one
+        self._ws_cache = None
 
     # -- reference menu (PoseODERNN.py:125-148) ------------------------------------------
     def _set_solver(self, ode_solver):
@@ -414,7 +416,10 @@ class PoseODERNN(nn.Module):
         if nbytes == 0:
             raise _lib.OdevioError("unsupported PoseODERNN configuration for the fused kernel "
                                    f"(D={cfg.D}, H={cfg.H}, L={cfg.L}, n={cfg.n_hidden})")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = self._cached_workspace(cfg, nbytes, dev, stream) if not save_ckpt else None
+        if ws is None:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         pose = torch.empty(B, S, 6, dtype=torch.float32, device=dev)
         hT = torch.empty(self.rnn_num_layers, B, self.f_len, dtype=torch.float32, device=dev)
         T = self.trace_steps
@@ -422,7 +427,6 @@ class PoseODERNN(nn.Module):
                  if (self.collect_stats or T) else None)
         status = torch.zeros(B, dtype=torch.int32, device=dev)
         w, keep = self._weights(fuse_in_kernel=(self.fuse_method == "soft" and fic is not None))
-        stream = torch.cuda.current_stream(dev).cuda_stream
         if do_profile:
             torch.cuda.nvtx.range_push("odeint")                               # PoseODERNN.py:103-104
         with torch.cuda.device(dev):
@@ -440,6 +444,31 @@ class PoseODERNN(nn.Module):
         self.last_trace = (stats[..., 2:].contiguous().view(torch.float32).view(S, self.rnn_num_layers, B, T, 2)
                            if T else None)
         return pose, hT, (cfg, ckpt, ckpt_bytes)
+
+    def _cached_workspace(self, cfg, nbytes, dev, stream):
+        """"Prepare the weights once" (fp16x3 inference): the library packs the weights into the workspace on every call
+        unless ``cfg.weights_prepacked`` says the images of an earlier call are still there.  The module keeps that
+        workspace and hands it back while nothing the images depend on has changed: same cfg, device, stream (forwards of
+        one module on one stream are ordered, so the scratch part of the workspace is never shared), and every parameter
+        at the same address and version counter (writes through ``param.data`` bypass the counter: call
+        ``invalidate_packed_weights()`` after such an update).  Returns None when the precision has no packed-weight reuse."""
+        self.last_prepacked = False
+        if cfg.precision != _lib.PRECISION["fp16x3"]:
+            return None
+        fields = tuple(getattr(cfg, n) for n, _ in cfg._fields_ if n not in ("weights_prepacked", "reserved"))
+        params = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (fields, str(dev), stream, params, nbytes)
+        cached = getattr(self, "_ws_cache", None)
+        if cached is not None and cached[0] == key:
+            cfg.weights_prepacked = 1
+            self.last_prepacked = True
+            return cached[1]
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self._ws_cache = (key, ws)
+        return ws
+
+    def invalidate_packed_weights(self):
+        self._ws_cache = None
 
     def evolve_state(self, state, ts):
         """``PoseODERNN.evolve_state`` (reference PoseODERNN.py:70-75): the IVP ``y' = ODEFunc(y)`` from

@@ -129,15 +129,30 @@ class FusedPoseNetAdam:
         _lib.check(rc)
 
 
-def fused_train_step(model, opt, fv, fi, ts, gts, world_size=1, group=None):
+def fused_train_step(model, opt, fv, fi, ts, gts, world_size=1, group=None, events=None):
     """One optimisation step on this rank's shard (scripts/train_model.py:69-86) with the glue on the device: fused forward
-    (checkpoints), fused loss + d loss / d poses, fused backward, ONE flat-bucket all-reduce, clip + Adam as its epilogue."""
+    (checkpoints), fused loss + d loss / d poses, fused backward, ONE flat-bucket all-reduce, clip + Adam as its epilogue.
+    ``events``: optional list that receives (name, start, end) CUDA-event triples of the phases (bench.py)."""
+    def mark():
+        if events is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
     opt.zero_grad()
+    t0 = mark()
     poses, _ = model(fv, fi, ts, prev=None)
+    t1 = mark()
     loss = fused_pose_loss(poses, gts)
     loss.backward()
     flat = opt.gather_grads(1.0 / world_size if world_size > 1 else 1.0)
+    t2 = mark()
     if world_size > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    t3 = mark()
     opt.step()
+    t4 = mark()
+    if events is not None:
+        events += [("forward", t0, t1), ("loss_backward", t1, t2), ("allreduce", t2, t3), ("clip_adam", t3, t4)]
     return loss.detach()

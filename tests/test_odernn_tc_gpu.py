@@ -1,6 +1,7 @@
-"""GPU parity of the tensor-core solver paths (cfg.precision = ODEVIO_PRECISION_TF32X3: odernn_tc.cu;
-ODEVIO_PRECISION_FP16X3: odernn_h3.cu): per interval one cluster kernel evolves all L*B rows (3xTF32 / 3xFP16
-ODEFunc GEMMs on tcgen05, solver loop in the cluster), then the FMA kernel runs the jump + head.  Same oracle, same tolerances as the fp32 FMA path
+"""GPU parity of the tensor-core solver paths.  cfg.precision = ODEVIO_PRECISION_TF32X3 (odernn_tc.cu): per interval one
+cluster kernel evolves all L*B rows, then the FMA kernel runs the jump + head.  ODEVIO_PRECISION_FP16X3 (odernn_h3.cu):
+ONE launch per forward -- solver loops of all intervals, rnn jump and pose head inside the cluster kernel (tanh rnn, "cat"
+fusion, L <= 2; GRU / "soft" fusion: per-interval launches + FMA jump).  Same oracle, same tolerances as the fp32 FMA path
 (tests/test_odernn_gpu.py): poses <= 1e-5 max-norm relative, identical step counts wherever the reference
 semantics determine them at fp32 precision."""
 
@@ -172,3 +173,51 @@ def test_tc_evolve_state_side_launch_l1(cuda_device, prec):
     with torch.no_grad():
         o = ref.evolve_state(state.cpu()[rows], ts.cpu()[rows])
     assert rel_err(got.cpu()[rows], o["y_end"]) <= STATE_RTOL
+
+
+def test_h3_single_launch_l1_prev_and_zero_length_intervals(cuda_device):
+    """The one-launch forward of odernn_h3.cu at L = 1 (64 sequences per tile, jump MMAs over 64 rows), with a carried
+    state `prev`, a ragged last tile (B = 70) and observation intervals of length zero for some rows (no solve, the jump
+    still runs: PoseODERNN.py:108-117)."""
+    ref, mod = make_pair(cuda_device, ode_solver="dopri5", ode_rtol=1e-3, ode_precision="fp16x3", rnn_num_layers=1, bias_std=0.05)
+    fv, fi, ts = inputs(70, S=6, irregular=True, seed=5, offset=12.0)
+    ts[::3, 3] = ts[::3, 2]                      # zero-length third interval on every third sequence
+    ts[5, 1] = ts[5, 0]
+    g = torch.Generator().manual_seed(9)
+    prev = 0.3 * torch.randn(1, 70, 768, generator=g)
+    out = run_pair(ref, mod, fv, fi, ts, prev=prev, ensemble=3)
+    _check(out)
+    st = mod.last_stats.cpu()
+    assert (st[2, 0, ::3, 0] == 0).all() and st[0, 0, 5, 0] == 0
+
+
+def test_h3_single_launch_prev_l2(cuda_device):
+    ref, mod = make_pair(cuda_device, ode_solver="dopri5", ode_rtol=1e-3, ode_precision="fp16x3", bias_std=0.05)
+    fv, fi, ts = inputs(45, S=4, irregular=True, seed=2, offset=3.25)
+    g = torch.Generator().manual_seed(6)
+    prev = 0.3 * torch.randn(2, 45, 768, generator=g)
+    out = run_pair(ref, mod, fv, fi, ts, prev=prev, ensemble=3)
+    _check(out)
+
+
+def test_h3_soft_fusion_takes_the_per_interval_path(cuda_device):
+    """FusionModule "soft" is evaluated in the FMA kernel's jump prologue: the fp16x3 mode then launches per interval."""
+    ref, mod = make_pair(cuda_device, ode_solver="dopri5", ode_rtol=1e-3, ode_precision="fp16x3", fuse_method="soft", bias_std=0.05)
+    out = run_pair(ref, mod, *inputs(20, S=3, irregular=True, seed=4), ensemble=3)
+    _check(out)
+
+
+def test_h3_weights_prepacked_reuse(cuda_device):
+    """Second forward with unchanged weights skips the packing launches (cfg.weights_prepacked) and is bit-identical;
+    an in-place weight update invalidates the cache."""
+    ref, mod = make_pair(cuda_device, ode_solver="dopri5", ode_rtol=1e-3, ode_precision="fp16x3", bias_std=0.05)
+    fv, fi, ts = (t.to(cuda_device) for t in inputs(40, S=3, irregular=True, seed=1))
+    with torch.no_grad():
+        p1, _ = mod(fv, fi, ts)
+        assert not mod.last_prepacked
+        p2, _ = mod(fv, fi, ts)
+        assert mod.last_prepacked and torch.equal(p1, p2)
+        mod.regressor[2].bias.add_(1.0)
+        p3, _ = mod(fv, fi, ts)
+        assert not mod.last_prepacked
+    assert torch.allclose(p3, p1 + 1.0, atol=1e-5)
