@@ -66,7 +66,7 @@ constexpr int H3_WARP_WPROD = 8, H3_WARP_XPROD = 9, H3_WARP_MMA = 10;
 constexpr int H3_THREADS = 32 * 11;
 constexpr int H3_EPI_THREADS = 32 * H3_EPI_WARPS;
 constexpr int H3_WCHUNK = 32768;          // bytes of a weight stage: T tiles x (hi | lo) x 128 features x KCH k (KCH = 64 / T)
-constexpr int H3_NWS = 4, H3_NXS = 4;     // ring depths (powers of two)
+constexpr int H3_NST = 4;                 // ring depth (power of two): stage s holds weight chunk + activation chunk g, s = g % 4
 
 struct H3Layer {
   int K, N;                 // input / output features
@@ -130,9 +130,12 @@ struct H3Rows {      // per-row solver state, replicated in every CTA of the clu
 
 struct H3Ctx {
   unsigned char* wring; unsigned char* xring;
-  uint64_t* w_full; uint64_t* w_empty; uint64_t* x_full; uint64_t* x_empty; uint64_t* accum_bar;
+  // full[s]: 2 arrivals (weight producer + activation producer, each with its bytes); empty[s]: 1 arrival (tcgen05.commit
+  // after the chunk's MMAs).  One wait + one commit per chunk in the MMA issuer: every instruction between two MMAs of
+  // the single issuing thread delays the tensor pipe (profiles/r02_mma_tma_probe.md, second part).
+  uint64_t* full; uint64_t* empty; uint64_t* accum_bar;
   uint32_t tmem, crank;
-  uint32_t wcount, xcount;   // chunks of all previous layers on each ring (identical in every role)
+  uint32_t count;            // chunks of all previous layers (identical in every role)
   uint32_t accum_phase;
   uint32_t w_ahead;          // weight producer: chunks of the coming layer already issued
 };
@@ -239,15 +242,15 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
 
   if (warp == H3_WARP_WPROD) {
     // ===== weight producer: one 32 KB bulk copy per chunk; whole warp, one elected lane issues
-    uint32_t g = c.wcount + c.w_ahead;
+    uint32_t g = c.count + c.w_ahead;
     if (active) {
       const unsigned char* src = L.Wimg + static_cast<size_t>(c.crank) * nch * H3_WCHUNK;
       for (int ch = static_cast<int>(c.w_ahead); ch < nch; ++ch, ++g) {
-        const uint32_t s = g & (H3_NWS - 1), ph = (g / H3_NWS) & 1u;
-        mbar_wait(&c.w_empty[s], ph ^ 1u);
+        const uint32_t s = g & (H3_NST - 1), ph = (g / H3_NST) & 1u;
+        mbar_wait(&c.empty[s], ph ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&c.w_full[s], H3_WCHUNK);
-          tma_load_1d(c.wring + s * H3_WCHUNK, src + static_cast<size_t>(ch) * H3_WCHUNK, H3_WCHUNK, &c.w_full[s]);
+          mbar_arrive_expect_tx(&c.full[s], H3_WCHUNK);
+          tma_load_1d(c.wring + s * H3_WCHUNK, src + static_cast<size_t>(ch) * H3_WCHUNK, H3_WCHUNK, &c.full[s]);
         }
         __syncwarp();
       }
@@ -255,13 +258,13 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
     uint32_t pre = 0;
     if (next_active) {
       const unsigned char* nsrc = next->Wimg + static_cast<size_t>(c.crank) * next->nch * H3_WCHUNK;
-      pre = next->nch < H3_NWS ? next->nch : H3_NWS;
+      pre = next->nch < H3_NST ? next->nch : H3_NST;
       for (uint32_t ch = 0; ch < pre; ++ch, ++g) {
-        const uint32_t s = g & (H3_NWS - 1), ph = (g / H3_NWS) & 1u;
-        mbar_wait(&c.w_empty[s], ph ^ 1u);
+        const uint32_t s = g & (H3_NST - 1), ph = (g / H3_NST) & 1u;
+        mbar_wait(&c.empty[s], ph ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&c.w_full[s], H3_WCHUNK);
-          tma_load_1d(c.wring + s * H3_WCHUNK, nsrc + static_cast<size_t>(ch) * H3_WCHUNK, H3_WCHUNK, &c.w_full[s]);
+          mbar_arrive_expect_tx(&c.full[s], H3_WCHUNK);
+          tma_load_1d(c.wring + s * H3_WCHUNK, nsrc + static_cast<size_t>(ch) * H3_WCHUNK, H3_WCHUNK, &c.full[s]);
         }
         __syncwarp();
       }
@@ -271,21 +274,22 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
     // ===== activation producer: one bulk copy (hi | lo images of KCH k x NR rows) per chunk
     if (active) {
       const uint32_t xcb = 4u * static_cast<uint32_t>(L.KCH) * NR;
-      uint32_t g = c.xcount;
+      uint32_t g = c.count;
       for (int ch = 0; ch < nch; ++ch, ++g) {
-        const uint32_t s = g & (H3_NXS - 1), ph = (g / H3_NXS) & 1u;
-        mbar_wait(&c.x_empty[s], ph ^ 1u);
+        const uint32_t s = g & (H3_NST - 1), ph = (g / H3_NST) & 1u;
+        mbar_wait(&c.empty[s], ph ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&c.x_full[s], xcb);
-          tma_load_1d(c.xring + s * XSTAGE, cl.xsrc + static_cast<size_t>(ch) * xcb, xcb, &c.x_full[s]);
+          mbar_arrive_expect_tx(&c.full[s], xcb);
+          tma_load_1d(c.xring + s * XSTAGE, cl.xsrc + static_cast<size_t>(ch) * xcb, xcb, &c.full[s]);
         }
         __syncwarp();
       }
     }
   } else if (warp == H3_WARP_MMA) {
-    // ===== MMA issuer: D^T[128 features x ncol rows] += W[128 x 16] X^T[16 x ncol], three products per k-step.  Whole
-    // warp with warp-uniform operands, one elected lane issues; the chunk body is fully unrolled (h3_issue_chunk) and
-    // there is no division anywhere in the loop.
+    // ===== MMA issuer: D^T[128 features x ncol rows] += W[128 x 16] X^T[16 x ncol], three products per k-step.  ONE
+    // elected lane runs the whole chunk loop (wait, 12 MMAs, commit): measured, a per-chunk warp reconvergence
+    // (elect + fence + syncwarp) costs ~200 clk and a second wait / commit ~55 clk each, none of it overlapped with the
+    // 12 x 50 clk of MMAs.  The chunk body is fully unrolled (h3_issue_chunk), no division anywhere in the loop.
     if (active) {
       const uint32_t nseg = static_cast<uint32_t>(L.nseg);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, c.tmem, 0);
@@ -293,35 +297,29 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
       // chunks per K segment (ceil): segment s takes chunks [s * cps, (s + 1) * cps)
       uint32_t cps = 1;
       while (cps * nseg < static_cast<uint32_t>(nch)) ++cps;
-      uint32_t seg = 0, in_seg = 0, gw = c.wcount, gx = c.xcount;
-      for (int ch = 0; ch < nch; ++ch, ++gw, ++gx) {
-        const uint32_t ws = gw & (H3_NWS - 1), wph = (gw / H3_NWS) & 1u;
-        const uint32_t xs = gx & (H3_NXS - 1), xph = (gx / H3_NXS) & 1u;
-        const long long tw0 = H3_CLOCK();
-        mbar_wait(&c.w_full[ws], wph);
-        const long long tw1 = H3_CLOCK();
-        mbar_wait(&c.x_full[xs], xph);
-        const long long tw2 = H3_CLOCK();
-        if (lane == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        uint32_t seg = 0, in_seg = 0, g = c.count;
+        const uint32_t wring_u = smem_u32(c.wring), xring_u = smem_u32(c.xring);
+        for (int ch = 0; ch < nch; ++ch, ++g) {
+          const uint32_t st = g & (H3_NST - 1), ph = (g / H3_NST) & 1u;
+          const long long tw0 = H3_CLOCK();
+          mbar_wait(&c.full[st], ph);
+          const long long tw1 = H3_CLOCK();
           if (ch == 0) { H3_STAMP(sb + 0); H3_SET(sb + 6, 0); H3_SET(sb + 7, 0); }
-          else { H3_ADD(sb + 6, tw1 - tw0); H3_ADD(sb + 7, tw2 - tw1); }     // starvation after the first chunk: W ring / X ring
+          else H3_ADD(sb + 6, tw1 - tw0);                            // starvation after the first chunk
           if (ch == nch - 1) H3_STAMP(sb + 5);
-        }
-        (void)tw0; (void)tw1; (void)tw2;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t wbase = smem_u32(c.wring + ws * H3_WCHUNK), xbase = smem_u32(c.xring + xs * XSTAGE);
-        if (elect_one()) {
+          (void)tw0; (void)tw1;
+          const uint32_t wbase = wring_u + st * H3_WCHUNK, xbase = xring_u + st * XSTAGE;
           if (L.T == 1) h3_issue_chunk<1, NR>(tmem_u, wbase, xbase, nseg, seg, in_seg != 0, ch != 0, col0, ncol);
           else h3_issue_chunk<2, NR>(tmem_u, wbase, xbase, nseg, seg, in_seg != 0, ch != 0, col0, ncol);
-          h3_commit(&c.w_empty[ws]);
-          h3_commit(&c.x_empty[xs]);
+          h3_commit(&c.empty[st]);
+          if (++in_seg == cps) { in_seg = 0; ++seg; }
         }
-        __syncwarp();
-        if (++in_seg == cps) { in_seg = 0; ++seg; }
+        h3_commit(c.accum_bar);
+        H3_STAMP(sb + 1);
       }
-      if (elect_one()) h3_commit(c.accum_bar);
       __syncwarp();
-      if (lane == 0) H3_STAMP(sb + 1);
     }
   } else if (warp < H3_EPI_WARPS && active) {
     // ===== epilogue: thread = output feature (TMEM lane); warps w and w + 4 share lane quarter w & 3 and alternate over
@@ -385,8 +383,7 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
   }
   if (active) {
     c.accum_phase ^= 1u;
-    c.wcount += static_cast<uint32_t>(nch);
-    c.xcount += static_cast<uint32_t>(nch);
+    c.count += static_cast<uint32_t>(nch);
   }
   __syncwarp();
   h3_cluster_sync();
@@ -605,10 +602,8 @@ __device__ __forceinline__ void h3_jump_input(const H3Params& p, const H3Rows<NR
 template <int NR>
 __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_constant__ H3Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t w_full[H3_NWS];
-  __shared__ __align__(8) uint64_t w_empty[H3_NWS];
-  __shared__ __align__(8) uint64_t x_full[H3_NXS];
-  __shared__ __align__(8) uint64_t x_empty[H3_NXS];
+  __shared__ __align__(8) uint64_t full_bar[H3_NST];
+  __shared__ __align__(8) uint64_t empty_bar[H3_NST];
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) H3Rows<NR> rs;
@@ -620,8 +615,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
   const DevTableau& tb = p.tab;
 
   if (tid == 0) {
-    for (int i = 0; i < H3_NWS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < H3_NXS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < H3_NST; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
     mbar_init(&accum_bar, 1);
     fence_barrier_init();
   }
@@ -634,9 +628,9 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   H3Ctx c;
-  c.wring = smem; c.xring = smem + H3_NWS * H3_WCHUNK;
-  c.w_full = w_full; c.w_empty = w_empty; c.x_full = x_full; c.x_empty = x_empty; c.accum_bar = &accum_bar;
-  c.tmem = tmem_slot; c.crank = crank; c.wcount = 0; c.xcount = 0; c.accum_phase = 0; c.w_ahead = 0;
+  c.wring = smem; c.xring = smem + H3_NST * H3_WCHUNK;
+  c.full = full_bar; c.empty = empty_bar; c.accum_bar = &accum_bar;
+  c.tmem = tmem_slot; c.crank = crank; c.count = 0; c.accum_phase = 0; c.w_ahead = 0;
 
   const int D = p.D, NL = p.NL;
   const int own_nf = D / H3_NC, own_f0 = static_cast<int>(crank) * own_nf;
@@ -995,7 +989,7 @@ int h3_plan(const odevio_odernn_cfg& c, H3Plan& pl) {
   pl.state_floats = (pl.state_floats + 255) / 256 * 256;
   pl.off_state = take(static_cast<size_t>(pl.nclusters) * pl.state_floats * sizeof(float));
   pl.total_bytes = off;
-  pl.smem_bytes = static_cast<size_t>(H3_NWS) * H3_WCHUNK + static_cast<size_t>(H3_NXS) * 4 * 64 * pl.NR + 1024;
+  pl.smem_bytes = static_cast<size_t>(H3_NST) * H3_WCHUNK + static_cast<size_t>(H3_NST) * 4 * 64 * pl.NR + 1024;
   return 0;
 }
 

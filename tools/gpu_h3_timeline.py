@@ -27,7 +27,7 @@ prev = t[3]
 for l in range(4):
     b = 16 + 10 * l
     print(f"layer {l}: first chunk +{t[b]-prev}  last chunk landed +{t[b+5]-prev}  mma issued +{t[b+1]-prev}  accum ready +{t[b+2]-prev}  "
-          f"epilogue done +{t[b+3]-prev}  barrier passed +{t[b+4]-prev}   | starved on W {t[b+6]}  on X {t[b+7]} (after chunk 0)")
+          f"epilogue done +{t[b+3]-prev}  barrier passed +{t[b+4]-prev}   | starved {t[b+6]} (after chunk 0)")
     prev = t[b + 4]
 print("stage total:", t[4] - t[1])
 print("error pass:", t[5] - t[4], " bar+partial store:", t[6] - t[5], " cluster barrier:", t[7] - t[6],
