@@ -347,6 +347,9 @@ ODEVIO_API int32_t odevio_imu_encoder_forward(int32_t B, int32_t S, int32_t i_f_
  *   bucket of n values -- the bucket of the NCCL gradient all-reduce.  step = 1, 2, ... ; norm_coef (DEVICE float[2],
  *   required with max_norm > 0) receives the total gradient norm and the clip coefficient.  All four arrays 16-byte
  *   aligned.  No host synchronisation.
+ * odevio_adam_step_groups: the same for the reference's TWO parameter groups (src/utils/utils.py:116-119: [other, regressor],
+ *   re-scheduled separately by scripts/train_model.py:215-216): elements [0, split) step with lr_first, elements
+ *   [split, n) with lr_rest; split a multiple of 4.  The clip norm is the whole bucket's.
  * workspace: odevio_train_glue_workspace_bytes() bytes, 16-byte aligned.
  */
 ODEVIO_API size_t odevio_train_glue_workspace_bytes(void);
@@ -355,6 +358,10 @@ ODEVIO_API int32_t odevio_pose_loss(int64_t n_rows, const float* pose, const flo
 ODEVIO_API int32_t odevio_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                                     int32_t step, float lr, float beta1, float beta2, float eps, float weight_decay,
                                     float max_norm, float* norm_coef, void* workspace, size_t workspace_bytes, void* stream);
+ODEVIO_API int32_t odevio_adam_step_groups(int64_t n, int64_t split, float* params, const float* grads, float* exp_avg,
+                                           float* exp_avg_sq, int32_t step, float lr_first, float lr_rest, float beta1, float beta2,
+                                           float eps, float weight_decay, float max_norm, float* norm_coef, void* workspace,
+                                           size_t workspace_bytes, void* stream);
 
 /* Diagnostics / measurement hooks (odevio_debug_*, odevio_microbench_ffma) are NOT part of the product ABI: they are
  * declared in include/odevio_debug.h. */

@@ -148,6 +148,9 @@ def load():
     lib.odevio_pose_loss.argtypes = [C.c_int64, _FP, _FP, C.c_float, C.c_float, _FP, _FP, _FP, C.c_size_t, _FP]
     lib.odevio_adam_step.restype = C.c_int32
     lib.odevio_adam_step.argtypes = [C.c_int64, _FP, _FP, _FP, _FP, C.c_int32] + [C.c_float] * 6 + [_FP, _FP, C.c_size_t, _FP]
+    lib.odevio_adam_step_groups.restype = C.c_int32
+    lib.odevio_adam_step_groups.argtypes = ([C.c_int64, C.c_int64, _FP, _FP, _FP, _FP, C.c_int32] + [C.c_float] * 7 +
+                                            [_FP, _FP, C.c_size_t, _FP])
     lib.odevio_debug_tc_geometry.restype = C.c_int32
     lib.odevio_debug_tc_geometry.argtypes = [C.POINTER(C.c_int32)]
     lib.odevio_debug_tc_timing.restype = C.c_int32

@@ -89,14 +89,14 @@ __global__ void clip_coef_kernel(int nblocks, const float* __restrict__ partial,
   norm_coef[1] = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
 }
 
-struct AdamArgs { float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt; };
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float coef, const AdamArgs& a) {
+struct AdamArgs { float lr, lr_rest, beta1, beta2, eps, wd, bc1, bc2_sqrt; long long split; };   // elements >= split step with lr_rest
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float coef, const AdamArgs& a, float lr) {
   g = g * coef;                                   // clip_grad_norm_ scales the gradients in place
   g = fmaf(a.wd, p, g);                           // Adam's L2 weight decay: grad + wd * param
   m = m + (1.f - a.beta1) * (g - m);              // exp_avg.lerp_(grad, 1 - beta1)
   v = fmaf((1.f - a.beta2) * g, g, a.beta2 * v);  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
   const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
-  p = p - (a.lr / a.bc1) * (m / denom);           // param.addcdiv_(exp_avg, denom, value = -step_size)
+  p = p - (lr / a.bc1) * (m / denom);             // param.addcdiv_(exp_avg, denom, value = -step_size)
 }
 __global__ void __launch_bounds__(TG_THREADS) adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
                                                           float* __restrict__ m, float* __restrict__ v,
@@ -108,12 +108,13 @@ __global__ void __launch_bounds__(TG_THREADS) adam_kernel(long long n, float* __
   for (long long i = blockIdx.x * static_cast<long long>(TG_THREADS) + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * TG_THREADS) {
     float4 pp = p4[i], mm = m4[i], vv = v4[i];
     const float4 gg = g4[i];
-    adam_one(pp.x, gg.x, mm.x, vv.x, coef, a); adam_one(pp.y, gg.y, mm.y, vv.y, coef, a);
-    adam_one(pp.z, gg.z, mm.z, vv.z, coef, a); adam_one(pp.w, gg.w, mm.w, vv.w, coef, a);
+    const float lr = (i << 2) < a.split ? a.lr : a.lr_rest;          // split is a multiple of 4 (checked by the host)
+    adam_one(pp.x, gg.x, mm.x, vv.x, coef, a, lr); adam_one(pp.y, gg.y, mm.y, vv.y, coef, a, lr);
+    adam_one(pp.z, gg.z, mm.z, vv.z, coef, a, lr); adam_one(pp.w, gg.w, mm.w, vv.w, coef, a, lr);
     p4[i] = pp; m4[i] = mm; v4[i] = vv;
   }
   if (blockIdx.x == 0)
-    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += TG_THREADS) adam_one(p[i], g[i], m[i], v[i], coef, a);
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += TG_THREADS) adam_one(p[i], g[i], m[i], v[i], coef, a, i < a.split ? a.lr : a.lr_rest);
 }
 
 }  // namespace
@@ -143,8 +144,17 @@ int32_t odevio_pose_loss(int64_t n_rows, const float* pose, const float* gts, fl
 int32_t odevio_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int32_t step,
                          float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
                          float* norm_coef, void* workspace, size_t workspace_bytes, void* stream_) {
+  return odevio_adam_step_groups(n, n, params, grads, exp_avg, exp_avg_sq, step, lr, lr, beta1, beta2, eps, weight_decay, max_norm,
+                                 norm_coef, workspace, workspace_bytes, stream_);
+}
+
+int32_t odevio_adam_step_groups(int64_t n, int64_t split, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                int32_t step, float lr_first, float lr_rest, float beta1, float beta2, float eps,
+                                float weight_decay, float max_norm, float* norm_coef, void* workspace, size_t workspace_bytes,
+                                void* stream_) {
+  const float lr = lr_first;
   if (!params || !grads || !exp_avg || !exp_avg_sq || !workspace) return ODEVIO_E_NULL;
-  if (n <= 0 || step < 1) return ODEVIO_E_SHAPE;
+  if (n <= 0 || step < 1 || split < 0 || split > n || (split & 3)) return ODEVIO_E_SHAPE;
   if (max_norm > 0.f && !norm_coef) return ODEVIO_E_NULL;
   if (workspace_bytes < odevio_train_glue_workspace_bytes() || (reinterpret_cast<uintptr_t>(workspace) & 15)) return ODEVIO_E_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(exp_avg) |
@@ -159,7 +169,7 @@ int32_t odevio_adam_step(int64_t n, float* params, const float* grads, float* ex
     clip_coef_kernel<<<1, 32, 0, stream>>>(static_cast<int>(nb), partial, max_norm, norm_coef);
   }
   AdamArgs a;
-  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
+  a.lr = lr; a.lr_rest = lr_rest; a.split = split; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
   a.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), static_cast<double>(step)));          // torch: Python doubles
   a.bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(step))));
   adam_kernel<<<static_cast<unsigned>(nb), TG_THREADS, 0, stream>>>(n, params, grads, exp_avg, exp_avg_sq, norm_coef, a);

@@ -64,10 +64,10 @@ def pose_loss(poses, gts):
     return 100 * angle + trans
 
 
-def make_optimizer(model, lr=1e-3, weight_decay=5e-5):
-    """utils/utils.py:143-157 (Adam over two Pose_net groups)."""
-    return torch.optim.Adam([{"params": list(model.get_regressor_params())},
-                             {"params": list(model.get_other_params())}],
+def make_optimizer(model, lr=1e-4, weight_decay=5e-5):
+    """utils/utils.py:115-130 (Adam over the two Pose_net groups, [other, regressor], both at lr_warmup = 1e-4)."""
+    return torch.optim.Adam([{"params": list(model.get_other_params()), "lr": lr},
+                             {"params": list(model.get_regressor_params()), "lr": lr}],
                             lr=lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=weight_decay)
 
 

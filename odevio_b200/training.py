@@ -70,20 +70,30 @@ def fused_pose_loss(poses, gts, w_angle=100.0, with_parts=False):
 class FusedPoseNetAdam:
     """Adam (+ global-norm clip) over the reference's ``Pose_net`` parameter set on one flat bucket.
 
-    ``params``: the regressor group then the other parameters (utils/utils.py:143-147), as ``pose_net_params(model)``
-    returns them.  Both reference groups share lr / weight_decay (utils.py:150-157), so one bucket is exact."""
+    The reference builds TWO parameter groups, ``[other parameters, regressor]`` in that order (utils/utils.py:116-119),
+    both starting at ``lr_warmup`` = 1e-4; its epoch loop then re-schedules only ``param_groups[0]['lr']``
+    (scripts/train_model.py:215-216: the group-1 line is commented out), so the regressor stays at 1e-4 while the rest
+    drops to 1e-5 / 1e-6.  ``param_groups`` here is the same two-entry list in the same order and ``step`` reads each
+    group's ``lr`` from it, so the reference loop drives this optimiser unchanged.  The bucket itself is laid out
+    regressor first (``pose_net_params``): elements ``[0, split)`` are the regressor segment."""
 
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-5, max_norm=5.0):
-        self.params = [p for p in pose_net_params(model) if p.requires_grad]
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-5, max_norm=5.0):
+        reg = [p for p in model.get_regressor_params() if p.requires_grad]
+        other = [p for p in model.get_other_params() if p.requires_grad]
+        self.params = reg + other
         if not self.params or not self.params[0].is_cuda:
             raise _lib.OdevioError("FusedPoseNetAdam needs the model on a CUDA device: odevio_b200 has no CPU path")
         dev = self.params[0].device
         # every parameter starts on a 256-byte boundary of the bucket (the kernels' bulk-TMA / 128-bit accesses assume the
         # alignment of a fresh allocation); the padding stays exactly zero under clip + Adam (g = 0, wd * 0 = 0)
         self.offsets, off = [], 0
-        for p in self.params:
+        for i, p in enumerate(self.params):
+            if i == len(reg):
+                self.split = off                   # first element of the "other" segment (a multiple of 64)
             self.offsets.append(off)
             off += (p.numel() + 63) // 64 * 64
+        if not other:
+            self.split = off
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
         with torch.no_grad():
@@ -96,12 +106,30 @@ class FusedPoseNetAdam:
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.norm_coef = torch.zeros(2, dtype=torch.float32, device=dev)      # [total grad norm, clip coefficient]
         self.step_count = 0
-        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self.betas, self.eps, self.weight_decay, self.max_norm = betas, eps, weight_decay, max_norm
+        self.param_groups = [{"params": other, "lr": lr}, {"params": reg, "lr": lr}]      # utils/utils.py:116-119 order
         self._ws, self._ws_bytes = _workspace(dev)
 
-    def zero_grad(self):
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, value):                            # one lr for both groups (the reference's constructor state)
+        for g in self.param_groups:
+            g["lr"] = value
+
+    def zero_grad(self, set_to_none=True):
         for p in self.params:
             p.grad = None
+
+    def _check_aliasing(self):
+        """model.to() / .double() or `p.data = ...` after construction would silently detach a parameter from the bucket."""
+        base = self.flat.data_ptr()
+        for p, o in zip(self.params, self.offsets):
+            if p.data_ptr() != base + 4 * o:
+                raise _lib.OdevioError("a Pose_net parameter no longer aliases the optimiser's flat bucket (model.to() / "
+                                       "re-assigned .data after FusedPoseNetAdam was built): rebuild the optimiser")
 
     def gather_grads(self, weight=1.0):
         """p.grad of every parameter -> the flat bucket (scaled); missing gradients count as zero."""
@@ -116,17 +144,38 @@ class FusedPoseNetAdam:
         return self.grads
 
     def step(self):
-        """clip_grad_norm_(max_norm) + Adam on the bucket (three launches, no host synchronisation)."""
+        """clip_grad_norm_(max_norm) + Adam on the bucket (three launches, no host synchronisation); the regressor segment
+        steps with ``param_groups[1]['lr']``, the rest with ``param_groups[0]['lr']``."""
         lib = _lib.load()
+        self._check_aliasing()
         self.step_count += 1
         dev = self.flat.device
         with torch.cuda.device(dev):
-            rc = lib.odevio_adam_step(self.flat.numel(), _lib.dptr(self.flat), _lib.dptr(self.grads), _lib.dptr(self.exp_avg),
-                                      _lib.dptr(self.exp_avg_sq), self.step_count, self.lr, self.betas[0], self.betas[1],
-                                      self.eps, self.weight_decay, float(self.max_norm or 0.0), _lib.dptr(self.norm_coef),
-                                      _lib.dptr(self._ws), self._ws_bytes,
-                                      C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            rc = lib.odevio_adam_step_groups(self.flat.numel(), self.split, _lib.dptr(self.flat), _lib.dptr(self.grads),
+                                             _lib.dptr(self.exp_avg), _lib.dptr(self.exp_avg_sq), self.step_count,
+                                             float(self.param_groups[1]["lr"]), float(self.param_groups[0]["lr"]),
+                                             self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                             float(self.max_norm or 0.0), _lib.dptr(self.norm_coef),
+                                             _lib.dptr(self._ws), self._ws_bytes,
+                                             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _lib.check(rc)
+
+    def state_dict(self):
+        """Moments, step count and group learning rates (resume: scripts/train_model.py saves optimizer.state_dict())."""
+        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "lr": [g["lr"] for g in self.param_groups], "betas": self.betas, "eps": self.eps,
+                "weight_decay": self.weight_decay, "max_norm": self.max_norm}
+
+    def load_state_dict(self, sd):
+        if sd["exp_avg"].numel() != self.exp_avg.numel():
+            raise _lib.OdevioError("optimizer state does not match this model's Pose_net bucket")
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        for g, lr in zip(self.param_groups, sd["lr"]):
+            g["lr"] = lr
+        self.betas, self.eps = tuple(sd["betas"]), sd["eps"]
+        self.weight_decay, self.max_norm = sd["weight_decay"], sd["max_norm"]
 
 
 def fused_train_step(model, opt, fv, fi, ts, gts, world_size=1, group=None, events=None):

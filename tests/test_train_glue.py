@@ -65,7 +65,12 @@ def test_fused_adam_matches_torch_adam_with_clip(cuda_device):
     ref_opt = make_optimizer(b, lr=1e-3, weight_decay=5e-5)
     keys = list(a.state_dict())
     g = torch.Generator().manual_seed(3)
+    assert [len(g["params"]) for g in fused.param_groups] == [len(g["params"]) for g in ref_opt.param_groups]
     for step in range(5):
+        if step == 3:
+            # the reference's epoch loop re-schedules ONLY group 0 (scripts/train_model.py:215-216; group 0 = the
+            # non-regressor parameters, utils/utils.py:116-119): the regressor keeps the warm-up rate
+            fused.param_groups[0]["lr"] = ref_opt.param_groups[0]["lr"] = 1e-5
         scale = 50.0 if step == 2 else 0.01                       # step 2 exceeds max_norm = 5
         for pa, pb in zip(pose_net_params(a), pose_net_params(b)):
             gr = (scale * torch.randn(pa.shape, generator=g) / pa.numel() ** 0.5).to(cuda_device)
@@ -79,6 +84,16 @@ def test_fused_adam_matches_torch_adam_with_clip(cuda_device):
         for pa, pb in zip(pose_net_params(a), pose_net_params(b)):
             assert ((pa - pb).abs().max() / pb.abs().max().clamp_min(1e-12)).item() <= 1e-5, step
     assert list(a.state_dict()) == keys                            # checkpoint keys unchanged by the flat views
+    # resume: moments / step / group rates survive a state_dict round trip into a fresh optimiser on the same model
+    sd = fused.state_dict()
+    again = FusedPoseNetAdam(a)
+    again.load_state_dict(sd)
+    assert again.step_count == 5 and again.param_groups[0]["lr"] == 1e-5 and again.param_groups[1]["lr"] == 1e-3
+    assert torch.equal(again.exp_avg, fused.exp_avg)
+    # a parameter re-assigned behind the optimiser's back is detected instead of silently ignored
+    a.regressor[2].bias.data = a.regressor[2].bias.data.clone()
+    with pytest.raises(Exception, match="no longer aliases"):
+        again.step()
 
 
 @pytest.mark.gpu
