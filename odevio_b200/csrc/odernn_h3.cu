@@ -62,8 +62,8 @@ __device__ long long g_h3_dbg[96];
 constexpr int H3_NC = 4;                  // CTAs per cluster = feature slices of every Linear
 constexpr int H3_MAXL = ODEVIO_MAX_ODE_LINEARS;
 constexpr int H3_EPI_WARPS = 8;           // warps 0-7: epilogue + elementwise solver passes
-constexpr int H3_WARP_WPROD = 8, H3_WARP_XPROD = 9, H3_WARP_MMA = 10;
-constexpr int H3_THREADS = 32 * 11;
+constexpr int H3_WARP_WPROD = 8, H3_WARP_XPROD = 9, H3_WARP_MMA = 10, H3_WARP_MMA2 = 11;
+constexpr int H3_THREADS = 32 * 12;
 constexpr int H3_EPI_THREADS = 32 * H3_EPI_WARPS;
 constexpr int H3_WCHUNK = 32768;          // bytes of a weight stage: T tiles x (hi | lo) x 128 features x KCH k (KCH = 64 / T)
 constexpr int H3_NST = 4;                 // ring depth (power of two): stage s holds weight chunk + activation chunk g, s = g % 4
@@ -198,19 +198,19 @@ __device__ __forceinline__ size_t h3_x_offset(int k, int n0, int kshift) {
 // accumulators of a tile are ncol columns apart.
 template <int T, int NR>
 __device__ __forceinline__ void h3_issue_chunk(uint32_t tmem, uint32_t wbase, uint32_t xbase, uint32_t nseg, uint32_t seg,
-                                               bool acc_main, bool acc_cross, uint32_t col0, uint32_t ncol) {
+                                               uint32_t cross, bool acc_main, bool acc_cross, uint32_t col0, uint32_t ncol) {
   constexpr uint32_t KCH = 64u / T, KS = KCH / 16u;
   constexpr uint32_t sbo = (KCH >> 3) * 128u;
   constexpr uint32_t hi_word = (sbo >> 4) | (1u << 14);                        // SBO | descriptor version 1 (bit 46)
   constexpr uint32_t tile_bytes = 128u * KCH * 2u, ximg_bytes = KCH * NR * 2u;
   // instruction descriptor: D fp32, A / B fp16, A K-major, B MN-major, N = ncol, M = 128
   const uint32_t idesc = (1u << 4) | (1u << 16) | ((ncol >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
-  const uint32_t acc_per_tile = (nseg + 1u) * ncol;
+  const uint32_t acc_per_tile = (nseg + 2u) * ncol;           // main segments + one cross-term accumulator per issuer
   const uint32_t xcol = xbase + (col0 >> 3) * sbo;
 #pragma unroll
   for (uint32_t t = 0; t < static_cast<uint32_t>(T); ++t) {
     const uint32_t a_hi = wbase + t * 2u * tile_bytes, a_lo = a_hi + tile_bytes;
-    const uint32_t d_main = tmem + t * acc_per_tile + seg * ncol, d_cross = tmem + t * acc_per_tile + nseg * ncol;
+    const uint32_t d_main = tmem + t * acc_per_tile + seg * ncol, d_cross = tmem + t * acc_per_tile + (nseg + cross) * ncol;
 #pragma unroll
     for (uint32_t ks = 0; ks < KS; ++ks) {
       const uint32_t o = ks * 256u;
@@ -285,39 +285,47 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
         __syncwarp();
       }
     }
-  } else if (warp == H3_WARP_MMA) {
-    // ===== MMA issuer: D^T[128 features x ncol rows] += W[128 x 16] X^T[16 x ncol], three products per k-step.  ONE
-    // elected lane runs the whole chunk loop (wait, 12 MMAs, commit): measured, a per-chunk warp reconvergence
-    // (elect + fence + syncwarp) costs ~200 clk and a second wait / commit ~55 clk each, none of it overlapped with the
-    // 12 x 50 clk of MMAs.  The chunk body is fully unrolled (h3_issue_chunk), no division anywhere in the loop.
+  } else if (warp == H3_WARP_MMA || warp == H3_WARP_MMA2) {
+    // ===== MMA issuers: D^T[128 features x ncol rows] += W[128 x 16] X^T[16 x ncol], three products per k-step.  In each
+    // of the two issuer warps ONE elected lane runs a whole chunk loop (wait, 12 MMAs, commit): measured, a per-chunk warp
+    // reconvergence (elect + fence + syncwarp) costs ~200 clk and every wait / commit ~55 clk, none of it overlapped with
+    // the 12 x 50 clk of MMAs of the same thread -- so the chunks alternate between two threads, each hiding the other's
+    // wait + commit.  Issuer i takes the chunks ch = i (mod 2) and owns its own accumulators (main segments
+    // [i * nseg / 2 ...) and cross-term accumulator i): the result does not depend on how the tensor pipe interleaves
+    // the two streams.  The chunk body is fully unrolled (h3_issue_chunk), no division anywhere in the loop.
     if (active) {
+      const uint32_t issuer = warp == H3_WARP_MMA ? 0u : 1u;
       const uint32_t nseg = static_cast<uint32_t>(L.nseg);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, c.tmem, 0);
       const uint32_t col0 = static_cast<uint32_t>(cl.col0), ncol = static_cast<uint32_t>(cl.ncol);
-      // chunks per K segment (ceil): segment s takes chunks [s * cps, (s + 1) * cps)
-      uint32_t cps = 1;
-      while (cps * nseg < static_cast<uint32_t>(nch)) ++cps;
+      // this issuer's chunks: ch = issuer, issuer + 2, ... (nmine of them) over its segments [seg0, seg0 + nsegi)
+      const uint32_t nmine = (static_cast<uint32_t>(nch) + 1u - issuer) >> 1;
+      const uint32_t nseg0 = (nseg + 1u) >> 1;
+      const uint32_t seg0 = issuer ? nseg0 : 0u, nsegi = issuer ? nseg - nseg0 : nseg0;
+      uint32_t cps = 1;                                               // chunks per segment (ceil)
+      while (cps * nsegi < nmine) ++cps;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
-        uint32_t seg = 0, in_seg = 0, g = c.count;
+        uint32_t seg = seg0, in_seg = 0, g = c.count + issuer;
         const uint32_t wring_u = smem_u32(c.wring), xring_u = smem_u32(c.xring);
-        for (int ch = 0; ch < nch; ++ch, ++g) {
+        for (uint32_t j = 0; j < nmine; ++j, g += 2) {
           const uint32_t st = g & (H3_NST - 1), ph = (g / H3_NST) & 1u;
           const long long tw0 = H3_CLOCK();
           mbar_wait(&c.full[st], ph);
           const long long tw1 = H3_CLOCK();
-          if (ch == 0) { H3_STAMP(sb + 0); H3_SET(sb + 6, 0); H3_SET(sb + 7, 0); }
-          else H3_ADD(sb + 6, tw1 - tw0);                            // starvation after the first chunk
-          if (ch == nch - 1) H3_STAMP(sb + 5);
+          if (issuer == 0) {
+            if (j == 0) { H3_STAMP(sb + 0); H3_SET(sb + 6, 0); H3_SET(sb + 7, 0); }
+            else H3_ADD(sb + 6, tw1 - tw0);                          // starvation after the first chunk
+          } else if (j + 1 == nmine) H3_STAMP(sb + 5);
           (void)tw0; (void)tw1;
           const uint32_t wbase = wring_u + st * H3_WCHUNK, xbase = xring_u + st * XSTAGE;
-          if (L.T == 1) h3_issue_chunk<1, NR>(tmem_u, wbase, xbase, nseg, seg, in_seg != 0, ch != 0, col0, ncol);
-          else h3_issue_chunk<2, NR>(tmem_u, wbase, xbase, nseg, seg, in_seg != 0, ch != 0, col0, ncol);
+          if (L.T == 1) h3_issue_chunk<1, NR>(tmem_u, wbase, xbase, nseg, seg, issuer, in_seg != 0, j != 0, col0, ncol);
+          else h3_issue_chunk<2, NR>(tmem_u, wbase, xbase, nseg, seg, issuer, in_seg != 0, j != 0, col0, ncol);
           h3_commit(&c.empty[st]);
           if (++in_seg == cps) { in_seg = 0; ++seg; }
         }
         h3_commit(c.accum_bar);
-        H3_STAMP(sb + 1);
+        if (issuer == 0) H3_STAMP(sb + 1);
       }
       __syncwarp();
     }
@@ -336,7 +344,7 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
       const int fl = (t == 0 ? 0 : L.Fc - 128) + m;                 // feature inside the CTA's slice
       const int f = static_cast<int>(c.crank) * L.Fc + fl;          // output feature of the Linear
       const float bias = L.bias2 ? add_(L.bias[f], L.bias2[f]) : L.bias[f];
-      const uint32_t tbase = c.tmem + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(t * (nseg + 1) * ncol);
+      const uint32_t tbase = c.tmem + (static_cast<uint32_t>(32 * q) << 16) + static_cast<uint32_t>(t * (nseg + 2) * ncol);
 #pragma unroll 1
       for (int cb = h; cb < (ncol >> 5); cb += 2) {
         const int colb = 32 * cb;                                   // column inside the accumulators
@@ -345,7 +353,10 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
         float acc[32];
         h3_tmem_ld32(tbase + static_cast<uint32_t>(nseg * ncol + colb), u);             // cross terms first (smallest)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(u[i]) * (1.0f / 2048.0f);
+        for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(u[i]);
+        h3_tmem_ld32(tbase + static_cast<uint32_t>((nseg + 1) * ncol + colb), u);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = (acc[i] + __uint_as_float(u[i])) * (1.0f / 2048.0f);
         for (int sgm = nseg - 1; sgm >= 0; --sgm) {
           h3_tmem_ld32(tbase + static_cast<uint32_t>(sgm * ncol + colb), u);
 #pragma unroll
@@ -616,7 +627,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
 
   if (tid == 0) {
     for (int i = 0; i < H3_NST; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
-    mbar_init(&accum_bar, 1);
+    mbar_init(&accum_bar, 2);                     // both MMA issuers commit
     fence_barrier_init();
   }
   if (warp == H3_WARP_MMA) {
@@ -936,10 +947,11 @@ int h3_plan_layer(int K, int N, int nctas, int ncol, H3LayerPlan& y) {
   y.K = K; y.N = N; y.Fc = Fc; y.T = T; y.KCH = KCH; y.nch = K / KCH; y.nctas = nctas;
   // the accumulate of tcgen05.mma truncates: at most ~12 k-steps of 16 go into one accumulator
   int nseg = (K / 16 + 11) / 12;
-  const int fit = 512 / (T * ncol) - 1;
+  const int fit = 512 / (T * ncol) - 2;                     // + one cross-term accumulator per MMA issuer
+  if (nseg < 2) nseg = 2;                                   // each issuer needs a main accumulator of its own
   if (nseg > fit) nseg = fit;
   if (nseg > y.nch) nseg = y.nch;
-  if (nseg < 1) return ODEVIO_E_SHAPE;
+  if (nseg < 2) return ODEVIO_E_SHAPE;
   y.nseg = nseg;
   return 0;
 }
