@@ -362,10 +362,17 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(u[i]);
         }
+        if (act == ACT_TANH) {
+          // inlined: the out-of-line apply_act4 call per 4 elements was a scheduling barrier between the 32 tanh chains and
+          // the image stores (measured: 2.8 k of the epilogue's 6.7 k clk in the activation, 2.5 k in the stores)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 a4 = apply_act4(make_float4(acc[4 * i] + bias, acc[4 * i + 1] + bias, acc[4 * i + 2] + bias, acc[4 * i + 3] + bias), act);
-          acc[4 * i] = a4.x; acc[4 * i + 1] = a4.y; acc[4 * i + 2] = a4.z; acc[4 * i + 3] = a4.w;
+          for (int i = 0; i < 32; ++i) acc[i] = tanhf(acc[i] + bias);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 a4 = apply_act4(make_float4(acc[4 * i] + bias, acc[4 * i + 1] + bias, acc[4 * i + 2] + bias, acc[4 * i + 3] + bias), act);
+            acc[4 * i] = a4.x; acc[4 * i + 1] = a4.y; acc[4 * i + 2] = a4.z; acc[4 * i + 3] = a4.w;
+          }
         }
         if (cl.out) {
           float4* dst = reinterpret_cast<float4*>(cl.out + static_cast<size_t>(f) * NR + col);
