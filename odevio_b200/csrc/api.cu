@@ -204,7 +204,12 @@ int plan_odernn(const odevio_odernn_cfg& c, OdePlan& pl) {
     if (c.endpoint_dense) return ODEVIO_E_ENUM;
     if (c.ckpt_loops < 0 || c.ckpt_loops > 4096) return ODEVIO_E_SHAPE;
     if (rt == 16) return ODEVIO_E_SHAPE;
-    if (rt == 0) rt = fit(8) ? 8 : 4;
+    if (rt == 0) {
+      // 4-sequence tiles when 8-sequence ones would leave half of the SMs idle (a rank of the 8-GPU training step holds
+      // 512 sequences = 64 tiles of 8): the step time of a single wave is the per-tile latency, which grows with the rows
+      rt = fit(8) ? 8 : 4;
+      if (rt == 8 && 2 * ((c.B + 7) / 8) <= nsm && (4 * c.L) % 8 == 0 && fit(4)) rt = 4;
+    }
   }
   if (rt == 0) {
     // Tile height: 16-row tiles amortise the weight stream better (~1.6x the time of an 8-row
