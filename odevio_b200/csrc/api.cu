@@ -151,8 +151,9 @@ int plan_odernn(const odevio_odernn_cfg& c, OdePlan& pl) {
   if (c.solver < 0 || c.solver > ODEVIO_SOLVER_RK4_38) return ODEVIO_E_ENUM;
   if (c.precision != ODEVIO_PRECISION_FP32 && c.precision != ODEVIO_PRECISION_TF32X3 && c.precision != ODEVIO_PRECISION_FP16X3)
     return ODEVIO_E_ENUM;
-  // tensor-core solvers (odernn_tc.cu, odernn_h3.cu): inference, end point rule y1, no step trace
-  if (c.precision != ODEVIO_PRECISION_FP32 && (c.save_checkpoints || c.endpoint_dense || c.trace_steps)) return ODEVIO_E_ENUM;
+  // tensor-core solvers (odernn_tc.cu, odernn_h3.cu): end point rule y1, no step trace.  Training (save_checkpoints): the
+  // one-launch FP16X3 forward writes the checkpoints itself; every other combination runs the FMA forward.
+  if (c.precision != ODEVIO_PRECISION_FP32 && !c.save_checkpoints && (c.endpoint_dense || c.trace_steps)) return ODEVIO_E_ENUM;
   if (c.rows_per_tile != 0 && c.rows_per_tile != 4 && c.rows_per_tile != 8 && c.rows_per_tile != 16) return ODEVIO_E_SHAPE;
   const bool fixed = c.solver == ODEVIO_SOLVER_RK4 || c.solver == ODEVIO_SOLVER_RK4_38;
   if (fixed && c.substeps < 1) return ODEVIO_E_SHAPE;
@@ -515,7 +516,13 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
   if (!cfg || !w || !ts || !hT || !workspace) return ODEVIO_E_NULL;
   if (!cfg->evolve_only && (!fv || !pose)) return ODEVIO_E_NULL;
   if (cfg->save_checkpoints && (!ckpt || cfg->evolve_only)) return ODEVIO_E_NULL;
-  const odevio_odernn_cfg& c = *cfg;
+  odevio_odernn_cfg c = *cfg;
+  // training forward: on tcgen05 when the one-launch kernel covers the configuration (tanh rnn, L <= 2, fusion applied by
+  // the host), else the FMA kernel -- the checkpoint layout is the same, the backward does not care who wrote it
+  if (c.save_checkpoints && c.precision != ODEVIO_PRECISION_FP32 &&
+      !(c.precision == ODEVIO_PRECISION_FP16X3 && odernn_h3_can_fuse_jump(c) && !w->fuse_w && !w->fuse_b && !c.trace_steps &&
+        !c.endpoint_dense))
+    c.precision = ODEVIO_PRECISION_FP32;
   OdePlan pl;
   const int rc = plan_odernn(c, pl);
   if (rc != 0) return rc;
@@ -552,6 +559,9 @@ int32_t odevio_odernn_forward(const odevio_odernn_cfg* cfg, const odevio_odernn_
                                h_bytes, stream);
     if (prc != 0) return prc;
     if (status) ODEVIO_CUDA_TRY(cudaMemsetAsync(status, 0, static_cast<size_t>(c.B) * sizeof(int32_t), stream));
+    if (c.save_checkpoints)
+      h3.set_checkpoints(reinterpret_cast<float*>(static_cast<unsigned char*>(ckpt) + pl.ckpt_head_bytes), static_cast<int*>(ckpt),
+                         pl.ckpt_floats_per_tile, pl.CK, pl.RT, pl.ntiles, c.S);
     return h3.run(h0, hT, ts, c.S + 1, 0, c.S, fv, fi, Dv, c.S, pose, stats, status, stream);
   }
 

@@ -116,6 +116,9 @@ struct H3Params {
   const float* reg_w1; const float* reg_b1;         // regressor.2: [6][128], [6]
   float* pose;               // [B][S_io][6]
   int* stats; int* status;
+  // training: checkpoints for odevio_odernn_backward in the FMA kernels' layout (odernn_params.h: per tile of RTf sequences
+  // and interval [Yend | Ypost | CK x (Y0 | dt[R] | upd[R])], T-layout [d][R], R = RTf * L, row r = l * RTf + m); nullptr: none
+  float* ckpt; int* nloops; size_t ckpt_floats_per_tile; int CK, RTf, ntiles_f, S_total;
 };
 
 template <int NR>
@@ -123,6 +126,8 @@ struct H3Rows {      // per-row solver state, replicated in every CTA of the clu
   __align__(16) float dt[NR];
   float t[NR], tend[NR], tmin[NR], tmax[NR];
   int run[NR], upd[NR], nsteps[NR], nacc[NR], status[NR];
+  float dtstep[NR];                   // the step size the current iteration was taken with (checkpoints)
+  int nsaved[NR / 4];                 // stored solver iterations of every checkpoint sub-tile in the current interval
   long long grow[NR];                 // state row of the tile's row (-1: beyond M)
   int bidx[NR], lyr[NR];
   float psum[H3_EPI_WARPS][NR];
@@ -617,6 +622,63 @@ __device__ __forceinline__ void h3_jump_input(const H3Params& p, const H3Rows<NR
   }
 }
 
+// Checkpoints (training): the 64-row tile is nsub = SPT / RTf sub-tiles of the FMA kernels' geometry (RTf sequences x L
+// layers, T-layout [d][R] with r = l * RTf + m).  Copies the CTA's feature slice of Yc into the slot of every sub-tile whose
+// bit is set in `mask`: stored iteration slot_of[u] (slot_of != nullptr) or the fixed array `fixed_idx` (0 = Yend, 1 = Ypost).
+template <int NR>
+__device__ __forceinline__ void h3_ckpt_copy(const H3Params& p, int tile, int interval, const float* Yc, int own_f0, int own_nf, int tid,
+                                             unsigned mask, const int* slot_of, int fixed_idx) {
+  const int RTf = p.RTf, nsub = p.SPT / RTf, R = RTf * p.L;
+  const size_t arr = static_cast<size_t>(p.D) * R, ivf = ckpt_interval_floats(p.D, R, p.CK);
+  const int pieces = RTf / 4;                                 // float4 pieces of one (feature, layer, sub-tile) run of rows
+  const int ntask = own_nf * p.L * nsub * pieces;
+  for (int task = tid; task < ntask; task += H3_EPI_THREADS) {
+    int r = task;
+    const int pc = r % pieces; r /= pieces;
+    const int u = r % nsub; r /= nsub;
+    const int l = r % p.L; r /= p.L;
+    const int d = own_f0 + r;
+    const int tf = tile * nsub + u;
+    if (!((mask >> u) & 1u) || tf >= p.ntiles_f) continue;
+    const float4 v = h3_ld4(Yc + static_cast<size_t>(d) * NR + l * p.SPT + u * RTf + 4 * pc);
+    float* dst = p.ckpt + static_cast<size_t>(tf) * p.ckpt_floats_per_tile + static_cast<size_t>(interval) * ivf +
+                 (slot_of ? 2 * arr + static_cast<size_t>(slot_of[u]) * (arr + 2 * R) : static_cast<size_t>(fixed_idx) * arr);
+    *reinterpret_cast<float4*>(dst + static_cast<size_t>(d) * R + l * RTf + 4 * pc) = v;
+  }
+}
+
+// One solver iteration's record (odernn_fwd.cu:PH_STEP_END): for every sub-tile with an accepted row, the state the iteration
+// started from (Yc before the commit), the step sizes it used and the accept flags.  Called by ALL threads of the CTA after
+// the controller's __syncthreads; ends with a __syncthreads.
+template <int NR>
+__device__ __forceinline__ void h3_ckpt_iteration(const H3Params& p, H3Rows<NR>& rs, int tile, int interval, const float* Yc, int own_f0,
+                                                  int own_nf, uint32_t crank) {
+  const int tid = threadIdx.x;
+  const int RTf = p.RTf, nsub = p.SPT / RTf, R = RTf * p.L;
+  unsigned mask = 0;
+  for (int u = 0; u < nsub; ++u) {
+    int any = 0;
+    for (int l = 0; l < p.L; ++l)
+      for (int m = 0; m < RTf; ++m) any |= rs.upd[l * p.SPT + u * RTf + m];
+    if (any && rs.nsaved[u] < p.CK) mask |= 1u << u;
+    else if (any && tid < NR && (tid % p.SPT) / RTf == u) rs.status[tid] = max(rs.status[tid], 3);      // checkpoint overflow
+  }
+  if (tid < H3_EPI_THREADS) h3_ckpt_copy<NR>(p, tile, interval, Yc, own_f0, own_nf, tid, mask, rs.nsaved, 0);
+  if (crank == 0 && tid < NR && rs.grow[tid] >= 0) {
+    const int l = tid / p.SPT, j = tid - l * p.SPT, u = j / RTf, m = j - u * RTf, tf = tile * nsub + u;
+    if (((mask >> u) & 1u) && tf < p.ntiles_f) {
+      const size_t arr = static_cast<size_t>(p.D) * R;
+      float* slot = p.ckpt + static_cast<size_t>(tf) * p.ckpt_floats_per_tile + static_cast<size_t>(interval) * ckpt_interval_floats(p.D, R, p.CK) +
+                    2 * arr + static_cast<size_t>(rs.nsaved[u]) * (arr + 2 * R);
+      slot[arr + l * RTf + m] = rs.dtstep[tid];
+      reinterpret_cast<int*>(slot + arr + R)[l * RTf + m] = rs.upd[tid];
+    }
+  }
+  __syncthreads();
+  if (tid < nsub && ((mask >> tid) & 1u)) rs.nsaved[tid] += 1;
+  __syncthreads();
+}
+
 template <int NR>
 __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_constant__ H3Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -716,6 +778,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
           run = valid ? 1 : 0;
         }
         rs.run[r] = run;
+        if (r < NR / 4) rs.nsaved[r] = 0;
       }
       int any_running = __syncthreads_or(run);
       int loops = 0;
@@ -812,15 +875,22 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
             float dtn = run ? dt_next : dt;
             dtn = fminf(fmaxf(dtn, sub_(rs.tmin[r], t)), sub_(rs.tmax[r], t));
             rs.t[r] = t;
+            rs.dtstep[r] = dt;
             rs.dt[r] = dtn;
             rs.run[r] = run;
           }
           any_running = __syncthreads_or(run);
+          if (p.ckpt) h3_ckpt_iteration<NR>(p, rs, tile, interval, Yc, own_f0, own_nf, crank);
           if (tid == 0) H3_STAMP(8);
           // ---- commit: accepted rows take y1; FSAL carry (end point rule "y1": exact landing makes y1 the value at t_end)
           if (epi) h3_commit_rows<NR>(sl, ns, tb.fsal, rs.upd);
           if (tid == 0) H3_STAMP(9);
         } else {
+          if (p.ckpt) {
+            if (tid < NR) { rs.dtstep[tid] = rs.dt[tid]; rs.upd[tid] = rs.grow[tid] >= 0 ? 1 : 0; }
+            __syncthreads();
+            h3_ckpt_iteration<NR>(p, rs, tile, interval, Yc, own_f0, own_nf, crank);
+          }
           if (epi) {
             H3_DISPATCH_STAGES(ns, (h3_fixed_commit<NSV, NR>(sl, tb, rs.dt)))
             if (tid < NR && rs.grow[tid] >= 0) { rs.nsteps[tid] += 1; rs.nacc[tid] += 1; }
@@ -842,6 +912,13 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
         if (p.status && rs.status[tid]) atomicMax(p.status + rs.bidx[tid], rs.status[tid]);
       }
 
+      if (p.ckpt) {
+        // state at the end of the interval's solves + the number of stored iterations of every sub-tile
+        if (epi) h3_ckpt_copy<NR>(p, tile, interval, Yc, own_f0, own_nf, tid, 0xffffffffu, nullptr, 0);
+        const int nsub = p.SPT / p.RTf;
+        if (crank == 0 && tid < nsub && tile * nsub + tid < p.ntiles_f)
+          p.nloops[static_cast<size_t>(tile * nsub + tid) * p.S_total + interval] = rs.nsaved[tid];
+      }
       if (p.do_jump) {
         // ---- rnn jump at the observation (PoseODERNN.py:112-117) and pose head (:119-122), all on this cluster
         if (epi) {
@@ -862,6 +939,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
           cl.xdst_kshift = top ? kshh : kshj; cl.xdst_colshift = top ? 0 : ncolj;
           h3_layer<NR>(c, p.jump[l], top ? &p.head : &p.jump[l + 1], cl, 0);
         }
+        if (p.ckpt && epi) h3_ckpt_copy<NR>(p, tile, interval, Yc, own_f0, own_nf, tid, 0xffffffffu, nullptr, 1);      // post-jump state
         {
           H3Call cl;
           cl.xsrc = xa0; cl.col0 = (p.L - 1) * ncolj; cl.ncol = ncolj;
@@ -1158,6 +1236,13 @@ int H3Evolve::max_clusters() {
   return maxc;
 }
 
+void H3Evolve::set_checkpoints(float* ckpt, int* nloops, size_t ckpt_floats_per_tile, int CK, int RTf, int ntiles_f, int S_total) {
+  if (!impl) return;
+  H3Params& p = impl->prm;
+  p.ckpt = ckpt; p.nloops = nloops; p.ckpt_floats_per_tile = ckpt_floats_per_tile; p.CK = CK; p.RTf = RTf; p.ntiles_f = ntiles_f;
+  p.S_total = S_total;
+}
+
 int H3Evolve::run(const float* h0, float* hT, const float* ts, int ts_ld, int interval0, int n_intervals, const float* fv,
                   const float* fi, int Dv, int S_io, float* pose, int* stats, int* status, cudaStream_t stream) {
   if (!impl) return ODEVIO_E_NULL;
@@ -1165,6 +1250,7 @@ int H3Evolve::run(const float* h0, float* hT, const float* ts, int ts_ld, int in
   H3Plan& pl = impl->pl;
   if (!hT || !ts || n_intervals < 1) return ODEVIO_E_NULL;
   if (p.do_jump && (!fv || !pose || Dv <= 0 || Dv > p.D || (Dv < p.D && !fi))) return ODEVIO_E_NULL;
+  if (p.ckpt && (p.SPT == 0 || p.RTf < 4 || p.RTf % 4 || p.SPT % p.RTf || p.SPT / p.RTf > 64 / 4)) return ODEVIO_E_SHAPE;
   p.h0 = h0; p.hT = hT; p.ts = ts; p.ts_ld = ts_ld; p.interval0 = interval0; p.nI = n_intervals;
   p.fv = fv; p.fi = fi; p.Dv = Dv; p.S_io = S_io; p.pose = pose; p.stats = stats; p.status = status;
   int nclusters = max_clusters();

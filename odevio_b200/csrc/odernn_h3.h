@@ -36,6 +36,9 @@ class H3Evolve {
   int prepare(const odevio_odernn_cfg& c, const DevTableau& tab, bool adaptive, const odevio_odernn_weights* w, bool with_jump,
               bool pack_weights, void* workspace, size_t workspace_bytes, cudaStream_t stream);
   int max_clusters();       // clusters of 4 CTAs that can be co-resident (cudaOccupancyMaxActiveClusters)
+  // Training: the following run() also writes the checkpoints odevio_odernn_backward replays, in the FMA kernels' layout
+  // (odernn_params.h) for tiles of RTf sequences (RTf = 4 or 8 divides 64 / L); nloops: [ntiles_f][S_total] stored iterations.
+  void set_checkpoints(float* ckpt, int* nloops, size_t ckpt_floats_per_tile, int CK, int RTf, int ntiles_f, int S_total);
   // Integrates the intervals [interval0, interval0 + n_intervals) of all L * B rows: state from h0 ([L][B][D]; nullptr =
   // zeros; may alias hT) to hT; with_jump: after every interval the rnn jump on the features fv / fi ([B][S_io][Dv],
   // [B][S_io][D - Dv]) and the pose head -> pose [B][S_io][6].

@@ -401,7 +401,10 @@ class PoseODERNN(nn.Module):
         cfg = self._cfg(B, S)
         ckpt, ckpt_bytes = None, 0
         if save_ckpt:
-            cfg.precision = _lib.PRECISION["fp32"]          # training runs the FMA kernels (checkpointed forward + fused backward)
+            # training: "fp16x3" keeps the checkpointed forward on tcgen05 (one launch; the library falls back to the FMA
+            # forward for GRU / L > 2), the fused backward is the FMA kernel either way; "tf32x3" has no training forward
+            if cfg.precision == _lib.PRECISION["tf32x3"] or self.endpoint == "dense":
+                cfg.precision = _lib.PRECISION["fp32"]
             cfg.save_checkpoints = 1
             cfg.ckpt_loops = self.ckpt_loops
             if cfg.rows_per_tile == 16:

@@ -133,3 +133,20 @@ def test_backward_shipped_run_config(cuda_device):
     """The reference's shipped ODE-RNN run (scripts/run_training.sh:9-24): L=3, H=1024, n=2, soft fusion."""
     _compare(cuda_device, 5, 2, tol=2 * GRAD_RTOL, rnn_num_layers=3, ode_hidden_dim=1024, ode_fn_num_layers=2,
              fuse_method="soft")
+
+
+@pytest.mark.parametrize("over", [
+    dict(ode_solver="rk4"), dict(ode_solver="dopri5", ode_rtol=1e-3), dict(ode_solver="tsit5"),
+    dict(ode_solver="dopri5", rnn_num_layers=1), dict(ode_solver="dopri5", ode_rows_per_tile=4),
+    dict(ode_solver="dopri5", fuse_method="soft"),
+])
+def test_backward_with_tcgen05_forward(cuda_device, over):
+    """Training with ode_precision="fp16x3": the checkpointed forward is the one-launch tcgen05 kernel (odernn_h3.cu), which
+    writes the checkpoints in the FMA kernels' layout; the fused backward replays them.  Same gradient criterion."""
+    tol = 2 * GRAD_RTOL if over.get("fuse_method") == "soft" else GRAD_RTOL
+    _compare(cuda_device, 11, 3, ode_precision="fp16x3", tol=tol, **over)
+    _compare(cuda_device, 70, 2, prev=True, hT_weight=0.5, ode_precision="fp16x3", tol=tol, **over)
+
+
+def test_backward_fp16x3_gru_falls_back_to_the_fma_forward(cuda_device):
+    _compare(cuda_device, 6, 2, ode_precision="fp16x3", ode_rnn_type="gru")
