@@ -540,7 +540,8 @@ class PoseCDE(nn.Module):
     Optional ``opt`` attributes (reference values are the defaults): ``cde_interp`` "linear"
     (rectilinear, integrated over batch row 0's times in seconds) | "cubic" (north_star: Hermite
     cubics with backward differences, integrated over the knot grid), ``cde_atol`` 1e-6,
-    ``cde_rtol`` 1e-4 (PoseCDE.py:101), ``cde_step_size`` (fixed-grid rk4), ``cde_max_steps``,
+    ``cde_rtol`` 1e-4 (PoseCDE.py:101), ``cde_step_size`` (fixed-grid rk4), ``cde_max_steps``, ``cde_history_limit``
+    (cubic mode: eval-mode history bounded to that many observations, same poses; default: the reference's unbounded growth),
     ``cde_rows_per_tile``.  The reference's ``adjoint`` flag only changes how gradients are computed;
     the fused backward for the CDE path is not built yet, so ``forward`` under autograd raises.
     """
@@ -576,6 +577,7 @@ class PoseCDE(nn.Module):
         self.step_size = getattr(opt, "cde_step_size", None)
         self.max_steps = int(getattr(opt, "cde_max_steps", 100000))
         self.rows_per_tile = int(getattr(opt, "cde_rows_per_tile", 0))
+        self.history_limit = getattr(opt, "cde_history_limit", None)     # cubic mode: observations kept across windows
         self.history = None          # (tobs [B,n], fv [B,n,.], fi [B,n,.] | None) in eval mode
         self.last_stats = None       # int32 [4]: n_steps, n_accepted, n_f_evals, status
         self.last_hidden = None      # [B,S,Hc]
@@ -614,6 +616,17 @@ class PoseCDE(nn.Module):
                 tobs = torch.cat([h_t, tobs], 1).contiguous()
                 fvc = torch.cat([h_v, fvc], 1).contiguous()
                 fic = None if fic is None else torch.cat([h_i, fic], 1).contiguous()
+            lim = self.history_limit
+            if lim and self.interp == "cubic" and tobs.shape[1] > max(lim, S + 1):
+                # Bounded history.  The reference lets `history` grow without bound (PoseCDE.py:88-92)
+                # although the window's solve only reads the path on [knot n - S, knot n - 1]: the Hermite cubic with backward
+                # differences needs one observation before the window and nothing older, so keeping the last
+                # max(limit, S + 1) observations leaves the poses unchanged (tests/test_cde_gpu.py).  Not offered for the
+                # reference's rectilinear path: it is integrated over ABSOLUTE seconds on an integer knot grid, so its
+                # result depends on how many knots precede the window.
+                keep_n = max(lim, S + 1)
+                tobs, fvc = tobs[:, -keep_n:].contiguous(), fvc[:, -keep_n:].contiguous()
+                fic = None if fic is None else fic[:, -keep_n:].contiguous()
             self.history = (tobs, fvc, fic)
         else:
             self.history = None

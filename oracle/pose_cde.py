@@ -50,6 +50,8 @@ class OraclePoseCDE(nn.Module):
         self.atol = getattr(opt, "cde_atol", 1e-6)
         self.rtol = getattr(opt, "cde_rtol", 1e-4)
         self.step_size = getattr(opt, "cde_step_size", None)
+        # restatement of odevio_b200.PoseCDE's bounded history (cubic mode only; None = the reference's unbounded growth)
+        self.history_limit = getattr(opt, "cde_history_limit", None)
         self.history = None
         self.last_stats = None
         self.vf_noise = None          # tests: (eps, torch.Generator) -> k <- k * (1 + eps * N(0,1)), conditioning probe
@@ -61,6 +63,8 @@ class OraclePoseCDE(nn.Module):
         obs = x
         if not self.training:                                           # PoseCDE.py:88-92
             self.history = torch.cat([self.history, x], dim=1) if prev is not None else x
+            if self.history_limit and self.interp == "cubic" and self.history.shape[1] > max(self.history_limit, x.shape[1] + 1):
+                self.history = self.history[:, -max(self.history_limit, x.shape[1] + 1):]
             obs = self.history
         else:
             self.history = None

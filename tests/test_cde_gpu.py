@@ -229,3 +229,27 @@ def test_training_raises(cuda_device):
     fv, fi, ts = data(4, 4, 32, False)
     with pytest.raises(odevio_b200.OdevioError):
         mod(fv.to(cuda_device), fi.to(cuda_device), ts.to(cuda_device))
+
+
+def test_bounded_history_windows_match_unbounded_oracle(cuda_device):
+    """f2: chained eval-mode windows with `cde_history_limit` -- the module keeps max(limit, S + 1)
+    observations instead of the reference's ever-growing history (PoseCDE.py:88-92) -- against the ORACLE running the
+    reference's unbounded history.  Cubic mode; the two paths are the same function, the solutions agree within the solver
+    tolerance (the knot index of the unbounded run loses ulp(t) of the in-segment parameter: tests/test_oracle_cde.py)."""
+    ref, mod = make_pair(cuda_device, Hc=32, cde_fn_num_layers=2, cde_interp="cubic", train=False, cde_history_limit=1)
+    ref.history_limit = None                      # the oracle keeps everything, as the reference does
+    ref.eval(); mod.eval()
+    g = torch.Generator().manual_seed(5)
+    B, S = 9, 5
+    t0 = torch.zeros(B, 1)
+    hc_ref = hc = None
+    for w in range(4):
+        fv, fi = 0.2 * torch.randn(B, S, 16, generator=g), 0.2 * torch.randn(B, S, 16, generator=g)
+        ts = torch.cat([t0, t0 + torch.cumsum(0.1 + 0.1 * torch.rand(B, S, generator=g), 1)], 1)
+        t0 = ts[:, -1:]
+        with torch.no_grad():
+            p_ref, hc_ref = ref(fv, fi, ts, prev=hc_ref)
+            p, hc = mod(fv.to(cuda_device), fi.to(cuda_device), ts.to(cuda_device), prev=hc)
+        mod.check_status()
+        assert ref.history.shape[1] == (w + 1) * S and mod.history[0].shape[1] == min((w + 1) * S, S + 1)
+        assert rel_err(p.cpu(), p_ref) <= 2e-4, (w, rel_err(p.cpu(), p_ref))

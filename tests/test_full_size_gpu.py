@@ -113,3 +113,26 @@ def test_config4_full_batch_gradient_rows_match_oracle_subset(cuda_device):
     _, _, _, g2 = run(B // 2, B)
     for n in g_all:
         assert rel_err(0.5 * (g1[n] + g2[n]), g_all[n]) <= 2e-5, n
+
+
+def test_streaming_windows_match_oracle(cuda_device):
+    """The streaming driver against the ORACLE (not the kernel against itself): three chained windows with the carried
+    state and absolute timestamps, trajectories that restart mid-stream (`reset(rows)`), fp16x3 one-launch kernel."""
+    from odevio_b200.streaming import StreamingPoseODERNN
+    from helpers import POSE_RTOL, rel_err
+    ref, mod = make_pair(cuda_device, bias_std=0.05, ode_solver="dopri5", ode_rtol=1e-3, ode_precision="fp16x3")
+    B, W = 12, 4
+    fv, fi, ts = inputs(B, 3 * W, irregular=True, seed=6, offset=3.0)
+    stream = StreamingPoseODERNN(mod)
+    state_ref = None
+    for k in range(3):
+        a, b = k * W, (k + 1) * W
+        if k == 2:                                   # trajectories 0 and 5 restart: zero state, like a fresh sequence
+            stream.reset([0, 5])
+            state_ref[:, [0, 5]] = 0.0
+        with torch.no_grad():
+            p_ref, state_ref = ref(fv[:, a:b], fi[:, a:b], ts[:, a:b + 1], prev=state_ref)
+        p = stream.step(fv[:, a:b].contiguous().to(cuda_device), fi[:, a:b].contiguous().to(cuda_device),
+                        ts[:, a:b + 1].contiguous().to(cuda_device))
+        assert rel_err(p.cpu(), p_ref) <= 4 * POSE_RTOL, (k, rel_err(p.cpu(), p_ref))
+        assert rel_err(stream.state.cpu(), state_ref) <= 2e-4

@@ -141,3 +141,43 @@ def test_pose_cde_reference_quirks():
         assert m.history.shape == (3, 4, 17) and torch.equal(m.history[:, :, 0], ts[:, 1:])
         m(fv, fi, ts + 0.4, prev=z0)
         assert m.history.shape == (3, 8, 17)
+
+
+def test_bounded_history_leaves_the_cubic_path_unchanged():
+    """odevio_b200.PoseCDE's `cde_history_limit` restated in the oracle: in cubic mode a window's solve reads the control path
+    on its own knots only (Hermite cubics with backward differences: one observation before the window), so truncating
+    the eval-mode history (reference PoseCDE.py:88-92 grows it without bound) must not change the poses."""
+    import copy
+    from oracle.modules import deepvio_initialization
+    from oracle.pose_cde import OraclePoseCDE
+    from oracle.pose_odernn import default_opt
+    opt = default_opt(v_f_len=8, i_f_len=8, cde_hidden_dim=16, cde_fn_num_layers=2, cde_interp="cubic")
+    torch.manual_seed(0)
+    full = OraclePoseCDE(opt)
+    deepvio_initialization(full)
+    full.eval()
+    lim_opt = copy.copy(opt)
+    lim_opt.cde_history_limit = 1                      # floor: window length + 1
+    lim = OraclePoseCDE(lim_opt)
+    lim.load_state_dict(full.state_dict())
+    lim.eval()
+    # In exact arithmetic the two are the same path; in floating point the knot index t loses ulp(t) of the in-segment
+    # parameter s = t - floor(t), so the adaptive steps differ at rounding level and the solutions within the solver
+    # tolerance (rtol 1e-4).  fp64: identical to 1e-9; fp32: within 2e-4 -- and the UNBOUNDED history is the less
+    # accurate of the two as the knot index grows (ulp(1000) = 6e-5 in fp32).
+    for dtype, tol in ((torch.float64, 1e-9), (torch.float32, 2e-4)):
+        a, b = copy.deepcopy(full).to(dtype), copy.deepcopy(lim).to(dtype)
+        g = torch.Generator().manual_seed(1)
+        B, S = 3, 4
+        t0 = torch.zeros(B, 1, dtype=dtype)
+        hc_a = hc_b = None
+        for w in range(4):
+            fv = (0.2 * torch.randn(B, S, 8, generator=g)).to(dtype)
+            fi = (0.2 * torch.randn(B, S, 8, generator=g)).to(dtype)
+            ts = torch.cat([t0, t0 + torch.cumsum(0.1 + 0.1 * torch.rand(B, S, generator=g), 1).to(dtype)], 1)
+            t0 = ts[:, -1:]
+            with torch.no_grad():
+                pa, hc_a = a(fv, fi, ts, prev=hc_a)
+                pb, hc_b = b(fv, fi, ts, prev=hc_b)
+            assert a.history.shape[1] == (w + 1) * S and b.history.shape[1] == min((w + 1) * S, S + 1)
+            assert ((pa - pb).abs().max() / pa.abs().max()).item() <= tol, (dtype, w)
