@@ -14,6 +14,8 @@
  *                              + regressor head              src/models/PoseODERNN.py:64-68,122
  *   odevio_odernn_backward     loss.backward() through the above (to.AutoDiffAdjoint is plain
  *                              autograd = discretise-then-optimise)  scripts/train_model.py:78
+ *   odevio_cde_backward        loss.backward() through PoseCDE.forward (cdeint adjoint=False = plain autograd through
+ *                              torchdiffeq's loop)           src/models/PoseCDE.py:98-101, scripts/train_model.py:78
  *   odevio_cde_forward         PoseCDE.forward               src/models/PoseCDE.py:76-103
  *                              + torchcde linear_interpolation_coeffs / LinearInterpolation / cdeint
  *                                (call sites src/models/PoseCDE.py:94-101)
@@ -39,7 +41,7 @@
 extern "C" {
 #endif
 
-#define ODEVIO_ABI_VERSION 3
+#define ODEVIO_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define ODEVIO_API __attribute__((visibility("default")))
@@ -288,6 +290,53 @@ ODEVIO_API int32_t odevio_cde_forward(const odevio_cde_cfg* cfg, const odevio_cd
                                       const double* tout, const float* z0_in,
                                       float* pose, float* z0_out, float* hidden, int32_t* stats,
                                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gradients of the PoseCDE parameters, PyTorch shapes (same members as odevio_cde_weights). */
+typedef struct odevio_cde_grads {
+  float* cde_w[ODEVIO_MAX_ODE_LINEARS];
+  float* cde_b[ODEVIO_MAX_ODE_LINEARS];
+  float* init_w;
+  float* init_b;
+  float* reg_w0;
+  float* reg_b0;
+  float* reg_w1;
+  float* reg_b1;
+} odevio_cde_grads;
+
+/*
+ * Training (reference src/models/PoseCDE.py:98-101 `cdeint(..., adjoint=False)` + scripts/train_model.py:78
+ * `loss.backward()`): plain autograd through torchdiffeq's solver loop = discretise-then-optimise with the accepted step
+ * sizes as constants.  odevio_cde_forward_ckpt is odevio_cde_forward that also leaves, for each of up to `ckpt_steps`
+ * accepted solver steps, the stage values and a log entry in `ckpt` (odevio_cde_ckpt_bytes(cfg, ckpt_steps) bytes;
+ * stats[3] = ODEVIO_STATUS_CKPT_OVERFLOW when the solve accepted more steps than that).  The log starts with
+ * int32 {n_accepted, n_pullbacks, status}; entry s (48 bytes, at byte 48 * (1 + s)) holds at int32 index 10 the number of
+ * vector-field pullbacks of all earlier steps -- the caller copies those n_accepted + 1 prefix counts to the HOST
+ * (`vjp_base`, last = n_pullbacks) and hands them to odevio_cde_backward, which walks the log backwards in chunks of at most
+ * `chunk_vjps` pullbacks per launch (that bounds the record streams of the deferred weight-gradient GEMMs:
+ * odevio_cde_backward_workspace_bytes(cfg, chunk_vjps)).
+ *   hidden [B,S,Hc], z0 [B,Hc]      outputs of the forward
+ *   has_prev                        the forward ran from z0_in (grad_prev [B,Hc] receives its gradient) instead of initial()
+ *   grad_pose [B,S,6]               incoming gradient; grad_z0 [B,Hc] or NULL: gradient of the returned z0
+ *   grad_x [B,So,Hc+1] or NULL      ZERO-INITIALISED by the caller; receives d loss / d observations (channel 0, the
+ *                                   timestamps, is left untouched)
+ */
+ODEVIO_API size_t odevio_cde_ckpt_bytes(const odevio_cde_cfg* cfg, int32_t ckpt_steps);
+ODEVIO_API int32_t odevio_cde_forward_ckpt(const odevio_cde_cfg* cfg, const odevio_cde_weights* w,
+                                           const float* tobs, const float* fv, const float* fi, int32_t Dv,
+                                           const double* tout, const float* z0_in,
+                                           float* pose, float* z0_out, float* hidden, int32_t* stats,
+                                           void* ckpt, size_t ckpt_bytes, int32_t ckpt_steps,
+                                           void* workspace, size_t workspace_bytes, void* stream);
+ODEVIO_API size_t odevio_cde_backward_workspace_bytes(const odevio_cde_cfg* cfg, int32_t chunk_vjps);
+ODEVIO_API int32_t odevio_cde_backward(const odevio_cde_cfg* cfg, const odevio_cde_weights* w,
+                                       const float* tobs, const float* fv, const float* fi, int32_t Dv,
+                                       const double* tout, int32_t has_prev, const float* hidden, const float* z0,
+                                       const void* ckpt, size_t ckpt_bytes, int32_t ckpt_steps,
+                                       const int32_t* vjp_base /* HOST [n_accepted + 1] */, int32_t n_accepted,
+                                       int32_t chunk_vjps,
+                                       const float* grad_pose, const float* grad_z0,
+                                       const odevio_cde_grads* g, float* grad_x, float* grad_prev,
+                                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------- ODEFunc.forward (tensor cores) ---- */
 

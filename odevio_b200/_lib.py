@@ -66,6 +66,10 @@ class CdeWeights(C.Structure):
     ]
 
 
+class CdeGrads(C.Structure):
+    _fields_ = CdeWeights._fields_
+
+
 CDE_SOLVER = {"dopri5": 0, "rk4": 1}
 CDE_INTERP = {"linear": 0, "cubic": 1}
 
@@ -83,7 +87,7 @@ class ImuEncoderWeights(C.Structure):
     ]
 
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 
@@ -130,6 +134,19 @@ def load():
     lib.odevio_cde_forward.argtypes = [
         C.POINTER(CdeCfg), C.POINTER(CdeWeights), _FP, _FP, _FP, C.c_int32, _FP, _FP,
         _FP, _FP, _FP, _FP, _FP, C.c_size_t, _FP]
+    lib.odevio_cde_ckpt_bytes.restype = C.c_size_t
+    lib.odevio_cde_ckpt_bytes.argtypes = [C.POINTER(CdeCfg), C.c_int32]
+    lib.odevio_cde_forward_ckpt.restype = C.c_int32
+    lib.odevio_cde_forward_ckpt.argtypes = [
+        C.POINTER(CdeCfg), C.POINTER(CdeWeights), _FP, _FP, _FP, C.c_int32, _FP, _FP,
+        _FP, _FP, _FP, _FP, _FP, C.c_size_t, C.c_int32, _FP, C.c_size_t, _FP]
+    lib.odevio_cde_backward_workspace_bytes.restype = C.c_size_t
+    lib.odevio_cde_backward_workspace_bytes.argtypes = [C.POINTER(CdeCfg), C.c_int32]
+    lib.odevio_cde_backward.restype = C.c_int32
+    lib.odevio_cde_backward.argtypes = [
+        C.POINTER(CdeCfg), C.POINTER(CdeWeights), _FP, _FP, _FP, C.c_int32, _FP, C.c_int32, _FP, _FP,
+        _FP, C.c_size_t, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+        _FP, _FP, C.POINTER(CdeGrads), _FP, _FP, _FP, C.c_size_t, _FP]
     lib.odevio_odefunc_workspace_bytes.restype = C.c_size_t
     lib.odevio_odefunc_workspace_bytes.argtypes = [C.c_int32] * 4
     lib.odevio_odefunc_forward.restype = C.c_int32

@@ -119,3 +119,94 @@ def odernn_apply(module, fvc, fic, Dv, ts_in, h0):
     if ts_in.requires_grad:
         raise _lib.OdevioError("gradients with respect to timestamps are not supported")
     return _OdeRnnFunction.apply(module, Dv, ts_in, fvc, fic, h0, *_param_list(module))
+
+
+class _CdeFunction(torch.autograd.Function):
+    """PoseCDE under autograd: ``odevio_cde_forward_ckpt`` + ``odevio_cde_backward`` (reference
+    src/models/PoseCDE.py:98-101 ``cdeint(adjoint=False)`` + scripts/train_model.py:78)."""
+
+    @staticmethod
+    def forward(ctx, module, Dv, tobs, tout, fvc, fic, z0_in, *params):
+        pose, z0, hidden, stats, (cfg, ckpt, cap) = module._launch(tobs, fvc, fic, Dv, tout, z0_in, save_ckpt=True)
+        module.last_stats = stats
+        # the one host read of the training step: the step log's pullback prefix counts (+ the solver status)
+        log = ckpt[: 48 * (1 + cap)].view(torch.int32).view(1 + cap, 12).cpu()
+        n_acc, n_vjp, status = (int(v) for v in log[0, :3])
+        if status != 0:
+            what = {1: "max_steps reached", 2: "non-finite error norm",
+                    3: f"more accepted solver steps than cde_ckpt_steps={cap} (raise opt.cde_ckpt_steps)"}.get(status, str(status))
+            raise RuntimeError(f"odevio_b200: CDE solve failed: {what}")
+        ctx.vjp_base = [int(v) for v in log[1:1 + n_acc, 10]] + [n_vjp]
+        ctx.n_acc, ctx.cap = n_acc, cap
+        ctx.module, ctx.cfg, ctx.Dv, ctx.ckpt = module, cfg, Dv, ckpt
+        ctx.has_fi, ctx.has_prev = fic is not None, z0_in is not None
+        ctx.save_for_backward(tobs, tout, fvc, hidden, z0, *([fic] if fic is not None else []), *params)
+        ctx.mark_non_differentiable(hidden)
+        ctx.set_materialize_grads(False)
+        return pose, z0, hidden
+
+    @staticmethod
+    def backward(ctx, gpose, gz0, _ghidden):
+        lib = _lib.load()
+        module, cfg = ctx.module, ctx.cfg
+        saved = ctx.saved_tensors
+        tobs, tout, fvc, hidden, z0 = saved[:5]
+        fic = saved[5] if ctx.has_fi else None
+        params = saved[6 if ctx.has_fi else 5:]
+        dev = fvc.device
+        B, S, So, Hc = cfg.B, cfg.S, cfg.So, cfg.Hc
+        n_acc, n_vjp = ctx.n_acc, ctx.vjp_base[-1]
+        # bound the record streams: halve the pullbacks per launch until the workspace fits the budget
+        per_step = max([b - a for a, b in zip(ctx.vjp_base[:-1], ctx.vjp_base[1:])] + [8])
+        chunk = max(n_vjp, per_step)
+        budget = int(module.bwd_record_gb * (1 << 30))
+        with torch.cuda.device(dev):
+            nbytes = lib.odevio_cde_backward_workspace_bytes(C.byref(cfg), chunk)
+            while nbytes > budget and chunk > per_step:
+                chunk = max(per_step, chunk // 2)
+                nbytes = lib.odevio_cde_backward_workspace_bytes(C.byref(cfg), chunk)
+        if nbytes == 0:
+            raise _lib.OdevioError("odevio_cde_backward: unsupported configuration")
+        ws = getattr(module, "_bwd_workspace", None)
+        if ws is None or ws.device != dev or ws.numel() < nbytes:
+            module._bwd_workspace = ws = None
+            module._bwd_workspace = ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        w, keep = module._weight_struct(params)
+        g = _lib.CdeGrads()
+        grads = [torch.zeros_like(p) for p in params]
+        n = cfg.n_layers + 1
+        for j in range(n):
+            g.cde_w[j], g.cde_b[j] = _lib.dptr(grads[2 * j]), _lib.dptr(grads[2 * j + 1])
+        k = 2 * n
+        g.init_w, g.init_b, g.reg_w0, g.reg_b0, g.reg_w1, g.reg_b1 = (_lib.dptr(grads[k + i]) for i in range(6))
+        gpose = (torch.zeros(B, S, 6, dtype=torch.float32, device=dev) if gpose is None else gpose.contiguous().float())
+        gz0_c = None if gz0 is None else gz0.contiguous().float()
+        need_in = ctx.needs_input_grad
+        gx = torch.zeros(B, So, Hc + 1, dtype=torch.float32, device=dev) if (need_in[4] or need_in[5]) else None
+        gprev = torch.zeros(B, Hc, dtype=torch.float32, device=dev) if ctx.has_prev else None
+        base = (C.c_int32 * len(ctx.vjp_base))(*ctx.vjp_base)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = lib.odevio_cde_backward(
+                C.byref(cfg), C.byref(w), _lib.dptr(tobs), _lib.dptr(fvc), _lib.dptr(fic), ctx.Dv, _lib.dptr(tout),
+                1 if ctx.has_prev else 0, _lib.dptr(hidden), _lib.dptr(z0), _lib.dptr(ctx.ckpt), ctx.ckpt.numel(), ctx.cap,
+                base, n_acc, chunk, _lib.dptr(gpose), _lib.dptr(gz0_c), C.byref(g), _lib.dptr(gx), _lib.dptr(gprev),
+                _lib.dptr(ws), ws.numel(), C.c_void_p(stream))
+        _lib.check(rc)
+        del keep
+        gfv = gfi = None
+        if gx is not None:
+            feats = gx[..., 1:]                     # channel 0 is the timestamp
+            if ctx.has_fi:
+                gfv, gfi = feats[..., :ctx.Dv].contiguous(), feats[..., ctx.Dv:].contiguous()
+            else:
+                gfv = feats.contiguous()
+        if ctx.has_prev:                            # initial() was not on the path
+            grads[k] = grads[k + 1] = None
+        return (None, None, None, None, gfv, gfi, gprev if need_in[6] else None, *grads)
+
+
+def cde_apply(module, Dv, tobs, tout, fvc, fic, z0_in):
+    if tobs.requires_grad:
+        raise _lib.OdevioError("gradients with respect to timestamps are not supported")
+    return _CdeFunction.apply(module, Dv, tobs, tout, fvc, fic, z0_in, *module._param_list())

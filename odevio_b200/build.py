@@ -69,19 +69,45 @@ def build_library(force=False, verbose=False, variant=None, defines=()):
     return path
 
 
+def _headers_digest():
+    h = hashlib.sha256()
+    for d in (CSRC, INCLUDE):
+        for f in sorted(os.listdir(d)):
+            if f.endswith((".h", ".cuh")):
+                with open(os.path.join(d, f), "rb") as fh:
+                    h.update(f.encode() + fh.read())
+    return h.hexdigest()
+
+
 def _build(libpath, tag, defines, verbose):
+    """Objects are compiled in parallel and reused when neither their source, any header nor the flags changed."""
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = _nvcc()
-    objs = []
+    hdr = _headers_digest()
     log = []
-    for src in sources():
+
+    def compile_one(src):
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + (f".{tag}" if tag else "") + ".o")
         cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
+        with open(src, "rb") as fh:
+            key = hashlib.sha256(fh.read() + hdr.encode() + " ".join(cmd).encode()).hexdigest()
+        stamp = obj + ".key"
+        if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == key:
+            return obj, "$ (cached) " + obj + "\n", 0
         r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-        if r.returncode != 0:
-            sys.stderr.write(log[-1])
-            raise RuntimeError(f"nvcc failed on {src}")
-        objs.append(obj)
+        if r.returncode == 0:
+            with open(stamp, "w") as fh:
+                fh.write(key)
+        return obj, "$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr, r.returncode
+
+    objs = []
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        for src, (obj, text, rc) in zip(sources(), ex.map(compile_one, sources())):
+            log.append(text)
+            if rc != 0:
+                sys.stderr.write(text)
+                raise RuntimeError(f"nvcc failed on {src}")
+            objs.append(obj)
     cmd = [nvcc, "-shared", "-o", libpath] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)

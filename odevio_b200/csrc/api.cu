@@ -26,6 +26,14 @@ cudaError_t launch_cde_fwd(const CdeParams& prm, const DevTableau& tab, int RT, 
                            size_t smem_bytes, cudaStream_t stream);
 cudaError_t cde_pack_final(const float* W, const float* b, int Hc, int C, int Gc, int ngroups, float* Wp,
                            float* bp, cudaStream_t stream);
+cudaError_t launch_cde_bwd(const CdeBwdParams& prm, const DevTableau& tab, int RT, int LL, int grid,
+                           size_t smem_bytes, cudaStream_t stream);
+cudaError_t cde_pack_final_t(const float* W, int Hc, int C, int Gc, int ngroups, float* WT, cudaStream_t stream);
+cudaError_t cde_unpack_final_grad(const float* dWp, const float* dbp, int Hc, int C, int Gc, float* dW, float* db,
+                                  cudaStream_t stream);
+cudaError_t wgrad_linear_ex(const float* G, int ldg, const float* A, int lda, long long M, int N, int K,
+                            float* dW0, float* dW1, int k_split, float* db0, float* db1, float* part, int nsm,
+                            int accumulate, cudaStream_t stream);
 int wgrad_splits(long long M, int N, int K, int nsm);
 int wgrad_tc_bn(int K);
 int wgrad_tc_splits(long long nblocks, int N, int K, int nsm);
@@ -416,6 +424,87 @@ int plan_cde(const odevio_cde_cfg& c, CdePlan& pl) {
   pl.off_red = take(static_cast<size_t>(2) * pl.grid * 2 * 2);      // doubles as float pairs
   pl.off_bar = take(64);
   pl.total_bytes = off * sizeof(float);
+  return 0;
+}
+
+// checkpoint buffer of the CDE training forward: [log: 1 + steps entries][steps][ntiles][Z, Y1, K0..K6][Hc][R]
+size_t cde_ckpt_log_bytes(int steps) { return align_up(sizeof(CdeStepRec) * static_cast<size_t>(1 + steps), 256); }
+size_t cde_ckpt_step_floats(const odevio_cde_cfg& c, const CdePlan& pl) {
+  return static_cast<size_t>(pl.ntiles) * (2 + kMaxStages) * c.Hc * pl.R;
+}
+
+struct CdeBwdPlan {
+  int nst, NgTot;
+  long long Mc;            // record rows per chunk
+  size_t buf_floats, staging_floats, stage_floats, smem_bytes;
+  size_t off_Wmlp[kMaxLinears], off_Wfin, off_bfin, off_WfinT, off_WinitP, off_Wreg0;
+  size_t off_recA[kMaxLinears + 1], off_recG[kMaxLinears], off_recGf;
+  size_t off_recA_reg0, off_recG_reg0, off_recA_reg1, off_recG_reg1, off_recA_init, off_recG_init;
+  size_t off_tile_state, off_scratch, scratch_floats_per_cta, off_dWp, off_dbp, off_dWinit, off_part;
+  size_t total_bytes;
+};
+
+int plan_cde_bwd(const odevio_cde_cfg& c, const CdePlan& pl, int chunk_vjps, CdeBwdPlan& bp) {
+  if (chunk_vjps < 8) return ODEVIO_E_SHAPE;
+  if (pl.R != 8 && pl.R != 16) return ODEVIO_E_SHAPE;
+  const int R = pl.R, Hc = c.Hc;
+  bp.NgTot = pl.ngroups * pl.Ng;
+  int nmax = pl.Ng > kRegHidden ? pl.Ng : kRegHidden;
+  if (pl.Cpad > nmax) nmax = pl.Cpad;
+  if (pl.Cpad > 1024) return ODEVIO_E_SHAPE;
+  bp.stage_floats = static_cast<size_t>(kStageK) * nmax;
+  size_t rows = static_cast<size_t>(Hc > pl.Cpad ? Hc : pl.Cpad);
+  if (rows < static_cast<size_t>(kRegHidden)) rows = kRegHidden;
+  bp.buf_floats = rows * R;
+  bp.staging_floats = static_cast<size_t>(pl.Ng) * R;
+  const size_t fixed_bytes = (2 * bp.buf_floats + bp.staging_floats + 2 * static_cast<size_t>(pl.Cpad) * R +
+                              2 * static_cast<size_t>(Hc) * R) * sizeof(float) + 16 + 2 * kMaxStagesRing * 8 + 128;
+  if (fixed_bytes + 2 * bp.stage_floats * sizeof(float) > kSmemLimit) return ODEVIO_E_SHAPE;
+  size_t nst = (kSmemLimit - fixed_bytes) / (bp.stage_floats * sizeof(float));
+  if (nst > kMaxStagesRing) nst = kMaxStagesRing;
+  bp.nst = static_cast<int>(nst);
+  bp.smem_bytes = fixed_bytes + nst * bp.stage_floats * sizeof(float);
+  bp.Mc = static_cast<long long>(chunk_vjps) * pl.ntiles * R;
+  const size_t Mc = static_cast<size_t>(bp.Mc);
+  const size_t rowsBS = static_cast<size_t>(pl.ntiles) * R * c.S;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = align_up(off + n, 64); return o; };
+  for (int j = 0; j < c.n_layers; ++j) bp.off_Wmlp[j] = take(static_cast<size_t>(Hc) * Hc);
+  bp.off_Wfin = take(static_cast<size_t>(pl.ngroups) * Hc * pl.Ng);
+  bp.off_bfin = take(static_cast<size_t>(bp.NgTot));
+  bp.off_WfinT = take(static_cast<size_t>(pl.ngroups) * pl.Ng * Hc);
+  bp.off_WinitP = take(static_cast<size_t>(Hc) * pl.Cpad);
+  bp.off_Wreg0 = take(static_cast<size_t>(Hc) * kRegHidden);
+  for (int j = 0; j <= c.n_layers; ++j) bp.off_recA[j] = take(Mc * Hc);
+  for (int j = 0; j < c.n_layers; ++j) bp.off_recG[j] = take(Mc * Hc);
+  bp.off_recGf = take(Mc * bp.NgTot);
+  bp.off_recA_reg0 = take(rowsBS * Hc);
+  bp.off_recG_reg0 = take(rowsBS * kRegHidden);
+  bp.off_recA_reg1 = take(rowsBS * kRegHidden);
+  bp.off_recG_reg1 = take(rowsBS * 8);
+  bp.off_recA_init = take(static_cast<size_t>(pl.ntiles) * R * pl.Cpad);
+  bp.off_recG_init = take(static_cast<size_t>(pl.ntiles) * R * Hc);
+  bp.off_tile_state = take(static_cast<size_t>(pl.ntiles) * 2 * Hc * R);
+  bp.scratch_floats_per_cta = align_up(static_cast<size_t>(kMaxStages + 2 + c.n_layers + 1) * Hc * R, 64);
+  bp.off_scratch = take(bp.scratch_floats_per_cta * pl.grid);
+  bp.off_dWp = take(static_cast<size_t>(bp.NgTot) * Hc);
+  bp.off_dbp = take(static_cast<size_t>(bp.NgTot));
+  bp.off_dWinit = take(static_cast<size_t>(Hc) * pl.Cpad);
+  // partial sums of the weight-gradient GEMMs
+  size_t part = 0;
+  auto need = [&](long long M, int N, int K) {
+    const size_t a = static_cast<size_t>(wgrad_splits(M, N, K, pl.nsm)) * N * K;
+    const size_t b = static_cast<size_t>(256) * N;
+    if (a > part) part = a;
+    if (b > part) part = b;
+  };
+  need(bp.Mc, Hc, Hc);
+  need(bp.Mc, bp.NgTot, Hc);
+  need(static_cast<long long>(c.B) * c.S, kRegHidden, Hc);
+  need(static_cast<long long>(c.B) * c.S, kPoseDim, kRegHidden);
+  need(c.B, Hc, pl.Cpad);
+  bp.off_part = take(part);
+  bp.total_bytes = off * sizeof(float);
   return 0;
 }
 
@@ -942,16 +1031,22 @@ size_t odevio_cde_workspace_bytes(const odevio_cde_cfg* cfg) {
   return pl.total_bytes;
 }
 
-int32_t odevio_cde_forward(const odevio_cde_cfg* cfg, const odevio_cde_weights* w,
-                           const float* tobs, const float* fv, const float* fi, int32_t Dv,
-                           const double* tout, const float* z0_in,
-                           float* pose, float* z0_out, float* hidden, int32_t* stats,
-                           void* workspace, size_t workspace_bytes, void* stream_) {
+static int32_t cde_forward_impl(const odevio_cde_cfg* cfg, const odevio_cde_weights* w,
+                                const float* tobs, const float* fv, const float* fi, int32_t Dv,
+                                const double* tout, const float* z0_in,
+                                float* pose, float* z0_out, float* hidden, int32_t* stats,
+                                void* ckpt, size_t ckpt_bytes, int32_t ckpt_steps,
+                                void* workspace, size_t workspace_bytes, void* stream_) {
   if (!cfg || !w || !tobs || !fv || !tout || !pose || !z0_out || !workspace) return ODEVIO_E_NULL;
   const odevio_cde_cfg& c = *cfg;
   CdePlan pl;
   const int rc = plan_cde(c, pl);
   if (rc != 0) return rc;
+  if (ckpt) {
+    if (ckpt_steps < 1 || !hidden) return ODEVIO_E_SHAPE;
+    const size_t need = cde_ckpt_log_bytes(ckpt_steps) + cde_ckpt_step_floats(c, pl) * ckpt_steps * sizeof(float);
+    if (ckpt_bytes < need || (reinterpret_cast<uintptr_t>(ckpt) & 255)) return ODEVIO_E_WORKSPACE;
+  }
   if (Dv <= 0 || Dv > c.Hc || (Dv < c.Hc && !fi) || (Dv == c.Hc && fi)) return ODEVIO_E_SHAPE;
   if (workspace_bytes < pl.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ODEVIO_E_WORKSPACE;
   for (int j = 0; j <= c.n_layers; ++j) if (!w->cde_w[j] || !w->cde_b[j]) return ODEVIO_E_NULL;
@@ -986,9 +1081,164 @@ int32_t odevio_cde_forward(const odevio_cde_cfg* cfg, const odevio_cde_weights* 
   p.ntiles = pl.ntiles; p.nst = pl.nst;
   p.buf_floats = static_cast<int>(pl.buf_floats); p.stage_floats = static_cast<int>(pl.stage_floats);
   p.staging_floats = static_cast<int>(pl.staging_floats);
+  if (ckpt) {
+    p.log = static_cast<CdeStepRec*>(ckpt);
+    p.ckpt = reinterpret_cast<float*>(static_cast<unsigned char*>(ckpt) + cde_ckpt_log_bytes(ckpt_steps));
+    p.ckpt_cap = ckpt_steps;
+    ODEVIO_CUDA_TRY(cudaMemsetAsync(ckpt, 0, sizeof(CdeStepRec), stream));
+  }
   DevTableau tab;
   if (!make_tableau(ODEVIO_SOLVER_DOPRI5, tab)) return ODEVIO_E_ENUM;
   ODEVIO_CUDA_TRY(launch_cde_fwd(p, tab, pl.RT, pl.LL, pl.grid, pl.smem_bytes, stream));
+  return 0;
+}
+
+int32_t odevio_cde_forward(const odevio_cde_cfg* cfg, const odevio_cde_weights* w,
+                           const float* tobs, const float* fv, const float* fi, int32_t Dv,
+                           const double* tout, const float* z0_in,
+                           float* pose, float* z0_out, float* hidden, int32_t* stats,
+                           void* workspace, size_t workspace_bytes, void* stream_) {
+  return cde_forward_impl(cfg, w, tobs, fv, fi, Dv, tout, z0_in, pose, z0_out, hidden, stats, nullptr, 0, 0,
+                          workspace, workspace_bytes, stream_);
+}
+
+size_t odevio_cde_ckpt_bytes(const odevio_cde_cfg* cfg, int32_t ckpt_steps) {
+  if (!cfg || ckpt_steps < 1) return 0;
+  CdePlan pl;
+  if (plan_cde(*cfg, pl) != 0) return 0;
+  return cde_ckpt_log_bytes(ckpt_steps) + cde_ckpt_step_floats(*cfg, pl) * ckpt_steps * sizeof(float);
+}
+
+int32_t odevio_cde_forward_ckpt(const odevio_cde_cfg* cfg, const odevio_cde_weights* w,
+                                const float* tobs, const float* fv, const float* fi, int32_t Dv,
+                                const double* tout, const float* z0_in,
+                                float* pose, float* z0_out, float* hidden, int32_t* stats,
+                                void* ckpt, size_t ckpt_bytes, int32_t ckpt_steps,
+                                void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!ckpt) return ODEVIO_E_NULL;
+  return cde_forward_impl(cfg, w, tobs, fv, fi, Dv, tout, z0_in, pose, z0_out, hidden, stats, ckpt, ckpt_bytes,
+                          ckpt_steps, workspace, workspace_bytes, stream_);
+}
+
+size_t odevio_cde_backward_workspace_bytes(const odevio_cde_cfg* cfg, int32_t chunk_vjps) {
+  if (!cfg) return 0;
+  CdePlan pl;
+  if (plan_cde(*cfg, pl) != 0) return 0;
+  CdeBwdPlan bp;
+  if (plan_cde_bwd(*cfg, pl, chunk_vjps, bp) != 0) return 0;
+  return bp.total_bytes;
+}
+
+int32_t odevio_cde_backward(const odevio_cde_cfg* cfg, const odevio_cde_weights* w,
+                            const float* tobs, const float* fv, const float* fi, int32_t Dv,
+                            const double* tout, int32_t has_prev, const float* hidden, const float* z0,
+                            const void* ckpt, size_t ckpt_bytes, int32_t ckpt_steps,
+                            const int32_t* vjp_base, int32_t n_accepted, int32_t chunk_vjps,
+                            const float* grad_pose, const float* grad_z0,
+                            const odevio_cde_grads* g, float* grad_x, float* grad_prev,
+                            void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!cfg || !w || !tobs || !fv || !tout || !hidden || !z0 || !ckpt || !vjp_base || !grad_pose || !g || !workspace)
+    return ODEVIO_E_NULL;
+  const odevio_cde_cfg& c = *cfg;
+  CdePlan pl;
+  int rc = plan_cde(c, pl);
+  if (rc != 0) return rc;
+  CdeBwdPlan bp;
+  rc = plan_cde_bwd(c, pl, chunk_vjps, bp);
+  if (rc != 0) return rc;
+  if (Dv <= 0 || Dv > c.Hc || (Dv < c.Hc && !fi) || (Dv == c.Hc && fi)) return ODEVIO_E_SHAPE;
+  if (n_accepted < 0 || n_accepted > ckpt_steps) return ODEVIO_E_SHAPE;
+  if (has_prev && !grad_prev) return ODEVIO_E_NULL;
+  if (workspace_bytes < bp.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ODEVIO_E_WORKSPACE;
+  {
+    const size_t need = cde_ckpt_log_bytes(ckpt_steps) + cde_ckpt_step_floats(c, pl) * ckpt_steps * sizeof(float);
+    if (ckpt_bytes < need || (reinterpret_cast<uintptr_t>(ckpt) & 255)) return ODEVIO_E_WORKSPACE;
+  }
+  const int NM = c.n_layers, Hc = c.Hc;
+  for (int j = 0; j <= NM; ++j) if (!w->cde_w[j] || !w->cde_b[j] || !g->cde_w[j] || !g->cde_b[j]) return ODEVIO_E_NULL;
+  if (!w->init_w || !w->init_b || !w->reg_w0 || !w->reg_b0 || !w->reg_w1) return ODEVIO_E_NULL;
+  if (!g->reg_w0 || !g->reg_b0 || !g->reg_w1 || !g->reg_b1) return ODEVIO_E_NULL;
+  if (!has_prev && (!g->init_w || !g->init_b)) return ODEVIO_E_NULL;
+
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* ws = static_cast<float*>(workspace);
+  CdeBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = c.B; p.S = c.S; p.So = c.So; p.Hc = Hc; p.C = pl.C; p.Cpad = pl.Cpad; p.NM = NM;
+  p.act = c.activation; p.solver = c.solver; p.interp = c.interp;
+  DevTableau tab;
+  if (!make_tableau(c.solver == ODEVIO_CDE_SOLVER_DOPRI5 ? ODEVIO_SOLVER_DOPRI5 : ODEVIO_SOLVER_RK4_38, tab)) return ODEVIO_E_ENUM;
+  p.ns = tab.n_stages; p.fsal = tab.fsal;
+  for (int j = 0; j < NM; ++j) {
+    float* dst = ws + bp.off_Wmlp[j];
+    ODEVIO_CUDA_TRY(transpose_pack(w->cde_w[j], Hc, Hc, dst, Hc, 0, 0, stream));
+    p.Wmlp[j] = dst; p.bmlp[j] = w->cde_b[j]; p.Wmlp_raw[j] = w->cde_w[j];
+  }
+  ODEVIO_CUDA_TRY(cde_pack_final(w->cde_w[NM], w->cde_b[NM], Hc, pl.C, pl.Gc, pl.ngroups, ws + bp.off_Wfin,
+                                 ws + bp.off_bfin, stream));
+  ODEVIO_CUDA_TRY(cde_pack_final_t(w->cde_w[NM], Hc, pl.C, pl.Gc, pl.ngroups, ws + bp.off_WfinT, stream));
+  p.Wfin = ws + bp.off_Wfin; p.bfin = ws + bp.off_bfin; p.WfinT = ws + bp.off_WfinT;
+  p.Gc = pl.Gc; p.ngroups = pl.ngroups; p.Ng = pl.Ng;
+  ODEVIO_CUDA_TRY(cudaMemsetAsync(ws + bp.off_WinitP, 0, sizeof(float) * Hc * pl.Cpad, stream));
+  ODEVIO_CUDA_TRY(cudaMemcpy2DAsync(ws + bp.off_WinitP, sizeof(float) * pl.Cpad, w->init_w, sizeof(float) * pl.C,
+                                    sizeof(float) * pl.C, Hc, cudaMemcpyDeviceToDevice, stream));
+  p.WinitP = ws + bp.off_WinitP;
+  ODEVIO_CUDA_TRY(transpose_pack(w->reg_w0, kRegHidden, Hc, ws + bp.off_Wreg0, kRegHidden, 0, 0, stream));
+  p.Wreg0 = ws + bp.off_Wreg0; p.breg0 = w->reg_b0; p.Wreg0_raw = w->reg_w0; p.Wreg1 = w->reg_w1;
+  p.tobs = tobs; p.fv = fv; p.fi = fi; p.Dv = Dv; p.tout = tout;
+  p.hidden = hidden; p.z0 = z0; p.has_prev = has_prev ? 1 : 0;
+  p.gpose = grad_pose; p.gz0 = grad_z0; p.gX = grad_x; p.gprev = grad_prev;
+  p.log = static_cast<const CdeStepRec*>(ckpt);
+  p.ckpt = reinterpret_cast<const float*>(static_cast<const unsigned char*>(ckpt) + cde_ckpt_log_bytes(ckpt_steps));
+  p.n_acc = n_accepted;
+  for (int j = 0; j <= NM; ++j) p.recA[j] = ws + bp.off_recA[j];
+  for (int j = 0; j < NM; ++j) p.recG[j] = ws + bp.off_recG[j];
+  p.recGf = ws + bp.off_recGf;
+  p.recA_reg0 = ws + bp.off_recA_reg0; p.recG_reg0 = ws + bp.off_recG_reg0;
+  p.recA_reg1 = ws + bp.off_recA_reg1; p.recG_reg1 = ws + bp.off_recG_reg1;
+  p.recA_init = ws + bp.off_recA_init; p.recG_init = ws + bp.off_recG_init;
+  p.tile_state = ws + bp.off_tile_state;
+  p.scratch = ws + bp.off_scratch; p.scratch_floats_per_cta = bp.scratch_floats_per_cta;
+  p.ntiles = pl.ntiles; p.nst = bp.nst;
+  p.buf_floats = static_cast<int>(bp.buf_floats); p.stage_floats = static_cast<int>(bp.stage_floats);
+  p.staging_floats = static_cast<int>(bp.staging_floats);
+
+  float* part = ws + bp.off_part;
+  float* dWp = ws + bp.off_dWp; float* dbp = ws + bp.off_dbp;
+  const long long rows_per_vjp = static_cast<long long>(pl.ntiles) * pl.R;
+  // walk the log backwards, at most chunk_vjps pullbacks (record rows) per launch
+  int hi = n_accepted;
+  bool first = true;
+  do {
+    int lo = hi;
+    while (lo > 0 && vjp_base[hi] - vjp_base[lo - 1] <= chunk_vjps) --lo;
+    if (lo == hi && hi > 0) return ODEVIO_E_SHAPE;          // one step alone exceeds the chunk
+    p.step_lo = lo; p.step_hi = hi; p.vjp_lo = n_accepted > 0 ? vjp_base[lo] : 0;
+    ODEVIO_CUDA_TRY(launch_cde_bwd(p, tab, pl.RT, pl.LL, pl.grid, bp.smem_bytes, stream));
+    const long long M = n_accepted > 0 ? static_cast<long long>(vjp_base[hi] - vjp_base[lo]) * rows_per_vjp : 0;
+    const int acc = first ? 0 : 1;
+    for (int j = 0; j < NM; ++j)
+      ODEVIO_CUDA_TRY(wgrad_linear_ex(p.recG[j], Hc, p.recA[j], Hc, M, Hc, Hc, g->cde_w[j], nullptr, 0, g->cde_b[j], nullptr,
+                                      part, pl.nsm, acc, stream));
+    ODEVIO_CUDA_TRY(wgrad_linear_ex(p.recGf, bp.NgTot, p.recA[NM], Hc, M, bp.NgTot, Hc, dWp, nullptr, 0, dbp, nullptr,
+                                    part, pl.nsm, acc, stream));
+    first = false;
+    hi = lo;
+  } while (hi > 0);
+  ODEVIO_CUDA_TRY(cde_unpack_final_grad(dWp, dbp, Hc, pl.C, pl.Gc, g->cde_w[NM], g->cde_b[NM], stream));
+  const long long BS = static_cast<long long>(c.B) * c.S;
+  ODEVIO_CUDA_TRY(wgrad_linear(p.recG_reg0, kRegHidden, p.recA_reg0, Hc, BS, kRegHidden, Hc, g->reg_w0, nullptr, 0,
+                               g->reg_b0, nullptr, part, pl.nsm, stream));
+  ODEVIO_CUDA_TRY(wgrad_linear(p.recG_reg1, 8, p.recA_reg1, kRegHidden, BS, kPoseDim, kRegHidden, g->reg_w1, nullptr, 0,
+                               g->reg_b1, nullptr, part, pl.nsm, stream));
+  if (!has_prev) {
+    // K = Cpad (the GEMM's float4 stores need K % 4 == 0; the padded input columns are zero), then drop the padding
+    float* dWi = ws + bp.off_dWinit;
+    ODEVIO_CUDA_TRY(wgrad_linear(p.recG_init, Hc, p.recA_init, pl.Cpad, c.B, Hc, pl.Cpad, dWi, nullptr, 0, g->init_b,
+                                 nullptr, part, pl.nsm, stream));
+    ODEVIO_CUDA_TRY(cudaMemcpy2DAsync(g->init_w, sizeof(float) * pl.C, dWi, sizeof(float) * pl.Cpad, sizeof(float) * pl.C,
+                                      Hc, cudaMemcpyDeviceToDevice, stream));
+  }
   return 0;
 }
 

@@ -371,6 +371,30 @@ cde_fwd_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ De
     return prm.tout[k];
   };
 
+  // training: checkpoint of an accepted step (Z, Y1, K0..K6 of my tiles) + its log entry     (cde_bwd.cu)
+  int vjp_total = 0;
+  auto save_step = [&](int step_idx, int onj) {
+    const size_t per_tile = static_cast<size_t>(2 + kMaxStages) * Hc * R;
+    if (!c.th.producer) {
+      for (int k2 = 0; k2 < my_tiles; ++k2) {
+        const int tl = static_cast<int>(blockIdx.x) + k2 * static_cast<int>(gridDim.x);
+        const float* src = tile_arrays(p, tl, R).Z;
+        float* dst = p.ckpt + (static_cast<size_t>(step_idx) * p.ntiles + tl) * per_tile;
+        for (int e = c.th.ctid; e < static_cast<int>(per_tile / 4); e += ncons)
+          st4(dst + static_cast<size_t>(e) * 4, ld4(src + static_cast<size_t>(e) * 4));
+      }
+    }
+    int cnt = 0;
+    for (int i = i_out; i < S && !(p.tout[i] > t_b); ++i) ++cnt;
+    if (blockIdx.x == 0 && tid == 0) {
+      CdeStepRec r;
+      r.ta = t_cur; r.tb = t_b; r.dt_s = dt_s; r.ta_s = ta_s; r.tb_s = tb_s; r.on_jump = onj;
+      r.out_first = i_out; r.out_count = cnt; r.vjp_base = vjp_total; r.pad = 0;
+      p.log[1 + step_idx] = r;
+    }
+    vjp_total += cde_step_vjps(adaptive ? tab.n_stages : 4, adaptive ? 1 : 0, onj, step_idx);
+  };
+
   // ---- sub-machine registers
   int pc = PC_INITZ, ret = PC_POSE0;
   int tk = 0;                       // index into this CTA's tile list
@@ -654,8 +678,13 @@ cde_fwd_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ De
           const double dfactor = ratio < 1.0 ? 1.0 : 0.2;
           dt = step * fmin(10.0, fmax(0.9 / pow(ratio, 0.2), dfactor));
         }
-        if (accept) { ++n_acc; pc = PC_OUTPUTS; }
-        else pc = PC_STEP_BEGIN;
+        if (accept) {
+          if (p.ckpt) {
+            if (n_acc >= p.ckpt_cap) { status = 3; pc = PC_END; break; }
+            save_step(n_acc, on_jump);
+          }
+          ++n_acc; pc = PC_OUTPUTS;
+        } else pc = PC_STEP_BEGIN;
         break;
       }
       case PC_OUTPUTS: {
@@ -707,6 +736,11 @@ cde_fwd_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ De
           }
           named_bar_sync(1, ncons);
         }
+        if (p.ckpt) {
+          if (n_acc >= p.ckpt_cap) { status = 3; pc = PC_END; break; }
+          // outputs of a grid interval: every t_out in (t_cur, t_b]  (same test as the output loop below)
+          save_step(n_acc, 0);
+        }
         ++n_steps; ++n_acc;
         pc = PC_AFTER_JUMP;      // reused as the rk4 output loop
         break;
@@ -743,6 +777,10 @@ cde_fwd_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ De
 
   if (blockIdx.x == 0 && tid == 0 && prm.stats) {
     prm.stats[0] = n_steps; prm.stats[1] = n_acc; prm.stats[2] = n_f; prm.stats[3] = status;
+  }
+  if (blockIdx.x == 0 && tid == 0 && prm.log) {
+    CdeLogHead* hd = reinterpret_cast<CdeLogHead*>(prm.log);
+    hd->n_acc = n_acc; hd->n_vjp = vjp_total; hd->status = status;
   }
 }
 

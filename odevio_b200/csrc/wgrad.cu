@@ -114,14 +114,15 @@ wgrad_gemm_kernel(const float* __restrict__ G, int ldg, const float* __restrict_
 // out[i (+ column remap)] = sum_z part[z][i]; optional split of the K axis into two destinations
 // (rnn: [dW_ih | dW_hh] from the [x ; h] record).  ld_split = K of the first destination (0: none).
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int N, int K,
-                                    float* __restrict__ out0, float* __restrict__ out1, int k_split) {
+                                    float* __restrict__ out0, float* __restrict__ out1, int k_split,
+                                    int accumulate = 0) {
   const size_t total = static_cast<size_t>(N) * K;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += part[static_cast<size_t>(z) * total + i];
     if (!out1) {
-      out0[i] = s;
+      out0[i] = accumulate ? out0[i] + s : s;
     } else {
       const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<size_t>(n) * K);
       if (k < k_split) out0[static_cast<size_t>(n) * k_split + k] = s;
@@ -162,9 +163,22 @@ int wgrad_splits(long long M, int N, int K, int nsm) {
 
 // dW (and optionally db) of one Linear from its record streams.  `part` must hold
 // wgrad_splits(...) * N * K floats (and >= 256 * N for the bias pass).
+cudaError_t wgrad_linear_ex(const float* G, int ldg, const float* A, int lda, long long M, int N, int K,
+                            float* dW0, float* dW1, int k_split, float* db0, float* db1, float* part, int nsm,
+                            int accumulate, cudaStream_t stream);
+
 cudaError_t wgrad_linear(const float* G, int ldg, const float* A, int lda, long long M, int N, int K,
                          float* dW0, float* dW1, int k_split, float* db0, float* db1, float* part, int nsm,
                          cudaStream_t stream) {
+  return wgrad_linear_ex(G, ldg, A, lda, M, N, K, dW0, dW1, k_split, db0, db1, part, nsm, 0, stream);
+}
+
+// accumulate != 0 (single destination only): dW0 += ..., db0 += ...   (record streams reduced chunk by chunk)
+cudaError_t wgrad_linear_ex(const float* G, int ldg, const float* A, int lda, long long M, int N, int K,
+                            float* dW0, float* dW1, int k_split, float* db0, float* db1, float* part, int nsm,
+                            int accumulate, cudaStream_t stream) {
+  if (accumulate && (dW1 || db1)) return cudaErrorInvalidValue;
+  if (M <= 0 && accumulate) return cudaSuccess;
   if (M <= 0) {
     cudaError_t e = cudaMemsetAsync(dW0, 0, sizeof(float) * static_cast<size_t>(N) * (dW1 ? k_split : K), stream);
     if (e != cudaSuccess) return e;
@@ -183,7 +197,7 @@ cudaError_t wgrad_linear(const float* G, int ldg, const float* A, int lda, long 
   const size_t total = static_cast<size_t>(N) * K;
   int rb = static_cast<int>((total + 255) / 256);
   if (rb > 4 * nsm) rb = 4 * nsm;
-  wgrad_reduce_kernel<<<rb, 256, 0, stream>>>(part, splits, N, K, dW0, dW1, k_split);
+  wgrad_reduce_kernel<<<rb, 256, 0, stream>>>(part, splits, N, K, dW0, dW1, k_split, accumulate);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (db0) {
@@ -195,7 +209,7 @@ cudaError_t wgrad_linear(const float* G, int ldg, const float* A, int lda, long 
     colsum_kernel<<<g2, 128, 0, stream>>>(G, ldg, M, N, brps, part);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    wgrad_reduce_kernel<<<(N + 255) / 256, 256, 0, stream>>>(part, bs, 1, N, db0, nullptr, 0);
+    wgrad_reduce_kernel<<<(N + 255) / 256, 256, 0, stream>>>(part, bs, 1, N, db0, nullptr, 0, accumulate);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (db1) {

@@ -542,8 +542,12 @@ class PoseCDE(nn.Module):
     cubics with backward differences, integrated over the knot grid), ``cde_atol`` 1e-6,
     ``cde_rtol`` 1e-4 (PoseCDE.py:101), ``cde_step_size`` (fixed-grid rk4), ``cde_max_steps``, ``cde_history_limit``
     (cubic mode: eval-mode history bounded to that many observations, same poses; default: the reference's unbounded growth),
-    ``cde_rows_per_tile``.  The reference's ``adjoint`` flag only changes how gradients are computed;
-    the fused backward for the CDE path is not built yet, so ``forward`` under autograd raises.
+    ``cde_rows_per_tile``, ``cde_ckpt_steps`` (training: accepted solver steps the checkpoints hold, default 256),
+    ``cde_bwd_record_gb`` (training: bound on the record streams of the deferred weight-gradient GEMMs, default 4).
+    Training: under autograd ``forward`` runs ``odevio_cde_forward_ckpt`` and ``loss.backward()`` runs the fused
+    ``odevio_cde_backward`` (odevio_b200/autograd.py) -- discretise-then-optimise with the accepted step sizes as
+    constants, which is what the reference's ``cdeint(adjoint=False)`` computes up to torchdiffeq's step-size terms; the
+    reference's ``adjoint`` flag only changes how (not which) gradients are computed and is accepted and ignored.
     """
 
     SOLVERS = ("dopri5", "rk4")
@@ -578,6 +582,8 @@ class PoseCDE(nn.Module):
         self.max_steps = int(getattr(opt, "cde_max_steps", 100000))
         self.rows_per_tile = int(getattr(opt, "cde_rows_per_tile", 0))
         self.history_limit = getattr(opt, "cde_history_limit", None)     # cubic mode: observations kept across windows
+        self.ckpt_steps = int(getattr(opt, "cde_ckpt_steps", 256))       # training: accepted solver steps the checkpoints hold
+        self.bwd_record_gb = float(getattr(opt, "cde_bwd_record_gb", 4.0))   # training: bound on the backward's record streams
         self.history = None          # (tobs [B,n], fv [B,n,.], fi [B,n,.] | None) in eval mode
         self.last_stats = None       # int32 [4]: n_steps, n_accepted, n_f_evals, status
         self.last_hidden = None      # [B,S,Hc]
@@ -598,9 +604,6 @@ class PoseCDE(nn.Module):
         if self.f_len != self.cde_hidden_dim:
             raise _lib.OdevioError(f"PoseCDE needs v_f_len + i_f_len == cde_hidden_dim (reduction_net is unused in "
                                    f"the reference, PoseCDE.py:53-57,62): {self.f_len} != {self.cde_hidden_dim}")
-        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or fv.requires_grad):
-            raise _lib.OdevioError("odevio_b200: the fused backward of the CDE path is not built; run PoseCDE "
-                                   "under torch.no_grad()")
         B, S = fv.shape[0], fv.shape[1]
         dev = fv.device
         if self.fuse_method == "cat":
@@ -627,7 +630,7 @@ class PoseCDE(nn.Module):
                 keep_n = max(lim, S + 1)
                 tobs, fvc = tobs[:, -keep_n:].contiguous(), fvc[:, -keep_n:].contiguous()
                 fic = None if fic is None else fic[:, -keep_n:].contiguous()
-            self.history = (tobs, fvc, fic)
+            self.history = (tobs.detach(), fvc.detach(), None if fic is None else fic.detach())
         else:
             self.history = None
         So = tobs.shape[1]
@@ -639,6 +642,32 @@ class PoseCDE(nn.Module):
         if z0_in is not None and tuple(z0_in.shape) != (B, self.cde_hidden_dim):
             raise _lib.OdevioError(f"prev must be [B,Hc]={B, self.cde_hidden_dim}, got {tuple(z0_in.shape)}")
 
+        needs_grad = torch.is_grad_enabled() and (
+            any(p.requires_grad for p in self._param_list()) or fvc.requires_grad or
+            (fic is not None and fic.requires_grad) or (z0_in is not None and z0_in.requires_grad))
+        if do_profile:
+            torch.cuda.nvtx.range_push("cdeint")
+        if needs_grad:
+            from .autograd import cde_apply
+            pose, z0, hidden = cde_apply(self, Dv, tobs, tout, fvc, fic, z0_in)
+        else:
+            pose, z0, hidden, stats, _ = self._launch(tobs, fvc, fic, Dv, tout, z0_in)
+            self.last_stats = stats
+        if do_profile:
+            torch.cuda.nvtx.range_pop()
+        self.last_hidden = hidden
+        return pose, z0                                                          # PoseCDE.py:103 returns z0
+
+    def _param_list(self):
+        """Flat parameter order shared by the autograd bridge's forward and backward."""
+        ps = []
+        for lin in self.cde_func.linears():
+            ps += [lin.weight, lin.bias]
+        ps += [self.initial[0].weight, self.initial[0].bias, self.regressor[0].weight, self.regressor[0].bias,
+               self.regressor[2].weight, self.regressor[2].bias]
+        return ps
+
+    def _cfg(self, B, S, So):
         cfg = _lib.default_cde_cfg()
         cfg.B, cfg.S, cfg.So, cfg.Hc = B, S, So, self.cde_hidden_dim
         cfg.n_layers = self.cde_fn_num_layers
@@ -650,7 +679,28 @@ class PoseCDE(nn.Module):
             step = 1.0            # torchcde injects min(diff(grid_points)) for fixed-grid solvers
         cfg.step_size = float(step or 0.0)
         cfg.max_steps, cfg.rows_per_tile = self.max_steps, self.rows_per_tile
-        nbytes = lib.odevio_cde_workspace_bytes(C.byref(cfg))
+        return cfg
+
+    def _weight_struct(self, params):
+        """odevio_cde_weights over the flat parameter list (``_param_list`` order)."""
+        w = _lib.CdeWeights()
+        keep = [_f32c(p.detach(), "parameter") for p in params]
+        n = self.cde_fn_num_layers + 1
+        for j in range(n):
+            w.cde_w[j], w.cde_b[j] = _lib.dptr(keep[2 * j]), _lib.dptr(keep[2 * j + 1])
+        k = 2 * n
+        w.init_w, w.init_b, w.reg_w0, w.reg_b0, w.reg_w1, w.reg_b1 = (_lib.dptr(keep[k + i]) for i in range(6))
+        return w, keep
+
+    def _launch(self, tobs, fvc, fic, Dv, tout, z0_in, save_ckpt=False):
+        """One ``odevio_cde_forward[_ckpt]`` launch.  Returns pose, z0, hidden, stats and (cfg, ckpt, ckpt_steps)."""
+        lib = _lib.load()
+        B, So = tobs.shape
+        S = tout.shape[0]
+        dev = tobs.device
+        cfg = self._cfg(B, S, So)
+        with torch.cuda.device(dev):
+            nbytes = lib.odevio_cde_workspace_bytes(C.byref(cfg))
         if nbytes == 0:
             raise _lib.OdevioError(f"unsupported PoseCDE configuration for the fused kernel (Hc={cfg.Hc}, "
                                    f"n={cfg.n_layers}, S={S}, So={So})")
@@ -659,34 +709,27 @@ class PoseCDE(nn.Module):
         z0 = torch.empty(B, self.cde_hidden_dim, dtype=torch.float32, device=dev)
         hidden = torch.empty(B, S, self.cde_hidden_dim, dtype=torch.float32, device=dev)
         stats = torch.zeros(4, dtype=torch.int32, device=dev)
-        w = _lib.CdeWeights()
-        keep = []
-
-        def ptr(p, name):
-            t = _f32c(p.detach(), name)
-            keep.append(t)
-            return _lib.dptr(t, name)
-
-        for j, lin in enumerate(self.cde_func.linears()):
-            w.cde_w[j] = ptr(lin.weight, f"cde_func.net.{2 * j}.weight")
-            w.cde_b[j] = ptr(lin.bias, f"cde_func.net.{2 * j}.bias")
-        w.init_w, w.init_b = ptr(self.initial[0].weight, "initial.0.weight"), ptr(self.initial[0].bias, "initial.0.bias")
-        w.reg_w0, w.reg_b0 = ptr(self.regressor[0].weight, "regressor.0.weight"), ptr(self.regressor[0].bias, "regressor.0.bias")
-        w.reg_w1, w.reg_b1 = ptr(self.regressor[2].weight, "regressor.2.weight"), ptr(self.regressor[2].bias, "regressor.2.bias")
+        w, keep = self._weight_struct(self._param_list())
         stream = torch.cuda.current_stream(dev).cuda_stream
-        if do_profile:
-            torch.cuda.nvtx.range_push("cdeint")
+        ckpt, cap = None, 0
         with torch.cuda.device(dev):
-            rc = lib.odevio_cde_forward(
-                C.byref(cfg), C.byref(w), _lib.dptr(tobs, "tobs"), _lib.dptr(fvc, "fv"), _lib.dptr(fic, "fi"), Dv,
-                _lib.dptr(tout, "tout"), _lib.dptr(z0_in, "prev"), _lib.dptr(pose), _lib.dptr(z0),
-                _lib.dptr(hidden), _lib.dptr(stats), _lib.dptr(ws), nbytes, C.c_void_p(stream))
-        if do_profile:
-            torch.cuda.nvtx.range_pop()
+            if save_ckpt:
+                cap = self.ckpt_steps
+                cbytes = lib.odevio_cde_ckpt_bytes(C.byref(cfg), cap)
+                ckpt = torch.empty(cbytes, dtype=torch.uint8, device=dev)
+                rc = lib.odevio_cde_forward_ckpt(
+                    C.byref(cfg), C.byref(w), _lib.dptr(tobs, "tobs"), _lib.dptr(fvc, "fv"), _lib.dptr(fic, "fi"), Dv,
+                    _lib.dptr(tout, "tout"), _lib.dptr(z0_in, "prev"), _lib.dptr(pose), _lib.dptr(z0),
+                    _lib.dptr(hidden), _lib.dptr(stats), _lib.dptr(ckpt), cbytes, cap, _lib.dptr(ws), nbytes,
+                    C.c_void_p(stream))
+            else:
+                rc = lib.odevio_cde_forward(
+                    C.byref(cfg), C.byref(w), _lib.dptr(tobs, "tobs"), _lib.dptr(fvc, "fv"), _lib.dptr(fic, "fi"), Dv,
+                    _lib.dptr(tout, "tout"), _lib.dptr(z0_in, "prev"), _lib.dptr(pose), _lib.dptr(z0),
+                    _lib.dptr(hidden), _lib.dptr(stats), _lib.dptr(ws), nbytes, C.c_void_p(stream))
         _lib.check(rc)
         del keep
-        self.last_stats, self.last_hidden = stats, hidden
-        return pose, z0                                                          # PoseCDE.py:103 returns z0
+        return pose, z0, hidden, stats, (cfg, ckpt, cap)
 
     def check_status(self):
         """Synchronising check of the last forward's solver status."""

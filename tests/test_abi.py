@@ -52,7 +52,7 @@ def test_struct_layout_matches_header(lib):
     assert (cfg.B, cfg.S, cfg.D, cfg.H, cfg.n_hidden, cfg.L) == (1, 10, 768, 512, 3, 2)
     assert abs(cfg.atol - 1e-6) < 1e-12 and abs(cfg.rtol - 1e-2) < 1e-9 and abs(cfg.dt0 - 1e-4) < 1e-11
     assert (cfg.accept_strict, cfg.floor_factor, cfg.endpoint_dense, cfg.exact_landing) == (1, 0, 0, 1)
-    assert lib.odevio_version() == _lib.ABI_VERSION == 3
+    assert lib.odevio_version() == _lib.ABI_VERSION == 4
 
 
 def test_workspace_and_validation_without_gpu(lib):
@@ -81,7 +81,8 @@ def test_training_geometry_and_sizes_without_gpu(lib):
     geo = (C.c_int32 * 8)()
     assert lib.odevio_odernn_geometry(C.byref(cfg), geo) == 0
     RT, R, ntiles, ns, CK = geo[0], geo[1], geo[2], geo[3], geo[4]
-    assert (RT, R, ntiles, ns, CK) == (8, 16, 13, 6, 16)          # dopri5: 6 stages enter y1 (FSAL)
+    # dopri5: 6 stages enter y1 (FSAL); 100 sequences: 4-sequence tiles (25 CTAs) rather than 13 CTAs of 8
+    assert (RT, R, ntiles, ns, CK) == (4, 8, 25, 6, 16)
     per_iv = 2 * 768 * R + CK * (768 * R + 2 * R)
     assert lib.odevio_odernn_ckpt_bytes(C.byref(cfg)) >= ntiles * 10 * per_iv * 4
     small = lib.odevio_odernn_backward_workspace_bytes(C.byref(cfg), 0)
@@ -98,6 +99,26 @@ def test_training_geometry_and_sizes_without_gpu(lib):
     g = _lib.OdeRnnGrads()
     rc = lib.odevio_odernn_backward(C.byref(cfg), C.byref(_lib.OdeRnnWeights()), None, None, 768, None, 0,
                                     None, 0, None, None, C.byref(g), None, None, None, 0, None)
+    assert rc == -1
+
+
+def test_cde_training_sizes_without_gpu(lib):
+    """CDE checkpoint / backward-workspace planning is pure host arithmetic."""
+    from odevio_b200 import _lib
+    cfg = _lib.default_cde_cfg()
+    cfg.B, cfg.Hc, cfg.interp = 40, 32, 1
+    R, ntiles = 8, 5
+    one = lib.odevio_cde_ckpt_bytes(C.byref(cfg), 1)
+    grow = lib.odevio_cde_ckpt_bytes(C.byref(cfg), 11) - one
+    assert 0 <= grow - 10 * ntiles * 9 * 32 * R * 4 <= 10 * 48 + 256             # Z, Y1, K0..K6 per step + the log entries
+    assert lib.odevio_cde_ckpt_bytes(C.byref(cfg), 0) == 0
+    small = lib.odevio_cde_backward_workspace_bytes(C.byref(cfg), 8)
+    big = lib.odevio_cde_backward_workspace_bytes(C.byref(cfg), 16)
+    # per pullback and row: inputs of the 4 Linears, gradients of the 3 hidden ones, the final Linear's 33 (+pad) channels
+    assert small > 0 and big - small >= 8 * ntiles * R * 4 * (4 * 32 + 3 * 32 + 33 * 32)
+    assert lib.odevio_cde_backward_workspace_bytes(C.byref(cfg), 4) == 0                           # below one step's pullbacks
+    rc = lib.odevio_cde_backward(C.byref(cfg), C.byref(_lib.CdeWeights()), None, None, None, 32, None, 0, None, None,
+                                 None, 0, 0, None, 0, 8, None, None, C.byref(_lib.CdeGrads()), None, None, None, 0, None)
     assert rc == -1
 
 

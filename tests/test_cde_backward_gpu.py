@@ -1,0 +1,149 @@
+"""GPU parity of the fused CDE backward (odevio_cde_forward_ckpt + odevio_cde_backward through the C ABI and the
+autograd bridge) against autograd through the CPU oracle (oracle/pose_cde.py) on the same seeded weights / inputs.
+
+What is compared: the reference trains PoseCDE with ``cdeint(..., adjoint=False)`` (PoseCDE.py:98-101) =
+plain autograd through torchdiffeq's solver loop, then ``loss.backward()`` (scripts/train_model.py:78).  The oracle's
+solver keeps the step sizes as python floats, so its autograd is exactly discretise-then-optimise with constant
+accepted steps -- the function the kernel differentiates.  Loss = the reference's training loss
+(scripts/train_model.py:72-77): 100 * MSE(angles) + MSE(translations) (+ a term on the returned z0 where noted).
+Tolerance: every parameter / input gradient within GRAD_RTOL = 2e-4 (max-norm relative, fp32 both sides), provided
+both sides took the same steps; when a borderline step was accepted on one side only, the bound is
+STEP_FLIP_RTOL (solver-tolerance order) and the line printed by the test says so."""
+
+import pytest
+import torch
+
+from helpers import rel_err
+from test_cde_gpu import data, make_pair
+
+pytestmark = pytest.mark.gpu
+
+GRAD_RTOL = 2e-4
+STEP_FLIP_RTOL = 1e-2
+
+
+def _loss(pose, gts):
+    return 100 * torch.nn.functional.mse_loss(pose[:, :, :3], gts[:, :, :3]) + \
+        torch.nn.functional.mse_loss(pose[:, :, 3:], gts[:, :, 3:])
+
+
+def _grads(model, fv, fi, ts, gts, prev, z0_weight):
+    model.zero_grad(set_to_none=True)
+    fv = fv.clone().requires_grad_(True)
+    fi = fi.clone().requires_grad_(True)
+    prev_ = None if prev is None else prev.clone().requires_grad_(True)
+    pose, z0 = model(fv, fi, ts, prev=prev_)
+    loss = _loss(pose, gts)
+    if z0_weight:
+        loss = loss + z0_weight * (z0 * z0).mean()
+    loss.backward()
+    out = {n: p.grad.detach().cpu().clone() for n, p in model.named_parameters() if p.grad is not None}
+    out["fv"], out["fi"] = fv.grad.cpu(), fi.grad.cpu()
+    if prev_ is not None:
+        out["prev"] = prev_.grad.cpu()
+    return loss.item(), out, pose.detach().cpu()
+
+
+def _compare(dev, B, S, Hc=32, prev=False, z0_weight=0.0, tol=GRAD_RTOL, ts_scale=1.0, seed=0, irregular=True,
+             mod_attrs=None, **over):
+    ref, mod = make_pair(dev, Hc=Hc, seed=seed, **over)
+    for k, v in (mod_attrs or {}).items():
+        setattr(mod, k, v)
+    fv, fi, ts = data(B, S, Hc, irregular, seed=seed + 2)
+    ts = ts * ts_scale
+    g = torch.Generator().manual_seed(9)
+    gts = 0.1 * torch.randn(B, S, 6, generator=g)
+    pv = 0.3 * torch.randn(B, Hc, generator=g) if prev else None
+    l_ref, g_ref, p_ref = _grads(ref, fv, fi, ts, gts, pv, z0_weight)
+    l_gpu, g_gpu, p_gpu = _grads(mod, fv.to(dev), fi.to(dev), ts.to(dev), gts.to(dev),
+                                 None if pv is None else pv.to(dev), z0_weight)
+    st = mod.last_stats.cpu().tolist()
+    ref_st = (ref.last_stats["n_steps"], ref.last_stats["n_accepted"], ref.last_stats["n_f_evals"])
+    assert st[3] == 0
+    same_steps = tuple(st[:3]) == ref_st
+    if not same_steps:
+        # a step whose error ratio sits within rounding of 1 was accepted on one side and rejected on the other (the
+        # forward tests show the oracle itself flips such steps under 2-ulp noise): the two sides then differentiate
+        # two slightly different -- equally valid -- discretisations, which agree to the solver tolerance only
+        tol = max(tol, STEP_FLIP_RTOL)
+    assert set(g_gpu) == set(g_ref), set(g_ref) ^ set(g_gpu)
+    errs = {k: rel_err(g_gpu[k], g_ref[k]) for k in g_ref}
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    print(f"steps {st[:3]} oracle {ref_st}  loss {l_gpu:.6f} / {l_ref:.6f}  pose error {rel_err(p_gpu, p_ref):.2e}  "
+          f"worst gradient error {max(errs.values()):.2e} ({max(errs, key=errs.get)})")
+    # the forward parity proper is tests/test_cde_gpu.py; here the poses only have to be the same solve
+    assert rel_err(p_gpu, p_ref) <= (2e-4 if same_steps else 5e-3)
+    assert not bad, (bad, errs)
+    assert abs(l_gpu - l_ref) <= (1e-5 if same_steps else 1e-3) * max(1.0, abs(l_ref))
+    return errs, st
+
+
+def test_cubic_dopri5(cuda_device):
+    """north_star cubic control path, dopri5: knot landings (jump re-evaluations), interpolated outputs."""
+    errs, st = _compare(cuda_device, 12, 10, cde_fn_num_layers=2, cde_interp="cubic")
+    assert st[1] > 10
+
+
+def test_reference_mode_linear_dopri5(cuda_device):
+    """Reference semantics (rectilinear path, integrated over row 0's seconds): only the time channel moves on the
+    first segment -- the feature gradients come through initial(X(knot 0)) alone."""
+    _compare(cuda_device, 12, 10, cde_fn_num_layers=2)
+
+
+def test_linear_crosses_knots(cuda_device):
+    """Steps landing on knots, values-only segments (feature gradients through dX/dt) and time-only segments."""
+    _compare(cuda_device, 9, 10, cde_fn_num_layers=2, ts_scale=4.0, seed=3)
+
+
+@pytest.mark.parametrize("interp,step", [("linear", None), ("cubic", None), ("cubic", 0.25), ("linear", 0.3)])
+def test_rk4_38(cuda_device, interp, step):
+    _compare(cuda_device, 8, 10, cde_fn_num_layers=2, cde_solver="rk4", cde_interp=interp, cde_step_size=step)
+
+
+@pytest.mark.parametrize("act,solver", [("softplus", "dopri5"), ("relu", "rk4"), ("leaky_relu", "rk4")])
+def test_activations(cuda_device, act, solver):
+    """The kinked activations on the fixed grid: under adaptive stepping a kink moves the accepted steps by rounding and
+    the ORACLE's own gradient is then ill-conditioned (same finding as tests/test_odernn_backward_gpu.py)."""
+    _compare(cuda_device, 8, 6, cde_fn_num_layers=3, cde_activation_fn=act, cde_interp="cubic", cde_solver=solver,
+             cde_step_size=0.25 if solver == "rk4" else None)
+
+
+def test_prev_state_and_returned_z0(cuda_device):
+    """z0 = prev (no initial network on the path); the returned z0 carries a loss term of its own."""
+    errs, _ = _compare(cuda_device, 6, 5, prev=True, z0_weight=0.5, cde_fn_num_layers=2, cde_interp="cubic")
+    assert "prev" in errs and "initial.0.weight" not in errs
+
+
+def test_returned_z0_through_initial(cuda_device):
+    _compare(cuda_device, 6, 5, z0_weight=0.5, cde_fn_num_layers=2, cde_interp="cubic")
+
+
+@pytest.mark.parametrize("Hc,B,rows", [(64, 20, 0), (128, 24, 0), (128, 40, 16), (24, 7, 8)])
+def test_shapes_and_tiles(cuda_device, Hc, B, rows):
+    _compare(cuda_device, B, 5, Hc=Hc, cde_fn_num_layers=2, cde_interp="cubic", cde_rows_per_tile=rows)
+
+
+def test_many_tiles_per_cta(cuda_device):
+    _compare(cuda_device, 8 * 148 + 13, 3, Hc=16, cde_fn_num_layers=1, cde_interp="cubic", cde_rows_per_tile=8,
+             cde_rtol=1e-3)
+
+
+def test_chunked_record_streams(cuda_device):
+    """A tiny record budget forces one launch per solver step; the chunks' weight gradients accumulate."""
+    errs1, st = _compare(cuda_device, 12, 6, cde_fn_num_layers=2, cde_interp="cubic")
+    errs2, _ = _compare(cuda_device, 12, 6, cde_fn_num_layers=2, cde_interp="cubic", mod_attrs={"bwd_record_gb": 1e-6})
+    assert st[1] > 4
+
+
+def test_soft_fusion_gradient(cuda_device):
+    """FusionModule 'soft' stays a torch op in front of the kernel: its parameters get their gradient through grad_x."""
+    errs, _ = _compare(cuda_device, 8, 5, cde_fn_num_layers=2, cde_interp="cubic", fuse_method="soft")
+    assert "fuse.net.0.weight" in errs
+
+
+def test_checkpoint_overflow_is_reported(cuda_device):
+    ref, mod = make_pair(cuda_device, cde_fn_num_layers=2, cde_interp="cubic")
+    mod.ckpt_steps = 3
+    fv, fi, ts = data(8, 10, 32, True)
+    with pytest.raises(RuntimeError, match="cde_ckpt_steps"):
+        mod(fv.to(cuda_device), fi.to(cuda_device), ts.to(cuda_device))

@@ -223,14 +223,6 @@ def test_unit_variance_features_measured_spread(cuda_device):
     assert err <= max(POSE_RTOL, 4 * max(spread, gap64))
 
 
-def test_training_raises(cuda_device):
-    import odevio_b200
-    ref, mod = make_pair(cuda_device)
-    fv, fi, ts = data(4, 4, 32, False)
-    with pytest.raises(odevio_b200.OdevioError):
-        mod(fv.to(cuda_device), fi.to(cuda_device), ts.to(cuda_device))
-
-
 def test_bounded_history_windows_match_unbounded_oracle(cuda_device):
     """f2: chained eval-mode windows with `cde_history_limit` -- the module keeps max(limit, S + 1)
     observations instead of the reference's ever-growing history (PoseCDE.py:88-92) -- against the ORACLE running the
