@@ -633,6 +633,35 @@ def run_cde(args, rank, world, local_rank):
                        # time-only segments legitimately skip all but one channel group
                        ("algorithmic_tflops" if interp == "cubic" else "nominal_tflops_incl_skipped_channels"):
                            flops / (per * 1e-3) / 1e12}
+        if args.train:
+            # training step of the same workload: checkpointing forward + fused backward (odevio_cde_backward), the
+            # reference's loss (scripts/train_model.py:72-77); gradients w.r.t. every parameter and the fused features
+            g = torch.Generator().manual_seed(5)
+            gts = (0.1 * torch.randn(B, S, 6, generator=g)).to(dev)
+            fvg, fig = fv.clone().requires_grad_(True), fi.clone().requires_grad_(True)
+            torch.cuda.reset_peak_memory_stats(dev)
+            fw = bw = 0.0
+            for it in range(1 + args.train_steps):
+                model.zero_grad(set_to_none=True)
+                fvg.grad = fig.grad = None
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
+                pose, _ = model(fvg, fig, ts)
+                ev[1].record()
+                loss = 100 * torch.nn.functional.mse_loss(pose[:, :, :3], gts[:, :, :3]) + \
+                    torch.nn.functional.mse_loss(pose[:, :, 3:], gts[:, :, 3:])
+                loss.backward()
+                ev[2].record()
+                torch.cuda.synchronize(dev)
+                if it > 0:
+                    fw += ev[0].elapsed_time(ev[1]); bw += ev[1].elapsed_time(ev[2])
+            n = max(args.train_steps, 1)
+            out[interp]["train"] = {"forward_ckpt_ms": fw / n, "loss_backward_ms": bw / n, "ms_per_step": (fw + bw) / n,
+                                    "seq_steps_per_s": B * S / ((fw + bw) / n * 1e-3), "steps": n, "warmup": 1,
+                                    "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "loss": float(loss.item()),
+                                    "backward_tflops": 3.0 * flops / (bw / n * 1e-3) / 1e12}
+            del fvg, fig, pose, loss
+            model._bwd_workspace = None
     if rank == 0:
         # roofline of the one cooperative launch of the cubic run (all of the forward is cde_fwd_kernel)
         from odevio_b200 import _lib

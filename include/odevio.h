@@ -252,8 +252,12 @@ typedef struct odevio_cde_cfg {
   float rtol;           /* reference 1e-4 */
   double step_size;     /* rk4: > 0 = fixed grid spacing with linear output interpolation, 0 = output times */
   int32_t max_steps;    /* dopri5 guard (status 1 when hit) */
-  int32_t rows_per_tile;/* 0 = auto; 8 or 16 */
-  int32_t reserved[6];
+  int32_t rows_per_tile;/* 0 = auto; 8 or 16 (CUDA-core kernel) */
+  int32_t precision;    /* ODEVIO_PRECISION_FP32 (default): CUDA-core FFMA kernel.  ODEVIO_PRECISION_FP16X3: the final
+                           Hc -> Hc*(Hc+1) Linear of CDEFunc on tcgen05 as 3xFP16 (fp32-level accuracy), weights resident in
+                           shared memory; Hc in {32, 64, 128}, B <= 32 * Hc, inference only (odevio_cde_forward_ckpt takes
+                           the CUDA-core kernel); other shapes: odevio_cde_workspace_bytes returns 0 / ODEVIO_E_SHAPE */
+  int32_t reserved[5];
 } odevio_cde_cfg;
 
 typedef struct odevio_cde_weights {

@@ -38,6 +38,10 @@ ODEVIO_API int32_t odevio_debug_odefunc_timeline(long long* host_dst);
  * of the ODEVIO_PRECISION_FP16X3 kernel (odernn_h3.cu). */
 ODEVIO_API int32_t odevio_debug_h3_timeline(long long* host_dst);
 
+/* Development: 32 clock64 sums of CTA 0 over all vector-field evaluations of the last tensor-core CDE launch (cde_tc.cu;
+ * slot meanings in tools/cde_tc_timeline.py).  Synchronises. */
+ODEVIO_API int32_t odevio_debug_cde_tc_timeline(long long* host_dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,7 +54,7 @@ class CdeCfg(C.Structure):
         ("B", C.c_int32), ("S", C.c_int32), ("So", C.c_int32), ("Hc", C.c_int32),
         ("n_layers", C.c_int32), ("activation", C.c_int32), ("solver", C.c_int32), ("interp", C.c_int32),
         ("atol", C.c_float), ("rtol", C.c_float), ("step_size", C.c_double),
-        ("max_steps", C.c_int32), ("rows_per_tile", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("max_steps", C.c_int32), ("rows_per_tile", C.c_int32), ("precision", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 

@@ -11,6 +11,8 @@
 #include "odernn_params.h"
 #include "odernn_tc.h"
 #include "odernn_h3.h"
+#include <stdlib.h>
+
 #include "cde_params.h"
 
 namespace odevio {
@@ -26,6 +28,10 @@ cudaError_t launch_cde_fwd(const CdeParams& prm, const DevTableau& tab, int RT, 
                            size_t smem_bytes, cudaStream_t stream);
 cudaError_t cde_pack_final(const float* W, const float* b, int Hc, int C, int Gc, int ngroups, float* Wp,
                            float* bp, cudaStream_t stream);
+cudaError_t cde_tc_debug_timeline(long long* host_dst);
+cudaError_t launch_cde_tc(const CdeParams& prm, const DevTableau& tab, int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t cde_tc_pack(const float* W, const float* b, int Hc, int C, unsigned char* Wimg, float* bval, float* W0t, float* b0,
+                        cudaStream_t stream);
 cudaError_t launch_cde_bwd(const CdeBwdParams& prm, const DevTableau& tab, int RT, int LL, int grid,
                            size_t smem_bytes, cudaStream_t stream);
 cudaError_t cde_pack_final_t(const float* W, int Hc, int C, int Gc, int ngroups, float* WT, cudaStream_t stream);
@@ -365,6 +371,8 @@ size_t ckpt_total_bytes(const odevio_odernn_cfg& c, const OdePlan& pl) {
 
 // ------------------------------------------------------------------ CDE planning
 struct CdePlan {
+  int tc, Bpad, nrt, RP;          // tensor-core kernel (cde_tc.cu): rows padded to 128, row tiles, rows per CTA in the row phase
+  size_t off_Wimg, off_bval, off_W0t, off_b0, off_state, off_Ximg, off_dXg;
   int RT, LL, R, ntiles, grid, nst, C, Cpad, Gc, ngroups, Ng, nsm;
   size_t buf_floats, staging_floats, stage_floats, smem_bytes;
   size_t off_Wmlp[kMaxLinears], off_Wfin, off_bfin, off_Winit, off_Wreg0;
@@ -373,6 +381,7 @@ struct CdePlan {
 };
 
 int plan_cde(const odevio_cde_cfg& c, CdePlan& pl) {
+  memset(&pl, 0, sizeof(pl));
   if (c.B <= 0 || c.S < 1 || c.S > kCdeMaxOut || c.So < 2 || c.So < c.S) return ODEVIO_E_SHAPE;
   if (c.Hc < 8 || c.Hc % 8 || c.Hc > 1024) return ODEVIO_E_SHAPE;
   if (c.n_layers < 1 || c.n_layers + 1 > ODEVIO_MAX_ODE_LINEARS) return ODEVIO_E_SHAPE;
@@ -386,6 +395,40 @@ int plan_cde(const odevio_cde_cfg& c, CdePlan& pl) {
   pl.nsm = nsm;
   pl.C = c.Hc + 1;
   pl.Cpad = (pl.C + 7) / 8 * 8;
+  pl.tc = 0;
+  if (c.precision == ODEVIO_PRECISION_FP16X3) {
+    // one CTA per hidden unit (cooperative grid), rows padded to the 128-row MMA tiles
+    if (c.Hc != 32 && c.Hc != 64 && c.Hc != 128) return ODEVIO_E_SHAPE;
+    if (c.Hc > nsm) return ODEVIO_E_SHAPE;
+    pl.tc = 1;
+    pl.Bpad = (c.B + 127) / 128 * 128;
+    pl.nrt = pl.Bpad / 128;
+    pl.RP = 4;
+    while (pl.RP < 32 && pl.RP * c.Hc < pl.Bpad) pl.RP *= 2;
+    if (pl.RP * c.Hc < pl.Bpad) return ODEVIO_E_SHAPE;
+    pl.grid = c.Hc;
+    size_t rows = static_cast<size_t>(c.Hc > pl.Cpad ? c.Hc : pl.Cpad);
+    if (rows < static_cast<size_t>(kRegHidden)) rows = kRegHidden;
+    pl.smem_bytes = 4u * c.Hc * c.Hc + 2u * 512u * c.Hc + (2 * rows * pl.RP + pl.RP + c.Hc + 512) * sizeof(float) + 64;
+    if (pl.smem_bytes > kSmemLimit) return ODEVIO_E_SHAPE;
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off = align_up(off + n, 64); return o; };
+    for (int j = 0; j < c.n_layers; ++j) pl.off_Wmlp[j] = take(static_cast<size_t>(c.Hc) * c.Hc);
+    pl.off_Winit = take(static_cast<size_t>(pl.Cpad) * c.Hc);
+    pl.off_Wreg0 = take(static_cast<size_t>(c.Hc) * kRegHidden);
+    pl.off_Wimg = take(static_cast<size_t>(c.Hc) * c.Hc * c.Hc);            // 4 Hc^3 bytes
+    pl.off_bval = take(static_cast<size_t>(c.Hc) * c.Hc);
+    pl.off_W0t = take(static_cast<size_t>(c.Hc) * c.Hc);
+    pl.off_b0 = take(static_cast<size_t>(c.Hc));
+    pl.off_state = take(static_cast<size_t>(2 + kMaxStages) * c.Hc * pl.Bpad);
+    pl.off_Ximg = take(static_cast<size_t>(pl.nrt) * 128 * c.Hc);          // nrt * 512 Hc bytes
+    pl.off_dXg = take(static_cast<size_t>(pl.Bpad) * c.Hc);
+    pl.off_red = take(static_cast<size_t>(2) * pl.grid * 2 * 2);
+    pl.off_bar = take(64);
+    pl.total_bytes = off * sizeof(float);
+    return 0;
+  }
+  if (c.precision != ODEVIO_PRECISION_FP32) return ODEVIO_E_ENUM;
   pl.Gc = 1024 / c.Hc; if (pl.Gc < 1) pl.Gc = 1; if (pl.Gc > pl.C) pl.Gc = pl.C;
   pl.ngroups = (pl.C + pl.Gc - 1) / pl.Gc;
   pl.Ng = pl.Gc * c.Hc;
@@ -852,6 +895,10 @@ int32_t odevio_debug_tc_timeline(long long* host_dst) {
   return host_dst ? odernn_tc_debug_timeline(host_dst) : ODEVIO_E_NULL;
 }
 
+int32_t odevio_debug_cde_tc_timeline(long long* host_dst) {
+  return host_dst ? static_cast<int32_t>(cde_tc_debug_timeline(host_dst)) : ODEVIO_E_NULL;
+}
+
 int32_t odevio_debug_h3_timeline(long long* host_dst) {
   return host_dst ? odernn_h3_debug_timeline(host_dst) : ODEVIO_E_NULL;
 }
@@ -1042,6 +1089,7 @@ static int32_t cde_forward_impl(const odevio_cde_cfg* cfg, const odevio_cde_weig
   CdePlan pl;
   const int rc = plan_cde(c, pl);
   if (rc != 0) return rc;
+  if (ckpt && pl.tc) return ODEVIO_E_ENUM;          // the checkpointing forward is the CUDA-core kernel
   if (ckpt) {
     if (ckpt_steps < 1 || !hidden) return ODEVIO_E_SHAPE;
     const size_t need = cde_ckpt_log_bytes(ckpt_steps) + cde_ckpt_step_floats(c, pl) * ckpt_steps * sizeof(float);
@@ -1064,9 +1112,19 @@ static int32_t cde_forward_impl(const odevio_cde_cfg* cfg, const odevio_cde_weig
     ODEVIO_CUDA_TRY(transpose_pack(w->cde_w[j], c.Hc, c.Hc, dst, c.Hc, 0, 0, stream));
     p.Wmlp[j] = dst; p.bmlp[j] = w->cde_b[j];
   }
-  ODEVIO_CUDA_TRY(cde_pack_final(w->cde_w[c.n_layers], w->cde_b[c.n_layers], c.Hc, pl.C, pl.Gc, pl.ngroups,
-                                 ws + pl.off_Wfin, ws + pl.off_bfin, stream));
-  p.Wfin = ws + pl.off_Wfin; p.bfin = ws + pl.off_bfin; p.Gc = pl.Gc; p.ngroups = pl.ngroups; p.Ng = pl.Ng;
+  if (pl.tc) {
+    unsigned char* wimg = reinterpret_cast<unsigned char*>(ws + pl.off_Wimg);
+    ODEVIO_CUDA_TRY(cde_tc_pack(w->cde_w[c.n_layers], w->cde_b[c.n_layers], c.Hc, pl.C, wimg, ws + pl.off_bval,
+                                ws + pl.off_W0t, ws + pl.off_b0, stream));
+    p.Wimg = wimg; p.bval = ws + pl.off_bval; p.W0t = ws + pl.off_W0t; p.b0 = ws + pl.off_b0;
+    p.Bpad = pl.Bpad; p.nrt = pl.nrt; p.RP = pl.RP;
+    { const char* ft = getenv("ODEVIO_CDE_FAST_TANH"); p.fast_tanh = (ft && ft[0] == '1') ? 1 : 0; }
+    p.state = ws + pl.off_state; p.Ximg = reinterpret_cast<unsigned char*>(ws + pl.off_Ximg); p.dXg = ws + pl.off_dXg;
+  } else {
+    ODEVIO_CUDA_TRY(cde_pack_final(w->cde_w[c.n_layers], w->cde_b[c.n_layers], c.Hc, pl.C, pl.Gc, pl.ngroups,
+                                   ws + pl.off_Wfin, ws + pl.off_bfin, stream));
+    p.Wfin = ws + pl.off_Wfin; p.bfin = ws + pl.off_bfin; p.Gc = pl.Gc; p.ngroups = pl.ngroups; p.Ng = pl.Ng;
+  }
   ODEVIO_CUDA_TRY(cudaMemsetAsync(ws + pl.off_Winit, 0, sizeof(float) * pl.Cpad * c.Hc, stream));
   ODEVIO_CUDA_TRY(transpose_pack(w->init_w, c.Hc, pl.C, ws + pl.off_Winit, c.Hc, 0, 0, stream));
   p.Winit = ws + pl.off_Winit; p.binit = w->init_b;
@@ -1074,7 +1132,7 @@ static int32_t cde_forward_impl(const odevio_cde_cfg* cfg, const odevio_cde_weig
   p.Wreg0 = ws + pl.off_Wreg0; p.breg0 = w->reg_b0; p.Wreg1 = w->reg_w1; p.breg1 = w->reg_b1;
   p.tobs = tobs; p.fv = fv; p.fi = fi; p.Dv = Dv; p.tout = tout; p.z0_in = z0_in;
   p.pose = pose; p.z0_out = z0_out; p.hout = hidden; p.stats = stats;
-  p.scratch = ws + pl.off_scratch; p.scratch_floats_per_tile = pl.scratch_floats_per_tile;
+  if (!pl.tc) { p.scratch = ws + pl.off_scratch; p.scratch_floats_per_tile = pl.scratch_floats_per_tile; }
   p.red = reinterpret_cast<double*>(ws + pl.off_red);
   p.bar = reinterpret_cast<unsigned int*>(ws + pl.off_bar);
   ODEVIO_CUDA_TRY(cudaMemsetAsync(p.bar, 0, 256, stream));
@@ -1089,7 +1147,8 @@ static int32_t cde_forward_impl(const odevio_cde_cfg* cfg, const odevio_cde_weig
   }
   DevTableau tab;
   if (!make_tableau(ODEVIO_SOLVER_DOPRI5, tab)) return ODEVIO_E_ENUM;
-  ODEVIO_CUDA_TRY(launch_cde_fwd(p, tab, pl.RT, pl.LL, pl.grid, pl.smem_bytes, stream));
+  if (pl.tc) ODEVIO_CUDA_TRY(launch_cde_tc(p, tab, pl.grid, pl.smem_bytes, stream));
+  else ODEVIO_CUDA_TRY(launch_cde_fwd(p, tab, pl.RT, pl.LL, pl.grid, pl.smem_bytes, stream));
   return 0;
 }
 
@@ -1105,7 +1164,7 @@ int32_t odevio_cde_forward(const odevio_cde_cfg* cfg, const odevio_cde_weights* 
 size_t odevio_cde_ckpt_bytes(const odevio_cde_cfg* cfg, int32_t ckpt_steps) {
   if (!cfg || ckpt_steps < 1) return 0;
   CdePlan pl;
-  if (plan_cde(*cfg, pl) != 0) return 0;
+  if (plan_cde(*cfg, pl) != 0 || pl.tc) return 0;
   return cde_ckpt_log_bytes(ckpt_steps) + cde_ckpt_step_floats(*cfg, pl) * ckpt_steps * sizeof(float);
 }
 
@@ -1123,7 +1182,7 @@ int32_t odevio_cde_forward_ckpt(const odevio_cde_cfg* cfg, const odevio_cde_weig
 size_t odevio_cde_backward_workspace_bytes(const odevio_cde_cfg* cfg, int32_t chunk_vjps) {
   if (!cfg) return 0;
   CdePlan pl;
-  if (plan_cde(*cfg, pl) != 0) return 0;
+  if (plan_cde(*cfg, pl) != 0 || pl.tc) return 0;
   CdeBwdPlan bp;
   if (plan_cde_bwd(*cfg, pl, chunk_vjps, bp) != 0) return 0;
   return bp.total_bytes;
@@ -1143,6 +1202,7 @@ int32_t odevio_cde_backward(const odevio_cde_cfg* cfg, const odevio_cde_weights*
   CdePlan pl;
   int rc = plan_cde(c, pl);
   if (rc != 0) return rc;
+  if (pl.tc) return ODEVIO_E_ENUM;                 // the backward replays the CUDA-core forward's checkpoints
   CdeBwdPlan bp;
   rc = plan_cde_bwd(c, pl, chunk_vjps, bp);
   if (rc != 0) return rc;

@@ -53,6 +53,16 @@ struct CdeParams {
   // training: checkpoints of every accepted step (cde_bwd.cu): ckpt[step][tile][Z, Y1, K0..K6][Hc][R] + the step log
   float* ckpt; int ckpt_cap;
   struct CdeStepRec* log;  // [1 + ckpt_cap]: slot 0 is the header (CdeLogHead)
+  // tensor-core kernel (cde_tc.cu): CTA h owns hidden unit h of the final Linear for ALL rows
+  int Bpad, nrt, RP;            // rows padded to 128, row tiles, rows per CTA in the row phase
+  float* state;                 // [9][Hc][Bpad] fp32 feature-major: Z, Y1, K0..K6
+  unsigned char* Ximg;          // [nrt][hi|lo][128 x Hc] fp16, K-major canonical image of the final Linear's input
+  float* dXg;                   // [nrt][Hc / 4][128 rows][4]  dX/dt of the value channels
+  const unsigned char* Wimg;    // [Hc (h)][hi|lo][Hc (c) x Hc (k)] fp16 K-major canonical image: W[h*C + 1 + c][k]
+  const float* bval;            // [Hc (h)][Hc (c)]  bias of the value channels
+  const float* W0t;             // [Hc (k)][Hc (h)]  time channel W[h*C + 0][k], K-major
+  const float* b0;              // [Hc]
+  int fast_tanh;                // epilogue tanh on the SFU approximations (absolute error ~2e-7) instead of tanhf
 };
 
 // One accepted solver step as the backward needs it (the step sizes are constants of the pullback).

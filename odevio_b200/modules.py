@@ -542,7 +542,8 @@ class PoseCDE(nn.Module):
     cubics with backward differences, integrated over the knot grid), ``cde_atol`` 1e-6,
     ``cde_rtol`` 1e-4 (PoseCDE.py:101), ``cde_step_size`` (fixed-grid rk4), ``cde_max_steps``, ``cde_history_limit``
     (cubic mode: eval-mode history bounded to that many observations, same poses; default: the reference's unbounded growth),
-    ``cde_rows_per_tile``, ``cde_ckpt_steps`` (training: accepted solver steps the checkpoints hold, default 256),
+    ``cde_rows_per_tile``, ``cde_precision`` ("auto" | "fp32" | "fp16x3": CUDA-core kernel or the tcgen05 kernel with the
+    final Linear's weights resident in shared memory, both fp32-accurate), ``cde_ckpt_steps`` (training: accepted solver steps the checkpoints hold, default 256),
     ``cde_bwd_record_gb`` (training: bound on the record streams of the deferred weight-gradient GEMMs, default 4).
     Training: under autograd ``forward`` runs ``odevio_cde_forward_ckpt`` and ``loss.backward()`` runs the fused
     ``odevio_cde_backward`` (odevio_b200/autograd.py) -- discretise-then-optimise with the accepted step sizes as
@@ -582,6 +583,10 @@ class PoseCDE(nn.Module):
         self.max_steps = int(getattr(opt, "cde_max_steps", 100000))
         self.rows_per_tile = int(getattr(opt, "cde_rows_per_tile", 0))
         self.history_limit = getattr(opt, "cde_history_limit", None)     # cubic mode: observations kept across windows
+        self.precision = getattr(opt, "cde_precision", "auto")           # "auto" | "fp32" | "fp16x3"
+        if self.precision not in ("auto", "fp32", "fp16x3"):
+            raise ValueError(f"cde_precision {self.precision} not supported")
+        self.last_precision = None
         self.ckpt_steps = int(getattr(opt, "cde_ckpt_steps", 256))       # training: accepted solver steps the checkpoints hold
         self.bwd_record_gb = float(getattr(opt, "cde_bwd_record_gb", 4.0))   # training: bound on the backward's record streams
         self.history = None          # (tobs [B,n], fv [B,n,.], fi [B,n,.] | None) in eval mode
@@ -667,7 +672,19 @@ class PoseCDE(nn.Module):
                self.regressor[2].weight, self.regressor[2].bias]
         return ps
 
-    def _cfg(self, B, S, So):
+    def _cfg(self, B, S, So, train=False):
+        """``precision``: "fp32" = the CUDA-core kernel, "fp16x3" = the tensor-core kernel (loud failure for shapes it does
+        not take), "auto" (default) = the tensor-core kernel whenever it takes the shape.  Training runs always use the
+        CUDA-core kernel (its checkpoints are what the fused backward replays)."""
+        cfg = self._cfg_base(B, S, So)
+        if train or self.precision == "fp32":
+            return cfg
+        cfg.precision = _lib.PRECISION["fp16x3"]
+        if self.precision == "auto" and _lib.load().odevio_cde_workspace_bytes(C.byref(cfg)) == 0:
+            cfg.precision = _lib.PRECISION["fp32"]
+        return cfg
+
+    def _cfg_base(self, B, S, So):
         cfg = _lib.default_cde_cfg()
         cfg.B, cfg.S, cfg.So, cfg.Hc = B, S, So, self.cde_hidden_dim
         cfg.n_layers = self.cde_fn_num_layers
@@ -698,8 +715,8 @@ class PoseCDE(nn.Module):
         B, So = tobs.shape
         S = tout.shape[0]
         dev = tobs.device
-        cfg = self._cfg(B, S, So)
         with torch.cuda.device(dev):
+            cfg = self._cfg(B, S, So, train=save_ckpt)
             nbytes = lib.odevio_cde_workspace_bytes(C.byref(cfg))
         if nbytes == 0:
             raise _lib.OdevioError(f"unsupported PoseCDE configuration for the fused kernel (Hc={cfg.Hc}, "
@@ -729,6 +746,7 @@ class PoseCDE(nn.Module):
                     _lib.dptr(hidden), _lib.dptr(stats), _lib.dptr(ws), nbytes, C.c_void_p(stream))
         _lib.check(rc)
         del keep
+        self.last_precision = "fp16x3" if cfg.precision == _lib.PRECISION["fp16x3"] else "fp32"
         return pose, z0, hidden, stats, (cfg, ckpt, cap)
 
     def check_status(self):

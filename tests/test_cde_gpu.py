@@ -24,6 +24,7 @@ HID_RTOL = 2e-5
 
 def make_pair(dev, Hc=32, seed=0, bias_std=0.05, train=True, **over):
     import odevio_b200
+    over.setdefault("cde_precision", "fp32")        # this file: the CUDA-core kernel (tests/test_cde_tc_gpu.py: tensor cores)
     opt = default_opt(v_f_len=Hc // 2, i_f_len=Hc // 2, cde_hidden_dim=Hc, **over)
     torch.manual_seed(seed)
     ref = OraclePoseCDE(opt)

@@ -1,0 +1,121 @@
+"""GPU parity of the tensor-core CDE forward (cde_tc.cu, ``cde_precision="fp16x3"``: CDEFunc's final Linear on tcgen05 as
+3xFP16 with the weights resident in shared memory) against the CPU oracle -- the same cases and the same criterion as the
+CUDA-core kernel's tests (tests/test_cde_gpu.py): poses <= 1e-5, widened only to 4x the oracle's own 2-8 ulp noise spread,
+identical (n_steps, n_accepted, n_f_evals) whenever the noisy oracle members reproduce them."""
+
+import pytest
+import torch
+
+from helpers import rel_err
+from test_cde_gpu import check, conditioning, data, make_pair, run
+
+pytestmark = pytest.mark.gpu
+
+
+def tc_pair(dev, **over):
+    ref, mod = make_pair(dev, cde_precision="fp16x3", **over)
+    return ref, mod
+
+
+def run_tc(ref, mod, *a, **k):
+    out = run(ref, mod, *a, **k)
+    assert mod.last_precision == "fp16x3"
+    return out
+
+
+@pytest.mark.parametrize("irregular", [False, True])
+def test_reference_mode_linear_dopri5(cuda_device, irregular):
+    ref, mod = tc_pair(cuda_device, cde_fn_num_layers=2)
+    check(run_tc(ref, mod, *data(12, 10, 32, irregular), cuda_device))
+
+
+def test_linear_crosses_knots(cuda_device):
+    """time-only segments (no feature phase at all) alternate with values-only segments; knot landings."""
+    ref, mod = tc_pair(cuda_device, cde_fn_num_layers=2)
+    fv, fi, ts = data(9, 10, 32, True, seed=3)
+    out = run_tc(ref, mod, fv, fi, ts * 4.0, cuda_device)
+    assert ref.last_stats["n_f_evals"] > 2 + 6 * ref.last_stats["n_steps"]
+    check(out)
+
+
+def test_cubic_dopri5(cuda_device):
+    ref, mod = tc_pair(cuda_device, cde_fn_num_layers=2, cde_interp="cubic")
+    out = run_tc(ref, mod, *data(12, 10, 32, True), cuda_device)
+    assert out["stats"][0] > 20
+    check(out)
+
+
+@pytest.mark.parametrize("interp,step", [("linear", None), ("cubic", None), ("cubic", 0.25), ("linear", 0.3)])
+def test_rk4_38(cuda_device, interp, step):
+    ref, mod = tc_pair(cuda_device, cde_fn_num_layers=2, cde_solver="rk4", cde_interp=interp, cde_step_size=step)
+    check(run_tc(ref, mod, *data(8, 10, 32, True), cuda_device))
+
+
+@pytest.mark.parametrize("act", ["relu", "leaky_relu", "softplus"])
+def test_activations(cuda_device, act):
+    ref, mod = tc_pair(cuda_device, cde_fn_num_layers=3, cde_activation_fn=act, cde_interp="cubic")
+    check(run_tc(ref, mod, *data(8, 6, 32, True), cuda_device))
+
+
+@pytest.mark.parametrize("Hc,B", [(64, 20), (128, 24), (32, 300), (64, 515), (128, 130)])
+def test_shapes_and_row_tiles(cuda_device, Hc, B):
+    """1 .. 5 row tiles of 128 sequences, 4 .. 16 rows per CTA in the row phase, ragged last tile."""
+    ref, mod = tc_pair(cuda_device, Hc=Hc, cde_fn_num_layers=2, cde_interp="cubic", cde_rtol=1e-3)
+    check(run_tc(ref, mod, *data(B, 5, Hc, True), cuda_device))
+
+
+def test_eval_mode_history_and_prev(cuda_device):
+    ref, mod = tc_pair(cuda_device, cde_fn_num_layers=2, train=False)
+    fv, fi, ts = data(6, 8, 32, True, seed=5)
+    check(run_tc(ref, mod, fv[:, :4], fi[:, :4], ts[:, :5], cuda_device))
+    g = torch.Generator().manual_seed(1)
+    prev = 0.3 * torch.randn(6, 32, generator=g)
+    check(run_tc(ref, mod, fv[:, 4:], fi[:, 4:], ts[:, 4:], cuda_device, prev=prev))
+
+
+def test_same_steps_as_the_cuda_core_kernel(cuda_device):
+    """The two kernels are the same solve: identical step counts, poses within the 3xFP16 product error."""
+    ref, mod = tc_pair(cuda_device, Hc=64, cde_fn_num_layers=2, cde_interp="cubic")
+    fv, fi, ts = (t.to(cuda_device) for t in data(200, 8, 64, True))
+    with torch.no_grad():
+        p_tc, _ = mod(fv, fi, ts)
+        st_tc = mod.last_stats.cpu().tolist()
+        mod.precision = "fp32"
+        p_fp, _ = mod(fv, fi, ts)
+        st_fp = mod.last_stats.cpu().tolist()
+    assert mod.last_precision == "fp32"
+    print(f"tensor-core vs CUDA-core kernel: pose {rel_err(p_tc.cpu(), p_fp.cpu()):.3e}, stats {st_tc} / {st_fp}")
+    assert rel_err(p_tc.cpu(), p_fp.cpu()) <= 2e-5
+    assert st_tc[3] == 0 and st_fp[3] == 0
+
+
+def test_unsupported_shape_is_loud_or_falls_back(cuda_device):
+    import odevio_b200
+    ref, mod = tc_pair(cuda_device, Hc=24, cde_fn_num_layers=2, cde_interp="cubic")
+    fv, fi, ts = (t.to(cuda_device) for t in data(7, 4, 24, True))
+    with torch.no_grad(), pytest.raises(odevio_b200.OdevioError):
+        mod(fv, fi, ts)
+    mod.precision = "auto"
+    with torch.no_grad():
+        mod(fv, fi, ts)
+    assert mod.last_precision == "fp32"
+
+
+@pytest.mark.parametrize("interp", ["linear", "cubic"])
+def test_configs2_full_size(cuda_device, interp):
+    """BASELINE configs[2] at FULL size (B = 1024, Hc = F = 128, n = 3, dopri5 1e-6 / 1e-4) on the tensor-core kernel."""
+    ref, mod = tc_pair(cuda_device, Hc=128, cde_fn_num_layers=3, cde_interp=interp)
+    fv, fi, ts = data(1024, 10, 128, True)
+    spread, stable = conditioning(ref, fv, fi, ts, None, None, n_members=2)
+    with torch.no_grad():
+        p_ref, z_ref = ref(fv, fi, ts)
+        p, z = mod(fv.to(cuda_device), fi.to(cuda_device), ts.to(cuda_device))
+    torch.cuda.synchronize()
+    mod.check_status()
+    assert mod.last_precision == "fp16x3"
+    out = dict(pose_err=rel_err(p.cpu(), p_ref), z0_err=rel_err(z.cpu(), z_ref), spread=spread, stable=stable,
+               stats=mod.last_stats.cpu().tolist(),
+               ref_stats=(ref.last_stats["n_steps"], ref.last_stats["n_accepted"], ref.last_stats["n_f_evals"]))
+    print(f"configs[2] {interp} (tensor cores): pose_err {out['pose_err']:.3e} (oracle noise spread {spread:.3e}, "
+          f"stable={stable}), stats kernel {out['stats'][:3]} oracle {out['ref_stats']}")
+    check(out)
