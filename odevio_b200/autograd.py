@@ -61,7 +61,8 @@ class _OdeRnnFunction(torch.autograd.Function):
         bad = int(ctx.status.max().item())
         if bad != 0:
             what = {1: "max_steps reached", 2: "non-finite error norm",
-                    3: "more solver iterations per interval than ode_ckpt_loops"}.get(bad, str(bad))
+                    3: "more solver iterations per interval than opt.ode_ckpt_loops (raise it; a solver without error "
+                       "control such as euler takes interval / ode_dt0 steps per interval)"}.get(bad, str(bad))
             raise RuntimeError(f"odevio_b200: cannot back-propagate, forward solve failed: {what}")
 
         nbytes = lib.odevio_odernn_backward_workspace_bytes(C.byref(cfg), ode_rows)

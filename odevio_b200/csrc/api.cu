@@ -371,7 +371,7 @@ size_t ckpt_total_bytes(const odevio_odernn_cfg& c, const OdePlan& pl) {
 
 // ------------------------------------------------------------------ CDE planning
 struct CdePlan {
-  int tc, Bpad, nrt, RP;          // tensor-core kernel (cde_tc.cu): rows padded to 128, row tiles, rows per CTA in the row phase
+  int tc, Bpad, nrt, RP, dx_cache;          // tensor-core kernel (cde_tc.cu): rows padded to 128, row tiles, rows per CTA in the row phase
   size_t off_Wimg, off_bval, off_W0t, off_b0, off_state, off_Ximg, off_dXg;
   int RT, LL, R, ntiles, grid, nst, C, Cpad, Gc, ngroups, Ng, nsm;
   size_t buf_floats, staging_floats, stage_floats, smem_bytes;
@@ -411,6 +411,10 @@ int plan_cde(const odevio_cde_cfg& c, CdePlan& pl) {
     if (rows < static_cast<size_t>(kRegHidden)) rows = kRegHidden;
     pl.smem_bytes = 4u * c.Hc * c.Hc + 2u * 512u * c.Hc + (2 * rows * pl.RP + pl.RP + c.Hc + 512) * sizeof(float) + 64;
     if (pl.smem_bytes > kSmemLimit) return ODEVIO_E_SHAPE;
+    // per-segment (m, d) cache of the control path's differences, when it fits next to the rest (1 KB static + alignment)
+    const size_t dxc = static_cast<size_t>(2) * pl.RP * pl.C * sizeof(float);
+    pl.dx_cache = pl.smem_bytes + dxc + 2048 <= kSmemLimit ? 1 : 0;
+    if (pl.dx_cache) pl.smem_bytes += dxc;
     size_t off = 0;
     auto take = [&](size_t n) { size_t o = off; off = align_up(off + n, 64); return o; };
     for (int j = 0; j < c.n_layers; ++j) pl.off_Wmlp[j] = take(static_cast<size_t>(c.Hc) * c.Hc);
@@ -1117,7 +1121,7 @@ static int32_t cde_forward_impl(const odevio_cde_cfg* cfg, const odevio_cde_weig
     ODEVIO_CUDA_TRY(cde_tc_pack(w->cde_w[c.n_layers], w->cde_b[c.n_layers], c.Hc, pl.C, wimg, ws + pl.off_bval,
                                 ws + pl.off_W0t, ws + pl.off_b0, stream));
     p.Wimg = wimg; p.bval = ws + pl.off_bval; p.W0t = ws + pl.off_W0t; p.b0 = ws + pl.off_b0;
-    p.Bpad = pl.Bpad; p.nrt = pl.nrt; p.RP = pl.RP;
+    p.Bpad = pl.Bpad; p.nrt = pl.nrt; p.RP = pl.RP; p.dx_cache = pl.dx_cache;
     { const char* ft = getenv("ODEVIO_CDE_FAST_TANH"); p.fast_tanh = (ft && ft[0] == '1') ? 1 : 0; }
     p.state = ws + pl.off_state; p.Ximg = reinterpret_cast<unsigned char*>(ws + pl.off_Ximg); p.dXg = ws + pl.off_dXg;
   } else {

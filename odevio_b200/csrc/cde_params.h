@@ -62,6 +62,7 @@ struct CdeParams {
   const float* bval;            // [Hc (h)][Hc (c)]  bias of the value channels
   const float* W0t;             // [Hc (k)][Hc (h)]  time channel W[h*C + 0][k], K-major
   const float* b0;              // [Hc]
+  int dx_cache;                 // (m, d) of the current knot segment cached in shared memory ([2][RP][C] floats fit)
   int fast_tanh;                // epilogue tanh on the SFU approximations (absolute error ~2e-7) instead of tanhf
 };
 

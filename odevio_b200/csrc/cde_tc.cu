@@ -72,6 +72,15 @@ __device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, uint32_t (&u)[32]) 
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tc_tmem_ld16(uint32_t taddr, uint32_t (&u)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tc_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void tc_split(float x, __half& hi, __half& lo) {
@@ -88,7 +97,7 @@ struct TCtx {
   const CdeParams* prm;
   int tid, warp, lane;
   unsigned char* wimg; unsigned char* xring;
-  float* bufA; float* bufB; float* dX0; float* biasv; float* part;
+  float* bufA; float* bufB; float* dX0; float* biasv; float* part; float* dxc;
   uint32_t oA, oB, oRing, oBias;        // byte offsets of bufA / bufB / xring / biasv from the dynamic shared-memory base
   double* redsm;
   uint64_t* full; uint64_t* empty; uint64_t* tfull; uint64_t* tempty; uint64_t* wbar; uint64_t* wfull; uint64_t* wfree;
@@ -328,6 +337,7 @@ cde_tc_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ Dev
   c.dX0 = fsm; fsm += p.RP;
   c.biasv = fsm; fsm += Hc;
   c.part = fsm; fsm += 2 * 2 * 128;
+  c.dxc = fsm;                                          // [2][RP][C] when p.dx_cache
   c.redsm = redsm;
   c.oA = static_cast<uint32_t>(reinterpret_cast<unsigned char*>(c.bufA) - smem);
   c.oB = static_cast<uint32_t>(reinterpret_cast<unsigned char*>(c.bufB) - smem);
@@ -394,6 +404,7 @@ cde_tc_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ Dev
     return p.tout[k];
   };
 
+  int cached_seg = -1;                                  // knot segment whose (m, d) are in shared memory
   // ================================================================ one vector-field evaluation -> K[out]
   auto eval_now = [&](int kind, int stage, float dts, float t, int perturb, int out, bool save_y1) {
     ++n_f;
@@ -410,9 +421,47 @@ cde_tc_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ Dev
       Recipe rc{kind, stage, dts, 0.f};
       build_rows(c, rc, tab, save_y1);
       TC_ACC(1, t_ev0);
-      // dX/dt of my rows: channel 0 -> dX0 (shared), value channels -> dXg [row][c - 1]   (cde_fwd.cu: control_derivative)
+      // dX/dt of my rows: channel 0 -> dX0 (shared), value channels -> dXg   (cde_fwd.cu: control_derivative)
       const float s = sub_(tt, static_cast<float>(seg));
       const int nch = time_only ? 1 : p.C;
+      if (p.dx_cache) {
+        // m and d of a knot segment do not change between evaluations: keep them in shared memory (the observation
+        // loads were 7 k clk of latency per evaluation), v = m + (d - m) ((4 - 3 s) s) as before
+        float* mS = c.dxc; float* dS = c.dxc + p.C * RP;
+        if (seg != cached_seg) {
+          for (int e = c.tid; e < RP * p.C; e += TC_WORK_THREADS) {
+            const int r = e / p.C, ch = e - r * p.C;
+            const int b = c.row0 + r;
+            float m = 0.f, d = 0.f;
+            if (b < p.B) {
+              if (p.interp == CDE_INTERP_LINEAR) {
+                const int mm = seg >> 1;
+                if (((seg & 1) == 0) == (ch == 0)) d = sub_(obs_val_t(p, b, mm + 1, ch), obs_val_t(p, b, mm, ch));
+                m = d;
+              } else {
+                const float x0 = obs_val_t(p, b, seg, ch), x1 = obs_val_t(p, b, seg + 1, ch);
+                d = sub_(x1, x0);
+                m = seg == 0 ? d : sub_(x0, obs_val_t(p, b, seg - 1, ch));
+              }
+            }
+            mS[e] = m; dS[e] = d;
+          }
+          cached_seg = seg;
+          named_bar_sync(1, TC_WORK_THREADS);
+        }
+        const float wq = mul_(sub_(4.0f, mul_(3.0f, s)), s);
+        for (int e = c.tid; e < RP * nch; e += TC_WORK_THREADS) {
+          const int r = e / nch, ch = e - r * nch;
+          const int b = c.row0 + r;
+          const float m = mS[r * p.C + ch], d = dS[r * p.C + ch];
+          const float v = p.interp == CDE_INTERP_LINEAR ? d : add_(m, mul_(sub_(d, m), wq));
+          if (ch == 0) c.dX0[r] = v;
+          else {
+            const int cc = ch - 1;
+            __stcg(p.dXg + (static_cast<size_t>(b >> 7) * (Hc >> 2) + (cc >> 2)) * 512 + static_cast<size_t>(b & 127) * 4 + (cc & 3), v);
+          }
+        }
+      } else
       for (int e = c.tid; e < RP * nch; e += TC_WORK_THREADS) {
         const int r = e / nch, ch = e - r * nch;
         const int b = c.row0 + r;
@@ -566,10 +615,6 @@ cde_tc_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ Dev
         float sum = 0.f;
         for (int cb = hf; cb < (Hc >> 5); cb += 2) {
           const uint32_t taddr = c.tmem + (static_cast<uint32_t>(32 * q) << 16) + s2 * 2u * Hc + 32u * cb;
-          uint32_t um[32], ux[32];
-          tc_tmem_ld32(taddr + Hc, ux);
-          tc_tmem_ld32(taddr, um);
-          tc_tmem_ld_wait();
           float dx[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) dx[i] = dxn[i];
@@ -586,6 +631,11 @@ cde_tc_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ Dev
               }
             }
           }
+          // (two x16 loads with a wait each were measured slower than one x32 pair: 51 k vs 41 k clk per evaluation)
+          uint32_t um[32], ux[32];
+          tc_tmem_ld32(taddr + Hc, ux);
+          tc_tmem_ld32(taddr, um);
+          tc_tmem_ld_wait();
           if (p.fast_tanh) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {

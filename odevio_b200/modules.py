@@ -513,8 +513,12 @@ class PoseODERNN(nn.Module):
         return out[0]
 
     def update_method(self):
-        """Reference PoseODERNN.update_method (PoseODERNN.py:77-86): switch to Euler with a fixed-step
-        controller (one step of ``ode_substeps`` per interval)."""
+        """Reference PoseODERNN.update_method (PoseODERNN.py:77-86): switch the solver to Euler.  Euler has no embedded
+        error estimate, so the controller accepts every step and never changes the step size: each interval is walked in
+        steps of ``ode_dt0`` (1e-4 s: ~1000 steps per 0.1 s interval), as restated in oracle/torchode_like.py [recalled
+        torchode semantics].  Training through it therefore needs ``opt.ode_ckpt_loops`` >= interval / ode_dt0
+        checkpoint slots per interval (default 16): the forward reports ODEVIO_STATUS_CKPT_OVERFLOW otherwise and
+        ``loss.backward()`` raises, naming the knob."""
         self.ode_solver = self._set_solver("euler")
 
     def check_status(self):
@@ -524,7 +528,8 @@ class PoseODERNN(nn.Module):
         bad = int(self.last_status.max().item())
         if bad != 0:
             what = {1: "max_steps reached", 2: "non-finite error norm",
-                    3: "more solver iterations per interval than ode_ckpt_loops (training checkpoints)"}.get(bad, str(bad))
+                    3: "more solver iterations per interval than ode_ckpt_loops (training checkpoints; a solver without "
+                       "error control such as euler takes interval / ode_dt0 steps)"}.get(bad, str(bad))
             raise RuntimeError(f"ODE solve failed for some rows: {what}")
 
 
