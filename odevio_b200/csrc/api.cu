@@ -165,9 +165,11 @@ int plan_odernn(const odevio_odernn_cfg& c, OdePlan& pl) {
   if (c.solver < 0 || c.solver > ODEVIO_SOLVER_RK4_38) return ODEVIO_E_ENUM;
   if (c.precision != ODEVIO_PRECISION_FP32 && c.precision != ODEVIO_PRECISION_TF32X3 && c.precision != ODEVIO_PRECISION_FP16X3)
     return ODEVIO_E_ENUM;
-  // tensor-core solvers (odernn_tc.cu, odernn_h3.cu): end point rule y1, no step trace.  Training (save_checkpoints): the
-  // one-launch FP16X3 forward writes the checkpoints itself; every other combination runs the FMA forward.
-  if (c.precision != ODEVIO_PRECISION_FP32 && !c.save_checkpoints && (c.endpoint_dense || c.trace_steps)) return ODEVIO_E_ENUM;
+  // tensor-core solvers: no step trace; the literal dense end point (endpoint_dense) is in odernn_h3.cu (FP16X3), not in
+  // the round-1 3xTF32 kernel.  Training (save_checkpoints): the one-launch FP16X3 forward writes the checkpoints itself;
+  // every other combination runs the FMA forward.
+  if (c.precision != ODEVIO_PRECISION_FP32 && !c.save_checkpoints &&
+      (c.trace_steps || (c.endpoint_dense && c.precision != ODEVIO_PRECISION_FP16X3))) return ODEVIO_E_ENUM;
   if (c.rows_per_tile != 0 && c.rows_per_tile != 4 && c.rows_per_tile != 8 && c.rows_per_tile != 16) return ODEVIO_E_SHAPE;
   const bool fixed = c.solver == ODEVIO_SOLVER_RK4 || c.solver == ODEVIO_SOLVER_RK4_38;
   if (fixed && c.substeps < 1) return ODEVIO_E_SHAPE;

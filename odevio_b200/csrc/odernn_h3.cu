@@ -106,7 +106,7 @@ struct H3Params {
   DevTableau tab;
   int adaptive, substeps;
   float atol, rtol, dt0, safety, fmin, fmax;
-  int accept_strict, floor_factor, max_steps, exact_landing;
+  int accept_strict, floor_factor, max_steps, exact_landing, endpoint_dense;
   const float* h0;           // [L][B][D] initial hidden state or nullptr (zeros); may alias hT
   float* hT;                 // [L][B][D] final hidden state
   const float* ts; int ts_ld;
@@ -127,6 +127,8 @@ struct H3Rows {      // per-row solver state, replicated in every CTA of the clu
   float t[NR], tend[NR], tmin[NR], tmax[NR];
   int run[NR], upd[NR], nsteps[NR], nacc[NR], status[NR];
   float dtstep[NR];                   // the step size the current iteration was taken with (checkpoints)
+  float x[NR];                        // dense end point: (t_end - t) / dt of the step that reached t_end
+  int toeval[NR], noteval[NR];        // this iteration's step reached t_end / t_end not evaluated yet
   int nsaved[NR / 4];                 // stored solver iterations of every checkpoint sub-tile in the current interval
   long long grow[NR];                 // state row of the tile's row (-1: beyond M)
   int bidx[NR], lyr[NR];
@@ -542,7 +544,9 @@ __device__ __forceinline__ void h3_fixed_commit(const H3Slice<NR>& sl, const Dev
 
 // accepted rows: Y <- Y1, FSAL carry K0 <- K[ns - 1]; other rows keep both
 template <int NR>
-__device__ __forceinline__ void h3_commit_rows(const H3Slice<NR>& sl, int ns, int fsal, const int* upd_rows) {
+__device__ __forceinline__ void h3_commit_rows(const H3Slice<NR>& sl, const DevTableau& tb, const int* upd_rows,
+                                               const int* toeval_rows, const float* x_rows, const float* dt_rows) {
+  const int ns = tb.n_stages, fsal = tb.fsal;
   float* Y = sl.base + kMaxStages * sl.arr;
   const float* Y1 = sl.base + (kMaxStages + 1) * sl.arr;
   const float* Kl = sl.base + static_cast<size_t>(ns - 1) * sl.arr;
@@ -555,7 +559,47 @@ __device__ __forceinline__ void h3_commit_rows(const H3Slice<NR>& sl, int ns, in
       if (!(u.x | u.y | u.z | u.w)) continue;
       const size_t off = static_cast<size_t>(f) * NR + n0;
       const float4 a = h3_ld4(Y1 + off), o = h3_ld4(Y + off);
-      h3_st4(Y + off, make_float4(u.x ? a.x : o.x, u.y ? a.y : o.y, u.z ? a.z : o.z, u.w ? a.w : o.w));
+      float4 v = make_float4(u.x ? a.x : o.x, u.y ? a.y : o.y, u.z ? a.z : o.z, u.w ? a.w : o.w);
+      const int4 te = *reinterpret_cast<const int4*>(toeval_rows + n0);
+      if (te.x | te.y | te.z | te.w) {
+        // dense output of the accepted step at x = (t_end - t) / dt: quartic through (y0, y1, dt f0, dt f1, y_mid), or the
+        // linear interpolant for the tableaus without b_mid -- operation order of odernn_fwd.cu: commit_pass / the oracle
+        const float4 dtv = *reinterpret_cast<const float4*>(dt_rows + n0);
+        const float4 xv = *reinterpret_cast<const float4*>(x_rows + n0);
+        const float y0[4] = {o.x, o.y, o.z, o.w}, y1[4] = {a.x, a.y, a.z, a.w};
+        const float dts[4] = {dtv.x, dtv.y, dtv.z, dtv.w}, xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        const int tev[4] = {te.x, te.y, te.z, te.w};
+        float out[4] = {v.x, v.y, v.z, v.w};
+        if (tb.has_mid) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          bool any = false;
+          for (int j = 0; j < ns; ++j) {
+            const float bm = tb.bmid[j];
+            if (bm == 0.f) continue;
+            const float4 k = h3_ld4(sl.base + static_cast<size_t>(j) * sl.arr + off);
+            const float kk[4] = {k.x, k.y, k.z, k.w};
+            for (int q = 0; q < 4; ++q) acc[q] = any ? add_(acc[q], mul_(kk[q], bm)) : mul_(kk[q], bm);
+            any = true;
+          }
+          const float4 k0 = h3_ld4(sl.base + off), kl = h3_ld4(Kl + off);
+          const float k0a[4] = {k0.x, k0.y, k0.z, k0.w}, kla[4] = {kl.x, kl.y, kl.z, kl.w};
+          for (int q = 0; q < 4; ++q) {
+            if (!tev[q]) continue;
+            const float ymid = add_(y0[q], mul_(dts[q], acc[q]));
+            const float f0 = mul_(dts[q], k0a[q]), f1 = mul_(dts[q], kla[q]);
+            const float ca = add_(sub_(mul_(2.0f, sub_(f1, f0)), mul_(8.0f, add_(y1[q], y0[q]))), mul_(16.0f, ymid));
+            const float cb = sub_(add_(add_(sub_(mul_(5.0f, f0), mul_(3.0f, f1)), mul_(18.0f, y0[q])), mul_(14.0f, y1[q])),
+                                  mul_(32.0f, ymid));
+            const float cc = add_(sub_(sub_(sub_(f1, mul_(4.0f, f0)), mul_(11.0f, y0[q])), mul_(5.0f, y1[q])), mul_(16.0f, ymid));
+            const float x = xs[q];
+            out[q] = add_(mul_(add_(mul_(add_(mul_(add_(mul_(ca, x), cb), x), cc), x), f0), x), y0[q]);
+          }
+        } else {
+          for (int q = 0; q < 4; ++q) if (tev[q]) out[q] = add_(y0[q], mul_(xs[q], sub_(y1[q], y0[q])));
+        }
+        v = make_float4(out[0], out[1], out[2], out[3]);
+      }
+      h3_st4(Y + off, v);
       if (fsal) {
         const float4 b = h3_ld4(Kl + off), o0 = h3_ld4(sl.base + off);
         h3_st4(sl.base + off, make_float4(u.x ? b.x : o0.x, u.y ? b.y : o0.y, u.z ? b.z : o0.z, u.w ? b.w : o0.w));
@@ -770,6 +814,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
         rs.t[r] = t0; rs.tend[r] = t1;
         rs.tmin[r] = fminf(t0, t1); rs.tmax[r] = fmaxf(t0, t1);
         rs.nsteps[r] = 0; rs.nacc[r] = 0; rs.upd[r] = 0; rs.status[r] = 0;
+        rs.toeval[r] = 0; rs.noteval[r] = 1; rs.x[r] = 1.0f;
         if (p.adaptive) {
           rs.dt[r] = fminf(fmaxf(p.dt0, sub_(rs.tmin[r], t0)), sub_(rs.tmax[r], t0));
           run = (valid && t0 < t1) ? 1 : 0;
@@ -867,7 +912,13 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
             rs.nsteps[r] += run;
             rs.nacc[r] += upd;
             const bool lands = p.exact_landing && dt >= sub_(tend, t);
-            t = upd ? (lands ? tend : add_(t, dt)) : t;
+            const float t_new = upd ? (lands ? tend : add_(t, dt)) : t;
+            // literal torchode end point (cfg.endpoint_dense): the state at t_end is the dense output of the step that
+            // reached it (odernn_fwd.cu: controller / commit_pass)
+            const int toeval = (upd && t_new >= tend && rs.noteval[r]) ? 1 : 0;
+            if (toeval) { rs.x[r] = __fdiv_rn(sub_(tend, t), dt); rs.noteval[r] = 0; }
+            rs.toeval[r] = toeval && p.endpoint_dense;
+            t = t_new;
             rs.upd[r] = upd;
             if (run && !finite) rs.status[r] = max(rs.status[r], 2);
             run = (run && t < tend && finite) ? 1 : 0;
@@ -883,7 +934,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
           if (p.ckpt) h3_ckpt_iteration<NR>(p, rs, tile, interval, Yc, own_f0, own_nf, crank);
           if (tid == 0) H3_STAMP(8);
           // ---- commit: accepted rows take y1; FSAL carry (end point rule "y1": exact landing makes y1 the value at t_end)
-          if (epi) h3_commit_rows<NR>(sl, ns, tb.fsal, rs.upd);
+          if (epi) h3_commit_rows<NR>(sl, tb, rs.upd, rs.toeval, rs.x, rs.dtstep);
           if (tid == 0) H3_STAMP(9);
         } else {
           if (p.ckpt) {
@@ -1216,7 +1267,7 @@ int H3Evolve::prepare(const odevio_odernn_cfg& c, const DevTableau& tab, bool ad
   p.ntiles = pl.ntiles;
   p.tab = tab; p.adaptive = adaptive ? 1 : 0; p.substeps = c.substeps;
   p.atol = c.atol; p.rtol = c.rtol; p.dt0 = c.dt0; p.safety = c.safety; p.fmin = c.factor_min; p.fmax = c.factor_max;
-  p.accept_strict = c.accept_strict; p.floor_factor = c.floor_factor; p.max_steps = c.max_steps; p.exact_landing = c.exact_landing;
+  p.accept_strict = c.accept_strict; p.floor_factor = c.floor_factor; p.max_steps = c.max_steps; p.exact_landing = c.exact_landing; p.endpoint_dense = c.endpoint_dense;
   p.do_jump = with_jump ? 1 : 0;
   return 0;
 }

@@ -21,7 +21,9 @@ defaults; ``getattr(opt, name, default)``):
   ode_max_steps=100000  per-interval guard (rows still running get status MAX_STEPS)
   ode_accept_strict=True, ode_floor_factor=False                         (SURVEY.md A.1 switches)
   ode_endpoint="y1" | "dense", ode_exact_landing=True   ("dense"/False = literal fp32 torchode
-                        arithmetic, which is ill-conditioned; see oracle/torchode_like.py)
+                        arithmetic, which is ill-conditioned; see oracle/torchode_like.py).  "dense" runs in
+                        the FMA kernel ("fp32") and in the one-launch tcgen05 kernel ("fp16x3"); training takes
+                        "dense" with exact landing (x = 1: the dense output is y1), not the literal variant
   ode_rows_per_tile=0   (auto) | 4 | 8 | 16
   ode_ckpt_loops=0      training: stored solver iterations per interval and tile (0 = 16)
 
@@ -403,15 +405,21 @@ class PoseODERNN(nn.Module):
         if save_ckpt:
             # training: "fp16x3" keeps the checkpointed forward on tcgen05 (one launch; the library falls back to the FMA
             # forward for GRU / L > 2), the fused backward is the FMA kernel either way; "tf32x3" has no training forward
-            if cfg.precision == _lib.PRECISION["tf32x3"] or self.endpoint == "dense":
+            if cfg.precision == _lib.PRECISION["tf32x3"]:
                 cfg.precision = _lib.PRECISION["fp32"]
+            if self.endpoint == "dense" and self.exact_landing:
+                # with exact landing the step that reaches t_end has x = (t_end - t) / dt = 1, where the quartic dense
+                # output IS y1 (its coefficients sum to y1 - y0 identically): the training forward / backward use the y1
+                # rule -- the same function and gradient, the forward differs from the dense evaluation by rounding only
+                cfg.endpoint_dense = 0
             cfg.save_checkpoints = 1
             cfg.ckpt_loops = self.ckpt_loops
             if cfg.rows_per_tile == 16:
                 cfg.rows_per_tile = 8
             ckpt_bytes = lib.odevio_odernn_ckpt_bytes(C.byref(cfg))
             if ckpt_bytes == 0:
-                raise _lib.OdevioError("training through the fused path needs ode_endpoint='y1', rows_per_tile in "
+                raise _lib.OdevioError("training through the fused path needs ode_endpoint='y1' (or 'dense' with "
+                                       "ode_exact_landing=True, which is the same function), rows_per_tile in "
                                        "{0, 4, 8} and D, H multiples of 128 "
                                        f"(endpoint={self.endpoint}, D={cfg.D}, H={cfg.H})")
             ckpt = torch.empty(ckpt_bytes, dtype=torch.uint8, device=dev)

@@ -134,10 +134,30 @@ def test_tc_evolve_state(cuda_device, prec):
     assert (ns == want["n_steps"]).float().mean().item() >= 0.97
 
 
-@pytest.mark.parametrize("prec", PRECISIONS)
-def test_tc_rejects_training_and_dense(cuda_device, prec):
-    """The tensor-core path is inference-only: training falls back to the FMA kernels (precision forced to fp32
-    for the checkpointed forward), the dense end-point rule is refused with a clear error."""
+def test_h3_literal_torchode_end_point(cuda_device):
+    """The literal torchode end point -- quartic dense output of the step that reaches t_end, no exact landing (SURVEY.md
+    A.1's reading of `ode_solution.ys[:, -1, :]`, PoseODERNN.py:75) -- on the one-launch tcgen05 kernel, held to the bound
+    the FMA kernel's test uses (tests/test_odernn_gpu.py::test_literal_torchode_arithmetic: the mode is ill-conditioned in
+    fp32, the ORACLE itself moves by > 1e-5 under 1e-7 weight noise); plus the well-conditioned variant (dense end point
+    WITH exact landing: x = 1, the quartic collapses onto y1 up to rounding) at the usual 1e-5 criterion."""
+    ref, mod = make_pair(cuda_device, ode_endpoint="dense", ode_exact_landing=False, bias_std=0.05, ode_precision="fp16x3")
+    out = run_pair(ref, mod, *inputs(16, irregular=True))
+    assert out["status_max"] == 0
+    print(f"literal end point on fp16x3: pose {out['pose_err']:.2e}, h {out['h_err']:.2e}")
+    assert out["pose_err"] <= 5e-4, _summary(out)
+    assert out["h_err"] <= 5e-4, _summary(out)
+    ref, mod = make_pair(cuda_device, ode_endpoint="dense", ode_exact_landing=True, bias_std=0.05, ode_precision="fp16x3")
+    out = run_pair(ref, mod, *inputs(16, irregular=True), ensemble=3)
+    _check(out)
+    # heun has no b_mid: linear interpolant between y0 and y1
+    ref, mod = make_pair(cuda_device, ode_endpoint="dense", ode_exact_landing=False, bias_std=0.05, ode_precision="fp16x3",
+                         ode_solver="heun", ode_rtol=1e-3)
+    out = run_pair(ref, mod, *inputs(8, S=4, irregular=True))
+    assert out["status_max"] == 0 and out["pose_err"] <= 5e-4, _summary(out)
+
+
+def test_tc_rejects_dense_on_tf32x3(cuda_device, prec="tf32x3"):
+    """The round-1 3xTF32 kernel has no dense end-point rule: refused with a clear error (the FP16X3 kernel has it)."""
     import odevio_b200
     from oracle.pose_odernn import default_opt
     mod = odevio_b200.PoseODERNN(default_opt(ode_precision=prec, ode_endpoint="dense")).to(cuda_device).eval()
