@@ -230,6 +230,25 @@ ODEVIO_API int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const od
                                const odevio_odernn_grads* g, float* grad_fused, float* grad_h0,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * The same backward, one RANGE of observation intervals [i_lo, i_hi] per call: bounds the record streams of the deferred
+ * weight-gradient GEMMs (they are ~20 MB per sequence at configs[3]: 84 GB for B = 4096 in one piece).  Call with the same
+ * workspace from the last range (i_hi = S - 1) down to the first (i_lo = 0); `rec_base` holds, for the (tile, interval)
+ * pairs of the range, their first record row RELATIVE to the range; `ode_rows` = record rows of this range,
+ * `ode_rows_plan` = the capacity the workspace was sized with (odevio_odernn_backward_workspace_bytes(cfg, ode_rows_plan),
+ * >= every range's ode_rows).  The hidden-state gradient is carried between the calls inside the workspace; the ODEFunc
+ * weight gradients accumulate over the calls (the first call overwrites), the rnn / regressor gradients, grad_fused and
+ * grad_h0 are complete after the i_lo = 0 call.  odevio_odernn_backward == one range [0, S - 1].
+ */
+ODEVIO_API int32_t odevio_odernn_backward_range(const odevio_odernn_cfg* cfg, const odevio_odernn_weights* w,
+                                                const float* fv, const float* fi, int32_t Dv,
+                                                const void* ckpt, size_t ckpt_bytes,
+                                                const int64_t* rec_base, int64_t ode_rows, int64_t ode_rows_plan,
+                                                int32_t i_lo, int32_t i_hi,
+                                                const float* grad_pose, const float* grad_hT,
+                                                const odevio_odernn_grads* g, float* grad_fused, float* grad_h0,
+                                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ Neural CDE (PoseCDE) ---- */
 
 /* cde solver menu: torchdiffeq names reachable through src/models/PoseCDE.py:72,101 */

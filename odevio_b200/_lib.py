@@ -126,6 +126,10 @@ def load():
     lib.odevio_odernn_backward.argtypes = [
         C.POINTER(OdeRnnCfg), C.POINTER(OdeRnnWeights), _FP, _FP, C.c_int32, _FP, C.c_size_t,
         _FP, C.c_int64, _FP, _FP, C.POINTER(OdeRnnGrads), _FP, _FP, _FP, C.c_size_t, _FP]
+    lib.odevio_odernn_backward_range.restype = C.c_int32
+    lib.odevio_odernn_backward_range.argtypes = [
+        C.POINTER(OdeRnnCfg), C.POINTER(OdeRnnWeights), _FP, _FP, C.c_int32, _FP, C.c_size_t,
+        _FP, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _FP, _FP, C.POINTER(OdeRnnGrads), _FP, _FP, _FP, C.c_size_t, _FP]
     lib.odevio_cde_default_cfg.restype = None
     lib.odevio_cde_default_cfg.argtypes = [C.POINTER(CdeCfg)]
     lib.odevio_cde_workspace_bytes.restype = C.c_size_t

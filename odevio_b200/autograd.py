@@ -54,23 +54,39 @@ class _OdeRnnFunction(torch.autograd.Function):
         _lib.check(lib.odevio_odernn_geometry(C.byref(cfg), geo))
         R, ntiles, ns = geo[1], geo[2], geo[3]
         nloops = ctx.ckpt[: ntiles * S * 4].view(torch.int32).to(torch.int64)
-        rows = nloops * (ns * R)
-        rec_base = (torch.cumsum(rows, 0) - rows).contiguous()
-        # the one host read of the training step: record-stream length (+ solver status)
-        ode_rows = int(rows.sum().item())
+        rows = (nloops * (ns * R)).view(ntiles, S)
+        # the one host read of the training step: record rows per observation interval (+ solver status)
+        per_iv = [int(v) for v in rows.sum(0).cpu()]
         bad = int(ctx.status.max().item())
         if bad != 0:
             what = {1: "max_steps reached", 2: "non-finite error norm",
                     3: "more solver iterations per interval than opt.ode_ckpt_loops (raise it; a solver without error "
                        "control such as euler takes interval / ode_dt0 steps per interval)"}.get(bad, str(bad))
             raise RuntimeError(f"odevio_b200: cannot back-propagate, forward solve failed: {what}")
-
-        nbytes = lib.odevio_odernn_backward_workspace_bytes(C.byref(cfg), ode_rows)
+        # Interval ranges, walked from the last interval to the first, each within the record budget
+        # (opt.ode_bwd_record_gb): the record streams are ~20 MB per sequence at configs[3] (84 GB at B = 4096 in one piece)
+        with torch.cuda.device(dev):
+            b0 = lib.odevio_odernn_backward_workspace_bytes(C.byref(cfg), 0)
+            b1 = lib.odevio_odernn_backward_workspace_bytes(C.byref(cfg), R * 1024)
+        if b0 == 0 or b1 == 0:
+            raise _lib.OdevioError("odevio_odernn_backward: unsupported configuration")
+        per_row = (b1 - b0) / (R * 1024)
+        cap_rows = max(int((module.bwd_record_gb * (1 << 30) - b0) / per_row), 0)
+        ranges, hi, acc = [], S - 1, 0
+        for i in range(S - 1, -1, -1):
+            if i < hi and acc + per_iv[i] > cap_rows:
+                ranges.append((i + 1, hi, acc))
+                hi, acc = i, 0
+            acc += per_iv[i]
+        ranges.append((0, hi, acc))
+        plan_rows = max(r[2] for r in ranges)
+        with torch.cuda.device(dev):
+            nbytes = lib.odevio_odernn_backward_workspace_bytes(C.byref(cfg), plan_rows)
         if nbytes == 0:
             raise _lib.OdevioError("odevio_odernn_backward: unsupported configuration")
-        # The record streams dominate (tens of GB at B = 4096).  The buffer is kept on the module and reused
-        # across steps: handed back to torch's caching allocator it gets split by the next forward's small
-        # allocations and the following request of ~the same size no longer fits (measured: OOM / retry stalls).
+        # The buffer is kept on the module and reused across steps: handed back to torch's caching allocator it gets split by
+        # the next forward's small allocations and the following request of ~the same size no longer fits (measured: OOM /
+        # retry stalls).
         ws = getattr(module, "_bwd_workspace", None)
         if ws is None or ws.device != dev or ws.numel() < nbytes:
             module._bwd_workspace = ws = None
@@ -100,13 +116,19 @@ class _OdeRnnFunction(torch.autograd.Function):
         gfused = torch.empty(B, S, D, dtype=torch.float32, device=dev) if (need_in[3] or need_in[4]) else None
         gh0 = torch.empty(L, B, D, dtype=torch.float32, device=dev) if (ctx.has_h0 and need_in[5]) else None
         stream = torch.cuda.current_stream(dev).cuda_stream
-        with torch.cuda.device(dev):
-            rc = lib.odevio_odernn_backward(
-                C.byref(cfg), C.byref(w), _lib.dptr(fvc), _lib.dptr(fic), ctx.Dv,
-                _lib.dptr(ctx.ckpt), ctx.ckpt_bytes, _lib.dptr(rec_base), ode_rows,
-                _lib.dptr(gpose), _lib.dptr(ghT_c), C.byref(g), _lib.dptr(gfused), _lib.dptr(gh0),
-                _lib.dptr(ws), ws.numel(), C.c_void_p(stream))
-        _lib.check(rc)
+        for lo, hi, nrows in ranges:
+            sub = rows[:, lo:hi + 1].reshape(-1)
+            base = torch.zeros(ntiles, S, dtype=torch.int64, device=dev)
+            base[:, lo:hi + 1] = (torch.cumsum(sub, 0) - sub).view(ntiles, hi - lo + 1)      # relative to the range
+            base = base.contiguous()
+            with torch.cuda.device(dev):
+                rc = lib.odevio_odernn_backward_range(
+                    C.byref(cfg), C.byref(w), _lib.dptr(fvc), _lib.dptr(fic), ctx.Dv,
+                    _lib.dptr(ctx.ckpt), ctx.ckpt_bytes, _lib.dptr(base), nrows, plan_rows, lo, hi,
+                    _lib.dptr(gpose), _lib.dptr(ghT_c), C.byref(g), _lib.dptr(gfused), _lib.dptr(gh0),
+                    _lib.dptr(ws), ws.numel(), C.c_void_p(stream))
+            _lib.check(rc)
+        module.last_bwd_ranges = [(lo, hi) for lo, hi, _ in ranges]
         gfv = gfi = None
         if gfused is not None:
             if ctx.has_fi:

@@ -46,6 +46,9 @@ int wgrad_tc_splits(long long nblocks, int N, int K, int nsm);
 cudaError_t wgrad_linear_tc(const float* Ghi, const float* Glo, const float* Ahi, const float* Alo,
                             long long nblocks, int N, int K, int R, float* dW, float* db, float* part, int nsm,
                             cudaStream_t stream);
+cudaError_t wgrad_linear_tc_ex(const float* Ghi, const float* Glo, const float* Ahi, const float* Alo,
+                               long long nblocks, int N, int K, int R, float* dW, float* db, float* part, int nsm,
+                               int accumulate, cudaStream_t stream);
 cudaError_t wgrad_linear(const float* G, int ldg, const float* A, int lda, long long M, int N, int K,
                          float* dW0, float* dW1, int k_split, float* db0, float* db1, float* part, int nsm,
                          cudaStream_t stream);
@@ -282,7 +285,7 @@ struct BwdPlan {
   size_t off_Wrnn[kMaxRnnLayers][4], off_brnn[kMaxRnnLayers][4];      // GRU: gate re-evaluation weights
   int Rb;
   int GW;                                                              // G-record width per jump row: D (rnn) | 6D (gru)
-  size_t off_part, part_floats;
+  size_t off_part, part_floats, off_tile_gy;
   long long jump_rows;
   size_t total_bytes;
 };
@@ -362,6 +365,7 @@ int plan_odernn_bwd(const odevio_odernn_cfg& c, const OdePlan& pl, long long ode
   need(bp.jump_rows, kPoseDim, kRegHidden);
   bp.part_floats = part;
   bp.off_part = take(part);
+  bp.off_tile_gy = take(static_cast<size_t>(pl.ntiles) * c.D * pl.R);      // hidden-state gradient carried between interval ranges
   bp.total_bytes = off * sizeof(float);
   return 0;
 }
@@ -947,22 +951,25 @@ size_t odevio_odernn_backward_workspace_bytes(const odevio_odernn_cfg* cfg, int6
   return bp.total_bytes;
 }
 
-int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn_weights* w,
-                               const float* fv, const float* fi, int32_t Dv,
-                               const void* ckpt, size_t ckpt_bytes,
-                               const int64_t* rec_base, int64_t ode_rows,
-                               const float* grad_pose, const float* grad_hT,
-                               const odevio_odernn_grads* g, float* grad_fused, float* grad_h0,
-                               void* workspace, size_t workspace_bytes, void* stream_) {
+static int32_t odernn_backward_impl(const odevio_odernn_cfg* cfg, const odevio_odernn_weights* w,
+                                    const float* fv, const float* fi, int32_t Dv,
+                                    const void* ckpt, size_t ckpt_bytes,
+                                    const int64_t* rec_base, int64_t ode_rows, int64_t ode_rows_plan, int32_t i_lo, int32_t i_hi,
+                                    const float* grad_pose, const float* grad_hT,
+                                    const odevio_odernn_grads* g, float* grad_fused, float* grad_h0,
+                                    void* workspace, size_t workspace_bytes, void* stream_) {
   if (!cfg || !w || !fv || !ckpt || !rec_base || !grad_pose || !g || !workspace) return ODEVIO_E_NULL;
   const odevio_odernn_cfg& c = *cfg;
   if (!c.save_checkpoints) return ODEVIO_E_ENUM;
+  if (i_lo < 0 || i_hi >= c.S || i_lo > i_hi || ode_rows > ode_rows_plan) return ODEVIO_E_SHAPE;
+  const bool first_range = i_hi == c.S - 1, last_range = i_lo == 0;
   OdePlan pl;
   int rc = plan_odernn(c, pl);
   if (rc != 0) return rc;
   BwdPlan bp;
-  rc = plan_odernn_bwd(c, pl, ode_rows, bp);
+  rc = plan_odernn_bwd(c, pl, ode_rows_plan, bp);
   if (rc != 0) return rc;
+  if (ode_rows % pl.R) return ODEVIO_E_SHAPE;
   if (Dv <= 0 || Dv > c.D || (Dv < c.D && !fi) || (Dv == c.D && fi)) return ODEVIO_E_SHAPE;
   if (workspace_bytes < bp.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ODEVIO_E_WORKSPACE;
   if (ckpt_bytes < ckpt_total_bytes(c, pl) || (reinterpret_cast<uintptr_t>(ckpt) & 255)) return ODEVIO_E_WORKSPACE;
@@ -984,7 +991,7 @@ int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn
   p.ns = bp.ns;
   for (int j = 0; j < NL; ++j) {
     float* dst = ws + bp.off_Wode[j];
-    ODEVIO_CUDA_TRY(transpose_pack(w->ode_w[j], pl.Node[j], pl.Kode[j], dst, pl.Node[j], 0, 0, stream));
+    if (first_range) ODEVIO_CUDA_TRY(transpose_pack(w->ode_w[j], pl.Node[j], pl.Kode[j], dst, pl.Node[j], 0, 0, stream));
     p.Wode[j] = dst; p.bode[j] = w->ode_b[j]; p.Kode[j] = pl.Kode[j]; p.Node[j] = pl.Node[j];
     p.Wode_raw[j] = w->ode_w[j];
     p.recA_ode[j] = ws + bp.off_recA_ode[j]; p.recG_ode[j] = ws + bp.off_recG_ode[j];
@@ -998,25 +1005,25 @@ int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn
       if (!w->rnn_b_ih[l] || !w->rnn_b_hh[l]) return ODEVIO_E_NULL;
       float* wr = ws + bp.off_Wrnn[l][0]; float* wz = ws + bp.off_Wrnn[l][1];
       float* wi = ws + bp.off_Wrnn[l][2]; float* wh = ws + bp.off_Wrnn[l][3];
-      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l], D, D, wr, D, 0, 0, stream));
-      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_hh[l], D, D, wr, D, D, 0, stream));
-      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l] + DDb, D, D, wz, D, 0, 0, stream));
-      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_hh[l] + DDb, D, D, wz, D, D, 0, stream));
-      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l] + 2 * DDb, D, D, wi, D, 0, 0, stream));
-      ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_hh[l] + 2 * DDb, D, D, wh, D, 0, 0, stream));
+      if (first_range) ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l], D, D, wr, D, 0, 0, stream));
+      if (first_range) ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_hh[l], D, D, wr, D, D, 0, stream));
+      if (first_range) ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l] + DDb, D, D, wz, D, 0, 0, stream));
+      if (first_range) ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_hh[l] + DDb, D, D, wz, D, D, 0, stream));
+      if (first_range) ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_ih[l] + 2 * DDb, D, D, wi, D, 0, 0, stream));
+      if (first_range) ODEVIO_CUDA_TRY(transpose_pack(w->rnn_w_hh[l] + 2 * DDb, D, D, wh, D, 0, 0, stream));
       float* br = ws + bp.off_brnn[l][0]; float* bz = ws + bp.off_brnn[l][1];
       float* bi = ws + bp.off_brnn[l][2]; float* bh = ws + bp.off_brnn[l][3];
-      ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_ih[l], w->rnn_b_hh[l], br, D, stream));
-      ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_ih[l] + D, w->rnn_b_hh[l] + D, bz, D, stream));
-      ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_ih[l] + 2 * D, nullptr, bi, D, stream));
-      ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_hh[l] + 2 * D, nullptr, bh, D, stream));
+      if (first_range) ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_ih[l], w->rnn_b_hh[l], br, D, stream));
+      if (first_range) ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_ih[l] + D, w->rnn_b_hh[l] + D, bz, D, stream));
+      if (first_range) ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_ih[l] + 2 * D, nullptr, bi, D, stream));
+      if (first_range) ODEVIO_CUDA_TRY(bias_sum(w->rnn_b_hh[l] + 2 * D, nullptr, bh, D, stream));
       p.Wrnn[l][0] = wr; p.Wrnn[l][1] = wz; p.Wrnn[l][2] = wi; p.Wrnn[l][3] = wh;
       p.brnn[l][0] = br; p.brnn[l][1] = bz; p.brnn[l][2] = bi; p.brnn[l][3] = bh;
     }
   }
   {
     float* dst = ws + bp.off_Wreg0;
-    ODEVIO_CUDA_TRY(transpose_pack(w->reg_w0, kRegHidden, D, dst, kRegHidden, 0, 0, stream));
+    if (first_range) ODEVIO_CUDA_TRY(transpose_pack(w->reg_w0, kRegHidden, D, dst, kRegHidden, 0, 0, stream));
     p.Wreg0 = dst; p.breg0 = w->reg_b0; p.Wreg0_raw = w->reg_w0; p.Wreg1 = w->reg_w1;
   }
   p.recA_reg0 = ws + bp.off_recA_reg0; p.recG_reg0 = ws + bp.off_recG_reg0;
@@ -1039,6 +1046,7 @@ int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn
     }
   }
   p.scratch = ws + bp.off_scratch; p.scratch_floats_per_cta = bp.scratch_floats_per_cta;
+  p.i_lo = i_lo; p.i_hi = i_hi; p.tile_gy = ws + bp.off_tile_gy;
   p.ntiles = pl.ntiles; p.nst = bp.nst; p.kc = bp.kc;
   p.buf_floats = static_cast<int>(bp.buf_floats); p.stage_floats = static_cast<int>(bp.stage_floats);
 
@@ -1047,8 +1055,10 @@ int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn
   // ---- deferred weight gradients: one dense GEMM per Linear over its record stream
   float* part = ws + bp.off_part;
   for (int j = 0; j < NL; ++j)       // ODEFunc Linears: tcgen05 3xTF32 GEMMs over the block-format streams
-    ODEVIO_CUDA_TRY(wgrad_linear_tc(p.recG_ode[j], p.recG_ode_lo[j], p.recA_ode[j], p.recA_ode_lo[j], ode_rows / pl.R,
-                                    pl.Node[j], pl.Kode[j], bp.Rb, g->ode_w[j], g->ode_b[j], part, pl.nsm, stream));
+    ODEVIO_CUDA_TRY(wgrad_linear_tc_ex(p.recG_ode[j], p.recG_ode_lo[j], p.recA_ode[j], p.recA_ode_lo[j], ode_rows / pl.R,
+                                       pl.Node[j], pl.Kode[j], bp.Rb, g->ode_w[j], g->ode_b[j], part, pl.nsm,
+                                       first_range ? 0 : 1, stream));
+  if (!last_range) return 0;          // the jump / head records are complete after the range that holds interval 0
   for (int l = 0; l < c.L; ++l) {
     if (c.rnn_type == ODEVIO_RNN_GRU) {
       // records: A = [x | h] (ld 2D), G = [G_ih | G_hh] (ld 6D); weight_ih / weight_hh are [3D][D]
@@ -1066,6 +1076,30 @@ int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn
   ODEVIO_CUDA_TRY(wgrad_linear(p.recG_reg1, 8, p.recA_reg1, kRegHidden, bp.jump_rows, kPoseDim, kRegHidden,
                                g->reg_w1, nullptr, 0, g->reg_b1, nullptr, part, pl.nsm, stream));
   return 0;
+}
+
+int32_t odevio_odernn_backward(const odevio_odernn_cfg* cfg, const odevio_odernn_weights* w,
+                               const float* fv, const float* fi, int32_t Dv,
+                               const void* ckpt, size_t ckpt_bytes,
+                               const int64_t* rec_base, int64_t ode_rows,
+                               const float* grad_pose, const float* grad_hT,
+                               const odevio_odernn_grads* g, float* grad_fused, float* grad_h0,
+                               void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!cfg) return ODEVIO_E_NULL;
+  return odernn_backward_impl(cfg, w, fv, fi, Dv, ckpt, ckpt_bytes, rec_base, ode_rows, ode_rows, 0, cfg->S - 1, grad_pose,
+                              grad_hT, g, grad_fused, grad_h0, workspace, workspace_bytes, stream_);
+}
+
+int32_t odevio_odernn_backward_range(const odevio_odernn_cfg* cfg, const odevio_odernn_weights* w,
+                                     const float* fv, const float* fi, int32_t Dv,
+                                     const void* ckpt, size_t ckpt_bytes,
+                                     const int64_t* rec_base, int64_t ode_rows, int64_t ode_rows_plan,
+                                     int32_t i_lo, int32_t i_hi,
+                                     const float* grad_pose, const float* grad_hT,
+                                     const odevio_odernn_grads* g, float* grad_fused, float* grad_h0,
+                                     void* workspace, size_t workspace_bytes, void* stream_) {
+  return odernn_backward_impl(cfg, w, fv, fi, Dv, ckpt, ckpt_bytes, rec_base, ode_rows, ode_rows_plan, i_lo, i_hi, grad_pose,
+                              grad_hT, g, grad_fused, grad_h0, workspace, workspace_bytes, stream_);
 }
 
 void odevio_cde_default_cfg(odevio_cde_cfg* cfg) {

@@ -208,14 +208,18 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
         const int r = e / D, d = e - r * D;
         const int l = r / RT, b = tile * RT + (r % RT);
         float v = 0.f;
-        if (prm.ghT && b < prm.B) v = prm.ghT[(static_cast<size_t>(l) * prm.B + b) * D + d];
+        if (prm.i_hi == S - 1) {
+          if (prm.ghT && b < prm.B) v = prm.ghT[(static_cast<size_t>(l) * prm.B + b) * D + d];
+        } else {
+          v = prm.tile_gy[static_cast<size_t>(tile) * D * R + static_cast<size_t>(d) * R + r];     // carried from the later range
+        }
         c.GY[static_cast<size_t>(d) * R + r] = v;
       }
     }
     __syncthreads();
 
     int ph = BP_HEAD1;
-    int i = S - 1, l = 0, it = 0, j = 0, lam = 0, gg = 0;
+    int i = prm.i_hi, l = 0, it = 0, j = 0, lam = 0, gg = 0;
     float* lin = c.bufA; float* lout = c.bufB;
     const float* Y0 = nullptr;
     long long row_it = 0;                 // first ODE-stream block of the current iteration (one block per stage)
@@ -438,7 +442,7 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
         }
         case BP_ITER: {
           if (it < 0) {
-            ph = (--i >= 0) ? BP_HEAD1 : BP_TILE_END;
+            ph = (--i >= prm.i_lo) ? BP_HEAD1 : BP_TILE_END;
             break;
           }
           const float* slot = ck_iv + 2 * arr + static_cast<size_t>(it) * (arr + 2 * R);
@@ -514,9 +518,11 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
       if (do_gemm) tile_gemm<RT, LL, true>(c.ring, c.pos, c.th, op.W, op.K, op.N, op.in, op.ode_layout, op.epi);
     }
 
-    // ---- gradient of the initial hidden state
+    // ---- gradient of the initial hidden state (last range), or the carry for the next launch
     __syncthreads();
-    if (!c.th.producer && prm.gh0) {
+    if (!c.th.producer && prm.i_lo > 0) {
+      for (int e = c.th.ctid; e < D * R; e += ncons) prm.tile_gy[static_cast<size_t>(tile) * D * R + e] = c.GY[e];
+    } else if (!c.th.producer && prm.gh0) {
       for (int e = c.th.ctid; e < D * R; e += ncons) {
         const int r = e / D, d = e - r * D;
         const int l2 = r / RT, b = tile * RT + (r % RT);

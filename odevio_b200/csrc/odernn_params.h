@@ -100,6 +100,8 @@ struct BwdParams {
   const float* fv; const float* fi; int Dv;
   const float* gpose;      // [B,S,6]
   const float* ghT;        // [L,B,D] or nullptr
+  int i_lo, i_hi;          // this launch walks the intervals i_hi .. i_lo (a training step may be split into interval ranges)
+  float* tile_gy;          // [ntiles][D*R]: gradient of the hidden state carried from one range to the next
   float* gh0;              // [L,B,D]
   float* gfused;           // [B,S,D] or nullptr
   // checkpoints written by the forward

@@ -215,12 +215,13 @@ __global__ void colsum_blocks_kernel(const float* __restrict__ Ghi, const float*
 
 }  // namespace
 
-__global__ void wgrad_reduce_kernel_tc(const float* __restrict__ part, int splits, size_t total, float* __restrict__ out) {
+__global__ void wgrad_reduce_kernel_tc(const float* __restrict__ part, int splits, size_t total, float* __restrict__ out,
+                                       int accumulate = 0) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += part[static_cast<size_t>(z) * total + i];
-    out[i] = s;
+    out[i] = accumulate ? out[i] + s : s;
   }
 }
 
@@ -245,11 +246,23 @@ int wgrad_tc_splits(long long nblocks, int N, int K, int nsm) {
 
 // dW [N][K] and db [N] of one ODEFunc Linear from its block-format streams (R rows per block).
 // `part` must hold max(splits * N * K, 256 * N) floats.
+cudaError_t wgrad_linear_tc_ex(const float* Ghi, const float* Glo, const float* Ahi, const float* Alo,
+                               long long nblocks, int N, int K, int R, float* dW, float* db, float* part, int nsm,
+                               int accumulate, cudaStream_t stream);
+
 cudaError_t wgrad_linear_tc(const float* Ghi, const float* Glo, const float* Ahi, const float* Alo,
                             long long nblocks, int N, int K, int R, float* dW, float* db, float* part, int nsm,
                             cudaStream_t stream) {
+  return wgrad_linear_tc_ex(Ghi, Glo, Ahi, Alo, nblocks, N, K, R, dW, db, part, nsm, 0, stream);
+}
+
+// accumulate != 0: dW += ..., db += ...  (the record streams of a training step reduced interval range by interval range)
+cudaError_t wgrad_linear_tc_ex(const float* Ghi, const float* Glo, const float* Ahi, const float* Alo,
+                               long long nblocks, int N, int K, int R, float* dW, float* db, float* part, int nsm,
+                               int accumulate, cudaStream_t stream) {
   const int bn = wgrad_tc_bn(K);
   if (!bn || N % TC_BM || R % 8 || R > 32) return cudaErrorInvalidValue;
+  if (nblocks <= 0 && accumulate) return cudaSuccess;
   if (nblocks <= 0) {
     cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * static_cast<size_t>(N) * K, stream);
     if (e != cudaSuccess) return e;
@@ -272,7 +285,7 @@ cudaError_t wgrad_linear_tc(const float* Ghi, const float* Glo, const float* Ahi
   const size_t total = static_cast<size_t>(N) * K;
   int rb = static_cast<int>((total + 255) / 256);
   if (rb > 4 * nsm) rb = 4 * nsm;
-  wgrad_reduce_kernel_tc<<<rb, 256, 0, stream>>>(part, splits, total, dW);
+  wgrad_reduce_kernel_tc<<<rb, 256, 0, stream>>>(part, splits, total, dW, accumulate);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   int bs = static_cast<int>((nblocks + 255) / 256);
@@ -283,7 +296,7 @@ cudaError_t wgrad_linear_tc(const float* Ghi, const float* Glo, const float* Ahi
   colsum_blocks_kernel<<<g2, 128, 0, stream>>>(Ghi, Glo, N, R, nblocks, bbps, part);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  wgrad_reduce_kernel_tc<<<(N + 255) / 256, 256, 0, stream>>>(part, bs, static_cast<size_t>(N), db);
+  wgrad_reduce_kernel_tc<<<(N + 255) / 256, 256, 0, stream>>>(part, bs, static_cast<size_t>(N), db, accumulate);
   return cudaGetLastError();
 }
 

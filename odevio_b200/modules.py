@@ -26,6 +26,8 @@ defaults; ``getattr(opt, name, default)``):
                         "dense" with exact landing (x = 1: the dense output is y1), not the literal variant
   ode_rows_per_tile=0   (auto) | 4 | 8 | 16
   ode_ckpt_loops=0      training: stored solver iterations per interval and tile (0 = 16)
+  ode_bwd_record_gb=24  training: bound on the record streams of the deferred weight-gradient GEMMs; the backward
+                        walks the observation intervals in as many ranges as that takes (B = 4096: 84 GB in one piece)
 
 Training: with grad enabled, ``forward`` goes through ``odevio_b200.autograd`` -- the fused
 forward with checkpoints, then ``odevio_odernn_backward`` (discretise-then-optimise, step sizes
@@ -281,6 +283,8 @@ class PoseODERNN(nn.Module):
         self.collect_stats = bool(getattr(opt, "ode_collect_stats", True))
         self.trace_steps = int(getattr(opt, "ode_trace_steps", 0))   # diagnostic: (dt, ratio) of first T steps
         self.ckpt_loops = int(getattr(opt, "ode_ckpt_loops", 0))     # training: stored solver iterations per interval (0 = 16)
+        self.bwd_record_gb = float(getattr(opt, "ode_bwd_record_gb", 24.0))   # training: bound on the backward's record streams
+        self.last_bwd_ranges = None                                  # interval ranges the last backward was walked in
         # "fp32": CUDA-core FFMA kernel; "tf32x3": ODEFunc GEMMs on tcgen05 (3xTF32, fp32-accurate), inference only
         self.precision = getattr(opt, "ode_precision", "fp32")
         if self.precision not in _lib.PRECISION:

@@ -202,6 +202,24 @@ def test_configs2_full_size(cuda_device, interp):
     check(out)
 
 
+@pytest.mark.parametrize("interp", ["linear", "cubic"])
+def test_reference_run_shape_hc400(cuda_device, interp):
+    """The reference's one PoseCDE run (scripts/run_training.sh:61-70) uses cde_hidden_dim = 400: a 400 x 401 x 400 final Linear
+    (257 MB, beyond L2; Gc = 2 channels per group, 201 groups).  Small batch: the CUDA-core kernel against the oracle, same
+    criterion as everywhere; the tensor-core kernel does not take this width ("auto" falls back, asserted)."""
+    import time
+    ref, mod = make_pair(cuda_device, Hc=400, cde_fn_num_layers=2, cde_interp=interp, cde_rtol=1e-3, cde_precision="auto")
+    fv, fi, ts = data(6, 4, 400, True)
+    out = run(ref, mod, fv, fi, ts, cuda_device)
+    assert mod.last_precision == "fp32"
+    with torch.no_grad():
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        mod(fv.to(cuda_device), fi.to(cuda_device), ts.to(cuda_device))
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print(f"Hc = 400 {interp}: pose_err {out['pose_err']:.2e}, stats {out['stats'][:3]}, {dt * 1e3:.1f} ms per forward (B = 6)")
+    check(out)
+
+
 def test_unit_variance_features_measured_spread(cuda_device):
     """BASELINE's N(0,1) features (the other CDE tests and the bench scale them to 0.2, see data()).
     With unit-variance features the random-init cubic CDE is ill-conditioned: this test MEASURES and prints

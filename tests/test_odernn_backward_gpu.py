@@ -150,3 +150,41 @@ def test_backward_with_tcgen05_forward(cuda_device, over):
 
 def test_backward_fp16x3_gru_falls_back_to_the_fma_forward(cuda_device):
     _compare(cuda_device, 6, 2, ode_precision="fp16x3", ode_rnn_type="gru")
+
+
+def test_interval_ranges_accumulate(cuda_device):
+    """A tiny record budget forces one backward launch per observation interval: the hidden-state gradient is carried between
+    the launches, the ODEFunc weight gradients accumulate -- same gradients as the single-range walk."""
+    ref, mod = make_pair(cuda_device, bias_std=0.05, ode_detach_dt=True, ode_rtol=1e-3)
+    ref.train(); mod.train()
+    fv, fi, ts = inputs(8, 4, irregular=True, seed=2)
+    g = torch.Generator().manual_seed(9)
+    gts = 0.1 * torch.randn(8, 4, 6, generator=g)
+    dev = cuda_device
+    _, g_one, _ = _grads(mod, fv.to(dev), fi.to(dev), ts.to(dev), gts.to(dev), None, 0.3)
+    assert mod.last_bwd_ranges == [(0, 3)]
+    mod.bwd_record_gb = 1e-6
+    _, g_many, _ = _grads(mod, fv.to(dev), fi.to(dev), ts.to(dev), gts.to(dev), None, 0.3)
+    assert mod.last_bwd_ranges == [(3, 3), (2, 2), (1, 1), (0, 0)]
+    _, g_ref, _ = _grads(ref, fv, fi, ts, gts, None, 0.3)
+    for k in g_ref:
+        assert rel_err(g_many[k], g_one[k]) <= 2e-6, (k, rel_err(g_many[k], g_one[k]))
+        assert rel_err(g_many[k], g_ref[k]) <= GRAD_RTOL, (k, rel_err(g_many[k], g_ref[k]))
+
+
+def test_dense_end_point_with_exact_landing_trains(cuda_device):
+    """ode_endpoint='dense' with exact landing: the step that reaches t_end has x = 1, where the dense output is y1
+    identically -- the fused training path takes it (y1 rule).  Target: the oracle's y1-rule gradient (same loss to 1e-6:
+    asserted); autograd through the oracle's own dense evaluation is not finite (0/0 in the masked rows of its where())."""
+    ref, _ = make_pair(cuda_device, bias_std=0.05, ode_detach_dt=True, ode_rtol=1e-3)                      # y1 rule
+    _, mod_d = make_pair(cuda_device, bias_std=0.05, ode_detach_dt=True, ode_rtol=1e-3, ode_endpoint="dense",
+                         ode_exact_landing=True)                                                              # same seed
+    ref.train(); mod_d.train()
+    fv, fi, ts = inputs(8, 3, irregular=True, seed=2)
+    gts = 0.1 * torch.randn(8, 3, 6, generator=torch.Generator().manual_seed(9))
+    dev = cuda_device
+    l_ref, g_ref, _ = _grads(ref, fv, fi, ts, gts, None, 0.0)
+    l_gpu, g_gpu, _ = _grads(mod_d, fv.to(dev), fi.to(dev), ts.to(dev), gts.to(dev), None, 0.0)
+    assert abs(l_gpu - l_ref) <= 1e-5 * abs(l_ref)
+    errs = {k: rel_err(g_gpu[k], g_ref[k]) for k in g_ref}
+    assert max(errs.values()) <= GRAD_RTOL, errs
