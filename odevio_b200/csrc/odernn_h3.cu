@@ -655,7 +655,8 @@ __device__ __forceinline__ void h3_jump_input(const H3Params& p, const H3Rows<NR
       float v = 0.f;
       if (rs.grow[n] >= 0) {
         const size_t row = static_cast<size_t>(rs.bidx[n]) * p.S_io + interval;
-        v = f < p.Dv ? __ldg(p.fv + row * p.Dv + f) : __ldg(p.fi + row * (D - p.Dv) + (f - p.Dv));
+        // read once per forward: streaming (evict-first) loads keep the 31 MB of features from displacing the L2-resident scratch
+        v = f < p.Dv ? __ldcs(p.fv + row * p.Dv + f) : __ldcs(p.fi + row * (D - p.Dv) + (f - p.Dv));
       }
       h3_split(v, hi[e], lo[e]);
     }
