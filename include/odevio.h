@@ -27,6 +27,9 @@
  * row-major fp32 with the PyTorch shapes quoted; `stream` is a cudaStream_t passed as void*.
  * Calls are asynchronous on `stream`, allocate nothing, never synchronise the device, and are
  * re-entrant across devices (the current device of the calling thread is used).
+ * Thread safety: calls on DIFFERENT devices may run concurrently; calls on the same device must be serialised by the
+ * caller (odevio_odernn_forward with ODEVIO_PRECISION_TF32X3 shares one side stream + fork / join events per device, and
+ * the measurement hooks of odevio_debug.h keep process-wide state).
  * Return value: 0 ok; <0 invalid argument (ODEVIO_E_*); >0 a cudaError_t from launch.
  * Per-row solver failures (non-finite error norm, max_steps hit) are reported through the
  * `status` output, never by hanging.

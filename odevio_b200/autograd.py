@@ -51,7 +51,8 @@ class _OdeRnnFunction(torch.autograd.Function):
         B, S, D, L = cfg.B, cfg.S, cfg.D, cfg.L
 
         geo = (C.c_int32 * 8)()
-        _lib.check(lib.odevio_odernn_geometry(C.byref(cfg), geo))
+        with torch.cuda.device(dev):              # the planner reads the SM count of the CURRENT device
+            _lib.check(lib.odevio_odernn_geometry(C.byref(cfg), geo))
         R, ntiles, ns = geo[1], geo[2], geo[3]
         nloops = ctx.ckpt[: ntiles * S * 4].view(torch.int32).to(torch.int64)
         rows = (nloops * (ns * R)).view(ntiles, S)

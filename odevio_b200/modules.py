@@ -420,14 +420,16 @@ class PoseODERNN(nn.Module):
             cfg.ckpt_loops = self.ckpt_loops
             if cfg.rows_per_tile == 16:
                 cfg.rows_per_tile = 8
-            ckpt_bytes = lib.odevio_odernn_ckpt_bytes(C.byref(cfg))
+            with torch.cuda.device(dev):          # the planner reads the SM count of the CURRENT device
+                ckpt_bytes = lib.odevio_odernn_ckpt_bytes(C.byref(cfg))
             if ckpt_bytes == 0:
                 raise _lib.OdevioError("training through the fused path needs ode_endpoint='y1' (or 'dense' with "
                                        "ode_exact_landing=True, which is the same function), rows_per_tile in "
                                        "{0, 4, 8} and D, H multiples of 128 "
                                        f"(endpoint={self.endpoint}, D={cfg.D}, H={cfg.H})")
             ckpt = torch.empty(ckpt_bytes, dtype=torch.uint8, device=dev)
-        nbytes = lib.odevio_odernn_workspace_bytes(C.byref(cfg))
+        with torch.cuda.device(dev):
+            nbytes = lib.odevio_odernn_workspace_bytes(C.byref(cfg))
         if nbytes == 0:
             raise _lib.OdevioError("unsupported PoseODERNN configuration for the fused kernel "
                                    f"(D={cfg.D}, H={cfg.H}, L={cfg.L}, n={cfg.n_hidden})")
