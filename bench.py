@@ -519,6 +519,36 @@ def measure_train(args, rank, world, dev):
                      "allreduce_ms": ar, "forward_ms": fw, "loss_backward_ms": bw, "clip_adam_ms": ad,
                      "allreduce_bytes": opt.flat.numel() * 4, "peak_mem_gb": mem, "loss": float(loss),
                      "timing": "CUDA events, max over ranks"})
+        # the collective itself, both ways, on the same gradient bucket: NCCL all-reduce + the three-launch clip / Adam step
+        # against ONE kernel over NVLink peer memory (odevio_allreduce_adam_peer: reduce-scatter by pull, clip, Adam on the
+        # rank's slice, all-gather by push); its own try: a symmetric-memory problem must not cost the numbers above
+        if world > 1:
+            try:
+                def timed(fn, n=20):
+                    for _ in range(3):
+                        fn()
+                    torch.cuda.synchronize(dev); dist.barrier()
+                    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    t0.record()
+                    for _ in range(n):
+                        fn()
+                    t1.record(); torch.cuda.synchronize(dev)
+                    return t0.elapsed_time(t1) / n * 1e3
+
+                def nccl_step():
+                    dist.all_reduce(opt.grads); opt.step()
+                us_nccl = timed(nccl_step)
+                peer = training.PeerFusedPoseNetAdam(model, lr=1e-4)
+                peer.grads.copy_(opt.grads)
+                us_peer = timed(peer.step_allreduce)
+                both = torch.tensor([us_nccl, us_peer], dtype=torch.float64, device=dev)
+                dist.all_reduce(both, op=dist.ReduceOp.MAX)
+                info["collective"] = {"nccl_allreduce_plus_clip_adam_us": both[0].item(), "peer_one_kernel_us": both[1].item(),
+                                      "bucket_bytes": opt.flat.numel() * 4, "launches": {"nccl": 4, "peer": 1},
+                                      "note": "gradient all-reduce + clip + Adam of the 15 MB Pose_net bucket; max over ranks"}
+                del peer
+            except Exception as exc:
+                info["collective"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         del model, opt, fv, fi, ts, gts
         torch.cuda.empty_cache()
     except Exception as exc:                       # the headline line must still be printed

@@ -438,6 +438,25 @@ ODEVIO_API int32_t odevio_adam_step_groups(int64_t n, int64_t split, float* para
                                            float eps, float weight_decay, float max_norm, float* norm_coef, void* workspace,
                                            size_t workspace_bytes, void* stream);
 
+/*
+ * Data-parallel training (the one collective of the path: the gradient all-reduce in front of clip + Adam,
+ * scripts/train_model.py:78-86 under torch.distributed): gradient all-reduce + global-norm clip + Adam in ONE kernel over
+ * NVLink peer memory.  Every rank's parameter bucket, gradient bucket and a 256-byte zero-initialised flag pad live in
+ * symmetric memory mapped into every process; `params_peers` / `grads_peers` / `pad_peers` are HOST arrays of `world` DEVICE
+ * pointers (index = rank).  Rank r reduces the r-th slice of the bucket by P2P loads (fixed order: bit-reproducible),
+ * exchanges its sum of squares through the pads, applies clip + Adam to its slice (exp_avg / exp_avg_sq: full-size arrays of
+ * which only this rank's slice is ever touched -- the optimiser state is sharded) and stores the new parameters into every
+ * rank's bucket.  Every rank must call it with the same arguments and `epoch` = 1, 2, ... (the flags are monotonic);
+ * grad_scale = 1 / world for the mean.  n a multiple of 4; norm_coef as in odevio_adam_step.  Launches cooperatively.
+ */
+ODEVIO_API size_t odevio_allreduce_adam_peer_workspace_bytes(int64_t n, int32_t world);
+ODEVIO_API int32_t odevio_allreduce_adam_peer(int64_t n, int64_t split, int32_t rank, int32_t world,
+                                              float* const* params_peers, const float* const* grads_peers,
+                                              uint32_t* const* pad_peers, float* exp_avg, float* exp_avg_sq, int32_t step,
+                                              uint32_t epoch, float grad_scale, float lr_first, float lr_rest, float beta1,
+                                              float beta2, float eps, float weight_decay, float max_norm, float* norm_coef,
+                                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* Diagnostics / measurement hooks (odevio_debug_*, odevio_microbench_ffma) are NOT part of the product ABI: they are
  * declared in include/odevio_debug.h. */
 

@@ -172,6 +172,12 @@ def load():
     lib.odevio_adam_step_groups.restype = C.c_int32
     lib.odevio_adam_step_groups.argtypes = ([C.c_int64, C.c_int64, _FP, _FP, _FP, _FP, C.c_int32] + [C.c_float] * 7 +
                                             [_FP, _FP, C.c_size_t, _FP])
+    lib.odevio_allreduce_adam_peer_workspace_bytes.restype = C.c_size_t
+    lib.odevio_allreduce_adam_peer_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
+    lib.odevio_allreduce_adam_peer.restype = C.c_int32
+    lib.odevio_allreduce_adam_peer.argtypes = ([C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.POINTER(_FP), C.POINTER(_FP),
+                                                C.POINTER(_FP), _FP, _FP, C.c_int32, C.c_uint32] + [C.c_float] * 8 +
+                                               [_FP, _FP, C.c_size_t, _FP])
     lib.odevio_debug_tc_geometry.restype = C.c_int32
     lib.odevio_debug_tc_geometry.argtypes = [C.POINTER(C.c_int32)]
     lib.odevio_debug_tc_timing.restype = C.c_int32

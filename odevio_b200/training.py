@@ -95,13 +95,13 @@ class FusedPoseNetAdam:
         if not other:
             self.split = off
         self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat = self._bucket(off, dev)
         with torch.no_grad():
             for p, o in zip(self.params, self.offsets):      # parameters become views of the flat buffer (keys / shapes unchanged)
                 n = p.numel()
                 self.flat[o:o + n].copy_(p.data.reshape(-1))
                 p.data = self.flat[o:o + n].view_as(p.data)
-        self.grads = torch.zeros_like(self.flat)
+        self.grads = self._bucket(off, dev)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.norm_coef = torch.zeros(2, dtype=torch.float32, device=dev)      # [total grad norm, clip coefficient]
@@ -109,6 +109,9 @@ class FusedPoseNetAdam:
         self.betas, self.eps, self.weight_decay, self.max_norm = betas, eps, weight_decay, max_norm
         self.param_groups = [{"params": other, "lr": lr}, {"params": reg, "lr": lr}]      # utils/utils.py:116-119 order
         self._ws, self._ws_bytes = _workspace(dev)
+
+    def _bucket(self, n, dev):
+        return torch.zeros(n, dtype=torch.float32, device=dev)
 
     @property
     def lr(self):
@@ -178,6 +181,84 @@ class FusedPoseNetAdam:
         self.weight_decay, self.max_norm = sd["weight_decay"], sd["max_norm"]
 
 
+class PeerFusedPoseNetAdam(FusedPoseNetAdam):
+    """FusedPoseNetAdam whose buckets live in symmetric memory: ``step_allreduce`` runs gradient all-reduce + clip + Adam as
+    ONE kernel over NVLink peer memory (``odevio_allreduce_adam_peer``: reduce-scatter by pull, norm exchange through flag
+    pads, Adam on this rank's slice, all-gather by push) instead of NCCL all-reduce + three launches.  The optimiser moments
+    are sharded: each rank only ever touches its slice (``state_dict`` gathers them).  All ranks must hold identical
+    parameters at construction (as under DDP) and call ``step_allreduce`` collectively.  ``world_size == 1`` (tests) uses
+    plain device tensors."""
+
+    def __init__(self, model, group=None, **kw):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._handles = []
+        super().__init__(model, **kw)
+        dev = self.flat.device
+        self.pad = self._bucket(64, dev)                    # 256 bytes of flags / partial norms, viewed as uint32 by the kernel
+        lib = _lib.load()
+        n = self.flat.numel()
+        self._peer_ws_bytes = lib.odevio_allreduce_adam_peer_workspace_bytes(n, self.world)
+        if self._peer_ws_bytes == 0:
+            raise _lib.OdevioError(f"odevio_allreduce_adam_peer: unsupported bucket / world size ({n}, {self.world})")
+        self._peer_ws = torch.empty(self._peer_ws_bytes, dtype=torch.uint8, device=dev)
+        self.epoch = 0
+
+        def ptrs(t):
+            if self.world == 1:
+                return (C.c_void_p * 1)(t.data_ptr())
+            import torch.distributed._symmetric_memory as symm_mem
+            h = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            self._handles.append(h)
+            return (C.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs])
+
+        self._p_params, self._p_grads, self._p_pad = ptrs(self.flat), ptrs(self.grads), ptrs(self.pad)
+        if self.world > 1:
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=self.group)                  # every rank's buckets are zeroed / filled before any peer access
+
+    def _bucket(self, n, dev):
+        if self.world == 1:
+            return torch.zeros(n, dtype=torch.float32, device=dev)
+        import torch.distributed._symmetric_memory as symm_mem
+        t = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        t.zero_()
+        return t
+
+    def step_allreduce(self):
+        """All-reduce (mean) of the gathered gradient bucket + clip + Adam, one launch, collectively on every rank."""
+        lib = _lib.load()
+        self._check_aliasing()
+        self.step_count += 1
+        self.epoch += 1
+        dev = self.flat.device
+        with torch.cuda.device(dev):
+            rc = lib.odevio_allreduce_adam_peer(
+                self.flat.numel(), self.split, self.rank, self.world, self._p_params, self._p_grads, self._p_pad,
+                _lib.dptr(self.exp_avg), _lib.dptr(self.exp_avg_sq), self.step_count, self.epoch, 1.0 / self.world,
+                float(self.param_groups[1]["lr"]), float(self.param_groups[0]["lr"]), self.betas[0], self.betas[1], self.eps,
+                self.weight_decay, float(self.max_norm or 0.0), _lib.dptr(self.norm_coef), _lib.dptr(self._peer_ws),
+                self._peer_ws_bytes, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc)
+
+    def state_dict(self):
+        sd = super().state_dict()
+        if self.world > 1:                                  # the moments of slice r live on rank r only
+            for k in ("exp_avg", "exp_avg_sq"):
+                dist.all_reduce(sd[k], op=dist.ReduceOp.SUM, group=self.group)     # the other slices are exactly zero
+        return sd
+
+    def load_state_dict(self, sd):
+        super().load_state_dict(sd)
+        if self.world > 1:                                  # keep only this rank's slice (the kernel never reads the rest)
+            n = self.flat.numel()
+            per = ((n // 4 + self.world - 1) // self.world) * 4
+            lo, hi = min(per * self.rank, n), min(per * (self.rank + 1), n)
+            for t in (self.exp_avg, self.exp_avg_sq):
+                t[:lo].zero_(); t[hi:].zero_()
+
+
 def fused_train_step(model, opt, fv, fi, ts, gts, world_size=1, group=None, events=None):
     """One optimisation step on this rank's shard (scripts/train_model.py:69-86) with the glue on the device: fused forward
     (checkpoints), fused loss + d loss / d poses, fused backward, ONE flat-bucket all-reduce, clip + Adam as its epilogue.
@@ -195,12 +276,16 @@ def fused_train_step(model, opt, fv, fi, ts, gts, world_size=1, group=None, even
     t1 = mark()
     loss = fused_pose_loss(poses, gts)
     loss.backward()
-    flat = opt.gather_grads(1.0 / world_size if world_size > 1 else 1.0)
+    peer = isinstance(opt, PeerFusedPoseNetAdam)
+    flat = opt.gather_grads(1.0 / world_size if (world_size > 1 and not peer) else 1.0)
     t2 = mark()
-    if world_size > 1:
+    if world_size > 1 and not peer:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     t3 = mark()
-    opt.step()
+    if peer:
+        opt.step_allreduce()          # all-reduce + clip + Adam in one kernel over NVLink peer memory
+    else:
+        opt.step()
     t4 = mark()
     if events is not None:
         events += [("forward", t0, t1), ("loss_backward", t1, t2), ("allreduce", t2, t3), ("clip_adam", t3, t4)]

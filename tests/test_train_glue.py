@@ -127,3 +127,45 @@ def test_fused_train_step_matches_reference_glue(cuda_device):
     db = torch.cat([(y.detach() - z).reshape(-1) for y, z in zip(pose_net_params(b), p0)])
     assert ((da - db).norm() / db.norm()).item() <= 2e-2, ((da - db).norm() / db.norm()).item()
     assert (da - db).abs().max().item() <= 2 * lr * steps
+
+
+@pytest.mark.gpu
+def test_peer_allreduce_adam_kernel_world1(cuda_device):
+    """odevio_allreduce_adam_peer with world = 1 (its own peer): the one-launch reduce + clip + Adam must equal the
+    three-launch odevio_adam_step_groups on identical gradients, incl. a clipped step and the two group rates."""
+    import odevio_b200
+    from odevio_b200.training import FusedPoseNetAdam, PeerFusedPoseNetAdam
+    from oracle.pose_odernn import default_opt
+    torch.manual_seed(0)
+    a = odevio_b200.PoseODERNN(default_opt()).to(cuda_device)
+    b = copy.deepcopy(a)
+    peer = PeerFusedPoseNetAdam(a, lr=1e-3)
+    base = FusedPoseNetAdam(b, lr=1e-3)
+    peer.param_groups[0]["lr"] = base.param_groups[0]["lr"] = 1e-4
+    g = torch.Generator().manual_seed(3)
+    for step in range(4):
+        scale = 50.0 if step == 2 else 0.01
+        for pa, pb in zip(pose_net_params(a), pose_net_params(b)):
+            gr = (scale * torch.randn(pa.shape, generator=g) / pa.numel() ** 0.5).to(cuda_device)
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        peer.gather_grads(); peer.step_allreduce()
+        base.gather_grads(); base.step()
+        assert abs(peer.norm_coef[0].item() - base.norm_coef[0].item()) <= 1e-6 * base.norm_coef[0].item()
+        for pa, pb in zip(pose_net_params(a), pose_net_params(b)):
+            assert ((pa - pb).abs().max() / pb.abs().max().clamp_min(1e-12)).item() <= 1e-6, step
+    assert torch.allclose(peer.exp_avg, base.exp_avg, rtol=1e-6, atol=0)
+
+
+@pytest.mark.gpu
+def test_peer_allreduce_adam_two_gpus():
+    """Two ranks over NVLink peer memory against NCCL all-reduce + the three-launch step (tools/peer_step_check.py);
+    skipped on a single-GPU box."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "peer_step_check.py")],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONPATH=root))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PEER_STEP_OK" in r.stdout
