@@ -610,6 +610,11 @@ cde_tc_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ Dev
       for (int rt = 0; rt < nrt; ++rt) {
         const uint32_t t = c.tcount + rt, s2 = t & 1u, ph = (t >> 1) & 1u;
         const int row = tile_of(rt) * 128 + rl;
+        // the time channel's term of my row, fetched now: its L2 round trip (1.5-2 k clk under load) sat on the critical path
+        // of every tile when it was loaded after the channel-half barrier below
+        float* const kp = Kout + static_cast<size_t>(h_own) * Bpad + row;
+        float kprev = 0.f;
+        if (hf == 0) kprev = __ldcg(kp);
         { TC_T0(); mbar_wait(&c.tfull[s2], ph); TC_ACC(8, _t0); }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float sum = 0.f;
@@ -658,10 +663,7 @@ cde_tc_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ Dev
         float* part = c.part + (t & 1u) * 256;
         part[hf * 128 + rl] = sum;
         named_bar_sync(2, TC_WORK_THREADS);
-        if (hf == 0) {
-          float* kp = Kout + static_cast<size_t>(h_own) * Bpad + row;
-          __stcg(kp, __ldcg(kp) + (part[rl] + part[128 + rl]));
-        }
+        if (hf == 0) __stcg(kp, kprev + (part[rl] + part[128 + rl]));
       }
     }
     c.tcount += static_cast<uint32_t>(nrt);
