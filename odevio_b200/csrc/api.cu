@@ -483,7 +483,8 @@ int plan_cde(const odevio_cde_cfg& c, CdePlan& pl) {
 // checkpoint buffer of the CDE training forward: [log: 1 + steps entries][steps][ntiles][Z, Y1, K0..K6][Hc][R]
 size_t cde_ckpt_log_bytes(int steps) { return align_up(sizeof(CdeStepRec) * static_cast<size_t>(1 + steps), 256); }
 size_t cde_ckpt_step_floats(const odevio_cde_cfg& c, const CdePlan& pl) {
-  return static_cast<size_t>(pl.ntiles) * (2 + kMaxStages) * c.Hc * pl.R;
+  if (pl.tc) return static_cast<size_t>(2 + kMaxStages) * c.Hc * pl.Bpad;          // cde_tc.cu: [9][Hc][Bpad]
+  return static_cast<size_t>(pl.ntiles) * (2 + kMaxStages) * c.Hc * pl.R;           // cde_fwd.cu: [tile][9][Hc][R]
 }
 
 struct CdeBwdPlan {
@@ -1129,7 +1130,6 @@ static int32_t cde_forward_impl(const odevio_cde_cfg* cfg, const odevio_cde_weig
   CdePlan pl;
   const int rc = plan_cde(c, pl);
   if (rc != 0) return rc;
-  if (ckpt && pl.tc) return ODEVIO_E_ENUM;          // the checkpointing forward is the CUDA-core kernel
   if (ckpt) {
     if (ckpt_steps < 1 || !hidden) return ODEVIO_E_SHAPE;
     const size_t need = cde_ckpt_log_bytes(ckpt_steps) + cde_ckpt_step_floats(c, pl) * ckpt_steps * sizeof(float);
@@ -1204,7 +1204,7 @@ int32_t odevio_cde_forward(const odevio_cde_cfg* cfg, const odevio_cde_weights* 
 size_t odevio_cde_ckpt_bytes(const odevio_cde_cfg* cfg, int32_t ckpt_steps) {
   if (!cfg || ckpt_steps < 1) return 0;
   CdePlan pl;
-  if (plan_cde(*cfg, pl) != 0 || pl.tc) return 0;
+  if (plan_cde(*cfg, pl) != 0) return 0;
   return cde_ckpt_log_bytes(ckpt_steps) + cde_ckpt_step_floats(*cfg, pl) * ckpt_steps * sizeof(float);
 }
 
@@ -1221,8 +1221,10 @@ int32_t odevio_cde_forward_ckpt(const odevio_cde_cfg* cfg, const odevio_cde_weig
 
 size_t odevio_cde_backward_workspace_bytes(const odevio_cde_cfg* cfg, int32_t chunk_vjps) {
   if (!cfg) return 0;
+  odevio_cde_cfg cb = *cfg;
+  cb.precision = ODEVIO_PRECISION_FP32;            // the backward kernel's geometry is the CUDA-core one whoever ran the forward
   CdePlan pl;
-  if (plan_cde(*cfg, pl) != 0 || pl.tc) return 0;
+  if (plan_cde(cb, pl) != 0) return 0;
   CdeBwdPlan bp;
   if (plan_cde_bwd(*cfg, pl, chunk_vjps, bp) != 0) return 0;
   return bp.total_bytes;
@@ -1238,11 +1240,14 @@ int32_t odevio_cde_backward(const odevio_cde_cfg* cfg, const odevio_cde_weights*
                             void* workspace, size_t workspace_bytes, void* stream_) {
   if (!cfg || !w || !tobs || !fv || !tout || !hidden || !z0 || !ckpt || !vjp_base || !grad_pose || !g || !workspace)
     return ODEVIO_E_NULL;
-  const odevio_cde_cfg& c = *cfg;
-  CdePlan pl;
-  int rc = plan_cde(c, pl);
+  odevio_cde_cfg c = *cfg;
+  CdePlan plf;                                     // the forward's plan: its checkpoint layout
+  int rc = plan_cde(c, plf);
   if (rc != 0) return rc;
-  if (pl.tc) return ODEVIO_E_ENUM;                 // the backward replays the CUDA-core forward's checkpoints
+  c.precision = ODEVIO_PRECISION_FP32;             // the backward kernel's geometry is the CUDA-core one whoever ran the forward
+  CdePlan pl;
+  rc = plan_cde(c, pl);
+  if (rc != 0) return rc;
   CdeBwdPlan bp;
   rc = plan_cde_bwd(c, pl, chunk_vjps, bp);
   if (rc != 0) return rc;
@@ -1251,7 +1256,7 @@ int32_t odevio_cde_backward(const odevio_cde_cfg* cfg, const odevio_cde_weights*
   if (has_prev && !grad_prev) return ODEVIO_E_NULL;
   if (workspace_bytes < bp.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255)) return ODEVIO_E_WORKSPACE;
   {
-    const size_t need = cde_ckpt_log_bytes(ckpt_steps) + cde_ckpt_step_floats(c, pl) * ckpt_steps * sizeof(float);
+    const size_t need = cde_ckpt_log_bytes(ckpt_steps) + cde_ckpt_step_floats(c, plf) * ckpt_steps * sizeof(float);
     if (ckpt_bytes < need || (reinterpret_cast<uintptr_t>(ckpt) & 255)) return ODEVIO_E_WORKSPACE;
   }
   const int NM = c.n_layers, Hc = c.Hc;
@@ -1291,6 +1296,16 @@ int32_t odevio_cde_backward(const odevio_cde_cfg* cfg, const odevio_cde_weights*
   p.log = static_cast<const CdeStepRec*>(ckpt);
   p.ckpt = reinterpret_cast<const float*>(static_cast<const unsigned char*>(ckpt) + cde_ckpt_log_bytes(ckpt_steps));
   p.n_acc = n_accepted;
+  {
+    const size_t arr = static_cast<size_t>(Hc) * pl.R;
+    if (plf.tc) {          // cde_tc.cu: [step][9][Hc][Bpad]; a tile's rows start at column tile * R
+      p.ck_step_stride = static_cast<size_t>(2 + kMaxStages) * Hc * plf.Bpad; p.ck_tile_stride = pl.R;
+      p.ck_jstride = static_cast<size_t>(Hc) * plf.Bpad; p.ck_hstride = plf.Bpad;
+    } else {               // cde_fwd.cu: [step][tile][9][Hc][R]
+      p.ck_step_stride = static_cast<size_t>(pl.ntiles) * (2 + kMaxStages) * arr; p.ck_tile_stride = (2 + kMaxStages) * arr;
+      p.ck_jstride = arr; p.ck_hstride = pl.R;
+    }
+  }
   for (int j = 0; j <= NM; ++j) p.recA[j] = ws + bp.off_recA[j];
   for (int j = 0; j < NM; ++j) p.recG[j] = ws + bp.off_recG[j];
   p.recGf = ws + bp.off_recGf;

@@ -131,23 +131,26 @@ __device__ __forceinline__ void build_arg(BC<RT>& c, const float* ck, int kind, 
                                           const DevTableau& tab, long long row0) {
   if (c.th.producer) return;
   const CdeBwdParams& p = *c.prm;
-  const size_t arr = static_cast<size_t>(p.Hc) * c.R;
-  const float* Z = ck; const float* Y1 = ck + arr; const float* K = ck + 2 * arr;
+  // checkpoint element (array j, feature h, rows 4 r4 ..): ck + j * ck_jstride + h * ck_hstride + 4 r4   (tile layout of
+  // cde_fwd.cu: [9][Hc][R]; feature-major layout of cde_tc.cu: [9][Hc][Bpad] with ck pointing at the tile's first row)
+  const size_t js = p.ck_jstride, hs = p.ck_hstride;
   const int nvec = p.Hc * c.rq4;
   const float third = static_cast<float>(1.0 / 3.0);
   for (int e = c.th.ctid; e < nvec; e += c.th.ncons) {
     const size_t off = static_cast<size_t>(e) * 4;
-    const float4 y4 = ld4(Z + off);
+    const int hh = e / c.rq4, r4 = e - hh * c.rq4;
+    const size_t coff = static_cast<size_t>(hh) * hs + 4 * r4;
+    const float4 y4 = ld4(ck + coff);
     const float y[4] = {y4.x, y4.y, y4.z, y4.w};
     float out[4];
-    auto ldk = [&](int j, float (&k)[4]) { const float4 v = ld4(K + j * arr + off); k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w; };
+    auto ldk = [&](int j, float (&k)[4]) { const float4 v = ld4(ck + (2 + j) * js + coff); k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w; };
     float k0[4], k1[4], k2[4];
     switch (kind) {
       case ZK_Z:
         for (int q = 0; q < 4; ++q) out[q] = y[q];
         break;
       case ZK_Y1: {
-        const float4 v = ld4(Y1 + off);
+        const float4 v = ld4(ck + js + coff);
         out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
         break;
       }
@@ -277,7 +280,6 @@ cde_bwd_kernel(const __grid_constant__ CdeBwdParams prm, const __grid_constant__
   c.GYN = sc + kMaxStages * arr;
   c.GZ = c.GYN + arr;
   c.HS = c.GZ + arr;                         // HS[l] = a_l, l = 0..NM
-  const size_t ck_tile_floats = static_cast<size_t>(2 + kMaxStages) * arr;
   const int nk = prm.interp == CDE_INTERP_LINEAR ? 2 * prm.So - 1 : prm.So;
   const int NgTot = prm.ngroups * prm.Ng;
   const int first_stage = prm.fsal ? 1 : 0;
@@ -324,7 +326,7 @@ cde_bwd_kernel(const __grid_constant__ CdeBwdParams prm, const __grid_constant__
         case D_STEP_BEGIN: {
           if (s < prm.step_lo) { pc = prm.step_lo == 0 ? D_FINAL : D_TILE_END; break; }
           rec = prm.log[1 + s];
-          ck = prm.ckpt + (static_cast<size_t>(s) * prm.ntiles + tile) * ck_tile_floats;
+          ck = prm.ckpt + static_cast<size_t>(s) * prm.ck_step_stride + static_cast<size_t>(tile) * prm.ck_tile_stride;
           for (int j = 0; j < ns; ++j) fill_arr<RT>(c, c.GK[j], nullptr);
           fill_arr<RT>(c, c.GYN, nullptr);
           if (!c.th.producer) named_bar_sync(1, ncons);
@@ -439,7 +441,7 @@ cde_bwd_kernel(const __grid_constant__ CdeBwdParams prm, const __grid_constant__
         case D_FINAL:
           if (prm.fsal && prm.n_acc > 0) {
             rec = prm.log[1];
-            ck = prm.ckpt + static_cast<size_t>(tile) * ck_tile_floats;
+            ck = prm.ckpt + static_cast<size_t>(tile) * prm.ck_tile_stride;
             start_vjp(ZK_Z, 0, 0.f, static_cast<float>(prm.tout[0]), 0, c.GKN, n_stage_vjps + (rec.on_jump ? 1 : 0), D_F0_DONE);
           } else {
             start_head(0, D_OUT0_DONE);

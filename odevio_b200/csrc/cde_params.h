@@ -106,6 +106,7 @@ struct CdeBwdParams {
   float* gX;                           // [B,So,C] accumulated (zeroed by the caller) or nullptr
   float* gprev;                        // [B,Hc] (has_prev)
   const float* ckpt; const CdeStepRec* log;
+  size_t ck_step_stride, ck_tile_stride, ck_jstride, ck_hstride;   // checkpoint layout (floats): cde_fwd.cu tiles or cde_tc.cu feature-major
   int step_lo, step_hi, n_acc, vjp_lo; // this launch walks steps step_hi-1 .. step_lo; records are relative to vjp_lo
   float* recA[kMaxLinears + 1];        // inputs of the CDEFunc Linears, row-major [M][Hc]
   float* recG[kMaxLinears];            // pre-activation gradients of the Hc->Hc Linears [M][Hc]

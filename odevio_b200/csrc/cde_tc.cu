@@ -405,6 +405,29 @@ cde_tc_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ Dev
   };
 
   int cached_seg = -1;                                  // knot segment whose (m, d) are in shared memory
+  // training: checkpoint of an accepted step -- Z, Y1, K0..K6 of my hidden unit for all sequences, in LOGICAL order
+  // [9][Hc][Bpad] (the index rotations resolved) -- and its log entry (cde_bwd.cu reads both; same log as cde_fwd.cu)
+  int vjp_total = 0;
+  auto save_step = [&](int step_idx, int onj) {
+    if (worker) {
+      float* dst0 = p.ckpt + static_cast<size_t>(step_idx) * (2 + kMaxStages) * Hc * Bpad + static_cast<size_t>(h_own) * Bpad;
+      for (int which = 0; which < 2 + kMaxStages; ++which) {
+        const float* src = arr_ptr(c, which) + static_cast<size_t>(h_own) * Bpad;
+        float* dst = dst0 + static_cast<size_t>(which) * Hc * Bpad;
+        for (int e = c.tid; e < (Bpad >> 2); e += TC_WORK_THREADS) stcg4(dst + 4 * e, ldcg4(src + 4 * e));
+      }
+    }
+    int cnt = 0;
+    for (int i = i_out; i < S && !(p.tout[i] > t_b); ++i) ++cnt;
+    if (blockIdx.x == 0 && c.tid == 0) {
+      CdeStepRec r;
+      r.ta = t_cur; r.tb = t_b; r.dt_s = dt_s; r.ta_s = ta_s; r.tb_s = tb_s; r.on_jump = onj;
+      r.out_first = i_out; r.out_count = cnt; r.vjp_base = vjp_total; r.pad = 0;
+      p.log[1 + step_idx] = r;
+    }
+    vjp_total += cde_step_vjps(adaptive ? tab.n_stages : 4, adaptive ? 1 : 0, onj, step_idx);
+    grid_sync(c);          // my copy reads ALL rows of my hidden unit: the next evaluation's row phases (other CTAs) overwrite them
+  };
   // ================================================================ one vector-field evaluation -> K[out]
   auto eval_now = [&](int kind, int stage, float dts, float t, int perturb, int out, bool save_y1) {
     ++n_f;
@@ -870,8 +893,13 @@ cde_tc_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ Dev
           const double dfactor = ratio < 1.0 ? 1.0 : 0.2;
           dt = step * fmin(10.0, fmax(0.9 / pow(ratio, 0.2), dfactor));
         }
-        if (accept) { ++n_acc; pc = PC_OUTPUTS; }
-        else pc = PC_STEP_BEGIN;
+        if (accept) {
+          if (p.ckpt) {
+            if (n_acc >= p.ckpt_cap) { status = 3; pc = PC_END; break; }
+            save_step(n_acc, on_jump);
+          }
+          ++n_acc; pc = PC_OUTPUTS;
+        } else pc = PC_STEP_BEGIN;
         break;
       }
       case PC_OUTPUTS: {
@@ -909,6 +937,10 @@ cde_tc_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ Dev
           }
         }
         grid_sync(c);
+        if (p.ckpt) {
+          if (n_acc >= p.ckpt_cap) { status = 3; pc = PC_END; break; }
+          save_step(n_acc, 0);
+        }
         ++n_steps; ++n_acc;
         pc = PC_AFTER_JUMP;
         break;
@@ -934,6 +966,10 @@ cde_tc_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ Dev
   }
 
   if (blockIdx.x == 0 && c.tid == 0) g_cde_tc_dbg[15] = clock64() - t_kernel0;
+  if (blockIdx.x == 0 && c.tid == 0 && p.log) {
+    CdeLogHead* hd = reinterpret_cast<CdeLogHead*>(p.log);
+    hd->n_acc = n_acc; hd->n_vjp = vjp_total; hd->status = status;
+  }
   if (blockIdx.x == 0 && c.tid == 0 && p.stats) {
     p.stats[0] = n_steps; p.stats[1] = n_acc; p.stats[2] = n_f; p.stats[3] = status;
   }

@@ -693,10 +693,10 @@ class PoseCDE(nn.Module):
 
     def _cfg(self, B, S, So, train=False):
         """``precision``: "fp32" = the CUDA-core kernel, "fp16x3" = the tensor-core kernel (loud failure for shapes it does
-        not take), "auto" (default) = the tensor-core kernel whenever it takes the shape.  Training runs always use the
-        CUDA-core kernel (its checkpoints are what the fused backward replays)."""
+        not take), "auto" (default) = the tensor-core kernel whenever it takes the shape.  Training forwards (checkpoints for
+        the fused backward) follow the same rule: both kernels write them, the backward reads either layout."""
         cfg = self._cfg_base(B, S, So)
-        if train or self.precision == "fp32":
+        if self.precision == "fp32":
             return cfg
         cfg.precision = _lib.PRECISION["fp16x3"]
         if self.precision == "auto" and _lib.load().odevio_cde_workspace_bytes(C.byref(cfg)) == 0:

@@ -147,3 +147,16 @@ def test_checkpoint_overflow_is_reported(cuda_device):
     fv, fi, ts = data(8, 10, 32, True)
     with pytest.raises(RuntimeError, match="cde_ckpt_steps"):
         mod(fv.to(cuda_device), fi.to(cuda_device), ts.to(cuda_device))
+
+
+@pytest.mark.parametrize("case", [dict(cde_interp="cubic"), dict(ts_scale=4.0, seed=3),
+                                  dict(cde_solver="rk4", cde_interp="cubic", cde_step_size=0.25),
+                                  dict(Hc=128, B=150, cde_interp="cubic")])
+def test_checkpoints_from_the_tensor_core_forward(cuda_device, case):
+    """Training with the checkpointing forward on tcgen05 (cde_tc.cu writes the stage values feature-major, the backward reads
+    either layout); the poses of the training forward are the tensor-core kernel's.  Bound 1e-3: the checkpointed states carry
+    the 3xFP16 forward's deviation from the oracle (poses 1e-6 .. 5e-5 here), which the cubic CDE amplifies into the gradient
+    (measured 7e-6 .. 5e-4); the pullback arithmetic itself is pinned at 2e-4 by the CUDA-core-forward cases above."""
+    case = dict(case)
+    B = case.pop("B", 12)
+    errs, st = _compare(cuda_device, B, 6, cde_fn_num_layers=2, cde_precision="fp16x3", tol=1e-3, **case)
