@@ -215,6 +215,104 @@ __device__ __forceinline__ void fill_arr(BC<RT>& c, float* dst, const float* src
   }
 }
 
+// ga[n][r] (+)= sum_k G[k][r] * WT[k][n]   for the pull-back through the final Linear: K = Gc * Hc rows of G (up to 1024), only
+// N = Hc outputs.  tile_gemm would leave half of the threads without a column pair (N / 2 = 64 pairs for 128 threads) and stream
+// the weight in 4 KB stages; here the K range of every stage is SPLIT over `ks` thread groups (each pair of columns is owned by
+// ks threads, their partial sums added in a fixed order through `scratch`), and a stage holds kc = up to 64 k-rows (32 KB).
+// Same ring protocol as tile_gemm (one lane of the producer warp streams, every consumer warp releases each stage).
+template <int RT, int LL>
+__device__ __forceinline__ void gemm_ksplit(const WeightRing& ring, RingPos& pos, const TileThread& th,
+                                            const float* __restrict__ WT, int K, int N, const float* inT, float* out,
+                                            float* scratch, bool first) {
+  constexpr int ncons = 128 * LL;
+  constexpr int R = RT * LL;
+  const int pairs = N >> 1;
+  int ks = 128 / pairs;                       // thread groups per column pair inside a 128-thread row block
+  if (ks > 2) ks = 2;                         // one partial set fits the scratch buffer
+  if (ks < 1) ks = 1;
+  int kc = 64;
+  while (kc > 8 && (static_cast<size_t>(kc) * N > ring.stage_floats || K % kc)) kc >>= 1;
+  const int nch = K / kc;
+  if (th.producer) {
+    if (th.lane == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(kc) * N * sizeof(float);
+      for (int ch = 0; ch < nch; ++ch) {
+        mbar_wait(&ring.empty[pos.stage], pos.phase ^ 1u);
+        mbar_arrive_expect_tx(&ring.full[pos.stage], bytes);
+        tma_load_1d(ring.buf + static_cast<size_t>(pos.stage) * ring.stage_floats, WT + static_cast<size_t>(ch) * kc * N, bytes,
+                    &ring.full[pos.stage]);
+        pos.advance(ring.nst);
+      }
+    } else {
+      for (int ch = 0; ch < nch; ++ch) pos.advance(ring.nst);
+    }
+    __syncwarp();
+    return;
+  }
+  const int rb = th.ctid / 128, t = th.ctid - rb * 128;          // row block (RT rows), thread inside it
+  const int cp = t % pairs, part = t / pairs;
+  const bool active = part < ks && pairs <= 128;
+  const int kpp = kc / ks;                                       // k-rows of a stage per thread group
+  float acc0[RT], acc1[RT];
+#pragma unroll
+  for (int r = 0; r < RT; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
+  const float* xrow = inT + rb * RT;
+  for (int ch = 0; ch < nch; ++ch) {
+    mbar_wait(&ring.full[pos.stage], pos.phase);
+    const float* ws = ring.buf + static_cast<size_t>(pos.stage) * ring.stage_floats;
+    const uint32_t cur = pos.stage;
+    pos.advance(ring.nst);
+    if (active) {
+      const float* wp = ws + static_cast<size_t>(part) * kpp * N + 2 * cp;
+      const float* xp = xrow + (static_cast<size_t>(ch) * kc + part * kpp) * R;
+#pragma unroll 4
+      for (int kk = 0; kk < kpp; ++kk) {
+        const float2 w = *reinterpret_cast<const float2*>(wp + kk * N);
+        float x[RT];
+#pragma unroll
+        for (int q = 0; q < RT / 4; ++q) {
+          const float4 v = ld4(xp + kk * R + 4 * q);
+          x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int r = 0; r < RT; ++r) { acc0[r] = fmaf(x[r], w.x, acc0[r]); acc1[r] = fmaf(x[r], w.y, acc1[r]); }
+      }
+    }
+    __syncwarp();
+    if (th.lane == 0) mbar_arrive(&ring.empty[cur]);
+  }
+  // partial sums of group 1 -> scratch [N][R]; group 0 adds them (fixed order) and writes / accumulates the result
+  if (active && part == 1) {
+#pragma unroll
+    for (int q = 0; q < RT / 4; ++q) {
+      st4(scratch + static_cast<size_t>(2 * cp) * R + rb * RT + 4 * q, make_float4(acc0[4 * q], acc0[4 * q + 1], acc0[4 * q + 2], acc0[4 * q + 3]));
+      st4(scratch + static_cast<size_t>(2 * cp + 1) * R + rb * RT + 4 * q, make_float4(acc1[4 * q], acc1[4 * q + 1], acc1[4 * q + 2], acc1[4 * q + 3]));
+    }
+  }
+  named_bar_sync(1, ncons);
+  if (active && part == 0) {
+#pragma unroll
+    for (int q = 0; q < RT / 4; ++q) {
+      float4 a = make_float4(acc0[4 * q], acc0[4 * q + 1], acc0[4 * q + 2], acc0[4 * q + 3]);
+      float4 b = make_float4(acc1[4 * q], acc1[4 * q + 1], acc1[4 * q + 2], acc1[4 * q + 3]);
+      float* o0 = out + static_cast<size_t>(2 * cp) * R + rb * RT + 4 * q;
+      float* o1 = out + static_cast<size_t>(2 * cp + 1) * R + rb * RT + 4 * q;
+      if (ks == 2) {
+        const float4 pa = ld4(scratch + static_cast<size_t>(2 * cp) * R + rb * RT + 4 * q);
+        const float4 pb = ld4(scratch + static_cast<size_t>(2 * cp + 1) * R + rb * RT + 4 * q);
+        a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w; b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+      }
+      if (!first) {
+        const float4 oa = ld4(o0), ob = ld4(o1);
+        a.x += oa.x; a.y += oa.y; a.z += oa.z; a.w += oa.w; b.x += ob.x; b.y += ob.y; b.z += ob.z; b.w += ob.w;
+      }
+      st4(o0, a); st4(o1, b);
+    }
+  }
+  pos.ready = 0;
+  named_bar_sync(1, ncons);
+}
+
 struct GemmOpD {
   const float* W; int K; int N;
   const float* in;
@@ -611,10 +709,16 @@ cde_bwd_kernel(const __grid_constant__ CdeBwdParams prm, const __grid_constant__
           break;
         }
         case V_GROUP_BWD: {
-          op.W = p.WfinT + static_cast<size_t>(v_group) * p.Ng * Hc; op.K = p.Ng; op.N = Hc; op.in = c.staging;
-          op.epi.mode = v_first ? EPI_STORE : EPI_ADD; op.epi.act = ACT_NONE;
-          op.epi.out0 = c.GA; op.epi.ld0 = R;
-          do_gemm = true;
+          if (Hc <= 256) {
+            // K = Gc * Hc rows, only Hc outputs: the k-split routine (all threads busy, 32 KB stages); `lout` is free here
+            gemm_ksplit<RT, LL>(c.ring, c.pos, c.th, p.WfinT + static_cast<size_t>(v_group) * p.Ng * Hc, p.Ng, Hc, c.staging,
+                                c.GA, lout, v_first);
+          } else {
+            op.W = p.WfinT + static_cast<size_t>(v_group) * p.Ng * Hc; op.K = p.Ng; op.N = Hc; op.in = c.staging;
+            op.epi.mode = v_first ? EPI_STORE : EPI_ADD; op.epi.act = ACT_NONE;
+            op.epi.out0 = c.GA; op.epi.ld0 = R;
+            do_gemm = true;
+          }
           v_first = false;
           ++v_group;
           pc = V_GROUP;
