@@ -57,8 +57,8 @@ class _OdeRnnFunction(torch.autograd.Function):
         nloops = ctx.ckpt[: ntiles * S * 4].view(torch.int32).to(torch.int64)
         rows = (nloops * (ns * R)).view(ntiles, S)
         # the one host read of the training step: record rows per observation interval (+ solver status)
-        per_iv = [int(v) for v in rows.sum(0).cpu()]
-        bad = int(ctx.status.max().item())
+        host = torch.cat([rows.sum(0), ctx.status.max().to(torch.int64).reshape(1)]).cpu()      # ONE device -> host copy
+        per_iv, bad = [int(v) for v in host[:-1]], int(host[-1])
         if bad != 0:
             what = {1: "max_steps reached", 2: "non-finite error norm",
                     3: "more solver iterations per interval than opt.ode_ckpt_loops (raise it; a solver without error "
