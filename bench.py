@@ -85,16 +85,70 @@ def algorithmic_flops(stats, B, S):
     return evals * f_ode + B * S * (f_rnn + f_reg), evals
 
 
+def _gpu_uuid(dev):
+    try:
+        import torch
+        return "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        return None
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks / throttle reasons sampled DURING the timed region: NVML polled every 5 ms from a thread (initialised before
+    the region starts, so even a 0.2 s region gets tens of samples); `nvidia-smi -lms` as the fallback when NVML cannot be
+    loaded (its process start-up can outlast a short region -- that is why it is only the fallback)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid, self.lines, self.proc = index, uuid, [], None
+        self.nvml, self.handle, self.samples, self.stop_flag, self.thread = None, None, [], False, None
+
+    def _start_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        if self.uuid:
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid)
+            except Exception:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid.encode())
+                except Exception:
+                    h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.nvml, self.handle = pynvml, h
+        self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        self._poll_once()                        # fails here (-> fallback) rather than in the thread
+        self.samples = []
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
+
+    def _poll_once(self):
+        n, h = self.nvml, self.handle
+        sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+        try:
+            r = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        self.samples.append((sm, r))
+
+    def _poll(self):
+        while not self.stop_flag:
+            try:
+                self._poll_once()
+            except Exception:
+                break
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            self._start_nvml()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"],
@@ -108,6 +162,18 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            n = self.nvml
+            bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+            reasons = sorted(nm for nm, b in bits.items() if any(r & b for _, r in self.samples))
+            load = [sm for sm, _ in self.samples if sm > 0]
+            return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                    "samples": len(self.samples), "source": "nvml, 5 ms poll"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -127,7 +193,8 @@ class ClockSampler:
                     reasons.add(nm)
         load = [v for v in sm if v > 0]
         return {"sm_mhz": statistics.median(load) if load else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 100"}
 
 
 def cpu_oracle_rate(steps, warmup, B, opt=None, irregular=True):
@@ -248,7 +315,7 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(max(args.warmup, 3)):
             model(fv, fi, ts)
         barrier()
-        sampler = ClockSampler(local_rank)
+        sampler = ClockSampler(local_rank, _gpu_uuid(dev))
         if rank == 0:
             sampler.start()
         evs = []

@@ -766,7 +766,10 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
   float* const headbuf = normpart + H3_NC * NR;                        // [128][NR] activations of regressor.0
   unsigned char* const xa0 = p.xa + static_cast<size_t>(cluster_id) * 2 * p.xa_buf_bytes;
   unsigned char* const xa1 = xa0 + p.xa_buf_bytes;
-  unsigned char* const xj = p.xj + static_cast<size_t>(cluster_id) * p.L * p.xj_buf_bytes;
+  // the jump-input images [x ; h] of the L layers live in the stage vectors K0 .. K(2L-1), which are dead between the end of an
+  // interval's solves and the next interval's first stage (FSAL does not carry across the jump): 25 MB less L2-resident
+  // scratch at configs[1] (2 D x NR x 4 B = 2 stage vectors per layer)
+  unsigned char* const xj = reinterpret_cast<unsigned char*>(st_base);
 
   const bool epi = warp < H3_EPI_WARPS;
   H3Slice<NR> sl;
@@ -1132,8 +1135,9 @@ int h3_plan(const odevio_odernn_cfg& c, H3Plan& pl) {
   }
   pl.xa_buf_bytes = (static_cast<size_t>(kmax) * pl.NR * 4 + 1023) / 1024 * 1024;       // hi + lo fp16 images of kmax x NR
   pl.off_xa = take(static_cast<size_t>(pl.nclusters) * 2 * pl.xa_buf_bytes);
-  pl.xj_buf_bytes = pl.can_jump ? static_cast<size_t>(2 * c.D) * pl.NR * 4 : 0;
-  pl.off_xj = take(static_cast<size_t>(pl.nclusters) * c.L * pl.xj_buf_bytes);
+  pl.xj_buf_bytes = pl.can_jump ? static_cast<size_t>(2 * c.D) * pl.NR * 4 : 0;        // aliases 2 stage vectors per layer (kernel)
+  if (pl.can_jump && 2 * c.L > kMaxStages) pl.can_jump = false;
+  pl.off_xj = off;
   pl.state_floats = (static_cast<size_t>(kMaxStages + 2) * c.D + H3_NC + kRegHidden) * pl.NR;
   pl.state_floats = (pl.state_floats + 255) / 256 * 256;
   pl.off_state = take(static_cast<size_t>(pl.nclusters) * pl.state_floats * sizeof(float));
