@@ -93,108 +93,105 @@ def _gpu_uuid(dev):
         return None
 
 
+_NVML_HELPER = r"""
+import sys, time
+import pynvml as n
+n.nvmlInit()
+uuid, index = sys.argv[1], int(sys.argv[2])
+h = None
+if uuid:
+    for u in (uuid, uuid.encode()):
+        try:
+            h = n.nvmlDeviceGetHandleByUUID(u); break
+        except Exception:
+            h = None
+if h is None:
+    h = n.nvmlDeviceGetHandleByIndex(index)
+mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+bits = [("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+        ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)]
+while True:
+    sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+    try:
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+    except Exception:
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    print(time.time(), sm, mx, "|".join(nm for nm, b in bits if r & b), flush=True)
+    time.sleep(0.005)
+"""
+
+
 class ClockSampler:
-    """SM clocks / throttle reasons sampled DURING the timed region: NVML polled every 5 ms from a thread (initialised before
-    the region starts, so even a 0.2 s region gets tens of samples); `nvidia-smi -lms` as the fallback when NVML cannot be
-    loaded (its process start-up can outlast a short region -- that is why it is only the fallback)."""
+    """SM clocks / throttle reasons sampled DURING the timed region.  A helper PROCESS polls NVML every 5 ms (started well
+    before the region, so even a 0.2 s region gets tens of samples; a separate process, so that a profiler attached to this
+    one cannot stall the bench through it); `nvidia-smi -lms 100` when the helper cannot load NVML.  start() launches the
+    helper, begin() / stop() bracket the timed region: only samples stamped inside it count."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index, uuid=None):
-        self.index, self.uuid, self.lines, self.proc = index, uuid, [], None
-        self.nvml, self.handle, self.samples, self.stop_flag, self.thread = None, None, [], False, None
+        self.index, self.uuid, self.lines, self.proc, self.kind, self.t0 = index, uuid, [], None, None, None
 
-    def _start_nvml(self):
-        import pynvml
-        pynvml.nvmlInit()
-        h = None
-        if self.uuid:
-            try:
-                h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid)
-            except Exception:
-                try:
-                    h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid.encode())
-                except Exception:
-                    h = None
-        if h is None:
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-        self.nvml, self.handle = pynvml, h
-        self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-        self._poll_once()                        # fails here (-> fallback) rather than in the thread
-        self.samples = []
-        self.thread = threading.Thread(target=self._poll, daemon=True)
-        self.thread.start()
-
-    def _poll_once(self):
-        n, h = self.nvml, self.handle
-        sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
-        try:
-            r = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
-        except Exception:
-            r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-        self.samples.append((sm, r))
-
-    def _poll(self):
-        while not self.stop_flag:
-            try:
-                self._poll_once()
-            except Exception:
-                break
-            time.sleep(0.005)
+    def _spawn(self, cmd):
+        self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        threading.Thread(target=self._pump, daemon=True).start()
 
     def start(self):
         try:
-            self._start_nvml()
-            return
-        except Exception:
-            self.nvml = None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
+            self._spawn([sys.executable, "-c", _NVML_HELPER, self.uuid or "", str(self.index)])
+            self.kind = "nvml"
+            deadline = time.time() + 3.0                 # the helper either prints within moments or died (no pynvml / NVML)
+            while time.time() < deadline and not self.lines and self.proc.poll() is None:
+                time.sleep(0.01)
+            if self.lines:
+                return
+            self.proc.kill()
         except OSError:
-            self.proc = None
+            pass
+        try:
+            self.lines = []
+            self._spawn(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"])
+            self.kind = "smi"
+        except OSError:
+            self.proc, self.kind = None, None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def begin(self):
+        self.t0 = time.time()
 
     def stop(self):
-        if self.nvml is not None:
-            self.stop_flag = True
-            self.thread.join(timeout=1.0)
-            n = self.nvml
-            bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown,
-                    "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
-                    "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown,
-                    "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
-            reasons = sorted(nm for nm, b in bits.items() if any(r & b for _, r in self.samples))
-            load = [sm for sm, _ in self.samples if sm > 0]
-            return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
-                    "samples": len(self.samples), "source": "nvml, 5 ms poll"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source (pynvml and nvidia-smi unavailable)"], "samples": 0}
+        t1 = time.time()
+        if self.kind == "smi":
+            time.sleep(0.15)
         self.proc.terminate()
+        t0 = self.t0 if self.t0 is not None else 0.0
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+        for stamp, ln in list(self.lines):
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
+                if self.kind == "nvml":
+                    f = ln.split(" ")
+                    ts_, s_, m_ = float(f[0]), float(f[1]), float(f[2])
+                    rs = [x for x in (f[3].split("|") if len(f) > 3 else []) if x]
+                else:
+                    f = [x.strip() for x in ln.split(",")]
+                    ts_, s_, m_ = stamp, float(f[1]), float(f[2])
+                    rs = [nm for nm, val in zip(self.NAMES, f[5:9]) if val.lower().startswith("active")]
+            except (ValueError, IndexError):
                 continue
-            for nm, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+            if ts_ < t0 or ts_ > t1 + 0.2:
+                continue
+            sm.append(s_); mx.append(m_); reasons.update(rs)
         load = [v for v in sm if v > 0]
-        return {"sm_mhz": statistics.median(load) if load else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
-                "source": "nvidia-smi -lms 100"}
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml helper process, 5 ms poll" if self.kind == "nvml" else "nvidia-smi -lms 100"}
 
 
 def cpu_oracle_rate(steps, warmup, B, opt=None, irregular=True):
@@ -312,12 +309,13 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- device-resident timing: K steps, L2 flushed between timed iterations
     with torch.no_grad():
+        sampler = ClockSampler(local_rank, _gpu_uuid(dev))
+        if rank == 0:
+            sampler.start()                      # helper process up and polling before the warm-up ends
         for _ in range(max(args.warmup, 3)):
             model(fv, fi, ts)
         barrier()
-        sampler = ClockSampler(local_rank, _gpu_uuid(dev))
-        if rank == 0:
-            sampler.start()
+        sampler.begin()
         evs = []
         for _ in range(args.steps):
             flush.fill_(1)

@@ -285,7 +285,7 @@ struct BwdPlan {
   size_t off_Wrnn[kMaxRnnLayers][4], off_brnn[kMaxRnnLayers][4];      // GRU: gate re-evaluation weights
   int Rb;
   int GW;                                                              // G-record width per jump row: D (rnn) | 6D (gru)
-  size_t off_part, part_floats, off_tile_gy;
+  size_t off_part, part_floats, off_tile_gy, off_tile_order;
   long long jump_rows;
   size_t total_bytes;
 };
@@ -366,6 +366,7 @@ int plan_odernn_bwd(const odevio_odernn_cfg& c, const OdePlan& pl, long long ode
   bp.part_floats = part;
   bp.off_part = take(part);
   bp.off_tile_gy = take(static_cast<size_t>(pl.ntiles) * c.D * pl.R);      // hidden-state gradient carried between interval ranges
+  bp.off_tile_order = take(static_cast<size_t>(pl.ntiles) + 64);          // int [ntiles] work-queue order + the queue head
   bp.total_bytes = off * sizeof(float);
   return 0;
 }
@@ -1048,6 +1049,8 @@ static int32_t odernn_backward_impl(const odevio_odernn_cfg* cfg, const odevio_o
   }
   p.scratch = ws + bp.off_scratch; p.scratch_floats_per_cta = bp.scratch_floats_per_cta;
   p.i_lo = i_lo; p.i_hi = i_hi; p.tile_gy = ws + bp.off_tile_gy;
+  p.tile_order = reinterpret_cast<const int*>(ws + bp.off_tile_order);
+  p.tile_counter = reinterpret_cast<int*>(ws + bp.off_tile_order) + pl.ntiles + 32;
   p.ntiles = pl.ntiles; p.nst = bp.nst; p.kc = bp.kc;
   p.buf_floats = static_cast<int>(bp.buf_floats); p.stage_floats = static_cast<int>(bp.stage_floats);
 

@@ -198,7 +198,19 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
   c.HS = c.GY + arr;                       // HS[(j * (NL-1) + lam) * harr]
   const size_t ivf = ckpt_interval_floats(D, R, prm.CK);
 
-  for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+  // Tiles are taken from a work queue in order of decreasing cost (bwd_tile_order_kernel): with 3.46 tiles per SM at
+  // B = 4096 a static round-robin costs 4 tile times on 68 of the 148 SMs; longest-first keeps the makespan at the mean.
+  // Records, carries and gradients are addressed by the tile, so the result does not depend on which CTA ran it.
+  int* const s_next_tile = reinterpret_cast<int*>(bars + 2 * MAX_STAGES);      // inside the plan's 128 B of slack after the barriers
+  for (int q = blockIdx.x;; q += gridDim.x) {
+    if (prm.tile_order) {
+      if (tid == 0) *s_next_tile = atomicAdd(prm.tile_counter, 1);
+      __syncthreads();
+      q = *s_next_tile;
+      __syncthreads();
+    }
+    if (q >= prm.ntiles) break;
+    const int tile = prm.tile_order ? prm.tile_order[q] : q;
     c.tile = tile;
     const int nvalid = min(RT, prm.B - tile * RT);
     const float* ck_tile = prm.ckpt + static_cast<size_t>(tile) * prm.ckpt_floats_per_tile;
@@ -533,6 +545,30 @@ odernn_bwd_kernel(const __grid_constant__ BwdParams prm) {
   }
 }
 
+// Longest-processing-time order of the tiles for one backward launch: cost = stored solver iterations of the tile over the
+// launch's interval range (every one is ns stage recomputations + ns stage pull-backs), rank by counting (ntiles <= 8192).
+constexpr int kOrderMaxTiles = 8192;
+__global__ void bwd_tile_order_kernel(const int* __restrict__ nloops, int S, int i_lo, int i_hi, int ntiles, int* __restrict__ order,
+                                      int* __restrict__ counter) {
+  __shared__ int cost[kOrderMaxTiles];
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
+    int s = 0;
+    for (int i = i_lo; i <= i_hi; ++i) s += nloops[static_cast<size_t>(t) * S + i];
+    cost[t] = s;
+  }
+  if (threadIdx.x == 0) *counter = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
+    const int ct = cost[t];
+    int rank = 0;
+    for (int u = 0; u < ntiles; ++u) {
+      const int cu = cost[u];
+      rank += (cu > ct || (cu == ct && u < t)) ? 1 : 0;
+    }
+    order[rank] = t;
+  }
+}
+
 template <int RT, int LL>
 static cudaError_t launch_one_b(const BwdParams& prm, int grid, size_t smem_bytes, cudaStream_t stream) {
   cudaError_t err = cudaFuncSetAttribute(odernn_bwd_kernel<RT, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -542,8 +578,17 @@ static cudaError_t launch_one_b(const BwdParams& prm, int grid, size_t smem_byte
   return cudaGetLastError();
 }
 
-cudaError_t launch_odernn_bwd(const BwdParams& prm, int rows_per_tile, int grid, size_t smem_bytes,
+cudaError_t launch_odernn_bwd(const BwdParams& prm_in, int rows_per_tile, int grid, size_t smem_bytes,
                               cudaStream_t stream) {
+  BwdParams prm = prm_in;
+  if (prm.tile_order && prm.tile_counter && prm.ntiles > grid && prm.ntiles <= kOrderMaxTiles) {
+    bwd_tile_order_kernel<<<1, 1024, 0, stream>>>(prm.nloops, prm.S, prm.i_lo, prm.i_hi, prm.ntiles,
+                                                  const_cast<int*>(prm.tile_order), prm.tile_counter);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  } else {
+    prm.tile_order = nullptr; prm.tile_counter = nullptr;          // one wave (or too many tiles to rank): static assignment
+  }
   if (rows_per_tile == 4) {
     switch (prm.L) {
       case 1: return launch_one_b<4, 1>(prm, grid, smem_bytes, stream);

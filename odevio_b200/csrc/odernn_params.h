@@ -102,6 +102,8 @@ struct BwdParams {
   const float* ghT;        // [L,B,D] or nullptr
   int i_lo, i_hi;          // this launch walks the intervals i_hi .. i_lo (a training step may be split into interval ranges)
   float* tile_gy;          // [ntiles][D*R]: gradient of the hidden state carried from one range to the next
+  const int* tile_order;   // [ntiles] tiles by decreasing cost of this launch (stored solver iterations of the range), or nullptr
+  int* tile_counter;       // work queue head: a CTA takes tile_order[atomicAdd(tile_counter, 1)] (zeroed by the ordering kernel)
   float* gh0;              // [L,B,D]
   float* gfused;           // [B,S,D] or nullptr
   // checkpoints written by the forward
