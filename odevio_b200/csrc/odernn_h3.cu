@@ -48,17 +48,31 @@ namespace {
 // development timeline (-DODEVIO_H3_TIMELINE): clock64 stamps / wait sums of cluster 0 / CTA 0, last solver iteration
 __device__ long long g_h3_dbg[96];
 #ifdef ODEVIO_H3_TIMELINE
-#define H3_STAMP(idx) do { if (blockIdx.x == 0) g_h3_dbg[idx] = clock64(); } while (0)
-#define H3_ADD(idx, v) do { if (blockIdx.x == 0) g_h3_dbg[idx] += (v); } while (0)
-#define H3_SET(idx, v) do { if (blockIdx.x == 0) g_h3_dbg[idx] = (v); } while (0)
+#ifndef H3_TL_STAGE
+#define H3_TL_STAGE -1                    // record only this stage of the iteration (-1: every stage, the last one survives)
+#endif
+#define H3_STAMP(idx) do { if (blockIdx.x == 0 && c.tl_on) g_h3_dbg[idx] = clock64(); } while (0)
+#define H3_ADD(idx, v) do { if (blockIdx.x == 0 && c.tl_on) g_h3_dbg[idx] += (v); } while (0)
+#define H3_SET(idx, v) do { if (blockIdx.x == 0 && c.tl_on) g_h3_dbg[idx] = (v); } while (0)
+#define H3_TL_SELECT(st) do { c.tl_on = (H3_TL_STAGE < 0 || (st) == H3_TL_STAGE) ? 1u : 0u; } while (0)
 #define H3_CLOCK() clock64()
 #else
 #define H3_STAMP(idx) do { } while (0)
 #define H3_ADD(idx, v) do { } while (0)
 #define H3_SET(idx, v) do { } while (0)
+#define H3_TL_SELECT(st) do { } while (0)
 #define H3_CLOCK() 0ll
 #endif
 
+// A/B switch (measured, NOT kept -- DESIGN.md 4.9): 1 forms the next stage's argument in the epilogue of the ODEFunc's last
+// Linear (H3Fuse) from partial sums prepared in the MMA shadows of the earlier Linears (H3Pre).  Same results (35 parity
+// tests green), the 15.7 k clk stage-argument pass and its cluster barrier disappear -- but every MMA stream that shares
+// the SM with a preparation pass gets ~2 k clk slower (operand chunks land later) and the last epilogue ~8 k clk longer
+// (warps of lane quarters 2 / 3 own two blocks; the second one's fetch is exposed): stage 74.7 k vs 75.9 k clk on the
+// timeline, configs[1] forward 16.2 ms vs 15.74 ms.
+#ifndef H3_FUSE_STAGE_ARG
+#define H3_FUSE_STAGE_ARG 0
+#endif
 constexpr int H3_NC = 4;                  // CTAs per cluster = feature slices of every Linear
 constexpr int H3_MAXL = ODEVIO_MAX_ODE_LINEARS;
 constexpr int H3_EPI_WARPS = 8;           // warps 0-7: epilogue + elementwise solver passes
@@ -90,6 +104,29 @@ struct H3Call {
   unsigned char* xdst;         // activation image that receives act(W x + b) as fp16 hi / lo, or nullptr
   int xdst_kshift;             // log2 of that image's chunk size
   int xdst_colshift;           // the image row that receives tile row n is n + xdst_colshift
+};
+
+// Next stage's argument fused into the epilogue of the ODEFunc's last Linear (which produces k_st): the epilogue thread
+// = feature also forms  y + dt * (S + a_st k_st),  S = sum_{j < st} a_j k_j,  for its rows and writes it as the activation
+// image of the next stage's first Linear -- the separate stage-argument pass and its cluster barrier go away.  S and y are
+// prepared by the epilogue warps in the shadow of the MMA streams of the stage's earlier Linears (H3Pre: coalesced pass,
+// same operation order as h3_stage_input) in an "epilogue layout" -- EL[((cb * 8 + i) * own_nf + fl) * 4 + n % 4] for
+// feature fl of the CTA's slice and tile row n = 32 cb + 4 i + n % 4 -- so that the 8 float4 loads of epilogue thread =
+// feature are coalesced across the warp; they are issued before the wait on the accumulators.
+struct H3Fuse {
+  const float* S;                      // EL scratch of the CTA's slice (nprev > 0)
+  const float* Yel;                    // y in the same layout
+  int own_nf;
+  float coef_last;                     // a[st + 1][st]
+  int nprev;                           // = st: earlier stages in S
+  const float* dt_rows;                // per-row step size (shared memory)
+  unsigned char* xa; int kshift;       // destination image
+};
+struct H3Pre {                         // the preparation pass: features 32 * it of the slice, it in [it0, it1)
+  const float* base; size_t arr; int own_f0, warp, fs, g, own_nf;      // the elementwise passes' thread mapping (H3Slice)
+  const float* coef; int nprev;        // a[st + 1][0 .. nprev)
+  float* S; float* Yel; int write_y;
+  int it0, it1;
 };
 
 struct H3Params {
@@ -145,6 +182,7 @@ struct H3Ctx {
   uint32_t count;            // chunks of all previous layers (identical in every role)
   uint32_t accum_phase;
   uint32_t w_ahead;          // weight producer: chunks of the coming layer already issued
+  uint32_t tl_on;            // development timeline: stamps enabled
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -230,6 +268,64 @@ __device__ __forceinline__ void h3_issue_chunk(uint32_t tmem, uint32_t wbase, ui
   }
 }
 
+// ---------------------------------------------------------------------------------------------- stage-argument preparation
+template <int NR>
+struct H3Slice {
+  float* base; size_t arr;       // K[j] = base + j * arr, Y = base + 7 * arr, Y1 = base + 8 * arr
+  int own_f0, nit, warp, fs, g;
+};
+__device__ __forceinline__ float4 h3_ld4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void h3_st4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
+
+template <int N>
+__device__ __forceinline__ float4 h3_wsum(const float4 (&k)[N > 0 ? N : 1], const float (&cf)[kMaxStages]) {
+  float4 a = make_float4(mul_(k[0].x, cf[0]), mul_(k[0].y, cf[0]), mul_(k[0].z, cf[0]), mul_(k[0].w, cf[0]));
+#pragma unroll
+  for (int j = 1; j < N; ++j) {
+    a.x = add_(a.x, mul_(k[j].x, cf[j])); a.y = add_(a.y, mul_(k[j].y, cf[j]));
+    a.z = add_(a.z, mul_(k[j].z, cf[j])); a.w = add_(a.w, mul_(k[j].w, cf[j]));
+  }
+  return a;
+}
+
+// S = sum_{j < N} a_j k_j (left to right, as h3_stage_input) and, when asked, y -> epilogue layout; the CTA's feature slice,
+// pass iterations [it0, it1)
+template <int N, int NR>
+__device__ __forceinline__ void h3_pre_pass_n(const H3Pre& pr) {
+  const H3Pre& sl = pr;
+  float cf[kMaxStages];
+#pragma unroll
+  for (int j = 0; j < kMaxStages; ++j) cf[j] = j < N ? pr.coef[j] : 0.f;
+  const float* Y = sl.base + kMaxStages * sl.arr;
+  const int own_nf = pr.own_nf;
+  for (int it = pr.it0; it < pr.it1; ++it) {
+    const int fl = 32 * it + 4 * sl.warp + sl.fs, f = sl.own_f0 + fl;
+#pragma unroll
+    for (int m = 0; m < NR / 32; ++m) {
+      const int n0 = 32 * m + 4 * sl.g;
+      const size_t off = static_cast<size_t>(f) * NR + n0;
+      const size_t el = ((static_cast<size_t>(m) * 8 + sl.g) * own_nf + fl) * 4;
+      float4 k[N > 0 ? N : 1];
+#pragma unroll
+      for (int j = 0; j < N; ++j) k[j] = h3_ld4(sl.base + j * sl.arr + off);
+      if (pr.write_y) h3_st4(pr.Yel + el, h3_ld4(Y + off));
+      if (N > 0) h3_st4(pr.S + el, h3_wsum<N>(k, cf));
+    }
+  }
+}
+template <int NR>
+__device__ __forceinline__ void h3_pre_pass(const H3Pre& pr) {
+  switch (pr.nprev) {
+    case 0: h3_pre_pass_n<0, NR>(pr); break;
+    case 1: h3_pre_pass_n<1, NR>(pr); break;
+    case 2: h3_pre_pass_n<2, NR>(pr); break;
+    case 3: h3_pre_pass_n<3, NR>(pr); break;
+    case 4: h3_pre_pass_n<4, NR>(pr); break;
+    case 5: h3_pre_pass_n<5, NR>(pr); break;
+    default: h3_pre_pass_n<6, NR>(pr); break;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- one Linear
 // All threads of all 4 CTAs call this with identical arguments.  Reads the cluster's activation image `cl.xsrc` (complete
 // and visible: the caller's previous step ended with a cluster barrier) and computes act(W x + b) for the tile rows
@@ -238,7 +334,8 @@ __device__ __forceinline__ void h3_issue_chunk(uint32_t tmem, uint32_t wbase, ui
 // the barrier.  `next` (may be nullptr): the Linear that certainly follows -- its first weight chunks are issued before
 // the barrier.
 template <int NR>
-__device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Layer* next, const H3Call& cl, int stamp = 0) {
+__device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Layer* next, const H3Call& cl, int stamp = 0,
+                                         const H3Fuse* fz = nullptr, const H3Pre* pre = nullptr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sb = 16 + 10 * stamp;          // timeline slots of this layer
   (void)sb;
@@ -339,11 +436,28 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
   } else if (warp < H3_EPI_WARPS && active) {
     // ===== epilogue: thread = output feature (TMEM lane); warps w and w + 4 share lane quarter w & 3 and alternate over
     // the 32-column blocks of the tile rows
+    const int q = warp & 3, h = warp >> 2;
+    const int nseg = L.nseg, act = L.act, ncol = cl.ncol;
+    // fused next-stage argument: partial sum over the earlier stages and y for this thread's FIRST block (tile 0, column block
+    // h), fetched while the MMAs run; later blocks fetch theirs on the fly
+    float fS[32], fY[32];
+    auto fz_fetch = [&](int fl, int cb) {
+      const size_t o = (static_cast<size_t>(cb) * 8 * fz->own_nf + fl) * 4;
+      const float4* ys = reinterpret_cast<const float4*>(fz->Yel + o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float4 v = __ldcg(ys + static_cast<size_t>(i) * fz->own_nf); fY[4 * i] = v.x; fY[4 * i + 1] = v.y; fY[4 * i + 2] = v.z; fY[4 * i + 3] = v.w; }
+      if (fz->nprev > 0) {
+        const float4* ss = reinterpret_cast<const float4*>(fz->S + o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float4 v = __ldcg(ss + static_cast<size_t>(i) * fz->own_nf); fS[4 * i] = v.x; fS[4 * i + 1] = v.y; fS[4 * i + 2] = v.z; fS[4 * i + 3] = v.w; }
+      }
+    };
+    if (pre) h3_pre_pass<NR>(*pre);
+    const bool fz_first = fz != nullptr && h < (ncol >> 5);
+    if (fz_first) fz_fetch(32 * q + lane, h);
     mbar_wait(c.accum_bar, c.accum_phase);
     if (tid == 0) H3_STAMP(sb + 2);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3, h = warp >> 2;
-    const int nseg = L.nseg, act = L.act, ncol = cl.ncol;
     for (int t = 0; t < L.T; ++t) {
       const int m = 32 * q + lane;                                  // row of the MMA tile = TMEM lane
       // tile 1 overlaps tile 0 when Fc < 256: only its upper Fc - 128 features are new (warp-uniform: Fc % 32 == 0)
@@ -386,14 +500,28 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
 #pragma unroll
           for (int i = 0; i < 8; ++i) __stcg(dst + i, make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]));
         }
-        if (cl.xdst) {
-          const size_t lo_off = static_cast<size_t>(2u * NR) << cl.xdst_kshift;       // KCH * NR * 2 bytes
+        unsigned char* xdst = cl.xdst;
+        int xdst_kshift = cl.xdst_kshift, xdst_colshift = cl.xdst_colshift;
+        if (fz) {
+          // y + dt * (sum_j a_j k_j), the sum left to right with the fresh k_st last (operation order of h3_stage_input)
+          if (!(t == 0 && cb == h)) fz_fetch(fl, cb);
+          const float cl_ = fz->coef_last;
+          const bool first = fz->nprev == 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float sacc = first ? mul_(acc[i], cl_) : add_(fS[i], mul_(acc[i], cl_));
+            acc[i] = add_(fY[i], mul_(fz->dt_rows[col + i], sacc));
+          }
+          xdst = fz->xa; xdst_kshift = fz->kshift; xdst_colshift = 0;
+        }
+        if (xdst) {
+          const size_t lo_off = static_cast<size_t>(2u * NR) << xdst_kshift;       // KCH * NR * 2 bytes
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             __half hi[8], lo[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) h3_split(acc[8 * j + i], hi[i], lo[i]);
-            unsigned char* dst = cl.xdst + h3_x_offset<NR>(f, col + cl.xdst_colshift + 8 * j, cl.xdst_kshift);
+            unsigned char* dst = xdst + h3_x_offset<NR>(f, col + xdst_colshift + 8 * j, xdst_kshift);
             __stcg(reinterpret_cast<uint4*>(dst),
                    make_uint4(h3_pack2(hi[0], hi[1]), h3_pack2(hi[2], hi[3]), h3_pack2(hi[4], hi[5]), h3_pack2(hi[6], hi[7])));
             __stcg(reinterpret_cast<uint4*>(dst + lo_off),
@@ -421,25 +549,6 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
 // feature = own_f0 + 32 * it + 4 * warp + fs, rows 32 * m + 4 * g + {0..3} (m < NR / 32): every float4 load of 8 lanes
 // covers 128 contiguous bytes.  Weighted sums run left to right over j in the oracle's order (oracle/_weighted_sum); zero
 // coefficients contribute an exact +-0.
-template <int NR>
-struct H3Slice {
-  float* base; size_t arr;       // K[j] = base + j * arr, Y = base + 7 * arr, Y1 = base + 8 * arr
-  int own_f0, nit, warp, fs, g;
-};
-__device__ __forceinline__ float4 h3_ld4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ void h3_st4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
-
-template <int N>
-__device__ __forceinline__ float4 h3_wsum(const float4 (&k)[N > 0 ? N : 1], const float (&cf)[kMaxStages]) {
-  float4 a = make_float4(mul_(k[0].x, cf[0]), mul_(k[0].y, cf[0]), mul_(k[0].z, cf[0]), mul_(k[0].w, cf[0]));
-#pragma unroll
-  for (int j = 1; j < N; ++j) {
-    a.x = add_(a.x, mul_(k[j].x, cf[j])); a.y = add_(a.y, mul_(k[j].y, cf[j]));
-    a.z = add_(a.z, mul_(k[j].z, cf[j])); a.w = add_(a.w, mul_(k[j].w, cf[j]));
-  }
-  return a;
-}
-
 // stage argument y + dt * sum_{j<N} a_j k_j -> fp16 hi / lo activation image of the first Linear
 template <int N, int NR>
 __device__ __forceinline__ void h3_stage_input(const H3Slice<NR>& sl, const float* coef, const float* dt_rows, unsigned char* xa,
@@ -755,7 +864,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
   H3Ctx c;
   c.wring = smem; c.xring = smem + H3_NST * H3_WCHUNK;
   c.full = full_bar; c.empty = empty_bar; c.accum_bar = &accum_bar;
-  c.tmem = tmem_slot; c.crank = crank; c.count = 0; c.accum_phase = 0; c.w_ahead = 0;
+  c.tmem = tmem_slot; c.crank = crank; c.count = 0; c.accum_phase = 0; c.w_ahead = 0; c.tl_on = 1;
 
   const int D = p.D, NL = p.NL;
   const int own_nf = D / H3_NC, own_f0 = static_cast<int>(crank) * own_nf;
@@ -836,18 +945,36 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
       while (any_running) {
         ++loops;
         if (tid == 0) H3_STAMP(0);
+        bool y_stale = true;             // y in epilogue layout is rewritten by the first preparation pass of every iteration
+        bool arg_ready = false;          // this stage's argument was written by the previous stage's last epilogue (H3Fuse)
         for (int st = (tb.fsal && have_k0) ? 1 : 0; st < ns; ++st) {
           // ---- stage argument -> activation image of the first Linear (own feature slice, all rows)
+          H3_TL_SELECT(st);
           if (tid == 0) H3_STAMP(1);
-          if (epi) {
-            if (st == 0) h3_stage_input<0, NR>(sl, tb.a[0], rs.dt, xa0, kshift0);
-            else H3_DISPATCH_STAGES(st, (h3_stage_input<(NSV < kMaxStages ? NSV : kMaxStages - 1), NR>(sl, tb.a[st], rs.dt, xa0, kshift0)))
-            asm volatile("fence.proxy.async;" ::: "memory");
+          if (!arg_ready) {
+            if (epi) {
+              if (st == 0) h3_stage_input<0, NR>(sl, tb.a[0], rs.dt, xa0, kshift0);
+              else H3_DISPATCH_STAGES(st, (h3_stage_input<(NSV < kMaxStages ? NSV : kMaxStages - 1), NR>(sl, tb.a[st], rs.dt, xa0, kshift0)))
+              asm volatile("fence.proxy.async;" ::: "memory");
+            }
+            if (tid == 0) H3_STAMP(2);
+            __syncwarp();
+            h3_cluster_sync();
           }
-          if (tid == 0) H3_STAMP(2);
-          __syncwarp();
-          h3_cluster_sync();
           if (tid == 0) H3_STAMP(3);
+          // the last Linear reads xa1 when NL is even: xa0 is free for the next stage's argument
+          const bool fuse_next = H3_FUSE_STAGE_ARG && st + 1 < ns && (NL & 1) == 0;
+          // scratch in epilogue layout, the CTA's slice of two stage-vector slots that are dead during the stages: Y1 (written by
+          // the error pass) for S, K[ns-1] (written by the last stage's last epilogue, after the last fused argument) for y
+          float* const el_S = st_base + (kMaxStages + 1) * arr + static_cast<size_t>(own_f0) * NR;
+          float* const el_Y = st_base + static_cast<size_t>(ns - 1) * arr + static_cast<size_t>(own_f0) * NR;
+          const float* const coef_next = tb.a[st + 1 < kMaxStages ? st + 1 : 0];
+          H3Fuse fz;
+          fz.S = el_S; fz.Yel = el_Y; fz.own_nf = own_nf; fz.coef_last = coef_next[st]; fz.nprev = st;
+          fz.dt_rows = rs.dt; fz.xa = xa0; fz.kshift = kshift0;
+          H3Pre pre;
+          pre.base = sl.base; pre.arr = sl.arr; pre.own_f0 = sl.own_f0; pre.warp = sl.warp; pre.fs = sl.fs; pre.g = sl.g; pre.own_nf = own_nf;
+          pre.coef = coef_next; pre.nprev = st; pre.S = el_S; pre.Yel = el_Y; pre.write_y = y_stale ? 1 : 0;
           // ---- ODEFunc on the tensor cores; last Linear (+ Tanh) -> K[st]
           for (int l = 0; l < NL; ++l) {
             const bool last = l == NL - 1;
@@ -857,10 +984,15 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
             cl.out = last ? st_base + static_cast<size_t>(st) * arr : nullptr;
             cl.xdst = last ? nullptr : ((l & 1) ? xa0 : xa1);
             cl.xdst_kshift = last ? 0 : h3_log2(p.lay[l + 1].KCH); cl.xdst_colshift = 0;
-            h3_layer<NR>(c, p.lay[l], next, cl, l);
+            // the preparation pass of the next argument is spread over the MMA shadows of the Linears before the last one
+            pre.it0 = l * sl.nit / (NL - 1); pre.it1 = (l + 1) * sl.nit / (NL - 1);
+            h3_layer<NR>(c, p.lay[l], next, cl, l, (last && fuse_next) ? &fz : nullptr, (!last && fuse_next) ? &pre : nullptr);
           }
+          arg_ready = fuse_next;
+          if (fuse_next) y_stale = false;
           if (tid == 0) H3_STAMP(4);
         }
+        H3_TL_SELECT(H3_TL_STAGE);
         have_k0 = true;
 
         if (p.adaptive) {

@@ -4,6 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from concurrent.futures import ThreadPoolExecutor
 from odevio_b200.build import build_library
 VARIANTS = {
+    "h3timeline": ["ODEVIO_H3_TIMELINE=1"],
+    "h3tl5f1": ["ODEVIO_H3_TIMELINE=1", "H3_TL_STAGE=5", "H3_FUSE_STAGE_ARG=1"],
+    "h3tl5f0": ["ODEVIO_H3_TIMELINE=1", "H3_TL_STAGE=5", "H3_FUSE_STAGE_ARG=0"],
     "w0p0": ["ODEVIO_PRODUCER_WAIT=0", "ODEVIO_EARLY_PROBE=0"],
     "w0p1": ["ODEVIO_PRODUCER_WAIT=0", "ODEVIO_EARLY_PROBE=1"],
     "w1p1": ["ODEVIO_PRODUCER_WAIT=1", "ODEVIO_EARLY_PROBE=1"],

@@ -3,7 +3,7 @@ iteration of cluster 0 / CTA 0 on one dopri5 interval (last stage of the iterati
 import os, sys, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-os.environ["ODEVIO_LIB_PATH"] = os.path.join(ROOT, "odevio_b200", "lib", "libodevio_b200.h3timeline.so")
+os.environ["ODEVIO_LIB_PATH"] = os.path.join(ROOT, "odevio_b200", "lib", "libodevio_b200.%s.so" % (sys.argv[2] if len(sys.argv) > 2 else "h3timeline"))
 import torch
 from helpers import make_pair
 from odevio_b200 import _lib
