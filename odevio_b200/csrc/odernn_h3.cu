@@ -560,17 +560,24 @@ __device__ __forceinline__ void h3_stage_input(const H3Slice<NR>& sl, const floa
   const size_t lo_off = static_cast<size_t>(2u * NR) << kshift;
   for (int it = 0; it < sl.nit; ++it) {
     const int f = sl.own_f0 + 32 * it + 4 * sl.warp + sl.fs;
+    // both row blocks' loads before the first store: the pass is bound by dependent L2 round trips, and the image stores
+    // (through a char pointer) would otherwise order block 1's loads behind block 0's stores
+    float4 yv[NR / 32];
+    float4 kv[NR / 32][N > 0 ? N : 1];
+#pragma unroll
+    for (int m = 0; m < NR / 32; ++m) {
+      const size_t off = static_cast<size_t>(f) * NR + 32 * m + 4 * sl.g;
+      yv[m] = h3_ld4(Y + off);
+#pragma unroll
+      for (int j = 0; j < N; ++j) kv[m][j] = h3_ld4(sl.base + j * sl.arr + off);
+    }
 #pragma unroll
     for (int m = 0; m < NR / 32; ++m) {
       const int n0 = 32 * m + 4 * sl.g;
-      const size_t off = static_cast<size_t>(f) * NR + n0;
-      float4 y = h3_ld4(Y + off);
-      float4 k[N > 0 ? N : 1];
-#pragma unroll
-      for (int j = 0; j < N; ++j) k[j] = h3_ld4(sl.base + j * sl.arr + off);
+      float4 y = yv[m];
       if (N > 0) {
         const float4 dt = *reinterpret_cast<const float4*>(dt_rows + n0);
-        const float4 s = h3_wsum<N>(k, cf);
+        const float4 s = h3_wsum<N>(kv[m], cf);
         y.x = add_(y.x, mul_(dt.x, s.x)); y.y = add_(y.y, mul_(dt.y, s.y));
         y.z = add_(y.z, mul_(dt.z, s.z)); y.w = add_(y.w, mul_(dt.w, s.w));
       }
