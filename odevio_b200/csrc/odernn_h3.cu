@@ -606,14 +606,21 @@ __device__ __forceinline__ void h3_error_pass(const H3Slice<NR>& sl, const DevTa
   for (int m = 0; m < NR / 32; ++m) { sum[m][0] = 0.f; sum[m][1] = 0.f; sum[m][2] = 0.f; sum[m][3] = 0.f; }
   for (int it = 0; it < sl.nit; ++it) {
     const int f = sl.own_f0 + 32 * it + 4 * sl.warp + sl.fs;
+    // both row blocks' loads before the first store (see h3_stage_input)
+    float4 y0v[NR / 32], kv[NR / 32][NS];
+#pragma unroll
+    for (int m = 0; m < NR / 32; ++m) {
+      const size_t off = static_cast<size_t>(f) * NR + 32 * m + 4 * sl.g;
+      y0v[m] = h3_ld4(Y + off);
+#pragma unroll
+      for (int j = 0; j < NS; ++j) kv[m][j] = h3_ld4(sl.base + j * sl.arr + off);
+    }
 #pragma unroll
     for (int m = 0; m < NR / 32; ++m) {
       const int n0 = 32 * m + 4 * sl.g;
       const size_t off = static_cast<size_t>(f) * NR + n0;
-      const float4 y0 = h3_ld4(Y + off);
-      float4 k[NS];
-#pragma unroll
-      for (int j = 0; j < NS; ++j) k[j] = h3_ld4(sl.base + j * sl.arr + off);
+      const float4 y0 = y0v[m];
+      const float4 (&k)[NS] = kv[m];
       const float4 dt = *reinterpret_cast<const float4*>(dt_rows + n0);
       const float4 sy = h3_wsum<NS>(k, cy);
       const float4 y1 = make_float4(add_(y0.x, mul_(dt.x, sy.x)), add_(y0.y, mul_(dt.y, sy.y)), add_(y0.z, mul_(dt.z, sy.z)),
@@ -666,15 +673,29 @@ __device__ __forceinline__ void h3_commit_rows(const H3Slice<NR>& sl, const DevT
   float* Y = sl.base + kMaxStages * sl.arr;
   const float* Y1 = sl.base + (kMaxStages + 1) * sl.arr;
   const float* Kl = sl.base + static_cast<size_t>(ns - 1) * sl.arr;
+  constexpr int MB = NR / 32;
   for (int it = 0; it < sl.nit; ++it) {
     const int f = sl.own_f0 + 32 * it + 4 * sl.warp + sl.fs;
+    // all loads of both row blocks (y1, y and the FSAL pair k_last, k_0) before the first store: the pass is bound by L2
+    // round trips, and it used to make two dependent ones per row block
+    int4 uv[MB];
+    float4 av[MB], ov[MB], bv[MB], o0v[MB];
 #pragma unroll
-    for (int m = 0; m < NR / 32; ++m) {
+    for (int m = 0; m < MB; ++m) {
       const int n0 = 32 * m + 4 * sl.g;
-      const int4 u = *reinterpret_cast<const int4*>(upd_rows + n0);
+      uv[m] = *reinterpret_cast<const int4*>(upd_rows + n0);
+      if (!(uv[m].x | uv[m].y | uv[m].z | uv[m].w)) continue;
+      const size_t off = static_cast<size_t>(f) * NR + n0;
+      av[m] = h3_ld4(Y1 + off); ov[m] = h3_ld4(Y + off);
+      if (fsal) { bv[m] = h3_ld4(Kl + off); o0v[m] = h3_ld4(sl.base + off); }
+    }
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      const int n0 = 32 * m + 4 * sl.g;
+      const int4 u = uv[m];
       if (!(u.x | u.y | u.z | u.w)) continue;
       const size_t off = static_cast<size_t>(f) * NR + n0;
-      const float4 a = h3_ld4(Y1 + off), o = h3_ld4(Y + off);
+      const float4 a = av[m], o = ov[m];
       float4 v = make_float4(u.x ? a.x : o.x, u.y ? a.y : o.y, u.z ? a.z : o.z, u.w ? a.w : o.w);
       const int4 te = *reinterpret_cast<const int4*>(toeval_rows + n0);
       if (te.x | te.y | te.z | te.w) {
@@ -717,7 +738,7 @@ __device__ __forceinline__ void h3_commit_rows(const H3Slice<NR>& sl, const DevT
       }
       h3_st4(Y + off, v);
       if (fsal) {
-        const float4 b = h3_ld4(Kl + off), o0 = h3_ld4(sl.base + off);
+        const float4 b = bv[m], o0 = o0v[m];
         h3_st4(sl.base + off, make_float4(u.x ? b.x : o0.x, u.y ? b.y : o0.y, u.z ? b.z : o0.z, u.w ? b.w : o0.w));
       }
     }
