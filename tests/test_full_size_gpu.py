@@ -27,6 +27,10 @@ def test_config2_full_batch_rows_match_oracle_subset(cuda_device):
     # same criterion as tests/test_odernn_gpu.py: step counts identical wherever the oracle itself is
     # stable under 2-32 ulp noise; poses within 1e-5, widened only to 4x the oracle's own noise spread
     stable, spread_p, _ = noise_ensemble(ref, fv[rows], fi[rows], ts[rows], n_members=6)
+    # raw numbers, un-widened (pytest -s / the GPU log): what the 1e-5 criterion sees before the noise allowance
+    print(f"configs[1] B=1024, {len(rows)} rows vs oracle: pose err {rel_err(p.cpu()[rows], p_ref):.3e} (oracle noise spread "
+          f"{spread_p:.3e}), step-count mismatches {int(neq.sum())}/{neq.numel()} of which {int((neq & stable).sum())} on entries "
+          f"the oracle's own 2-32 ulp ensemble determines ({int((~stable).sum())} undetermined)")
     assert int((neq & stable).sum()) <= max(1, neq.numel() // 200), (int(neq.sum()), int((~stable).sum()))
     assert rel_err(p.cpu()[rows], p_ref) <= max(POSE_RTOL, 4 * spread_p), (rel_err(p.cpu()[rows], p_ref), spread_p)
     # shard invariance at full size: bit-identical rows
