@@ -530,7 +530,7 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
         }
       }
     }
-    asm volatile("fence.proxy.async;" ::: "memory");             // generic-proxy global stores -> bulk copies of all 4 CTAs
+    asm volatile("fence.proxy.async.global;" ::: "memory");             // generic-proxy global stores -> bulk copies of all 4 CTAs
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     if (tid == 0) H3_STAMP(sb + 3);
   }
@@ -983,7 +983,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
             if (epi) {
               if (st == 0) h3_stage_input<0, NR>(sl, tb.a[0], rs.dt, xa0, kshift0);
               else H3_DISPATCH_STAGES(st, (h3_stage_input<(NSV < kMaxStages ? NSV : kMaxStages - 1), NR>(sl, tb.a[st], rs.dt, xa0, kshift0)))
-              asm volatile("fence.proxy.async;" ::: "memory");
+              asm volatile("fence.proxy.async.global;" ::: "memory");
             }
             if (tid == 0) H3_STAMP(2);
             __syncwarp();
@@ -1138,7 +1138,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
         // ---- rnn jump at the observation (PoseODERNN.py:112-117) and pose head (:119-122), all on this cluster
         if (epi) {
           h3_jump_input<NR>(p, rs, Yc, xj, own_f0, own_nf, interval, tid);
-          asm volatile("fence.proxy.async;" ::: "memory");
+          asm volatile("fence.proxy.async.global;" ::: "memory");
         }
         __syncwarp();
         h3_cluster_sync();
