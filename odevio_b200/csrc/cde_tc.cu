@@ -556,7 +556,7 @@ cde_tc_kernel(const __grid_constant__ CdeParams prm, const __grid_constant__ Dev
                  make_uint4(tc_pack2(lo[0], lo[1]), tc_pack2(lo[2], lo[3]), tc_pack2(lo[4], lo[5]), tc_pack2(lo[6], lo[7])));
         }
       }
-      asm volatile("fence.proxy.async;" ::: "memory");        // generic-proxy global stores -> the bulk copies of every CTA
+      asm volatile("fence.proxy.async.global;" ::: "memory");        // generic-proxy global stores -> the bulk copies of every CTA
     } else if (c.warp == TC_WARP_PROD && has_rows) {
       // weight stream of the row phase: Linear l -> ring stage (count & 1), one bulk copy each (4 Hc^2 <= stage bytes)
       if (elect_one()) {

@@ -304,7 +304,7 @@ __device__ __forceinline__ void ft_layer(FtCtx& c, const FtLayer& L) {
         else store_chunk_hilo<FT_KCH>(nx, nx + c.xa_buf_floats, r, n0, v);
       }
     }
-    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("fence.proxy.async.global;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     if (tid == 0) FT_STAMP(8 + L.stamp * 8 + 3);           // epilogue done
   }
@@ -354,7 +354,7 @@ __device__ __forceinline__ void ft_layer(FtCtx& c, const FtLayer& L) {
           else store_chunk_hilo<FT_KCH>(nx, nx + c.xa_buf_floats, r, n0, v);
         }
       }
-      asm volatile("fence.proxy.async;" ::: "memory");
+      asm volatile("fence.proxy.async.global;" ::: "memory");
     }
     __syncwarp();
   }

@@ -122,7 +122,7 @@ odefunc_tc_kernel(const __grid_constant__ FtParams p) {
         if (FT_SPLIT) store_chunk<FT_KCH>(dst0, r, k0, v);
         else store_chunk_hilo<FT_KCH>(dst0, dst0 + p.xa_buf_floats, r, k0, v);
       }
-      asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy stores -> visible to the bulk-copy (async) proxy
+      asm volatile("fence.proxy.async.global;" ::: "memory");      // generic-proxy stores -> visible to the bulk-copy (async) proxy
     }
     __syncwarp();
     if (tid == 0) FT_STAMP(0);

@@ -345,7 +345,7 @@ odernn_tc_evolve_kernel(const __grid_constant__ TcParams p) {
           if (st == 0) tc_stage_input<0, KCH, SPLIT>(sl, tb.a[0], dt, xa_cluster, p.xa_buf_floats);
           else TC_DISPATCH_STAGES(st, (tc_stage_input<(NSV < kMaxStages ? NSV : kMaxStages - 1), KCH, SPLIT>(sl, tb.a[st], dt, xa_cluster, p.xa_buf_floats)))
           TC_STAMP(42);
-          asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores -> bulk-copy (async) proxy of all CTAs
+          asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy stores -> bulk-copy (async) proxy of all CTAs
           TC_STAMP(43);
         }
         __syncwarp();
