@@ -70,6 +70,12 @@ __device__ long long g_h3_dbg[96];
 // the SM with a preparation pass gets ~2 k clk slower (operand chunks land later) and the last epilogue ~8 k clk longer
 // (warps of lane quarters 2 / 3 own two blocks; the second one's fetch is exposed): stage 74.7 k vs 75.9 k clk on the
 // timeline, configs[1] forward 16.2 ms vs 15.74 ms.
+#ifndef H3_TMEM_PAIR
+#define H3_TMEM_PAIR 0                    // A/B: the two cross-term accumulators of an epilogue block fetched with one tcgen05.wait::ld
+#endif
+#ifndef H3_COMMIT_BATCH
+#define H3_COMMIT_BATCH 1                 // A/B: commit pass fetches both row blocks (and the FSAL pair) before its first store
+#endif
 #ifndef H3_FUSE_STAGE_ARG
 #define H3_FUSE_STAGE_ARG 0
 #endif
@@ -217,6 +223,19 @@ __device__ __forceinline__ void h3_tmem_ld32(uint32_t taddr, uint32_t (&u)[32]) 
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void h3_tmem_ld32_nowait(uint32_t taddr, uint32_t (&u)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+        "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+        "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void h3_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // x = hi + lo * 2^-11: hi = fp16(x), lo = fp16((x - hi) * 2^11)  (x - hi is exact in fp32)
 __device__ __forceinline__ void h3_split(float x, __half& hi, __half& lo) {
@@ -472,12 +491,24 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
         const int col = cl.col0 + colb;                             // tile row
         uint32_t u[32];
         float acc[32];
+#if H3_TMEM_PAIR
+        {
+          // both cross-term accumulators with one wait (acc is not live yet: no extra registers)
+          uint32_t u2[32];
+          h3_tmem_ld32_nowait(tbase + static_cast<uint32_t>(nseg * ncol + colb), u);
+          h3_tmem_ld32_nowait(tbase + static_cast<uint32_t>((nseg + 1) * ncol + colb), u2);
+          h3_tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = (__uint_as_float(u[i]) + __uint_as_float(u2[i])) * (1.0f / 2048.0f);
+        }
+#else
         h3_tmem_ld32(tbase + static_cast<uint32_t>(nseg * ncol + colb), u);             // cross terms first (smallest)
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(u[i]);
         h3_tmem_ld32(tbase + static_cast<uint32_t>((nseg + 1) * ncol + colb), u);
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[i] = (acc[i] + __uint_as_float(u[i])) * (1.0f / 2048.0f);
+#endif
         for (int sgm = nseg - 1; sgm >= 0; --sgm) {
           h3_tmem_ld32(tbase + static_cast<uint32_t>(sgm * ncol + colb), u);
 #pragma unroll
@@ -685,9 +716,11 @@ __device__ __forceinline__ void h3_commit_rows(const H3Slice<NR>& sl, const DevT
       const int n0 = 32 * m + 4 * sl.g;
       uv[m] = *reinterpret_cast<const int4*>(upd_rows + n0);
       if (!(uv[m].x | uv[m].y | uv[m].z | uv[m].w)) continue;
+#if H3_COMMIT_BATCH
       const size_t off = static_cast<size_t>(f) * NR + n0;
       av[m] = h3_ld4(Y1 + off); ov[m] = h3_ld4(Y + off);
       if (fsal) { bv[m] = h3_ld4(Kl + off); o0v[m] = h3_ld4(sl.base + off); }
+#endif
     }
 #pragma unroll
     for (int m = 0; m < MB; ++m) {
@@ -695,6 +728,9 @@ __device__ __forceinline__ void h3_commit_rows(const H3Slice<NR>& sl, const DevT
       const int4 u = uv[m];
       if (!(u.x | u.y | u.z | u.w)) continue;
       const size_t off = static_cast<size_t>(f) * NR + n0;
+#if !H3_COMMIT_BATCH
+      av[m] = h3_ld4(Y1 + off); ov[m] = h3_ld4(Y + off);
+#endif
       const float4 a = av[m], o = ov[m];
       float4 v = make_float4(u.x ? a.x : o.x, u.y ? a.y : o.y, u.z ? a.z : o.z, u.w ? a.w : o.w);
       const int4 te = *reinterpret_cast<const int4*>(toeval_rows + n0);
@@ -738,6 +774,9 @@ __device__ __forceinline__ void h3_commit_rows(const H3Slice<NR>& sl, const DevT
       }
       h3_st4(Y + off, v);
       if (fsal) {
+#if !H3_COMMIT_BATCH
+        bv[m] = h3_ld4(Kl + off); o0v[m] = h3_ld4(sl.base + off);
+#endif
         const float4 b = bv[m], o0 = o0v[m];
         h3_st4(sl.base + off, make_float4(u.x ? b.x : o0.x, u.y ? b.y : o0.y, u.z ? b.z : o0.z, u.w ? b.w : o0.w));
       }

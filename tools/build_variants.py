@@ -5,6 +5,9 @@ from concurrent.futures import ThreadPoolExecutor
 from odevio_b200.build import build_library
 VARIANTS = {
     "h3timeline": ["ODEVIO_H3_TIMELINE=1"],
+    "h3cb0": ["H3_COMMIT_BATCH=0"],
+    "h3pair": ["H3_TMEM_PAIR=1"],
+    "h3pair_cb0": ["H3_TMEM_PAIR=1", "H3_COMMIT_BATCH=0"],
     "h3tl5f1": ["ODEVIO_H3_TIMELINE=1", "H3_TL_STAGE=5", "H3_FUSE_STAGE_ARG=1"],
     "h3tl5f0": ["ODEVIO_H3_TIMELINE=1", "H3_TL_STAGE=5", "H3_FUSE_STAGE_ARG=0"],
     "w0p0": ["ODEVIO_PRODUCER_WAIT=0", "ODEVIO_EARLY_PROBE=0"],
