@@ -70,6 +70,12 @@ __device__ long long g_h3_dbg[96];
 // the SM with a preparation pass gets ~2 k clk slower (operand chunks land later) and the last epilogue ~8 k clk longer
 // (warps of lane quarters 2 / 3 own two blocks; the second one's fetch is exposed): stage 74.7 k vs 75.9 k clk on the
 // timeline, configs[1] forward 16.2 ms vs 15.74 ms.
+#ifndef H3_XJ_ALIAS
+#define H3_XJ_ALIAS 1                     // jump-input images alias the stage vectors K0 .. K(2L-1) (needs a cluster barrier before they are written)
+#endif
+#ifndef H3_SKIP_LAST_BARRIER
+#define H3_SKIP_LAST_BARRIER 0            // A/B: no cluster barrier after the ODEFunc's last Linear (the following pass is CTA-local): 14.95 vs 14.85 ms, not kept
+#endif
 #ifndef H3_TMEM_PAIR
 #define H3_TMEM_PAIR 0                    // A/B: the two cross-term accumulators of an epilogue block fetched with one tcgen05.wait::ld
 #endif
@@ -354,7 +360,7 @@ __device__ __forceinline__ void h3_pre_pass(const H3Pre& pr) {
 // the barrier.
 template <int NR>
 __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Layer* next, const H3Call& cl, int stamp = 0,
-                                         const H3Fuse* fz = nullptr, const H3Pre* pre = nullptr) {
+                                         const H3Fuse* fz = nullptr, const H3Pre* pre = nullptr, bool end_barrier = true) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sb = 16 + 10 * stamp;          // timeline slots of this layer
   (void)sb;
@@ -570,8 +576,12 @@ __device__ __forceinline__ void h3_layer(H3Ctx& c, const H3Layer& L, const H3Lay
     c.count += static_cast<uint32_t>(nch);
   }
   __syncwarp();
-  h3_cluster_sync();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // end_barrier == false (uniform over the cluster): the caller's next step only touches this CTA's own feature slice and
+  // ends with a cluster barrier of its own, which then also orders this Linear's results and its TMEM reads
+  if (end_barrier) {
+    h3_cluster_sync();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
   if (tid == 0) H3_STAMP(sb + 4);
 }
 
@@ -945,7 +955,11 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
   // the jump-input images [x ; h] of the L layers live in the stage vectors K0 .. K(2L-1), which are dead between the end of an
   // interval's solves and the next interval's first stage (FSAL does not carry across the jump): 25 MB less L2-resident
   // scratch at configs[1] (2 D x NR x 4 B = 2 stage vectors per layer)
+#if H3_XJ_ALIAS
   unsigned char* const xj = reinterpret_cast<unsigned char*>(st_base);
+#else
+  unsigned char* const xj = p.xj + static_cast<size_t>(cluster_id) * p.L * p.xj_buf_bytes;
+#endif
 
   const bool epi = warp < H3_EPI_WARPS;
   H3Slice<NR> sl;
@@ -1027,6 +1041,9 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
             if (tid == 0) H3_STAMP(2);
             __syncwarp();
             h3_cluster_sync();
+#if H3_SKIP_LAST_BARRIER
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#endif
           }
           if (tid == 0) H3_STAMP(3);
           // the last Linear reads xa1 when NL is even: xa0 is free for the next stage's argument
@@ -1053,7 +1070,14 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
             cl.xdst_kshift = last ? 0 : h3_log2(p.lay[l + 1].KCH); cl.xdst_colshift = 0;
             // the preparation pass of the next argument is spread over the MMA shadows of the Linears before the last one
             pre.it0 = l * sl.nit / (NL - 1); pre.it1 = (l + 1) * sl.nit / (NL - 1);
-            h3_layer<NR>(c, p.lay[l], next, cl, l, (last && fuse_next) ? &fz : nullptr, (!last && fuse_next) ? &pre : nullptr);
+            // The barrier after the ODEFunc's last Linear is dropped (H3_SKIP_LAST_BARRIER): what follows -- the next stage's
+            // argument pass, or the error / commit pass -- reads and writes only this CTA's feature slice of the stage vectors
+            // and ends with a cluster barrier of its own; the argument image xa0 it overwrites was last read by the Linear
+            // before the last one (the last Linear reads xa1 when NL is even), i.e. before every CTA's previous barrier.
+            const bool skip_end = H3_SKIP_LAST_BARRIER && last && (NL & 1) == 0 && !fuse_next;
+            h3_layer<NR>(c, p.lay[l], next, cl, l, (last && fuse_next) ? &fz : nullptr, (!last && fuse_next) ? &pre : nullptr, !skip_end);
+            // the passes walk the slice with another thread mapping than the epilogue: CTA-level barrier of the epilogue warps
+            if (skip_end && epi) named_bar_sync(1, H3_EPI_THREADS);
           }
           arg_ready = fuse_next;
           if (fuse_next) y_stale = false;
@@ -1175,6 +1199,12 @@ __global__ void __launch_bounds__(H3_THREADS, 1) odernn_h3_kernel(const __grid_c
       }
       if (p.do_jump) {
         // ---- rnn jump at the observation (PoseODERNN.py:112-117) and pose head (:119-122), all on this cluster
+        // The jump-input images alias the stage vectors K0 .. K(2L-1) of ALL four feature slices: every CTA must be through
+        // its commit pass (which reads and rewrites its slice of K0 for the FSAL carry) before any CTA writes them.
+#if H3_XJ_ALIAS
+        __syncwarp();
+        h3_cluster_sync();
+#endif
         if (epi) {
           h3_jump_input<NR>(p, rs, Yc, xj, own_f0, own_nf, interval, tid);
           asm volatile("fence.proxy.async.global;" ::: "memory");
@@ -1336,7 +1366,11 @@ int h3_plan(const odevio_odernn_cfg& c, H3Plan& pl) {
   pl.off_xa = take(static_cast<size_t>(pl.nclusters) * 2 * pl.xa_buf_bytes);
   pl.xj_buf_bytes = pl.can_jump ? static_cast<size_t>(2 * c.D) * pl.NR * 4 : 0;        // aliases 2 stage vectors per layer (kernel)
   if (pl.can_jump && 2 * c.L > kMaxStages) pl.can_jump = false;
+#if H3_XJ_ALIAS
   pl.off_xj = off;
+#else
+  pl.off_xj = take(static_cast<size_t>(pl.nclusters) * c.L * pl.xj_buf_bytes);
+#endif
   pl.state_floats = (static_cast<size_t>(kMaxStages + 2) * c.D + H3_NC + kRegHidden) * pl.NR;
   pl.state_floats = (pl.state_floats + 255) / 256 * 256;
   pl.off_state = take(static_cast<size_t>(pl.nclusters) * pl.state_floats * sizeof(float));

@@ -6,6 +6,8 @@ from odevio_b200.build import build_library
 VARIANTS = {
     "h3timeline": ["ODEVIO_H3_TIMELINE=1"],
     "h3cb0": ["H3_COMMIT_BATCH=0"],
+    "h3skip0": ["H3_SKIP_LAST_BARRIER=0"],
+    "h3noalias": ["H3_XJ_ALIAS=0"],
     "h3pair": ["H3_TMEM_PAIR=1"],
     "h3pair_cb0": ["H3_TMEM_PAIR=1", "H3_COMMIT_BATCH=0"],
     "h3tl5f1": ["ODEVIO_H3_TIMELINE=1", "H3_TL_STAGE=5", "H3_FUSE_STAGE_ARG=1"],
